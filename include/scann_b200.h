@@ -1,0 +1,149 @@
+/*
+ * scann_b200.h -- C ABI of the B200-native ScaNN batched query path.
+ *
+ * Drop-in boundary.  Plain pointers and sizes only; no torch,
+ * pybind or C++ types cross this header.  Every entry point names the reference
+ * interface it replaces (paths relative to /root/reference/scann/).
+ *
+ * Error convention: functions return an absl::StatusCode-numbered int
+ * (0 OK, 3 INVALID_ARGUMENT, 9 FAILED_PRECONDITION, 12 UNIMPLEMENTED, 13 INTERNAL);
+ * the message is available through scann_b200_last_error() (thread local).
+ * CUDA failures map to INTERNAL; the library never aborts the process and has
+ * no CPU fallback: without a usable CUDA device index creation fails.
+ */
+#ifndef SCANN_B200_H_
+#define SCANN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCANN_B200_ABI_VERSION 1
+
+enum { SCANN_B200_DOT_PRODUCT = 0, SCANN_B200_SQUARED_L2 = 1 };
+
+enum {
+  SCANN_B200_OK = 0,
+  SCANN_B200_INVALID_ARGUMENT = 3,
+  SCANN_B200_FAILED_PRECONDITION = 9,
+  SCANN_B200_UNIMPLEMENTED = 12,
+  SCANN_B200_INTERNAL = 13,
+};
+
+typedef struct scann_b200_index scann_b200_index;
+
+/*
+ * Everything a searcher is made of, as host pointers in the serialized-asset layouts
+ * (scann_ops/cc/scann.cc:105-233 LoadArtifacts).  The library copies
+ * what it needs to the device during scann_b200_index_create; the caller keeps ownership.
+ *   tree-AH      : centers + tokens + codes (+ soar_codes) + codebook (+ dataset for reordering)
+ *   brute force  : dataset (f32) or bf16_dataset, n_leaves = n_blocks = 0
+ */
+typedef struct {
+  int32_t distance;            /* SCANN_B200_DOT_PRODUCT | SCANN_B200_SQUARED_L2 */
+  uint32_t n;                  /* datapoints in the whole (unsharded) database */
+  uint32_t d;                  /* dimensionality */
+  uint32_t n_leaves;           /* L partitions (serialized_partitioner.pb) */
+  uint32_t n_blocks;           /* B AH blocks (ah_codebook.pb) */
+  uint32_t dims_per_block;     /* row stride of `codebook` (short blocks are zero padded) */
+  const int32_t* block_dims;   /* [B] real dims per block, NULL => all dims_per_block */
+  const float* centers;        /* [L][D] */
+  const int32_t* tokens;       /* datapoint_to_token.npy: [N], or [2N] with SOAR (-1 = none) */
+  int32_t soar;                /* tokens has 2N entries, soar_codes present */
+  const uint8_t* codes;        /* hashed_dataset.npy [N][B], one 4-bit code per byte */
+  const uint8_t* soar_codes;   /* hashed_dataset_soar.npy [N][B] or NULL */
+  const float* codebook;       /* [B][16][dims_per_block] */
+  const float* dataset;        /* dataset.npy [N][D] or NULL (no exact reordering) */
+  const int16_t* bf16_dataset; /* bfloat16_dataset.npy [N][D] or NULL */
+  float overretrieve;          /* DatabaseSpillingConfig.overretrieve_factor */
+  int32_t default_leaves;      /* QuerySpillingConfig.max_spill_centers */
+  int32_t default_pre_nn;      /* ExactReordering.approx_num_neighbors */
+  int32_t default_final_nn;    /* ScannConfig.num_neighbors */
+  int32_t device;              /* CUDA device ordinal */
+  int32_t shard_rank;          /* this index holds datapoints with id % shard_world == shard_rank */
+  int32_t shard_world;         /* 1 = unsharded */
+} scann_b200_index_desc;
+
+/* Replaces ScannInterface::Initialize(ScannArtifacts) (scann_ops/cc/scann.cc:355-381) and the
+ * per-leaf asymmetric_hashing2::Searcher construction incl. CreatePackedDataset
+ * (hashes/internal/asymmetric_hashing_impl.cc:690-737). */
+int scann_b200_index_create(const scann_b200_index_desc* desc, scann_b200_index** out);
+void scann_b200_index_destroy(scann_b200_index* index);
+
+/* Replaces ScannInterface::SearchBatched (scann_ops/cc/scann.cc:463-475) +
+ * ReshapeBatchedNNResult (scann.h:165-180): host buffers in, host buffers out.
+ * final_nn / pre_reorder_nn / leaves: -1 = index default (scann_ops_pybind.py:75-78).
+ * out_idx / out_dist are [nq][out_k]; short rows are padded with (0, NaN). */
+int scann_b200_search_batched(scann_b200_index* index, const float* queries, uint32_t nq,
+                              int32_t final_nn, int32_t pre_reorder_nn, int32_t leaves,
+                              uint32_t* out_idx, float* out_dist, int32_t out_k);
+
+/* Same computation with every buffer already resident on the index's device
+ * (queries [nq][D] f32, outputs [nq][out_k]); enqueued on the index's stream and
+ * synchronised before returning.  This is the kernel-side throughput leg of bench.py. */
+int scann_b200_search_batched_device(scann_b200_index* index, const float* d_queries, uint32_t nq,
+                                     int32_t final_nn, int32_t pre_reorder_nn, int32_t leaves,
+                                     uint32_t* d_out_idx, float* d_out_dist, int32_t out_k);
+
+/* Sharded search: this rank's local pre-reorder candidates with their
+ * exact distance already computed.  Records are (global datapoint id, AH score, exact distance),
+ * rows sorted by (AH score, tie-break key), padded with id 0xFFFFFFFF.  Device buffers
+ * [nq][n_cand]; n_cand must be >= the over-retrieved pre-reorder count. */
+int scann_b200_search_partial_device(scann_b200_index* index, const float* d_queries, uint32_t nq,
+                                     int32_t pre_reorder_nn, int32_t leaves, uint32_t* d_ids,
+                                     uint64_t* d_tiebreak, float* d_ah_score, float* d_exact,
+                                     int32_t n_cand);
+/* Merge `world` gathered partial lists ([world][nq][n_cand], as all-gathered) into the final
+ * top-k, reproducing "global top-N' by AH score -> exact distance -> top-k by (distance, id)". */
+int scann_b200_merge_partials_device(scann_b200_index* index, uint32_t nq, int32_t world,
+                                     int32_t n_cand, const uint32_t* d_ids,
+                                     const uint64_t* d_tiebreak, const float* d_ah_score,
+                                     const float* d_exact, int32_t pre_reorder_nn, int32_t final_nn,
+                                     uint32_t* d_out_idx, float* d_out_dist, int32_t out_k);
+
+const char* scann_b200_last_error(void);
+int scann_b200_abi_version(void);
+
+/* ---- parity / measurement hooks (used by tests/ and bench.py) ---- */
+
+/* KMeansTreePartitioner::TokensForDatapointWithSpillingBatched
+ * (partitioning/kmeans_tree_partitioner.cc:642-730): the P nearest leaves per query and the
+ * distance to their centres, sorted by (distance, leaf).  Host buffers [nq][P]. */
+int scann_b200_debug_tokenize(scann_b200_index* index, const float* queries, uint32_t nq,
+                              int32_t leaves, int32_t* out_leaf, float* out_dist);
+/* AsymmetricQueryer::CreateLookupTable (hashes/asymmetric_hashing2/querying.h:284-329):
+ * u8 LUT [nq][B][16] and fixed point multiplier [nq]. */
+int scann_b200_debug_lut(scann_b200_index* index, const float* queries, uint32_t nq,
+                         uint8_t* out_lut, float* out_mult);
+/* LUT16Interface::GetDistances (hashes/internal/lut16_interface.h:40-135): int16 scores of
+ * every slot of `leaf` under the given u8 LUT [B][16].  out has leaf-size entries. */
+int scann_b200_debug_leaf_scores(scann_b200_index* index, const uint8_t* lut, uint32_t leaf,
+                                 int16_t* out, uint32_t out_len);
+/* TreeAHHybridResidual::FindNeighborsBatchedImpl (tree_x_hybrid/tree_ah_hybrid_residual.cc:631-786)
+ * up to FinishUnsorted: the over-retrieved pre-reorder candidates per query, sorted by
+ * (score, leaf, slot).  Host buffers [nq][cap]; out_count [nq]. */
+int scann_b200_debug_candidates(scann_b200_index* index, const float* queries, uint32_t nq,
+                                int32_t pre_reorder_nn, int32_t leaves, int32_t cap,
+                                uint32_t* out_leaf, uint32_t* out_slot, uint32_t* out_dp,
+                                float* out_score, uint32_t* out_count);
+uint32_t scann_b200_leaf_size(const scann_b200_index* index, uint32_t leaf);
+
+typedef struct {
+  uint64_t scan_bytes_alg;   /* sum over probed (query, leaf) of ceil(n/32)*16*B */
+  uint64_t scan_pairs;       /* probed (query, leaf) pairs */
+  uint64_t scan_lookups;     /* (query, slot, block) lookups issued by the scan kernels */
+  uint32_t kernel_launches;  /* kernels launched by the last search call */
+  uint32_t overflow_retries; /* candidate-buffer overflow re-scans (0 in the common case) */
+  float ms_tokenize, ms_lut, ms_pilot, ms_worklist, ms_scan, ms_compact, ms_finalize, ms_total;
+  uint32_t scan_kernel_count; /* launches of the dominant LUT16 scan kernel in the last call */
+} scann_b200_stats;
+/* Timing (CUDA events on the index's stream) and traffic figures of the last search call. */
+int scann_b200_last_stats(scann_b200_index* index, scann_b200_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCANN_B200_H_ */

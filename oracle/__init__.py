@@ -1,0 +1,179 @@
+"""ctypes wrapper around the CPU oracle (oracle/scann_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs.  The product package
+(scann_b200) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class _Desc(C.Structure):
+  _fields_ = [
+      ("distance", C.c_int32), ("n", C.c_uint32), ("d", C.c_uint32),
+      ("n_leaves", C.c_uint32), ("n_blocks", C.c_uint32), ("dims_per_block", C.c_uint32),
+      ("block_dims", C.c_void_p), ("centers", C.c_void_p), ("tokens", C.c_void_p),
+      ("soar", C.c_int32), ("codes", C.c_void_p), ("soar_codes", C.c_void_p),
+      ("codebook", C.c_void_p), ("dataset", C.c_void_p), ("bf16_dataset", C.c_void_p),
+      ("overretrieve", C.c_float), ("default_leaves", C.c_int32),
+      ("default_pre_nn", C.c_int32), ("default_final_nn", C.c_int32),
+  ]
+
+
+def build(force=False):
+  so = os.path.join(_HERE, "libscann_oracle.so")
+  src = os.path.join(_HERE, "scann_oracle.c")
+  if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    subprocess.check_call(["make", "-C", _HERE, "-s"])
+  return so
+
+
+def lib():
+  global _LIB
+  if _LIB is None:
+    so = os.path.join(_HERE, "libscann_oracle.so")
+    if not os.path.exists(so):
+      build()
+    L = C.CDLL(so)
+    L.so_index_create.restype = C.c_void_p
+    L.so_index_create.argtypes = [C.POINTER(_Desc)]
+    L.so_index_destroy.argtypes = [C.c_void_p]
+    L.so_last_error.restype = C.c_char_p
+    L.so_search_batched.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.so_tokenize.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+    L.so_lut.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.so_leaf_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+    L.so_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+    L.so_leaf_size.restype = C.c_uint32
+    L.so_leaf_size.argtypes = [C.c_void_p, C.c_uint32]
+    L.so_leaf_datapoints.restype = C.POINTER(C.c_uint32)
+    L.so_leaf_datapoints.argtypes = [C.c_void_p, C.c_uint32]
+    L.so_disjoint.argtypes = [C.c_void_p]
+    L.so_last_scan_bytes.restype = C.c_uint64
+    L.so_last_boundary_band.restype = C.c_uint64
+    _LIB = L
+  return _LIB
+
+
+def _p(a):
+  return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleIndex:
+  """CPU oracle searcher built from the same arrays the CUDA index is built from."""
+
+  def __init__(self, arrays, leaves_to_search, pre_reorder_nn, final_nn):
+    L = lib()
+    a = arrays
+    self._keep = []
+
+    def own(x, dt):
+      if x is None:
+        return None
+      y = np.ascontiguousarray(x, dtype=dt)
+      self._keep.append(y)
+      return y
+
+    self.n, self.d = a.n, a.d
+    self.B = 0 if a.codes is None else a.codes.shape[1]
+    self.L = 0 if a.centers is None else a.centers.shape[0]
+    d = _Desc()
+    d.distance = 0 if a.distance == "dot_product" else 1
+    d.n, d.d, d.n_leaves, d.n_blocks = a.n, a.d, self.L, self.B
+    d.dims_per_block = 0 if a.codebook is None else a.codebook.shape[2]
+    d.block_dims = _p(own(a.block_dims, np.int32))
+    d.centers = _p(own(a.centers, np.float32))
+    d.tokens = _p(own(a.tokens, np.int32))
+    d.soar = 1 if a.soar else 0
+    d.codes = _p(own(a.codes, np.uint8))
+    d.soar_codes = _p(own(a.soar_codes, np.uint8))
+    d.codebook = _p(own(a.codebook, np.float32))
+    d.dataset = _p(own(a.dataset, np.float32))
+    d.bf16_dataset = _p(own(a.bf16_dataset, np.int16))
+    d.overretrieve = a.overretrieve
+    d.default_leaves = leaves_to_search
+    d.default_pre_nn = pre_reorder_nn
+    d.default_final_nn = final_nn
+    self._h = L.so_index_create(C.byref(d))
+    if not self._h:
+      raise RuntimeError(L.so_last_error().decode())
+    self.default_leaves = leaves_to_search
+    self.default_pre_nn = pre_reorder_nn
+    self.default_final_nn = final_nn
+
+  def __del__(self):
+    if getattr(self, "_h", None):
+      lib().so_index_destroy(self._h)
+      self._h = None
+
+  def search_batched(self, q, final_nn=-1, pre_nn=-1, leaves=-1, impl=0, threads=1, batch=256):
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    k = final_nn if final_nn > 0 else self.default_final_nn
+    idx = np.empty((q.shape[0], k), dtype=np.uint32)
+    dist = np.empty((q.shape[0], k), dtype=np.float32)
+    rc = lib().so_search_batched(self._h, _p(q), q.shape[0], final_nn, pre_nn, leaves, _p(idx), _p(dist),
+                                 k, impl, threads, batch)
+    if rc:
+      raise RuntimeError(lib().so_last_error().decode())
+    return idx, dist
+
+  def tokenize(self, q, leaves=-1):
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    P = min(leaves if leaves > 0 else self.default_leaves, self.L)
+    leaf = np.empty((q.shape[0], P), dtype=np.int32)
+    dist = np.empty((q.shape[0], P), dtype=np.float32)
+    lib().so_tokenize(self._h, _p(q), q.shape[0], P, _p(leaf), _p(dist))
+    return leaf, dist
+
+  def lut(self, q):
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    lut = np.empty((q.shape[0], self.B, 16), dtype=np.uint8)
+    mult = np.empty(q.shape[0], dtype=np.float32)
+    lib().so_lut(self._h, _p(q), q.shape[0], _p(lut), _p(mult))
+    return lut, mult
+
+  def leaf_size(self, leaf):
+    return int(lib().so_leaf_size(self._h, leaf))
+
+  def leaf_datapoints(self, leaf):
+    n = self.leaf_size(leaf)
+    ptr = lib().so_leaf_datapoints(self._h, leaf)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.empty(0, np.uint32)
+
+  def leaf_scores(self, lut, leaf):
+    lut = np.ascontiguousarray(lut, dtype=np.uint8)
+    out = np.empty(self.leaf_size(leaf), dtype=np.int16)
+    lib().so_leaf_scores(self._h, _p(lut), leaf, _p(out))
+    return out
+
+  def candidates(self, q, pre_nn=-1, leaves=-1, cap=None):
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    nq = q.shape[0]
+    if cap is None:
+      npre = pre_nn if pre_nn > 0 else self.default_pre_nn
+      cap = int(npre * 4 + 8)
+    leaf = np.zeros((nq, cap), np.uint32)
+    slot = np.zeros((nq, cap), np.uint32)
+    dp = np.zeros((nq, cap), np.uint32)
+    score = np.zeros((nq, cap), np.float32)
+    acc = np.zeros((nq, cap), np.int32)
+    cnt = np.zeros(nq, np.uint32)
+    lib().so_candidates(self._h, _p(q), nq, pre_nn, leaves, cap, _p(leaf), _p(slot), _p(dp), _p(score),
+                        _p(acc), _p(cnt))
+    return dict(leaf=leaf, slot=slot, dp=dp, score=score, acc=acc, count=cnt,
+                scan_bytes=int(lib().so_last_scan_bytes()), band=int(lib().so_last_boundary_band()))
+
+  @property
+  def disjoint(self):
+    return bool(lib().so_disjoint(self._h))
+
+  @staticmethod
+  def last_scan_bytes():
+    return int(lib().so_last_scan_bytes())

@@ -1,0 +1,212 @@
+// exact_math.cuh -- float kernels whose rounding sequence is part of the parity contract.
+//
+// Each function reproduces, operation by operation, the arithmetic of one CPU kernel of the
+// reference so that LUT bytes, centre distances and reorder distances are bit-identical to
+// the oracle (oracle/scann_oracle.c holds the same restatements for the CPU).  All float
+// operations are written with explicit round-to-nearest intrinsics so that nvcc can neither
+// contract a mul+add into an FMA nor split an FMA.
+//
+// Paths are relative to /root/reference/scann/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+// distance_measures/one_to_many/one_to_many_symmetric.h:373-503 (AVX2 one-to-many, dims >= 8):
+// eight fnmadd lanes, top+bottom fold, 4-wide and 2-wide steps, (x0+x2)+(x1+x3), fused tail.
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float neg_dot_avx2_order(LoadQ q, LoadX x, uint32_t n) {
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a[l] = __fmaf_rn(-q(j + l), x(j + l), a[l]);
+  }
+  float b[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) b[l] = __fadd_rn(a[l + 4], a[l]);
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) b[l] = __fmaf_rn(-q(j + l), x(j + l), b[l]);
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    b[2] = __fmaf_rn(-q(j), x(j), b[2]);
+    b[3] = __fmaf_rn(-q(j + 1), x(j + 1), b[3]);
+    j += 2;
+  }
+  float r = __fadd_rn(__fadd_rn(b[0], b[2]), __fadd_rn(b[1], b[3]));
+  if (j < n) r = __fmaf_rn(-q(j), x(j), r);
+  return r;
+}
+
+// SquaredL2DistanceLambdas::FmaTerm (one_to_many_symmetric.h:1043-1051).
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float sql2_avx2_order(LoadQ q, LoadX x, uint32_t n) {
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const float t = __fsub_rn(q(j + l), x(j + l));
+      a[l] = __fmaf_rn(t, t, a[l]);
+    }
+  }
+  float b[4];
+#pragma unroll
+  for (int l = 0; l < 4; ++l) b[l] = __fadd_rn(a[l + 4], a[l]);
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float t = __fsub_rn(q(j + l), x(j + l));
+      b[l] = __fmaf_rn(t, t, b[l]);
+    }
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    const float t2 = __fsub_rn(q(j), x(j)), t3 = __fsub_rn(q(j + 1), x(j + 1));
+    b[2] = __fmaf_rn(t2, t2, b[2]);
+    b[3] = __fmaf_rn(t3, t3, b[3]);
+    j += 2;
+  }
+  float r = __fadd_rn(__fadd_rn(b[0], b[2]), __fadd_rn(b[1], b[3]));
+  if (j < n) {
+    const float t = __fsub_rn(q(j), x(j));
+    r = __fmaf_rn(t, t, r);
+  }
+  return r;
+}
+
+// one_to_many_symmetric.h:691-800 (Highway path for dims < 8, 4 lanes, no FMA).
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float neg_dot_small(LoadQ q, LoadX x, uint32_t n) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  for (; j + 4 <= n; j += 4) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[l] = __fsub_rn(a[l], __fmul_rn(q(j + l), x(j + l)));
+  }
+  if (j + 2 <= n) {
+    a[0] = __fsub_rn(a[0], __fmul_rn(q(j), x(j)));
+    a[1] = __fsub_rn(a[1], __fmul_rn(q(j + 1), x(j + 1)));
+    j += 2;
+  }
+  float r = __fadd_rn(__fadd_rn(a[0], a[2]), __fadd_rn(a[1], a[3]));
+  if (j < n) r = __fsub_rn(r, __fmul_rn(q(j), x(j)));
+  return r;
+}
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float sql2_small(LoadQ q, LoadX x, uint32_t n) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  for (; j + 4 <= n; j += 4) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float t = __fsub_rn(q(j + l), x(j + l));
+      a[l] = __fadd_rn(a[l], __fmul_rn(t, t));
+    }
+  }
+  if (j + 2 <= n) {
+    const float t0 = __fsub_rn(q(j), x(j)), t1 = __fsub_rn(q(j + 1), x(j + 1));
+    a[0] = __fadd_rn(a[0], __fmul_rn(t0, t0));
+    a[1] = __fadd_rn(a[1], __fmul_rn(t1, t1));
+    j += 2;
+  }
+  float r = __fadd_rn(__fadd_rn(a[0], a[2]), __fadd_rn(a[1], a[3]));
+  if (j < n) {
+    const float t = __fsub_rn(q(j), x(j));
+    r = __fadd_rn(r, __fmul_rn(t, t));
+  }
+  return r;
+}
+
+// distance_measures/one_to_one/dot_product_sse4.cc:242-296 (DenseDotProductSse4, float).
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float dot_sse4_order(LoadQ q, LoadX x, uint32_t n) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  if (n >= 8) {
+    float a0[4], a1[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      a0[l] = __fmul_rn(q(l), x(l));
+      a1[l] = __fmul_rn(q(4 + l), x(4 + l));
+    }
+    j = 8;
+    for (; j + 8 <= n; j += 8) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        a0[l] = __fadd_rn(a0[l], __fmul_rn(q(j + l), x(j + l)));
+        a1[l] = __fadd_rn(a1[l], __fmul_rn(q(j + 4 + l), x(j + 4 + l)));
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[l] = __fadd_rn(a0[l], a1[l]);
+  }
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[l] = __fadd_rn(a[l], __fmul_rn(q(j + l), x(j + l)));
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    a[0] = __fadd_rn(a[0], 0.0f);
+    a[1] = __fadd_rn(a[1], 0.0f);
+    a[2] = __fadd_rn(a[2], __fmul_rn(q(j), x(j)));
+    a[3] = __fadd_rn(a[3], __fmul_rn(q(j + 1), x(j + 1)));
+    j += 2;
+  }
+  if (j < n) a[0] = __fadd_rn(a[0], __fmul_rn(q(j), x(j)));
+  return __fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3]));
+}
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float sql2_sse4_order(LoadQ q, LoadX x, uint32_t n) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  if (n >= 8) {
+    float a0[4], a1[4];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float t0 = __fsub_rn(q(l), x(l)), t1 = __fsub_rn(q(4 + l), x(4 + l));
+      a0[l] = __fmul_rn(t0, t0);
+      a1[l] = __fmul_rn(t1, t1);
+    }
+    j = 8;
+    for (; j + 8 <= n; j += 8) {
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float t0 = __fsub_rn(q(j + l), x(j + l)), t1 = __fsub_rn(q(j + 4 + l), x(j + 4 + l));
+        a0[l] = __fadd_rn(a0[l], __fmul_rn(t0, t0));
+        a1[l] = __fadd_rn(a1[l], __fmul_rn(t1, t1));
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[l] = __fadd_rn(a0[l], a1[l]);
+  }
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float t = __fsub_rn(q(j + l), x(j + l));
+      a[l] = __fadd_rn(a[l], __fmul_rn(t, t));
+    }
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    const float t2 = __fsub_rn(q(j), x(j)), t3 = __fsub_rn(q(j + 1), x(j + 1));
+    a[2] = __fadd_rn(a[2], __fmul_rn(t2, t2));
+    a[3] = __fadd_rn(a[3], __fmul_rn(t3, t3));
+    j += 2;
+  }
+  if (j < n) {
+    const float t = __fsub_rn(q(j), x(j));
+    a[0] = __fadd_rn(a[0], __fmul_rn(t, t));
+  }
+  return __fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3]));
+}
+
+// lut16_avx2.inc:429,472-476: dist = float(acc) * float(1.0 / mult) + bias, two roundings.
+__device__ __forceinline__ float ah_float_score(int acc, float inv_mult, float bias) {
+  return __fadd_rn(__fmul_rn((float)acc, inv_mult), bias);
+}
+
+}  // namespace sb

@@ -1,0 +1,650 @@
+// index.cu -- the C ABI (include/scann_b200.h) and the host-side search driver.
+//
+// Host-side mirror of, in the reference:
+//   ScannInterface::Initialize / SearchBatched        scann_ops/cc/scann.cc:355-381,463-475
+//   SingleMachineSearcherBase::FindNeighborsBatched   base/single_machine_base.cc:569-587
+//   TreeAHHybridResidual::BuildLeafSearchers           tree_x_hybrid/tree_ah_hybrid_residual.cc:325-495
+//   TreeAHHybridResidual::FindNeighborsBatchedImpl     tree_x_hybrid/tree_ah_hybrid_residual.cc:631-846
+// There is no CPU path: every stage is a CUDA kernel; without a device creation fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/scann_b200.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                              \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess)                                                                    \
+      return fail(SCANN_B200_INTERNAL, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),    \
+                  __FILE__, __LINE__, cudaGetErrorString(_e));                                \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~PinnedBuf() { if (p) cudaFreeHost(p); }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; bytes = 0;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+size_t word_pos(int W, int j, int m) {
+  const int N4 = W / 4, R = W % 4;
+  if (j < 4 * N4) return (size_t)(j / 4) * 128 + (size_t)m * 4 + (j % 4);
+  const int jj = j - 4 * N4;
+  if (R >= 2 && jj < 2) return (size_t)N4 * 128 + (size_t)m * 2 + jj;
+  return (size_t)N4 * 128 + (R >= 2 ? 64 : 0) + m;
+}
+
+enum { EV_START, EV_TOK, EV_LUT, EV_PILOT, EV_WORK, EV_SCAN, EV_COMPACT, EV_FIN, EV_COUNT };
+
+}  // namespace
+
+struct scann_b200_index {
+  sb::DevIndex dev{};
+  scann_b200_index_desc desc{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+  std::vector<uint32_t> h_leaf_size;
+  // persistent device arrays
+  DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
+      codes, slot_dp, dataset, dp_row;
+  // workspace
+  DevBuf q, dist, leaves, bias, lut, mult, inv, pilot_end, buf, cnt, tau, ovf, leaf_cnt, leaf_eoff,
+      leaf_cur, item_off, entry_q, entry_bias, counters, stats, out_idx, out_dist;
+  PinnedBuf h_q, h_idx, h_dist, h_counters;
+  cudaEvent_t ev[EV_COUNT] = {};
+  scann_b200_stats last{};
+  uint32_t max_chunk = 16384;
+};
+
+namespace {
+
+int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
+  const uint32_t N = d->n, D = d->d, L = d->n_leaves, B = d->n_blocks;
+  if (d->distance != SCANN_B200_DOT_PRODUCT && d->distance != SCANN_B200_SQUARED_L2)
+    return fail(SCANN_B200_INVALID_ARGUMENT, "unknown distance measure %d", d->distance);
+  if (!L || !B) return fail(SCANN_B200_UNIMPLEMENTED, "only tree-AH indexes are implemented (n_leaves=%u, n_blocks=%u)", L, B);
+  if (!d->centers || !d->tokens || !d->codes || !d->codebook)
+    return fail(SCANN_B200_INVALID_ARGUMENT, "tree-AH index needs centers, tokens, codes and codebook");
+  if (B > 128) return fail(SCANN_B200_UNIMPLEMENTED, "n_blocks=%u > 128 not supported yet", B);
+  if (d->soar && !d->soar_codes) return fail(SCANN_B200_INVALID_ARGUMENT, "SOAR index without soar_codes");
+  const int world = d->shard_world > 0 ? d->shard_world : 1, rank = d->shard_rank;
+  if (rank < 0 || rank >= world) return fail(SCANN_B200_INVALID_ARGUMENT, "bad shard rank %d/%d", rank, world);
+  sb::DevIndex& v = ix->dev;
+  v.distance = d->distance; v.n = N; v.d = D; v.L = L; v.B = B; v.W = (B + 7) / 8; v.dpb = d->dims_per_block;
+  const int W = (int)v.W;
+
+  // datapoints_by_token in file order (scann_ops/cc/scann.cc:88-98), filtered to this shard
+  const uint32_t mult = d->soar ? 2 : 1;
+  const size_t len = (size_t)N * mult;
+  std::vector<uint32_t> lsize(L, 0);
+  for (size_t j = 0; j < len; ++j) {
+    const int32_t t = d->tokens[j];
+    if (t < 0) continue;
+    if ((uint32_t)t >= L) return fail(SCANN_B200_INVALID_ARGUMENT, "token %d out of range [0,%u)", t, L);
+    if ((j / mult) % world != (size_t)rank) continue;
+    lsize[t]++;
+  }
+  std::vector<uint32_t> goff(L + 1, 0), ntiles(L, 0), gpt(L, 0);
+  for (uint32_t l = 0; l < L; ++l) {
+    const uint32_t ng = (lsize[l] + 31) / 32;
+    goff[l + 1] = goff[l] + ng;
+    if (ng) {
+      ntiles[l] = (ng + sb::kMaxGroupsPerTile - 1) / sb::kMaxGroupsPerTile;
+      gpt[l] = (ng + ntiles[l] - 1) / ntiles[l];
+    }
+  }
+  const size_t ngroups = goff[L];
+  if (ngroups * 32 > 0xFFFFFFF0ull) return fail(SCANN_B200_UNIMPLEMENTED, "more than 2^32 slots");
+  std::vector<uint32_t> slot_dp(ngroups * 32, 0xFFFFFFFFu);
+  std::vector<uint32_t> codes((size_t)ngroups * W * 32, 0u);
+  int disjoint = 1;
+  {
+    std::vector<uint32_t> cur(L, 0);
+    for (size_t j = 0; j < len; ++j) {
+      const int32_t t = d->tokens[j];
+      if (t < 0) continue;
+      const uint32_t i = (uint32_t)(j / mult);
+      if (d->soar && (j & 1) && d->tokens[j - 1] >= 0) disjoint = 0;
+      if (i % world != (uint32_t)rank) continue;
+      const uint32_t s = cur[t]++;
+      const size_t g = goff[t] + s / 32;
+      const int m = (int)(s % 32);
+      slot_dp[g * 32 + m] = i;
+      // tree_ah_hybrid_residual.cc:385-396: the SOAR code row iff tok[2i+1] == leaf
+      const uint8_t* row = d->codes + (size_t)i * B;
+      if (d->soar && d->tokens[2 * (size_t)i + 1] == t) row = d->soar_codes + (size_t)i * B;
+      uint32_t* gw = codes.data() + g * W * 32;
+      for (int jw = 0; jw < W; ++jw) {
+        uint32_t wv = 0;
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t b = 8 * jw + k;
+          if (b < B) {
+            if (row[b] > 15) return fail(SCANN_B200_INVALID_ARGUMENT, "AH code %u > 15 at datapoint %u block %u", row[b], i, b);
+            wv |= (uint32_t)row[b] << (4 * k);
+          }
+        }
+        gw[word_pos(W, jw, m)] = wv;
+      }
+    }
+  }
+  v.disjoint = disjoint;
+  ix->h_leaf_size = lsize;
+
+  std::vector<int32_t> bdims(B);
+  std::vector<uint32_t> boff(B + 1, 0);
+  for (uint32_t b = 0; b < B; ++b) {
+    bdims[b] = d->block_dims ? d->block_dims[b] : (int32_t)d->dims_per_block;
+    if (bdims[b] <= 0 || (uint32_t)bdims[b] > d->dims_per_block)
+      return fail(SCANN_B200_INVALID_ARGUMENT, "block %u has %d dims (stride %u)", b, bdims[b], d->dims_per_block);
+    boff[b + 1] = boff[b] + (uint32_t)bdims[b];
+  }
+  if (boff[B] > D) return fail(SCANN_B200_INVALID_ARGUMENT, "AH blocks cover %u dims > dimensionality %u", boff[B], D);
+
+#define UP(buf, ptr, bytes_)                                                        \
+  do {                                                                              \
+    CU(buf.ensure((bytes_) ? (bytes_) : 16));                                       \
+    if (bytes_) CU(cudaMemcpy(buf.p, ptr, (bytes_), cudaMemcpyHostToDevice));       \
+  } while (0)
+  UP(ix->centers, d->centers, sizeof(float) * (size_t)L * D);
+  if (d->distance == SCANN_B200_SQUARED_L2) {
+    // many_to_many_impl.inc:236-257: ||c||^2 = -(fnmadd chain over dims)
+    std::vector<float> cn(L);
+    for (uint32_t l = 0; l < L; ++l) {
+      float a = 0.f;
+      for (uint32_t k = 0; k < D; ++k) a = fmaf(-d->centers[(size_t)l * D + k], d->centers[(size_t)l * D + k], a);
+      cn[l] = a * -1.0f;
+    }
+    UP(ix->cnorm, cn.data(), sizeof(float) * L);
+  }
+  UP(ix->codebook, d->codebook, sizeof(float) * (size_t)B * 16 * d->dims_per_block);
+  UP(ix->block_dims, bdims.data(), sizeof(int32_t) * B);
+  UP(ix->block_off, boff.data(), sizeof(uint32_t) * (B + 1));
+  UP(ix->leaf_size, lsize.data(), sizeof(uint32_t) * L);
+  UP(ix->leaf_goff, goff.data(), sizeof(uint32_t) * (L + 1));
+  UP(ix->leaf_ntiles, ntiles.data(), sizeof(uint32_t) * L);
+  UP(ix->leaf_gpt, gpt.data(), sizeof(uint32_t) * L);
+  UP(ix->codes, codes.data(), sizeof(uint32_t) * codes.size());
+  UP(ix->slot_dp, slot_dp.data(), sizeof(uint32_t) * slot_dp.size());
+  v.dataset = nullptr; v.dp_row = nullptr;
+  if (d->dataset) {
+    if (world == 1) {
+      UP(ix->dataset, d->dataset, sizeof(float) * (size_t)N * D);
+    } else {
+      std::vector<uint32_t> rowmap(N, 0xFFFFFFFFu);
+      size_t rows = 0;
+      for (uint32_t i = rank; i < N; i += world) rowmap[i] = (uint32_t)rows++;
+      CU(ix->dataset.ensure(sizeof(float) * std::max<size_t>(rows, 1) * D));
+      // rows of this shard are strided in the host array: copy with a pitched memcpy
+      if (rows)
+        CU(cudaMemcpy2D(ix->dataset.p, sizeof(float) * D, d->dataset + (size_t)rank * D,
+                        sizeof(float) * D * world, sizeof(float) * D, rows, cudaMemcpyHostToDevice));
+      UP(ix->dp_row, rowmap.data(), sizeof(uint32_t) * N);
+      v.dp_row = ix->dp_row.as<uint32_t>();
+    }
+    v.dataset = ix->dataset.as<float>();
+  }
+#undef UP
+  v.centers = ix->centers.as<float>();
+  v.centers_t = nullptr;
+  v.center_sqnorm = ix->cnorm.as<float>();
+  v.codebook = ix->codebook.as<float>();
+  v.block_dims = ix->block_dims.as<int32_t>();
+  v.block_off = ix->block_off.as<uint32_t>();
+  v.leaf_size = ix->leaf_size.as<uint32_t>();
+  v.leaf_goff = ix->leaf_goff.as<uint32_t>();
+  v.leaf_ntiles = ix->leaf_ntiles.as<uint32_t>();
+  v.leaf_gpt = ix->leaf_gpt.as<uint32_t>();
+  v.codes = ix->codes.as<uint32_t>();
+  v.slot_dp = ix->slot_dp.as<uint32_t>();
+  return 0;
+}
+
+struct Params { uint32_t k, npre, nover, P; };
+
+int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Params* p) {
+  // scann_ops/cc/scann.cc:406-430 + SetUnspecifiedParametersToDefaults
+  const bool has_reorder = ix->dev.dataset != nullptr;
+  const int k = final_nn > 0 ? final_nn : ix->desc.default_final_nn;
+  int npre = has_reorder ? (pre_nn > 0 ? pre_nn : ix->desc.default_pre_nn) : k;
+  int P = leaves > 0 ? leaves : ix->desc.default_leaves;
+  if (k <= 0 || npre <= 0 || P <= 0) return fail(SCANN_B200_INVALID_ARGUMENT, "search parameters must be positive (k=%d pre=%d leaves=%d)", k, npre, P);
+  if ((uint32_t)P > ix->dev.L) P = (int)ix->dev.L;
+  // tree_ah_hybrid_residual.h:263-267 + internal/utils.h:146-157
+  long long nover = npre;
+  if (!ix->dev.disjoint) {
+    const double r = (double)npre * (double)ix->desc.overretrieve;
+    nover = r > 2147483647.0 ? 2147483647LL : (long long)(int)r;
+  }
+  if (nover > 16384 || npre > 16384) return fail(SCANN_B200_UNIMPLEMENTED, "pre-reorder neighbours %lld > 16384 not supported", nover);
+  if (nover < 1) nover = 1;
+  if (P > 4096) return fail(SCANN_B200_UNIMPLEMENTED, "leaves_to_search %d > 4096 not supported", P);
+  p->k = (uint32_t)k; p->npre = (uint32_t)npre; p->nover = (uint32_t)nover; p->P = (uint32_t)P;
+  return 0;
+}
+
+uint32_t pick_cap(uint32_t nover) {
+  uint32_t cap = 2048;
+  while (cap < 4 * nover) cap <<= 1;
+  return cap;
+}
+
+int ensure_workspace(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_t out_k, uint32_t cap) {
+  const sb::DevIndex& v = ix->dev;
+  CU(ix->q.ensure(sizeof(float) * (size_t)nq * v.d));
+  CU(ix->dist.ensure(sizeof(float) * (size_t)nq * v.L));
+  CU(ix->leaves.ensure(sizeof(int32_t) * (size_t)nq * p.P));
+  CU(ix->bias.ensure(sizeof(float) * (size_t)nq * p.P));
+  CU(ix->lut.ensure((size_t)nq * v.W * 128));
+  CU(ix->mult.ensure(sizeof(float) * nq));
+  CU(ix->inv.ensure(sizeof(float) * nq));
+  CU(ix->pilot_end.ensure(sizeof(int32_t) * nq));
+  CU(ix->buf.ensure(sizeof(uint64_t) * (size_t)nq * cap));
+  CU(ix->cnt.ensure(sizeof(uint32_t) * nq));
+  CU(ix->tau.ensure(sizeof(uint64_t) * nq));
+  CU(ix->ovf.ensure(sizeof(uint32_t) * nq));
+  CU(ix->leaf_cnt.ensure(sizeof(uint32_t) * (v.L + 1)));
+  CU(ix->leaf_eoff.ensure(sizeof(uint32_t) * (v.L + 1)));
+  CU(ix->leaf_cur.ensure(sizeof(uint32_t) * (v.L + 1)));
+  CU(ix->item_off.ensure(sizeof(uint32_t) * (v.L + 1)));
+  CU(ix->entry_q.ensure(sizeof(uint32_t) * (size_t)nq * p.P));
+  CU(ix->entry_bias.ensure(sizeof(float) * (size_t)nq * p.P));
+  CU(ix->counters.ensure(sizeof(uint32_t) * 8));
+  CU(ix->stats.ensure(sizeof(unsigned long long) * 4));
+  CU(ix->out_idx.ensure(sizeof(uint32_t) * (size_t)nq * out_k));
+  CU(ix->out_dist.ensure(sizeof(float) * (size_t)nq * out_k));
+  CU(ix->h_counters.ensure(64));
+  return 0;
+}
+
+struct PartialOut { uint32_t* ids; uint64_t* tie; float* ah; float* exact; uint32_t cap; };
+
+// One chunk of queries, everything on the device.  d_q [nq][D]; outputs may be null when
+// only partial (sharded) records are wanted.
+int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Params& p,
+                 uint32_t* d_out_idx, float* d_out_dist, uint32_t out_k, const PartialOut* part,
+                 bool stop_after_candidates) {
+  const sb::DevIndex& v = ix->dev;
+  cudaStream_t s = ix->stream;
+  const uint32_t cap = pick_cap(p.nover);
+  if (int rc = ensure_workspace(ix, nq, p, out_k ? out_k : 1, cap)) return rc;
+  sb::ScanWork w{};
+  w.leaves = ix->leaves.as<int32_t>(); w.bias = ix->bias.as<float>(); w.lut = ix->lut.as<uint8_t>();
+  w.mult = ix->mult.as<float>(); w.inv_mult = ix->inv.as<float>(); w.pilot_end = ix->pilot_end.as<int32_t>();
+  w.buf = ix->buf.as<uint64_t>(); w.cnt = ix->cnt.as<uint32_t>(); w.tau = ix->tau.as<uint64_t>();
+  w.ovf = ix->ovf.as<uint32_t>(); w.leaf_cnt = ix->leaf_cnt.as<uint32_t>(); w.leaf_eoff = ix->leaf_eoff.as<uint32_t>();
+  w.leaf_cur = ix->leaf_cur.as<uint32_t>(); w.item_off = ix->item_off.as<uint32_t>();
+  w.entry_q = ix->entry_q.as<uint32_t>(); w.entry_bias = ix->entry_bias.as<float>();
+  w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
+  w.nq = nq; w.P = p.P; w.cap = cap; w.nover = p.nover; w.quads_per_item = 4;
+  int launches = 0;
+  uint32_t scan_launches = 0, retries = 0;
+
+  CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
+  CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
+  CU(cudaEventRecord(ix->ev[EV_START], s));
+  sb::launch_tokenize(v, d_q, nq, ix->dist.as<float>(), s);
+  sb::launch_topp(v, ix->dist.as<float>(), nq, p.P, ix->leaves.as<int32_t>(), ix->bias.as<float>(), s);
+  launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ix->ev[EV_TOK], s));
+  sb::launch_lut(v, d_q, nq, ix->lut.as<uint8_t>(), ix->mult.as<float>(), ix->inv.as<float>(), s);
+  launches += 1;
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ix->ev[EV_LUT], s));
+  CU(sb::launch_pilot(v, w, s));
+  launches += 1;
+  CU(cudaEventRecord(ix->ev[EV_PILOT], s));
+  sb::launch_worklist(v, w, false, s, &launches);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ix->ev[EV_WORK], s));
+  CU(sb::launch_scan(v, w, 0, s));
+  launches += 1; scan_launches += 1;
+  CU(cudaEventRecord(ix->ev[EV_SCAN], s));
+  CU(sb::launch_compact(v, w, false, s));
+  launches += 1;
+  CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
+  // overflow check: one 32-byte read back per chunk
+  uint32_t* hc = ix->h_counters.as<uint32_t>();
+  CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  while (hc[2] != 0) {
+    if (++retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
+    CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
+    sb::launch_worklist(v, w, true, s, &launches);
+    CU(sb::launch_scan(v, w, 0, s));
+    CU(sb::launch_compact(v, w, true, s));
+    launches += 2; scan_launches += 1;
+    CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  if (!stop_after_candidates) {
+    sb::FinalizeArgs a{};
+    a.q = d_q; a.nq = nq; a.npre = p.npre; a.k = p.k; a.out_k = out_k;
+    a.out_idx = d_out_idx; a.out_dist = d_out_dist;
+    if (part) { a.part_ids = part->ids; a.part_tie = part->tie; a.part_ah = part->ah; a.part_exact = part->exact; a.part_cap = part->cap; }
+    CU(sb::launch_finalize(v, w, a, s));
+    launches += 1;
+  }
+  CU(cudaEventRecord(ix->ev[EV_FIN], s));
+  unsigned long long hs[4];
+  CU(cudaMemcpyAsync(hs, w.stats, sizeof hs, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  float ms[EV_COUNT] = {0};
+  for (int i = 1; i < EV_COUNT; ++i) CU(cudaEventElapsedTime(&ms[i], ix->ev[i - 1], ix->ev[i]));
+  scann_b200_stats& st = ix->last;
+  st.scan_bytes_alg += hs[0];
+  st.scan_pairs += hs[1];
+  st.scan_lookups += hs[0] * 2;
+  st.kernel_launches += (uint32_t)launches;
+  st.overflow_retries += retries;
+  st.scan_kernel_count += scan_launches;
+  st.ms_tokenize += ms[EV_TOK]; st.ms_lut += ms[EV_LUT]; st.ms_pilot += ms[EV_PILOT];
+  st.ms_worklist += ms[EV_WORK]; st.ms_scan += ms[EV_SCAN]; st.ms_compact += ms[EV_COMPACT];
+  st.ms_finalize += ms[EV_FIN];
+  float tot = 0;
+  CU(cudaEventElapsedTime(&tot, ix->ev[EV_START], ix->ev[EV_FIN]));
+  st.ms_total += tot;
+  return 0;
+}
+
+int check_query_args(scann_b200_index* ix, const void* q, uint32_t nq) {
+  if (!ix) return fail(SCANN_B200_INVALID_ARGUMENT, "null index");
+  if (nq && !q) return fail(SCANN_B200_INVALID_ARGUMENT, "null queries");
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* scann_b200_last_error(void) { return g_err.c_str(); }
+int scann_b200_abi_version(void) { return SCANN_B200_ABI_VERSION; }
+
+int scann_b200_index_create(const scann_b200_index_desc* desc, scann_b200_index** out) {
+  if (!desc || !out) return fail(SCANN_B200_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(SCANN_B200_FAILED_PRECONDITION, "no CUDA device available (%s); scann_b200 has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (desc->device < 0 || desc->device >= ndev) return fail(SCANN_B200_INVALID_ARGUMENT, "device %d out of range", desc->device);
+  CU(cudaSetDevice(desc->device));
+  scann_b200_index* ix = new scann_b200_index();
+  ix->desc = *desc;
+  ix->device = desc->device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, desc->device) == cudaSuccess) ix->sm_count = prop.multiProcessorCount;
+  int rc = build_index(ix, desc);
+  if (rc == 0) {
+    cudaError_t se = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) rc = fail(SCANN_B200_INTERNAL, "cudaStreamCreate: %s", cudaGetErrorString(se));
+    for (int i = 0; i < EV_COUNT && rc == 0; ++i)
+      if (cudaEventCreate(&ix->ev[i]) != cudaSuccess) rc = fail(SCANN_B200_INTERNAL, "cudaEventCreate failed");
+  }
+  if (rc) { delete ix; return rc; }
+  // host pointers must not outlive this call
+  ix->desc.centers = nullptr; ix->desc.tokens = nullptr; ix->desc.codes = nullptr; ix->desc.soar_codes = nullptr;
+  ix->desc.codebook = nullptr; ix->desc.dataset = nullptr; ix->desc.bf16_dataset = nullptr; ix->desc.block_dims = nullptr;
+  *out = ix;
+  return 0;
+}
+
+void scann_b200_index_destroy(scann_b200_index* ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
+  for (int i = 0; i < EV_COUNT; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+  delete ix;
+}
+
+uint32_t scann_b200_leaf_size(const scann_b200_index* ix, uint32_t leaf) {
+  return (ix && leaf < ix->h_leaf_size.size()) ? ix->h_leaf_size[leaf] : 0;
+}
+
+int scann_b200_search_batched_device(scann_b200_index* ix, const float* d_queries, uint32_t nq,
+                                     int32_t final_nn, int32_t pre_nn, int32_t leaves,
+                                     uint32_t* d_out_idx, float* d_out_dist, int32_t out_k) {
+  if (int rc = check_query_args(ix, d_queries, nq)) return rc;
+  Params p;
+  if (int rc = resolve(ix, final_nn, pre_nn, leaves, &p)) return rc;
+  if (out_k <= 0 || !d_out_idx || !d_out_dist) return fail(SCANN_B200_INVALID_ARGUMENT, "bad output buffers");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  ix->last = scann_b200_stats{};
+  for (uint32_t s0 = 0; s0 < nq; s0 += ix->max_chunk) {
+    const uint32_t c = std::min(ix->max_chunk, nq - s0);
+    if (int rc = search_chunk(ix, d_queries + (size_t)s0 * ix->dev.d, c, p, d_out_idx + (size_t)s0 * out_k,
+                              d_out_dist + (size_t)s0 * out_k, (uint32_t)out_k, nullptr, false))
+      return rc;
+  }
+  return 0;
+}
+
+int scann_b200_search_batched(scann_b200_index* ix, const float* queries, uint32_t nq, int32_t final_nn,
+                              int32_t pre_nn, int32_t leaves, uint32_t* out_idx, float* out_dist,
+                              int32_t out_k) {
+  if (int rc = check_query_args(ix, queries, nq)) return rc;
+  Params p;
+  if (int rc = resolve(ix, final_nn, pre_nn, leaves, &p)) return rc;
+  if (out_k <= 0 || !out_idx || !out_dist) return fail(SCANN_B200_INVALID_ARGUMENT, "bad output buffers");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  ix->last = scann_b200_stats{};
+  const uint32_t D = ix->dev.d;
+  for (uint32_t s0 = 0; s0 < nq; s0 += ix->max_chunk) {
+    const uint32_t c = std::min(ix->max_chunk, nq - s0);
+    CU(ix->q.ensure(sizeof(float) * (size_t)c * D));
+    CU(ix->out_idx.ensure(sizeof(uint32_t) * (size_t)c * out_k));
+    CU(ix->out_dist.ensure(sizeof(float) * (size_t)c * out_k));
+    CU(ix->h_q.ensure(sizeof(float) * (size_t)c * D));
+    CU(ix->h_idx.ensure(sizeof(uint32_t) * (size_t)c * out_k));
+    CU(ix->h_dist.ensure(sizeof(float) * (size_t)c * out_k));
+    memcpy(ix->h_q.p, queries + (size_t)s0 * D, sizeof(float) * (size_t)c * D);
+    CU(cudaMemcpyAsync(ix->q.p, ix->h_q.p, sizeof(float) * (size_t)c * D, cudaMemcpyHostToDevice, ix->stream));
+    if (int rc = search_chunk(ix, ix->q.as<float>(), c, p, ix->out_idx.as<uint32_t>(), ix->out_dist.as<float>(),
+                              (uint32_t)out_k, nullptr, false))
+      return rc;
+    CU(cudaMemcpyAsync(ix->h_idx.p, ix->out_idx.p, sizeof(uint32_t) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaMemcpyAsync(ix->h_dist.p, ix->out_dist.p, sizeof(float) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaStreamSynchronize(ix->stream));
+    memcpy(out_idx + (size_t)s0 * out_k, ix->h_idx.p, sizeof(uint32_t) * (size_t)c * out_k);
+    memcpy(out_dist + (size_t)s0 * out_k, ix->h_dist.p, sizeof(float) * (size_t)c * out_k);
+  }
+  return 0;
+}
+
+int scann_b200_search_partial_device(scann_b200_index* ix, const float* d_queries, uint32_t nq,
+                                     int32_t pre_nn, int32_t leaves, uint32_t* d_ids, uint64_t* d_tie,
+                                     float* d_ah, float* d_exact, int32_t n_cand) {
+  if (int rc = check_query_args(ix, d_queries, nq)) return rc;
+  Params p;
+  if (int rc = resolve(ix, -1, pre_nn, leaves, &p)) return rc;
+  if (!d_ids || !d_tie || !d_ah || !d_exact || n_cand < (int)p.npre)
+    return fail(SCANN_B200_INVALID_ARGUMENT, "partial buffers too small: n_cand=%d < %u", n_cand, p.npre);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  ix->last = scann_b200_stats{};
+  for (uint32_t s0 = 0; s0 < nq; s0 += ix->max_chunk) {
+    const uint32_t c = std::min(ix->max_chunk, nq - s0);
+    PartialOut po{d_ids + (size_t)s0 * n_cand, d_tie + (size_t)s0 * n_cand, d_ah + (size_t)s0 * n_cand,
+                  d_exact + (size_t)s0 * n_cand, (uint32_t)n_cand};
+    if (int rc = search_chunk(ix, d_queries + (size_t)s0 * ix->dev.d, c, p, nullptr, nullptr, 0, &po, false)) return rc;
+  }
+  return 0;
+}
+
+int scann_b200_merge_partials_device(scann_b200_index* ix, uint32_t nq, int32_t world, int32_t n_cand,
+                                     const uint32_t* d_ids, const uint64_t* d_tie, const float* d_ah,
+                                     const float* d_exact, int32_t pre_nn, int32_t final_nn,
+                                     uint32_t* d_out_idx, float* d_out_dist, int32_t out_k) {
+  if (!ix) return fail(SCANN_B200_INVALID_ARGUMENT, "null index");
+  Params p;
+  if (int rc = resolve(ix, final_nn, pre_nn, -1, &p)) return rc;
+  if ((long long)world * n_cand > 32768) return fail(SCANN_B200_UNIMPLEMENTED, "merge of %d x %d candidates too large", world, n_cand);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  CU(sb::launch_merge_partials(ix->dev, nq, world, n_cand, d_ids, d_tie, d_ah, d_exact, p.npre, p.k, d_out_idx,
+                               d_out_dist, (uint32_t)out_k, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return 0;
+}
+
+int scann_b200_last_stats(scann_b200_index* ix, scann_b200_stats* out) {
+  if (!ix || !out) return fail(SCANN_B200_INVALID_ARGUMENT, "null argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  *out = ix->last;
+  return 0;
+}
+
+// ---- debug / parity hooks ------------------------------------------------------------------
+
+int scann_b200_debug_tokenize(scann_b200_index* ix, const float* queries, uint32_t nq, int32_t leaves,
+                              int32_t* out_leaf, float* out_dist) {
+  if (int rc = check_query_args(ix, queries, nq)) return rc;
+  Params p;
+  if (int rc = resolve(ix, -1, -1, leaves, &p)) return rc;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  const sb::DevIndex& v = ix->dev;
+  if (int rc = ensure_workspace(ix, nq, p, 1, pick_cap(p.nover))) return rc;
+  CU(cudaMemcpyAsync(ix->q.p, queries, sizeof(float) * (size_t)nq * v.d, cudaMemcpyHostToDevice, ix->stream));
+  sb::launch_tokenize(v, ix->q.as<float>(), nq, ix->dist.as<float>(), ix->stream);
+  sb::launch_topp(v, ix->dist.as<float>(), nq, p.P, ix->leaves.as<int32_t>(), ix->bias.as<float>(), ix->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out_leaf, ix->leaves.p, sizeof(int32_t) * (size_t)nq * p.P, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaMemcpyAsync(out_dist, ix->bias.p, sizeof(float) * (size_t)nq * p.P, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return 0;
+}
+
+int scann_b200_debug_lut(scann_b200_index* ix, const float* queries, uint32_t nq, uint8_t* out_lut, float* out_mult) {
+  if (int rc = check_query_args(ix, queries, nq)) return rc;
+  Params p;
+  if (int rc = resolve(ix, -1, -1, -1, &p)) return rc;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  const sb::DevIndex& v = ix->dev;
+  if (int rc = ensure_workspace(ix, nq, p, 1, pick_cap(p.nover))) return rc;
+  CU(cudaMemcpyAsync(ix->q.p, queries, sizeof(float) * (size_t)nq * v.d, cudaMemcpyHostToDevice, ix->stream));
+  sb::launch_lut(v, ix->q.as<float>(), nq, ix->lut.as<uint8_t>(), ix->mult.as<float>(), ix->inv.as<float>(), ix->stream);
+  CU(cudaGetLastError());
+  // device rows are padded to 8W blocks; return the first B blocks of each
+  CU(cudaMemcpy2DAsync(out_lut, (size_t)v.B * 16, ix->lut.p, (size_t)v.W * 128, (size_t)v.B * 16, nq,
+                       cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaMemcpyAsync(out_mult, ix->mult.p, sizeof(float) * nq, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return 0;
+}
+
+int scann_b200_debug_leaf_scores(scann_b200_index* ix, const uint8_t* lut, uint32_t leaf, int16_t* out, uint32_t out_len) {
+  if (!ix || !lut || !out) return fail(SCANN_B200_INVALID_ARGUMENT, "null argument");
+  if (leaf >= ix->dev.L) return fail(SCANN_B200_INVALID_ARGUMENT, "leaf %u out of range", leaf);
+  const uint32_t n = ix->h_leaf_size[leaf];
+  if (out_len < n) return fail(SCANN_B200_INVALID_ARGUMENT, "output too small");
+  if (n == 0) return 0;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  const sb::DevIndex& v = ix->dev;
+  DevBuf dl, dout;
+  CU(dl.ensure((size_t)v.W * 128));
+  CU(dout.ensure(sizeof(int16_t) * n));
+  CU(cudaMemsetAsync(dl.p, 0, (size_t)v.W * 128, ix->stream));
+  CU(cudaMemcpyAsync(dl.p, lut, (size_t)v.B * 16, cudaMemcpyHostToDevice, ix->stream));
+  sb::launch_leaf_scores(v, dl.as<uint8_t>(), leaf, dout.as<int16_t>(), ix->stream);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dout.p, sizeof(int16_t) * n, cudaMemcpyDeviceToHost, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return 0;
+}
+
+int scann_b200_debug_candidates(scann_b200_index* ix, const float* queries, uint32_t nq, int32_t pre_nn,
+                                int32_t leaves, int32_t cap, uint32_t* out_leaf, uint32_t* out_slot,
+                                uint32_t* out_dp, float* out_score, uint32_t* out_count) {
+  if (int rc = check_query_args(ix, queries, nq)) return rc;
+  Params p;
+  if (int rc = resolve(ix, -1, pre_nn, leaves, &p)) return rc;
+  if (nq > ix->max_chunk) return fail(SCANN_B200_INVALID_ARGUMENT, "debug_candidates: at most %u queries", ix->max_chunk);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  const sb::DevIndex& v = ix->dev;
+  ix->last = scann_b200_stats{};
+  CU(ix->q.ensure(sizeof(float) * (size_t)nq * v.d));
+  CU(cudaMemcpyAsync(ix->q.p, queries, sizeof(float) * (size_t)nq * v.d, cudaMemcpyHostToDevice, ix->stream));
+  if (int rc = search_chunk(ix, ix->q.as<float>(), nq, p, nullptr, nullptr, 0, nullptr, true)) return rc;
+  const uint32_t dcap = pick_cap(p.nover);
+  std::vector<uint64_t> keys((size_t)nq * dcap);
+  std::vector<uint32_t> cnt(nq);
+  std::vector<uint32_t> goff(v.L + 1), sdp;
+  CU(cudaMemcpy(keys.data(), ix->buf.p, sizeof(uint64_t) * keys.size(), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(cnt.data(), ix->cnt.p, sizeof(uint32_t) * nq, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(goff.data(), ix->leaf_goff.p, sizeof(uint32_t) * (v.L + 1), cudaMemcpyDeviceToHost));
+  sdp.resize((size_t)goff[v.L] * 32);
+  CU(cudaMemcpy(sdp.data(), ix->slot_dp.p, sizeof(uint32_t) * sdp.size(), cudaMemcpyDeviceToHost));
+  for (uint32_t i = 0; i < nq; ++i) {
+    const uint32_t n = std::min<uint32_t>(std::min(cnt[i], p.nover), (uint32_t)cap);
+    out_count[i] = n;
+    for (uint32_t j = 0; j < n; ++j) {
+      const uint64_t k = keys[(size_t)i * dcap + j];
+      const uint32_t gs = (uint32_t)k, g = gs / 32;
+      const uint32_t leaf = (uint32_t)(std::upper_bound(goff.begin(), goff.end(), g) - goff.begin()) - 1;
+      const size_t o = (size_t)i * cap + j;
+      out_leaf[o] = leaf;
+      out_slot[o] = gs - goff[leaf] * 32;
+      out_dp[o] = sdp[gs];
+      uint32_t ord = (uint32_t)(k >> 32);
+      uint32_t u = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
+      memcpy(&out_score[o], &u, 4);
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

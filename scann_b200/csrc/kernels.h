@@ -1,0 +1,87 @@
+// kernels.h -- launch wrappers for the sm_100a kernels of the batched query path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr int kScanThreads = 128;     // 4 warps per scan CTA
+constexpr int kScanWarps = 4;
+constexpr int kMaxGroupsPerTile = 32; // 32-slot groups per (leaf tile) work item
+constexpr int kQueriesPerQuad = 4;    // queries packed into one 64-bit LUT entry
+
+// Device view of one searcher (all pointers are device pointers).
+struct DevIndex {
+  int distance;
+  uint32_t n, d, L, B, W, dpb;
+  int disjoint;
+  const float* centers;       // [L][D]
+  const float* centers_t;     // [D][L] (unused by the kernels, kept for debugging)
+  const float* center_sqnorm; // [L] squared-L2 tokenization only
+  const float* codebook;      // [B][16][dpb]
+  const int32_t* block_dims;  // [B]
+  const uint32_t* block_off;  // [B+1]
+  const uint32_t* leaf_size;  // [L] real slots
+  const uint32_t* leaf_goff;  // [L+1] offset in 32-slot groups
+  const uint32_t* leaf_ntiles;// [L] work tiles per leaf
+  const uint32_t* leaf_gpt;   // [L] groups per tile
+  const uint32_t* codes;      // [groups][W*32] packed nibble words (see pack_codes in index.cu)
+  const uint32_t* slot_dp;    // [groups*32] datapoint id per slot, 0xFFFFFFFF padding
+  const float* dataset;       // [rows][D] f32 rows for exact reordering (NULL if none)
+  const uint32_t* dp_row;     // [N] datapoint id -> row of `dataset` (NULL = identity)
+};
+
+struct ScanWork {
+  // per-batch work description, all device pointers
+  const int32_t* leaves;      // [nq][P] probed leaves sorted by (distance, leaf)
+  const float* bias;          // [nq][P] distance to centre
+  const uint8_t* lut;         // [nq][W*8*16]
+  const float* mult;          // [nq]
+  const float* inv_mult;      // [nq]
+  int32_t* pilot_end;         // [nq] first rank the pilot did not scan
+  uint64_t* buf;              // [nq][cap] candidate keys
+  uint32_t* cnt;              // [nq]
+  uint64_t* tau;              // [nq] push only keys < tau
+  uint32_t* ovf;              // [nq] overflow flag
+  uint32_t* leaf_cnt;         // [L+1]
+  uint32_t* leaf_eoff;        // [L+1]
+  uint32_t* leaf_cur;         // [L]
+  uint32_t* item_off;         // [L+1]
+  uint32_t* entry_q;          // [nq*P]
+  float* entry_bias;          // [nq*P]
+  uint32_t* counters;         // [8]: 0 item counter, 1 n_items, 2 n_ovf, 3 n_entries
+  unsigned long long* stats;  // [4]: 0 bytes_alg, 1 pairs, 2 lookups
+  uint32_t nq, P, cap, nover, quads_per_item;
+};
+
+// ---- query preparation ----
+void launch_tokenize(const DevIndex& ix, const float* q, uint32_t nq, float* dist, cudaStream_t s);
+void launch_topp(const DevIndex& ix, const float* dist, uint32_t nq, uint32_t P, int32_t* leaves,
+                 float* bias, cudaStream_t s);
+void launch_lut(const DevIndex& ix, const float* q, uint32_t nq, uint8_t* lut, float* mult,
+                float* inv_mult, cudaStream_t s);
+// ---- scan ----
+size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover);
+size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item);
+cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s);
+void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, cudaStream_t s, int* launches);
+cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s);
+cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s);
+// ---- finalize ----
+struct FinalizeArgs {
+  const float* q;         // [nq][D]
+  uint32_t nq, npre, k, out_k;
+  uint32_t* out_idx;      // [nq][out_k]
+  float* out_dist;        // [nq][out_k]
+  // partial (sharded) outputs, optional
+  uint32_t* part_ids; uint64_t* part_tie; float* part_ah; float* part_exact; uint32_t part_cap;
+};
+cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const FinalizeArgs& a, cudaStream_t s);
+cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, int n_cand,
+                                  const uint32_t* ids, const uint64_t* tie, const float* ah,
+                                  const float* exact, uint32_t npre, uint32_t k, uint32_t* out_idx,
+                                  float* out_dist, uint32_t out_k, cudaStream_t s);
+// ---- debug ----
+void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s);
+
+}  // namespace sb

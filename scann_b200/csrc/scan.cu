@@ -1,0 +1,581 @@
+// scan.cu -- the LUT16 scan: 4-bit codes x uint8 LUT, int16 accumulate, fused threshold top-N.
+//
+// Replaces (a7/a8/a9) of SURVEY.md section 8:
+//   TreeAHHybridResidual::FindNeighborsBatchedImpl     tree_x_hybrid/tree_ah_hybrid_residual.cc:631-786
+//   LUT16Avx2<>::GetTopFloatDistances / BottomLoop     hashes/internal/lut16_avx2.inc:55-124,404-527
+//   FastTopNeighbors<float>                            utils/fast_top_neighbors.h:43-299
+//
+// B200 formulation.  The CPU kernel looks one query's 16-entry uint8 table up with vpshufb
+// for 32 datapoints at a time.  Here the unit of work is a QUAD of four queries that probe
+// the same leaf: their four uint8 tables are interleaved in shared memory into one table of
+// 64-bit entries  T[b][c] = {lut0 | lut1 << 16, lut2 | lut3 << 16},  so ONE conflict-free
+// LDS.64 (16 distinct entries = 16 distinct bank pairs, equal entries broadcast) serves four
+// (query, datapoint, block) lookups and two 32-bit adds accumulate four u16 sums
+// (B <= 256 => sum <= 65280, no carry between the halves).  Each thread owns one datapoint
+// of a 32-slot group: its B nibbles live in W = ceil(B/8) registers, loaded once per work
+// item with coalesced 128-bit loads and reused for every quad of the item.
+//
+// Top-N.  Every query owns a candidate buffer buf[q][cap] in HBM, a count and a threshold
+// key tau[q] (score, global slot).  A PILOT kernel (one CTA per query) scans the nearest
+// leaves until it has seen >= N candidates, keeps the exact N best in shared memory and
+// publishes tau.  The MAIN kernel scans every remaining (query, leaf) pair, grouped by leaf
+// into quads, with an integer pre-filter (sum <= thr, conservative) and an exact 64-bit key
+// comparison; survivors are appended with one warp-aggregated atomic.  COMPACT sorts each
+// buffer and keeps the N smallest keys.  The result is the exact top-N under
+// (float score, leaf, slot) -- the contract of SURVEY.md section 7 hard-part 1 -- regardless of
+// scheduling.  If a buffer overflowed, the host re-scans only the affected queries with the
+// tightened tau (duplicates are removed by key), so no candidate can be lost.
+#include "common.cuh"
+#include "exact_math.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+constexpr uint32_t kInvalidQuery = 0xFFFFFFFFu;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+constexpr int kMaxQPI = 16;  // queries per work item (4 quads)
+
+// ---- packed code layout -------------------------------------------------------------------
+// Per 32-slot group: W 32-bit words per slot (nibble k of word j = code of block 8j+k), stored
+// as planes so that a warp's loads are contiguous: floor(W/4) uint4 planes (512 B each), then
+// one uint2 plane if W%4 >= 2, then one u32 plane if W is odd.  W*128 bytes per group.
+template <int W>
+__device__ __forceinline__ void load_codes(const uint32_t* __restrict__ gbase, int lane,
+                                           uint32_t (&w)[W]) {
+  constexpr int N4 = W / 4, R = W % 4;
+#pragma unroll
+  for (int p = 0; p < N4; ++p) {
+    const uint4 v = ldg_stream_v4(gbase + p * 128 + lane * 4);
+    w[4 * p + 0] = v.x; w[4 * p + 1] = v.y; w[4 * p + 2] = v.z; w[4 * p + 3] = v.w;
+  }
+  if constexpr (R >= 2) {
+    const uint2 v = ldg_stream_v2(gbase + N4 * 128 + lane * 2);
+    w[4 * N4 + 0] = v.x; w[4 * N4 + 1] = v.y;
+  }
+  if constexpr (R & 1) {
+    w[W - 1] = ldg_stream_u32(gbase + N4 * 128 + ((R >= 2) ? 64 : 0) + lane);
+  }
+}
+
+// Four queries' u16 sums for one datapoint: a01 = s0 | s1 << 16, a23 = s2 | s3 << 16.
+template <int W>
+__device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigned char* tbl,
+                                           int nlast, uint32_t& a01, uint32_t& a23) {
+  uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (j == W - 1 && k >= nlast) continue;
+      const uint32_t off = (k == 0) ? ((w[j] << 3) & 0x78u) : ((w[j] >> (4 * k - 3)) & 0x78u);
+      const uint2 v = *reinterpret_cast<const uint2*>(tbl + (8 * j + k) * 128 + off);
+      if (k & 1) { x1 += v.x; y1 += v.y; } else { x0 += v.x; y0 += v.y; }
+    }
+  }
+  a01 = x0 + x1;
+  a23 = y0 + y1;
+}
+
+// Interleave up to four uint8 LUTs (8W*16 bytes each, NULL = all zero) into a quad table.
+__device__ __forceinline__ void build_quad_table(uint2* __restrict__ tbl, const uint8_t* l0,
+                                                 const uint8_t* l1, const uint8_t* l2,
+                                                 const uint8_t* l3, int n_entries, int tid,
+                                                 int nthreads) {
+  for (int t = tid; t < n_entries / 4; t += nthreads) {
+    const uint32_t a = l0 ? reinterpret_cast<const uint32_t*>(l0)[t] : 0u;
+    const uint32_t b = l1 ? reinterpret_cast<const uint32_t*>(l1)[t] : 0u;
+    const uint32_t c = l2 ? reinterpret_cast<const uint32_t*>(l2)[t] : 0u;
+    const uint32_t d = l3 ? reinterpret_cast<const uint32_t*>(l3)[t] : 0u;
+    uint4 o0, o1;
+    o0.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu; o0.y = __byte_perm(c, d, 0x0400) & 0x00FF00FFu;
+    o0.z = __byte_perm(a, b, 0x0501) & 0x00FF00FFu; o0.w = __byte_perm(c, d, 0x0501) & 0x00FF00FFu;
+    o1.x = __byte_perm(a, b, 0x0602) & 0x00FF00FFu; o1.y = __byte_perm(c, d, 0x0602) & 0x00FF00FFu;
+    o1.z = __byte_perm(a, b, 0x0703) & 0x00FF00FFu; o1.w = __byte_perm(c, d, 0x0703) & 0x00FF00FFu;
+    reinterpret_cast<uint4*>(tbl)[2 * t] = o0;
+    reinterpret_cast<uint4*>(tbl)[2 * t + 1] = o1;
+  }
+}
+
+// Largest accumulator value whose float score is <= the score of `tau` (conservative integer
+// pre-filter; the reference's trunc((eps - bias) * mult) of lut16_avx2.inc:432-438 may drop a
+// candidate that is strictly better than eps, this one never does).
+__device__ int acc_threshold(uint64_t tau, float mult, float inv, float bias) {
+  if (tau == kKeyMax) return 40000;
+  const float ts = ord2f((uint32_t)(tau >> 32));
+  const float est = __fmul_rn(__fsub_rn(ts, bias), mult);
+  int t;
+  if (!(est < 40000.f)) t = 32767;
+  else if (!(est > -40000.f)) t = -32769;
+  else t = (int)floorf(est);
+  t = min(t, 32767);
+  t = max(t, -32769);
+  while (t < 32767 && ah_float_score(t + 1, inv, bias) <= ts) ++t;
+  while (t >= -32768 && ah_float_score(t, inv, bias) > ts) --t;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------
+// Pilot: one CTA per query, nearest leaves first, exact top-N in shared memory.
+// ---------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kScanThreads)
+pilot_kernel(DevIndex ix, ScanWork w, int capl) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint2* tbl = reinterpret_cast<uint2*>(smem);                       // [W*128]
+  uint64_t* scand = reinterpret_cast<uint64_t*>(smem + W * 128 * 8);  // [capl]
+  __shared__ uint64_t s_tau;
+  __shared__ int s_thr;
+  __shared__ uint32_t s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t q = blockIdx.x;
+  const int nlast = (int)ix.B - 8 * (W - 1);
+  const int off128 = 128 * (int)ix.B;
+  const uint32_t nover = w.nover;
+  build_quad_table(tbl, w.lut + (size_t)q * W * 128, nullptr, nullptr, nullptr, W * 128, tid, kScanThreads);
+  if (tid == 0) { s_tau = kKeyMax; s_cnt = 0; }
+  const float mult = w.mult[q], inv = w.inv_mult[q];
+  uint32_t seen = 0;
+  uint32_t r = 0;
+  for (; r < w.P; ++r) {
+    const int leaf = w.leaves[(size_t)q * w.P + r];
+    if (leaf < 0) break;
+    const float bias = w.bias[(size_t)q * w.P + r];
+    const uint32_t n = ix.leaf_size[leaf];
+    const uint32_t gbeg = ix.leaf_goff[leaf], ng = ix.leaf_goff[leaf + 1] - gbeg;
+    __syncthreads();
+    if (tid == 0) s_thr = acc_threshold(s_tau, mult, inv, bias) + off128;
+    __syncthreads();
+    for (uint32_t g0 = 0; g0 < ng; g0 += kScanWarps) {
+      const uint32_t g = g0 + warp;
+      if (g < ng) {
+        uint32_t cw[W];
+        load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
+        uint32_t a01, a23;
+        score_quad<W>(cw, reinterpret_cast<const unsigned char*>(tbl), nlast, a01, a23);
+        const int s0 = (int)(a01 & 0xFFFFu);
+        bool p = (g * 32 + lane < n) && s0 <= s_thr;
+        uint64_t key = 0;
+        if (p) {
+          key = make_key(ah_float_score(s0 - off128, inv, bias), (gbeg + g) * 32 + lane);
+          p = key < s_tau;
+        }
+        const uint32_t m = __ballot_sync(kFull, p);
+        if (m) {
+          const int leader = __ffs(m) - 1;
+          uint32_t base = 0;
+          if (lane == leader) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
+          base = __shfl_sync(kFull, base, leader);
+          if (p) scand[base + __popc(m & ((1u << lane) - 1u))] = key;
+        }
+      }
+      __syncthreads();
+      const uint32_t c = s_cnt;
+      __syncthreads();  // everyone has read s_cnt before the next round may bump it
+      if (c > (uint32_t)(capl - kScanThreads)) {
+        for (int i = c + tid; i < capl; i += kScanThreads) scand[i] = kKeyMax;
+        __syncthreads();
+        block_bitonic_sort(scand, capl);
+        if (tid == 0) {
+          if (c >= nover) { s_cnt = nover; s_tau = scand[nover - 1]; }
+          s_thr = acc_threshold(s_tau, mult, inv, bias) + off128;
+        }
+        __syncthreads();
+      }
+    }
+    seen += n;
+    if (seen >= nover) { ++r; break; }
+  }
+  __syncthreads();
+  const uint32_t c = s_cnt;
+  int np2 = 2;
+  while ((uint32_t)np2 < c) np2 <<= 1;
+  for (int i = c + tid; i < np2; i += kScanThreads) scand[i] = kKeyMax;
+  __syncthreads();
+  block_bitonic_sort(scand, np2);
+  const uint32_t keep = min(c, nover);
+  for (uint32_t i = tid; i < keep; i += kScanThreads) w.buf[(size_t)q * w.cap + i] = scand[i];
+  if (tid == 0) {
+    w.cnt[q] = keep;
+    w.tau[q] = (keep >= nover) ? scand[nover - 1] : kKeyMax;
+    w.pilot_end[q] = (int32_t)r;
+    w.ovf[q] = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Work list: (query, rank >= pilot_end) pairs bucketed by leaf, then cut into items of
+// (leaf tile, <= quads_per_item quads).
+// ---------------------------------------------------------------------------------------
+__global__ void worklist_count_kernel(DevIndex ix, ScanWork w, int only_ovf, int count_stats) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)w.nq * w.P;
+  unsigned long long bytes = 0, pairs = 0;
+  if (i < total) {
+    const uint32_t q = (uint32_t)(i / w.P), r = (uint32_t)(i % w.P);
+    const int leaf = w.leaves[i];
+    if (leaf >= 0) {
+      if (count_stats) {
+        const uint32_t ng = ix.leaf_goff[leaf + 1] - ix.leaf_goff[leaf];
+        bytes = (unsigned long long)ng * 16ull * ix.B;
+        pairs = 1;
+      }
+      if ((int)r >= w.pilot_end[q] && (!only_ovf || w.ovf[q])) atomicAdd(&w.leaf_cnt[leaf], 1u);
+    }
+  }
+  if (count_stats) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      bytes += __shfl_xor_sync(kFull, bytes, o);
+      pairs += __shfl_xor_sync(kFull, pairs, o);
+    }
+    if ((threadIdx.x & 31) == 0 && pairs) {
+      atomicAdd(&w.stats[0], bytes);
+      atomicAdd(&w.stats[1], pairs);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) worklist_scan_kernel(DevIndex ix, ScanWork w) {
+  __shared__ uint32_t wsum_e[32], wsum_i[32];
+  __shared__ uint32_t carry_e, carry_i;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) { carry_e = 0; carry_i = 0; }
+  __syncthreads();
+  for (uint32_t base = 0; base < ix.L; base += 1024) {
+    const uint32_t l = base + tid;
+    uint32_t ce = 0, ci = 0;
+    if (l < ix.L) {
+      ce = w.leaf_cnt[l];
+      const uint32_t qpi = w.quads_per_item * kQueriesPerQuad;
+      ci = ((ce + qpi - 1) / qpi) * ix.leaf_ntiles[l];
+    }
+    uint32_t se = ce, si = ci;  // inclusive warp scan
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t te = __shfl_up_sync(kFull, se, o), ti = __shfl_up_sync(kFull, si, o);
+      if (lane >= o) { se += te; si += ti; }
+    }
+    if (lane == 31) { wsum_e[warp] = se; wsum_i[warp] = si; }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t ve = wsum_e[lane], vi = wsum_i[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t te = __shfl_up_sync(kFull, ve, o), ti = __shfl_up_sync(kFull, vi, o);
+        if (lane >= o) { ve += te; vi += ti; }
+      }
+      wsum_e[lane] = ve; wsum_i[lane] = vi;
+    }
+    __syncthreads();
+    const uint32_t pe = carry_e + (warp ? wsum_e[warp - 1] : 0u) + se - ce;
+    const uint32_t pi = carry_i + (warp ? wsum_i[warp - 1] : 0u) + si - ci;
+    if (l < ix.L) { w.leaf_eoff[l] = pe; w.item_off[l] = pi; w.leaf_cur[l] = 0; }
+    __syncthreads();
+    if (tid == 0) { carry_e += wsum_e[31]; carry_i += wsum_i[31]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    w.leaf_eoff[ix.L] = carry_e;
+    w.item_off[ix.L] = carry_i;
+    w.counters[0] = 0;
+    w.counters[1] = carry_i;
+    w.counters[3] = carry_e;
+  }
+}
+
+__global__ void worklist_scatter_kernel(DevIndex ix, ScanWork w, int only_ovf) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)w.nq * w.P;
+  if (i >= total) return;
+  const uint32_t q = (uint32_t)(i / w.P), r = (uint32_t)(i % w.P);
+  const int leaf = w.leaves[i];
+  if (leaf < 0) return;
+  if ((int)r < w.pilot_end[q] || (only_ovf && !w.ovf[q])) return;
+  const uint32_t pos = w.leaf_eoff[leaf] + atomicAdd(&w.leaf_cur[leaf], 1u);
+  w.entry_q[pos] = q;
+  w.entry_bias[pos] = w.bias[i];
+}
+
+void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, cudaStream_t s,
+                     int* launches) {
+  cudaMemsetAsync(w.leaf_cnt, 0, sizeof(uint32_t) * (ix.L + 1), s);
+  const size_t total = (size_t)w.nq * w.P;
+  const int blocks = (int)((total + 255) / 256);
+  worklist_count_kernel<<<blocks, 256, 0, s>>>(ix, w, only_overflowed ? 1 : 0, only_overflowed ? 0 : 1);
+  worklist_scan_kernel<<<1, 1024, 0, s>>>(ix, w);
+  worklist_scatter_kernel<<<blocks, 256, 0, s>>>(ix, w, only_overflowed ? 1 : 0);
+  if (launches) *launches += 3;
+}
+
+// ---------------------------------------------------------------------------------------
+// Main scan: persistent CTAs pull (leaf tile, query chunk) items from an atomic counter.
+// ---------------------------------------------------------------------------------------
+template <int W>
+__global__ void __launch_bounds__(kScanThreads)
+scan_main_kernel(DevIndex ix, ScanWork w) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint2* tables = reinterpret_cast<uint2*>(smem);  // [quads_per_item][W*128]
+  __shared__ uint32_t s_q[kMaxQPI];
+  __shared__ int s_thr[kMaxQPI];
+  __shared__ uint64_t s_tau[kMaxQPI];
+  __shared__ float s_inv[kMaxQPI], s_bias[kMaxQPI];
+  __shared__ uint32_t s_item, s_leaf;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nlast = (int)ix.B - 8 * (W - 1);
+  const int off128 = 128 * (int)ix.B;
+  const uint32_t n_items = w.counters[1];
+  const uint32_t qpi = w.quads_per_item * kQueriesPerQuad;
+  constexpr int kTblEntries = W * 128;
+  for (;;) {
+    __syncthreads();  // previous item's tables are no longer read
+    if (tid == 0) {
+      const uint32_t item = atomicAdd(&w.counters[0], 1u);
+      s_item = item;
+      if (item < n_items) {  // leaf = upper_bound(item_off, item) - 1
+        uint32_t lo = 0, hi = ix.L;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (w.item_off[mid + 1] <= item) lo = mid + 1; else hi = mid;
+        }
+        s_leaf = lo;
+      }
+    }
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item >= n_items) break;
+    const uint32_t leaf = s_leaf;
+    const uint32_t local = item - w.item_off[leaf];
+    const uint32_t ntiles = ix.leaf_ntiles[leaf];
+    const uint32_t chunk = local / ntiles, tile = local - chunk * ntiles;
+    const uint32_t gpt = ix.leaf_gpt[leaf];
+    const uint32_t gbeg = ix.leaf_goff[leaf], ng = ix.leaf_goff[leaf + 1] - gbeg;
+    const uint32_t g0 = tile * gpt, g1 = min(g0 + gpt, ng);
+    const uint32_t nleaf = ix.leaf_size[leaf];
+    const uint32_t ebase = w.leaf_eoff[leaf] + chunk * qpi;
+    const uint32_t ecount = min(qpi, w.leaf_eoff[leaf + 1] - ebase);
+    const uint32_t nquads = (ecount + 3) >> 2;
+    if (tid < (int)qpi) {
+      uint32_t qq = kInvalidQuery;
+      int thr = -1;
+      if ((uint32_t)tid < ecount) {
+        qq = w.entry_q[ebase + tid];
+        const float bias = w.entry_bias[ebase + tid];
+        const uint64_t tau = w.tau[qq];
+        const float inv = w.inv_mult[qq];
+        thr = acc_threshold(tau, w.mult[qq], inv, bias) + off128;
+        if (thr < -1) thr = -1;
+        s_tau[tid] = tau; s_inv[tid] = inv; s_bias[tid] = bias;
+      }
+      s_q[tid] = qq;
+      s_thr[tid] = thr;
+    }
+    __syncthreads();
+    for (uint32_t qd = 0; qd < nquads; ++qd) {
+      const uint8_t* lp[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t qq = s_q[qd * 4 + i];
+        lp[i] = (qq == kInvalidQuery) ? nullptr : w.lut + (size_t)qq * kTblEntries;
+      }
+      build_quad_table(tables + (size_t)qd * kTblEntries, lp[0], lp[1], lp[2], lp[3], kTblEntries, tid,
+                       kScanThreads);
+    }
+    __syncthreads();
+    for (uint32_t g = g0 + warp; g < g1; g += kScanWarps) {
+      uint32_t cw[W];
+      load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
+      const bool valid = g * 32 + lane < nleaf;
+      const uint32_t gslot = (gbeg + g) * 32 + lane;
+      for (uint32_t qd = 0; qd < nquads; ++qd) {
+        uint32_t a01, a23;
+        score_quad<W>(cw, reinterpret_cast<const unsigned char*>(tables + (size_t)qd * kTblEntries),
+                      nlast, a01, a23);
+        const int sv[4] = {(int)(a01 & 0xFFFFu), (int)(a01 >> 16), (int)(a23 & 0xFFFFu), (int)(a23 >> 16)};
+        bool pv[4];
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          pv[i] = valid && sv[i] <= s_thr[qd * 4 + i];
+          any |= pv[i];
+        }
+        if (__any_sync(kFull, any)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int qi = qd * 4 + i;
+            bool p = pv[i];
+            uint64_t key = 0;
+            if (p) {
+              key = make_key(ah_float_score(sv[i] - off128, s_inv[qi], s_bias[qi]), gslot);
+              p = key < s_tau[qi];
+            }
+            const uint32_t m = __ballot_sync(kFull, p);
+            if (m) {
+              const uint32_t qq = s_q[qi];
+              const int leader = __ffs(m) - 1;
+              uint32_t base = 0;
+              if (lane == leader) base = atomicAdd(&w.cnt[qq], (uint32_t)__popc(m));
+              base = __shfl_sync(kFull, base, leader);
+              if (p) {
+                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+                if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = key;
+                else w.ovf[qq] = 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Compact: sort one query's buffer, drop duplicate keys (re-scan mode), keep the N smallest,
+// publish the new tau.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kScanThreads)
+compact_kernel(ScanWork w, int dedup) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* s = reinterpret_cast<uint64_t*>(smem);
+  __shared__ uint32_t s_dups;
+  const int tid = threadIdx.x;
+  const uint32_t q = blockIdx.x;
+  const uint32_t nraw = w.cnt[q];
+  const uint32_t n = min(nraw, w.cap);
+  const bool over = nraw > w.cap;
+  if (n == 0) {
+    if (tid == 0) w.ovf[q] = 0;
+    return;
+  }
+  int np2 = 2;
+  while ((uint32_t)np2 < n) np2 <<= 1;
+  for (int i = tid; i < np2; i += kScanThreads) s[i] = (uint32_t)i < n ? w.buf[(size_t)q * w.cap + i] : kKeyMax;
+  if (tid == 0) s_dups = 0;
+  __syncthreads();
+  block_bitonic_sort(s, np2);
+  uint32_t nuniq = n;
+  if (dedup) {
+    // keys are unique per (leaf, slot); equal neighbours are re-pushes of the same candidate
+    uint32_t mine = 0;
+    for (int i0 = 0; i0 < np2; i0 += kScanThreads) {
+      const int i = i0 + tid;
+      const bool dup = i > 0 && (uint32_t)i < n && s[i] == s[i - 1];
+      __syncthreads();
+      if (dup) { s[i] = kKeyMax; ++mine; }
+      __syncthreads();
+    }
+    if (mine) atomicAdd(&s_dups, mine);
+    __syncthreads();
+    nuniq = n - s_dups;
+    if (s_dups) block_bitonic_sort(s, np2);
+  }
+  const uint32_t keep = min(nuniq, w.nover);
+  for (uint32_t i = tid; i < keep; i += kScanThreads) w.buf[(size_t)q * w.cap + i] = s[i];
+  if (tid == 0) {
+    w.cnt[q] = keep;
+    w.tau[q] = (keep >= w.nover) ? s[w.nover - 1] : kKeyMax;
+    w.ovf[q] = over ? 1u : 0u;
+    if (over) atomicAdd(&w.counters[2], 1u);
+  }
+}
+
+// ---- debug: int16 scores of one leaf under one uint8 LUT ---------------------------------
+template <int W>
+__global__ void __launch_bounds__(kScanThreads)
+leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, int16_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint2* tbl = reinterpret_cast<uint2*>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  build_quad_table(tbl, lut, nullptr, nullptr, nullptr, W * 128, tid, kScanThreads);
+  __syncthreads();
+  const int nlast = (int)ix.B - 8 * (W - 1);
+  const uint32_t gbeg = ix.leaf_goff[leaf], ng = ix.leaf_goff[leaf + 1] - gbeg;
+  const uint32_t n = ix.leaf_size[leaf];
+  for (uint32_t g = blockIdx.x * kScanWarps + warp; g < ng; g += gridDim.x * kScanWarps) {
+    uint32_t cw[W];
+    load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
+    uint32_t a01, a23;
+    score_quad<W>(cw, reinterpret_cast<const unsigned char*>(tbl), nlast, a01, a23);
+    const uint32_t slot = g * 32 + lane;
+    if (slot < n) out[slot] = (int16_t)((int)(a01 & 0xFFFFu) - 128 * (int)ix.B);
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------
+#define SB_DISPATCH_W(Wv, ...)                                                         \
+  switch (Wv) {                                                                          \
+    case 1: { constexpr int W = 1; __VA_ARGS__; } break;   case 2: { constexpr int W = 2; __VA_ARGS__; } break;   \
+    case 3: { constexpr int W = 3; __VA_ARGS__; } break;   case 4: { constexpr int W = 4; __VA_ARGS__; } break;   \
+    case 5: { constexpr int W = 5; __VA_ARGS__; } break;   case 6: { constexpr int W = 6; __VA_ARGS__; } break;   \
+    case 7: { constexpr int W = 7; __VA_ARGS__; } break;   case 8: { constexpr int W = 8; __VA_ARGS__; } break;   \
+    case 9: { constexpr int W = 9; __VA_ARGS__; } break;   case 10: { constexpr int W = 10; __VA_ARGS__; } break; \
+    case 11: { constexpr int W = 11; __VA_ARGS__; } break; case 12: { constexpr int W = 12; __VA_ARGS__; } break; \
+    case 13: { constexpr int W = 13; __VA_ARGS__; } break; case 14: { constexpr int W = 14; __VA_ARGS__; } break; \
+    case 15: { constexpr int W = 15; __VA_ARGS__; } break; case 16: { constexpr int W = 16; __VA_ARGS__; } break; \
+    default: return cudaErrorInvalidValue;                                               \
+  }
+
+static int pilot_capl(uint32_t nover) {
+  int capl = 256;
+  while ((uint32_t)capl < nover + kScanThreads) capl <<= 1;
+  return capl;
+}
+size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover) {
+  return (size_t)ix.W * 128 * 8 + (size_t)pilot_capl(nover) * 8;
+}
+size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item) {
+  return (size_t)quads_per_item * ix.W * 128 * 8;
+}
+
+cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) {
+  const int capl = pilot_capl(w.nover);
+  const size_t smem = pilot_smem_bytes(ix, w.nover);
+  SB_DISPATCH_W(ix.W, {
+    cudaError_t e = cudaFuncSetAttribute(pilot_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pilot_kernel<W><<<w.nq, kScanThreads, smem, s>>>(ix, w, capl);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s) {
+  const size_t smem = scan_smem_bytes(ix, w.quads_per_item);
+  SB_DISPATCH_W(ix.W, {
+    cudaError_t e = cudaFuncSetAttribute(scan_main_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (grid <= 0) {  // persistent: exactly as many CTAs as can be resident
+      int dev = 0, sms = 148, per_sm = 1;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_main_kernel<W>, kScanThreads, smem);
+      if (e != cudaSuccess) return e;
+      grid = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    scan_main_kernel<W><<<grid, kScanThreads, smem, s>>>(ix, w);
+  });
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s) {
+  (void)ix;
+  int np2 = 2;
+  while ((uint32_t)np2 < w.cap) np2 <<= 1;
+  const size_t smem = (size_t)np2 * 8;
+  cudaError_t e = cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  compact_kernel<<<w.nq, kScanThreads, smem, s>>>(w, dedup ? 1 : 0);
+  return cudaGetLastError();
+}
+
+void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s) {
+  const size_t smem = (size_t)ix.W * 128 * 8;
+  auto run = [&]() -> cudaError_t {
+    SB_DISPATCH_W(ix.W, {
+      cudaFuncSetAttribute(leaf_scores_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      leaf_scores_kernel<W><<<8, kScanThreads, smem, s>>>(ix, lut, leaf, out);
+    });
+    return cudaSuccess;
+  };
+  run();
+}
+
+}  // namespace sb

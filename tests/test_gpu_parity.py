@@ -1,0 +1,108 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+from conftest import get_case
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    dict(),                                         # C1-like: D=100, dpb=2 -> B=50 (W=7, partial word)
+    dict(dpb=3, d=100),                             # VARIABLE_CHUNK: B=34, last block 1 dim
+    dict(dpb=1, d=40, leaves=50, n=8000),           # B=40
+    dict(dpb=4, d=96, leaves=64, n=12000),          # B=24 (W=3), Highway 4-lane LUT path
+    dict(dpb=8, d=128, leaves=32, n=6000),          # B=16, AVX2-order LUT path
+    dict(soar=1.5),                                 # SOAR spilled leaves + dedup
+    dict(n=3000, leaves=300, probe=40, pre=150),    # tiny / empty leaves, pilot spans many leaves
+]
+
+
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_tokenize_bit_exact(kw):
+  c = get_case(**kw)
+  l0, d0 = c.oracle.tokenize(c.q)
+  l1, d1 = c.native.tokenize(c.q)
+  np.testing.assert_array_equal(l0, l1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_lut_bit_exact(kw):
+  c = get_case(**kw)
+  t0, m0 = c.oracle.lut(c.q)
+  t1, m1 = c.native.lut(c.q)
+  np.testing.assert_array_equal(m0.view(np.uint32), m1.view(np.uint32))
+  np.testing.assert_array_equal(t0, t1)
+
+
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_lut16_int16_scores_bit_exact(kw):
+  c = get_case(**kw)
+  luts, _ = c.oracle.lut(c.q[:3])
+  L = c.arrays.centers.shape[0]
+  for qi in range(3):
+    for leaf in list(range(0, L, max(1, L // 7))) + [L - 1]:
+      assert c.native.leaf_size(leaf) == c.oracle.leaf_size(leaf)
+      s0 = c.oracle.leaf_scores(luts[qi], leaf)
+      s1 = c.native.leaf_scores(luts[qi], leaf)
+      np.testing.assert_array_equal(s0, s1)
+
+
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_pre_reorder_candidates_bit_exact(kw):
+  c = get_case(**kw)
+  a = c.oracle.candidates(c.q)
+  b = c.native.candidates(c.q)
+  np.testing.assert_array_equal(a["count"], b["count"])
+  for i in range(len(c.q)):
+    n = a["count"][i]
+    np.testing.assert_array_equal(a["leaf"][i, :n], b["leaf"][i, :n])
+    np.testing.assert_array_equal(a["slot"][i, :n], b["slot"][i, :n])
+    np.testing.assert_array_equal(a["dp"][i, :n], b["dp"][i, :n])
+    np.testing.assert_array_equal(a["score"][i, :n].view(np.uint32), b["score"][i, :n].view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_search_batched_ids_and_distances(kw):
+  c = get_case(**kw)
+  i0, d0 = c.oracle.search_batched(c.q)
+  i1, d1 = c.native.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  # float distances within 1e-5 relative of a float64 recomputation (north star tolerance)
+  truth = np.einsum("qd,qkd->qk", c.q.astype(np.float64), c.db[i1.astype(np.int64)].astype(np.float64))
+  np.testing.assert_allclose(d1, truth, rtol=1e-5, atol=1e-5)
+
+
+def test_parameter_overrides_and_padding():
+  c = get_case()
+  i0, d0 = c.oracle.search_batched(c.q, final_nn=20, pre_nn=50, leaves=3)
+  i1, d1 = c.native.search_batched(c.q, final_nn=20, pre_nn=50, leaves=3)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  # more neighbours requested than candidates exist -> (0, NaN) padding (scann.h:175-178)
+  i2, d2 = c.native.search_batched(c.q[:4], final_nn=30, pre_nn=8, leaves=1)
+  assert np.isnan(d2[:, 8:]).all() and (i2[:, 8:] == 0).all()
+  i3, d3 = c.oracle.search_batched(c.q[:4], final_nn=30, pre_nn=8, leaves=1)
+  np.testing.assert_array_equal(i2, i3)
+
+
+def test_large_batch_matches_small_batches():
+  c = get_case(nq=700)
+  i_all, d_all = c.native.search_batched(c.q)
+  for s in (0, 333):
+    i_p, d_p = c.native.search_batched(c.q[s:s + 100])
+    np.testing.assert_array_equal(i_all[s:s + 100], i_p)
+    np.testing.assert_array_equal(d_all[s:s + 100].view(np.uint32), d_p.view(np.uint32))
+  i0, d0 = c.oracle.search_batched(c.q, impl=1)
+  np.testing.assert_array_equal(i0, i_all)
+
+
+def test_stats_scan_bytes_match_oracle():
+  c = get_case()
+  c.native.search_batched(c.q)
+  st = c.native.stats()
+  c.oracle.search_batched(c.q)
+  assert st["scan_bytes_alg"] == c.oracle.last_scan_bytes()
+  assert st["scan_pairs"] == len(c.q) * c.probe
+  assert st["kernel_launches"] >= 8
