@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- batched QPS of the B200 tree-AH query path on the glove-100-angular shape.
+
+Contract (task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line on rank 0.  A "step" is one `search_batched` pass of the hot path over one batch of
+10,000 synthetic queries.
+
+  value        whole-job QPS with queries and outputs resident in HBM, timed with CUDA events
+               recorded on the library's own stream (scann_b200_last_stats.ms_total), summed
+               over the K steps, max over ranks.
+  e2e          the same metric through scann_b200_search_batched (HOST buffers: pinned staging,
+               H2D of the queries and D2H of ids/distances inside the timed region), wall clock.
+  roofline     LUT16 scan kernel: algorithmic bytes (sum over probed (query, leaf) of
+               ceil(n/32)*16*B) / its CUDA-event duration, against the measured
+               HBM copy bandwidth of MEASURED_PEAKS.json.
+  cpu_baseline the CPU oracle's AVX2 restatement of the reference path on this box's cores.
+
+`--impl reference` times that CPU implementation (oracle/, AVX2 vpshufb LUT16 kernel, all host
+threads, search_batched_parallel semantics) on the same workload; the reference binary itself
+cannot be built in this image.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n, d, leaves, probe, dims_per_block, reorder, k, nq, generator)
+    "c2_glove_shape": dict(n=1_183_514, d=100, leaves=2000, probe=100, dpb=2, pre=100, k=10, nq=10000,
+                           clusters=8000, normalize=True, seed=3, train_sample=250000),
+    "c1_synthetic": dict(n=100_000, d=100, leaves=100, probe=10, dpb=2, pre=100, k=10, nq=10000,
+                         clusters=400, normalize=False, seed=1, train_sample=100000),
+}
+
+
+def log(*a):
+  print(*a, file=sys.stderr, flush=True)
+
+
+def make_data(wl):
+  from scann_b200 import datasets
+  db = datasets.clustered(wl["n"], wl["d"], wl["clusters"], seed=wl["seed"], centers_seed=100 + wl["seed"],
+                          normalize=wl["normalize"])
+  q = datasets.clustered(wl["nq"], wl["d"], wl["clusters"], seed=wl["seed"] + 1, centers_seed=100 + wl["seed"],
+                         normalize=wl["normalize"])
+  return db, q
+
+
+def build_arrays(wl, db, device):
+  from scann_b200 import index_build
+  return index_build.build_tree_ah(db, "dot_product", num_leaves=wl["leaves"], dims_per_block=wl["dpb"],
+                                   training_sample_size=wl["train_sample"], tree_iters=12, ah_iters=10,
+                                   seed=0, device=device)
+
+
+class ClockSampler(threading.Thread):
+  """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+  FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+            "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, gpu_index):
+    super().__init__(daemon=True)
+    self.gpu_index = gpu_index
+    self.samples = []
+    self.stop_flag = threading.Event()
+
+  def run(self):
+    while not self.stop_flag.is_set():
+      try:
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                              "-i", str(self.gpu_index)], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 7:
+          self.samples.append(parts)
+      except Exception:
+        pass
+      self.stop_flag.wait(0.2)
+
+  def summary(self):
+    if not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+    sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+    mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": reasons, "samples": len(self.samples)}
+
+
+def measured_peak():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    try:
+      return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+      pass
+  return 6650.0, "fallback"
+
+
+def recall_at_k(found, truth):
+  k = truth.shape[1]
+  hit = 0
+  for i in range(found.shape[0]):
+    hit += len(set(found[i, :k].tolist()) & set(truth[i].tolist()))
+  return hit / (found.shape[0] * k)
+
+
+def cpu_reference_run(oracle_index, q, sample, threads, steps, warmup):
+  """Times the oracle's AVX2 path on a bounded sample; returns QPS."""
+  qs = np.ascontiguousarray(q[:sample])
+  for _ in range(warmup):
+    oracle_index.search_batched(qs[:min(sample, 256)], impl=1, threads=threads, batch=256)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    oracle_index.search_batched(qs, impl=1, threads=threads, batch=256)
+  dt = time.perf_counter() - t0
+  return sample * steps / dt, dt / steps
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--workload", default="c2_glove_shape", choices=list(WORKLOADS))
+  ap.add_argument("--leaves", type=int, default=0, help="override leaves_to_search")
+  ap.add_argument("--cpu-sample", type=int, default=2000)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  wl = dict(WORKLOADS[args.workload])
+  if args.leaves > 0:
+    wl["probe"] = args.leaves
+
+  import torch
+  if args.impl == "reference":
+    if rank != 0:
+      return 0
+    return run_reference(args, wl)
+
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+
+  from scann_b200 import _lib
+  t0 = time.time()
+  db, q = make_data(wl)
+  log(f"[rank {rank}] data {db.shape} in {time.time() - t0:.1f}s")
+  t0 = time.time()
+  shm = f"/dev/shm/scann_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{args.workload}.npz"
+  if world > 1:
+    from scann_b200 import index_build
+    if rank == 0:
+      arrays = build_arrays(wl, db, dev)
+      np.savez(shm, centers=arrays.centers, tokens=arrays.tokens, codes=arrays.codes, codebook=arrays.codebook,
+               block_dims=arrays.block_dims)
+    dist.barrier()
+    if rank != 0:
+      z = np.load(shm)
+      arrays = index_build.IndexArrays(distance="dot_product", dataset=db, n=db.shape[0], d=db.shape[1])
+      arrays.centers, arrays.tokens, arrays.codes = z["centers"], z["tokens"], z["codes"]
+      arrays.codebook, arrays.block_dims, arrays.residual = z["codebook"], z["block_dims"], True
+    dist.barrier()
+    if rank == 0:
+      os.unlink(shm)
+  else:
+    arrays = build_arrays(wl, db, dev)
+  log(f"[rank {rank}] index built in {time.time() - t0:.1f}s")
+  t0 = time.time()
+  ix = _lib.NativeIndex(arrays, wl["probe"], wl["pre"], wl["k"], device=local_rank, shard_rank=rank,
+                        shard_world=world)
+  log(f"[rank {rank}] device index in {time.time() - t0:.1f}s")
+
+  nq, k = wl["nq"], wl["k"]
+  d_q = torch.from_numpy(q).to(dev)
+  d_idx = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+  d_dist = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+  torch.cuda.synchronize()
+
+  # ground truth for recall (exact f32 brute force on the GPU)
+  d_db = torch.from_numpy(db).to(dev)
+  truth = torch.empty((nq, k), dtype=torch.int64, device=dev)
+  for s in range(0, nq, 1000):
+    truth[s:s + 1000] = torch.topk(d_q[s:s + 1000] @ d_db.T, k, dim=1).indices
+  truth = truth.cpu().numpy()
+  del d_db
+  torch.cuda.empty_cache()
+
+  if world > 1:
+    step_dev, step_host = make_sharded_steps(ix, wl, q, d_q, d_idx, d_dist, dist, world, dev)
+  else:
+    def step_dev():
+      ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)
+      return ix.stats()
+
+    def step_host():
+      return ix.search_batched(q)
+
+  for _ in range(args.warmup):
+    step_dev()
+  found = d_idx.cpu().numpy().view(np.uint32)
+  rec = recall_at_k(found, truth)
+
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  if dist is not None:
+    dist.barrier()
+  torch.cuda.synchronize()
+  ms_total = 0.0
+  agg = {}
+  wall0 = time.perf_counter()
+  for _ in range(args.steps):
+    flush.zero_()  # L2 flush between timed iterations (not inside the CUDA-event interval)
+    torch.cuda.synchronize()
+    st = step_dev()
+    ms_total += st["ms_total"]
+    for key, val in st.items():
+      agg[key] = agg.get(key, 0) + val
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  wall = time.perf_counter() - wall0
+
+  # end to end through the host-buffer C ABI call
+  step_host()
+  torch.cuda.synchronize()
+  if dist is not None:
+    dist.barrier()
+  e0 = time.perf_counter()
+  e2e_steps = max(3, min(args.steps, 10))
+  for _ in range(e2e_steps):
+    idx_h, dist_h = step_host()
+  if dist is not None:
+    dist.barrier()
+  e2e_s = (time.perf_counter() - e0)
+  sampler.stop_flag.set()
+  sampler.join(timeout=2)
+
+  if dist is not None:
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+  if rank != 0:
+    if dist is not None:
+      dist.destroy_process_group()
+    return 0
+
+  value = nq * args.steps / (ms_total / 1e3)
+  e2e_value = nq * e2e_steps / e2e_s
+  peak, peak_src = measured_peak()
+  scan_launches = max(1, agg.get("scan_kernel_count", 1))
+  bytes_per_launch = agg["scan_bytes_alg"] / scan_launches
+  ms_per_launch = agg["ms_scan"] / scan_launches
+  achieved = bytes_per_launch / (ms_per_launch * 1e-3) / 1e9 if ms_per_launch > 0 else 0.0
+  out = {
+      "metric": "batched QPS at recall@10>=0.90 (tree-AH search_batched)", "value": value, "unit": "queries/s",
+      "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+      "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+      "dtype": "u8 LUT / int16 accumulate (scan), f32 (tokenize, reorder)", "data": "synthetic",
+      "config": {"workload": args.workload, "n": wl["n"], "d": wl["d"], "leaves": wl["leaves"],
+                 "leaves_to_search": wl["probe"], "ah_blocks": wl["d"] // wl["dpb"], "reorder": wl["pre"],
+                 "k": k, "queries_per_step": nq, "recall_at_10": rec,
+                 "l2_flush": "256 MiB write between timed steps", "parallelism": f"db-shard x{world}",
+                 "wall_s_timed_region": wall},
+      "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(q.nbytes),
+              "d2h_bytes_per_step": int(nq * k * 8), "steps": e2e_steps},
+      "gpu_launches": int(agg.get("kernel_launches", 0)),
+      "clocks": sampler.summary(),
+      "roofline": {"bound": "hbm", "kernel": "scan_main_kernel<W>", "achieved": achieved, "peak": peak,
+                   "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
+                   "traffic": None, "alg_bytes_per_launch": bytes_per_launch, "ms_per_launch": ms_per_launch,
+                   "lookups_per_s": 2 * bytes_per_launch / (ms_per_launch * 1e-3) if ms_per_launch else None},
+      "stage_ms_per_step": {s: agg[s] / args.steps for s in agg if s.startswith("ms_")},
+      "overflow_retries": int(agg.get("overflow_retries", 0)),
+  }
+  if not args.no_cpu_baseline and world == 1:
+    import oracle
+    threads = os.cpu_count() or 1
+    oi = oracle.OracleIndex(arrays, wl["probe"], wl["pre"], wl["k"])
+    i_cpu, _ = oi.search_batched(q[:64], impl=1)
+    parity = bool(np.array_equal(i_cpu, idx_h[:64]))
+    qps, _ = cpu_reference_run(oi, q, min(args.cpu_sample, nq), threads, 1, 1)
+    qps1, _ = cpu_reference_run(oi, q, min(500, nq), 1, 1, 0)
+    out["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                           "sample": f"first {min(args.cpu_sample, nq)} queries of the step, batches of 256 "
+                                     f"(search_batched_parallel semantics), AVX2 vpshufb oracle",
+                           "single_thread_qps": qps1, "ids_equal_gpu_first_64": parity}
+  print(json.dumps(out), flush=True)
+  if dist is not None:
+    dist.destroy_process_group()
+  return 0
+
+
+def make_sharded_steps(ix, wl, q, d_q, d_idx, d_dist, dist, world, dev):
+  """Sharded search: local candidates -> one NCCL all-gather -> merge."""
+  import ctypes as C
+  import torch
+  from scann_b200 import _lib
+  nq, k, ncand = wl["nq"], wl["k"], wl["pre"]
+  L = _lib.lib()
+  ids = torch.empty((nq, ncand), dtype=torch.int32, device=dev)
+  tie = torch.empty((nq, ncand), dtype=torch.int64, device=dev)
+  ah = torch.empty((nq, ncand), dtype=torch.float32, device=dev)
+  ex = torch.empty((nq, ncand), dtype=torch.float32, device=dev)
+  g_ids = torch.empty((world, nq, ncand), dtype=torch.int32, device=dev)
+  g_tie = torch.empty((world, nq, ncand), dtype=torch.int64, device=dev)
+  g_ah = torch.empty((world, nq, ncand), dtype=torch.float32, device=dev)
+  g_ex = torch.empty((world, nq, ncand), dtype=torch.float32, device=dev)
+  vp = C.c_void_p
+
+  def run(dq_ptr):
+    _lib.check(L.scann_b200_search_partial_device(ix._h, vp(dq_ptr), nq, -1, -1, vp(ids.data_ptr()),
+                                                  vp(tie.data_ptr()), vp(ah.data_ptr()), vp(ex.data_ptr()), ncand))
+    st = ix.stats()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    dist.all_gather_into_tensor(g_ids, ids)
+    dist.all_gather_into_tensor(g_tie, tie)
+    dist.all_gather_into_tensor(g_ah, ah)
+    dist.all_gather_into_tensor(g_ex, ex)
+    t1.record()
+    torch.cuda.synchronize()
+    _lib.check(L.scann_b200_merge_partials_device(ix._h, nq, world, ncand, vp(g_ids.data_ptr()), vp(g_tie.data_ptr()),
+                                                  vp(g_ah.data_ptr()), vp(g_ex.data_ptr()), -1, -1,
+                                                  vp(d_idx.data_ptr()), vp(d_dist.data_ptr()), k))
+    st["ms_allgather"] = t0.elapsed_time(t1)
+    st["ms_total"] = st["ms_total"] + st["ms_allgather"]
+    return st
+
+  def step_dev():
+    return run(d_q.data_ptr())
+
+  hq = torch.from_numpy(q).pin_memory()
+
+  def step_host():
+    dq = hq.to(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    run(dq.data_ptr())
+    return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy()
+
+  return step_dev, step_host
+
+
+def run_reference(args, wl):
+  """CPU arm: the oracle's AVX2 restatement of the reference path, all host threads."""
+  import oracle
+  t0 = time.time()
+  db, q = make_data(wl)
+  import torch
+  arrays = build_arrays(wl, db, "cuda:0" if torch.cuda.is_available() else "cpu")
+  log(f"[reference] data+index in {time.time() - t0:.1f}s")
+  threads = os.cpu_count() or 1
+  oi = oracle.OracleIndex(arrays, wl["probe"], wl["pre"], wl["k"])
+  sample = min(args.cpu_sample, wl["nq"])
+  steps, warmup = max(1, args.steps), max(0, args.warmup)
+  # keep the whole run within a few minutes: probe the speed first
+  qps_probe, _ = cpu_reference_run(oi, q, min(256, sample), threads, 1, 0)
+  budget_s = 120.0
+  max_steps = max(1, int(budget_s * qps_probe / sample))
+  steps_run = min(steps, max_steps)
+  qps, s_per_step = cpu_reference_run(oi, q, sample, threads, steps_run, min(warmup, 1))
+  out = {
+      "impl": "reference", "metric": "batched QPS at recall@10>=0.90 (tree-AH search_batched)", "value": qps,
+      "unit": "queries/s", "n_gpus": args.gpus, "steps": steps_run, "warmup": min(warmup, 1),
+      "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+      "dtype": "u8 LUT / int16 accumulate (AVX2)", "data": "synthetic",
+      "config": {"workload": args.workload, "n": wl["n"], "d": wl["d"], "leaves": wl["leaves"],
+                 "leaves_to_search": wl["probe"], "reorder": wl["pre"], "k": wl["k"],
+                 "queries_per_step": sample},
+      "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                       "sample": f"{sample} queries per step, batches of 256 over {threads} threads"},
+      "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(out), flush=True)
+  return 0
+
+
+if __name__ == "__main__":
+  sys.exit(main())
