@@ -139,6 +139,8 @@ typedef struct {
   uint32_t overflow_retries; /* candidate-buffer overflow re-scans (0 in the common case) */
   float ms_tokenize, ms_lut, ms_pilot, ms_worklist, ms_scan, ms_compact, ms_finalize, ms_total;
   uint32_t scan_kernel_count; /* launches of the dominant LUT16 scan kernel in the last call */
+  uint64_t cand_sum;          /* candidates buffered per query after the main scan, summed */
+  uint64_t cand_max;          /* ... and the maximum over queries */
 } scann_b200_stats;
 /* Timing (CUDA events on the index's stream) and traffic figures of the last search call. */
 int scann_b200_last_stats(scann_b200_index* index, scann_b200_stats* out);

@@ -35,6 +35,7 @@ class Stats(C.Structure):
       ("ms_tokenize", C.c_float), ("ms_lut", C.c_float), ("ms_pilot", C.c_float),
       ("ms_worklist", C.c_float), ("ms_scan", C.c_float), ("ms_compact", C.c_float),
       ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("scan_kernel_count", C.c_uint32),
+      ("cand_sum", C.c_uint64), ("cand_max", C.c_uint64),
   ]
 
   def as_dict(self):

@@ -270,7 +270,7 @@ int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Pa
 }
 
 uint32_t pick_cap(uint32_t nover) {
-  uint32_t cap = 2048;
+  uint32_t cap = 4096;
   while (cap < 4 * nover) cap <<= 1;
   return cap;
 }
@@ -382,6 +382,8 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   st.scan_bytes_alg += hs[0];
   st.scan_pairs += hs[1];
   st.scan_lookups += hs[0] * 2;
+  st.cand_sum += hs[2];
+  st.cand_max = std::max<uint64_t>(st.cand_max, hs[3]);
   st.kernel_launches += (uint32_t)launches;
   st.overflow_retries += retries;
   st.scan_kernel_count += scan_launches;

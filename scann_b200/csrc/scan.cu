@@ -442,7 +442,11 @@ compact_kernel(ScanWork w, int dedup) {
   const uint32_t nraw = w.cnt[q];
   const uint32_t n = min(nraw, w.cap);
   const bool over = nraw > w.cap;
-  if (n == 0) {
+  if (tid == 0 && !dedup) {  // candidate-inflow statistics of the main pass
+    atomicAdd(&w.stats[2], (unsigned long long)nraw);
+    atomicMax(&w.stats[3], (unsigned long long)nraw);
+  }
+  if (n == 0 || (dedup && w.ovf[q] == 0)) {  // re-scan passes only touch flagged queries
     if (tid == 0) w.ovf[q] = 0;
     return;
   }
