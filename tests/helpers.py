@@ -1,0 +1,123 @@
+"""Shared helpers: golden fixture loading and an independent numpy restatement of the path."""
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+  return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+  from scann_b200 import index_build
+  z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+  a = index_build.IndexArrays(distance="dot_product", dataset=z["dataset"], n=z["dataset"].shape[0],
+                              d=z["dataset"].shape[1])
+  a.centers, a.tokens, a.codes = z["centers"], z["tokens"], z["codes"]
+  a.codebook, a.block_dims = z["codebook"], z["block_dims"]
+  a.soar = bool(int(z["soar"]))
+  a.soar_codes = z["soar_codes"] if a.soar else None
+  a.overretrieve = float(z["overretrieve"])
+  a.residual = True
+  return a, z
+
+
+def f32(x):
+  return np.asarray(x, dtype=np.float32)
+
+
+def fma32(a, b, c):
+  """float32 fused multiply-add emulated in float64 (product of two f32 is exact in f64)."""
+  return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(np.float32)
+
+
+def np_center_distances(q, centers):
+  """many_to_many_impl.inc:551-563: acc = fnmadd(q[d], c[d], acc), sequential in d."""
+  acc = np.zeros((q.shape[0], centers.shape[0]), np.float32)
+  for d in range(q.shape[1]):
+    acc = fma32(-q[:, d:d + 1], centers[None, :, d], acc)
+  return acc
+
+
+def np_lut_dpb2(q, codebook):
+  """asymmetric_hashing_impl.cc:505-645 for dims_per_block == 2 (two products, one add, no FMA)."""
+  nq, B = q.shape[0], codebook.shape[0]
+  qb = q.reshape(nq, B, 1, 2)
+  p0 = f32(qb[..., 0] * codebook[None, :, :, 0])
+  p1 = f32(qb[..., 1] * codebook[None, :, :, 1])
+  raw = f32(f32(-p0) - p1)                                   # [nq, B, 16]
+  mx = np.abs(raw).reshape(nq, -1).max(1)
+  denom = np.maximum(mx, np.sqrt(np.float32(np.finfo(np.float32).eps))).astype(np.float32)
+  mult = (np.float32(127.0) / denom).astype(np.float32)
+  v = f32(raw * mult[:, None, None])
+  r = np.where(v >= 0, np.floor(v + np.float32(0.5)), np.ceil(v - np.float32(0.5)))  # round half away
+  # floor(v+0.5) in f32 can differ from round() only when v+0.5 rounds up to the next integer;
+  # redo those in float64, which represents v + 0.5 exactly
+  v64 = v.astype(np.float64)
+  r = np.where(v64 >= 0, np.floor(v64 + 0.5), np.ceil(v64 - 0.5))
+  return (r + 128).astype(np.uint8), mult
+
+
+def np_slots(tokens, n_leaves, soar):
+  """datapoints_by_token in file order (scann.cc:88-98)."""
+  mult = 2 if soar else 1
+  out = [[] for _ in range(n_leaves)]
+  for j, t in enumerate(tokens.tolist()):
+    if t >= 0:
+      out[t].append(j // mult)
+  return [np.asarray(x, dtype=np.int64) for x in out]
+
+
+def np_search(arrays, q, probe, pre, k):
+  """End-to-end numpy restatement (dims_per_block == 2, dot product)."""
+  a = arrays
+  L, B = a.centers.shape[0], a.codes.shape[1]
+  cd = np_center_distances(q, a.centers)
+  lut, mult = np_lut_dpb2(q, a.codebook)
+  slots = np_slots(a.tokens, L, a.soar)
+  disjoint = not a.soar
+  nover = pre if disjoint else int(float(pre) * float(np.float32(a.overretrieve)))
+  ids = np.zeros((q.shape[0], k), np.uint32)
+  dists = np.full((q.shape[0], k), np.nan, np.float32)
+  cands = []
+  for i in range(q.shape[0]):
+    order = np.lexsort((np.arange(L), cd[i]))[:probe]
+    inv = np.float32(1.0 / np.float64(mult[i]))
+    rows = []
+    for leaf in order.tolist():
+      dps = slots[leaf]
+      if len(dps) == 0:
+        continue
+      codes = a.codes[dps]
+      if a.soar:
+        sec = a.tokens[2 * dps + 1] == leaf
+        codes = np.where(sec[:, None], a.soar_codes[dps], codes)
+      acc = lut[i][np.arange(B)[None, :], codes].astype(np.int32).sum(1) - 128 * B
+      score = f32(f32(acc.astype(np.float32) * inv) + cd[i, leaf])
+      for s in range(len(dps)):
+        rows.append((float(score[s]), leaf, s, int(dps[s]), np.float32(score[s])))
+    rows.sort(key=lambda r: (r[0], r[1], r[2]))
+    rows = rows[:nover]
+    cands.append(rows)
+    best = {}
+    if disjoint:
+      best = {r[3]: r[4] for r in rows}
+    else:
+      for r in rows:
+        if r[3] in best:
+          best[r[3]] = np.float32(np.float32(0.5) * best[r[3]] + np.float32(0.5) * r[4])
+        else:
+          best[r[3]] = r[4]
+      keep = sorted(best.items(), key=lambda kv: (float(kv[1]), kv[0]))[:pre]
+      best = dict(keep)
+    ex = []
+    for dp in best:
+      ex.append((-float(np.dot(q[i].astype(np.float64), a.dataset[dp].astype(np.float64))), dp))
+    ex.sort()
+    for j, (dist, dp) in enumerate(ex[:k]):
+      ids[i, j] = dp
+      dists[i, j] = -dist
+  return ids, dists, cd, lut, mult, cands

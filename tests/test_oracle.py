@@ -1,0 +1,96 @@
+"""CPU tests: the oracle against committed golden fixtures and an independent numpy restatement."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import golden_names, load_golden, np_center_distances, np_lut_dpb2, np_search, np_slots
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_golden(name):
+  a, z = load_golden(name)
+  oi = oracle.OracleIndex(a, int(z["probe"]), int(z["pre"]), int(z["k"]))
+  q = z["queries"]
+  leaf, cdist = oi.tokenize(q)
+  np.testing.assert_array_equal(leaf, z["exp_leaf"])
+  np.testing.assert_array_equal(cdist.view(np.uint32), z["exp_center_dist"].view(np.uint32))
+  lut, mult = oi.lut(q)
+  np.testing.assert_array_equal(lut, z["exp_lut"])
+  np.testing.assert_array_equal(mult.view(np.uint32), z["exp_mult"].view(np.uint32))
+  np.testing.assert_array_equal(oi.leaf_scores(lut[0], int(leaf[0, 0])), z["exp_scores_q0_leaf0"])
+  c = oi.candidates(q)
+  np.testing.assert_array_equal(c["count"], z["exp_cand_count"])
+  np.testing.assert_array_equal(c["dp"], z["exp_cand_dp"])
+  np.testing.assert_array_equal(c["acc"], z["exp_cand_acc"])
+  for impl in (0, 1):
+    idx, dist = oi.search_batched(q, impl=impl)
+    np.testing.assert_array_equal(idx, z["exp_idx"])
+    np.testing.assert_array_equal(dist.view(np.uint32), z["exp_dist"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["dot_b16", "dot_soar_b25"])
+def test_oracle_matches_numpy_restatement(name):
+  a, z = load_golden(name)
+  probe, pre, k = int(z["probe"]), int(z["pre"]), int(z["k"])
+  oi = oracle.OracleIndex(a, probe, pre, k)
+  q = z["queries"][:12]
+  ids, dists, cd, lut, mult, cands = np_search(a, q, probe, pre, k)
+  leaf, cdist = oi.tokenize(q)
+  for i in range(len(q)):
+    np.testing.assert_array_equal(cdist[i].view(np.uint32), cd[i, leaf[i]].view(np.uint32))
+    assert sorted(leaf[i].tolist()) == sorted(np.lexsort((np.arange(cd.shape[1]), cd[i]))[:probe].tolist())
+  olut, omult = oi.lut(q)
+  np.testing.assert_array_equal(omult.view(np.uint32), mult.view(np.uint32))
+  np.testing.assert_array_equal(olut, lut)
+  c = oi.candidates(q)
+  for i in range(len(q)):
+    n = int(c["count"][i])
+    assert n == len(cands[i])
+    np.testing.assert_array_equal(c["leaf"][i, :n], [r[1] for r in cands[i]])
+    np.testing.assert_array_equal(c["slot"][i, :n], [r[2] for r in cands[i]])
+    np.testing.assert_array_equal(c["dp"][i, :n], [r[3] for r in cands[i]])
+    np.testing.assert_array_equal(c["score"][i, :n].view(np.uint32),
+                                  np.asarray([r[4] for r in cands[i]], np.float32).view(np.uint32))
+  oidx, odist = oi.search_batched(q)
+  # ids: identical except where two float32 reorder distances tie within rounding of the f64 truth
+  np.testing.assert_allclose(odist, dists, rtol=1e-5, atol=1e-5)
+  assert (oidx == ids).mean() > 0.98
+
+
+def test_leaf_membership_and_packing():
+  a, z = load_golden("dot_soar_b25")
+  oi = oracle.OracleIndex(a, int(z["probe"]), int(z["pre"]), int(z["k"]))
+  slots = np_slots(a.tokens, a.centers.shape[0], True)
+  assert not oi.disjoint
+  for leaf, dps in enumerate(slots):
+    assert oi.leaf_size(leaf) == len(dps)
+    np.testing.assert_array_equal(oi.leaf_datapoints(leaf), dps)
+
+
+def test_scalar_and_avx2_and_parallel_agree():
+  a, z = load_golden("dot_b16")
+  oi = oracle.OracleIndex(a, 6, 50, 10)
+  q = z["queries"]
+  i0, d0 = oi.search_batched(q, impl=0)
+  i1, d1 = oi.search_batched(q, impl=1)
+  i2, d2 = oi.search_batched(q, impl=1, threads=3, batch=5)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(i0, i2)
+  np.testing.assert_array_equal(d0.view(np.uint32), d2.view(np.uint32))
+
+
+def test_recall_against_brute_force():
+  a, z = load_golden("dot_b16")
+  oi = oracle.OracleIndex(a, 8, 100, 10)
+  q = z["queries"]
+  idx, _ = oi.search_batched(q)
+  truth = np.argsort(-(q.astype(np.float64) @ a.dataset.astype(np.float64).T), axis=1)[:, :10]
+  rec = np.mean([len(set(idx[i].tolist()) & set(truth[i].tolist())) / 10 for i in range(len(q))])
+  assert rec > 0.9
+
+
+def test_padding_when_fewer_candidates_than_k():
+  a, z = load_golden("dot_b16")
+  oi = oracle.OracleIndex(a, 1, 5, 10)
+  idx, dist = oi.search_batched(z["queries"][:3], final_nn=10, pre_nn=5, leaves=1)
+  assert np.isnan(dist[:, 5:]).all() and (idx[:, 5:] == 0).all() and not np.isnan(dist[:, :5]).any()
