@@ -188,8 +188,12 @@ def main():
     arrays = build_arrays(wl, db, dev)
   log(f"[rank {rank}] index built in {time.time() - t0:.1f}s")
   t0 = time.time()
-  ix = _lib.NativeIndex(arrays, wl["probe"], wl["pre"], wl["k"], device=local_rank, shard_rank=rank,
-                        shard_world=world)
+  if world > 1:
+    from scann_b200 import distributed as sdist
+    searcher = sdist.ShardedSearcher(arrays, wl["probe"], wl["pre"], wl["k"], rank, world, local_rank)
+    ix = searcher.index
+  else:
+    ix = _lib.NativeIndex(arrays, wl["probe"], wl["pre"], wl["k"], device=local_rank)
   log(f"[rank {rank}] device index in {time.time() - t0:.1f}s")
 
   nq, k = wl["nq"], wl["k"]
@@ -209,7 +213,7 @@ def main():
   torch.cuda.empty_cache()
 
   if world > 1:
-    step_dev, step_host = make_sharded_steps(ix, wl, q, d_q, d_idx, d_dist, dist, world, dev)
+    step_dev, step_host = make_sharded_steps(searcher, wl, q, d_q, d_idx, d_dist)
   else:
     def step_dev():
       ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)
@@ -314,52 +318,20 @@ def main():
   return 0
 
 
-def make_sharded_steps(ix, wl, q, d_q, d_idx, d_dist, dist, world, dev):
+def make_sharded_steps(searcher, wl, q, d_q, d_idx, d_dist):
   """Sharded search: local candidates -> one NCCL all-gather -> merge."""
-  import ctypes as C
   import torch
-  from scann_b200 import _lib
-  nq, k, ncand = wl["nq"], wl["k"], wl["pre"]
-  L = _lib.lib()
-  ids = torch.empty((nq, ncand), dtype=torch.int32, device=dev)
-  tie = torch.empty((nq, ncand), dtype=torch.int64, device=dev)
-  ah = torch.empty((nq, ncand), dtype=torch.float32, device=dev)
-  ex = torch.empty((nq, ncand), dtype=torch.float32, device=dev)
-  g_ids = torch.empty((world, nq, ncand), dtype=torch.int32, device=dev)
-  g_tie = torch.empty((world, nq, ncand), dtype=torch.int64, device=dev)
-  g_ah = torch.empty((world, nq, ncand), dtype=torch.float32, device=dev)
-  g_ex = torch.empty((world, nq, ncand), dtype=torch.float32, device=dev)
-  vp = C.c_void_p
-
-  def run(dq_ptr):
-    _lib.check(L.scann_b200_search_partial_device(ix._h, vp(dq_ptr), nq, -1, -1, vp(ids.data_ptr()),
-                                                  vp(tie.data_ptr()), vp(ah.data_ptr()), vp(ex.data_ptr()), ncand))
-    st = ix.stats()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    dist.all_gather_into_tensor(g_ids, ids)
-    dist.all_gather_into_tensor(g_tie, tie)
-    dist.all_gather_into_tensor(g_ah, ah)
-    dist.all_gather_into_tensor(g_ex, ex)
-    t1.record()
-    torch.cuda.synchronize()
-    _lib.check(L.scann_b200_merge_partials_device(ix._h, nq, world, ncand, vp(g_ids.data_ptr()), vp(g_tie.data_ptr()),
-                                                  vp(g_ah.data_ptr()), vp(g_ex.data_ptr()), -1, -1,
-                                                  vp(d_idx.data_ptr()), vp(d_dist.data_ptr()), k))
-    st["ms_allgather"] = t0.elapsed_time(t1)
-    st["ms_total"] = st["ms_total"] + st["ms_allgather"]
-    return st
 
   def step_dev():
-    return run(d_q.data_ptr())
+    st = searcher.search_batched_device(d_q, d_idx, d_dist)
+    st["ms_total"] = st["ms_total"] + st["ms_allgather"] + st.get("ms_merge", 0.0)
+    return st
 
   hq = torch.from_numpy(q).pin_memory()
 
   def step_host():
-    dq = hq.to(dev, non_blocking=True)
-    torch.cuda.synchronize()
-    run(dq.data_ptr())
+    dq = hq.to(d_q.device, non_blocking=True)
+    searcher.search_batched_device(dq, d_idx, d_dist)
     return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy()
 
   return step_dev, step_host

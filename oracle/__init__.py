@@ -51,6 +51,7 @@ def lib():
     L.so_lut.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.so_leaf_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.so_candidates.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6
+    L.so_exact_distances.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
     L.so_leaf_size.restype = C.c_uint32
     L.so_leaf_size.argtypes = [C.c_void_p, C.c_uint32]
     L.so_leaf_datapoints.restype = C.POINTER(C.c_uint32)
@@ -110,7 +111,10 @@ class OracleIndex:
 
   def __del__(self):
     if getattr(self, "_h", None):
-      lib().so_index_destroy(self._h)
+      try:
+        lib().so_index_destroy(self._h)
+      except Exception:  # interpreter shutdown
+        pass
       self._h = None
 
   def search_batched(self, q, final_nn=-1, pre_nn=-1, leaves=-1, impl=0, threads=1, batch=256):
@@ -169,6 +173,15 @@ class OracleIndex:
                         _p(acc), _p(cnt))
     return dict(leaf=leaf, slot=slot, dp=dp, score=score, acc=acc, count=cnt,
                 scan_bytes=int(lib().so_last_scan_bytes()), band=int(lib().so_last_boundary_band()))
+
+  def exact_distances(self, q, dps):
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    dps = np.ascontiguousarray(dps, dtype=np.uint32)
+    out = np.empty(dps.shape[0], dtype=np.float32)
+    rc = lib().so_exact_distances(self._h, _p(q), _p(dps), dps.shape[0], _p(out))
+    if rc:
+      raise RuntimeError(lib().so_last_error().decode())
+    return out
 
   @property
   def disjoint(self):

@@ -709,6 +709,12 @@ static float exact_distance(const so_index* ix, const float* q, uint32_t dp) {
   return D < 8 ? sql2_small(q, x, D) : sql2_avx2_order(q, x, D);
 }
 
+int so_exact_distances(const so_index* ix, const float* q, const uint32_t* dps, uint32_t n, float* out) {
+  if (!ix->d.dataset) return fail("no dataset");
+  for (uint32_t i = 0; i < n; ++i) out[i] = exact_distance(ix, q, dps[i]);
+  return 0;
+}
+
 typedef struct {
   int k, npre, nover, P;
 } sp_t;

@@ -1,4 +1,5 @@
-// finalize.cu -- slot -> datapoint id, SOAR de-duplication, exact reordering, final top-k.
+// finalize.cu -- slot -> datapoint id, SOAR de-duplication, exact reordering, final top-k,
+// and the merge of sharded partial results.
 //
 // Replaces (a2/a10/a11) of SURVEY.md section 8:
 //   global index decode                          tree_x_hybrid/tree_ah_hybrid_residual.cc:771-778
@@ -16,6 +17,7 @@
 namespace sb {
 
 constexpr int kFinThreads = 128;
+constexpr uint32_t kInvalidId = 0xFFFFFFFFu;
 
 __device__ __forceinline__ float exact_distance(const DevIndex& ix, const float* __restrict__ q,
                                                 uint32_t dp) {
@@ -25,6 +27,58 @@ __device__ __forceinline__ float exact_distance(const DevIndex& ix, const float*
   auto lx = [&](uint32_t i) { return __ldg(x + i); };
   if (ix.distance == 0) return ix.d < 8 ? neg_dot_small(lq, lx, ix.d) : neg_dot_avx2_order(lq, lx, ix.d);
   return ix.d < 8 ? sql2_small(lq, lx, ix.d) : sql2_avx2_order(lq, lx, ix.d);
+}
+
+// Bitonic sort of (u64 key, u32 payload) pairs in shared memory.
+__device__ __forceinline__ void block_bitonic_sort_kv(uint64_t* s, uint32_t* pay, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        const int l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int r = l | j;
+        const uint64_t a = s[l], b = s[r];
+        const bool up = (l & k) == 0;
+        if ((a > b) == up) {
+          s[l] = b; s[r] = a;
+          const uint32_t pa = pay[l];
+          pay[l] = pay[r]; pay[r] = pa;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// SOAR de-duplication on a sorted-by-(dp, score) array ka[0..n): writes (score', dp) keys into kb
+// (kKeyMax for removed / padding entries) and returns the number of removed entries via *removed.
+// kpay/kpay_out optionally carry a payload (index of the first copy).
+__device__ __forceinline__ void soar_merge_sorted(const uint64_t* ka, uint64_t* kb, const uint32_t* pin,
+                                                  uint32_t* pout, uint32_t n, int np2, uint32_t* s_removed) {
+  uint32_t removed = 0;
+  for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+    uint64_t k = kKeyMax;
+    uint32_t p = 0;
+    if ((uint32_t)i < n) {
+      const uint64_t cur = ka[i];
+      const uint32_t dp = (uint32_t)(cur >> 32);
+      const bool dup_of_prev = i > 0 && (uint32_t)(ka[i - 1] >> 32) == dp;
+      const bool has_next = (uint32_t)(i + 1) < n && (uint32_t)(ka[i + 1] >> 32) == dp;
+      if (dup_of_prev) {
+        ++removed;
+      } else {
+        float sc = ord2f((uint32_t)cur);
+        if (has_next) {  // 0.5f * a + 0.5f * b (internal/utils.cc:146)
+          const float other = ord2f((uint32_t)ka[i + 1]);
+          sc = __fadd_rn(__fmul_rn(0.5f, sc), __fmul_rn(0.5f, other));
+        }
+        k = make_key(sc, dp);
+        if (pin) p = pin[i];
+      }
+    }
+    kb[i] = k;
+    if (pout) pout[i] = p;
+  }
+  if (removed) atomicAdd(s_removed, removed);
 }
 
 // One CTA per query.  Input: buf[q][0..cnt) sorted ascending (score, global slot), cnt <= nover.
@@ -39,8 +93,34 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
   const uint32_t q = blockIdx.x;
   const uint32_t n = min(w.cnt[q], w.nover);
   const uint64_t* src = w.buf + (size_t)q * w.cap;
+  const bool reorder = ix.dataset != nullptr;
   for (uint32_t i = tid; i < ix.d; i += kFinThreads) sq[i] = a.q[(size_t)q * ix.d + i];
   if (tid == 0) s_removed = 0;
+  __syncthreads();
+
+  if (a.part_ids) {
+    // Sharded mode: emit the raw over-retrieved candidates (before SOAR de-duplication, which is
+    // only exact on the global top list) with their exact distances.
+    for (uint32_t i = tid; i < a.part_cap; i += kFinThreads) {
+      const size_t o = (size_t)q * a.part_cap + i;
+      if (i < n) {
+        const uint64_t s = src[i];
+        const uint32_t gslot = (uint32_t)s;
+        const uint32_t dp = ix.slot_dp[gslot];
+        a.part_ids[o] = dp;
+        a.part_tie[o] = (s & 0xFFFFFFFF00000000ull) | (ix.slot_tie ? ix.slot_tie[gslot] : gslot);
+        a.part_ah[o] = ord2f((uint32_t)(s >> 32));
+        a.part_exact[o] = reorder ? exact_distance(ix, sq, dp) : ord2f((uint32_t)(s >> 32));
+      } else {
+        a.part_ids[o] = kInvalidId;
+        a.part_tie[o] = kKeyMax;
+        a.part_ah[o] = INFINITY;
+        a.part_exact[o] = INFINITY;
+      }
+    }
+    return;
+  }
+
   uint32_t m;  // candidates that go to reordering
   if (ix.disjoint) {
     // (score, slot) order is already final; keys become (score, dp)
@@ -66,34 +146,11 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
     }
     __syncthreads();
     block_bitonic_sort(ka, np2);
-    uint32_t removed = 0;
-    for (int i = tid; i < np2; i += kFinThreads) {
-      uint64_t k = kKeyMax;
-      if ((uint32_t)i < n) {
-        const uint64_t cur = ka[i];
-        const uint32_t dp = (uint32_t)(cur >> 32);
-        const bool dup_of_prev = i > 0 && (uint32_t)(ka[i - 1] >> 32) == dp;
-        const bool has_next = (uint32_t)(i + 1) < n && (uint32_t)(ka[i + 1] >> 32) == dp;
-        if (dup_of_prev) {
-          ++removed;
-        } else {
-          float sc = ord2f((uint32_t)cur);
-          if (has_next) {  // 0.5f * a + 0.5f * b (internal/utils.cc:146)
-            const float other = ord2f((uint32_t)ka[i + 1]);
-            sc = __fadd_rn(__fmul_rn(0.5f, sc), __fmul_rn(0.5f, other));
-          }
-          k = make_key(sc, dp);
-        }
-      }
-      kb[i] = k;
-    }
-    if (removed) atomicAdd(&s_removed, removed);
+    soar_merge_sorted(ka, kb, nullptr, nullptr, n, np2, &s_removed);
     __syncthreads();
     block_bitonic_sort(kb, np2);
     m = min(n - s_removed, a.npre);
   }
-  // optional partial output for the sharded path: (id, tie-break key, AH score, exact distance)
-  const bool reorder = ix.dataset != nullptr;
   for (int i = tid; i < np2; i += kFinThreads) {
     uint64_t k = kKeyMax;
     if ((uint32_t)i < m) {
@@ -101,33 +158,10 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
       const uint32_t dp = (uint32_t)c;
       const float dist = reorder ? exact_distance(ix, sq, dp) : ord2f((uint32_t)(c >> 32));
       k = make_key(dist, dp);
-      if (a.part_ids) {
-        const size_t o = (size_t)q * a.part_cap + i;
-        a.part_ids[o] = dp;
-        a.part_tie[o] = ix.disjoint ? src[i] : c;
-        a.part_ah[o] = ord2f((uint32_t)(c >> 32));
-        a.part_exact[o] = dist;
-      }
-    } else if (a.part_ids && (uint32_t)i < a.part_cap) {
-      const size_t o = (size_t)q * a.part_cap + i;
-      a.part_ids[o] = 0xFFFFFFFFu;
-      a.part_tie[o] = kKeyMax;
-      a.part_ah[o] = INFINITY;
-      a.part_exact[o] = INFINITY;
     }
     ka[i] = k;
   }
-  if (a.part_ids) {
-    for (uint32_t i = np2 + tid; i < a.part_cap; i += kFinThreads) {
-      const size_t o = (size_t)q * a.part_cap + i;
-      a.part_ids[o] = 0xFFFFFFFFu;
-      a.part_tie[o] = kKeyMax;
-      a.part_ah[o] = INFINITY;
-      a.part_exact[o] = INFINITY;
-    }
-  }
   __syncthreads();
-  if (!a.out_idx) return;
   block_bitonic_sort(ka, np2);
   const uint32_t kk = min(a.k, m);
   const float mulr = ix.distance == 0 ? -1.0f : 1.0f;  // scann.cc:364-369
@@ -153,83 +187,98 @@ cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const Finaliz
   return cudaGetLastError();
 }
 
-// Merge `world` all-gathered partial lists: global top-N' by (AH score, tie-break key), then
-// top-k by (exact distance, id).  SURVEY.md section 8e.
+// Merge `world` all-gathered partial lists ([world][nq][n_cand]): global top-nover by the
+// (AH score, unsharded slot) key, SOAR de-duplication, top-npre by (score, id), then top-k by
+// (exact distance, id).  Reproduces the single-GPU result exactly.
 __global__ void __launch_bounds__(kFinThreads)
-merge_partials_kernel(int distance, uint32_t nq, int world, int n_cand, const uint32_t* __restrict__ ids,
-                      const uint64_t* __restrict__ tie, const float* __restrict__ ah,
-                      const float* __restrict__ exact, uint32_t npre, uint32_t k, uint32_t* out_idx,
-                      float* out_dist, uint32_t out_k, int np2) {
+merge_partials_kernel(int distance, int disjoint, uint32_t nq, int world, int n_cand,
+                      const uint32_t* __restrict__ ids, const uint64_t* __restrict__ tie,
+                      const float* __restrict__ exact, uint32_t nover, uint32_t npre, uint32_t k,
+                      uint32_t* out_idx, float* out_dist, uint32_t out_k, int np2) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t* ka = reinterpret_cast<uint64_t*>(smem);   // [np2] sort keys
-  uint32_t* pay = reinterpret_cast<uint32_t*>(ka + np2);  // [np2] payload index
-  (void)ah;
+  uint64_t* ka = reinterpret_cast<uint64_t*>(smem);        // [np2]
+  uint64_t* kb = ka + np2;                                  // [np2]
+  uint32_t* pa = reinterpret_cast<uint32_t*>(kb + np2);     // [np2] payload: record offset
+  uint32_t* pb = pa + np2;                                  // [np2]
+  __shared__ uint32_t s_removed, s_valid;
   const int tid = threadIdx.x;
   const uint32_t q = blockIdx.x;
   const int total = world * n_cand;
-  // 1) rank all candidates by the tie-break key (score bits in the high half): since a u64
-  //    bitonic sort cannot carry a payload, sort (key) and find payloads by a second pass.
+  auto rec = [&](int i) { return ((size_t)(i / n_cand) * nq + q) * n_cand + (i % n_cand); };
+  if (tid == 0) { s_removed = 0; s_valid = 0; }
+  __syncthreads();
+  uint32_t nvalid = 0;
   for (int i = tid; i < np2; i += kFinThreads) {
     uint64_t key = kKeyMax;
     if (i < total) {
-      const int r = i / n_cand, c = i % n_cand;
-      const size_t o = ((size_t)r * nq + q) * n_cand + c;
-      if (ids[o] != 0xFFFFFFFFu) key = tie[o];
+      const size_t o = rec(i);
+      if (ids[o] != kInvalidId) { key = tie[o]; ++nvalid; }
     }
+    ka[i] = key;
+    pa[i] = (uint32_t)i;
+  }
+  if (nvalid) atomicAdd(&s_valid, nvalid);
+  __syncthreads();
+  block_bitonic_sort_kv(ka, pa, np2);
+  const uint32_t n = min(s_valid, nover);  // global over-retrieved candidate list
+  uint32_t m;
+  if (disjoint) {
+    for (int i = tid; i < np2; i += kFinThreads) {
+      uint64_t key = kKeyMax;
+      if ((uint32_t)i < n) key = (ka[i] & 0xFFFFFFFF00000000ull) | ids[rec((int)pa[i])];
+      kb[i] = key;
+      pb[i] = pa[i];
+    }
+    m = min(n, npre);
+    __syncthreads();
+  } else {
+    __syncthreads();
+    // (dp, score) keys, payload = record
+    for (int i = tid; i < np2; i += kFinThreads) {
+      uint64_t key = kKeyMax;
+      uint32_t p = pa[i];
+      if ((uint32_t)i < n) key = ((uint64_t)ids[rec((int)p)] << 32) | (ka[i] >> 32);
+      kb[i] = key;
+      pb[i] = p;
+    }
+    __syncthreads();
+    block_bitonic_sort_kv(kb, pb, np2);
+    soar_merge_sorted(kb, ka, pb, pa, n, np2, &s_removed);
+    __syncthreads();
+    block_bitonic_sort_kv(ka, pa, np2);
+    m = min(n - s_removed, npre);
+    for (int i = tid; i < np2; i += kFinThreads) { kb[i] = ka[i]; pb[i] = pa[i]; }
+    __syncthreads();
+  }
+  for (int i = tid; i < np2; i += kFinThreads) {
+    uint64_t key = kKeyMax;
+    if ((uint32_t)i < m) key = make_key(exact[rec((int)pb[i])], (uint32_t)kb[i]);
     ka[i] = key;
   }
   __syncthreads();
   block_bitonic_sort(ka, np2);
-  // threshold key = npre-th smallest
-  const uint32_t navail = min((uint32_t)total, (uint32_t)np2);
-  uint64_t thr = kKeyMax;
-  {
-    uint32_t cnt_valid = 0;
-    // count valid via binary search for first kKeyMax
-    int lo = 0, hi = (int)navail;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ka[mid] == kKeyMax) hi = mid; else lo = mid + 1; }
-    cnt_valid = (uint32_t)lo;
-    const uint32_t m = min(cnt_valid, npre);
-    thr = m ? ka[m - 1] : 0;
-    if (m == 0) thr = 0;
-    __syncthreads();
-    // 2) gather the selected ones as (exact distance, id) keys
-    for (int i = tid; i < np2; i += kFinThreads) pay[i] = 0;
-    __syncthreads();
-    for (int i = tid; i < np2; i += kFinThreads) {
-      uint64_t key = kKeyMax;
-      if (i < total && m) {
-        const int r = i / n_cand, c = i % n_cand;
-        const size_t o = ((size_t)r * nq + q) * n_cand + c;
-        if (ids[o] != 0xFFFFFFFFu && tie[o] <= thr) key = make_key(exact[o], ids[o]);
-      }
-      ka[i] = key;
-    }
-    __syncthreads();
-    block_bitonic_sort(ka, np2);
-    const uint32_t kk = min(k, m);
-    const float mulr = distance == 0 ? -1.0f : 1.0f;
-    for (uint32_t i = tid; i < out_k; i += kFinThreads) {
-      uint32_t id = 0;
-      float dist = __uint_as_float(0x7FC00000u);
-      if (i < kk) { id = (uint32_t)ka[i]; dist = mulr * ord2f((uint32_t)(ka[i] >> 32)); }
-      out_idx[(size_t)q * out_k + i] = id;
-      out_dist[(size_t)q * out_k + i] = dist;
-    }
+  const uint32_t kk = min(k, m);
+  const float mulr = distance == 0 ? -1.0f : 1.0f;
+  for (uint32_t i = tid; i < out_k; i += kFinThreads) {
+    uint32_t id = 0;
+    float dist = __uint_as_float(0x7FC00000u);
+    if (i < kk) { id = (uint32_t)ka[i]; dist = mulr * ord2f((uint32_t)(ka[i] >> 32)); }
+    out_idx[(size_t)q * out_k + i] = id;
+    out_dist[(size_t)q * out_k + i] = dist;
   }
 }
 
 cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, int n_cand,
-                                  const uint32_t* ids, const uint64_t* tie, const float* ah,
-                                  const float* exact, uint32_t npre, uint32_t k, uint32_t* out_idx,
+                                  const uint32_t* ids, const uint64_t* tie, const float* exact,
+                                  uint32_t nover, uint32_t npre, uint32_t k, uint32_t* out_idx,
                                   float* out_dist, uint32_t out_k, cudaStream_t s) {
   int np2 = 2;
   while (np2 < world * n_cand) np2 <<= 1;
-  const size_t smem = (size_t)np2 * 12;
+  const size_t smem = (size_t)np2 * 24;
   cudaError_t e = cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  merge_partials_kernel<<<nq, kFinThreads, smem, s>>>(ix.distance, nq, world, n_cand, ids, tie, ah, exact,
-                                                      npre, k, out_idx, out_dist, out_k, np2);
+  merge_partials_kernel<<<nq, kFinThreads, smem, s>>>(ix.distance, ix.disjoint, nq, world, n_cand, ids, tie, exact,
+                                                      nover, npre, k, out_idx, out_dist, out_k, np2);
   return cudaGetLastError();
 }
 

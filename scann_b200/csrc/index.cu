@@ -93,7 +93,7 @@ struct scann_b200_index {
   std::vector<uint32_t> h_leaf_size;
   // persistent device arrays
   DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
-      codes, slot_dp, dataset, dp_row;
+      codes, slot_dp, slot_tie, dataset, dp_row;
   // workspace
   DevBuf q, dist, leaves, bias, lut, mult, inv, pilot_end, buf, cnt, tau, ovf, leaf_cnt, leaf_eoff,
       leaf_cur, item_off, entry_q, entry_bias, counters, stats, out_idx, out_dist;
@@ -123,14 +123,19 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   // datapoints_by_token in file order (scann_ops/cc/scann.cc:88-98), filtered to this shard
   const uint32_t mult = d->soar ? 2 : 1;
   const size_t len = (size_t)N * mult;
-  std::vector<uint32_t> lsize(L, 0);
+  std::vector<uint32_t> lsize(L, 0), lsize_full(L, 0);
   for (size_t j = 0; j < len; ++j) {
     const int32_t t = d->tokens[j];
     if (t < 0) continue;
     if ((uint32_t)t >= L) return fail(SCANN_B200_INVALID_ARGUMENT, "token %d out of range [0,%u)", t, L);
+    lsize_full[t]++;
     if ((j / mult) % world != (size_t)rank) continue;
     lsize[t]++;
   }
+  // unsharded group offsets: the tie-break half of a candidate key must be the slot the
+  // datapoint has in the UNSHARDED index, so that sharded + merged == single GPU
+  std::vector<uint32_t> goff_full(L + 1, 0);
+  for (uint32_t l = 0; l < L; ++l) goff_full[l + 1] = goff_full[l] + (lsize_full[l] + 31) / 32;
   std::vector<uint32_t> goff(L + 1, 0), ntiles(L, 0), gpt(L, 0);
   for (uint32_t l = 0; l < L; ++l) {
     const uint32_t ng = (lsize[l] + 31) / 32;
@@ -143,20 +148,23 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   const size_t ngroups = goff[L];
   if (ngroups * 32 > 0xFFFFFFF0ull) return fail(SCANN_B200_UNIMPLEMENTED, "more than 2^32 slots");
   std::vector<uint32_t> slot_dp(ngroups * 32, 0xFFFFFFFFu);
+  std::vector<uint32_t> slot_tie(world > 1 ? ngroups * 32 : 0, 0xFFFFFFFFu);
   std::vector<uint32_t> codes((size_t)ngroups * W * 32, 0u);
   int disjoint = 1;
   {
-    std::vector<uint32_t> cur(L, 0);
+    std::vector<uint32_t> cur(L, 0), cur_full(L, 0);
     for (size_t j = 0; j < len; ++j) {
       const int32_t t = d->tokens[j];
       if (t < 0) continue;
       const uint32_t i = (uint32_t)(j / mult);
       if (d->soar && (j & 1) && d->tokens[j - 1] >= 0) disjoint = 0;
+      const uint32_t s_full = cur_full[t]++;
       if (i % world != (uint32_t)rank) continue;
       const uint32_t s = cur[t]++;
       const size_t g = goff[t] + s / 32;
       const int m = (int)(s % 32);
       slot_dp[g * 32 + m] = i;
+      if (world > 1) slot_tie[g * 32 + m] = goff_full[t] * 32 + s_full;
       // tree_ah_hybrid_residual.cc:385-396: the SOAR code row iff tok[2i+1] == leaf
       const uint8_t* row = d->codes + (size_t)i * B;
       if (d->soar && d->tokens[2 * (size_t)i + 1] == t) row = d->soar_codes + (size_t)i * B;
@@ -212,6 +220,11 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   UP(ix->leaf_gpt, gpt.data(), sizeof(uint32_t) * L);
   UP(ix->codes, codes.data(), sizeof(uint32_t) * codes.size());
   UP(ix->slot_dp, slot_dp.data(), sizeof(uint32_t) * slot_dp.size());
+  v.slot_tie = nullptr;
+  if (world > 1) {
+    UP(ix->slot_tie, slot_tie.data(), sizeof(uint32_t) * slot_tie.size());
+    v.slot_tie = ix->slot_tie.as<uint32_t>();
+  }
   v.dataset = nullptr; v.dp_row = nullptr;
   if (d->dataset) {
     if (world == 1) {
@@ -509,8 +522,8 @@ int scann_b200_search_partial_device(scann_b200_index* ix, const float* d_querie
   if (int rc = check_query_args(ix, d_queries, nq)) return rc;
   Params p;
   if (int rc = resolve(ix, -1, pre_nn, leaves, &p)) return rc;
-  if (!d_ids || !d_tie || !d_ah || !d_exact || n_cand < (int)p.npre)
-    return fail(SCANN_B200_INVALID_ARGUMENT, "partial buffers too small: n_cand=%d < %u", n_cand, p.npre);
+  if (!d_ids || !d_tie || !d_ah || !d_exact || n_cand < (int)p.nover)
+    return fail(SCANN_B200_INVALID_ARGUMENT, "partial buffers too small: n_cand=%d < %u", n_cand, p.nover);
   std::lock_guard<std::mutex> lock(ix->mu);
   CU(cudaSetDevice(ix->device));
   ix->last = scann_b200_stats{};
@@ -530,10 +543,11 @@ int scann_b200_merge_partials_device(scann_b200_index* ix, uint32_t nq, int32_t 
   if (!ix) return fail(SCANN_B200_INVALID_ARGUMENT, "null index");
   Params p;
   if (int rc = resolve(ix, final_nn, pre_nn, -1, &p)) return rc;
-  if ((long long)world * n_cand > 32768) return fail(SCANN_B200_UNIMPLEMENTED, "merge of %d x %d candidates too large", world, n_cand);
+  if ((long long)world * n_cand > 8192) return fail(SCANN_B200_UNIMPLEMENTED, "merge of %d x %d candidates too large", world, n_cand);
   std::lock_guard<std::mutex> lock(ix->mu);
   CU(cudaSetDevice(ix->device));
-  CU(sb::launch_merge_partials(ix->dev, nq, world, n_cand, d_ids, d_tie, d_ah, d_exact, p.npre, p.k, d_out_idx,
+  (void)d_ah;
+  CU(sb::launch_merge_partials(ix->dev, nq, world, n_cand, d_ids, d_tie, d_exact, p.nover, p.npre, p.k, d_out_idx,
                                d_out_dist, (uint32_t)out_k, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   return 0;

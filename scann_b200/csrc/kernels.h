@@ -27,6 +27,7 @@ struct DevIndex {
   const uint32_t* leaf_gpt;   // [L] groups per tile
   const uint32_t* codes;      // [groups][W*32] packed nibble words (see pack_codes in index.cu)
   const uint32_t* slot_dp;    // [groups*32] datapoint id per slot, 0xFFFFFFFF padding
+  const uint32_t* slot_tie;   // [groups*32] slot of the datapoint in the unsharded index (NULL = identity)
   const float* dataset;       // [rows][D] f32 rows for exact reordering (NULL if none)
   const uint32_t* dp_row;     // [N] datapoint id -> row of `dataset` (NULL = identity)
 };
@@ -78,8 +79,8 @@ struct FinalizeArgs {
 };
 cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const FinalizeArgs& a, cudaStream_t s);
 cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, int n_cand,
-                                  const uint32_t* ids, const uint64_t* tie, const float* ah,
-                                  const float* exact, uint32_t npre, uint32_t k, uint32_t* out_idx,
+                                  const uint32_t* ids, const uint64_t* tie, const float* exact,
+                                  uint32_t nover, uint32_t npre, uint32_t k, uint32_t* out_idx,
                                   float* out_dist, uint32_t out_k, cudaStream_t s);
 // ---- debug ----
 void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s);

@@ -1,0 +1,147 @@
+"""Sharded search over the GPUs of one box.
+
+The database shards by datapoint id (`id % world == rank`) inside every leaf; centres, AH
+codebook, tokenization and LUT build are replicated, so no query-side exchange is needed.
+Each rank produces its local over-retrieved pre-reorder candidates with exact distances
+(`scann_b200_search_partial_device`), ONE all-gather exchanges them (records of
+(id u32, tie-break key u64, AH score f32, exact distance f32)), and every rank merges to the
+global result (`scann_b200_merge_partials_device`).  The merged result is bit-identical to the
+single-GPU result because the tie-break key carries the slot of the datapoint in the
+UNSHARDED index.
+
+`torch.distributed` (NCCL on GPUs) is plumbing only.  `merge_partials_reference` is the
+host-side statement of the merge rule; tests use it with the gloo backend on CPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+INVALID_ID = 0xFFFFFFFF
+KEY_MAX = 0xFFFFFFFFFFFFFFFF
+
+
+def nover_for(pre_nn, disjoint, overretrieve):
+  """tree_ah_hybrid_residual.h:263-267 (NumNeighborsWithSpillingMultiplier)."""
+  if disjoint:
+    return int(pre_nn)
+  return int(float(pre_nn) * float(np.float32(overretrieve)))
+
+
+def shard_tokens(tokens, soar, rank, world):
+  """Token array of one shard: datapoints of other ranks are marked absent (-1)."""
+  t = np.array(tokens, dtype=np.int32, copy=True)
+  mult = 2 if soar else 1
+  ids = np.arange(t.shape[0]) // mult
+  t[ids % world != rank] = -1
+  return t
+
+
+def f2ord(x):
+  """Order-preserving u32 image of float32 (same mapping as the kernels)."""
+  u = (np.asarray(x, dtype=np.float32) + np.float32(0.0)).view(np.uint32)
+  return np.where(u & 0x80000000, ~u, u | 0x80000000).astype(np.uint32)
+
+
+def merge_partials_reference(ids, tie, exact, nover, npre, k, disjoint, dot_product=True):
+  """Host statement of the merge rule for ONE query.
+
+  ids/tie/exact: 1-D arrays over all ranks' records (padding: id == INVALID_ID).
+  Returns (ids[k], distances[k]) padded with (0, NaN).
+  """
+  valid = ids != INVALID_ID
+  ids, tie, exact = ids[valid], tie[valid], exact[valid]
+  order = np.argsort(tie, kind="stable")[:nover]
+  ids, tie, exact = ids[order], tie[order], exact[order]
+  score_ord = (tie >> np.uint64(32)).astype(np.uint32)
+  u = np.where(score_ord & 0x80000000, score_ord & 0x7FFFFFFF, ~score_ord).astype(np.uint32)
+  score = u.view(np.float32)
+  if disjoint:
+    sel = np.arange(min(len(ids), npre))
+    sel_ids, sel_exact = ids[sel], exact[sel]
+  else:
+    best = {}
+    for i in range(len(ids)):
+      dp = int(ids[i])
+      if dp in best:
+        a, e = best[dp]
+        lo, hi = (a, score[i]) if a <= score[i] else (score[i], a)
+        best[dp] = (np.float32(np.float32(0.5) * lo + np.float32(0.5) * hi), e)
+      else:
+        best[dp] = (score[i], exact[i])
+    items = sorted(best.items(), key=lambda kv: (int(f2ord(kv[1][0])), kv[0]))[:npre]
+    sel_ids = np.asarray([kv[0] for kv in items], dtype=np.uint32)
+    sel_exact = np.asarray([kv[1][1] for kv in items], dtype=np.float32)
+  keys = sorted(zip(f2ord(sel_exact).tolist(), sel_ids.tolist(), sel_exact.tolist()))[:k]
+  out_i = np.zeros(k, np.uint32)
+  out_d = np.full(k, np.nan, np.float32)
+  for j, (_, dp, ex) in enumerate(keys):
+    out_i[j] = dp
+    out_d[j] = -ex if dot_product else ex
+  return out_i, out_d
+
+
+class ShardedSearcher:
+  """One rank of a sharded searcher.  `group` is a torch.distributed process group (NCCL)."""
+
+  def __init__(self, arrays, leaves_to_search, pre_reorder_nn, final_nn, rank, world, device, group=None):
+    import torch
+    self.torch = torch
+    self.rank, self.world, self.group = rank, world, group
+    self.dev = torch.device("cuda", device)
+    self.index = _lib.NativeIndex(arrays, leaves_to_search, pre_reorder_nn, final_nn, device=device,
+                                  shard_rank=rank, shard_world=world)
+    self.pre, self.k = pre_reorder_nn, final_nn
+    self.ncand = nover_for(pre_reorder_nn, not arrays.soar, arrays.overretrieve)
+    self._bufs = None
+
+  def _buffers(self, nq):
+    t = self.torch
+    if self._bufs is None or self._bufs[0].shape[0] != nq:
+      n, w, dev = self.ncand, self.world, self.dev
+      local = (t.empty((nq, n), dtype=t.int32, device=dev), t.empty((nq, n), dtype=t.int64, device=dev),
+               t.empty((nq, n), dtype=t.float32, device=dev), t.empty((nq, n), dtype=t.float32, device=dev))
+      # concatenated along dim 0 = [world][nq][n] in memory (accepted by both NCCL and gloo)
+      gathered = tuple(t.empty((w * nq, n), dtype=x.dtype, device=dev) for x in (local[0], local[1], local[3]))
+      self._bufs = local + gathered
+    return self._bufs
+
+  def search_batched_device(self, d_q, d_idx, d_dist):
+    """d_q [nq, D] f32 cuda tensor; d_idx [nq, k] int32, d_dist [nq, k] f32 outputs. Returns stats."""
+    import torch.distributed as dist
+    t = self.torch
+    nq = d_q.shape[0]
+    ids, tie, ah, ex, g_ids, g_tie, g_ex = self._buffers(nq)
+    L = _lib.lib()
+    vp = C.c_void_p
+    h = self.index._h
+    _lib.check(L.scann_b200_search_partial_device(h, vp(d_q.data_ptr()), nq, -1, -1, vp(ids.data_ptr()),
+                                                  vp(tie.data_ptr()), vp(ah.data_ptr()), vp(ex.data_ptr()),
+                                                  self.ncand))
+    st = self.index.stats()
+    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    e0.record()
+    dist.all_gather_into_tensor(g_ids, ids, group=self.group)
+    dist.all_gather_into_tensor(g_tie, tie, group=self.group)
+    dist.all_gather_into_tensor(g_ex, ex, group=self.group)
+    e1.record()
+    t.cuda.synchronize()
+    import time
+    t_merge = time.perf_counter()
+    _lib.check(L.scann_b200_merge_partials_device(h, nq, self.world, self.ncand, vp(g_ids.data_ptr()),
+                                                  vp(g_tie.data_ptr()), None, vp(g_ex.data_ptr()), -1, -1,
+                                                  vp(d_idx.data_ptr()), vp(d_dist.data_ptr()), d_idx.shape[1]))
+    st["ms_merge"] = (time.perf_counter() - t_merge) * 1e3  # the call synchronises its stream
+    st["ms_allgather"] = e0.elapsed_time(e1)
+    st["allgather_bytes_per_rank"] = int(nq * self.ncand * 16)
+    return st
+
+  def search_batched(self, q):
+    """Host buffers in / out (numpy)."""
+    t = self.torch
+    d_q = t.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(self.dev)
+    d_idx = t.empty((q.shape[0], self.k), dtype=t.int32, device=self.dev)
+    d_dist = t.empty((q.shape[0], self.k), dtype=t.float32, device=self.dev)
+    self.search_batched_device(d_q, d_idx, d_dist)
+    return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy()

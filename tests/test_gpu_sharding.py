@@ -1,0 +1,68 @@
+"""GPU: sharded search == unsharded search, bit for bit.
+
+Shards are emulated on ONE device (two index handles, records concatenated the way an
+all-gather would lay them out); the NCCL exchange itself is exercised by `bench.py --gpus N`.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import get_case
+
+pytestmark = pytest.mark.gpu
+
+
+def run_sharded(case, world):
+  import torch
+  from scann_b200 import _lib, distributed as sd
+  a = case.arrays
+  q = np.ascontiguousarray(case.q, dtype=np.float32)
+  nq = q.shape[0]
+  ncand = sd.nover_for(case.pre, not a.soar, a.overretrieve)
+  dev = torch.device("cuda", 0)
+  d_q = torch.from_numpy(q).to(dev)
+  g_ids = torch.empty((world, nq, ncand), dtype=torch.int32, device=dev)
+  g_tie = torch.empty((world, nq, ncand), dtype=torch.int64, device=dev)
+  g_ah = torch.empty((world, nq, ncand), dtype=torch.float32, device=dev)
+  g_ex = torch.empty((world, nq, ncand), dtype=torch.float32, device=dev)
+  torch.cuda.synchronize()
+  L = _lib.lib()
+  vp = C.c_void_p
+  shards = []
+  for r in range(world):
+    ix = _lib.NativeIndex(a, case.probe, case.pre, case.k, device=0, shard_rank=r, shard_world=world)
+    shards.append(ix)
+    _lib.check(L.scann_b200_search_partial_device(ix._h, vp(d_q.data_ptr()), nq, -1, -1, vp(g_ids[r].data_ptr()),
+                                                  vp(g_tie[r].data_ptr()), vp(g_ah[r].data_ptr()),
+                                                  vp(g_ex[r].data_ptr()), ncand))
+  d_idx = torch.empty((nq, case.k), dtype=torch.int32, device=dev)
+  d_dist = torch.empty((nq, case.k), dtype=torch.float32, device=dev)
+  _lib.check(L.scann_b200_merge_partials_device(shards[0]._h, nq, world, ncand, vp(g_ids.data_ptr()),
+                                                vp(g_tie.data_ptr()), None, vp(g_ex.data_ptr()), -1, -1,
+                                                vp(d_idx.data_ptr()), vp(d_dist.data_ptr()), case.k))
+  torch.cuda.synchronize()
+  # host statement of the merge rule on the same records
+  ids_h = g_ids.cpu().numpy().view(np.uint32)
+  tie_h = g_tie.cpu().numpy().view(np.uint64)
+  ex_h = g_ex.cpu().numpy()
+  ref_i = np.zeros((nq, case.k), np.uint32)
+  for i in range(min(nq, 8)):
+    ref_i[i], _ = sd.merge_partials_reference(ids_h[:, i].reshape(-1), tie_h[:, i].reshape(-1), ex_h[:, i].reshape(-1),
+                                              ncand, case.pre, case.k, not a.soar)
+  for ix in shards:
+    ix.close()
+  return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy(), ref_i
+
+
+@pytest.mark.parametrize("kw,world", [(dict(), 2), (dict(), 3), (dict(soar=1.5), 2), (dict(soar=1.5), 4),
+                                      (dict(n=3000, leaves=300, probe=40, pre=150), 8)])
+def test_sharded_equals_unsharded(kw, world):
+  c = get_case(**kw)
+  i1, d1 = c.native.search_batched(c.q)
+  i2, d2, ref_i = run_sharded(c, world)
+  np.testing.assert_array_equal(i1, i2)
+  np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
+  np.testing.assert_array_equal(ref_i[:8], i2[:8])
+  i0, d0 = c.oracle.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i2)
