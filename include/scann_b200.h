@@ -107,6 +107,34 @@ int scann_b200_merge_partials_device(scann_b200_index* index, uint32_t nq, int32
 const char* scann_b200_last_error(void);
 int scann_b200_abi_version(void);
 
+/* ---- serialized assets (the reference's on-disk format) ---- */
+
+typedef struct scann_b200_assets scann_b200_assets;
+
+/* Replaces ScannInterface::LoadArtifacts (scann_ops/cc/scann.cc:105-264): reads binary
+ * scann_config.pb from `artifacts_dir` and every asset listed in the text-format ScannAssets
+ * manifest (`assets_pbtxt` = contents of scann_assets.pbtxt; relative paths are re-rooted at
+ * artifacts_dir): serialized_partitioner.pb, ah_codebook.pb, datapoint_to_token.npy,
+ * hashed_dataset[_soar].npy, dataset.npy, bfloat16_dataset.npy.  The handle owns the host copies. */
+int scann_b200_assets_load(const char* artifacts_dir, const char* assets_pbtxt, scann_b200_assets** out);
+void scann_b200_assets_free(scann_b200_assets* assets);
+/* Fills an index descriptor whose pointers alias the handle's memory (valid until _free) and whose
+ * defaults (num_neighbors, approx_num_neighbors, max_spill_centers, SOAR, overretrieve, distance)
+ * come from the loaded ScannConfig.  device / shard fields are left 0 / 0 / 1. */
+int scann_b200_assets_describe(const scann_b200_assets* assets, scann_b200_index_desc* out);
+/* The loaded ScannConfig in protobuf text format (ScannNumpy::config, scann_npy.cc). */
+const char* scann_b200_assets_config(const scann_b200_assets* assets);
+/* Replaces ScannInterface::Serialize (scann_ops/cc/scann.cc:504-601) + the manifest of
+ * ScannNumpy::Serialize (scann_npy.cc:272-282): writes scann_config.pb (binary ScannConfig encoded
+ * from `config_text`) and one file per non-null array of `desc`; returns the text-format
+ * ScannAssets manifest in `assets_pbtxt_out` (the caller writes scann_assets.pbtxt). */
+int scann_b200_assets_save(const char* artifacts_dir, const scann_b200_index_desc* desc,
+                           const char* config_text, int relative_path, char* assets_pbtxt_out,
+                           size_t assets_pbtxt_cap);
+/* ScannConfig text <-> binary (ParseTextProto scann.h:185-188; WriteProtobufToFile). */
+int scann_b200_config_text_to_binary(const char* text, void* out, size_t cap, size_t* out_len);
+int scann_b200_config_binary_to_text(const void* bin, size_t len, char* out, size_t cap);
+
 /* ---- parity / measurement hooks (used by tests/ and bench.py) ---- */
 
 /* KMeansTreePartitioner::TokensForDatapointWithSpillingBatched

@@ -48,6 +48,9 @@ EXPORTS = [
     "scann_b200_merge_partials_device", "scann_b200_last_error", "scann_b200_abi_version",
     "scann_b200_debug_tokenize", "scann_b200_debug_lut", "scann_b200_debug_leaf_scores",
     "scann_b200_debug_candidates", "scann_b200_leaf_size", "scann_b200_last_stats",
+    "scann_b200_assets_load", "scann_b200_assets_free", "scann_b200_assets_describe",
+    "scann_b200_assets_config", "scann_b200_assets_save", "scann_b200_config_text_to_binary",
+    "scann_b200_config_binary_to_text",
 ]
 
 
@@ -82,6 +85,15 @@ def lib():
   L.scann_b200_leaf_size.argtypes = [vp, u32]
   L.scann_b200_leaf_size.restype = u32
   L.scann_b200_last_stats.argtypes = [vp, C.POINTER(Stats)]
+  L.scann_b200_assets_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+  L.scann_b200_assets_free.argtypes = [vp]
+  L.scann_b200_assets_free.restype = None
+  L.scann_b200_assets_describe.argtypes = [vp, C.POINTER(IndexDesc)]
+  L.scann_b200_assets_config.argtypes = [vp]
+  L.scann_b200_assets_config.restype = C.c_char_p
+  L.scann_b200_assets_save.argtypes = [C.c_char_p, C.POINTER(IndexDesc), C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
+  L.scann_b200_config_text_to_binary.argtypes = [C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+  L.scann_b200_config_binary_to_text.argtypes = [vp, C.c_size_t, C.c_char_p, C.c_size_t]
   _LIB = L
   return L
 

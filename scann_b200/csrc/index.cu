@@ -83,6 +83,10 @@ enum { EV_START, EV_TOK, EV_LUT, EV_PILOT, EV_WORK, EV_SCAN, EV_COMPACT, EV_FIN,
 
 }  // namespace
 
+namespace sb {
+void set_last_error(const char* msg) { g_err = msg ? msg : ""; }  // used by assets.cc
+}  // namespace sb
+
 struct scann_b200_index {
   sb::DevIndex dev{};
   scann_b200_index_desc desc{};

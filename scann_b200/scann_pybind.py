@@ -1,0 +1,272 @@
+"""`scann_pybind.ScannNumpy` -- the class `scann_ops_pybind.py` talks to.
+
+Mirror of the pybind class bound in scann/scann_ops/cc/python/scann_pybind.cc:28-53 and
+implemented in scann_ops/cc/scann_npy.cc: same constructor overloads, method names, argument
+meaning, return shapes/dtypes and exception types/prefixes (scann_npy.cc:41-47,62-76,214-256).
+Everything on the query path goes through the C ABI (include/scann_b200.h); this file only
+marshals numpy buffers, like scann_npy.cc does.  Index training (k-means, AH codebooks) is done by
+`index_build` (out of scope of the hot path).
+"""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+from . import _lib, config as cfgmod, index_build
+
+
+def _runtime(prefix, exc):
+  msg = exc.message if isinstance(exc, _lib.ScannB200Error) else str(exc)
+  return RuntimeError(prefix + msg)
+
+
+class _Plan:
+  """What the ScannConfig asks for, reduced to the fields the query path needs."""
+
+  def __init__(self, text):
+    try:
+      c = cfgmod.parse(text)
+    except cfgmod.TextProtoError as e:
+      raise RuntimeError(f"Error initializing searcher: Failed to parse config: {e}")
+    self.msg = c
+    name = c.path("distance_measure", "distance_measure", default="SquaredL2Distance")
+    dist = {"DotProductDistance": "dot_product", "SquaredL2Distance": "squared_l2"}.get(name)
+    if dist is None:
+      raise RuntimeError(f"Error initializing searcher: UNIMPLEMENTED: distance measure {name}")
+    self.distance = dist
+    self.num_neighbors = cfgmod.as_int(c.get("num_neighbors"), 1)
+    self.partitioning = c.get("partitioning")
+    self.ah = c.path("hash", "asymmetric_hash")
+    self.brute_force = c.get("brute_force")
+    self.reordering = c.get("exact_reordering")
+    self.autopilot = c.get("autopilot")
+
+  def check_supported(self):
+    def unimpl(what):
+      raise RuntimeError(f"Error initializing searcher: UNIMPLEMENTED: {what} is outside the scann_b200 hot path")
+    if self.autopilot is not None:
+      unimpl("autopilot")
+    if self.partitioning is None or self.ah is None:
+      unimpl("a searcher without tree() + score_ah()")
+    p, ah = self.partitioning, self.ah
+    if p.has("projection") or p.has("bottom_up_top_level_partitioner"):
+      unimpl("PCA/truncate projections and upper_tree")
+    if p.get("query_tokenization_type", "FLOAT") != "FLOAT":
+      unimpl("quantized centroids")
+    if p.path("query_spilling", "spilling_type") not in ("FIXED_NUMBER_OF_CENTERS",):
+      unimpl("query spilling other than FIXED_NUMBER_OF_CENTERS")
+    if ah.get("lookup_type") != "INT8_LUT16" or cfgmod.as_int(ah.get("num_clusters_per_block"), 256) != 16:
+      unimpl("lut256 / non-LUT16 asymmetric hashing")
+    if ah.path("projection", "projection_type") not in ("CHUNK", "VARIABLE_CHUNK"):
+      unimpl("AH projections other than CHUNK / VARIABLE_CHUNK")
+    if self.distance == "squared_l2":
+      unimpl("squared-L2 tree-AH (TreeXHybridSMMD)")
+    if not cfgmod.as_bool(ah.get("use_residual_quantization"), False):
+      unimpl("non-residual tree-AH")
+    r = self.reordering
+    if r is not None:
+      if cfgmod.as_bool(r.path("fixed_point", "enabled"), False) or cfgmod.as_bool(r.path("bfloat16", "enabled"), False):
+        unimpl("int8 / bfloat16 reordering")
+
+  def dims_per_block(self):
+    proj = self.ah.get("projection")
+    if proj.get("projection_type") == "CHUNK":
+      return cfgmod.as_int(proj.get("num_dims_per_block"))
+    blocks = proj.all("variable_blocks")
+    return cfgmod.as_int(blocks[0].get("num_dims_per_block"))
+
+
+class ScannNumpy:
+  """ScannNumpy(artifacts_dir: str, assets_pbtxt: str) | ScannNumpy(db, config_text, training_threads)."""
+
+  def __init__(self, *args):
+    self._index = None
+    self._arrays = None
+    self._assets = None
+    if len(args) == 2 and isinstance(args[0], str):
+      self._load(args[0], args[1])
+    elif len(args) == 3:
+      self._build(args[0], args[1], args[2])
+    else:
+      raise TypeError("ScannNumpy(artifacts_dir, assets_pbtxt) or ScannNumpy(dataset, config, training_threads)")
+
+  # ---- construction ----
+  def _build(self, db, config_text, training_threads):
+    del training_threads  # training runs on the GPU (or torch CPU threads)
+    db = np.asarray(db)
+    if db.ndim != 2:
+      raise ValueError("Dataset input must be two-dimensional")  # scann_npy.cc:70-71
+    plan = _Plan(config_text)
+    plan.check_supported()
+    self._config_text = config_text
+    db = np.ascontiguousarray(db, dtype=np.float32)
+    p, ah = plan.partitioning, plan.ah
+    soar = p.path("database_spilling", "spilling_type") in ("TWO_CENTER_ORTHOGONALITY_AMPLIFIED", "SOAR")
+    lam = cfgmod.as_float(p.path("database_spilling", "orthogonality_amplification_lambda"), 1.5) if soar else None
+    thr = cfgmod.as_float(ah.get("noise_shaping_threshold"), math.nan)
+    if thr is not None and not math.isnan(thr):
+      # anisotropic (noise-shaped) encoding is an index-build feature; the plain
+      # nearest-centre encoder is used and the threshold is recorded in the config only.
+      pass
+    try:
+      arrays = index_build.build_tree_ah(
+          db, plan.distance, num_leaves=cfgmod.as_int(p.get("num_children")),
+          dims_per_block=plan.dims_per_block(),
+          training_sample_size=cfgmod.as_int(p.get("expected_sample_size"), 100000),
+          tree_iters=cfgmod.as_int(p.get("max_clustering_iterations"), 12),
+          ah_iters=cfgmod.as_int(ah.get("max_clustering_iterations"), 10),
+          soar_lambda=lam, overretrieve=cfgmod.as_float(p.path("database_spilling", "overretrieve_factor"), 2.0),
+          spherical=p.get("partitioning_type", "GENERIC") == "SPHERICAL",
+          keep_dataset=plan.reordering is not None)
+      self._finish(arrays, plan)
+    except _lib.ScannB200Error as e:
+      raise _runtime("Error initializing searcher: ", e)
+
+  def _finish(self, arrays, plan):
+    leaves = cfgmod.as_int(plan.partitioning.path("query_spilling", "max_spill_centers"), arrays.centers.shape[0])
+    final_nn = plan.num_neighbors
+    pre = cfgmod.as_int(plan.reordering.get("approx_num_neighbors"), final_nn) if plan.reordering is not None else final_nn
+    self._arrays = arrays
+    self._plan = plan
+    self._n, self._d = arrays.n, arrays.d
+    self._index = _lib.NativeIndex(arrays, leaves, pre, final_nn)
+
+  def _load(self, artifacts_dir, assets_pbtxt):
+    L = _lib.lib()
+    h = C.c_void_p()
+    rc = L.scann_b200_assets_load(artifacts_dir.encode(), assets_pbtxt.encode(), C.byref(h))
+    if rc:
+      raise RuntimeError("Error loading artifacts: " + L.scann_b200_last_error().decode("utf-8", "replace"))
+    try:
+      desc = _lib.IndexDesc()
+      rc = L.scann_b200_assets_describe(h, C.byref(desc))
+      if rc:
+        raise RuntimeError("Error loading artifacts: " + L.scann_b200_last_error().decode("utf-8", "replace"))
+      self._config_text = L.scann_b200_assets_config(h).decode()
+      plan = _Plan(self._config_text)
+      plan.check_supported()
+      arrays = _arrays_from_desc(desc, plan)
+      self._finish(arrays, plan)
+    except _lib.ScannB200Error as e:
+      raise _runtime("Error loading artifacts: ", e)
+    finally:
+      L.scann_b200_assets_free(h)
+
+  # ---- queries (scann_npy.cc:209-270) ----
+  def search(self, q, final_nn, pre_reorder_nn, leaves):
+    q = np.asarray(q)
+    if q.ndim != 1:
+      raise ValueError("Query must be one-dimensional")
+    idx, dist = self.search_batched(q[None, :], final_nn, pre_reorder_nn, leaves, False, 0)
+    valid = ~np.isnan(dist[0])
+    return idx[0][valid], dist[0][valid]
+
+  def search_batched(self, queries, final_nn, pre_reorder_nn, leaves, parallel=False, batch_size=256):
+    del parallel, batch_size  # one GPU path; the CPU library's thread fan-out has no analogue here
+    queries = np.asarray(queries)
+    if queries.ndim != 2:
+      raise ValueError("Queries must be in two-dimensional array")
+    if queries.shape[1] != self._d:
+      raise RuntimeError("Error during search: Query doesn't match dataset dimsensionality")  # scann.cc:467-468
+    try:
+      return self._index.search_batched(queries, final_nn, pre_reorder_nn, leaves)
+    except _lib.ScannB200Error as e:
+      raise _runtime("Error during search: ", e)
+
+  # ---- serialization (scann_npy.cc:272-282) ----
+  def serialize(self, path, relative_path=False):
+    a = self._arrays
+    L = _lib.lib()
+    keep = []
+
+    def own(x, dt):
+      if x is None:
+        return None
+      y = np.ascontiguousarray(x, dtype=dt)
+      keep.append(y)
+      return _lib.ptr(y)
+
+    d = _lib.IndexDesc()
+    d.distance = 0 if a.distance == "dot_product" else 1
+    d.n, d.d = a.n, a.d
+    d.n_leaves, d.n_blocks, d.dims_per_block = a.centers.shape[0], a.codes.shape[1], a.codebook.shape[2]
+    d.block_dims = own(a.block_dims, np.int32)
+    d.centers = own(a.centers, np.float32)
+    d.tokens = own(a.tokens, np.int32)
+    d.soar = 1 if a.soar else 0
+    d.codes = own(a.codes, np.uint8)
+    d.soar_codes = own(a.soar_codes, np.uint8)
+    d.codebook = own(a.codebook, np.float32)
+    d.dataset = own(a.dataset, np.float32)
+    d.overretrieve = a.overretrieve
+    buf = C.create_string_buffer(1 << 16)
+    rc = L.scann_b200_assets_save(path.encode(), C.byref(d), self._config_text.encode(), 1 if relative_path else 0,
+                                  buf, len(buf))
+    if rc:
+      raise RuntimeError("Failed to extract SingleMachineFactoryOptions: " + L.scann_b200_last_error().decode())
+    with open(os.path.join(path, "scann_assets.pbtxt"), "w") as f:
+      f.write(buf.value.decode())
+
+  # ---- misc surface ----
+  def config(self):
+    return self._config_text
+
+  def size(self):
+    return self._n
+
+  def set_num_threads(self, num_threads):
+    del num_threads
+
+  def stats(self):
+    return self._index.stats()
+
+  def _unsupported(self, what):
+    raise RuntimeError(f"{what} is not supported by the scann_b200 query path (out of scope, SURVEY.md section 8)")
+
+  def upsert(self, *a, **k):
+    self._unsupported("upsert")
+
+  def delete(self, *a, **k):
+    self._unsupported("delete")
+
+  def rebalance(self, *a, **k):
+    self._unsupported("rebalance")
+
+  def reserve(self, *a, **k):
+    self._unsupported("reserve")
+
+  def get_health_stats(self):
+    self._unsupported("get_health_stats")
+
+  def initialize_health_stats(self):
+    self._unsupported("initialize_health_stats")
+
+  @staticmethod
+  def suggest_autopilot(config, n, dim):
+    raise RuntimeError("suggest_autopilot is not supported by the scann_b200 query path")
+
+
+def _arrays_from_desc(desc, plan):
+  """Copies the arrays a loaded-assets descriptor points at into an IndexArrays."""
+
+  def arr(ptr, shape, dt):
+    if not ptr:
+      return None
+    n = int(np.prod(shape))
+    buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dt).reshape(shape).copy()
+
+  n, d, L, B, S = desc.n, desc.d, desc.n_leaves, desc.n_blocks, desc.dims_per_block
+  a = index_build.IndexArrays(distance="dot_product" if desc.distance == 0 else "squared_l2", dataset=None, n=n, d=d)
+  a.dataset = arr(desc.dataset, (n, d), np.float32)
+  a.centers = arr(desc.centers, (L, d), np.float32)
+  a.soar = bool(desc.soar)
+  a.tokens = arr(desc.tokens, (n * (2 if a.soar else 1),), np.int32)
+  a.codes = arr(desc.codes, (n, B), np.uint8)
+  a.soar_codes = arr(desc.soar_codes, (n, B), np.uint8)
+  a.codebook = arr(desc.codebook, (B, 16, S), np.float32)
+  a.block_dims = arr(desc.block_dims, (B,), np.int32)
+  a.overretrieve = float(desc.overretrieve)
+  a.residual = True
+  return a
