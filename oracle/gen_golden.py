@@ -20,6 +20,7 @@ CASES = {
     "dot_b16": dict(n=2000, d=32, leaves=16, dpb=2, soar=None, probe=4, pre=40, k=10, seed=21),
     "dot_soar_b25": dict(n=1500, d=50, leaves=12, dpb=2, soar=1.5, probe=5, pre=30, k=10, seed=22),
     "dot_varchunk_b11": dict(n=1200, d=32, leaves=10, dpb=3, soar=None, probe=3, pre=25, k=5, seed=23),
+    "l2_b16": dict(n=2000, d=32, leaves=16, dpb=2, soar=None, probe=4, pre=40, k=10, seed=24, distance="squared_l2"),
 }
 
 
@@ -29,7 +30,7 @@ def main():
   for name, c in CASES.items():
     db = datasets.clustered(c["n"], c["d"], 4 * c["leaves"], seed=c["seed"], centers_seed=100 + c["seed"])
     q = datasets.clustered(24, c["d"], 4 * c["leaves"], seed=c["seed"] + 1, centers_seed=100 + c["seed"])
-    a = index_build.build_tree_ah(db, "dot_product", num_leaves=c["leaves"], dims_per_block=c["dpb"],
+    a = index_build.build_tree_ah(db, c.get("distance", "dot_product"), num_leaves=c["leaves"], dims_per_block=c["dpb"],
                                   training_sample_size=c["n"], soar_lambda=c["soar"], tree_iters=5, ah_iters=5,
                                   device="cpu")
     oi = oracle.OracleIndex(a, c["probe"], c["pre"], c["k"])
@@ -42,7 +43,7 @@ def main():
         os.path.join(out_dir, name + ".npz"),
         dataset=db, queries=q, centers=a.centers, tokens=a.tokens, codes=a.codes,
         soar_codes=a.soar_codes if a.soar_codes is not None else np.zeros((0, 0), np.uint8),
-        codebook=a.codebook, block_dims=a.block_dims, soar=np.int32(1 if a.soar else 0),
+        codebook=a.codebook, block_dims=a.block_dims, soar=np.int32(1 if a.soar else 0), distance=np.str_(a.distance),
         overretrieve=np.float32(a.overretrieve), probe=np.int32(c["probe"]), pre=np.int32(c["pre"]), k=np.int32(c["k"]),
         exp_leaf=leaf, exp_center_dist=cdist, exp_lut=lut, exp_mult=mult, exp_scores_q0_leaf0=scores0,
         exp_cand_count=cand["count"], exp_cand_leaf=cand["leaf"], exp_cand_slot=cand["slot"],

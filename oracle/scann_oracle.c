@@ -507,6 +507,20 @@ static inline float ah_float_score(int32_t acc, float inv_mult, float bias) {
   return m + bias;
 }
 
+/* Dot-product tree-AH (TreeAHHybridResidual): inv = float(1.0 / double(mult)) (lut16_avx2.inc:429),
+ * ties broken by the packed (leaf, slot) global-top-N index (tree_ah_hybrid_residual.h:234-247).
+ * Squared-L2 tree-AH (TreeXHybridSMMD, non-residual codes): per-leaf int16 top-N, then
+ * dist = acc * (1.0f / mult) with NO bias (hashes/asymmetric_hashing2/querying.h:450-455), pushed
+ * into the per-query FastTopNeighbors<float> under GLOBAL datapoint ids
+ * (base/single_machine_base.cc:759-808), so ties are broken by datapoint id. */
+static inline float inv_multiplier(const so_index* ix, float mult) {
+  if (ix->d.distance == SO_SQUARED_L2) return 1.0f / mult;
+  return (float)(1.0 / (double)mult);
+}
+static inline uint32_t tie_index(const so_index* ix, uint32_t gslot) {
+  return ix->d.distance == SO_SQUARED_L2 ? ix->leaf_dp[gslot] : gslot;
+}
+
 /* exact top-N collector on (score, global slot) keys: the contract of SURVEY 7.1 /
  * utils/fast_top_neighbors.h:90-118,530-548 FinishUnsorted (N smallest, ties -> smaller
  * index).  Buffer of 2N like the reference; threshold tightened on every collection. */
@@ -561,11 +575,11 @@ static void scan_leaf_scalar(const so_index* ix, uint32_t leaf, const uint8_t* l
                              float bias, topn_t* tn) {
   const uint32_t B = ix->d.n_blocks;
   const uint32_t base = ix->leaf_off[leaf], n = ix->leaf_off[leaf + 1] - base;
-  const float inv_mult = (float)(1.0 / (double)mult);
+  const float inv_mult = inv_multiplier(ix, mult);
   for (uint32_t s = 0; s < n; ++s) {
     int32_t acc = score_slot(lut, ix->slot_codes + (size_t)(base + s) * B, B);
     float sc = ah_float_score(acc, inv_mult, bias);
-    topn_push(tn, ((uint64_t)f2ord(sc) << 32) | (base + s));
+    topn_push(tn, ((uint64_t)f2ord(sc) << 32) | tie_index(ix, base + s));
   }
 }
 
@@ -639,7 +653,7 @@ static void scan_leaf_avx2(const so_index* ix, uint32_t leaf, int nqb, const uin
   int32_t thr[SO_MAXQ];
   uint64_t seen_thr[SO_MAXQ];
   for (int j = 0; j < nqb; ++j) {
-    inv[j] = (float)(1.0 / (double)mults[j]);
+    inv[j] = inv_multiplier(ix, mults[j]);
     seen_thr[j] = tns[j]->thr;
     thr[j] = int_threshold(seen_thr[j], mults[j], inv[j], biases[j]);
   }
@@ -660,7 +674,7 @@ static void scan_leaf_avx2(const so_index* ix, uint32_t leaf, int nqb, const uin
         uint32_t bit = o < 16 ? (m0 >> (2 * o)) & 1 : (m1 >> (2 * (o - 16))) & 1;
         if (!bit) continue;
         float s = ah_float_score(sc[j][o], inv[j], biases[j]);
-        topn_push(tns[j], ((uint64_t)f2ord(s) << 32) | (base + 32 * g + o));
+        topn_push(tns[j], ((uint64_t)f2ord(s) << 32) | tie_index(ix, base + 32 * g + o));
         if (tns[j]->thr != seen_thr[j]) {
           seen_thr[j] = tns[j]->thr;
           thr[j] = int_threshold(seen_thr[j], mults[j], inv[j], biases[j]);
@@ -769,7 +783,9 @@ static void search_batch(const so_index* ix, const float* q, uint32_t nq, sp_t s
   for (uint32_t i = 0; i < nq; ++i)
     for (int r = 0; r < P; ++r) {
       uint32_t l = (uint32_t)leaves[(size_t)i * P + r];
-      lq[cur[l]] = i; lb[cur[l]] = biases[(size_t)i * P + r]; cur[l]++;
+      lq[cur[l]] = i;
+      lb[cur[l]] = ix->d.distance == SO_SQUARED_L2 ? 0.0f : biases[(size_t)i * P + r];
+      cur[l]++;
     }
   uint64_t bytes = 0;
   /* The reference visits leaves in descending centre-norm order (:121-143); the exact
@@ -812,7 +828,7 @@ static void finish_query(const so_index* ix, const float* q, sp_t sp, uint64_t* 
   cand_t* c = (cand_t*)malloc(sizeof(cand_t) * (n + 1));
   uint64_t* k2 = (uint64_t*)malloc(sizeof(uint64_t) * (n + 1));
   for (size_t i = 0; i < n; ++i) {
-    c[i].dp = ix->leaf_dp[(uint32_t)keys[i]];
+    c[i].dp = ix->d.distance == SO_SQUARED_L2 ? (uint32_t)keys[i] : ix->leaf_dp[(uint32_t)keys[i]];
     c[i].score = ord2f((uint32_t)(keys[i] >> 32));
   }
   size_t m = n;
@@ -887,11 +903,18 @@ int so_candidates(const so_index* ix, const float* q, uint32_t nq, int pre_nn, i
   for (uint32_t i = 0; i < nq; ++i) {
     float mult;
     lut_one(ix, q + (size_t)i * D, lut, &mult, raw);
-    const float inv = (float)(1.0 / (double)mult);
+    const float inv = inv_multiplier(ix, mult);
     size_t n = ns[i] < (size_t)cap ? ns[i] : (size_t)cap;
     out_count[i] = (uint32_t)n;
     float last = n ? ord2f((uint32_t)(keys[i][ns[i] - 1] >> 32)) : 0.0f;
     for (size_t j = 0; j < n; ++j) {
+      if (ix->d.distance == SO_SQUARED_L2) { /* keys carry the datapoint id, not the slot */
+        size_t o = (size_t)i * cap + j;
+        out_leaf[o] = 0xFFFFFFFFu; out_slot[o] = 0xFFFFFFFFu; out_acc[o] = 0;
+        out_dp[o] = (uint32_t)keys[i][j];
+        out_score[o] = ord2f((uint32_t)(keys[i][j] >> 32));
+        continue;
+      }
       uint32_t gs = (uint32_t)keys[i][j];
       uint32_t lo = 0, hi = L; /* leaf of global slot */
       while (hi - lo > 1) { uint32_t mid = (lo + hi) / 2; if (ix->leaf_off[mid] <= gs) lo = mid; else hi = mid; }

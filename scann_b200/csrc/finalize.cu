@@ -106,9 +106,10 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
       if (i < n) {
         const uint64_t s = src[i];
         const uint32_t gslot = (uint32_t)s;
-        const uint32_t dp = ix.slot_dp[gslot];
+        const uint32_t dp = ix.key_by_dp ? gslot : ix.slot_dp[gslot];
         a.part_ids[o] = dp;
-        a.part_tie[o] = (s & 0xFFFFFFFF00000000ull) | (ix.slot_tie ? ix.slot_tie[gslot] : gslot);
+        a.part_tie[o] = ix.key_by_dp ? s
+                                     : ((s & 0xFFFFFFFF00000000ull) | (ix.slot_tie ? ix.slot_tie[gslot] : gslot));
         a.part_ah[o] = ord2f((uint32_t)(s >> 32));
         a.part_exact[o] = reorder ? exact_distance(ix, sq, dp) : ord2f((uint32_t)(s >> 32));
       } else {
@@ -128,7 +129,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
       uint64_t k = kKeyMax;
       if ((uint32_t)i < n) {
         const uint64_t s = src[i];
-        k = (s & 0xFFFFFFFF00000000ull) | ix.slot_dp[(uint32_t)s];
+        k = ix.key_by_dp ? s : ((s & 0xFFFFFFFF00000000ull) | ix.slot_dp[(uint32_t)s]);
       }
       kb[i] = k;
     }

@@ -187,6 +187,8 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     }
   }
   v.disjoint = disjoint;
+  v.key_by_dp = d->distance == SCANN_B200_SQUARED_L2 ? 1 : 0;
+  if (v.key_by_dp && d->soar) return fail(SCANN_B200_INVALID_ARGUMENT, "SOAR requires dot product distance.");
   ix->h_leaf_size = lsize;
 
   std::vector<int32_t> bdims(B);
@@ -653,12 +655,18 @@ int scann_b200_debug_candidates(scann_b200_index* ix, const float* queries, uint
     out_count[i] = n;
     for (uint32_t j = 0; j < n; ++j) {
       const uint64_t k = keys[(size_t)i * dcap + j];
-      const uint32_t gs = (uint32_t)k, g = gs / 32;
-      const uint32_t leaf = (uint32_t)(std::upper_bound(goff.begin(), goff.end(), g) - goff.begin()) - 1;
       const size_t o = (size_t)i * cap + j;
-      out_leaf[o] = leaf;
-      out_slot[o] = gs - goff[leaf] * 32;
-      out_dp[o] = sdp[gs];
+      if (v.key_by_dp) {  // squared-L2 keys carry the datapoint id instead of the slot
+        out_leaf[o] = 0xFFFFFFFFu;
+        out_slot[o] = 0xFFFFFFFFu;
+        out_dp[o] = (uint32_t)k;
+      } else {
+        const uint32_t gs = (uint32_t)k, g = gs / 32;
+        const uint32_t leaf = (uint32_t)(std::upper_bound(goff.begin(), goff.end(), g) - goff.begin()) - 1;
+        out_leaf[o] = leaf;
+        out_slot[o] = gs - goff[leaf] * 32;
+        out_dp[o] = sdp[gs];
+      }
       uint32_t ord = (uint32_t)(k >> 32);
       uint32_t u = (ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord;
       memcpy(&out_score[o], &u, 4);

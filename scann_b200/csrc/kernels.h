@@ -15,6 +15,9 @@ struct DevIndex {
   int distance;
   uint32_t n, d, L, B, W, dpb;
   int disjoint;
+  // Squared-L2 tree-AH (TreeXHybridSMMD semantics): no bias, inv = 1.0f / mult, candidate keys are
+  // (score, datapoint id) instead of (score, global slot).  See oracle/scann_oracle.c tie_index().
+  int key_by_dp;
   const float* centers;       // [L][D]
   const float* centers_t;     // [D][L] (unused by the kernels, kept for debugging)
   const float* center_sqnorm; // [L] squared-L2 tokenization only

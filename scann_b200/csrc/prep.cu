@@ -246,7 +246,8 @@ lut_kernel(DevIndex ix, const float* __restrict__ q, uint8_t* __restrict__ lut,
     const float mult = __fdiv_rn(127.0f, denom);
     s_mult = mult;
     mult_out[qi] = mult;
-    inv_out[qi] = (float)(1.0 / (double)mult);
+    // lut16_avx2.inc:429 (dot, double division) vs querying.h:450 (squared L2, 1.0f / mult)
+    inv_out[qi] = ix.key_by_dp ? __fdiv_rn(1.0f, mult) : (float)(1.0 / (double)mult);
   }
   __syncthreads();
   const float mult = s_mult;

@@ -139,7 +139,7 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   for (; r < w.P; ++r) {
     const int leaf = w.leaves[(size_t)q * w.P + r];
     if (leaf < 0) break;
-    const float bias = w.bias[(size_t)q * w.P + r];
+    const float bias = ix.key_by_dp ? 0.f : w.bias[(size_t)q * w.P + r];
     const uint32_t n = ix.leaf_size[leaf];
     const uint32_t gbeg = ix.leaf_goff[leaf], ng = ix.leaf_goff[leaf + 1] - gbeg;
     __syncthreads();
@@ -156,7 +156,8 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
         bool p = (g * 32 + lane < n) && s0 <= s_thr;
         uint64_t key = 0;
         if (p) {
-          key = make_key(ah_float_score(s0 - off128, inv, bias), (gbeg + g) * 32 + lane);
+          const uint32_t gslot = (gbeg + g) * 32 + lane;
+          key = make_key(ah_float_score(s0 - off128, inv, bias), ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
           p = key < s_tau;
         }
         const uint32_t m = __ballot_sync(kFull, p);
@@ -359,7 +360,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       int thr = -1;
       if ((uint32_t)tid < ecount) {
         qq = w.entry_q[ebase + tid];
-        const float bias = w.entry_bias[ebase + tid];
+        const float bias = ix.key_by_dp ? 0.f : w.entry_bias[ebase + tid];
         const uint64_t tau = w.tau[qq];
         const float inv = w.inv_mult[qq];
         thr = acc_threshold(tau, w.mult[qq], inv, bias) + off128;
@@ -405,7 +406,8 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
             bool p = pv[i];
             uint64_t key = 0;
             if (p) {
-              key = make_key(ah_float_score(sv[i] - off128, s_inv[qi], s_bias[qi]), gslot);
+              key = make_key(ah_float_score(sv[i] - off128, s_inv[qi], s_bias[qi]),
+                             ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
               p = key < s_tau[qi];
             }
             const uint32_t m = __ballot_sync(kFull, p);

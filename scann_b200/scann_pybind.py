@@ -60,10 +60,11 @@ class _Plan:
       unimpl("lut256 / non-LUT16 asymmetric hashing")
     if ah.path("projection", "projection_type") not in ("CHUNK", "VARIABLE_CHUNK"):
       unimpl("AH projections other than CHUNK / VARIABLE_CHUNK")
-    if self.distance == "squared_l2":
-      unimpl("squared-L2 tree-AH (TreeXHybridSMMD)")
-    if not cfgmod.as_bool(ah.get("use_residual_quantization"), False):
-      unimpl("non-residual tree-AH")
+    residual = cfgmod.as_bool(ah.get("use_residual_quantization"), False)
+    if self.distance == "dot_product" and not residual:
+      unimpl("non-residual dot-product tree-AH")
+    if self.distance == "squared_l2" and residual:
+      unimpl("residual squared-L2 tree-AH")
     r = self.reordering
     if r is not None:
       if cfgmod.as_bool(r.path("fixed_point", "enabled"), False) or cfgmod.as_bool(r.path("bfloat16", "enabled"), False):

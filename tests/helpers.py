@@ -14,14 +14,15 @@ def golden_names():
 def load_golden(name):
   from scann_b200 import index_build
   z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
-  a = index_build.IndexArrays(distance="dot_product", dataset=z["dataset"], n=z["dataset"].shape[0],
+  dist = str(z["distance"]) if "distance" in z.files else "dot_product"
+  a = index_build.IndexArrays(distance=dist, dataset=z["dataset"], n=z["dataset"].shape[0],
                               d=z["dataset"].shape[1])
   a.centers, a.tokens, a.codes = z["centers"], z["tokens"], z["codes"]
   a.codebook, a.block_dims = z["codebook"], z["block_dims"]
   a.soar = bool(int(z["soar"]))
   a.soar_codes = z["soar_codes"] if a.soar else None
   a.overretrieve = float(z["overretrieve"])
-  a.residual = True
+  a.residual = dist == "dot_product"
   return a, z
 
 

@@ -14,6 +14,8 @@ CASES = [
     dict(dpb=8, d=128, leaves=32, n=6000),          # B=16, AVX2-order LUT path
     dict(soar=1.5),                                 # SOAR spilled leaves + dedup
     dict(n=3000, leaves=300, probe=40, pre=150),    # tiny / empty leaves, pilot spans many leaves
+    dict(distance="squared_l2", d=64, leaves=50, n=10000),           # TreeXHybridSMMD semantics (C4 shape family)
+    dict(distance="squared_l2", d=30, dpb=4, leaves=20, n=5000, probe=6, pre=64),
 ]
 
 
@@ -70,7 +72,11 @@ def test_search_batched_ids_and_distances(kw):
   np.testing.assert_array_equal(i0, i1)
   np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
   # float distances within 1e-5 relative of a float64 recomputation (north star tolerance)
-  truth = np.einsum("qd,qkd->qk", c.q.astype(np.float64), c.db[i1.astype(np.int64)].astype(np.float64))
+  rows = c.db[i1.astype(np.int64)].astype(np.float64)
+  if c.arrays.distance == "dot_product":
+    truth = np.einsum("qd,qkd->qk", c.q.astype(np.float64), rows)
+  else:
+    truth = ((c.q.astype(np.float64)[:, None, :] - rows) ** 2).sum(-1)
   np.testing.assert_allclose(d1, truth, rtol=1e-5, atol=1e-5)
 
 

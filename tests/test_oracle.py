@@ -89,6 +89,19 @@ def test_recall_against_brute_force():
   assert rec > 0.9
 
 
+def test_squared_l2_recall_and_distances():
+  a, z = load_golden("l2_b16")
+  oi = oracle.OracleIndex(a, 8, 100, 10)
+  q = z["queries"]
+  idx, dist = oi.search_batched(q)
+  d2 = ((q.astype(np.float64)[:, None, :] - a.dataset.astype(np.float64)[None, :, :]) ** 2).sum(-1)
+  truth = np.argsort(d2, axis=1)[:, :10]
+  rec = np.mean([len(set(idx[i].tolist()) & set(truth[i].tolist())) / 10 for i in range(len(q))])
+  assert rec > 0.9
+  np.testing.assert_allclose(dist, np.take_along_axis(d2, idx.astype(np.int64), axis=1), rtol=1e-5)
+  assert (np.diff(dist, axis=1) >= 0).all()          # ascending squared distances, not negated
+
+
 def test_padding_when_fewer_candidates_than_k():
   a, z = load_golden("dot_b16")
   oi = oracle.OracleIndex(a, 1, 5, 10)
