@@ -29,6 +29,50 @@ __device__ __forceinline__ float exact_distance(const DevIndex& ix, const float*
   return ix.d < 8 ? sql2_small(lq, lx, ix.d) : sql2_avx2_order(lq, lx, ix.d);
 }
 
+// The same arithmetic as exact_distance (dims >= 8), spread over 8 consecutive lanes: lane l
+// owns AVX lane l of the reference kernel (one_to_many_symmetric.h:373-503), so a row's 32-byte
+// sectors are fetched by 8 threads at once instead of one thread walking the row.  All 32 lanes
+// of the warp must call this together; the result is valid in the lanes with l == 0.
+__device__ __forceinline__ float exact_distance_lanes8(const DevIndex& ix, const float* __restrict__ q,
+                                                       uint32_t dp, int l) {
+  const uint32_t row = ix.dp_row ? ix.dp_row[dp] : dp;
+  const float* __restrict__ x = ix.dataset + (size_t)row * ix.d;
+  const uint32_t n = ix.d;
+  const bool dot = ix.distance == 0;
+  float a = 0.f;
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8) {
+    const float xv = __ldg(x + j + l), qv = q[j + l];
+    if (dot) a = __fmaf_rn(-qv, xv, a);
+    else { const float t = __fsub_rn(qv, xv); a = __fmaf_rn(t, t, a); }
+  }
+  float b = __fadd_rn(__shfl_down_sync(0xFFFFFFFFu, a, 4, 8), a);  // lanes 0..3: a[l+4] + a[l]
+  if (j + 4 <= n) {
+    if (l < 4) {
+      const float xv = __ldg(x + j + l), qv = q[j + l];
+      if (dot) b = __fmaf_rn(-qv, xv, b);
+      else { const float t = __fsub_rn(qv, xv); b = __fmaf_rn(t, t, b); }
+    }
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    if (l == 2 || l == 3) {
+      const float xv = __ldg(x + j + (l - 2)), qv = q[j + (l - 2)];
+      if (dot) b = __fmaf_rn(-qv, xv, b);
+      else { const float t = __fsub_rn(qv, xv); b = __fmaf_rn(t, t, b); }
+    }
+    j += 2;
+  }
+  const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));   // lanes 0,1: b0+b2, b1+b3
+  float r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));        // lane 0: (b0+b2)+(b1+b3)
+  if (j < n && l == 0) {
+    const float xv = __ldg(x + j), qv = q[j];
+    if (dot) r = __fmaf_rn(-qv, xv, r);
+    else { const float t = __fsub_rn(qv, xv); r = __fmaf_rn(t, t, r); }
+  }
+  return r;
+}
+
 // Bitonic sort of (u64 key, u32 payload) pairs in shared memory.
 __device__ __forceinline__ void block_bitonic_sort_kv(uint64_t* s, uint32_t* pay, int n) {
   for (int k = 2; k <= n; k <<= 1) {
@@ -111,12 +155,24 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
         a.part_tie[o] = ix.key_by_dp ? s
                                      : ((s & 0xFFFFFFFF00000000ull) | (ix.slot_tie ? ix.slot_tie[gslot] : gslot));
         a.part_ah[o] = ord2f((uint32_t)(s >> 32));
-        a.part_exact[o] = reorder ? exact_distance(ix, sq, dp) : ord2f((uint32_t)(s >> 32));
+        if (!reorder) a.part_exact[o] = ord2f((uint32_t)(s >> 32));
+        else if (ix.d < 8) a.part_exact[o] = exact_distance(ix, sq, dp);
       } else {
         a.part_ids[o] = kInvalidId;
         a.part_tie[o] = kKeyMax;
         a.part_ah[o] = INFINITY;
         a.part_exact[o] = INFINITY;
+      }
+    }
+    if (reorder && ix.d >= 8) {
+      const int l = tid & 7, grp = tid >> 3;
+      for (uint32_t c0 = 0; c0 < n; c0 += kFinThreads / 8) {
+        const uint32_t c = c0 + grp;
+        const bool valid = c < n;
+        const uint32_t gslot = (uint32_t)src[valid ? c : 0];
+        const uint32_t dp = ix.key_by_dp ? gslot : ix.slot_dp[gslot];
+        const float dist = exact_distance_lanes8(ix, sq, dp, l);
+        if (valid && l == 0) a.part_exact[(size_t)q * a.part_cap + c] = dist;
       }
     }
     return;
@@ -152,15 +208,25 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
     block_bitonic_sort(kb, np2);
     m = min(n - s_removed, a.npre);
   }
-  for (int i = tid; i < np2; i += kFinThreads) {
-    uint64_t k = kKeyMax;
-    if ((uint32_t)i < m) {
+  for (int i = tid; i < np2; i += kFinThreads) ka[i] = kKeyMax;
+  __syncthreads();
+  if (reorder && ix.d >= 8) {
+    // 8 lanes per candidate row, 16 rows per pass
+    const int l = tid & 7, grp = tid >> 3;
+    for (uint32_t c0 = 0; c0 < m; c0 += kFinThreads / 8) {
+      const uint32_t c = c0 + grp;
+      const bool valid = c < m;
+      const uint32_t dp = (uint32_t)kb[valid ? c : 0];
+      const float dist = exact_distance_lanes8(ix, sq, dp, l);
+      if (valid && l == 0) ka[c] = make_key(dist, dp);
+    }
+  } else {
+    for (uint32_t i = tid; i < m; i += kFinThreads) {
       const uint64_t c = kb[i];
       const uint32_t dp = (uint32_t)c;
       const float dist = reorder ? exact_distance(ix, sq, dp) : ord2f((uint32_t)(c >> 32));
-      k = make_key(dist, dp);
+      ka[i] = make_key(dist, dp);
     }
-    ka[i] = k;
   }
   __syncthreads();
   block_bitonic_sort(ka, np2);

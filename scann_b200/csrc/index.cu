@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -289,7 +290,14 @@ int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Pa
 }
 
 uint32_t pick_cap(uint32_t nover) {
-  uint32_t cap = 4096;
+  // Candidate buffer entries per query.  Big enough that the heavy tail of the candidate inflow
+  // (C2: mean 290, max 13k per query) never needs a re-scan; SCANN_B200_CAND_CAP shrinks it so
+  // that tests can exercise the overflow path.
+  uint32_t cap = 16384;
+  if (const char* e = getenv("SCANN_B200_CAND_CAP")) {
+    const long v = strtol(e, nullptr, 10);
+    if (v >= 64 && v <= (1 << 20)) { cap = 64; while (cap < (uint32_t)v) cap <<= 1; }
+  }
   while (cap < 4 * nover) cap <<= 1;
   return cap;
 }
@@ -367,7 +375,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   launches += 1; scan_launches += 1;
   CU(cudaEventRecord(ix->ev[EV_SCAN], s));
   CU(sb::launch_compact(v, w, false, s));
-  launches += 1;
+  launches += cap > 1024 ? 2 : 1;
   CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
   // overflow check: one 32-byte read back per chunk
   uint32_t* hc = ix->h_counters.as<uint32_t>();
@@ -379,7 +387,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
     sb::launch_worklist(v, w, true, s, &launches);
     CU(sb::launch_scan(v, w, 0, s));
     CU(sb::launch_compact(v, w, true, s));
-    launches += 2; scan_launches += 1;
+    launches += cap > 1024 ? 3 : 2; scan_launches += 1;
     CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
   }

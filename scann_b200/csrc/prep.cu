@@ -184,12 +184,116 @@ topp_kernel(const float* __restrict__ dist, int L, int P, int Ppow2, int32_t* __
   }
 }
 
+// Warp-per-query variant of the same selection (no block barriers): used when P <= 256, which
+// covers every configuration of BASELINE.json.  8 queries per 256-thread block.
+constexpr int kToppWarpMaxP = 256;
+
+__global__ void __launch_bounds__(256)
+topp_warp_kernel(const float* __restrict__ dist, int nq, int L, int P, int Ppow2,
+                 int32_t* __restrict__ leaves, float* __restrict__ bias) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= nq) return;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw) + warp * 256;
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 8 * 256 * 4) + (size_t)warp * Ppow2;
+  const float* row = dist + (size_t)q * L;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t prefix = 0, mask = 0, need = (uint32_t)P;
+  if (P < L) {
+    for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hist[lane * 8 + k] = 0;
+      __syncwarp();
+      for (int i = lane; i < L; i += 32) {
+        const uint32_t o = f2ord(row[i]);
+        if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+      }
+      __syncwarp();
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; tot += c[k]; }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= need);
+      const int tl = hit ? (__ffs(hit) - 1) : 31;
+      uint32_t digit = 255, nneed = need;
+      if (lane == tl) {
+        uint32_t cum = incl - tot;
+        digit = (uint32_t)lane * 8 + 7;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; break; }
+          cum += c[k];
+        }
+        nneed = need - cum;
+      }
+      digit = __shfl_sync(0xFFFFFFFFu, digit, tl);
+      need = __shfl_sync(0xFFFFFFFFu, nneed, tl);
+      prefix |= digit << shift;
+      mask |= 0xFFu << shift;
+      __syncwarp();
+    }
+  } else {
+    prefix = 0xFFFFFFFFu;
+    need = 0xFFFFFFFFu;
+  }
+  for (int i = lane; i < Ppow2; i += 32) skeys[i] = kKeyMax;
+  __syncwarp();
+  uint32_t count = 0, base_eq = 0;
+  for (int t0 = 0; t0 < L; t0 += 32) {
+    const int i = t0 + lane;
+    const bool valid = i < L;
+    const uint32_t o = valid ? f2ord(row[i]) : 0xFFFFFFFFu;
+    const bool less = valid && o < prefix;
+    const bool eq = valid && o == prefix;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, eq);
+    const uint32_t rank = base_eq + __popc(m & lt);
+    const bool take = less || (eq && rank < need);
+    const uint32_t tm = __ballot_sync(0xFFFFFFFFu, take);
+    if (take) {
+      const uint32_t pos = count + __popc(tm & lt);
+      if (pos < (uint32_t)Ppow2) skeys[pos] = ((uint64_t)o << 32) | (uint32_t)i;
+    }
+    count += __popc(tm);
+    base_eq += __popc(m);
+  }
+  __syncwarp();
+  for (int k = 2; k <= Ppow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (Ppow2 >> 1); t += 32) {
+        const int l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int r = l | j;
+        const uint64_t a = skeys[l], b = skeys[r];
+        const bool up = (l & k) == 0;
+        if ((a > b) == up) { skeys[l] = b; skeys[r] = a; }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < P; i += 32) {
+    const uint64_t k = skeys[i];
+    const uint32_t l = (uint32_t)k;
+    leaves[(size_t)q * P + i] = (k == kKeyMax) ? -1 : (int32_t)l;
+    bias[(size_t)q * P + i] = (k == kKeyMax) ? 0.f : row[l];
+  }
+}
+
 void launch_topp(const DevIndex& ix, const float* dist, uint32_t nq, uint32_t P, int32_t* leaves,
                  float* bias, cudaStream_t s) {
   int pp = 1;
   while (pp < (int)P) pp <<= 1;
   if (pp < 2) pp = 2;
-  topp_kernel<<<nq, kToppThreads, (size_t)pp * 8, s>>>(dist, (int)ix.L, (int)P, pp, leaves, bias);
+  if (pp <= kToppWarpMaxP) {
+    const size_t smem = 8 * 256 * 4 + (size_t)8 * pp * 8;
+    topp_warp_kernel<<<(nq + 7) / 8, 256, smem, s>>>(dist, (int)nq, (int)ix.L, (int)P, pp, leaves, bias);
+  } else {
+    topp_kernel<<<nq, kToppThreads, (size_t)pp * 8, s>>>(dist, (int)ix.L, (int)P, pp, leaves, bias);
+  }
 }
 
 // ---------------------------------------------------------------------------------------

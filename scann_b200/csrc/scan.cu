@@ -435,7 +435,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
 // publish the new tau.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads)
-compact_kernel(ScanWork w, int dedup) {
+compact_kernel(ScanWork w, int dedup, uint32_t lo, uint32_t hi) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* s = reinterpret_cast<uint64_t*>(smem);
   __shared__ uint32_t s_dups;
@@ -444,6 +444,9 @@ compact_kernel(ScanWork w, int dedup) {
   const uint32_t nraw = w.cnt[q];
   const uint32_t n = min(nraw, w.cap);
   const bool over = nraw > w.cap;
+  // size classes: the launch with lo == 0 handles n <= hi (small shared memory, high occupancy),
+  // the second launch the heavy tail (lo < n)
+  if (!((n > lo && n <= hi) || (lo == 0 && n == 0))) return;
   if (tid == 0 && !dedup) {  // candidate-inflow statistics of the main pass
     atomicAdd(&w.stats[2], (unsigned long long)nraw);
     atomicMax(&w.stats[3], (unsigned long long)nraw);
@@ -568,7 +571,13 @@ cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cu
   const size_t smem = (size_t)np2 * 8;
   cudaError_t e = cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  compact_kernel<<<w.nq, kScanThreads, smem, s>>>(w, dedup ? 1 : 0);
+  const uint32_t small = 1024;
+  if (w.cap <= small) {
+    compact_kernel<<<w.nq, kScanThreads, smem, s>>>(w, dedup ? 1 : 0, 0u, w.cap);
+  } else {
+    compact_kernel<<<w.nq, kScanThreads, (size_t)small * 8, s>>>(w, dedup ? 1 : 0, 0u, small);
+    compact_kernel<<<w.nq, kScanThreads, smem, s>>>(w, dedup ? 1 : 0, small, w.cap);
+  }
   return cudaGetLastError();
 }
 

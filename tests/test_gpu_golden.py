@@ -45,9 +45,18 @@ def test_overflow_rescan_is_exact():
                                 tree_iters=4, ah_iters=4, device="cpu")
   rng = np.random.default_rng(5)
   q = rng.standard_normal((40, 32)).astype(np.float32) * 3.0   # queries unlike the data
+  import os
   ix = _lib.NativeIndex(a, 150, 100, 10)
   oi = oracle.OracleIndex(a, 150, 100, 10)
-  i1, d1 = ix.search_batched(q)
   i0, d0 = oi.search_batched(q, impl=1)
+  os.environ["SCANN_B200_CAND_CAP"] = "256"     # tiny candidate buffers: force the re-scan path
+  try:
+    i1, d1 = ix.search_batched(q)
+    assert ix.stats()["overflow_retries"] >= 1
+  finally:
+    del os.environ["SCANN_B200_CAND_CAP"]
   np.testing.assert_array_equal(i0, i1)
   np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  i2, d2 = ix.search_batched(q)                  # default buffers: no re-scan needed
+  assert ix.stats()["overflow_retries"] == 0
+  np.testing.assert_array_equal(i0, i2)

@@ -14,6 +14,7 @@ CASES = [
     dict(dpb=8, d=128, leaves=32, n=6000),          # B=16, AVX2-order LUT path
     dict(soar=1.5),                                 # SOAR spilled leaves + dedup
     dict(n=3000, leaves=300, probe=40, pre=150),    # tiny / empty leaves, pilot spans many leaves
+    dict(n=6000, leaves=300, probe=300, pre=50, d=32),               # every leaf probed (P > 256: block top-P path)
     dict(distance="squared_l2", d=64, leaves=50, n=10000),           # TreeXHybridSMMD semantics (C4 shape family)
     dict(distance="squared_l2", d=30, dpb=4, leaves=20, n=5000, probe=6, pre=64),
 ]
