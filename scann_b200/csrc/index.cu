@@ -282,7 +282,7 @@ int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Pa
     const double r = (double)npre * (double)ix->desc.overretrieve;
     nover = r > 2147483647.0 ? 2147483647LL : (long long)(int)r;
   }
-  if (nover > 16384 || npre > 16384) return fail(SCANN_B200_UNIMPLEMENTED, "pre-reorder neighbours %lld > 16384 not supported", nover);
+  if (nover > 8192 || npre > 8192) return fail(SCANN_B200_UNIMPLEMENTED, "pre-reorder neighbours %lld > 8192 not supported", nover);
   if (nover < 1) nover = 1;
   if (P > 4096) return fail(SCANN_B200_UNIMPLEMENTED, "leaves_to_search %d > 4096 not supported", P);
   p->k = (uint32_t)k; p->npre = (uint32_t)npre; p->nover = (uint32_t)nover; p->P = (uint32_t)P;
@@ -298,7 +298,7 @@ uint32_t pick_cap(uint32_t nover) {
     const long v = strtol(e, nullptr, 10);
     if (v >= 64 && v <= (1 << 20)) { cap = 64; while (cap < (uint32_t)v) cap <<= 1; }
   }
-  while (cap < 4 * nover) cap <<= 1;
+  while (cap < 2 * nover) cap <<= 1;  // nover <= 8192 => cap <= 16384 keys = 128 KB of shared memory in compact_big_kernel
   return cap;
 }
 

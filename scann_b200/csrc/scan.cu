@@ -434,31 +434,21 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
 // Compact: sort one query's buffer, drop duplicate keys (re-scan mode), keep the N smallest,
 // publish the new tau.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads)
-compact_kernel(ScanWork w, int dedup, uint32_t lo, uint32_t hi) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  uint64_t* s = reinterpret_cast<uint64_t*>(smem);
-  __shared__ uint32_t s_dups;
+__device__ __forceinline__ void compact_one(const ScanWork& w, uint32_t q, int dedup, uint64_t* s,
+                                            uint32_t* s_dups) {
   const int tid = threadIdx.x;
-  const uint32_t q = blockIdx.x;
   const uint32_t nraw = w.cnt[q];
   const uint32_t n = min(nraw, w.cap);
   const bool over = nraw > w.cap;
-  // size classes: the launch with lo == 0 handles n <= hi (small shared memory, high occupancy),
-  // the second launch the heavy tail (lo < n)
-  if (!((n > lo && n <= hi) || (lo == 0 && n == 0))) return;
-  if (tid == 0 && !dedup) {  // candidate-inflow statistics of the main pass
-    atomicAdd(&w.stats[2], (unsigned long long)nraw);
-    atomicMax(&w.stats[3], (unsigned long long)nraw);
-  }
   if (n == 0 || (dedup && w.ovf[q] == 0)) {  // re-scan passes only touch flagged queries
+    __syncthreads();
     if (tid == 0) w.ovf[q] = 0;
     return;
   }
   int np2 = 2;
   while ((uint32_t)np2 < n) np2 <<= 1;
   for (int i = tid; i < np2; i += kScanThreads) s[i] = (uint32_t)i < n ? w.buf[(size_t)q * w.cap + i] : kKeyMax;
-  if (tid == 0) s_dups = 0;
+  if (tid == 0) *s_dups = 0;
   __syncthreads();
   block_bitonic_sort(s, np2);
   uint32_t nuniq = n;
@@ -472,10 +462,10 @@ compact_kernel(ScanWork w, int dedup, uint32_t lo, uint32_t hi) {
       if (dup) { s[i] = kKeyMax; ++mine; }
       __syncthreads();
     }
-    if (mine) atomicAdd(&s_dups, mine);
+    if (mine) atomicAdd(s_dups, mine);
     __syncthreads();
-    nuniq = n - s_dups;
-    if (s_dups) block_bitonic_sort(s, np2);
+    nuniq = n - *s_dups;
+    if (*s_dups) block_bitonic_sort(s, np2);
   }
   const uint32_t keep = min(nuniq, w.nover);
   for (uint32_t i = tid; i < keep; i += kScanThreads) w.buf[(size_t)q * w.cap + i] = s[i];
@@ -484,6 +474,37 @@ compact_kernel(ScanWork w, int dedup, uint32_t lo, uint32_t hi) {
     w.tau[q] = (keep >= w.nover) ? s[w.nover - 1] : kKeyMax;
     w.ovf[q] = over ? 1u : 0u;
     if (over) atomicAdd(&w.counters[2], 1u);
+  }
+}
+
+// Common case: one CTA per query, shared memory for `hi` keys only (high occupancy).  Queries
+// with more buffered candidates are appended to a list (w.entry_q is free after the scan) and
+// handled by compact_big_kernel with a handful of large-shared-memory CTAs.
+__global__ void __launch_bounds__(kScanThreads)
+compact_small_kernel(ScanWork w, int dedup, uint32_t hi) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t s_dups;
+  const uint32_t q = blockIdx.x;
+  const uint32_t nraw = w.cnt[q];
+  if (threadIdx.x == 0 && !dedup) {  // candidate-inflow statistics of the main pass
+    atomicAdd(&w.stats[2], (unsigned long long)nraw);
+    atomicMax(&w.stats[3], (unsigned long long)nraw);
+  }
+  if (min(nraw, w.cap) > hi) {
+    if (threadIdx.x == 0) w.entry_q[atomicAdd(&w.counters[4], 1u)] = q;
+    return;
+  }
+  compact_one(w, q, dedup, reinterpret_cast<uint64_t*>(smem), &s_dups);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+compact_big_kernel(ScanWork w, int dedup) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t s_dups;
+  const uint32_t nbig = w.counters[4];
+  for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
+    compact_one(w, w.entry_q[i], dedup, reinterpret_cast<uint64_t*>(smem), &s_dups);
+    __syncthreads();
   }
 }
 
@@ -568,15 +589,15 @@ cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cu
   (void)ix;
   int np2 = 2;
   while ((uint32_t)np2 < w.cap) np2 <<= 1;
-  const size_t smem = (size_t)np2 * 8;
-  cudaError_t e = cudaFuncSetAttribute(compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const uint32_t small = (uint32_t)np2 < 1024u ? (uint32_t)np2 : 1024u;
+  cudaError_t e = cudaMemsetAsync(w.counters + 4, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  const uint32_t small = 1024;
-  if (w.cap <= small) {
-    compact_kernel<<<w.nq, kScanThreads, smem, s>>>(w, dedup ? 1 : 0, 0u, w.cap);
-  } else {
-    compact_kernel<<<w.nq, kScanThreads, (size_t)small * 8, s>>>(w, dedup ? 1 : 0, 0u, small);
-    compact_kernel<<<w.nq, kScanThreads, smem, s>>>(w, dedup ? 1 : 0, small, w.cap);
+  compact_small_kernel<<<w.nq, kScanThreads, (size_t)small * 8, s>>>(w, dedup ? 1 : 0, small);
+  if ((uint32_t)np2 > small) {
+    const size_t smem = (size_t)np2 * 8;
+    e = cudaFuncSetAttribute(compact_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    compact_big_kernel<<<296, kScanThreads, smem, s>>>(w, dedup ? 1 : 0);
   }
   return cudaGetLastError();
 }
