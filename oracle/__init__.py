@@ -190,3 +190,18 @@ class OracleIndex:
   @staticmethod
   def last_scan_bytes():
     return int(lib().so_last_scan_bytes())
+
+
+def bruteforce_bf16(db_bf16, q, k, threads=1):
+  """Exact bf16 brute force on the CPU: db_bf16 [N, D] int16 (bf16 bits), q [nq, D] f32."""
+  L = lib()
+  L.so_bruteforce_bf16.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_int]
+  db = np.ascontiguousarray(db_bf16, dtype=np.int16)
+  q = np.ascontiguousarray(q, dtype=np.float32)
+  idx = np.empty((q.shape[0], k), np.uint32)
+  dist = np.empty((q.shape[0], k), np.float32)
+  rc = L.so_bruteforce_bf16(_p(db), db.shape[0], db.shape[1], _p(q), q.shape[0], k, _p(idx), _p(dist), threads)
+  if rc:
+    raise RuntimeError(L.so_last_error().decode())
+  return idx, dist

@@ -934,3 +934,70 @@ int so_candidates(const so_index* ix, const float* q, uint32_t nq, int pre_nn, i
   free(lut); free(raw); free(keys); free(ns);
   return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/* bfloat16 brute force (config C3)                                           */
+/* ------------------------------------------------------------------------- */
+
+/* utils/bfloat16_helpers.h:30-48 (Bfloat16Decompress): bits << 16. */
+static inline float bf16_to_f32(int16_t b) {
+  uint32_t u = (uint32_t)(uint16_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+/* brute_force/bfloat16_brute_force.cc:131-147: dist_i = -sum_d q[d] * f32(bf16 x[i][d]) with an f32
+ * query and f32 accumulation, over ALL rows, then the k smallest (distance, index).
+ * The lane order of OneToManyBf16FloatImpl (one_to_many_asymmetric_impl.inc) is not part of the
+ * contract (the north star states recall@k equality for bf16 brute force); the oracle uses the
+ * same 8-lane FMA order as the float reorder kernel so that the GPU re-scoring can be bit-exact. */
+static float neg_dot_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n) {
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8)
+    for (int l = 0; l < 8; ++l) a[l] = fmaf(-q[j + l], bf16_to_f32(x[j + l]), a[l]);
+  float b[4];
+  for (int l = 0; l < 4; ++l) b[l] = a[l + 4] + a[l];
+  if (j + 4 <= n) {
+    for (int l = 0; l < 4; ++l) b[l] = fmaf(-q[j + l], bf16_to_f32(x[j + l]), b[l]);
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    b[2] = fmaf(-q[j], bf16_to_f32(x[j]), b[2]);
+    b[3] = fmaf(-q[j + 1], bf16_to_f32(x[j + 1]), b[3]);
+    j += 2;
+  }
+  float r = (b[0] + b[2]) + (b[1] + b[3]);
+  if (j < n) r = fmaf(-q[j], bf16_to_f32(x[j]), r);
+  return r;
+}
+
+int so_bruteforce_bf16(const int16_t* db, uint32_t n, uint32_t d, const float* q, uint32_t nq, int k,
+                       uint32_t* out_idx, float* out_dist, int threads) {
+  if (k <= 0) return fail("k must be positive");
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 1 ? threads : 1)
+#endif
+  for (uint32_t i = 0; i < nq; ++i) {
+    topn_t tn;
+    topn_init(&tn, (size_t)k);
+    const float* qi = q + (size_t)i * d;
+    for (uint32_t r = 0; r < n; ++r) {
+      float dist = neg_dot_bf16_avx2_order(qi, db + (size_t)r * d, d);
+      topn_push(&tn, ((uint64_t)f2ord(dist) << 32) | r);
+    }
+    topn_finish(&tn);
+    for (int j = 0; j < k; ++j) {
+      if ((size_t)j < tn.n) {
+        out_idx[(size_t)i * k + j] = (uint32_t)tn.buf[j];
+        out_dist[(size_t)i * k + j] = -ord2f((uint32_t)(tn.buf[j] >> 32));
+      } else {
+        out_idx[(size_t)i * k + j] = 0;
+        out_dist[(size_t)i * k + j] = NAN;
+      }
+    }
+    free(tn.buf);
+  }
+  return 0;
+}

@@ -1,0 +1,355 @@
+// bruteforce.cu -- bf16 brute-force MIPS scoring as a tcgen05 / TMEM tensor-core GEMM fed by TMA,
+// with the top-k pre-filter fused into the TMEM epilogue.
+//
+// Replaces (a12) of SURVEY.md section 8:
+//   Bfloat16BruteForceSearcher::FindNeighborsImpl   brute_force/bfloat16_brute_force.cc:101-152
+//   OneToManyBf16FloatImpl                          distance_measures/one_to_many/one_to_many_asymmetric_impl.inc
+//   FastTopNeighbors::PushBlock                      utils/fast_top_neighbors.h:394-440
+// The reference streams the whole bf16 database once PER QUERY (f32 query x bf16 row, f32
+// accumulate).  Here a batch of queries is one GEMM  S[q][i] = sum_d q[d] * x[i][d]:
+//   * the f32 query is split into two bf16 terms (hi + lo, 16 mantissa bits) stacked as two
+//     A operands; both MMAs accumulate into the same fp32 TMEM tile, so the approximate score
+//     is within ~2^-16 relative of the f32-query score;
+//   * 128 queries x 256 database rows per CTA, K walked in 64-element (128-byte, SWIZZLE_128B)
+//     slices through a 3-stage TMA -> mbarrier -> tcgen05.mma pipeline (one elected thread
+//     issues the MMAs, tcgen05.commit releases the stage);
+//   * the epilogue warps read the accumulator with tcgen05.ld (one TMEM lane = one query) and
+//     push only scores that beat the query's current threshold key into the same per-query
+//     candidate buffers the LUT16 scan uses; the database is walked in geometrically growing
+//     rounds with a compaction between rounds, so the inflow stays ~4k' per round;
+//   * the final k' candidates are re-scored exactly (f32 query x bf16 row, f32 FMA chain, the
+//     oracle's arithmetic) and the top-k of those is returned, so ids and distances are the
+//     reference's as long as the true top-k is inside the over-retrieved k' = 2k + 64 set.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace sb {
+
+namespace bf {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kSplits = 2;
+constexpr int kStages = 3;
+constexpr int kABytes = BM * BK * 2;                       // 16 KB per split
+constexpr int kBBytes = BN * BK * 2;                       // 32 KB
+constexpr int kStageBytes = kSplits * kABytes + kBBytes;   // 64 KB
+constexpr int kThreads = 256;                              // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kTmemCols = 256;
+constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row atoms of 1024 B (SBO), LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct GemmArgs {
+  uint32_t nq, n_total, m_pad;   // queries, database rows, padded query rows per split
+  uint32_t row0, row1;           // database rows [row0, row1) of this round
+  uint32_t num_kb;               // ceil(D / 64)
+  uint64_t* buf; uint32_t* cnt; const uint64_t* tau; uint32_t* ovf; uint32_t cap;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t n0 = a.row0 + blockIdx.x * BN;
+  const uint32_t m0 = blockIdx.y * BM;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer ----
+      for (uint32_t kb = 0; kb < a.num_kb; ++kb) {
+        const int st = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        uint8_t* base = smem + (size_t)st * kStageBytes;
+        mbar_expect_tx(&full_bar[st], kStageBytes);
+        for (int s = 0; s < kSplits; ++s)
+          tma_load_2d(base + s * kABytes, &tmA, &full_bar[st], (int)(kb * BK), (int)(s * a.m_pad + m0));
+        tma_load_2d(base + kSplits * kABytes, &tmB, &full_bar[st], (int)(kb * BK), (int)n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---- MMA issuer ----
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      for (uint32_t kb = 0; kb < a.num_kb; ++kb) {
+        const int st = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&full_bar[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sbase = smem_u32(smem + (size_t)st * kStageBytes);
+        const uint32_t sB = sbase + kSplits * kABytes;
+#pragma unroll
+        for (int s = 0; s < kSplits; ++s) {
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = umma_desc_sw128(sbase + s * kABytes + k * 32);
+            const uint64_t bd = umma_desc_sw128(sB + k * 32);
+            umma_bf16(tmem, ad, bd, idesc, (kb | (uint32_t)s | (uint32_t)k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);    // accumulator complete
+    }
+  } else if (warp >= 4) {  // ---- epilogue: TMEM -> threshold filter -> candidate buffers ----
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const uint32_t q = m0 + quad * 32 + lane;      // one TMEM lane = one query
+    const bool qvalid = q < a.nq;
+    const uint64_t tau = qvalid ? a.tau[q] : 0ull;
+    const uint32_t tau_ord = (uint32_t)(tau >> 32);
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t dp = n0 + c + j;
+        const float dist = -__uint_as_float(v[j]);  // DotProductDistance = -<q, x>
+        const uint32_t o = f2ord(dist);
+        if (qvalid && o <= tau_ord && dp < a.row1) {
+          const uint64_t key = ((uint64_t)o << 32) | dp;
+          if (key < tau) {
+            const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
+            if (pos < a.cap) a.buf[(size_t)q * a.cap + pos] = key;
+            else a.ovf[q] = 1u;
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+}
+
+// f32 queries -> two stacked bf16 operands: hi = bf16(q), lo = bf16(q - hi); padded rows are zero.
+__global__ void split_queries_kernel(const float* __restrict__ q, uint32_t nq, uint32_t d, uint32_t dp,
+                                     uint32_t m_pad, __nv_bfloat16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)m_pad * dp;
+  if (i >= total) return;
+  const uint32_t r = (uint32_t)(i / dp), c = (uint32_t)(i % dp);
+  float v = (r < nq && c < d) ? q[(size_t)r * d + c] : 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  out[i] = hi;
+  out[total + i] = lo;
+}
+
+__global__ void init_topk_state_kernel(uint32_t nq, uint32_t* cnt, uint64_t* tau, uint32_t* ovf) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) { cnt[i] = 0; tau[i] = kKeyMax; ovf[i] = 0; }
+}
+
+// Exact re-scoring of the k' candidates (f32 query x bf16 row, the oracle's 8-lane FMA order),
+// final top-k by (distance, id), output.
+__global__ void __launch_bounds__(128)
+rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db, uint32_t d, uint32_t dpitch,
+               const uint64_t* __restrict__ buf, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t kprime,
+               uint32_t k, uint32_t out_k, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int np2) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
+  float* sq = reinterpret_cast<float*>(ka + np2);
+  const int tid = threadIdx.x;
+  const uint32_t qi = blockIdx.x;
+  const uint32_t m = min(cnt[qi], kprime);
+  const uint64_t* src = buf + (size_t)qi * cap;
+  for (uint32_t i = tid; i < d; i += 128) sq[i] = q[(size_t)qi * d + i];
+  for (int i = tid; i < np2; i += 128) ka[i] = kKeyMax;
+  __syncthreads();
+  const int l = tid & 7, grp = tid >> 3;
+  for (uint32_t c0 = 0; c0 < m; c0 += 16) {
+    const uint32_t c = c0 + grp;
+    const bool valid = c < m;
+    const uint32_t dp = (uint32_t)src[valid ? c : 0];
+    const __nv_bfloat16* x = db + (size_t)dp * dpitch;
+    float acc = 0.f;
+    uint32_t j = 0;
+    for (; j + 8 <= d; j += 8) acc = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), acc);
+    float b = __fadd_rn(__shfl_down_sync(0xFFFFFFFFu, acc, 4, 8), acc);
+    if (j + 4 <= d) { if (l < 4) b = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), b); j += 4; }
+    if (j + 2 <= d) { if (l == 2 || l == 3) b = __fmaf_rn(-sq[j + l - 2], __bfloat162float(x[j + l - 2]), b); j += 2; }
+    const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));
+    float r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));
+    if (j < d && l == 0) r = __fmaf_rn(-sq[j], __bfloat162float(x[j]), r);
+    if (valid && l == 0) ka[c] = make_key(r, dp);
+  }
+  __syncthreads();
+  block_bitonic_sort(ka, np2);
+  const uint32_t kk = min(k, m);
+  for (uint32_t i = tid; i < out_k; i += 128) {
+    uint32_t id = 0;
+    float dist = __uint_as_float(0x7FC00000u);
+    if (i < kk) { id = (uint32_t)ka[i]; dist = -ord2f((uint32_t)(ka[i] >> 32)); }
+    out_idx[(size_t)qi * out_k + i] = id;
+    out_dist[(size_t)qi * out_k + i] = dist;
+  }
+}
+
+}  // namespace bf
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return (EncodeTiledFn) nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+static cudaError_t make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                             uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return cudaErrorNotSupported;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bf::BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+size_t bf_query_operand_bytes(uint32_t nq, uint32_t dpitch) {
+  const uint32_t m_pad = (nq + bf::BM - 1) / bf::BM * bf::BM;
+  return (size_t)bf::kSplits * m_pad * dpitch * 2;
+}
+
+cudaError_t bf_split_queries(const float* q, uint32_t nq, uint32_t d, uint32_t dpitch, void* a_operand, cudaStream_t s) {
+  const uint32_t m_pad = (nq + bf::BM - 1) / bf::BM * bf::BM;
+  const size_t total = (size_t)m_pad * dpitch;
+  bf::split_queries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q, nq, d, dpitch, m_pad,
+                                                                           reinterpret_cast<__nv_bfloat16*>(a_operand));
+  return cudaGetLastError();
+}
+
+cudaError_t bf_init_state(uint32_t nq, uint32_t* cnt, uint64_t* tau, uint32_t* ovf, cudaStream_t s) {
+  bf::init_topk_state_kernel<<<(nq + 255) / 256, 256, 0, s>>>(nq, cnt, tau, ovf);
+  return cudaGetLastError();
+}
+
+// One round: database rows [row0, row1) against all queries.
+cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, uint32_t n_total, uint32_t dpitch,
+                          uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s) {
+  const uint32_t m_pad = (nq + bf::BM - 1) / bf::BM * bf::BM;
+  CUtensorMap tmA, tmB;
+  cudaError_t e = make_tmap(&tmA, a_operand, (uint64_t)bf::kSplits * m_pad, dpitch, dpitch, bf::BM);
+  if (e != cudaSuccess) return e;
+  e = make_tmap(&tmB, db, n_total, dpitch, dpitch, bf::BN);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(bf::gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  bf::GemmArgs a{};
+  a.nq = nq; a.n_total = n_total; a.m_pad = m_pad; a.row0 = row0; a.row1 = row1;
+  a.num_kb = (dpitch + bf::BK - 1) / bf::BK;
+  a.buf = w.buf; a.cnt = w.cnt; a.tau = w.tau; a.ovf = w.ovf; a.cap = w.cap;
+  dim3 grid((row1 - row0 + bf::BN - 1) / bf::BN, m_pad / bf::BM);
+  bf::gemm_filter_kernel<<<grid, bf::kThreads, bf::kSmemBytes, s>>>(tmA, tmB, a);
+  return cudaGetLastError();
+}
+
+cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
+                       uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t* out_idx, float* out_dist, cudaStream_t s) {
+  int np2 = 2;
+  while ((uint32_t)np2 < kprime) np2 <<= 1;
+  const size_t smem = (size_t)np2 * 8 + (((size_t)d + 3) & ~(size_t)3) * 4;
+  cudaError_t e = cudaFuncSetAttribute(bf::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  bf::rescore_kernel<<<nq, 128, smem, s>>>(q, reinterpret_cast<const __nv_bfloat16*>(db), d, dpitch, w.buf, w.cnt, w.cap,
+                                           kprime, k, out_k, out_idx, out_dist, np2);
+  return cudaGetLastError();
+}
+
+}  // namespace sb

@@ -106,6 +106,10 @@ struct scann_b200_index {
   cudaEvent_t ev[EV_COUNT] = {};
   scann_b200_stats last{};
   uint32_t max_chunk = 16384;
+  // brute-force (bf16) searcher: database rows as bf16 with a 16-byte aligned pitch
+  bool brute = false;
+  uint32_t bf_dpitch = 0;
+  DevBuf bf_db, bf_a;
 };
 
 namespace {
@@ -114,7 +118,24 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   const uint32_t N = d->n, D = d->d, L = d->n_leaves, B = d->n_blocks;
   if (d->distance != SCANN_B200_DOT_PRODUCT && d->distance != SCANN_B200_SQUARED_L2)
     return fail(SCANN_B200_INVALID_ARGUMENT, "unknown distance measure %d", d->distance);
-  if (!L || !B) return fail(SCANN_B200_UNIMPLEMENTED, "only tree-AH indexes are implemented (n_leaves=%u, n_blocks=%u)", L, B);
+  if (!L && !B) {
+    // Bfloat16BruteForceSearcher (brute_force/bfloat16_brute_force.cc): bf16 rows, MIPS only
+    if (!d->bf16_dataset) return fail(SCANN_B200_UNIMPLEMENTED, "brute force is implemented for bfloat16 datasets only (bfloat16_dataset.npy)");
+    if (d->distance != SCANN_B200_DOT_PRODUCT) return fail(SCANN_B200_UNIMPLEMENTED, "bfloat16 brute force supports dot product distance only");
+    const int world_bf = d->shard_world > 0 ? d->shard_world : 1;
+    if (world_bf != 1) return fail(SCANN_B200_UNIMPLEMENTED, "sharded brute force is not implemented");
+    sb::DevIndex& vb = ix->dev;
+    vb = sb::DevIndex{};
+    vb.distance = d->distance; vb.n = N; vb.d = D; vb.disjoint = 1;
+    ix->brute = true;
+    ix->bf_dpitch = (D + 7) / 8 * 8;
+    CU(ix->bf_db.ensure((size_t)std::max<uint32_t>(N, 1) * ix->bf_dpitch * 2));
+    CU(cudaMemset(ix->bf_db.p, 0, (size_t)std::max<uint32_t>(N, 1) * ix->bf_dpitch * 2));
+    if (N) CU(cudaMemcpy2D(ix->bf_db.p, (size_t)ix->bf_dpitch * 2, d->bf16_dataset, (size_t)D * 2, (size_t)D * 2, N,
+                           cudaMemcpyHostToDevice));
+    return 0;
+  }
+  if (!L || !B) return fail(SCANN_B200_UNIMPLEMENTED, "only tree-AH and bf16 brute-force indexes are implemented (n_leaves=%u, n_blocks=%u)", L, B);
   if (!d->centers || !d->tokens || !d->codes || !d->codebook)
     return fail(SCANN_B200_INVALID_ARGUMENT, "tree-AH index needs centers, tokens, codes and codebook");
   if (B > 128) return fail(SCANN_B200_UNIMPLEMENTED, "n_blocks=%u > 128 not supported yet", B);
@@ -270,6 +291,12 @@ struct Params { uint32_t k, npre, nover, P; };
 
 int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Params* p) {
   // scann_ops/cc/scann.cc:406-430 + SetUnspecifiedParametersToDefaults
+  if (ix->brute) {
+    const int kb = final_nn > 0 ? final_nn : ix->desc.default_final_nn;
+    if (kb <= 0) return fail(SCANN_B200_INVALID_ARGUMENT, "final_num_neighbors must be positive");
+    p->k = (uint32_t)kb; p->npre = p->k; p->nover = p->k; p->P = 1;
+    return 0;
+  }
   const bool has_reorder = ix->dev.dataset != nullptr;
   const int k = final_nn > 0 ? final_nn : ix->desc.default_final_nn;
   int npre = has_reorder ? (pre_nn > 0 ? pre_nn : ix->desc.default_pre_nn) : k;
@@ -423,6 +450,81 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   return 0;
 }
 
+// Brute force (bf16): geometric rounds of [tcgen05 GEMM + threshold filter] -> compaction, then an
+// exact re-scoring of the k' best.  Mirrors Bfloat16BruteForceSearcher::FindNeighborsImpl
+// (brute_force/bfloat16_brute_force.cc:101-152) for a whole batch of queries.
+int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_t k, uint32_t* d_out_idx,
+                    float* d_out_dist, uint32_t out_k) {
+  const sb::DevIndex& v = ix->dev;
+  cudaStream_t s = ix->stream;
+  const uint32_t kprime = 2 * k + 64;
+  if (kprime > 8192) return fail(SCANN_B200_UNIMPLEMENTED, "brute force with k=%u > 4064 is not supported", k);
+  const uint32_t cap = pick_cap(kprime);
+  CU(ix->bf_a.ensure(sb::bf_query_operand_bytes(nq, ix->bf_dpitch)));
+  CU(ix->buf.ensure(sizeof(uint64_t) * (size_t)nq * cap));
+  CU(ix->cnt.ensure(sizeof(uint32_t) * nq));
+  CU(ix->tau.ensure(sizeof(uint64_t) * nq));
+  CU(ix->ovf.ensure(sizeof(uint32_t) * nq));
+  CU(ix->entry_q.ensure(sizeof(uint32_t) * (size_t)nq));
+  CU(ix->counters.ensure(sizeof(uint32_t) * 8));
+  CU(ix->stats.ensure(sizeof(unsigned long long) * 4));
+  CU(ix->h_counters.ensure(64));
+  sb::ScanWork w{};
+  w.buf = ix->buf.as<uint64_t>(); w.cnt = ix->cnt.as<uint32_t>(); w.tau = ix->tau.as<uint64_t>();
+  w.ovf = ix->ovf.as<uint32_t>(); w.entry_q = ix->entry_q.as<uint32_t>();
+  w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
+  w.nq = nq; w.cap = cap; w.nover = kprime;
+  uint32_t launches = 0, gemm_launches = 0;
+  CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
+  CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
+  CU(cudaEventRecord(ix->ev[EV_START], s));
+  CU(sb::bf_split_queries(d_q, nq, v.d, ix->bf_dpitch, ix->bf_a.p, s));
+  CU(sb::bf_init_state(nq, w.cnt, w.tau, w.ovf, s));
+  launches += 2;
+  CU(cudaEventRecord(ix->ev[EV_TOK], s));
+  // rounds: the first one must hold >= k' rows (everything passes an infinite threshold) and fit
+  // the candidate buffers; afterwards the inflow per round is ~ k' * growth
+  uint32_t row0 = 0;
+  uint32_t chunk = std::max<uint32_t>(4096, 4 * kprime);
+  chunk = std::min(chunk, cap / 2);
+  while (row0 < v.n) {
+    const uint32_t row1 = (uint64_t)row0 + chunk >= v.n ? v.n : row0 + chunk;
+    CU(sb::bf_gemm_round(ix->bf_a.p, ix->bf_db.p, nq, v.n, ix->bf_dpitch, row0, row1, w, s));
+    CU(sb::launch_compact(v, w, false, s));
+    launches += 1 + (cap > 1024 ? 2 : 1);
+    gemm_launches += 1;
+    row0 = row1;
+    chunk = (uint32_t)std::min<uint64_t>((uint64_t)row1 * 3, 0x40000000ull);  // next round: 3x what has been seen
+  }
+  CU(cudaEventRecord(ix->ev[EV_SCAN], s));
+  uint32_t* hc = ix->h_counters.as<uint32_t>();
+  CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (hc[2] != 0) return fail(SCANN_B200_INTERNAL, "brute force: candidate buffer overflow (%u queries)", hc[2]);
+  CU(sb::bf_rescore(d_q, ix->bf_db.p, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, d_out_idx, d_out_dist, s));
+  launches += 1;
+  CU(cudaEventRecord(ix->ev[EV_FIN], s));
+  CU(cudaStreamSynchronize(s));
+  float ms_prep = 0, ms_gemm = 0, ms_fin = 0, tot = 0;
+  CU(cudaEventElapsedTime(&ms_prep, ix->ev[EV_START], ix->ev[EV_TOK]));
+  CU(cudaEventElapsedTime(&ms_gemm, ix->ev[EV_TOK], ix->ev[EV_SCAN]));
+  CU(cudaEventElapsedTime(&ms_fin, ix->ev[EV_SCAN], ix->ev[EV_FIN]));
+  CU(cudaEventElapsedTime(&tot, ix->ev[EV_START], ix->ev[EV_FIN]));
+  scann_b200_stats& st = ix->last;
+  st.kernel_launches += launches;
+  st.scan_kernel_count += gemm_launches;
+  st.ms_tokenize += ms_prep; st.ms_scan += ms_gemm; st.ms_finalize += ms_fin; st.ms_total += tot;
+  st.scan_pairs += (uint64_t)nq * v.n;
+  st.scan_bytes_alg += (uint64_t)v.n * ix->bf_dpitch * 2;  // compulsory database bytes of one pass
+  return 0;
+}
+
+int run_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Params& p, uint32_t* d_out_idx,
+              float* d_out_dist, uint32_t out_k) {
+  if (ix->brute) return search_bf_chunk(ix, d_q, nq, p.k, d_out_idx, d_out_dist, out_k);
+  return search_chunk(ix, d_q, nq, p, d_out_idx, d_out_dist, out_k, nullptr, false);
+}
+
 int check_query_args(scann_b200_index* ix, const void* q, uint32_t nq) {
   if (!ix) return fail(SCANN_B200_INVALID_ARGUMENT, "null index");
   if (nq && !q) return fail(SCANN_B200_INVALID_ARGUMENT, "null queries");
@@ -490,8 +592,8 @@ int scann_b200_search_batched_device(scann_b200_index* ix, const float* d_querie
   ix->last = scann_b200_stats{};
   for (uint32_t s0 = 0; s0 < nq; s0 += ix->max_chunk) {
     const uint32_t c = std::min(ix->max_chunk, nq - s0);
-    if (int rc = search_chunk(ix, d_queries + (size_t)s0 * ix->dev.d, c, p, d_out_idx + (size_t)s0 * out_k,
-                              d_out_dist + (size_t)s0 * out_k, (uint32_t)out_k, nullptr, false))
+    if (int rc = run_chunk(ix, d_queries + (size_t)s0 * ix->dev.d, c, p, d_out_idx + (size_t)s0 * out_k,
+                           d_out_dist + (size_t)s0 * out_k, (uint32_t)out_k))
       return rc;
   }
   return 0;
@@ -518,8 +620,8 @@ int scann_b200_search_batched(scann_b200_index* ix, const float* queries, uint32
     CU(ix->h_dist.ensure(sizeof(float) * (size_t)c * out_k));
     memcpy(ix->h_q.p, queries + (size_t)s0 * D, sizeof(float) * (size_t)c * D);
     CU(cudaMemcpyAsync(ix->q.p, ix->h_q.p, sizeof(float) * (size_t)c * D, cudaMemcpyHostToDevice, ix->stream));
-    if (int rc = search_chunk(ix, ix->q.as<float>(), c, p, ix->out_idx.as<uint32_t>(), ix->out_dist.as<float>(),
-                              (uint32_t)out_k, nullptr, false))
+    if (int rc = run_chunk(ix, ix->q.as<float>(), c, p, ix->out_idx.as<uint32_t>(), ix->out_dist.as<float>(),
+                           (uint32_t)out_k))
       return rc;
     CU(cudaMemcpyAsync(ix->h_idx.p, ix->out_idx.p, sizeof(uint32_t) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
     CU(cudaMemcpyAsync(ix->h_dist.p, ix->out_dist.p, sizeof(float) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
