@@ -36,6 +36,8 @@ WORKLOADS = {
     # name: (n, d, leaves, probe, dims_per_block, reorder, k, nq, generator)
     "c2_glove_shape": dict(n=1_183_514, d=100, leaves=2000, probe=100, dpb=2, pre=100, k=10, nq=10000,
                            clusters=8000, normalize=True, seed=3, train_sample=250000),
+    # C3: brute-force MIPS over a bf16 database (BASELINE.json configs[2])
+    "c3_bruteforce_bf16": dict(kind="bruteforce", n=1_000_000, d=768, k=100, nq=10000, seed=5),
     "c1_synthetic": dict(n=100_000, d=100, leaves=100, probe=10, dpb=2, pre=100, k=10, nq=10000,
                          clusters=400, normalize=False, seed=1, train_sample=100000),
 }
@@ -148,6 +150,8 @@ def main():
     wl["probe"] = args.leaves
 
   import torch
+  if wl.get("kind") == "bruteforce":
+    return run_bruteforce(args, wl, rank, world, local_rank)
   if args.impl == "reference":
     if rank != 0:
       return 0
@@ -335,6 +339,102 @@ def make_sharded_steps(searcher, wl, q, d_q, d_idx, d_dist):
     return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy()
 
   return step_dev, step_host
+
+
+def run_bruteforce(args, wl, rank, world, local_rank):
+  """C3: bf16 brute force, 10k queries x 1M x 768, k = 100 (tcgen05 GEMM + fused top-k pre-filter)."""
+  import torch
+  from scann_b200 import _lib, index_build
+  if world > 1 and rank != 0:
+    return 0  # replicas only at N > 1 for this workload; rank 0 reports one replica
+  n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]
+  rng = np.random.default_rng(wl["seed"])
+  t0 = time.time()
+  bits = np.empty((n, d), np.int16)
+  for s0 in range(0, n, 1 << 16):
+    bits[s0:s0 + (1 << 16)] = index_build.bfloat16_quantize(rng.standard_normal((min(1 << 16, n - s0), d), dtype=np.float32))
+  q = np.random.default_rng(wl["seed"] + 1).standard_normal((nq, d), dtype=np.float32)
+  log(f"[bf] data in {time.time() - t0:.1f}s")
+  a = index_build.IndexArrays(distance="dot_product", dataset=None, n=n, d=d)
+  a.bf16_dataset = bits
+  if args.impl == "reference":
+    import oracle
+    threads = os.cpu_count() or 1
+    sample = max(threads, 16)
+    t0 = time.perf_counter()
+    oracle.bruteforce_bf16(bits, q[:sample], k, threads=threads)
+    dt = time.perf_counter() - t0
+    qps = sample / dt
+    print(json.dumps({"impl": "reference", "metric": "batched QPS, bf16 brute-force MIPS k=100", "value": qps,
+                      "unit": "queries/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 db x f32 query",
+                      "data": "synthetic", "config": {"workload": args.workload, "n": n, "d": d, "k": k,
+                                                      "queries_per_step": sample},
+                      "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                                       "sample": f"{sample} queries, one per thread"},
+                      "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
+          flush=True)
+    return 0
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  ix = _lib.NativeIndex(a, 1, k, k, device=local_rank)
+  d_q = torch.from_numpy(q).to(dev)
+  d_idx = torch.zeros((nq, k), dtype=torch.int32, device=dev)
+  d_dist = torch.zeros((nq, k), dtype=torch.float32, device=dev)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  torch.cuda.synchronize()
+  for _ in range(args.warmup):
+    ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)
+  # recall against an f32 GEMM on the decompressed rows (first 512 queries)
+  x = (torch.from_numpy(bits.view(np.uint16).astype(np.int32)).to(dev) << 16).view(torch.float32)
+  gt = torch.topk(d_q[:512] @ x.T, k, dim=1).indices.cpu().numpy()
+  del x
+  torch.cuda.empty_cache()
+  found = d_idx[:512].cpu().numpy().view(np.uint32)
+  rec = recall_at_k(found, gt)
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  ms_total, agg = 0.0, {}
+  for _ in range(args.steps):
+    flush.zero_()
+    torch.cuda.synchronize()
+    ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)
+    st = ix.stats()
+    ms_total += st["ms_total"]
+    for key, val in st.items():
+      agg[key] = agg.get(key, 0) + val
+  e2e_steps = max(2, min(args.steps, 5))
+  ix.search_batched(q)
+  e0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    ix.search_batched(q)
+  e2e_s = time.perf_counter() - e0
+  sampler.stop_flag.set()
+  sampler.join(timeout=2)
+  flops = 2.0 * nq * n * d * 2  # two bf16 split terms per product
+  gemm_s = agg["ms_scan"] / args.steps * 1e-3
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except Exception:
+    pass
+  peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+  out = {"metric": "batched QPS, bf16 brute-force MIPS k=100", "value": nq * args.steps / (ms_total * 1e-3),
+         "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+         "dtype": "bf16 x (bf16 hi + bf16 lo) -> f32 (tcgen05), f32 re-scoring", "data": "synthetic",
+         "config": {"workload": args.workload, "n": n, "d": d, "k": k, "queries_per_step": nq,
+                    "recall_at_100_first512": rec, "l2_flush": "256 MiB write between timed steps"},
+         "e2e": {"value": nq * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q.nbytes),
+                 "d2h_bytes_per_step": int(nq * k * 8), "steps": e2e_steps},
+         "gpu_launches": int(agg["kernel_launches"]), "clocks": sampler.summary(),
+         "roofline": {"bound": "tensor", "kernel": "bf::gemm_filter_kernel", "achieved": flops / gemm_s / 1e12,
+                      "peak": peak, "peak_source": "measured sustained" if peaks else "fallback", "unit": "TFLOP/s",
+                      "frac": flops / gemm_s / 1e12 / peak, "traffic": None,
+                      "useful_tflops_f32_equivalent": flops / 2 / gemm_s / 1e12},
+         "stage_ms_per_step": {s: agg[s] / args.steps for s in agg if s.startswith("ms_")}}
+  print(json.dumps(out), flush=True)
+  return 0
 
 
 def run_reference(args, wl):
