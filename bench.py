@@ -165,6 +165,8 @@ def main():
   if world > 1:
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+      os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
     dist.init_process_group("nccl", device_id=dev)
 
   from scann_b200 import _lib
