@@ -114,8 +114,54 @@ __device__ int acc_threshold(uint64_t tau, float mult, float inv, float bias) {
   return t;
 }
 
+// K-th smallest (1-based) of n UNIQUE u64 keys in shared memory: 8-pass MSB radix select.
+// All threads of the block call it; `hist` (256 words) and `sh` (2 words + 1 u64) are shared scratch.
+struct SelectScratch { uint32_t hist[256]; unsigned long long prefix; uint32_t need; };
+__device__ __forceinline__ uint64_t block_radix_select(const uint64_t* s, uint32_t n, uint32_t K, SelectScratch* sc) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint64_t prefix = 0, mask = 0;
+  uint32_t need = K;
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += blockDim.x) sc->hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+      const uint64_t k = s[i];
+      if ((k & mask) == prefix) atomicAdd(&sc->hist[(uint32_t)(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {  // warp 0: 8 bins per lane, warp scan, pick the bin where the count crosses `need`
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { c[k] = sc->hist[lane * 8 + k]; tot += c[k]; }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t hit = __ballot_sync(kFull, incl >= need);
+      const int tl = hit ? (__ffs(hit) - 1) : 31;
+      if (lane == tl) {
+        uint32_t cum = incl - tot, digit = (uint32_t)lane * 8 + 7;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; break; }
+          cum += c[k];
+        }
+        sc->prefix = prefix | ((uint64_t)digit << shift);
+        sc->need = need - cum;
+      }
+    }
+    __syncthreads();
+    prefix = sc->prefix;
+    need = sc->need;
+    mask |= 0xFFull << shift;
+  }
+  return prefix;
+}
+
 // ---------------------------------------------------------------------------------------
-// Pilot: one CTA per query, nearest leaves first, exact top-N in shared memory.
+// Pilot: one CTA per query, nearest leaves first, exact top-N threshold in shared memory.
 // ---------------------------------------------------------------------------------------
 template <int W>
 __global__ void __launch_bounds__(kScanThreads)
@@ -126,11 +172,13 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   __shared__ uint64_t s_tau;
   __shared__ int s_thr;
   __shared__ uint32_t s_cnt;
+  __shared__ SelectScratch s_sel;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t q = blockIdx.x;
   const int nlast = (int)ix.B - 8 * (W - 1);
   const int off128 = 128 * (int)ix.B;
   const uint32_t nover = w.nover;
+  uint64_t* grow = w.buf + (size_t)q * w.cap;  // this query's buffer row doubles as compaction scratch
   build_quad_table(tbl, w.lut + (size_t)q * W * 128, nullptr, nullptr, nullptr, W * 128, tid, kScanThreads);
   if (tid == 0) { s_tau = kKeyMax; s_cnt = 0; }
   const float mult = w.mult[q], inv = w.inv_mult[q];
@@ -173,12 +221,20 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
       const uint32_t c = s_cnt;
       __syncthreads();  // everyone has read s_cnt before the next round may bump it
       if (c > (uint32_t)(capl - kScanThreads)) {
-        for (int i = c + tid; i < capl; i += kScanThreads) scand[i] = kKeyMax;
+        // keep the N smallest: radix-select the N-th key, compact through the global row (no sort:
+        // the compaction after the main scan orders everything anyway).  c > capl-128 >= N here.
+        const uint64_t T = block_radix_select(scand, c, nover, &s_sel);
+        if (tid == 0) s_cnt = 0;
         __syncthreads();
-        block_bitonic_sort(scand, capl);
+        for (uint32_t i = tid; i < c; i += kScanThreads) {
+          const uint64_t k = scand[i];
+          if (k <= T) grow[atomicAdd(&s_cnt, 1u)] = k;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < nover; i += kScanThreads) scand[i] = grow[i];
         if (tid == 0) {
-          if (c >= nover) { s_cnt = nover; s_tau = scand[nover - 1]; }
-          s_thr = acc_threshold(s_tau, mult, inv, bias) + off128;
+          s_tau = T;
+          s_thr = acc_threshold(T, mult, inv, bias) + off128;
         }
         __syncthreads();
       }
@@ -187,17 +243,15 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
     if (seen >= nover) { ++r; break; }
   }
   __syncthreads();
+  // publish: every buffered candidate (unsorted, at most capl) and the N-th smallest key as tau
   const uint32_t c = s_cnt;
-  int np2 = 2;
-  while ((uint32_t)np2 < c) np2 <<= 1;
-  for (int i = c + tid; i < np2; i += kScanThreads) scand[i] = kKeyMax;
-  __syncthreads();
-  block_bitonic_sort(scand, np2);
-  const uint32_t keep = min(c, nover);
-  for (uint32_t i = tid; i < keep; i += kScanThreads) w.buf[(size_t)q * w.cap + i] = scand[i];
+  uint64_t tau = kKeyMax;
+  if (c >= nover) tau = block_radix_select(scand, c, nover, &s_sel);
+  const uint32_t keep = min(c, w.cap);
+  for (uint32_t i = tid; i < keep; i += kScanThreads) grow[i] = scand[i];
   if (tid == 0) {
     w.cnt[q] = keep;
-    w.tau[q] = (keep >= nover) ? scand[nover - 1] : kKeyMax;
+    w.tau[q] = tau;
     w.pilot_end[q] = (int32_t)r;
     w.ovf[q] = 0;
   }
