@@ -58,15 +58,18 @@ __device__ __forceinline__ void load_codes(const uint32_t* __restrict__ gbase, i
 }
 
 // Four queries' u16 sums for one datapoint: a01 = s0 | s1 << 16, a23 = s2 | s3 << 16.
-template <int W>
+// NL = number of real blocks in the last word: 1..8 compile-time (the padded lookups vanish from
+// the instruction stream), 0 = use the runtime `nlast` (predicated lookups).
+template <int W, int NL = 0>
 __device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigned char* tbl,
                                            int nlast, uint32_t& a01, uint32_t& a23) {
   uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  const int nl = NL ? NL : nlast;
 #pragma unroll
   for (int j = 0; j < W; ++j) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      if (j == W - 1 && k >= nlast) continue;
+      if (j == W - 1 && k >= nl) continue;
       const uint32_t off = (k == 0) ? ((w[j] << 3) & 0x78u) : ((w[j] >> (4 * k - 3)) & 0x78u);
       const uint2 v = *reinterpret_cast<const uint2*>(tbl + (8 * j + k) * 128 + off);
       if (k & 1) { x1 += v.x; y1 += v.y; } else { x0 += v.x; y0 += v.y; }
@@ -365,7 +368,7 @@ void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed
 // ---------------------------------------------------------------------------------------
 // Main scan: persistent CTAs pull (leaf tile, query chunk) items from an atomic counter.
 // ---------------------------------------------------------------------------------------
-template <int W>
+template <int W, int NL>
 __global__ void __launch_bounds__(kScanThreads)
 scan_main_kernel(DevIndex ix, ScanWork w) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -443,7 +446,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       const uint32_t gslot = (gbeg + g) * 32 + lane;
       for (uint32_t qd = 0; qd < nquads; ++qd) {
         uint32_t a01, a23;
-        score_quad<W>(cw, reinterpret_cast<const unsigned char*>(tables + (size_t)qd * kTblEntries),
+        score_quad<W, NL>(cw, reinterpret_cast<const unsigned char*>(tables + (size_t)qd * kTblEntries),
                       nlast, a01, a23);
         const int sv[4] = {(int)(a01 & 0xFFFFu), (int)(a01 >> 16), (int)(a23 & 0xFFFFu), (int)(a23 >> 16)};
         bool pv[4];
@@ -666,20 +669,31 @@ cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) 
   return cudaGetLastError();
 }
 
+template <int W, int NL>
+static cudaError_t launch_scan_t(const DevIndex& ix, const ScanWork& w, int grid, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(scan_main_kernel<W, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (grid <= 0) {  // persistent: exactly as many CTAs as can be resident
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_main_kernel<W, NL>, kScanThreads, smem);
+    if (e != cudaSuccess) return e;
+    grid = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  scan_main_kernel<W, NL><<<grid, kScanThreads, smem, s>>>(ix, w);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s) {
   const size_t smem = scan_smem_bytes(ix, w.quads_per_item);
+  // the common block counts (B % 8 == 0, 2, 4) get a kernel without padded lookups
+  const int nlast = (int)ix.B - 8 * ((int)ix.W - 1);
   SB_DISPATCH_W(ix.W, {
-    cudaError_t e = cudaFuncSetAttribute(scan_main_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (grid <= 0) {  // persistent: exactly as many CTAs as can be resident
-      int dev = 0, sms = 148, per_sm = 1;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_main_kernel<W>, kScanThreads, smem);
-      if (e != cudaSuccess) return e;
-      grid = sms * (per_sm > 0 ? per_sm : 1);
-    }
-    scan_main_kernel<W><<<grid, kScanThreads, smem, s>>>(ix, w);
+    if (nlast == 8) return launch_scan_t<W, 8>(ix, w, grid, smem, s);
+    if (nlast == 2) return launch_scan_t<W, 2>(ix, w, grid, smem, s);
+    if (nlast == 4) return launch_scan_t<W, 4>(ix, w, grid, smem, s);
+    return launch_scan_t<W, 0>(ix, w, grid, smem, s);
   });
   return cudaGetLastError();
 }
