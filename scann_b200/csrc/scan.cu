@@ -79,6 +79,24 @@ __device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigne
   a23 = y0 + y1;
 }
 
+// The same scoring with everything but the load and the add hoisted out of the quad loop:
+// ad[i] = shared address of block row i's entry for this slot in quad table 0; quad QD's table is a
+// compile-time displacement away, so one lookup is exactly LDS.64 [ad + imm] + one IADD3 half.
+template <int W, int NL, int QD>
+__device__ __forceinline__ void score_quad_addr(const uint32_t (&ad)[8 * W], int nlast, uint32_t& a01, uint32_t& a23) {
+  uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  const int nl = NL ? NL : nlast;
+#pragma unroll
+  for (int i = 0; i < 8 * W; ++i) {
+    if (i >= 8 * (W - 1) + nl) continue;
+    uint32_t vx, vy;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8));
+    if (i & 1) { x1 += vx; y1 += vy; } else { x0 += vx; y0 += vy; }
+  }
+  a01 = x0 + x1;
+  a23 = y0 + y1;
+}
+
 // Interleave up to four uint8 LUTs (8W*16 bytes each, NULL = all zero) into a quad table.
 __device__ __forceinline__ void build_quad_table(uint2* __restrict__ tbl, const uint8_t* l0,
                                                  const uint8_t* l1, const uint8_t* l2,
@@ -444,10 +462,17 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
       const bool valid = g * 32 + lane < nleaf;
       const uint32_t gslot = (gbeg + g) * 32 + lane;
-      for (uint32_t qd = 0; qd < nquads; ++qd) {
-        uint32_t a01, a23;
-        score_quad<W, NL>(cw, reinterpret_cast<const unsigned char*>(tables + (size_t)qd * kTblEntries),
-                      nlast, a01, a23);
+      uint32_t ad[8 * W];
+      {
+        const uint32_t tb32 = (uint32_t)__cvta_generic_to_shared(tables);
+#pragma unroll
+        for (int j = 0; j < W; ++j)
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            ad[8 * j + k] = tb32 + (8 * j + k) * 128 +
+                            ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
+      }
+      auto filter = [&](const uint32_t qd, const uint32_t a01, const uint32_t a23) {
         const int sv[4] = {(int)(a01 & 0xFFFFu), (int)(a01 >> 16), (int)(a23 & 0xFFFFu), (int)(a23 >> 16)};
         bool pv[4];
         bool any = false;
@@ -482,7 +507,15 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
             }
           }
         }
-      }
+      };
+#define SB_DO_QUAD(QD)                                       \
+  if (QD < nquads) {                                         \
+    uint32_t a01, a23;                                       \
+    score_quad_addr<W, NL, QD>(ad, nlast, a01, a23);         \
+    filter(QD, a01, a23);                                    \
+  }
+      SB_DO_QUAD(0) SB_DO_QUAD(1) SB_DO_QUAD(2) SB_DO_QUAD(3)
+#undef SB_DO_QUAD
     }
   }
 }
