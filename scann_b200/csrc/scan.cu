@@ -8,9 +8,10 @@
 // B200 formulation.  The CPU kernel looks one query's 16-entry uint8 table up with vpshufb
 // for 32 datapoints at a time.  Here the unit of work is a QUAD of four queries that probe
 // the same leaf: their four uint8 tables are interleaved in shared memory into one table of
-// 64-bit entries  T[b][c] = {lut0 | lut1 << 16, lut2 | lut3 << 16},  so ONE conflict-free
-// LDS.64 (16 distinct entries = 16 distinct bank pairs, equal entries broadcast) serves four
-// (query, datapoint, block) lookups and two 32-bit adds accumulate four u16 sums
+// 32-bit entries  T[b][c] = lut0 | lut1 << 8 | lut2 << 16 | lut3 << 24,  so ONE conflict-free
+// LDS.32 (16 distinct entries = 16 distinct banks, equal entries broadcast: a single wavefront
+// per warp) serves four (query, datapoint, block) lookups; a mask and a byte permute split the
+// word into (q0, q2) and (q1, q3) u16 lanes and two 32-bit adds accumulate four u16 sums
 // (B <= 256 => sum <= 65280, no carry between the halves).  Each thread owns one datapoint
 // of a 32-slot group: its B nibbles live in W = ceil(B/8) registers, loaded once per work
 // item with coalesced 128-bit loads and reused for every quad of the item.
@@ -70,13 +71,15 @@ __device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigne
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (j == W - 1 && k >= nl) continue;
-      const uint32_t off = (k == 0) ? ((w[j] << 3) & 0x78u) : ((w[j] >> (4 * k - 3)) & 0x78u);
-      const uint2 v = *reinterpret_cast<const uint2*>(tbl + (8 * j + k) * 128 + off);
-      if (k & 1) { x1 += v.x; y1 += v.y; } else { x0 += v.x; y0 += v.y; }
+      const uint32_t off = (k == 0) ? ((w[j] << 2) & 0x3Cu) : ((w[j] >> (4 * k - 2)) & 0x3Cu);
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(tbl + (8 * j + k) * 64 + off);
+      const uint32_t e = v & 0x00FF00FFu, o = __byte_perm(v, 0u, 0x4341);  // (q0,q2) and (q1,q3) as u16 lanes
+      if (k & 1) { x1 += e; y1 += o; } else { x0 += e; y0 += o; }
     }
   }
-  a01 = x0 + x1;
-  a23 = y0 + y1;
+  const uint32_t ae = x0 + x1, ao = y0 + y1;  // ae = s0 | s2 << 16, ao = s1 | s3 << 16
+  a01 = __byte_perm(ae, ao, 0x5410);
+  a23 = __byte_perm(ae, ao, 0x7632);
 }
 
 // The same scoring with everything but the load and the add hoisted out of the quad loop:
@@ -89,16 +92,18 @@ __device__ __forceinline__ void score_quad_addr(const uint32_t (&ad)[8 * W], int
 #pragma unroll
   for (int i = 0; i < 8 * W; ++i) {
     if (i >= 8 * (W - 1) + nl) continue;
-    uint32_t vx, vy;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8));
-    if (i & 1) { x1 += vx; y1 += vy; } else { x0 += vx; y0 += vy; }
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(ad[i]), "n"(QD * W * 128 * 4));
+    const uint32_t e = v & 0x00FF00FFu, o = __byte_perm(v, 0u, 0x4341);
+    if (i & 1) { x1 += e; y1 += o; } else { x0 += e; y0 += o; }
   }
-  a01 = x0 + x1;
-  a23 = y0 + y1;
+  const uint32_t ae = x0 + x1, ao = y0 + y1;
+  a01 = __byte_perm(ae, ao, 0x5410);
+  a23 = __byte_perm(ae, ao, 0x7632);
 }
 
 // Interleave up to four uint8 LUTs (8W*16 bytes each, NULL = all zero) into a quad table.
-__device__ __forceinline__ void build_quad_table(uint2* __restrict__ tbl, const uint8_t* l0,
+__device__ __forceinline__ void build_quad_table(uint32_t* __restrict__ tbl, const uint8_t* l0,
                                                  const uint8_t* l1, const uint8_t* l2,
                                                  const uint8_t* l3, int n_entries, int tid,
                                                  int nthreads) {
@@ -107,13 +112,15 @@ __device__ __forceinline__ void build_quad_table(uint2* __restrict__ tbl, const 
     const uint32_t b = l1 ? reinterpret_cast<const uint32_t*>(l1)[t] : 0u;
     const uint32_t c = l2 ? reinterpret_cast<const uint32_t*>(l2)[t] : 0u;
     const uint32_t d = l3 ? reinterpret_cast<const uint32_t*>(l3)[t] : 0u;
-    uint4 o0, o1;
-    o0.x = __byte_perm(a, b, 0x0400) & 0x00FF00FFu; o0.y = __byte_perm(c, d, 0x0400) & 0x00FF00FFu;
-    o0.z = __byte_perm(a, b, 0x0501) & 0x00FF00FFu; o0.w = __byte_perm(c, d, 0x0501) & 0x00FF00FFu;
-    o1.x = __byte_perm(a, b, 0x0602) & 0x00FF00FFu; o1.y = __byte_perm(c, d, 0x0602) & 0x00FF00FFu;
-    o1.z = __byte_perm(a, b, 0x0703) & 0x00FF00FFu; o1.w = __byte_perm(c, d, 0x0703) & 0x00FF00FFu;
-    reinterpret_cast<uint4*>(tbl)[2 * t] = o0;
-    reinterpret_cast<uint4*>(tbl)[2 * t + 1] = o1;
+    // 4x4 byte transpose: entry i = a.byte[i] | b.byte[i] << 8 | c.byte[i] << 16 | d.byte[i] << 24
+    const uint32_t ab01 = __byte_perm(a, b, 0x5140), cd01 = __byte_perm(c, d, 0x5140);
+    const uint32_t ab23 = __byte_perm(a, b, 0x7362), cd23 = __byte_perm(c, d, 0x7362);
+    uint4 o;
+    o.x = __byte_perm(ab01, cd01, 0x5410);
+    o.y = __byte_perm(ab01, cd01, 0x7632);
+    o.z = __byte_perm(ab23, cd23, 0x5410);
+    o.w = __byte_perm(ab23, cd23, 0x7632);
+    reinterpret_cast<uint4*>(tbl)[t] = o;
   }
 }
 
@@ -188,8 +195,8 @@ template <int W>
 __global__ void __launch_bounds__(kScanThreads)
 pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint2* tbl = reinterpret_cast<uint2*>(smem);                       // [W*128]
-  uint64_t* scand = reinterpret_cast<uint64_t*>(smem + W * 128 * 8);  // [capl]
+  uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);                  // [W*128]
+  uint64_t* scand = reinterpret_cast<uint64_t*>(smem + W * 128 * 4);  // [capl]
   __shared__ uint64_t s_tau;
   __shared__ int s_thr;
   __shared__ uint32_t s_cnt;
@@ -390,7 +397,7 @@ template <int W, int NL>
 __global__ void __launch_bounds__(kScanThreads)
 scan_main_kernel(DevIndex ix, ScanWork w) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint2* tables = reinterpret_cast<uint2*>(smem);  // [quads_per_item][W*128]
+  uint32_t* tables = reinterpret_cast<uint32_t*>(smem);  // [quads_per_item][W*128]
   __shared__ uint32_t s_q[kMaxQPI];
   __shared__ int s_thr[kMaxQPI];
   __shared__ uint64_t s_tau[kMaxQPI];
@@ -469,8 +476,8 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
         for (int j = 0; j < W; ++j)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            ad[8 * j + k] = tb32 + (8 * j + k) * 128 +
-                            ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
+            ad[8 * j + k] = tb32 + (8 * j + k) * 64 +
+                            ((k == 0) ? ((cw[j] << 2) & 0x3Cu) : ((cw[j] >> (4 * k - 2)) & 0x3Cu));
       }
       auto filter = [&](const uint32_t qd, const uint32_t a01, const uint32_t a23) {
         const int sv[4] = {(int)(a01 & 0xFFFFu), (int)(a01 >> 16), (int)(a23 & 0xFFFFu), (int)(a23 >> 16)};
@@ -648,7 +655,7 @@ template <int W>
 __global__ void __launch_bounds__(kScanThreads)
 leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, int16_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint2* tbl = reinterpret_cast<uint2*>(smem);
+  uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   build_quad_table(tbl, lut, nullptr, nullptr, nullptr, W * 128, tid, kScanThreads);
   __syncthreads();
@@ -685,10 +692,10 @@ static int pilot_capl(uint32_t nover) {
   return capl;
 }
 size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover) {
-  return (size_t)ix.W * 128 * 8 + (size_t)pilot_capl(nover) * 8;
+  return (size_t)ix.W * 128 * 4 + (size_t)pilot_capl(nover) * 8;
 }
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item) {
-  return (size_t)quads_per_item * ix.W * 128 * 8;
+  return (size_t)quads_per_item * ix.W * 128 * 4;
 }
 
 cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) {
@@ -749,7 +756,7 @@ cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cu
 }
 
 void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s) {
-  const size_t smem = (size_t)ix.W * 128 * 8;
+  const size_t smem = (size_t)ix.W * 128 * 4;
   auto run = [&]() -> cudaError_t {
     SB_DISPATCH_W(ix.W, {
       cudaFuncSetAttribute(leaf_scores_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
