@@ -56,6 +56,7 @@ struct ScanWork {
   uint32_t* counters;         // [8]: 0 item counter, 1 n_items, 2 n_ovf, 3 n_entries
   unsigned long long* stats;  // [4]: 0 bytes_alg, 1 pairs, 2 lookups
   uint32_t nq, P, cap, nover, quads_per_item;
+  uint32_t one;               // always 1; a runtime value so the scan's IMAD accumulates stay IMADs
 };
 
 // ---- query preparation ----

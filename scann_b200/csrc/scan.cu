@@ -86,7 +86,8 @@ __device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigne
 // ad[i] = shared address of block row i's entry for this slot in quad table 0; quad QD's table is a
 // compile-time displacement away, so one lookup is exactly LDS.64 [ad + imm] + one IADD3 half.
 template <int W, int NL, int QD>
-__device__ __forceinline__ void score_quad_addr(const uint32_t (&ad)[8 * W], int nlast, uint32_t& a01, uint32_t& a23) {
+__device__ __forceinline__ void score_quad_addr(const uint32_t (&ad)[8 * W], int nlast, uint32_t one,
+                                                uint32_t& a01, uint32_t& a23) {
   uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   const int nl = NL ? NL : nlast;
 #pragma unroll
@@ -95,7 +96,16 @@ __device__ __forceinline__ void score_quad_addr(const uint32_t (&ad)[8 * W], int
     uint32_t v;
     asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(ad[i]), "n"(QD * W * 128 * 4));
     const uint32_t e = v & 0x00FF00FFu, o = __byte_perm(v, 0u, 0x4341);
-    if (i & 1) { x1 += e; y1 += o; } else { x0 += e; y0 += o; }
+    // The ALU pipe already carries the mask and the permute of every lookup; the two accumulates
+    // go to the FMA pipe as IMAD (acc = e * one + acc, `one` is a runtime 1 so ptxas cannot turn
+    // it back into IADD3), which balances LDS : ALU : FMA at 1 : 2 : 2 per lookup-warp.
+    if (i & 1) {
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x1) : "r"(e), "r"(one));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y1) : "r"(o), "r"(one));
+    } else {
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x0) : "r"(e), "r"(one));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y0) : "r"(o), "r"(one));
+    }
   }
   const uint32_t ae = x0 + x1, ao = y0 + y1;
   a01 = __byte_perm(ae, ao, 0x5410);
@@ -518,7 +528,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
 #define SB_DO_QUAD(QD)                                       \
   if (QD < nquads) {                                         \
     uint32_t a01, a23;                                       \
-    score_quad_addr<W, NL, QD>(ad, nlast, a01, a23);         \
+    score_quad_addr<W, NL, QD>(ad, nlast, w.one, a01, a23);  \
     filter(QD, a01, a23);                                    \
   }
       SB_DO_QUAD(0) SB_DO_QUAD(1) SB_DO_QUAD(2) SB_DO_QUAD(3)
