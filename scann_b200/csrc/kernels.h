@@ -8,7 +8,7 @@ namespace sb {
 constexpr int kScanThreads = 128;     // 4 warps per scan CTA
 constexpr int kScanWarps = 4;
 constexpr int kMaxGroupsPerTile = 32; // 32-slot groups per (leaf tile) work item
-constexpr int kQueriesPerQuad = 4;    // queries packed into one 64-bit LUT entry
+constexpr int kQueriesPerQuad = 8;    // queries packed into one 64-bit LUT entry of the main scan (an "oct")
 
 // Device view of one searcher (all pointers are device pointers).
 struct DevIndex {

@@ -34,7 +34,7 @@ namespace sb {
 
 constexpr uint32_t kInvalidQuery = 0xFFFFFFFFu;
 constexpr uint32_t kFull = 0xFFFFFFFFu;
-constexpr int kMaxQPI = 16;  // queries per work item (4 quads)
+constexpr int kMaxQPI = 32;  // queries per work item (4 octs of 8 queries)
 
 // ---- packed code layout -------------------------------------------------------------------
 // Per 32-slot group: W 32-bit words per slot (nibble k of word j = code of block 8j+k), stored
@@ -82,34 +82,57 @@ __device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigne
   a23 = __byte_perm(ae, ao, 0x7632);
 }
 
-// The same scoring with everything but the load and the add hoisted out of the quad loop:
-// ad[i] = shared address of block row i's entry for this slot in quad table 0; quad QD's table is a
-// compile-time displacement away, so one lookup is exactly LDS.64 [ad + imm] + one IADD3 half.
+// Main-scan scoring.  An OCT of eight queries shares one table of 64-bit entries
+//   T[b][c] = { lut0 | lut1 << 8 | lut2 << 16 | lut3 << 24,  lut4 | lut5 << 8 | lut6 << 16 | lut7 << 24 },
+// so one LDS.64 (the LSU issues about one warp-wide shared load per two cycles whatever its width)
+// serves EIGHT (query, datapoint, block) lookups.  Two masks and two byte permutes (ALU pipe) split
+// the pair of words into four registers of two u16 lanes, four IMADs (FMA pipe, `one` is a runtime 1
+// so ptxas cannot fold them back into IADD3s) accumulate them: LDS : ALU : FMA = 1 : 4 : 4 per eight
+// lookups.  ad[i] is the shared address of block row i's entry for this slot in oct table 0; oct QD's
+// table is a compile-time displacement away.
 template <int W, int NL, int QD>
-__device__ __forceinline__ void score_quad_addr(const uint32_t (&ad)[8 * W], int nlast, uint32_t one,
-                                                uint32_t& a01, uint32_t& a23) {
-  uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+__device__ __forceinline__ void score_oct_addr(const uint32_t (&ad)[8 * W], int nlast, uint32_t one,
+                                               uint32_t (&acc)[4]) {
+  uint32_t e0 = 0, o0 = 0, e1 = 0, o1 = 0;
   const int nl = NL ? NL : nlast;
 #pragma unroll
   for (int i = 0; i < 8 * W; ++i) {
     if (i >= 8 * (W - 1) + nl) continue;
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(ad[i]), "n"(QD * W * 128 * 4));
-    const uint32_t e = v & 0x00FF00FFu, o = __byte_perm(v, 0u, 0x4341);
-    // The ALU pipe already carries the mask and the permute of every lookup; the two accumulates
-    // go to the FMA pipe as IMAD (acc = e * one + acc, `one` is a runtime 1 so ptxas cannot turn
-    // it back into IADD3), which balances LDS : ALU : FMA at 1 : 2 : 2 per lookup-warp.
-    if (i & 1) {
-      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x1) : "r"(e), "r"(one));
-      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y1) : "r"(o), "r"(one));
-    } else {
-      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x0) : "r"(e), "r"(one));
-      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y0) : "r"(o), "r"(one));
-    }
+    uint32_t vx, vy;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8));
+    const uint32_t xe = vx & 0x00FF00FFu, xo = __byte_perm(vx, 0u, 0x4341);
+    const uint32_t ye = vy & 0x00FF00FFu, yo = __byte_perm(vy, 0u, 0x4341);
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e0) : "r"(xe), "r"(one));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(o0) : "r"(xo), "r"(one));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e1) : "r"(ye), "r"(one));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(o1) : "r"(yo), "r"(one));
   }
-  const uint32_t ae = x0 + x1, ao = y0 + y1;
-  a01 = __byte_perm(ae, ao, 0x5410);
-  a23 = __byte_perm(ae, ao, 0x7632);
+  acc[0] = e0; acc[1] = o0; acc[2] = e1; acc[3] = o1;  // (s0,s2) (s1,s3) (s4,s6) (s5,s7) as u16 lanes
+}
+
+// Interleave up to eight uint8 LUTs (8W*16 bytes each, NULL = all zero) into an oct table.
+__device__ __forceinline__ void build_oct_table(uint2* __restrict__ tbl, const uint8_t* const (&l)[8],
+                                                int n_entries, int tid, int nthreads) {
+  for (int t = tid; t < n_entries / 4; t += nthreads) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = l[i] ? reinterpret_cast<const uint32_t*>(l[i])[t] : 0u;
+    uint32_t x[4], y[4];
+    {
+      const uint32_t ab01 = __byte_perm(v[0], v[1], 0x5140), cd01 = __byte_perm(v[2], v[3], 0x5140);
+      const uint32_t ab23 = __byte_perm(v[0], v[1], 0x7362), cd23 = __byte_perm(v[2], v[3], 0x7362);
+      x[0] = __byte_perm(ab01, cd01, 0x5410); x[1] = __byte_perm(ab01, cd01, 0x7632);
+      x[2] = __byte_perm(ab23, cd23, 0x5410); x[3] = __byte_perm(ab23, cd23, 0x7632);
+    }
+    {
+      const uint32_t ab01 = __byte_perm(v[4], v[5], 0x5140), cd01 = __byte_perm(v[6], v[7], 0x5140);
+      const uint32_t ab23 = __byte_perm(v[4], v[5], 0x7362), cd23 = __byte_perm(v[6], v[7], 0x7362);
+      y[0] = __byte_perm(ab01, cd01, 0x5410); y[1] = __byte_perm(ab01, cd01, 0x7632);
+      y[2] = __byte_perm(ab23, cd23, 0x5410); y[3] = __byte_perm(ab23, cd23, 0x7632);
+    }
+    reinterpret_cast<uint4*>(tbl)[2 * t] = make_uint4(x[0], y[0], x[1], y[1]);
+    reinterpret_cast<uint4*>(tbl)[2 * t + 1] = make_uint4(x[2], y[2], x[3], y[3]);
+  }
 }
 
 // Interleave up to four uint8 LUTs (8W*16 bytes each, NULL = all zero) into a quad table.
@@ -407,7 +430,7 @@ template <int W, int NL>
 __global__ void __launch_bounds__(kScanThreads)
 scan_main_kernel(DevIndex ix, ScanWork w) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t* tables = reinterpret_cast<uint32_t*>(smem);  // [quads_per_item][W*128]
+  uint2* tables = reinterpret_cast<uint2*>(smem);  // [octs per item][W*128] 64-bit entries
   __shared__ uint32_t s_q[kMaxQPI];
   __shared__ int s_thr[kMaxQPI];
   __shared__ uint64_t s_tau[kMaxQPI];
@@ -446,7 +469,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
     const uint32_t nleaf = ix.leaf_size[leaf];
     const uint32_t ebase = w.leaf_eoff[leaf] + chunk * qpi;
     const uint32_t ecount = min(qpi, w.leaf_eoff[leaf + 1] - ebase);
-    const uint32_t nquads = (ecount + 3) >> 2;
+    const uint32_t nquads = (ecount + kQueriesPerQuad - 1) / kQueriesPerQuad;  // octs in this item
     if (tid < (int)qpi) {
       uint32_t qq = kInvalidQuery;
       int thr = -1;
@@ -464,14 +487,13 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
     }
     __syncthreads();
     for (uint32_t qd = 0; qd < nquads; ++qd) {
-      const uint8_t* lp[4];
+      const uint8_t* lp[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t qq = s_q[qd * 4 + i];
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t qq = s_q[qd * 8 + i];
         lp[i] = (qq == kInvalidQuery) ? nullptr : w.lut + (size_t)qq * kTblEntries;
       }
-      build_quad_table(tables + (size_t)qd * kTblEntries, lp[0], lp[1], lp[2], lp[3], kTblEntries, tid,
-                       kScanThreads);
+      build_oct_table(tables + (size_t)qd * kTblEntries, lp, kTblEntries, tid, kScanThreads);
     }
     __syncthreads();
     for (uint32_t g = g0 + warp; g < g1; g += kScanWarps) {
@@ -486,22 +508,23 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
         for (int j = 0; j < W; ++j)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            ad[8 * j + k] = tb32 + (8 * j + k) * 64 +
-                            ((k == 0) ? ((cw[j] << 2) & 0x3Cu) : ((cw[j] >> (4 * k - 2)) & 0x3Cu));
+            ad[8 * j + k] = tb32 + (8 * j + k) * 128 +
+                            ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
       }
-      auto filter = [&](const uint32_t qd, const uint32_t a01, const uint32_t a23) {
-        const int sv[4] = {(int)(a01 & 0xFFFFu), (int)(a01 >> 16), (int)(a23 & 0xFFFFu), (int)(a23 >> 16)};
-        bool pv[4];
+      auto filter = [&](const uint32_t qd, const uint32_t (&acc)[4]) {
+        const int sv[8] = {(int)(acc[0] & 0xFFFFu), (int)(acc[1] & 0xFFFFu), (int)(acc[0] >> 16), (int)(acc[1] >> 16),
+                           (int)(acc[2] & 0xFFFFu), (int)(acc[3] & 0xFFFFu), (int)(acc[2] >> 16), (int)(acc[3] >> 16)};
+        bool pv[8];
         bool any = false;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          pv[i] = valid && sv[i] <= s_thr[qd * 4 + i];
+        for (int i = 0; i < 8; ++i) {
+          pv[i] = valid && sv[i] <= s_thr[qd * 8 + i];
           any |= pv[i];
         }
         if (__any_sync(kFull, any)) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int qi = qd * 4 + i;
+          for (int i = 0; i < 8; ++i) {
+            const int qi = qd * 8 + i;
             bool p = pv[i];
             uint64_t key = 0;
             if (p) {
@@ -527,9 +550,9 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       };
 #define SB_DO_QUAD(QD)                                       \
   if (QD < nquads) {                                         \
-    uint32_t a01, a23;                                       \
-    score_quad_addr<W, NL, QD>(ad, nlast, w.one, a01, a23);  \
-    filter(QD, a01, a23);                                    \
+    uint32_t acc[4];                                         \
+    score_oct_addr<W, NL, QD>(ad, nlast, w.one, acc);        \
+    filter(QD, acc);                                         \
   }
       SB_DO_QUAD(0) SB_DO_QUAD(1) SB_DO_QUAD(2) SB_DO_QUAD(3)
 #undef SB_DO_QUAD
@@ -705,7 +728,7 @@ size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover) {
   return (size_t)ix.W * 128 * 4 + (size_t)pilot_capl(nover) * 8;
 }
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item) {
-  return (size_t)quads_per_item * ix.W * 128 * 4;
+  return (size_t)quads_per_item * ix.W * 128 * 8;
 }
 
 cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) {
