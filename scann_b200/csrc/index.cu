@@ -376,7 +376,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   w.leaf_cur = ix->leaf_cur.as<uint32_t>(); w.item_off = ix->item_off.as<uint32_t>();
   w.entry_q = ix->entry_q.as<uint32_t>(); w.entry_bias = ix->entry_bias.as<float>();
   w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
-  w.nq = nq; w.P = p.P; w.cap = cap; w.nover = p.nover; w.quads_per_item = 4; w.one = 1;
+  w.nq = nq; w.P = p.P; w.cap = cap; w.nover = p.nover; w.quads_per_item = 2; w.one = 1;  // 2 octs = 16 queries per work item
   int launches = 0;
   uint32_t scan_launches = 0, retries = 0;
 

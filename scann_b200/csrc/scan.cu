@@ -426,15 +426,58 @@ void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed
 // ---------------------------------------------------------------------------------------
 // Main scan: persistent CTAs pull (leaf tile, query chunk) items from an atomic counter.
 // ---------------------------------------------------------------------------------------
+struct ItemMeta {
+  uint64_t tau[kMaxQPI];
+  uint32_t q[kMaxQPI];
+  int thr[kMaxQPI];
+  float inv[kMaxQPI], bias[kMaxQPI];
+};
+
+// Rare path of the main scan: exact key test and warp-aggregated append for one oct.  All 32 lanes call.
+__device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork& w, const ItemMeta* meta, uint32_t qd,
+                                             uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t pm,
+                                             uint32_t gslot, int off128) {
+  const int lane = threadIdx.x & 31;
+  const int sv[8] = {(int)(a0 & 0xFFFFu), (int)(a1 & 0xFFFFu), (int)(a0 >> 16), (int)(a1 >> 16),
+                     (int)(a2 & 0xFFFFu), (int)(a3 & 0xFFFFu), (int)(a2 >> 16), (int)(a3 >> 16)};
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int qi = qd * 8 + i;
+    bool p = (pm >> i) & 1u;
+    if (!__any_sync(kFull, p)) continue;
+    uint64_t key = 0;
+    if (p) {
+      key = make_key(ah_float_score(sv[i] - off128, meta->inv[qi], meta->bias[qi]),
+                     ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
+      p = key < meta->tau[qi];
+    }
+    const uint32_t m = __ballot_sync(kFull, p);
+    if (m) {
+      const uint32_t qq = meta->q[qi];
+      const int leader = __ffs(m) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(&w.cnt[qq], (uint32_t)__popc(m));
+      base = __shfl_sync(kFull, base, leader);
+      if (p) {
+        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = key;
+        else w.ovf[qq] = 1u;
+      }
+    }
+  }
+}
+
 template <int W, int NL>
 __global__ void __launch_bounds__(kScanThreads)
 scan_main_kernel(DevIndex ix, ScanWork w) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint2* tables = reinterpret_cast<uint2*>(smem);  // [octs per item][W*128] 64-bit entries
-  __shared__ uint32_t s_q[kMaxQPI];
-  __shared__ int s_thr[kMaxQPI];
-  __shared__ uint64_t s_tau[kMaxQPI];
-  __shared__ float s_inv[kMaxQPI], s_bias[kMaxQPI];
+  __shared__ ItemMeta meta;
+  uint32_t (&s_q)[kMaxQPI] = meta.q;
+  int (&s_thr)[kMaxQPI] = meta.thr;
+  uint64_t (&s_tau)[kMaxQPI] = meta.tau;
+  float (&s_inv)[kMaxQPI] = meta.inv;
+  float (&s_bias)[kMaxQPI] = meta.bias;
   __shared__ uint32_t s_item, s_leaf;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nlast = (int)ix.B - 8 * (W - 1);
@@ -511,42 +554,15 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
             ad[8 * j + k] = tb32 + (8 * j + k) * 128 +
                             ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
       }
+      // fast path inline (8 compares per oct), candidate push out of line: the scoring loops of the
+      // octs are unrolled copies and must stay inside the instruction cache
       auto filter = [&](const uint32_t qd, const uint32_t (&acc)[4]) {
         const int sv[8] = {(int)(acc[0] & 0xFFFFu), (int)(acc[1] & 0xFFFFu), (int)(acc[0] >> 16), (int)(acc[1] >> 16),
                            (int)(acc[2] & 0xFFFFu), (int)(acc[3] & 0xFFFFu), (int)(acc[2] >> 16), (int)(acc[3] >> 16)};
-        bool pv[8];
-        bool any = false;
+        uint32_t pm = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          pv[i] = valid && sv[i] <= s_thr[qd * 8 + i];
-          any |= pv[i];
-        }
-        if (__any_sync(kFull, any)) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int qi = qd * 8 + i;
-            bool p = pv[i];
-            uint64_t key = 0;
-            if (p) {
-              key = make_key(ah_float_score(sv[i] - off128, s_inv[qi], s_bias[qi]),
-                             ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
-              p = key < s_tau[qi];
-            }
-            const uint32_t m = __ballot_sync(kFull, p);
-            if (m) {
-              const uint32_t qq = s_q[qi];
-              const int leader = __ffs(m) - 1;
-              uint32_t base = 0;
-              if (lane == leader) base = atomicAdd(&w.cnt[qq], (uint32_t)__popc(m));
-              base = __shfl_sync(kFull, base, leader);
-              if (p) {
-                const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-                if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = key;
-                else w.ovf[qq] = 1u;
-              }
-            }
-          }
-        }
+        for (int i = 0; i < 8; ++i) pm |= (valid && sv[i] <= s_thr[qd * 8 + i]) ? (1u << i) : 0u;
+        if (__any_sync(kFull, pm != 0)) push_candidates(ix, w, &meta, qd, acc[0], acc[1], acc[2], acc[3], pm, gslot, off128);
       };
 #define SB_DO_QUAD(QD)                                       \
   if (QD < nquads) {                                         \
@@ -554,7 +570,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
     score_oct_addr<W, NL, QD>(ad, nlast, w.one, acc);        \
     filter(QD, acc);                                         \
   }
-      SB_DO_QUAD(0) SB_DO_QUAD(1) SB_DO_QUAD(2) SB_DO_QUAD(3)
+      SB_DO_QUAD(0) SB_DO_QUAD(1)
 #undef SB_DO_QUAD
     }
   }
