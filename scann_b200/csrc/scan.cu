@@ -30,6 +30,13 @@
 #include "exact_math.cuh"
 #include "kernels.h"
 
+// How the main scan accumulates the four u16-lane registers of an oct lookup:
+//   0 = plain adds (ptxas merges pairs into IADD3 on the ALU pipe), 1 = two on ALU + two IMAD on the
+//   FMA pipe, 2 = all four as IMAD.  Measured on B200 (C2): see DESIGN.md.
+#ifndef SB_SCAN_ACC
+#define SB_SCAN_ACC 2
+#endif
+
 namespace sb {
 
 constexpr uint32_t kInvalidQuery = 0xFFFFFFFFu;
@@ -102,10 +109,19 @@ __device__ __forceinline__ void score_oct_addr(const uint32_t (&ad)[8 * W], int 
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8));
     const uint32_t xe = vx & 0x00FF00FFu, xo = __byte_perm(vx, 0u, 0x4341);
     const uint32_t ye = vy & 0x00FF00FFu, yo = __byte_perm(vy, 0u, 0x4341);
+#if SB_SCAN_ACC == 0
+    (void)one;
+    e0 += xe; o0 += xo; e1 += ye; o1 += yo;
+#elif SB_SCAN_ACC == 1
+    e0 += xe; o0 += xo;
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e1) : "r"(ye), "r"(one));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(o1) : "r"(yo), "r"(one));
+#else
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e0) : "r"(xe), "r"(one));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(o0) : "r"(xo), "r"(one));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e1) : "r"(ye), "r"(one));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(o1) : "r"(yo), "r"(one));
+#endif
   }
   acc[0] = e0; acc[1] = o0; acc[2] = e1; acc[3] = o1;  // (s0,s2) (s1,s3) (s4,s6) (s5,s7) as u16 lanes
 }
