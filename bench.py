@@ -109,6 +109,16 @@ def measured_peak():
   return 6650.0, "fallback"
 
 
+def ncu_traffic(name):
+  """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+  ncu --set full capture of this workload (profiles/); None if the summary is missing."""
+  try:
+    t = json.load(open(os.path.join(ROOT, "profiles", name)))
+    return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+  except Exception:
+    return None
+
+
 def recall_at_k(found, truth):
   k = truth.shape[1]
   hit = 0
@@ -320,7 +330,8 @@ def main():
       "clocks": sampler.summary(),
       "roofline": {"bound": "hbm", "kernel": "scan_main_kernel<W>", "achieved": achieved, "peak": peak,
                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                   "traffic": None, "alg_bytes_per_launch": bytes_per_launch, "ms_per_launch": ms_per_launch,
+                   "traffic": ncu_traffic("r01_scan_main_traffic.json") if args.workload == "c2_glove_shape" else None,
+                   "alg_bytes_per_launch": bytes_per_launch, "ms_per_launch": ms_per_launch,
                    "lookups_per_s": 2 * bytes_per_launch / (ms_per_launch * 1e-3) if ms_per_launch else None},
       "stage_ms_per_step": {s: agg[s] / args.steps for s in agg if s.startswith("ms_")},
       "overflow_retries": int(agg.get("overflow_retries", 0)),
