@@ -175,8 +175,8 @@ def main():
   if world > 1:
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-      os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line only)
+    # stdout carries exactly one JSON line: NCCL's version banner / warnings go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
 
   from scann_b200 import _lib
