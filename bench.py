@@ -47,6 +47,28 @@ def log(*a):
   print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly one JSON line.  Libraries loaded by the run (NCCL's version banner, for one)
+# write to fd 1 directly, so fd 1 is pointed at stderr for the whole run and the result line goes to a
+# saved duplicate of the original stdout.
+_RESULT_FD = None
+
+
+def _claim_stdout():
+  global _RESULT_FD
+  if _RESULT_FD is None:
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+  line = (json.dumps(obj) + "\n").encode()
+  sys.stdout.flush()
+  fd = 1 if _RESULT_FD is None else _RESULT_FD
+  while line:
+    line = line[os.write(fd, line):]
+
+
 def make_data(wl):
   from scann_b200 import datasets
   db = datasets.clustered(wl["n"], wl["d"], wl["clusters"], seed=wl["seed"], centers_seed=100 + wl["seed"],
@@ -175,8 +197,6 @@ def main():
   if world > 1:
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    # stdout carries exactly one JSON line: NCCL's version banner / warnings go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
 
   from scann_b200 import _lib
@@ -357,7 +377,7 @@ def main():
                            "sample": f"first {min(args.cpu_sample, nq)} queries of the step, batches of 256 "
                                      f"(search_batched_parallel semantics), AVX2 vpshufb oracle",
                            "single_thread_qps": qps1, "ids_equal_gpu_first_64": parity}
-  print(json.dumps(out), flush=True)
+  emit(out)
   if dist is not None:
     dist.destroy_process_group()
   return 0
@@ -406,15 +426,14 @@ def run_bruteforce(args, wl, rank, world, local_rank):
     oracle.bruteforce_bf16(bits, q[:sample], k, threads=threads)
     dt = time.perf_counter() - t0
     qps = sample / dt
-    print(json.dumps({"impl": "reference", "metric": "batched QPS, bf16 brute-force MIPS k=100", "value": qps,
+    emit({"impl": "reference", "metric": "batched QPS, bf16 brute-force MIPS k=100", "value": qps,
                       "unit": "queries/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 db x f32 query",
                       "data": "synthetic", "config": {"workload": args.workload, "n": n, "d": d, "k": k,
                                                       "queries_per_step": sample},
                       "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                                        "sample": f"{sample} queries, one per thread"},
-                      "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}),
-          flush=True)
+                      "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     return 0
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
@@ -474,7 +493,7 @@ def run_bruteforce(args, wl, rank, world, local_rank):
                       "frac": flops / gemm_s / 1e12 / peak, "traffic": None,
                       "useful_tflops_f32_equivalent": flops / 2 / gemm_s / 1e12},
          "stage_ms_per_step": {s: agg[s] / args.steps for s in agg if s.startswith("ms_")}}
-  print(json.dumps(out), flush=True)
+  emit(out)
   return 0
 
 
@@ -508,9 +527,10 @@ def run_reference(args, wl):
                        "sample": f"{sample} queries per step, batches of 256 over {threads} threads"},
       "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
-  print(json.dumps(out), flush=True)
+  emit(out)
   return 0
 
 
 if __name__ == "__main__":
+  _claim_stdout()
   sys.exit(main())
