@@ -33,13 +33,10 @@ namespace bf {
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kSplits = 2;
-constexpr int kStages = 3;
 constexpr int kABytes = BM * BK * 2;                       // 16 KB per split
 constexpr int kBBytes = BN * BK * 2;                       // 32 KB
-constexpr int kStageBytes = kSplits * kABytes + kBBytes;   // 64 KB
 constexpr int kThreads = 256;                              // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
-constexpr int kTmemCols = 256;
-constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024;
+constexpr int kTmemCols = 512;                             // two 256-column fp32 accumulators
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,29 +97,54 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 struct GemmArgs {
-  uint32_t nq, n_total, m_pad;   // queries, database rows, padded query rows per split
-  uint32_t row0, row1;           // database rows [row0, row1) of this round
-  uint32_t num_kb;               // ceil(D / 64)
+  uint32_t nq, m_pad;            // valid A rows, padded A rows per split
+  uint32_t mt, nt;               // tiles along M (A rows) and N (B rows of this launch)
+  uint32_t row0, row1;           // B rows [row0, row1) of this launch
+  uint32_t num_kb;               // ceil(K / 64)
+  // kEpiFilter: candidate buffers
   uint64_t* buf; uint32_t* cnt; const uint64_t* tau; uint32_t* ovf; uint32_t cap;
+  // kEpiStore: raw accumulators, out[a_row * ld + b_row]
+  float* out; uint32_t ld;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int kEpiFilter = 0, kEpiStore = 1;
+
+template <int kSplitsT>
+struct StageLayout {
+  static constexpr int kBytes = kSplitsT * kABytes + kBBytes;
+  static constexpr int kStagesT = kSplitsT == 1 ? 4 : 3;
+  static constexpr size_t kSmem = (size_t)kStagesT * kBytes + 1024;
+};
+
+// Persistent GEMM: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the A
+// (query) tile index fastest, so the CTAs resident at any moment share a couple of B tiles through
+// L2 while the whole A operand stays L2-resident.  The fp32 accumulator is double-buffered in TMEM
+// (2 x 256 columns): the epilogue warps drain tile i while the MMA warp already accumulates tile
+// i + 1.
+template <int kSplitsT, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
+  using SL = StageLayout<kSplitsT>;
+  constexpr int kSt = SL::kStagesT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+  __shared__ __align__(8) uint64_t full_bar[kSt], empty_bar[kSt], tmem_full_bar[2], tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ uint32_t s_masks[kEpi == kEpiFilter ? BN / 32 : 1][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t n0 = a.row0 + blockIdx.x * BN;
-  const uint32_t m0 = blockIdx.y * BM;
+  const uint32_t total_tiles = a.mt * a.nt;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    for (int i = 0; i < kSt; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -136,67 +158,133 @@ gemm_filter_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {  // ---- TMA producer ----
-      for (uint32_t kb = 0; kb < a.num_kb; ++kb) {
-        const int st = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1);
-        uint8_t* base = smem + (size_t)st * kStageBytes;
-        mbar_expect_tx(&full_bar[st], kStageBytes);
-        for (int s = 0; s < kSplits; ++s)
-          tma_load_2d(base + s * kABytes, &tmA, &full_bar[st], (int)(kb * BK), (int)(s * a.m_pad + m0));
-        tma_load_2d(base + kSplits * kABytes, &tmB, &full_bar[st], (int)(kb * BK), (int)n0);
+      uint32_t it = 0;  // running k-block counter across tiles
+      for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const uint32_t m0 = (t % a.mt) * BM, n0 = a.row0 + (t / a.mt) * BN;
+        for (uint32_t kb = 0; kb < a.num_kb; ++kb, ++it) {
+          const int st = it % kSt;
+          const uint32_t ph = (it / kSt) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          uint8_t* base = smem + (size_t)st * SL::kBytes;
+          mbar_expect_tx(&full_bar[st], SL::kBytes);
+          for (int s = 0; s < kSplitsT; ++s)
+            tma_load_2d(base + s * kABytes, &tmA, &full_bar[st], (int)(kb * BK), (int)(s * a.m_pad + m0));
+          tma_load_2d(base + kSplitsT * kABytes, &tmB, &full_bar[st], (int)(kb * BK), (int)n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---- MMA issuer ----
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      for (uint32_t kb = 0; kb < a.num_kb; ++kb) {
-        const int st = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[st], ph);
+      uint32_t it = 0, lt = 0;
+      for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1);  // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sbase = smem_u32(smem + (size_t)st * kStageBytes);
-        const uint32_t sB = sbase + kSplits * kABytes;
+        const uint32_t tacc = tmem + as * BN;
+        for (uint32_t kb = 0; kb < a.num_kb; ++kb, ++it) {
+          const int st = it % kSt;
+          const uint32_t ph = (it / kSt) & 1;
+          mbar_wait(&full_bar[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sbase = smem_u32(smem + (size_t)st * SL::kBytes);
+          const uint32_t sB = sbase + kSplitsT * kABytes;
 #pragma unroll
-        for (int s = 0; s < kSplits; ++s) {
+          for (int s = 0; s < kSplitsT; ++s) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128(sbase + s * kABytes + k * 32);
-            const uint64_t bd = umma_desc_sw128(sB + k * 32);
-            umma_bf16(tmem, ad, bd, idesc, (kb | (uint32_t)s | (uint32_t)k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(sbase + s * kABytes + k * 32);
+              const uint64_t bd = umma_desc_sw128(sB + k * 32);
+              umma_bf16(tacc, ad, bd, idesc, (kb | (uint32_t)s | (uint32_t)k) != 0 ? 1u : 0u);
+            }
           }
+          umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[st]);  // frees the smem stage once these MMAs have read it
-      }
-      umma_commit(&tmem_full_bar);    // accumulator complete
-    }
-  } else if (warp >= 4) {  // ---- epilogue: TMEM -> threshold filter -> candidate buffers ----
-    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
-    const uint32_t q = m0 + quad * 32 + lane;      // one TMEM lane = one query
-    const bool qvalid = q < a.nq;
-    const uint64_t tau = qvalid ? a.tau[q] : 0ull;
-    const uint32_t tau_ord = (uint32_t)(tau >> 32);
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c, v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const uint32_t dp = n0 + c + j;
-        const float dist = -__uint_as_float(v[j]);  // DotProductDistance = -<q, x>
-        const uint32_t o = f2ord(dist);
-        if (qvalid && o <= tau_ord && dp < a.row1) {
-          const uint64_t key = ((uint64_t)o << 32) | dp;
-          if (key < tau) {
-            const uint32_t pos = atomicAdd(&a.cnt[q], 1u);
-            if (pos < a.cap) a.buf[(size_t)q * a.cap + pos] = key;
-            else a.ovf[q] = 1u;
-          }
-        }
+        umma_commit(&tmem_full_bar[as]);  // accumulator complete
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp >= 4) {  // ---- epilogue: one TMEM lane = one A row (query) ----
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    uint32_t lt = 0;
+    for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      const uint32_t m0 = (t % a.mt) * BM, n0 = a.row0 + (t / a.mt) * BN;
+      const uint32_t q = m0 + quad * 32 + lane;
+      const bool qvalid = q < a.nq;
+      const uint32_t tbase = tmem + as * BN + ((uint32_t)(quad * 32) << 16);
+      if (kEpi == kEpiFilter) {
+        const uint64_t tau = qvalid ? a.tau[q] : 0ull;
+        const uint32_t tau_ord = (uint32_t)(tau >> 32), tau_lo = (uint32_t)tau;
+        mbar_wait(&tmem_full_bar[as], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // pass 1: which of this query's 256 scores beat its threshold key
+        uint32_t* masks = &s_masks[0][threadIdx.x - 128];  // [chunk][epilogue thread]
+        uint32_t total = 0;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)(c * 32), v);
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t dp = n0 + c * 32 + j;
+            const uint32_t o = f2ord(-__uint_as_float(v[j]));  // DotProductDistance = -<q, x>
+            const bool pass = (o < tau_ord || (o == tau_ord && dp < tau_lo)) && dp < a.row1;
+            m |= (pass ? 1u : 0u) << j;
+          }
+          m = qvalid ? m : 0u;
+          masks[c * 128] = m;
+          total += __popc(m);
+        }
+        // one reservation per (query, tile), then pass 2 re-reads only the chunks with survivors
+        uint32_t pos = total ? atomicAdd(&a.cnt[q], total) : 0u;
+        if (__any_sync(0xFFFFFFFFu, total != 0)) {
+          uint64_t* dst = a.buf + (size_t)q * a.cap;
+#pragma unroll 1
+          for (int c = 0; c < BN / 32; ++c) {
+            const uint32_t m = masks[c * 128];
+            if (__any_sync(0xFFFFFFFFu, m != 0)) {
+              uint32_t v[32];
+              tmem_ld32(tbase + (uint32_t)(c * 32), v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if ((m >> j) & 1u) {
+                  const uint32_t dp = n0 + c * 32 + j;
+                  const uint32_t o = f2ord(-__uint_as_float(v[j]));
+                  if (pos < a.cap) dst[pos] = ((uint64_t)o << 32) | dp;
+                  else a.ovf[q] = 1u;
+                  ++pos;
+                }
+              }
+            }
+          }
+        }
+      } else {
+        mbar_wait(&tmem_full_bar[as], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* dst = a.out + (size_t)q * a.ld;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)(c * 32), v);
+          const uint32_t col = n0 + c * 32;
+          if (qvalid) {
+            if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(dst + col + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < a.row1) dst[col + j] = __uint_as_float(v[j]);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+    }
   }
   __syncthreads();
   if (warp == 2) {
@@ -320,6 +408,29 @@ cudaError_t bf_init_state(uint32_t nq, uint32_t* cnt, uint64_t* tau, uint32_t* o
   return cudaGetLastError();
 }
 
+static int sm_count() {
+  static int sms = [] {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n > 0 ? n : 148;
+  }();
+  return sms;
+}
+
+template <int kSplitsT, int kEpi>
+static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const bf::GemmArgs& a, cudaStream_t s) {
+  using SL = bf::StageLayout<kSplitsT>;
+  cudaError_t e = cudaFuncSetAttribute(bf::gemm_kernel<kSplitsT, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SL::kSmem);
+  if (e != cudaSuccess) return e;
+  const uint32_t tiles = a.mt * a.nt;
+  if (tiles == 0) return cudaSuccess;
+  const uint32_t grid = tiles < (uint32_t)sm_count() ? tiles : (uint32_t)sm_count();  // persistent, one CTA per SM
+  bf::gemm_kernel<kSplitsT, kEpi><<<grid, bf::kThreads, SL::kSmem, s>>>(tmA, tmB, a);
+  return cudaGetLastError();
+}
+
 // One round: database rows [row0, row1) against all queries.
 cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, uint32_t n_total, uint32_t dpitch,
                           uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s) {
@@ -329,15 +440,29 @@ cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, ui
   if (e != cudaSuccess) return e;
   e = make_tmap(&tmB, db, n_total, dpitch, dpitch, bf::BN);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(bf::gemm_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::kSmemBytes);
-  if (e != cudaSuccess) return e;
   bf::GemmArgs a{};
-  a.nq = nq; a.n_total = n_total; a.m_pad = m_pad; a.row0 = row0; a.row1 = row1;
+  a.nq = nq; a.m_pad = m_pad; a.row0 = row0; a.row1 = row1;
+  a.mt = m_pad / bf::BM; a.nt = (row1 - row0 + bf::BN - 1) / bf::BN;
   a.num_kb = (dpitch + bf::BK - 1) / bf::BK;
   a.buf = w.buf; a.cnt = w.cnt; a.tau = w.tau; a.ovf = w.ovf; a.cap = w.cap;
-  dim3 grid((row1 - row0 + bf::BN - 1) / bf::BN, m_pad / bf::BM);
-  bf::gemm_filter_kernel<<<grid, bf::kThreads, bf::kSmemBytes, s>>>(tmA, tmB, a);
-  return cudaGetLastError();
+  return launch_gemm<bf::kSplits, bf::kEpiFilter>(tmA, tmB, a, s);
+}
+
+// Plain C[a_row][b_row] = sum_k A[a_row][k] * B[b_row][k] (bf16 operands, fp32 accumulate and output): the
+// tokenization pre-filter's GEMM (prep.cu), K = the concatenated hi/lo terms.
+cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows_pad, const void* b_operand,
+                         uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s) {
+  CUtensorMap tmA, tmB;
+  cudaError_t e = make_tmap(&tmA, a_operand, a_rows_pad, kpitch, kpitch, bf::BM);
+  if (e != cudaSuccess) return e;
+  e = make_tmap(&tmB, b_operand, b_rows, kpitch, kpitch, bf::BN);
+  if (e != cudaSuccess) return e;
+  bf::GemmArgs a{};
+  a.nq = a_rows; a.m_pad = a_rows_pad; a.row0 = 0; a.row1 = b_rows;
+  a.mt = a_rows_pad / bf::BM; a.nt = (b_rows + bf::BN - 1) / bf::BN;
+  a.num_kb = (kpitch + bf::BK - 1) / bf::BK;
+  a.out = out; a.ld = ld;
+  return launch_gemm<1, bf::kEpiStore>(tmA, tmB, a, s);
 }
 
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,

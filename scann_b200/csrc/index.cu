@@ -484,9 +484,13 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   CU(cudaEventRecord(ix->ev[EV_TOK], s));
   // rounds: the first one must hold >= k' rows (everything passes an infinite threshold) and fit
   // the candidate buffers; afterwards the inflow per round is ~ k' * growth
+  // (every row seen so far has a 1-in-rows chance per kept slot, so a round over g x the rows seen
+  // pushes ~ g * k' keys).  Rounds are sized so that k' * (1 + g) stays within the 1024 keys the
+  // one-CTA-per-query compaction sorts in shared memory.
   uint32_t row0 = 0;
-  uint32_t chunk = std::max<uint32_t>(4096, 4 * kprime);
+  uint32_t chunk = std::max<uint32_t>(1024, (kprime + 255) / 256 * 256);
   chunk = std::min(chunk, cap / 2);
+  const uint32_t growth = 3 * kprime <= 1000 ? 2 : (2 * kprime <= 1000 ? 1 : 2);
   while (row0 < v.n) {
     const uint32_t row1 = (uint64_t)row0 + chunk >= v.n ? v.n : row0 + chunk;
     CU(sb::bf_gemm_round(ix->bf_a.p, ix->bf_db.p, nq, v.n, ix->bf_dpitch, row0, row1, w, s));
@@ -494,7 +498,7 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
     launches += 1 + (cap > 1024 ? 2 : 1);
     gemm_launches += 1;
     row0 = row1;
-    chunk = (uint32_t)std::min<uint64_t>((uint64_t)row1 * 3, 0x40000000ull);  // next round: 3x what has been seen
+    chunk = (uint32_t)std::min<uint64_t>((uint64_t)row1 * growth, 0x40000000ull);
   }
   CU(cudaEventRecord(ix->ev[EV_SCAN], s));
   uint32_t* hc = ix->h_counters.as<uint32_t>();

@@ -94,6 +94,10 @@ cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, ui
                           uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s);
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
                        uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t* out_idx, float* out_dist, cudaStream_t s);
+// out[a_row * ld + b_row] = sum_k A[a_row][k] * B[b_row][k]; bf16 operands with row pitch kpitch (multiple of 64),
+// a_rows_pad a multiple of 128 (padding rows readable), fp32 accumulate on tcgen05.
+cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows_pad, const void* b_operand,
+                         uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s);
 // ---- debug ----
 void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s);
 
