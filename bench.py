@@ -355,6 +355,7 @@ def main():
                    "lookups_per_s": 2 * bytes_per_launch / (ms_per_launch * 1e-3) if ms_per_launch else None},
       "stage_ms_per_step": {s: agg[s] / args.steps for s in agg if s.startswith("ms_")},
       "overflow_retries": int(agg.get("overflow_retries", 0)),
+      "tokenize_fallbacks_per_step": agg.get("tokenize_fallbacks", 0) / args.steps,
       "candidates_per_query": {"mean": agg.get("cand_sum", 0) / (nq * args.steps), "max_over_steps_sum": int(agg.get("cand_max", 0))},
   }
   if db_sharded is not None:

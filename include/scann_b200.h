@@ -169,6 +169,7 @@ typedef struct {
   uint32_t scan_kernel_count; /* launches of the dominant LUT16 scan kernel in the last call */
   uint64_t cand_sum;          /* candidates buffered per query after the main scan, summed */
   uint64_t cand_max;          /* ... and the maximum over queries */
+  uint64_t tokenize_fallbacks; /* queries whose tensor-core tokenization pre-filter fell back to exact distances */
 } scann_b200_stats;
 /* Timing (CUDA events on the index's stream) and traffic figures of the last search call. */
 int scann_b200_last_stats(scann_b200_index* index, scann_b200_stats* out);

@@ -36,6 +36,7 @@ class Stats(C.Structure):
       ("ms_worklist", C.c_float), ("ms_scan", C.c_float), ("ms_compact", C.c_float),
       ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("scan_kernel_count", C.c_uint32),
       ("cand_sum", C.c_uint64), ("cand_max", C.c_uint64),
+      ("tokenize_fallbacks", C.c_uint64),
   ]
 
   def as_dict(self):

@@ -98,9 +98,9 @@ struct scann_b200_index {
   std::vector<uint32_t> h_leaf_size;
   // persistent device arrays
   DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
-      codes, slot_dp, slot_tie, dataset, dp_row;
+      codes, slot_dp, slot_tie, dataset, dp_row, tok_b;
   // workspace
-  DevBuf q, dist, leaves, bias, lut, mult, inv, pilot_end, buf, cnt, tau, ovf, leaf_cnt, leaf_eoff,
+  DevBuf tok_a, q, dist, leaves, bias, lut, mult, inv, pilot_end, buf, cnt, tau, ovf, leaf_cnt, leaf_eoff,
       leaf_cur, item_off, entry_q, entry_bias, counters, stats, out_idx, out_dist;
   PinnedBuf h_q, h_idx, h_dist, h_counters;
   cudaEvent_t ev[EV_COUNT] = {};
@@ -273,6 +273,21 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   }
 #undef UP
   v.centers = ix->centers.as<float>();
+  {
+    // bf16 centre operand of the tensor-core tokenization (prep.cu) and the norm bound of its error term
+    double cmax2 = 0.0;
+    for (uint32_t l = 0; l < L; ++l) {
+      double a = 0.0;
+      for (uint32_t k = 0; k < D; ++k) a += (double)d->centers[(size_t)l * D + k] * (double)d->centers[(size_t)l * D + k];
+      cmax2 = std::max(cmax2, a);
+    }
+    v.center_max_norm = (float)(std::sqrt(cmax2) * 1.0001);
+    v.tok_kp = sb::tokenize_kpitch(D);
+    CU(ix->tok_b.ensure(sb::tokenize_operand_bytes(L, D)));
+    CU(sb::build_tokenize_operand(v.centers, L, D, 2, ix->tok_b.p, 0));
+    CU(cudaStreamSynchronize(0));
+    v.tok_b = ix->tok_b.p;
+  }
   v.centers_t = nullptr;
   v.center_sqnorm = ix->cnorm.as<float>();
   v.codebook = ix->codebook.as<float>();
@@ -333,6 +348,7 @@ int ensure_workspace(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_
   const sb::DevIndex& v = ix->dev;
   CU(ix->q.ensure(sizeof(float) * (size_t)nq * v.d));
   CU(ix->dist.ensure(sizeof(float) * (size_t)nq * v.L));
+  CU(ix->tok_a.ensure(sb::tokenize_operand_bytes(nq, v.d)));
   CU(ix->leaves.ensure(sizeof(int32_t) * (size_t)nq * p.P));
   CU(ix->bias.ensure(sizeof(float) * (size_t)nq * p.P));
   CU(ix->lut.ensure((size_t)nq * v.W * 128));
@@ -383,10 +399,8 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
   CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
   CU(cudaEventRecord(ix->ev[EV_START], s));
-  sb::launch_tokenize(v, d_q, nq, ix->dist.as<float>(), s);
-  sb::launch_topp(v, ix->dist.as<float>(), nq, p.P, ix->leaves.as<int32_t>(), ix->bias.as<float>(), s);
-  launches += 2;
-  CU(cudaGetLastError());
+  CU(sb::launch_tokenize_topp(v, d_q, nq, p.P, ix->dist.as<float>(), ix->tok_a.p, ix->leaves.as<int32_t>(),
+                              ix->bias.as<float>(), w.counters + 5, s, &launches));
   CU(cudaEventRecord(ix->ev[EV_TOK], s));
   sb::launch_lut(v, d_q, nq, ix->lut.as<uint8_t>(), ix->mult.as<float>(), ix->inv.as<float>(), s);
   launches += 1;
@@ -408,6 +422,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   uint32_t* hc = ix->h_counters.as<uint32_t>();
   CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  const uint32_t tok_fallbacks = hc[5];
   while (hc[2] != 0) {
     if (++retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
     CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
@@ -438,6 +453,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   st.scan_lookups += hs[0] * 2;
   st.cand_sum += hs[2];
   st.cand_max = std::max<uint64_t>(st.cand_max, hs[3]);
+  st.tokenize_fallbacks += tok_fallbacks;
   st.kernel_launches += (uint32_t)launches;
   st.overflow_retries += retries;
   st.scan_kernel_count += scan_launches;
@@ -692,9 +708,8 @@ int scann_b200_debug_tokenize(scann_b200_index* ix, const float* queries, uint32
   const sb::DevIndex& v = ix->dev;
   if (int rc = ensure_workspace(ix, nq, p, 1, pick_cap(p.nover))) return rc;
   CU(cudaMemcpyAsync(ix->q.p, queries, sizeof(float) * (size_t)nq * v.d, cudaMemcpyHostToDevice, ix->stream));
-  sb::launch_tokenize(v, ix->q.as<float>(), nq, ix->dist.as<float>(), ix->stream);
-  sb::launch_topp(v, ix->dist.as<float>(), nq, p.P, ix->leaves.as<int32_t>(), ix->bias.as<float>(), ix->stream);
-  CU(cudaGetLastError());
+  CU(sb::launch_tokenize_topp(v, ix->q.as<float>(), nq, p.P, ix->dist.as<float>(), ix->tok_a.p,
+                              ix->leaves.as<int32_t>(), ix->bias.as<float>(), nullptr, ix->stream, nullptr));
   CU(cudaMemcpyAsync(out_leaf, ix->leaves.p, sizeof(int32_t) * (size_t)nq * p.P, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaMemcpyAsync(out_dist, ix->bias.p, sizeof(float) * (size_t)nq * p.P, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));

@@ -33,6 +33,10 @@ struct DevIndex {
   const uint32_t* slot_tie;   // [groups*32] slot of the datapoint in the unsharded index (NULL = identity)
   const float* dataset;       // [rows][D] f32 rows for exact reordering (NULL if none)
   const uint32_t* dp_row;     // [N] datapoint id -> row of `dataset` (NULL = identity)
+  // tensor-core tokenization (prep.cu): centres as the bf16 operand [L][tok_kp] = [hi | hi | lo | 0]
+  const void* tok_b;
+  uint32_t tok_kp;
+  float center_max_norm;      // >= max_l ||c_l||
 };
 
 struct ScanWork {
@@ -65,6 +69,14 @@ void launch_topp(const DevIndex& ix, const float* dist, uint32_t nq, uint32_t P,
                  float* bias, cudaStream_t s);
 void launch_lut(const DevIndex& ix, const float* q, uint32_t nq, uint8_t* lut, float* mult,
                 float* inv_mult, cudaStream_t s);
+// tokenization + top-P in one call: tcgen05 GEMM pre-filter + exact refinement when the index carries the bf16
+// centre operand (tokenize_tensor_path), else the SIMT pair above.  `a_ws` holds tokenize_operand_bytes(nq, d).
+uint32_t tokenize_kpitch(uint32_t d);
+size_t tokenize_operand_bytes(uint32_t rows, uint32_t d);
+cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, int lo_term, void* out, cudaStream_t s);
+bool tokenize_tensor_path(const DevIndex& ix, uint32_t P);
+cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq, uint32_t P, float* dist, void* a_ws,
+                                 int32_t* leaves, float* bias, uint32_t* fallbacks, cudaStream_t s, int* launches);
 // ---- scan ----
 size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover);
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item);

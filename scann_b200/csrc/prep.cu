@@ -4,7 +4,10 @@
 //         partitioning/kmeans_tree_partitioner.cc:642-730, many_to_many_impl.inc:522-567
 // (a5)    AsymmetricQueryer::CreateLookupTable hashes/asymmetric_hashing2/querying.h:284-329,
 //         hashes/internal/asymmetric_hashing_impl.cc:505-645
+#include <cuda_bf16.h>
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "exact_math.cuh"
@@ -188,60 +191,74 @@ topp_kernel(const float* __restrict__ dist, int L, int P, int Ppow2, int32_t* __
 // covers every configuration of BASELINE.json.  8 queries per 256-thread block.
 constexpr int kToppWarpMaxP = 256;
 
-__global__ void __launch_bounds__(256)
-topp_warp_kernel(const float* __restrict__ dist, int nq, int L, int P, int Ppow2,
-                 int32_t* __restrict__ leaves, float* __restrict__ bias) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int q = blockIdx.x * 8 + warp;
-  if (q >= nq) return;
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw) + warp * 256;
-  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 8 * 256 * 4) + (size_t)warp * Ppow2;
-  const float* row = dist + (size_t)q * L;
-  const uint32_t lt = (1u << lane) - 1u;
-  uint32_t prefix = 0, mask = 0, need = (uint32_t)P;
-  if (P < L) {
-    for (int shift = 24; shift >= 0; shift -= 8) {
+// MSB radix select by one warp: returns the order-image `prefix` of the P-th smallest value of
+// ordfn(0..L-1) and, in `need`, how many elements equal to it belong to the P smallest.
+template <typename F>
+__device__ __forceinline__ uint32_t warp_radix_select(F ordfn, int L, uint32_t P, uint32_t* hist, int lane,
+                                                      uint32_t& need_out) {
+  uint32_t prefix = 0, mask = 0, need = P;
+  for (int shift = 24; shift >= 0; shift -= 8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) hist[lane * 8 + k] = 0;
-      __syncwarp();
-      for (int i = lane; i < L; i += 32) {
-        const uint32_t o = f2ord(row[i]);
-        if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+    for (int k = 0; k < 8; ++k) hist[lane * 8 + k] = 0;
+    __syncwarp();
+    for (int i = lane; i < L; i += 32) {
+      const uint32_t o = ordfn(i);
+      if ((o & mask) == prefix) atomicAdd(&hist[(o >> shift) & 255u], 1u);
+    }
+    __syncwarp();
+    uint32_t c[8], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; tot += c[k]; }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= need);
+    const int tl = hit ? (__ffs(hit) - 1) : 31;
+    uint32_t digit = 255, nneed = need;
+    if (lane == tl) {
+      uint32_t cum = incl - tot;
+      digit = (uint32_t)lane * 8 + 7;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; break; }
+        cum += c[k];
       }
-      __syncwarp();
-      uint32_t c[8], tot = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; tot += c[k]; }
-      uint32_t incl = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += t;
+      nneed = need - cum;
+    }
+    digit = __shfl_sync(0xFFFFFFFFu, digit, tl);
+    need = __shfl_sync(0xFFFFFFFFu, nneed, tl);
+    prefix |= digit << shift;
+    mask |= 0xFFu << shift;
+    __syncwarp();
+  }
+  need_out = need;
+  return prefix;
+}
+
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t* skeys, int n, int lane) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n >> 1); t += 32) {
+        const int l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int r = l | j;
+        const uint64_t a = skeys[l], b = skeys[r];
+        const bool up = (l & k) == 0;
+        if ((a > b) == up) { skeys[l] = b; skeys[r] = a; }
       }
-      const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= need);
-      const int tl = hit ? (__ffs(hit) - 1) : 31;
-      uint32_t digit = 255, nneed = need;
-      if (lane == tl) {
-        uint32_t cum = incl - tot;
-        digit = (uint32_t)lane * 8 + 7;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; break; }
-          cum += c[k];
-        }
-        nneed = need - cum;
-      }
-      digit = __shfl_sync(0xFFFFFFFFu, digit, tl);
-      need = __shfl_sync(0xFFFFFFFFu, nneed, tl);
-      prefix |= digit << shift;
-      mask |= 0xFFu << shift;
       __syncwarp();
     }
-  } else {
-    prefix = 0xFFFFFFFFu;
-    need = 0xFFFFFFFFu;
   }
+}
+
+// Exact top-P of one row of distances by one warp; writes P sorted (leaf, distance) pairs.
+__device__ __forceinline__ void warp_topp_exact(const float* row, int L, int P, int Ppow2, uint32_t* hist,
+                                                uint64_t* skeys, int lane, int32_t* leaves, float* bias) {
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t prefix = 0xFFFFFFFFu, need = 0xFFFFFFFFu;
+  if (P < L) prefix = warp_radix_select([&](int i) { return f2ord(row[i]); }, L, (uint32_t)P, hist, lane, need);
   for (int i = lane; i < Ppow2; i += 32) skeys[i] = kKeyMax;
   __syncwarp();
   uint32_t count = 0, base_eq = 0;
@@ -263,24 +280,25 @@ topp_warp_kernel(const float* __restrict__ dist, int nq, int L, int P, int Ppow2
     base_eq += __popc(m);
   }
   __syncwarp();
-  for (int k = 2; k <= Ppow2; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = lane; t < (Ppow2 >> 1); t += 32) {
-        const int l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int r = l | j;
-        const uint64_t a = skeys[l], b = skeys[r];
-        const bool up = (l & k) == 0;
-        if ((a > b) == up) { skeys[l] = b; skeys[r] = a; }
-      }
-      __syncwarp();
-    }
-  }
+  warp_bitonic_sort(skeys, Ppow2, lane);
   for (int i = lane; i < P; i += 32) {
     const uint64_t k = skeys[i];
     const uint32_t l = (uint32_t)k;
-    leaves[(size_t)q * P + i] = (k == kKeyMax) ? -1 : (int32_t)l;
-    bias[(size_t)q * P + i] = (k == kKeyMax) ? 0.f : row[l];
+    leaves[i] = (k == kKeyMax) ? -1 : (int32_t)l;
+    bias[i] = (k == kKeyMax) ? 0.f : row[l];
   }
+}
+
+__global__ void __launch_bounds__(256)
+topp_warp_kernel(const float* __restrict__ dist, int nq, int L, int P, int Ppow2,
+                 int32_t* __restrict__ leaves, float* __restrict__ bias) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * 8 + warp;
+  if (q >= nq) return;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw) + warp * 256;
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 8 * 256 * 4) + (size_t)warp * Ppow2;
+  warp_topp_exact(dist + (size_t)q * L, L, P, Ppow2, hist, skeys, lane, leaves + (size_t)q * P, bias + (size_t)q * P);
 }
 
 void launch_topp(const DevIndex& ix, const float* dist, uint32_t nq, uint32_t P, int32_t* leaves,
@@ -294,6 +312,382 @@ void launch_topp(const DevIndex& ix, const float* dist, uint32_t nq, uint32_t P,
   } else {
     topp_kernel<<<nq, kToppThreads, (size_t)pp * 8, s>>>(dist, (int)ix.L, (int)P, pp, leaves, bias);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// Tokenization on the tensor cores (north-star item 1): the query x centre contraction runs as a
+// bf16 tcgen05 GEMM (bruteforce.cu) and only the few centres that can belong to the top P are
+// re-scored with the reference's exact fp32 FMA chain, so the result is bit-identical to the SIMT
+// path above.
+//   * q = qh + ql (+ O(2^-18)), c = ch + cl (+ O(2^-18)) in bf16; operands are concatenated along
+//     K as A = [qh | ql | qh], B = [ch | ch | cl], so one plain GEMM yields qh.ch + ql.ch + qh.cl.
+//   * |approx - chain| <= eps(q) := (K * 2^-21 + 2^-15) * |q| * max|c| (dropped terms <= 4 * 2^-18,
+//     fp32 accumulation of K exact products <= K * 2^-22, the chain's own rounding <= D * 2^-24, all
+//     relative to sum |q_d c_d| <= |q| |c|), plus the fp32 roundings of |q|^2 + |c|^2 - 2S for L2.
+//   * With T = the P-th smallest approximate distance, every centre of the exact top P has an
+//     approximate distance <= T + 2 eps (otherwise P centres would be strictly closer).  Those
+//     candidates (P plus a handful) get the exact chain and are sorted by (distance, leaf).
+//   * If a query has more candidates than the warp's buffer (degenerate inputs: zero query, equal
+//     centres), the warp falls back to exact distances for all L centres.
+// ---------------------------------------------------------------------------------------
+__global__ void split_rows_kernel(const float* __restrict__ src, uint32_t rows, uint32_t d, uint32_t kp,
+                                  uint32_t rows_pad, int lo_term, __nv_bfloat16* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)rows_pad * kp) return;
+  const uint32_t r = (uint32_t)(i / kp), c = (uint32_t)(i % kp);
+  const uint32_t term = c / d, k = c % d;
+  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+  if (r < rows && term < 3) {
+    const float x = src[(size_t)r * d + k];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    v = ((int)term == lo_term) ? __float2bfloat16_rn(x - __bfloat162float(hi)) : hi;
+  }
+  out[i] = v;
+}
+
+uint32_t tokenize_kpitch(uint32_t d) { return (3 * d + 63) / 64 * 64; }
+size_t tokenize_operand_bytes(uint32_t rows, uint32_t d) {
+  return (size_t)((rows + 127) / 128 * 128) * tokenize_kpitch(d) * 2;
+}
+cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, int lo_term, void* out, cudaStream_t s) {
+  const uint32_t kp = tokenize_kpitch(d), rows_pad = (rows + 127) / 128 * 128;
+  const size_t total = (size_t)rows_pad * kp;
+  split_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, rows, d, kp, rows_pad, lo_term,
+                                                                     reinterpret_cast<__nv_bfloat16*>(out));
+  return cudaGetLastError();
+}
+
+constexpr int kRefineMaxCand = 512;
+
+// One warp per query.  The row of approximate distances is mapped to a fixed-point image
+//   u = min(uint((a - min) * 2^31 * (1 - 2^-10) / (max - min)), 2^31 - 1),
+// which is monotone in the distance and spreads the row evenly over the 256 bins of the first
+// radix pass (the leading sign/exponent bits of the float image are common to nearly all distances
+// of a query; a histogram over them only serialises shared-memory atomic conflicts).  The MSB radix
+// select on u stops as soon as everything up to the end of the pivot's bucket fits the candidate
+// buffer: an upper bound hi_u of the P-th smallest is all that is needed.  Candidates are the
+// centres with u <= hi_u + ceil(2 eps * scale) + 1024; the 1024 covers the fp32 roundings of the
+// map (2 ulp of a value < 2^31), so this is a superset of {a <= a_P + 2 eps}.
+// kSmemRow: u is staged in shared memory once (L <= kRefineSmemL, L % 4 == 0), so the passes touch
+// no global memory; otherwise any L, u recomputed from the row on every pass.
+constexpr int kRefineSmemL = 2048;
+
+template <bool kSmemRow>
+__global__ void __launch_bounds__(256)
+topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ S, int nq, int P, int Ppow2, int Cp,
+                   float eps_rel, int32_t* __restrict__ leaves, float* __restrict__ bias, uint32_t* fallbacks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= nq) return;
+  const int L = (int)ix.L, D = (int)ix.d, Dp = (D + 3) & ~3;
+  const bool sql2 = ix.distance == 1;
+  const int Lp = (L + 127) & ~127;  // whole LDS.128 iterations of the warp
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw) + warp * 256;
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 8 * 256 * 4) + (size_t)warp * Cp;
+  float* sq = reinterpret_cast<float*>(smem_raw + 8 * 256 * 4 + (size_t)8 * Cp * 8) + (size_t)warp * Dp;
+  uint32_t* srow = reinterpret_cast<uint32_t*>(smem_raw + 8 * 256 * 4 + (size_t)8 * Cp * 8 + (size_t)8 * Dp * 4) +
+                   (size_t)warp * Lp;
+  float* row = S + (size_t)qi * L;
+  const uint32_t lt = (1u << lane) - 1u;
+
+  float ssq = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float v = q[(size_t)qi * D + k];
+    sq[k] = v;
+    ssq = fmaf(v, v, ssq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, o);
+  __syncwarp();
+  float qn = 0.f;
+  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
+    if (lane == 0) {
+      double acc = 0.0;
+      for (int k = 0; k < D; ++k) acc += (double)sq[k] * (double)sq[k];
+      qn = (float)acc;
+    }
+    qn = __shfl_sync(0xFFFFFFFFu, qn, 0);
+  }
+  const float qnorm = sqrtf(ssq) * 1.001f, cmax = ix.center_max_norm;
+  float eps = eps_rel * qnorm * cmax;
+  if (sql2) eps = 2.f * eps + (float)(D + 8) * 1.1920929e-7f * (qn + cmax * cmax + 2.f * qnorm * cmax);
+  auto approx = [&](float sdot, float cn) -> float {
+    return sql2 ? __fsub_rn(__fadd_rn(cn, qn), __fmul_rn(2.f, sdot)) : -sdot;
+  };
+
+  // ---- pass A: approximate distances (to shared memory), their min and max ----
+  float amin = __int_as_float(0x7F800000), amax = __int_as_float(0xFF800000);
+  if constexpr (kSmemRow) {
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const float4* cn4 = reinterpret_cast<const float4*>(ix.center_sqnorm);
+#pragma unroll 4
+    for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i4 < (L >> 2)) {
+        const float4 v = row4[i4];
+        float4 cn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sql2) cn = cn4[i4];
+        a = make_float4(approx(v.x, cn.x), approx(v.y, cn.y), approx(v.z, cn.z), approx(v.w, cn.w));
+        amin = fminf(fminf(amin, a.x), fminf(a.y, fminf(a.z, a.w)));
+        amax = fmaxf(fmaxf(amax, a.x), fmaxf(a.y, fmaxf(a.z, a.w)));
+      }
+      reinterpret_cast<float4*>(srow)[i4] = a;
+    }
+  } else {
+#pragma unroll 4
+    for (int i = lane; i < L; i += 32) {
+      const float a = approx(row[i], sql2 ? ix.center_sqnorm[i] : 0.f);
+      amin = fminf(amin, a);
+      amax = fmaxf(amax, a);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    amin = fminf(amin, __shfl_xor_sync(0xFFFFFFFFu, amin, o));
+    amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
+  }
+  const float span = __fsub_rn(amax, amin);
+  const float scale = (span > 0.f && span < __int_as_float(0x7F800000)) ? __fdiv_rn(2145386496.f, span) : 0.f;
+  auto ufn = [&](float a) -> uint32_t {
+    return min(__float2uint_rz(__fmul_rn(__fsub_rn(a, amin), scale)), 0x7FFFFFFFu);
+  };
+  // fn(i, u) over the row in warp-uniform trip counts; slots past L carry u = 0xFFFFFFFF
+  auto for_each_u = [&](auto&& fn) {
+    if constexpr (kSmemRow) {
+      for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+        const uint4 u = reinterpret_cast<const uint4*>(srow)[i4];
+        fn(i4 * 4, u.x); fn(i4 * 4 + 1, u.y); fn(i4 * 4 + 2, u.z); fn(i4 * 4 + 3, u.w);
+      }
+    } else {
+      for (int t0 = 0; t0 < L; t0 += 32) {
+        const int i = t0 + lane;
+        fn(i, i < L ? ufn(approx(row[i], sql2 ? ix.center_sqnorm[i] : 0.f)) : 0xFFFFFFFFu);
+      }
+    }
+  };
+
+  uint32_t lim_u = 0x7FFFFFFFu;
+  if (P < L) {
+    uint32_t mask = 0, prefix = 0, need = (uint32_t)P, below = 0;
+    for (int shift = 23;; ) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hist[lane * 8 + k] = 0;
+      __syncwarp();
+      if (kSmemRow && shift == 23) {
+        // first pass: convert the staged distances to u in place
+        __syncwarp();
+        for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+          const float4 a = reinterpret_cast<const float4*>(srow)[i4];
+          uint4 u = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+          if (i4 < (L >> 2)) {
+            u = make_uint4(ufn(a.x), ufn(a.y), ufn(a.z), ufn(a.w));
+            atomicAdd(&hist[u.x >> 23], 1u); atomicAdd(&hist[u.y >> 23], 1u);
+            atomicAdd(&hist[u.z >> 23], 1u); atomicAdd(&hist[u.w >> 23], 1u);
+          }
+          reinterpret_cast<uint4*>(srow)[i4] = u;
+        }
+      } else {
+        for_each_u([&](int, uint32_t u) {
+          if (u <= 0x7FFFFFFFu && (u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        });
+      }
+      __syncwarp();
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; tot += c[k]; }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= need);
+      const int tl = hit ? (__ffs(hit) - 1) : 31;
+      uint32_t digit = 255, cum = 0, bucket = 0;
+      if (lane == tl) {
+        cum = incl - tot;
+        digit = (uint32_t)lane * 8 + 7;
+        bucket = c[7];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; bucket = c[k]; break; }
+          cum += c[k];
+        }
+      }
+      digit = __shfl_sync(0xFFFFFFFFu, digit, tl);
+      cum = __shfl_sync(0xFFFFFFFFu, cum, tl);
+      bucket = __shfl_sync(0xFFFFFFFFu, bucket, tl);
+      prefix |= digit << shift;
+      mask |= 0xFFu << shift;
+      below += cum;
+      need -= cum;
+      __syncwarp();
+      if (shift == 0 || below + bucket + 16 <= (uint32_t)Cp) break;
+      shift = shift > 8 ? shift - 8 : 0;
+    }
+    const uint32_t hi_u = prefix | (~mask & 0x7FFFFFFFu);
+    const float widen = __fmul_ru(__fmul_ru(2.f * eps, scale), 1.000001f);
+    const uint32_t extra = widen < 2.0e9f ? __float2uint_ru(widen) + 1024u : 0x7FFFFFFFu;  // NaN -> everything
+    lim_u = hi_u + min(extra, 0x7FFFFFFFu - hi_u);
+  } else if constexpr (kSmemRow) {
+    // every centre is a candidate: only mark the valid slots
+    for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+      const uint32_t f = i4 < (L >> 2) ? 0u : 0xFFFFFFFFu;
+      reinterpret_cast<uint4*>(srow)[i4] = make_uint4(f, f, f, f);
+    }
+    __syncwarp();
+  }
+  uint32_t count = 0;
+  for_each_u([&](int i, uint32_t u) {
+    const bool take = u <= lim_u;
+    const uint32_t tm = __ballot_sync(0xFFFFFFFFu, take);
+    if (take) {
+      const uint32_t pos = count + __popc(tm & lt);
+      if (pos < (uint32_t)Cp) skeys[pos] = (uint64_t)(uint32_t)i;
+    }
+    count += __popc(tm);
+  });
+  __syncwarp();
+
+  // exact fp32 chain of up to four centres at a time (independent chains hide the load latency)
+  auto exact4 = [&](const int (&idx)[4], const bool (&live)[4], float (&acc)[4]) {
+    const float* c[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      c[t] = ix.centers + (size_t)idx[t] * D;
+      acc[t] = sql2 ? __fadd_rn(ix.center_sqnorm[idx[t]], qn) : 0.f;
+    }
+    if ((D & 3) == 0) {
+      // 8 dims of all four rows are in flight before the first FMA of the chunk
+      for (int k0 = 0; k0 < D; k0 += 8) {
+        float4 v[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            v[u][t] = live[t] ? __ldg(reinterpret_cast<const float4*>(c[t] + min(k0 + 4 * u, D - 4)))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sql2) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              v[u][t] = make_float4(__fmul_rn(v[u][t].x, 2.f), __fmul_rn(v[u][t].y, 2.f), __fmul_rn(v[u][t].z, 2.f),
+                                    __fmul_rn(v[u][t].w, 2.f));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int k = k0 + 4 * u;
+          if (k < D) {
+            const float4 qv = *reinterpret_cast<const float4*>(sq + k);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              acc[t] = __fmaf_rn(-qv.x, v[u][t].x, acc[t]);
+              acc[t] = __fmaf_rn(-qv.y, v[u][t].y, acc[t]);
+              acc[t] = __fmaf_rn(-qv.z, v[u][t].z, acc[t]);
+              acc[t] = __fmaf_rn(-qv.w, v[u][t].w, acc[t]);
+            }
+          }
+        }
+      }
+    } else {
+      const float scale2 = sql2 ? 2.0f : 1.0f;
+      for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[t] = __fmaf_rn(-sq[k], __fmul_rn(__ldg(c[t] + k), scale2), acc[t]);
+      }
+    }
+  };
+
+  int32_t* lout = leaves + (size_t)qi * P;
+  float* bout = bias + (size_t)qi * P;
+  if (count <= (uint32_t)Cp) {
+    int ns = 2;
+    while ((uint32_t)ns < count) ns <<= 1;
+    for (int j0 = 0; j0 < ns; j0 += 128) {
+      int idx[4];
+      float acc[4];
+      bool live[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = j0 + t * 32 + lane;
+        live[t] = (uint32_t)j < count;
+        idx[t] = live[t] ? (int)(uint32_t)skeys[j] : 0;
+      }
+      exact4(idx, live, acc);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = j0 + t * 32 + lane;
+        if (j < ns) skeys[j] = live[t] ? (((uint64_t)f2ord(acc[t]) << 32) | (uint32_t)idx[t]) : kKeyMax;
+      }
+    }
+    __syncwarp();
+    warp_bitonic_sort(skeys, ns, lane);
+    for (int i = lane; i < P; i += 32) {
+      const uint64_t k = i < ns ? skeys[i] : kKeyMax;
+      lout[i] = (k == kKeyMax) ? -1 : (int32_t)(uint32_t)k;
+      bout[i] = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
+    }
+  } else {
+    if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1u);
+    for (int i0 = 0; i0 < L; i0 += 128) {
+      int idx[4];
+      float acc[4];
+      bool live[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        idx[t] = min(i0 + t * 32 + lane, L - 1);
+        live[t] = i0 + t * 32 + lane < L;
+      }
+      exact4(idx, live, acc);
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (i0 + t * 32 + lane < L) row[i0 + t * 32 + lane] = acc[t];
+    }
+    __syncwarp();
+    warp_topp_exact(row, L, P, Ppow2, hist, skeys, lane, lout, bout);
+  }
+}
+
+bool tokenize_tensor_path(const DevIndex& ix, uint32_t P) {
+  if (!ix.tok_b || P + 32 > (uint32_t)kRefineMaxCand || ix.d > 2048) return false;
+  const char* e = getenv("SCANN_B200_TOKENIZE");
+  if (e && !strcmp(e, "simt")) return false;
+  if (e && !strcmp(e, "tcgen05")) return true;
+  return ix.L >= 256;  // below that the SIMT GEMM is already negligible
+}
+
+cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq, uint32_t P, float* dist, void* a_ws,
+                                 int32_t* leaves, float* bias, uint32_t* fallbacks, cudaStream_t s, int* launches) {
+  if (!tokenize_tensor_path(ix, P)) {
+    launch_tokenize(ix, q, nq, dist, s);
+    launch_topp(ix, dist, nq, P, leaves, bias, s);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+  }
+  cudaError_t e = build_tokenize_operand(q, nq, ix.d, 1, a_ws, s);
+  if (e != cudaSuccess) return e;
+  e = gemm_bf16_nt(a_ws, nq, (nq + 127) / 128 * 128, ix.tok_b, ix.L, ix.tok_kp, dist, ix.L, s);
+  if (e != cudaSuccess) return e;
+  int pp = 2, cp = 64;
+  while (pp < (int)P) pp <<= 1;
+  while (cp < (int)P + 32) cp <<= 1;
+  if (cp < pp) cp = pp;
+  const float eps_rel = (float)ix.tok_kp * 4.76837158e-7f + 3.05175781e-5f;  // K * 2^-21 + 2^-15
+  const size_t smem = 8 * 256 * 4 + (size_t)8 * cp * 8 + (size_t)8 * ((ix.d + 3) & ~3u) * 4;
+#define SB_REFINE(kS, bytes)                                                                                    \
+  do {                                                                                                          \
+    e = cudaFuncSetAttribute(topp_refine_kernel<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+    if (e != cudaSuccess) return e;                                                                             \
+    topp_refine_kernel<kS><<<(nq + 7) / 8, 256, (bytes), s>>>(ix, q, dist, (int)nq, (int)P, pp, cp, eps_rel,    \
+                                                              leaves, bias, fallbacks);                         \
+  } while (0)
+  if (ix.L <= (uint32_t)kRefineSmemL && (ix.L & 3u) == 0) SB_REFINE(true, smem + (size_t)8 * ((ix.L + 127) & ~127u) * 4);
+  else SB_REFINE(false, smem);
+#undef SB_REFINE
+  if (launches) *launches += 3;
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------

@@ -113,3 +113,52 @@ def test_stats_scan_bytes_match_oracle():
   assert st["scan_bytes_alg"] == c.oracle.last_scan_bytes()
   assert st["scan_pairs"] == len(c.q) * c.probe
   assert st["kernel_launches"] >= 8
+
+
+# ---- tokenization: the tcgen05 pre-filter + exact refinement against the SIMT path and the oracle ----
+TOK_CASES = [
+    dict(),
+    dict(soar=1.5),
+    dict(n=6000, leaves=300, probe=40, pre=50, d=32),
+    dict(n=20000, leaves=1000, probe=100, d=100),          # L > 256: the default picks the tensor path
+    dict(distance="squared_l2", d=64, leaves=50, n=10000),
+    dict(distance="squared_l2", d=30, dpb=4, leaves=300, n=6000, probe=64, pre=64),
+    dict(dpb=3, d=100, leaves=700, n=15000, probe=37),     # D % 4 == 0 but 3D not a multiple of 64; odd P
+    dict(dpb=3, d=99, leaves=300, n=8000, probe=33),       # D % 4 != 0: scalar centre loads
+]
+
+
+@pytest.mark.parametrize("mode", ["tcgen05", "simt"])
+@pytest.mark.parametrize("kw", TOK_CASES, ids=[str(i) for i in range(len(TOK_CASES))])
+def test_tokenize_modes_bit_exact(kw, mode, monkeypatch):
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", mode)
+  c = get_case(**kw)
+  l0, d0 = c.oracle.tokenize(c.q)
+  l1, d1 = c.native.tokenize(c.q)
+  np.testing.assert_array_equal(l0, l1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  i0, e0 = c.oracle.search_batched(c.q)
+  i1, e1 = c.native.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(e0.view(np.uint32), e1.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [dict(n=6000, leaves=300, probe=40, pre=50, d=32),
+                                dict(distance="squared_l2", d=64, leaves=50, n=10000)], ids=["dot", "l2"])
+def test_tokenize_degenerate_queries_fall_back_to_exact(kw, monkeypatch):
+  """Zero / tiny / huge / duplicated queries: the candidate window of the pre-filter degenerates (every centre ties),
+  the kernel must fall back to exact distances and still match the oracle bit for bit."""
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", "tcgen05")
+  c = get_case(**kw)
+  q = c.q[:64].copy()
+  q[0] = 0.0
+  q[1] = 1e-30
+  q[2] *= 1e-20
+  q[3] *= 1e15
+  q[4] = -q[5]
+  q[6] = c.arrays.centers[7]
+  q[8, 1:] = 0.0
+  l0, d0 = c.oracle.tokenize(q)
+  l1, d1 = c.native.tokenize(q)
+  np.testing.assert_array_equal(l0, l1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
