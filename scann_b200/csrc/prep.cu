@@ -330,19 +330,20 @@ void launch_topp(const DevIndex& ix, const float* dist, uint32_t nq, uint32_t P,
 //   * If a query has more candidates than the warp's buffer (degenerate inputs: zero query, equal
 //     centres), the warp falls back to exact distances for all L centres.
 // ---------------------------------------------------------------------------------------
-__global__ void split_rows_kernel(const float* __restrict__ src, uint32_t rows, uint32_t d, uint32_t kp,
-                                  uint32_t rows_pad, int lo_term, __nv_bfloat16* __restrict__ out) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)rows_pad * kp) return;
-  const uint32_t r = (uint32_t)(i / kp), c = (uint32_t)(i % kp);
-  const uint32_t term = c / d, k = c % d;
-  __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-  if (r < rows && term < 3) {
-    const float x = src[(size_t)r * d + k];
+__global__ void __launch_bounds__(128)
+split_rows_kernel(const float* __restrict__ src, uint32_t rows, uint32_t d, uint32_t kp, int lo_term,
+                  __nv_bfloat16* __restrict__ out) {
+  const uint32_t r = blockIdx.x;
+  __nv_bfloat16* o = out + (size_t)r * kp;
+  for (uint32_t k = threadIdx.x; k < d; k += 128) {
+    const float x = r < rows ? src[(size_t)r * d + k] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-    v = ((int)term == lo_term) ? __float2bfloat16_rn(x - __bfloat162float(hi)) : hi;
+    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    o[k] = hi;
+    o[d + k] = lo_term == 1 ? lo : hi;
+    o[2 * d + k] = lo_term == 2 ? lo : hi;
   }
-  out[i] = v;
+  for (uint32_t k = 3 * d + threadIdx.x; k < kp; k += 128) o[k] = __float2bfloat16_rn(0.f);
 }
 
 uint32_t tokenize_kpitch(uint32_t d) { return (3 * d + 63) / 64 * 64; }
@@ -351,15 +352,13 @@ size_t tokenize_operand_bytes(uint32_t rows, uint32_t d) {
 }
 cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, int lo_term, void* out, cudaStream_t s) {
   const uint32_t kp = tokenize_kpitch(d), rows_pad = (rows + 127) / 128 * 128;
-  const size_t total = (size_t)rows_pad * kp;
-  split_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, rows, d, kp, rows_pad, lo_term,
-                                                                     reinterpret_cast<__nv_bfloat16*>(out));
+  split_rows_kernel<<<rows_pad, 128, 0, s>>>(src, rows, d, kp, lo_term, reinterpret_cast<__nv_bfloat16*>(out));
   return cudaGetLastError();
 }
 
 constexpr int kRefineMaxCand = 512;
 
-// One warp per query.  The row of approximate distances is mapped to a fixed-point image
+// One 128-thread CTA per query.  The row of approximate distances is mapped to a fixed-point image
 //   u = min(uint((a - min) * 2^31 * (1 - 2^-10) / (max - min)), 2^31 - 1),
 // which is monotone in the distance and spreads the row evenly over the 256 bins of the first
 // radix pass (the leading sign/exponent bits of the float image are common to nearly all distances
@@ -370,45 +369,49 @@ constexpr int kRefineMaxCand = 512;
 // map (2 ulp of a value < 2^31), so this is a superset of {a <= a_P + 2 eps}.
 // kSmemRow: u is staged in shared memory once (L <= kRefineSmemL, L % 4 == 0), so the passes touch
 // no global memory; otherwise any L, u recomputed from the row on every pass.
-constexpr int kRefineSmemL = 2048;
+constexpr int kRefineSmemL = 4096;
+constexpr int kRefineThreads = 128;
 
 template <bool kSmemRow>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kRefineThreads)
 topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ S, int nq, int P, int Ppow2, int Cp,
                    float eps_rel, int32_t* __restrict__ leaves, float* __restrict__ bias, uint32_t* fallbacks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int qi = blockIdx.x * 8 + warp;
-  if (qi >= nq) return;
+  __shared__ uint32_t hist[256];
+  __shared__ float red_a[4], red_b[4];
+  __shared__ uint32_t s_sel[4];  // digit, cum, bucket, candidate counter
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int qi = blockIdx.x;
   const int L = (int)ix.L, D = (int)ix.d, Dp = (D + 3) & ~3;
   const bool sql2 = ix.distance == 1;
-  const int Lp = (L + 127) & ~127;  // whole LDS.128 iterations of the warp
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw) + warp * 256;
-  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw + 8 * 256 * 4) + (size_t)warp * Cp;
-  float* sq = reinterpret_cast<float*>(smem_raw + 8 * 256 * 4 + (size_t)8 * Cp * 8) + (size_t)warp * Dp;
-  uint32_t* srow = reinterpret_cast<uint32_t*>(smem_raw + 8 * 256 * 4 + (size_t)8 * Cp * 8 + (size_t)8 * Dp * 4) +
-                   (size_t)warp * Lp;
+  const int Lp = (L + 511) & ~511;  // whole LDS.128 iterations of the block
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
+  float* sq = reinterpret_cast<float*>(smem_raw + (size_t)Cp * 8);
+  uint32_t* srow = reinterpret_cast<uint32_t*>(smem_raw + (size_t)Cp * 8 + (size_t)Dp * 4);
   float* row = S + (size_t)qi * L;
-  const uint32_t lt = (1u << lane) - 1u;
 
   float ssq = 0.f;
-  for (int k = lane; k < D; k += 32) {
+  for (int k = tid; k < D; k += kRefineThreads) {
     const float v = q[(size_t)qi * D + k];
     sq[k] = v;
     ssq = fmaf(v, v, ssq);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, o);
-  __syncwarp();
+  if (lane == 0) red_a[warp] = ssq;
+  __syncthreads();
+  ssq = red_a[0] + red_a[1] + red_a[2] + red_a[3];
   float qn = 0.f;
   if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
-    if (lane == 0) {
+    if (tid == 0) {
       double acc = 0.0;
       for (int k = 0; k < D; ++k) acc += (double)sq[k] * (double)sq[k];
-      qn = (float)acc;
+      red_b[0] = (float)acc;
     }
-    qn = __shfl_sync(0xFFFFFFFFu, qn, 0);
+    __syncthreads();
+    qn = red_b[0];
   }
+  __syncthreads();
   const float qnorm = sqrtf(ssq) * 1.001f, cmax = ix.center_max_norm;
   float eps = eps_rel * qnorm * cmax;
   if (sql2) eps = 2.f * eps + (float)(D + 8) * 1.1920929e-7f * (qn + cmax * cmax + 2.f * qnorm * cmax);
@@ -422,7 +425,7 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
     const float4* row4 = reinterpret_cast<const float4*>(row);
     const float4* cn4 = reinterpret_cast<const float4*>(ix.center_sqnorm);
 #pragma unroll 4
-    for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+    for (int i4 = tid; i4 < (Lp >> 2); i4 += kRefineThreads) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i4 < (L >> 2)) {
         const float4 v = row4[i4];
@@ -436,7 +439,7 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
     }
   } else {
 #pragma unroll 4
-    for (int i = lane; i < L; i += 32) {
+    for (int i = tid; i < L; i += kRefineThreads) {
       const float a = approx(row[i], sql2 ? ix.center_sqnorm[i] : 0.f);
       amin = fminf(amin, a);
       amax = fmaxf(amax, a);
@@ -447,21 +450,25 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
     amin = fminf(amin, __shfl_xor_sync(0xFFFFFFFFu, amin, o));
     amax = fmaxf(amax, __shfl_xor_sync(0xFFFFFFFFu, amax, o));
   }
+  if (lane == 0) { red_a[warp] = amin; red_b[warp] = amax; }
+  __syncthreads();
+  amin = fminf(fminf(red_a[0], red_a[1]), fminf(red_a[2], red_a[3]));
+  amax = fmaxf(fmaxf(red_b[0], red_b[1]), fmaxf(red_b[2], red_b[3]));
   const float span = __fsub_rn(amax, amin);
   const float scale = (span > 0.f && span < __int_as_float(0x7F800000)) ? __fdiv_rn(2145386496.f, span) : 0.f;
   auto ufn = [&](float a) -> uint32_t {
     return min(__float2uint_rz(__fmul_rn(__fsub_rn(a, amin), scale)), 0x7FFFFFFFu);
   };
-  // fn(i, u) over the row in warp-uniform trip counts; slots past L carry u = 0xFFFFFFFF
+  // fn(i, u) over the row in block-uniform trip counts; slots past L carry u = 0xFFFFFFFF
   auto for_each_u = [&](auto&& fn) {
     if constexpr (kSmemRow) {
-      for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+      for (int i4 = tid; i4 < (Lp >> 2); i4 += kRefineThreads) {
         const uint4 u = reinterpret_cast<const uint4*>(srow)[i4];
         fn(i4 * 4, u.x); fn(i4 * 4 + 1, u.y); fn(i4 * 4 + 2, u.z); fn(i4 * 4 + 3, u.w);
       }
     } else {
-      for (int t0 = 0; t0 < L; t0 += 32) {
-        const int i = t0 + lane;
+      for (int t0 = 0; t0 < L; t0 += kRefineThreads) {
+        const int i = t0 + tid;
         fn(i, i < L ? ufn(approx(row[i], sql2 ? ix.center_sqnorm[i] : 0.f)) : 0xFFFFFFFFu);
       }
     }
@@ -471,13 +478,12 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   if (P < L) {
     uint32_t mask = 0, prefix = 0, need = (uint32_t)P, below = 0;
     for (int shift = 23;; ) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) hist[lane * 8 + k] = 0;
-      __syncwarp();
+      hist[tid] = 0;
+      hist[tid + kRefineThreads] = 0;
+      __syncthreads();
       if (kSmemRow && shift == 23) {
-        // first pass: convert the staged distances to u in place
-        __syncwarp();
-        for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+        // first pass: convert the staged distances to u in place (each thread revisits its own slots)
+        for (int i4 = tid; i4 < (Lp >> 2); i4 += kRefineThreads) {
           const float4 a = reinterpret_cast<const float4*>(srow)[i4];
           uint4 u = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
           if (i4 < (L >> 2)) {
@@ -492,37 +498,35 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
           if (u <= 0x7FFFFFFFu && (u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         });
       }
-      __syncwarp();
-      uint32_t c[8], tot = 0;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t c[8], tot = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; tot += c[k]; }
-      uint32_t incl = tot;
+        for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; tot += c[k]; }
+        uint32_t incl = tot;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= need);
-      const int tl = hit ? (__ffs(hit) - 1) : 31;
-      uint32_t digit = 255, cum = 0, bucket = 0;
-      if (lane == tl) {
-        cum = incl - tot;
-        digit = (uint32_t)lane * 8 + 7;
-        bucket = c[7];
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        const uint32_t hit = __ballot_sync(0xFFFFFFFFu, incl >= need);
+        const int tl = hit ? (__ffs(hit) - 1) : 31;
+        if (lane == tl) {
+          uint32_t cum = incl - tot, digit = (uint32_t)lane * 8 + 7, bucket = c[7];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; bucket = c[k]; break; }
-          cum += c[k];
+          for (int k = 0; k < 8; ++k) {
+            if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; bucket = c[k]; break; }
+            cum += c[k];
+          }
+          s_sel[0] = digit; s_sel[1] = cum; s_sel[2] = bucket;
         }
       }
-      digit = __shfl_sync(0xFFFFFFFFu, digit, tl);
-      cum = __shfl_sync(0xFFFFFFFFu, cum, tl);
-      bucket = __shfl_sync(0xFFFFFFFFu, bucket, tl);
+      __syncthreads();
+      const uint32_t digit = s_sel[0], cum = s_sel[1], bucket = s_sel[2];
       prefix |= digit << shift;
       mask |= 0xFFu << shift;
       below += cum;
       need -= cum;
-      __syncwarp();
       if (shift == 0 || below + bucket + 16 <= (uint32_t)Cp) break;
       shift = shift > 8 ? shift - 8 : 0;
     }
@@ -532,72 +536,58 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
     lim_u = hi_u + min(extra, 0x7FFFFFFFu - hi_u);
   } else if constexpr (kSmemRow) {
     // every centre is a candidate: only mark the valid slots
-    for (int i4 = lane; i4 < (Lp >> 2); i4 += 32) {
+    for (int i4 = tid; i4 < (Lp >> 2); i4 += kRefineThreads) {
       const uint32_t f = i4 < (L >> 2) ? 0u : 0xFFFFFFFFu;
       reinterpret_cast<uint4*>(srow)[i4] = make_uint4(f, f, f, f);
     }
-    __syncwarp();
   }
-  uint32_t count = 0;
+  if (tid == 0) s_sel[3] = 0;
+  __syncthreads();
+  // ~P of L slots qualify: a per-thread reservation is cheaper than warp-aggregating every slot
   for_each_u([&](int i, uint32_t u) {
-    const bool take = u <= lim_u;
-    const uint32_t tm = __ballot_sync(0xFFFFFFFFu, take);
-    if (take) {
-      const uint32_t pos = count + __popc(tm & lt);
+    if (u <= lim_u) {
+      const uint32_t pos = atomicAdd(&s_sel[3], 1u);
       if (pos < (uint32_t)Cp) skeys[pos] = (uint64_t)(uint32_t)i;
     }
-    count += __popc(tm);
   });
-  __syncwarp();
+  __syncthreads();
+  const uint32_t count = s_sel[3];
 
-  // exact fp32 chain of up to four centres at a time (independent chains hide the load latency)
-  auto exact4 = [&](const int (&idx)[4], const bool (&live)[4], float (&acc)[4]) {
-    const float* c[4];
+  // the reference's exact fp32 chain for one centre (scalar loads: fallback and D % 4 != 0)
+  auto exact = [&](int idx) -> float {
+    const float* c = ix.centers + (size_t)idx * D;
+    float acc = sql2 ? __fadd_rn(ix.center_sqnorm[idx], qn) : 0.f;
+    const float scale2 = sql2 ? 2.0f : 1.0f;
+#pragma unroll 4
+    for (int k = 0; k < D; ++k) acc = __fmaf_rn(-sq[k], __fmul_rn(__ldg(c + k), scale2), acc);
+    return acc;
+  };
+  // the same chain with 16-byte loads, 16 dims in flight before the first FMA of a chunk (D % 4 == 0)
+  auto exact_v4 = [&](int idx) -> float {
+    const float* c = ix.centers + (size_t)idx * D;
+    float acc = sql2 ? __fadd_rn(ix.center_sqnorm[idx], qn) : 0.f;
+    for (int k0 = 0; k0 < D; k0 += 16) {
+      float4 v[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      c[t] = ix.centers + (size_t)idx[t] * D;
-      acc[t] = sql2 ? __fadd_rn(ix.center_sqnorm[idx[t]], qn) : 0.f;
-    }
-    if ((D & 3) == 0) {
-      // 8 dims of all four rows are in flight before the first FMA of the chunk
-      for (int k0 = 0; k0 < D; k0 += 8) {
-        float4 v[2][4];
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(c + min(k0 + 4 * u, D - 4)));
+      if (sql2) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 4; ++u)
+          v[u] = make_float4(__fmul_rn(v[u].x, 2.f), __fmul_rn(v[u].y, 2.f), __fmul_rn(v[u].z, 2.f), __fmul_rn(v[u].w, 2.f));
+      }
 #pragma unroll
-          for (int t = 0; t < 4; ++t)
-            v[u][t] = live[t] ? __ldg(reinterpret_cast<const float4*>(c[t] + min(k0 + 4 * u, D - 4)))
-                              : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sql2) {
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              v[u][t] = make_float4(__fmul_rn(v[u][t].x, 2.f), __fmul_rn(v[u][t].y, 2.f), __fmul_rn(v[u][t].z, 2.f),
-                                    __fmul_rn(v[u][t].w, 2.f));
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int k = k0 + 4 * u;
-          if (k < D) {
-            const float4 qv = *reinterpret_cast<const float4*>(sq + k);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              acc[t] = __fmaf_rn(-qv.x, v[u][t].x, acc[t]);
-              acc[t] = __fmaf_rn(-qv.y, v[u][t].y, acc[t]);
-              acc[t] = __fmaf_rn(-qv.z, v[u][t].z, acc[t]);
-              acc[t] = __fmaf_rn(-qv.w, v[u][t].w, acc[t]);
-            }
-          }
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + 4 * u;
+        if (k < D) {
+          const float4 qv = *reinterpret_cast<const float4*>(sq + k);
+          acc = __fmaf_rn(-qv.x, v[u].x, acc);
+          acc = __fmaf_rn(-qv.y, v[u].y, acc);
+          acc = __fmaf_rn(-qv.z, v[u].z, acc);
+          acc = __fmaf_rn(-qv.w, v[u].w, acc);
         }
       }
-    } else {
-      const float scale2 = sql2 ? 2.0f : 1.0f;
-      for (int k = 0; k < D; ++k) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) acc[t] = __fmaf_rn(-sq[k], __fmul_rn(__ldg(c[t] + k), scale2), acc[t]);
-      }
     }
+    return acc;
   };
 
   int32_t* lout = leaves + (size_t)qi * P;
@@ -605,48 +595,65 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   if (count <= (uint32_t)Cp) {
     int ns = 2;
     while ((uint32_t)ns < count) ns <<= 1;
-    for (int j0 = 0; j0 < ns; j0 += 128) {
-      int idx[4];
-      float acc[4];
-      bool live[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int j = j0 + t * 32 + lane;
-        live[t] = (uint32_t)j < count;
-        idx[t] = live[t] ? (int)(uint32_t)skeys[j] : 0;
-      }
-      exact4(idx, live, acc);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int j = j0 + t * 32 + lane;
-        if (j < ns) skeys[j] = live[t] ? (((uint64_t)f2ord(acc[t]) << 32) | (uint32_t)idx[t]) : kKeyMax;
-      }
+    for (int j0 = warp * 32; j0 < ns; j0 += kRefineThreads) {  // warp-uniform trip count
+      const int j = j0 + lane;
+      const bool live = (uint32_t)j < count;
+      const uint32_t idx = live ? (uint32_t)skeys[j] : 0u;
+      float e = 0.f;
+      if (live) e = (D & 3) == 0 ? exact_v4((int)idx) : exact((int)idx);
+      if (j < ns) skeys[j] = live ? (((uint64_t)f2ord(e) << 32) | idx) : kKeyMax;
     }
-    __syncwarp();
-    warp_bitonic_sort(skeys, ns, lane);
-    for (int i = lane; i < P; i += 32) {
-      const uint64_t k = i < ns ? skeys[i] : kKeyMax;
+    __syncthreads();
+    if (ns <= 128) {
+      // one warp sorts up to 128 keys in registers (4 per lane, key index = 4 * lane + r)
+      if (warp == 0) {
+        uint64_t kr[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) kr[r] = (4 * lane + r) < ns ? skeys[4 * lane + r] : kKeyMax;
+#pragma unroll
+        for (int k = 2; k <= 128; k <<= 1) {
+#pragma unroll
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 4) {
+              const int lj = j >> 2;  // partner lane distance
+              const bool up = ((4 * lane) & k) == 0;
+              const bool lower = (lane & lj) == 0;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const uint64_t o = __shfl_xor_sync(0xFFFFFFFFu, kr[r], lj);
+                const bool take_min = lower == up;
+                kr[r] = take_min ? (kr[r] < o ? kr[r] : o) : (kr[r] > o ? kr[r] : o);
+              }
+            } else {
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                if ((r & j) == 0) {
+                  const int i = 4 * lane + r;
+                  const bool up = (i & k) == 0;
+                  const uint64_t x = kr[r], y = kr[r | j];
+                  if ((x > y) == up) { kr[r] = y; kr[r | j] = x; }
+                }
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) skeys[4 * lane + r] = kr[r];
+      }
+      __syncthreads();
+    } else {
+      block_bitonic_sort(skeys, ns);
+    }
+    for (int i = tid; i < P; i += kRefineThreads) {
+      const uint64_t k = i < max(ns, 128) && i < Cp ? skeys[i] : kKeyMax;
       lout[i] = (k == kKeyMax) ? -1 : (int32_t)(uint32_t)k;
       bout[i] = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
     }
   } else {
-    if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1u);
-    for (int i0 = 0; i0 < L; i0 += 128) {
-      int idx[4];
-      float acc[4];
-      bool live[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        idx[t] = min(i0 + t * 32 + lane, L - 1);
-        live[t] = i0 + t * 32 + lane < L;
-      }
-      exact4(idx, live, acc);
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (i0 + t * 32 + lane < L) row[i0 + t * 32 + lane] = acc[t];
-    }
-    __syncwarp();
-    warp_topp_exact(row, L, P, Ppow2, hist, skeys, lane, lout, bout);
+    if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1u);
+    for (int i = tid; i < L; i += kRefineThreads) row[i] = exact(i);
+    __syncthreads();
+    if (warp == 0) warp_topp_exact(row, L, P, Ppow2, hist, skeys, lane, lout, bout);
   }
 }
 
@@ -675,15 +682,16 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   while (cp < (int)P + 32) cp <<= 1;
   if (cp < pp) cp = pp;
   const float eps_rel = (float)ix.tok_kp * 4.76837158e-7f + 3.05175781e-5f;  // K * 2^-21 + 2^-15
-  const size_t smem = 8 * 256 * 4 + (size_t)8 * cp * 8 + (size_t)8 * ((ix.d + 3) & ~3u) * 4;
+  if (cp < 128) cp = 128;  // the in-register sort writes 128 keys back
+  const size_t smem = (size_t)cp * 8 + (size_t)((ix.d + 3) & ~3u) * 4;
 #define SB_REFINE(kS, bytes)                                                                                    \
   do {                                                                                                          \
     e = cudaFuncSetAttribute(topp_refine_kernel<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
     if (e != cudaSuccess) return e;                                                                             \
-    topp_refine_kernel<kS><<<(nq + 7) / 8, 256, (bytes), s>>>(ix, q, dist, (int)nq, (int)P, pp, cp, eps_rel,    \
-                                                              leaves, bias, fallbacks);                         \
+    topp_refine_kernel<kS><<<nq, kRefineThreads, (bytes), s>>>(ix, q, dist, (int)nq, (int)P, pp, cp, eps_rel,   \
+                                                               leaves, bias, fallbacks);                        \
   } while (0)
-  if (ix.L <= (uint32_t)kRefineSmemL && (ix.L & 3u) == 0) SB_REFINE(true, smem + (size_t)8 * ((ix.L + 127) & ~127u) * 4);
+  if (ix.L <= (uint32_t)kRefineSmemL && (ix.L & 3u) == 0) SB_REFINE(true, smem + (size_t)((ix.L + 511) & ~511u) * 4);
   else SB_REFINE(false, smem);
 #undef SB_REFINE
   if (launches) *launches += 3;
