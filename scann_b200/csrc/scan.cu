@@ -237,6 +237,99 @@ __device__ __forceinline__ uint64_t block_radix_select(const uint64_t* s, uint32
   return prefix;
 }
 
+// Upper bound of the K-th smallest (1-based) of n u64 keys in shared memory, n >= K: returns an actual
+// key T >= the K-th smallest and, in *n_le, how many keys are <= T.  One histogram pass over a linear,
+// monotone 256-bin image of the keys' high words (the float score), a second one inside the pivot's bin
+// when that bin is crowded, then a max-reduction: 3-4 block barriers per level instead of the 24 of the
+// exact 8-pass select.  A pruning threshold only has to be an upper bound, it need not be tight.
+__device__ __forceinline__ uint64_t block_select_bound(const uint64_t* s, uint32_t n, uint32_t K, SelectScratch* sc,
+                                                       uint32_t* n_le) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ uint32_t sb_lo[4], sb_hi[4];
+  __shared__ unsigned long long sb_max[4];
+  uint32_t lo = 0, hi = 0xFFFFFFFFu, need = K, below = 0;  // current high-word range [lo, hi] holding the K-th key
+  uint64_t T = 0;
+  for (int level = 0; level < 2; ++level) {
+    // range of the high words inside [lo, hi]
+    uint32_t mn = 0xFFFFFFFFu, mx = 0;
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+      const uint32_t o = (uint32_t)(s[i] >> 32);
+      if (o >= lo && o <= hi) { mn = min(mn, o); mx = max(mx, o); }
+    }
+    mn = __reduce_min_sync(kFull, mn);
+    mx = __reduce_max_sync(kFull, mx);
+    for (int i = tid; i < 256; i += blockDim.x) sc->hist[i] = 0;
+    if (lane == 0) { sb_lo[tid >> 5] = mn; sb_hi[tid >> 5] = mx; }
+    __syncthreads();
+    mn = min(min(sb_lo[0], sb_lo[1]), min(sb_lo[2], sb_lo[3]));
+    mx = max(max(sb_hi[0], sb_hi[1]), max(sb_hi[2], sb_hi[3]));
+    const float scale = mx > mn ? 255.9f / (float)(mx - mn) : 0.f;
+    auto bin = [&](uint32_t o) -> uint32_t { return min((uint32_t)((float)(o - mn) * scale), 255u); };
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+      const uint32_t o = (uint32_t)(s[i] >> 32);
+      if (o >= lo && o <= hi) atomicAdd(&sc->hist[bin(o)], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t c[8], tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { c[k] = sc->hist[lane * 8 + k]; tot += c[k]; }
+      uint32_t incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t hit = __ballot_sync(kFull, incl >= need);
+      const int tl = hit ? (__ffs(hit) - 1) : 31;
+      if (lane == tl) {
+        uint32_t cum = incl - tot, digit = (uint32_t)lane * 8 + 7, bucket = c[7];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (cum + c[k] >= need) { digit = (uint32_t)lane * 8 + k; bucket = c[k]; break; }
+          cum += c[k];
+        }
+        sc->prefix = ((unsigned long long)digit << 32) | bucket;
+        sc->need = cum;
+      }
+    }
+    __syncthreads();
+    const uint32_t digit = (uint32_t)(sc->prefix >> 32), bucket = (uint32_t)sc->prefix, cum = sc->need;
+    // largest key of the pivot's bin and the new range
+    unsigned long long tmax = 0;
+    uint32_t nlo = 0xFFFFFFFFu, nhi = 0;
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+      const uint64_t k = s[i];
+      const uint32_t o = (uint32_t)(k >> 32);
+      if (o >= lo && o <= hi && bin(o) == digit) {
+        tmax = max(tmax, (unsigned long long)k);
+        nlo = min(nlo, o);
+        nhi = max(nhi, o);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long t = __shfl_xor_sync(kFull, tmax, o);
+      tmax = max(tmax, t);
+    }
+    nlo = __reduce_min_sync(kFull, nlo);
+    nhi = __reduce_max_sync(kFull, nhi);
+    __syncthreads();  // sb_* are re-used
+    if (lane == 0) { sb_max[tid >> 5] = tmax; sb_lo[tid >> 5] = nlo; sb_hi[tid >> 5] = nhi; }
+    __syncthreads();
+    T = max(max(sb_max[0], sb_max[1]), max(sb_max[2], sb_max[3]));
+    nlo = min(min(sb_lo[0], sb_lo[1]), min(sb_lo[2], sb_lo[3]));
+    nhi = max(max(sb_hi[0], sb_hi[1]), max(sb_hi[2], sb_hi[3]));
+    __syncthreads();
+    *n_le = below + cum + bucket;
+    if (bucket <= 16 || nlo == nhi) break;  // tight enough, or the bin cannot be split by the high word
+    lo = nlo; hi = nhi;
+    below += cum;
+    need -= cum;
+  }
+  return T;
+}
+
 // ---------------------------------------------------------------------------------------
 // Pilot: one CTA per query, nearest leaves first, exact top-N threshold in shared memory.
 // ---------------------------------------------------------------------------------------
@@ -300,7 +393,10 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
       if (c > (uint32_t)(capl - kScanThreads)) {
         // keep the N smallest: radix-select the N-th key, compact through the global row (no sort:
         // the compaction after the main scan orders everything anyway).  c > capl-128 >= N here.
-        const uint64_t T = block_radix_select(scand, c, nover, &s_sel);
+        uint32_t n_le = 0;
+        uint64_t T = block_select_bound(scand, c, nover, &s_sel, &n_le);
+        if (n_le > (uint32_t)capl / 2) T = block_radix_select(scand, c, nover, &s_sel);  // crowded bin: exact select
+        const uint32_t nkeep = n_le > (uint32_t)capl / 2 ? nover : n_le;
         if (tid == 0) s_cnt = 0;
         __syncthreads();
         for (uint32_t i = tid; i < c; i += kScanThreads) {
@@ -308,7 +404,7 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
           if (k <= T) grow[atomicAdd(&s_cnt, 1u)] = k;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < nover; i += kScanThreads) scand[i] = grow[i];
+        for (uint32_t i = tid; i < nkeep; i += kScanThreads) scand[i] = grow[i];
         if (tid == 0) {
           s_tau = T;
           s_thr = acc_threshold(T, mult, inv, bias) + off128;
@@ -323,11 +419,24 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   // publish: every buffered candidate (unsorted, at most capl) and the N-th smallest key as tau
   const uint32_t c = s_cnt;
   uint64_t tau = kKeyMax;
-  if (c >= nover) tau = block_radix_select(scand, c, nover, &s_sel);
-  const uint32_t keep = min(c, w.cap);
-  for (uint32_t i = tid; i < keep; i += kScanThreads) grow[i] = scand[i];
+  if (c >= nover) {
+    uint32_t n_le = 0;
+    tau = block_select_bound(scand, c, nover, &s_sel, &n_le);
+    if (n_le > w.cap || n_le > 2 * nover + 64) tau = block_radix_select(scand, c, nover, &s_sel);  // crowded bin
+  }
+  // only keys <= tau can still matter; the rest of the pilot's buffer is dropped here
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < c; i += kScanThreads) {
+    const uint64_t k = scand[i];
+    if (k <= tau) {
+      const uint32_t pos = atomicAdd(&s_cnt, 1u);
+      if (pos < w.cap) grow[pos] = k;
+    }
+  }
+  __syncthreads();
   if (tid == 0) {
-    w.cnt[q] = keep;
+    w.cnt[q] = min(s_cnt, w.cap);
     w.tau[q] = tau;
     w.pilot_end[q] = (int32_t)r;
     w.ovf[q] = 0;
@@ -752,7 +861,7 @@ leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, 
   }
 
 static int pilot_capl(uint32_t nover) {
-  int capl = 256;
+  int capl = 1024;  // a whole typical leaf is buffered before the first (and usually only) selection
   while ((uint32_t)capl < nover + kScanThreads) capl <<= 1;
   return capl;
 }
