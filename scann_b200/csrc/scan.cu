@@ -723,37 +723,14 @@ __device__ __forceinline__ void compact_one(const ScanWork& w, uint32_t q, int d
   __syncthreads();
   uint32_t nuniq = n;
   if (!dedup && n > 1024u && n > w.nover) {
-    // Heavy tail: do not sort thousands of keys to keep N of them.  Keys are unique, so an
-    // 8-pass MSB radix select finds the exact N-th smallest key T; the N keys <= T are compacted
-    // through the query's own buffer row and only those are sorted.
-    __shared__ uint32_t hist[256];
-    __shared__ unsigned long long sel_prefix;
-    __shared__ uint32_t sel_need, sel_cnt;
-    uint64_t prefix = 0, mask = 0;
-    uint32_t need = w.nover;
-    for (int shift = 56; shift >= 0; shift -= 8) {
-      for (int i = tid; i < 256; i += kScanThreads) hist[i] = 0;
-      __syncthreads();
-      for (uint32_t i = tid; i < n; i += kScanThreads) {
-        const uint64_t k = s[i];
-        if ((k & mask) == prefix) atomicAdd(&hist[(uint32_t)(k >> shift) & 255u], 1u);
-      }
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t cum = 0;
-        int dsel = 255;
-        for (int dgt = 0; dgt < 256; ++dgt) {
-          if (cum + hist[dgt] >= need) { dsel = dgt; break; }
-          cum += hist[dgt];
-        }
-        sel_prefix = prefix | ((uint64_t)dsel << shift);
-        sel_need = need - cum;
-      }
-      __syncthreads();
-      prefix = sel_prefix;
-      need = sel_need;
-      mask |= 0xFFull << shift;
-    }
+    // Heavy tail: do not sort thousands of keys to keep N of them.  A bound select finds a key T >= the
+    // N-th smallest with only a few more than N keys <= T (exact 8-pass radix select if its bin is
+    // crowded); those keys are compacted through the query's own buffer row and only they are sorted.
+    __shared__ SelectScratch sc;
+    __shared__ uint32_t sel_cnt;
+    uint32_t n_le = 0;
+    uint64_t prefix = block_select_bound(s, n, w.nover, &sc, &n_le);
+    if (n_le > 1024u) prefix = block_radix_select(s, n, w.nover, &sc);  // crowded bin: exact N-th key
     if (tid == 0) sel_cnt = 0;
     __syncthreads();
     for (uint32_t i = tid; i < n; i += kScanThreads) {
@@ -761,7 +738,7 @@ __device__ __forceinline__ void compact_one(const ScanWork& w, uint32_t q, int d
       if (k <= prefix) w.buf[(size_t)q * w.cap + atomicAdd(&sel_cnt, 1u)] = k;
     }
     __syncthreads();
-    nuniq = sel_cnt;  // == nover
+    nuniq = sel_cnt;  // nover (exact select) or a few more (bound select)
     np2 = 2;
     while ((uint32_t)np2 < nuniq) np2 <<= 1;
     for (int i = tid; i < np2; i += kScanThreads) s[i] = (uint32_t)i < nuniq ? w.buf[(size_t)q * w.cap + i] : kKeyMax;
