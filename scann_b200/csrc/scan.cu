@@ -441,6 +441,26 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
     w.pilot_end[q] = (int32_t)r;
     w.ovf[q] = 0;
   }
+  // Work-list counts of the leaves left to the main scan, and the traffic statistics of all probed
+  // leaves (worklist_count_kernel's job, done here while the query's leaf list is hot).
+  unsigned long long bytes = 0, pairs = 0;
+  for (uint32_t rr = tid; rr < w.P; rr += kScanThreads) {
+    const int leaf = w.leaves[(size_t)q * w.P + rr];
+    if (leaf >= 0) {
+      bytes += (unsigned long long)(ix.leaf_goff[leaf + 1] - ix.leaf_goff[leaf]) * 16ull * ix.B;
+      pairs += 1;
+      if (rr >= r) atomicAdd(&w.leaf_cnt[leaf], 1u);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    bytes += __shfl_xor_sync(kFull, bytes, o);
+    pairs += __shfl_xor_sync(kFull, pairs, o);
+  }
+  if (lane == 0 && pairs) {
+    atomicAdd(&w.stats[0], bytes);
+    atomicAdd(&w.stats[1], pairs);
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -537,15 +557,20 @@ __global__ void worklist_scatter_kernel(DevIndex ix, ScanWork w, int only_ovf) {
   w.entry_bias[pos] = w.bias[i];
 }
 
+// The first work list of a batch is counted by the pilot kernel (launch_pilot zeroes leaf_cnt); the
+// re-scan lists of overflowed queries are counted here.
 void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, cudaStream_t s,
                      int* launches) {
-  cudaMemsetAsync(w.leaf_cnt, 0, sizeof(uint32_t) * (ix.L + 1), s);
   const size_t total = (size_t)w.nq * w.P;
   const int blocks = (int)((total + 255) / 256);
-  worklist_count_kernel<<<blocks, 256, 0, s>>>(ix, w, only_overflowed ? 1 : 0, only_overflowed ? 0 : 1);
+  if (only_overflowed) {
+    cudaMemsetAsync(w.leaf_cnt, 0, sizeof(uint32_t) * (ix.L + 1), s);
+    worklist_count_kernel<<<blocks, 256, 0, s>>>(ix, w, 1, 0);
+    if (launches) *launches += 1;
+  }
   worklist_scan_kernel<<<1, 1024, 0, s>>>(ix, w);
   worklist_scatter_kernel<<<blocks, 256, 0, s>>>(ix, w, only_overflowed ? 1 : 0);
-  if (launches) *launches += 3;
+  if (launches) *launches += 2;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -851,6 +876,8 @@ size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item) {
 
 cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) {
   const int capl = pilot_capl(w.nover);
+  cudaError_t em = cudaMemsetAsync(w.leaf_cnt, 0, sizeof(uint32_t) * (ix.L + 1), s);
+  if (em != cudaSuccess) return em;
   const size_t smem = pilot_smem_bytes(ix, w.nover);
   SB_DISPATCH_W(ix.W, {
     cudaError_t e = cudaFuncSetAttribute(pilot_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
