@@ -489,7 +489,7 @@ def run_bruteforce(args, wl, rank, world, local_rank):
          "e2e": {"value": nq * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q.nbytes),
                  "d2h_bytes_per_step": int(nq * k * 8), "steps": e2e_steps},
          "gpu_launches": int(agg["kernel_launches"]), "clocks": sampler.summary(),
-         "roofline": {"bound": "tensor", "kernel": "bf::gemm_filter_kernel", "achieved": flops / gemm_s / 1e12,
+         "roofline": {"bound": "tensor", "kernel": "bf::gemm_pair_kernel<2, filter>", "achieved": flops / gemm_s / 1e12,
                       "peak": peak, "peak_source": "measured sustained" if peaks else "fallback", "unit": "TFLOP/s",
                       "frac": flops / gemm_s / 1e12 / peak, "traffic": None,
                       "useful_tflops_f32_equivalent": flops / 2 / gemm_s / 1e12},

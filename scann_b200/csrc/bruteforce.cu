@@ -23,6 +23,9 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -105,10 +108,69 @@ struct GemmArgs {
   uint64_t* buf; uint32_t* cnt; const uint64_t* tau; uint32_t* ovf; uint32_t cap;
   // kEpiStore: raw accumulators, out[a_row * ld + b_row]
   float* out; uint32_t ld;
+  int prof;   // debug: CTA 0 prints where its MMA thread waited (SCANN_B200_GEMM_PROFILE=1)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Threshold filter of one accumulator tile for one query (= one TMEM lane), 256 columns.
+// Pass 1 builds a per-chunk bit mask with ONE float compare per score against thr = -distance(tau)
+// (a superset of "key < tau": score ties with tau are included); one reservation per (query, tile);
+// pass 2 re-reads only chunks with survivors, applies the exact 64-bit key test and pads the few
+// reserved-but-rejected slots with kKeyMax, which every later compaction sorts past the end.
+__device__ __forceinline__ void filter_tile(const GemmArgs& a, uint32_t tbase, uint32_t q, bool qvalid, uint32_t n0,
+                                            uint32_t* masks /* [BN/32] stride 128 */) {
+  const uint64_t tau = qvalid ? a.tau[q] : 0ull;
+  float thr = __int_as_float(0x7F800000);                         // +inf: nothing passes
+  if (qvalid) thr = tau == kKeyMax ? __int_as_float(0xFF800000)   // -inf: everything passes
+                                   : -ord2f((uint32_t)(tau >> 32));
+  uint32_t total = 0;
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tbase + (uint32_t)(c * 32), v);
+    uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (__uint_as_float(v[j]) >= thr) m0 |= 1u << j;
+      if (__uint_as_float(v[j + 1]) >= thr) m1 |= 2u << j;
+      if (__uint_as_float(v[j + 2]) >= thr) m2 |= 4u << j;
+      if (__uint_as_float(v[j + 3]) >= thr) m3 |= 8u << j;
+    }
+    uint32_t m = (m0 | m1) | (m2 | m3);
+    const uint32_t col = n0 + c * 32;  // columns past the end of this round's rows do not exist
+    if (col + 32 > a.row1) m &= col < a.row1 ? (0xFFFFFFFFu >> (32 - (a.row1 - col))) : 0u;
+    masks[c * 128] = m;
+    total += __popc(m);
+  }
+  uint32_t pos = total ? atomicAdd(&a.cnt[q], total) : 0u;
+  if (__any_sync(0xFFFFFFFFu, total != 0)) {
+    const uint32_t end = pos + total;
+    uint64_t* dst = a.buf + (size_t)q * a.cap;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const uint32_t m = masks[c * 128];
+      if (__any_sync(0xFFFFFFFFu, m != 0)) {
+        uint32_t v[32];
+        tmem_ld32(tbase + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if ((m >> j) & 1u) {
+            const uint64_t key = ((uint64_t)f2ord(-__uint_as_float(v[j])) << 32) | (n0 + c * 32 + j);
+            if (key < tau) {
+              if (pos < a.cap) dst[pos] = key;
+              ++pos;
+            }
+          }
+        }
+      }
+    }
+    for (; pos < end; ++pos)
+      if (pos < a.cap) dst[pos] = kKeyMax;
+    if (end > a.cap) a.ovf[q] = 1u;
+  }
 }
 
 constexpr int kEpiFilter = 0, kEpiStore = 1;
@@ -213,52 +275,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool qvalid = q < a.nq;
       const uint32_t tbase = tmem + as * BN + ((uint32_t)(quad * 32) << 16);
       if (kEpi == kEpiFilter) {
-        const uint64_t tau = qvalid ? a.tau[q] : 0ull;
-        const uint32_t tau_ord = (uint32_t)(tau >> 32), tau_lo = (uint32_t)tau;
         mbar_wait(&tmem_full_bar[as], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // pass 1: which of this query's 256 scores beat its threshold key
-        uint32_t* masks = &s_masks[0][threadIdx.x - 128];  // [chunk][epilogue thread]
-        uint32_t total = 0;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tbase + (uint32_t)(c * 32), v);
-          uint32_t m = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const uint32_t dp = n0 + c * 32 + j;
-            const uint32_t o = f2ord(-__uint_as_float(v[j]));  // DotProductDistance = -<q, x>
-            const bool pass = (o < tau_ord || (o == tau_ord && dp < tau_lo)) && dp < a.row1;
-            m |= (pass ? 1u : 0u) << j;
-          }
-          m = qvalid ? m : 0u;
-          masks[c * 128] = m;
-          total += __popc(m);
-        }
-        // one reservation per (query, tile), then pass 2 re-reads only the chunks with survivors
-        uint32_t pos = total ? atomicAdd(&a.cnt[q], total) : 0u;
-        if (__any_sync(0xFFFFFFFFu, total != 0)) {
-          uint64_t* dst = a.buf + (size_t)q * a.cap;
-#pragma unroll 1
-          for (int c = 0; c < BN / 32; ++c) {
-            const uint32_t m = masks[c * 128];
-            if (__any_sync(0xFFFFFFFFu, m != 0)) {
-              uint32_t v[32];
-              tmem_ld32(tbase + (uint32_t)(c * 32), v);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if ((m >> j) & 1u) {
-                  const uint32_t dp = n0 + c * 32 + j;
-                  const uint32_t o = f2ord(-__uint_as_float(v[j]));
-                  if (pos < a.cap) dst[pos] = ((uint64_t)o << 32) | dp;
-                  else a.ovf[q] = 1u;
-                  ++pos;
-                }
-              }
-            }
-          }
-        }
+        filter_tile(a, tbase, q, qvalid, n0, &s_masks[0][threadIdx.x - 128]);
       } else {
         mbar_wait(&tmem_full_bar[as], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -290,6 +309,191 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- CTA-pair variant (cta_group::2) ---------------------------------------------------------
+// Two CTAs of a cluster (one TPC) work on one 256 x 256 tile: each owns 128 A rows (its own
+// accumulator half in its own TMEM) and loads only HALF of the B tile (128 rows); the leader CTA's
+// single MMA thread issues tcgen05.mma.cta_group::2 (M = 256), which reads A and the B halves from both
+// CTAs' shared memory.  Per SM this halves the B bytes fetched from L2 and written to / read from
+// shared memory, which is what bounds the one-CTA kernel (60 B/clk/SM of TMA traffic against an L2
+// that sustains ~42 B/clk/SM, plus operand reads on the same shared-memory port).
+//   full_bar      leader's: armed by the leader's producer for BOTH CTAs' bytes; the peer's TMA
+//                 completes its bytes on the leader's barrier (address with the peer bit cleared)
+//   empty_bar     per CTA: tcgen05.commit multicast to both CTAs
+//   tmem_full     per CTA: tcgen05.commit multicast to both CTAs
+//   tmem_empty    leader's: 8 arrivals (4 epilogue warps x 2 CTAs), the peer arrives remotely
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // shared::cluster address of the same variable in CTA 0 of the pair
+constexpr int kBHalfBytes = (BN / 2) * BK * 2;  // 16 KB
+
+template <int kSplitsT>
+struct StageLayout2 {
+  static constexpr int kBytes = kSplitsT * kABytes + kBHalfBytes;
+  static constexpr int kStagesT = kSplitsT == 1 ? 6 : 4;
+  static constexpr size_t kSmem = (size_t)kStagesT * kBytes + 1024;
+};
+
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int kSplitsT, int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, GemmArgs a) {
+  using SL = StageLayout2<kSplitsT>;
+  constexpr int kSt = SL::kStagesT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[kSt], empty_bar[kSt], tmem_full_bar[2], tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ uint32_t s_masks[kEpi == kEpiFilter ? BN / 32 : 1][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const uint32_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t mt2 = (a.mt + 1) >> 1;  // A tiles are taken two at a time
+  const uint32_t total_tiles = mt2 * a.nt;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBh)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kSt; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---- TMA producer (both CTAs) ----
+      uint32_t it = 0;
+      for (uint32_t t = pair; t < total_tiles; t += npairs) {
+        const uint32_t m0 = ((t % mt2) * 2 + rank) * BM, n0 = a.row0 + (t / mt2) * BN + rank * (BN / 2);
+        for (uint32_t kb = 0; kb < a.num_kb; ++kb, ++it) {
+          const int st = it % kSt;
+          const uint32_t ph = (it / kSt) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          uint8_t* base = smem + (size_t)st * SL::kBytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * SL::kBytes);
+          for (int s = 0; s < kSplitsT; ++s)
+            tma_load_2d_pair(base + s * kABytes, &tmA, &full_bar[st], (int)(kb * BK), (int)(s * a.m_pad + m0));
+          tma_load_2d_pair(base + kSplitsT * kABytes, &tmBh, &full_bar[st], (int)(kb * BK), (int)n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {  // ---- MMA issuer (leader CTA only) ----
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      uint32_t it = 0, lt = 0;
+      long long w_empty = 0, w_full = 0;
+      const long long t_begin = clock64();
+      for (uint32_t t = pair; t < total_tiles; t += npairs, ++lt) {
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        long long c0 = clock64();
+        mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+        w_empty += clock64() - c0;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem + as * BN;
+        for (uint32_t kb = 0; kb < a.num_kb; ++kb, ++it) {
+          const int st = it % kSt;
+          const uint32_t ph = (it / kSt) & 1;
+          c0 = clock64();
+          mbar_wait(&full_bar[st], ph);
+          w_full += clock64() - c0;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sbase = smem_u32(smem + (size_t)st * SL::kBytes);
+          const uint32_t sB = sbase + kSplitsT * kABytes;
+#pragma unroll
+          for (int s = 0; s < kSplitsT; ++s) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = umma_desc_sw128(sbase + s * kABytes + k * 32);
+              const uint64_t bd = umma_desc_sw128(sB + k * 32);
+              umma_bf16_pair(tacc, ad, bd, idesc, (kb | (uint32_t)s | (uint32_t)k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_pair(&empty_bar[st]);
+        }
+        umma_commit_pair(&tmem_full_bar[as]);
+      }
+      if (a.prof && blockIdx.x == 0)
+        printf("[gemm_pair] tiles %u kb %u: total %lld clk, wait tmem_empty %lld, wait full %lld\n", lt, a.num_kb,
+               clock64() - t_begin, w_empty, w_full);
+    }
+  } else if (warp >= 4) {  // ---- epilogue (both CTAs, each its own 128 A rows) ----
+    const int quad = warp & 3;
+    uint32_t lt = 0;
+    for (uint32_t t = pair; t < total_tiles; t += npairs, ++lt) {
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      const uint32_t m0 = ((t % mt2) * 2 + rank) * BM, n0 = a.row0 + (t / mt2) * BN;
+      const uint32_t q = m0 + quad * 32 + lane;
+      const bool qvalid = q < a.nq;
+      const uint32_t tbase = tmem + as * BN + ((uint32_t)(quad * 32) << 16);
+      if (kEpi == kEpiFilter) {
+        mbar_wait(&tmem_full_bar[as], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        filter_tile(a, tbase, q, qvalid, n0, &s_masks[0][threadIdx.x - 128]);
+      } else {
+        mbar_wait(&tmem_full_bar[as], aph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float* dst = a.out + (size_t)q * a.ld;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tbase + (uint32_t)(c * 32), v);
+          const uint32_t col = n0 + c * 32;
+          if (qvalid) {
+            if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(dst + col + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < a.row1) dst[col + j] = __uint_as_float(v[j]);
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[as]);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();  // the peer's shared memory and barriers stay valid until both CTAs are done
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -390,13 +594,16 @@ static cudaError_t make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, u
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// A rows are padded to whole CTA pairs (2 x 128 rows)
+static uint32_t bf_m_pad(uint32_t nq) { return (nq + 2 * bf::BM - 1) / (2 * bf::BM) * (2 * bf::BM); }
+
 size_t bf_query_operand_bytes(uint32_t nq, uint32_t dpitch) {
-  const uint32_t m_pad = (nq + bf::BM - 1) / bf::BM * bf::BM;
+  const uint32_t m_pad = bf_m_pad(nq);
   return (size_t)bf::kSplits * m_pad * dpitch * 2;
 }
 
 cudaError_t bf_split_queries(const float* q, uint32_t nq, uint32_t d, uint32_t dpitch, void* a_operand, cudaStream_t s) {
-  const uint32_t m_pad = (nq + bf::BM - 1) / bf::BM * bf::BM;
+  const uint32_t m_pad = bf_m_pad(nq);
   const size_t total = (size_t)m_pad * dpitch;
   bf::split_queries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(q, nq, d, dpitch, m_pad,
                                                                            reinterpret_cast<__nv_bfloat16*>(a_operand));
@@ -431,20 +638,42 @@ static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, c
   return cudaGetLastError();
 }
 
+template <int kSplitsT, int kEpi>
+static cudaError_t launch_gemm_pair(const CUtensorMap& tmA, const CUtensorMap& tmBh, const bf::GemmArgs& a, cudaStream_t s) {
+  using SL = bf::StageLayout2<kSplitsT>;
+  cudaError_t e = cudaFuncSetAttribute(bf::gemm_pair_kernel<kSplitsT, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)SL::kSmem);
+  if (e != cudaSuccess) return e;
+  const uint32_t tiles = ((a.mt + 1) / 2) * a.nt;
+  if (tiles == 0) return cudaSuccess;
+  const uint32_t pairs = (uint32_t)sm_count() / 2;
+  const uint32_t grid = 2 * (tiles < pairs ? tiles : pairs);  // persistent, one CTA pair per TPC
+  bf::gemm_pair_kernel<kSplitsT, kEpi><<<grid, bf::kThreads, SL::kSmem, s>>>(tmA, tmBh, a);
+  return cudaGetLastError();
+}
+
+static bool use_pair_kernel() {
+  const char* e = getenv("SCANN_B200_GEMM");
+  return !(e && !strcmp(e, "1cta"));
+}
+
 // One round: database rows [row0, row1) against all queries.
 cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, uint32_t n_total, uint32_t dpitch,
                           uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s) {
-  const uint32_t m_pad = (nq + bf::BM - 1) / bf::BM * bf::BM;
+  const uint32_t m_pad = bf_m_pad(nq);
+  const bool pair = use_pair_kernel();
   CUtensorMap tmA, tmB;
   cudaError_t e = make_tmap(&tmA, a_operand, (uint64_t)bf::kSplits * m_pad, dpitch, dpitch, bf::BM);
   if (e != cudaSuccess) return e;
-  e = make_tmap(&tmB, db, n_total, dpitch, dpitch, bf::BN);
+  e = make_tmap(&tmB, db, n_total, dpitch, dpitch, pair ? bf::BN / 2 : bf::BN);
   if (e != cudaSuccess) return e;
   bf::GemmArgs a{};
   a.nq = nq; a.m_pad = m_pad; a.row0 = row0; a.row1 = row1;
   a.mt = m_pad / bf::BM; a.nt = (row1 - row0 + bf::BN - 1) / bf::BN;
   a.num_kb = (dpitch + bf::BK - 1) / bf::BK;
   a.buf = w.buf; a.cnt = w.cnt; a.tau = w.tau; a.ovf = w.ovf; a.cap = w.cap;
+  { const char* pe = getenv("SCANN_B200_GEMM_PROFILE"); a.prof = pe && pe[0] == '1'; }
+  if (pair) return launch_gemm_pair<bf::kSplits, bf::kEpiFilter>(tmA, tmB, a, s);
   return launch_gemm<bf::kSplits, bf::kEpiFilter>(tmA, tmB, a, s);
 }
 
