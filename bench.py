@@ -479,7 +479,9 @@ def run_bruteforce(args, wl, rank, world, local_rank):
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
   except Exception:
     pass
-  peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+  # the GEMM rounds run as ~20 ms bursts between L2 flushes, i.e. "a kernel timed alone": burst peak
+  peak = float(peaks.get("bf16_tflops", 1590.0))
+  peak_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
   out = {"metric": "batched QPS, bf16 brute-force MIPS k=100", "value": nq * args.steps / (ms_total * 1e-3),
          "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
          "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -490,8 +492,10 @@ def run_bruteforce(args, wl, rank, world, local_rank):
                  "d2h_bytes_per_step": int(nq * k * 8), "steps": e2e_steps},
          "gpu_launches": int(agg["kernel_launches"]), "clocks": sampler.summary(),
          "roofline": {"bound": "tensor", "kernel": "bf::gemm_pair_kernel<2, filter>", "achieved": flops / gemm_s / 1e12,
-                      "peak": peak, "peak_source": "measured sustained" if peaks else "fallback", "unit": "TFLOP/s",
+                      "peak": peak, "peak_source": "measured burst" if peaks else "fallback", "unit": "TFLOP/s",
                       "frac": flops / gemm_s / 1e12 / peak, "traffic": None,
+                      "frac_of_sustained_peak": flops / gemm_s / 1e12 / peak_sustained,
+                      "note": "flops count both bf16 query terms (hi + lo); time includes the compactions between rounds",
                       "useful_tflops_f32_equivalent": flops / 2 / gemm_s / 1e12},
          "stage_ms_per_step": {s: agg[s] / args.steps for s in agg if s.startswith("ms_")}}
   emit(out)

@@ -38,7 +38,8 @@ constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kSplits = 2;
 constexpr int kABytes = BM * BK * 2;                       // 16 KB per split
 constexpr int kBBytes = BN * BK * 2;                       // 32 KB
-constexpr int kThreads = 256;                              // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+constexpr int kThreads = 384;                              // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-11 epilogue
+constexpr int kEpiWarps = 8;                               // two per TMEM lane quadrant, 128 columns each
 constexpr int kTmemCols = 512;                             // two 256-column fp32 accumulators
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,14 +122,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // pass 2 re-reads only chunks with survivors, applies the exact 64-bit key test and pads the few
 // reserved-but-rejected slots with kKeyMax, which every later compaction sorts past the end.
 __device__ __forceinline__ void filter_tile(const GemmArgs& a, uint32_t tbase, uint32_t q, bool qvalid, uint32_t n0,
-                                            uint32_t* masks /* [BN/32] stride 128 */) {
+                                            uint32_t* masks /* [BN/32] stride 128 */, int c_begin, int c_end) {
   const uint64_t tau = qvalid ? a.tau[q] : 0ull;
   float thr = __int_as_float(0x7F800000);                         // +inf: nothing passes
   if (qvalid) thr = tau == kKeyMax ? __int_as_float(0xFF800000)   // -inf: everything passes
                                    : -ord2f((uint32_t)(tau >> 32));
   uint32_t total = 0;
 #pragma unroll 1
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = c_begin; c < c_end; ++c) {
     uint32_t v[32];
     tmem_ld32(tbase + (uint32_t)(c * 32), v);
     uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
@@ -150,7 +151,7 @@ __device__ __forceinline__ void filter_tile(const GemmArgs& a, uint32_t tbase, u
     const uint32_t end = pos + total;
     uint64_t* dst = a.buf + (size_t)q * a.cap;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
+    for (int c = c_begin; c < c_end; ++c) {
       const uint32_t m = masks[c * 128];
       if (__any_sync(0xFFFFFFFFu, m != 0)) {
         uint32_t v[32];
@@ -206,7 +207,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kSt; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -267,6 +268,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {  // ---- epilogue: one TMEM lane = one A row (query) ----
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;  // which 128 columns of the tile
     uint32_t lt = 0;
     for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
@@ -277,13 +279,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (kEpi == kEpiFilter) {
         mbar_wait(&tmem_full_bar[as], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        filter_tile(a, tbase, q, qvalid, n0, &s_masks[0][threadIdx.x - 128]);
+        filter_tile(a, tbase, q, qvalid, n0, &s_masks[0][quad * 32 + lane], half * (BN / 64), (half + 1) * (BN / 64));
       } else {
         mbar_wait(&tmem_full_bar[as], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* dst = a.out + (size_t)q * a.ld;
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)(c * 32), v);
           const uint32_t col = n0 + c * 32;
@@ -381,7 +383,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kSt; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -451,6 +453,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {  // ---- epilogue (both CTAs, each its own 128 A rows) ----
     const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
     uint32_t lt = 0;
     for (uint32_t t = pair; t < total_tiles; t += npairs, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
@@ -461,13 +464,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (kEpi == kEpiFilter) {
         mbar_wait(&tmem_full_bar[as], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        filter_tile(a, tbase, q, qvalid, n0, &s_masks[0][threadIdx.x - 128]);
+        filter_tile(a, tbase, q, qvalid, n0, &s_masks[0][quad * 32 + lane], half * (BN / 64), (half + 1) * (BN / 64));
       } else {
         mbar_wait(&tmem_full_bar[as], aph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float* dst = a.out + (size_t)q * a.ld;
 #pragma unroll
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)(c * 32), v);
           const uint32_t col = n0 + c * 32;
