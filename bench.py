@@ -407,8 +407,8 @@ def run_bruteforce(args, wl, rank, world, local_rank):
   """C3: bf16 brute force, 10k queries x 1M x 768, k = 100 (tcgen05 GEMM + fused top-k pre-filter)."""
   import torch
   from scann_b200 import _lib, index_build
-  if world > 1 and rank != 0:
-    return 0  # replicas only at N > 1 for this workload; rank 0 reports one replica
+  if world > 1 and rank != 0 and args.impl == "reference":
+    return 0
   n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]
   rng = np.random.default_rng(wl["seed"])
   t0 = time.time()
@@ -438,6 +438,11 @@ def run_bruteforce(args, wl, rank, world, local_rank):
     return 0
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
   ix = _lib.NativeIndex(a, 1, k, k, device=local_rank)
   d_q = torch.from_numpy(q).to(dev)
   d_idx = torch.zeros((nq, k), dtype=torch.int32, device=dev)
@@ -456,6 +461,9 @@ def run_bruteforce(args, wl, rank, world, local_rank):
   sampler = ClockSampler(local_rank)
   sampler.start()
   ms_total, agg = 0.0, {}
+  if dist is not None:
+    dist.barrier()
+  torch.cuda.synchronize()
   for _ in range(args.steps):
     flush.zero_()
     torch.cuda.synchronize()
@@ -466,12 +474,52 @@ def run_bruteforce(args, wl, rank, world, local_rank):
       agg[key] = agg.get(key, 0) + val
   e2e_steps = max(2, min(args.steps, 5))
   ix.search_batched(q)
+  if dist is not None:
+    dist.barrier()
   e0 = time.perf_counter()
   for _ in range(e2e_steps):
     ix.search_batched(q)
   e2e_s = time.perf_counter() - e0
   sampler.stop_flag.set()
   sampler.join(timeout=2)
+  row_sharded = None
+  if dist is not None:
+    # max over ranks of the device time and of the end-to-end wall time (one replica per GPU, weak scaling)
+    t = torch.tensor([ms_total, e2e_s], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s = float(t[0]), float(t[1])
+    # the database row-sharded over the ranks: same 10k queries everywhere, local top-k, all-gather, merge
+    from scann_b200 import distributed as sd
+    ref_idx = d_idx.clone()
+    del ix
+    torch.cuda.empty_cache()
+    sh = sd.ShardedBruteForce(a, k, rank, world, local_rank)
+    for _ in range(args.warmup):
+      sh.search_batched_device(d_q, d_idx, d_dist)
+    same = bool((d_idx == ref_idx).all().item())
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sh_ms, sh_agg = 0.0, {}
+    for _ in range(args.steps):
+      flush.zero_()
+      dist.barrier()
+      torch.cuda.synchronize()
+      w0 = time.perf_counter()
+      st = sh.search_batched_device(d_q, d_idx, d_dist)
+      torch.cuda.synchronize()
+      sh_ms += (time.perf_counter() - w0) * 1e3
+      for key, val in st.items():
+        sh_agg[key] = sh_agg.get(key, 0) + val
+    t = torch.tensor([sh_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    row_sharded = {"value": nq * args.steps / (float(t[0]) * 1e-3), "unit": "queries/s",
+                   "ids_equal_replica": same, "timing": "wall clock around search + all-gather + merge, max over ranks",
+                   "allgather_bytes_per_rank": sh_agg.get("allgather_bytes_per_rank", 0) // max(args.steps, 1),
+                   "stage_ms_per_step": {s_: sh_agg[s_] / args.steps for s_ in sh_agg if s_.startswith("ms_")}}
+    if rank != 0:
+      dist.destroy_process_group()
+      return 0
   flops = 2.0 * nq * n * d * 2  # two bf16 split terms per product
   gemm_s = agg["ms_scan"] / args.steps * 1e-3
   peaks = {}
@@ -482,14 +530,15 @@ def run_bruteforce(args, wl, rank, world, local_rank):
   # the GEMM rounds run as ~20 ms bursts between L2 flushes, i.e. "a kernel timed alone": burst peak
   peak = float(peaks.get("bf16_tflops", 1590.0))
   peak_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
-  out = {"metric": "batched QPS, bf16 brute-force MIPS k=100", "value": nq * args.steps / (ms_total * 1e-3),
-         "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+  out = {"metric": "batched QPS, bf16 brute-force MIPS k=100", "value": world * nq * args.steps / (ms_total * 1e-3),
+         "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
          "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
          "dtype": "bf16 x (bf16 hi + bf16 lo) -> f32 (tcgen05), f32 re-scoring", "data": "synthetic",
-         "config": {"workload": args.workload, "n": n, "d": d, "k": k, "queries_per_step": nq,
-                    "recall_at_100_first512": rec, "l2_flush": "256 MiB write between timed steps"},
-         "e2e": {"value": nq * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q.nbytes),
-                 "d2h_bytes_per_step": int(nq * k * 8), "steps": e2e_steps},
+         "config": {"workload": args.workload, "n": n, "d": d, "k": k, "queries_per_step": nq * world,
+                    "recall_at_100_first512": rec, "l2_flush": "256 MiB write between timed steps",
+                    "parallelism": f"query-parallel x{world} (one replica and one {nq}-query batch per GPU)"},
+         "e2e": {"value": world * nq * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q.nbytes) * world,
+                 "d2h_bytes_per_step": int(nq * k * 8) * world, "steps": e2e_steps},
          "gpu_launches": int(agg["kernel_launches"]), "clocks": sampler.summary(),
          "roofline": {"bound": "tensor", "kernel": "bf::gemm_pair_kernel<2, filter>", "achieved": flops / gemm_s / 1e12,
                       "peak": peak, "peak_source": "measured burst" if peaks else "fallback", "unit": "TFLOP/s",
@@ -498,6 +547,9 @@ def run_bruteforce(args, wl, rank, world, local_rank):
                       "note": "flops count both bf16 query terms (hi + lo); time includes the compactions between rounds",
                       "useful_tflops_f32_equivalent": flops / 2 / gemm_s / 1e12},
          "stage_ms_per_step": {s: agg[s] / args.steps for s in agg if s.startswith("ms_")}}
+  if row_sharded is not None:
+    out["row_sharded"] = row_sharded
+    dist.destroy_process_group()
   emit(out)
   return 0
 

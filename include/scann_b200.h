@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SCANN_B200_ABI_VERSION 1
+#define SCANN_B200_ABI_VERSION 2
 
 enum { SCANN_B200_DOT_PRODUCT = 0, SCANN_B200_SQUARED_L2 = 1 };
 
@@ -103,6 +103,16 @@ int scann_b200_merge_partials_device(scann_b200_index* index, uint32_t nq, int32
                                      const uint64_t* d_tiebreak, const float* d_ah_score,
                                      const float* d_exact, int32_t pre_reorder_nn, int32_t final_nn,
                                      uint32_t* d_out_idx, float* d_out_dist, int32_t out_k);
+
+/* Row-sharded brute force (the reference has no multi-device searcher, the single
+ * device semantics are Bfloat16BruteForceSearcher::FindNeighborsImpl, brute_force/bfloat16_brute_force.cc:101-152).
+ * A brute-force index created with shard_world > 1 keeps the contiguous rows
+ * [rank * ceil(N / world), ...) and its search calls return GLOBAL ids.  This entry point merges the
+ * `world` all-gathered local results ([world][nq][k_in] ids + API-signed distances) into the global
+ * top-k by (distance, id): identical to the unsharded result. */
+int scann_b200_merge_topk_device(scann_b200_index* index, uint32_t nq, int32_t world, int32_t k_in,
+                                 const uint32_t* d_ids, const float* d_dists, int32_t final_nn,
+                                 uint32_t* d_out_idx, float* d_out_dist, int32_t out_k);
 
 const char* scann_b200_last_error(void);
 int scann_b200_abi_version(void);

@@ -46,7 +46,8 @@ class Stats(C.Structure):
 EXPORTS = [
     "scann_b200_index_create", "scann_b200_index_destroy", "scann_b200_search_batched",
     "scann_b200_search_batched_device", "scann_b200_search_partial_device",
-    "scann_b200_merge_partials_device", "scann_b200_last_error", "scann_b200_abi_version",
+    "scann_b200_merge_partials_device", "scann_b200_merge_topk_device", "scann_b200_last_error",
+    "scann_b200_abi_version",
     "scann_b200_debug_tokenize", "scann_b200_debug_lut", "scann_b200_debug_leaf_scores",
     "scann_b200_debug_candidates", "scann_b200_leaf_size", "scann_b200_last_stats",
     "scann_b200_assets_load", "scann_b200_assets_free", "scann_b200_assets_describe",
@@ -77,6 +78,7 @@ def lib():
   L.scann_b200_search_batched_device.argtypes = [vp, vp, u32, i32, i32, i32, vp, vp, i32]
   L.scann_b200_search_partial_device.argtypes = [vp, vp, u32, i32, i32, vp, vp, vp, vp, i32]
   L.scann_b200_merge_partials_device.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, i32]
+  L.scann_b200_merge_topk_device.argtypes = [vp, u32, i32, i32, vp, vp, i32, vp, vp, i32]
   L.scann_b200_last_error.restype = C.c_char_p
   L.scann_b200_abi_version.restype = C.c_int
   L.scann_b200_debug_tokenize.argtypes = [vp, vp, u32, i32, vp, vp]

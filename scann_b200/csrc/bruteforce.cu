@@ -524,7 +524,8 @@ __global__ void init_topk_state_kernel(uint32_t nq, uint32_t* cnt, uint64_t* tau
 __global__ void __launch_bounds__(128)
 rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db, uint32_t d, uint32_t dpitch,
                const uint64_t* __restrict__ buf, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t kprime,
-               uint32_t k, uint32_t out_k, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int np2) {
+               uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist,
+               int np2) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
   float* sq = reinterpret_cast<float*>(ka + np2);
@@ -558,7 +559,7 @@ rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db
   for (uint32_t i = tid; i < out_k; i += 128) {
     uint32_t id = 0;
     float dist = __uint_as_float(0x7FC00000u);
-    if (i < kk) { id = (uint32_t)ka[i]; dist = -ord2f((uint32_t)(ka[i] >> 32)); }
+    if (i < kk) { id = (uint32_t)ka[i] + id_base; dist = -ord2f((uint32_t)(ka[i] >> 32)); }
     out_idx[(size_t)qi * out_k + i] = id;
     out_dist[(size_t)qi * out_k + i] = dist;
   }
@@ -698,14 +699,15 @@ cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows
 }
 
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
-                       uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t* out_idx, float* out_dist, cudaStream_t s) {
+                       uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist,
+                       cudaStream_t s) {
   int np2 = 2;
   while ((uint32_t)np2 < kprime) np2 <<= 1;
   const size_t smem = (size_t)np2 * 8 + (((size_t)d + 3) & ~(size_t)3) * 4;
   cudaError_t e = cudaFuncSetAttribute(bf::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   bf::rescore_kernel<<<nq, 128, smem, s>>>(q, reinterpret_cast<const __nv_bfloat16*>(db), d, dpitch, w.buf, w.cnt, w.cap,
-                                           kprime, k, out_k, out_idx, out_dist, np2);
+                                           kprime, k, out_k, id_base, out_idx, out_dist, np2);
   return cudaGetLastError();
 }
 

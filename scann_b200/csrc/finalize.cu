@@ -349,4 +349,49 @@ cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, in
   return cudaGetLastError();
 }
 
+
+// Row-sharded brute force: every rank contributes its local top-k as (global id, API-signed
+// distance); the global top-k is the k smallest (internal distance, id) keys of the union, which is exactly
+// the single-GPU result because the exact re-scoring of a row does not depend on which shard holds it.
+__global__ void __launch_bounds__(kFinThreads)
+merge_topk_kernel(int distance, uint32_t nq, int world, int k_in, const uint32_t* __restrict__ ids,
+                  const float* __restrict__ dists, uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k,
+                  int np2) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
+  const int tid = threadIdx.x;
+  const uint32_t q = blockIdx.x;
+  const int total = world * k_in;
+  const float sign = distance == 0 ? -1.f : 1.f;  // API distance -> internal distance (scann.cc:364-369)
+  for (int i = tid; i < np2; i += kFinThreads) {
+    uint64_t key = kKeyMax;
+    if (i < total) {
+      const size_t o = ((size_t)(i / k_in) * nq + q) * k_in + (i % k_in);
+      const float d = dists[o];
+      if (d == d) key = make_key(sign * d, ids[o]);  // NaN marks the padding of a short row
+    }
+    ka[i] = key;
+  }
+  __syncthreads();
+  block_bitonic_sort(ka, np2);
+  for (uint32_t i = tid; i < out_k; i += kFinThreads) {
+    uint32_t id = 0;
+    float dist = __uint_as_float(0x7FC00000u);
+    if (i < k && (int)i < np2 && ka[i] != kKeyMax) { id = (uint32_t)ka[i]; dist = sign * ord2f((uint32_t)(ka[i] >> 32)); }
+    out_idx[(size_t)q * out_k + i] = id;
+    out_dist[(size_t)q * out_k + i] = dist;
+  }
+}
+
+cudaError_t launch_merge_topk(int distance, uint32_t nq, int world, int k_in, const uint32_t* ids, const float* dists,
+                              uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k, cudaStream_t s) {
+  int np2 = 2;
+  while (np2 < world * k_in) np2 <<= 1;
+  const size_t smem = (size_t)np2 * 8;
+  cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  merge_topk_kernel<<<nq, kFinThreads, smem, s>>>(distance, nq, world, k_in, ids, dists, k, out_idx, out_dist, out_k, np2);
+  return cudaGetLastError();
+}
+
 }  // namespace sb

@@ -109,6 +109,7 @@ struct scann_b200_index {
   // brute-force (bf16) searcher: database rows as bf16 with a 16-byte aligned pitch
   bool brute = false;
   uint32_t bf_dpitch = 0;
+  uint32_t bf_row0 = 0;  // first database row of this shard (row-sharded brute force)
   DevBuf bf_db, bf_a;
 };
 
@@ -122,17 +123,23 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     // Bfloat16BruteForceSearcher (brute_force/bfloat16_brute_force.cc): bf16 rows, MIPS only
     if (!d->bf16_dataset) return fail(SCANN_B200_UNIMPLEMENTED, "brute force is implemented for bfloat16 datasets only (bfloat16_dataset.npy)");
     if (d->distance != SCANN_B200_DOT_PRODUCT) return fail(SCANN_B200_UNIMPLEMENTED, "bfloat16 brute force supports dot product distance only");
+    // row-sharded brute force: rank r keeps the contiguous rows [r * ceil(N / world), ...) and reports global ids
     const int world_bf = d->shard_world > 0 ? d->shard_world : 1;
-    if (world_bf != 1) return fail(SCANN_B200_UNIMPLEMENTED, "sharded brute force is not implemented");
+    const int rank_bf = d->shard_rank;
+    if (rank_bf < 0 || rank_bf >= world_bf) return fail(SCANN_B200_INVALID_ARGUMENT, "shard_rank %d outside [0, %d)", rank_bf, world_bf);
+    const uint32_t per = (N + (uint32_t)world_bf - 1) / (uint32_t)world_bf;
+    const uint32_t row0 = std::min<uint64_t>((uint64_t)per * rank_bf, N), row1 = std::min<uint64_t>((uint64_t)row0 + per, N);
+    const uint32_t nloc = row1 - row0;
     sb::DevIndex& vb = ix->dev;
     vb = sb::DevIndex{};
-    vb.distance = d->distance; vb.n = N; vb.d = D; vb.disjoint = 1;
+    vb.distance = d->distance; vb.n = nloc; vb.d = D; vb.disjoint = 1;
     ix->brute = true;
+    ix->bf_row0 = row0;
     ix->bf_dpitch = (D + 7) / 8 * 8;
-    CU(ix->bf_db.ensure((size_t)std::max<uint32_t>(N, 1) * ix->bf_dpitch * 2));
-    CU(cudaMemset(ix->bf_db.p, 0, (size_t)std::max<uint32_t>(N, 1) * ix->bf_dpitch * 2));
-    if (N) CU(cudaMemcpy2D(ix->bf_db.p, (size_t)ix->bf_dpitch * 2, d->bf16_dataset, (size_t)D * 2, (size_t)D * 2, N,
-                           cudaMemcpyHostToDevice));
+    CU(ix->bf_db.ensure((size_t)std::max<uint32_t>(nloc, 1) * ix->bf_dpitch * 2));
+    CU(cudaMemset(ix->bf_db.p, 0, (size_t)std::max<uint32_t>(nloc, 1) * ix->bf_dpitch * 2));
+    if (nloc) CU(cudaMemcpy2D(ix->bf_db.p, (size_t)ix->bf_dpitch * 2, d->bf16_dataset + (size_t)row0 * D, (size_t)D * 2,
+                              (size_t)D * 2, nloc, cudaMemcpyHostToDevice));
     return 0;
   }
   if (!L || !B) return fail(SCANN_B200_UNIMPLEMENTED, "only tree-AH and bf16 brute-force indexes are implemented (n_leaves=%u, n_blocks=%u)", L, B);
@@ -521,7 +528,7 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (hc[2] != 0) return fail(SCANN_B200_INTERNAL, "brute force: candidate buffer overflow (%u queries)", hc[2]);
-  CU(sb::bf_rescore(d_q, ix->bf_db.p, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, d_out_idx, d_out_dist, s));
+  CU(sb::bf_rescore(d_q, ix->bf_db.p, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
   launches += 1;
   CU(cudaEventRecord(ix->ev[EV_FIN], s));
   CU(cudaStreamSynchronize(s));
@@ -685,6 +692,22 @@ int scann_b200_merge_partials_device(scann_b200_index* ix, uint32_t nq, int32_t 
   (void)d_ah;
   CU(sb::launch_merge_partials(ix->dev, nq, world, n_cand, d_ids, d_tie, d_exact, p.nover, p.npre, p.k, d_out_idx,
                                d_out_dist, (uint32_t)out_k, ix->stream));
+  CU(cudaStreamSynchronize(ix->stream));
+  return 0;
+}
+
+int scann_b200_merge_topk_device(scann_b200_index* ix, uint32_t nq, int32_t world, int32_t k_in, const uint32_t* d_ids,
+                                 const float* d_dists, int32_t final_nn, uint32_t* d_out_idx, float* d_out_dist,
+                                 int32_t out_k) {
+  if (!ix) return fail(SCANN_B200_INVALID_ARGUMENT, "null index");
+  if (!d_ids || !d_dists || !d_out_idx || !d_out_dist || world < 1 || k_in < 1 || out_k < 1)
+    return fail(SCANN_B200_INVALID_ARGUMENT, "merge_topk: bad arguments");
+  if ((long long)world * k_in > 8192) return fail(SCANN_B200_UNIMPLEMENTED, "merge of %d x %d results too large", world, k_in);
+  const int k = final_nn > 0 ? final_nn : k_in;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  CU(cudaSetDevice(ix->device));
+  CU(sb::launch_merge_topk(ix->dev.distance, nq, world, k_in, d_ids, d_dists, (uint32_t)k, d_out_idx, d_out_dist,
+                           (uint32_t)out_k, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   return 0;
 }

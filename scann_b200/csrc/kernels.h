@@ -98,6 +98,8 @@ cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, in
                                   const uint32_t* ids, const uint64_t* tie, const float* exact,
                                   uint32_t nover, uint32_t npre, uint32_t k, uint32_t* out_idx,
                                   float* out_dist, uint32_t out_k, cudaStream_t s);
+cudaError_t launch_merge_topk(int distance, uint32_t nq, int world, int k_in, const uint32_t* ids, const float* dists,
+                              uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k, cudaStream_t s);
 // ---- bf16 brute force (tcgen05 GEMM + fused top-k pre-filter), bruteforce.cu ----
 size_t bf_query_operand_bytes(uint32_t nq, uint32_t dpitch);
 cudaError_t bf_split_queries(const float* q, uint32_t nq, uint32_t d, uint32_t dpitch, void* a_operand, cudaStream_t s);
@@ -105,7 +107,8 @@ cudaError_t bf_init_state(uint32_t nq, uint32_t* cnt, uint64_t* tau, uint32_t* o
 cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, uint32_t n_total, uint32_t dpitch,
                           uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s);
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
-                       uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t* out_idx, float* out_dist, cudaStream_t s);
+                       uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist,
+                       cudaStream_t s);
 // out[a_row * ld + b_row] = sum_k A[a_row][k] * B[b_row][k]; bf16 operands with row pitch kpitch (multiple of 64),
 // a_rows_pad a multiple of 128 (padding rows readable), fp32 accumulate on tcgen05.
 cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows_pad, const void* b_operand,

@@ -145,3 +145,81 @@ class ShardedSearcher:
     d_dist = t.empty((q.shape[0], self.k), dtype=t.float32, device=self.dev)
     self.search_batched_device(d_q, d_idx, d_dist)
     return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy()
+
+
+def merge_topk_reference(ids, dists, k, dot_product=True):
+  """numpy restatement of scann_b200_merge_topk_device: ids/dists [world][nq][k_in] (API-signed distances, NaN =
+  padding) -> global top-k by (internal distance, id)."""
+  world, nq, k_in = ids.shape
+  out_i = np.zeros((nq, k), dtype=np.uint32)
+  out_d = np.full((nq, k), np.nan, dtype=np.float32)
+  sign = np.float32(-1.0 if dot_product else 1.0)
+  for q in range(nq):
+    i = ids[:, q, :].reshape(-1).astype(np.uint32)
+    d = dists[:, q, :].reshape(-1).astype(np.float32)
+    ok = ~np.isnan(d)
+    i, d = i[ok], d[ok]
+    order = np.lexsort((i, sign * d))[:k]
+    out_i[q, :len(order)] = i[order]
+    out_d[q, :len(order)] = d[order]
+  return out_i, out_d
+
+
+class ShardedBruteForce:
+  """One rank of a row-sharded bf16 brute-force searcher (BASELINE.json configs[2] at N > 1 GPUs): local top-k over
+  this rank's rows, one all-gather of (id, distance), merge on the device.  Equal to the unsharded result."""
+
+  def __init__(self, arrays, final_nn, rank, world, device, group=None):
+    import torch
+    self.torch = torch
+    self.rank, self.world, self.group = rank, world, group
+    self.dev = torch.device("cuda", device)
+    self.index = _lib.NativeIndex(arrays, 1, final_nn, final_nn, device=device, shard_rank=rank, shard_world=world)
+    self.k = final_nn
+    self._bufs = None
+
+  def _buffers(self, nq):
+    t = self.torch
+    if self._bufs is None or self._bufs[0].shape[0] != nq:
+      k, w, dev = self.k, self.world, self.dev
+      self._bufs = (t.empty((nq, k), dtype=t.int32, device=dev), t.empty((nq, k), dtype=t.float32, device=dev),
+                    t.empty((w * nq, k), dtype=t.int32, device=dev), t.empty((w * nq, k), dtype=t.float32, device=dev))
+    return self._bufs
+
+  def search_batched_device(self, d_q, d_idx, d_dist):
+    import torch.distributed as dist
+    t = self.torch
+    nq = d_q.shape[0]
+    ids, ds, g_ids, g_ds = self._buffers(nq)
+    L = _lib.lib()
+    vp = C.c_void_p
+    h = self.index._h
+    _lib.check(L.scann_b200_search_batched_device(h, vp(d_q.data_ptr()), nq, self.k, -1, -1, vp(ids.data_ptr()),
+                                                  vp(ds.data_ptr()), self.k))
+    st = self.index.stats()
+    e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+    e0.record()
+    if self.world > 1:
+      dist.all_gather_into_tensor(g_ids, ids, group=self.group)
+      dist.all_gather_into_tensor(g_ds, ds, group=self.group)
+    else:
+      g_ids.copy_(ids)
+      g_ds.copy_(ds)
+    e1.record()
+    t.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    _lib.check(L.scann_b200_merge_topk_device(h, nq, self.world, self.k, vp(g_ids.data_ptr()), vp(g_ds.data_ptr()),
+                                              self.k, vp(d_idx.data_ptr()), vp(d_dist.data_ptr()), d_idx.shape[1]))
+    st["ms_merge"] = (time.perf_counter() - t0) * 1e3
+    st["ms_allgather"] = e0.elapsed_time(e1)
+    st["allgather_bytes_per_rank"] = int(nq * self.k * 8)
+    return st
+
+  def search_batched(self, q):
+    t = self.torch
+    d_q = t.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(self.dev)
+    d_idx = t.empty((q.shape[0], self.k), dtype=t.int32, device=self.dev)
+    d_dist = t.empty((q.shape[0], self.k), dtype=t.float32, device=self.dev)
+    self.search_batched_device(d_q, d_idx, d_dist)
+    return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy()

@@ -22,14 +22,14 @@ def test_library_exports_every_declared_symbol():
   for n in names:
     assert hasattr(lib, n), f"{n} declared in include/scann_b200.h but not exported"
   assert sorted(_lib.EXPORTS) == names
-  assert lib.scann_b200_abi_version() == 1
+  assert lib.scann_b200_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
   from scann_b200 import _lib
   # 6 u32/i32, 3 pointers, i32 (+pad), 5 pointers, float + 6 i32
   assert ctypes.sizeof(_lib.IndexDesc) == 24 + 24 + 8 + 40 + 28 + 4
-  assert ctypes.sizeof(_lib.Stats) == 24 + 8 + 32 + 4 + 4 + 16
+  assert ctypes.sizeof(_lib.Stats) == 24 + 8 + 32 + 4 + 4 + 16 + 8
 
 
 def test_create_fails_loudly_without_gpu_or_arguments():

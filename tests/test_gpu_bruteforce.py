@@ -48,3 +48,38 @@ def test_bf16_bruteforce_recall_equals_oracle_recall():
   gt = np.argsort(-(q.astype(np.float64) @ x.T), axis=1)[:, :k]
   rec = lambda r: np.mean([len(set(r[i].tolist()) & set(gt[i].tolist())) / k for i in range(len(q))])
   assert rec(idx) == rec(oi) and rec(idx) > 0.999
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_row_sharded_bruteforce_equals_unsharded(world):
+  """Every shard on this one GPU, the all-gather replaced by a concatenation: local top-k with global ids,
+  scann_b200_merge_topk_device, against the unsharded index and the numpy restatement of the merge."""
+  import ctypes as C
+  import torch
+  from scann_b200 import _lib, distributed
+  n, d, nq, k = 30011, 96, 140, 50
+  a, bits, q = make(n, d, nq, seed=17)
+  full = _lib.NativeIndex(a, 1, k, k)
+  fi, fd = full.search_batched(q)
+  ids = np.zeros((world, nq, k), dtype=np.uint32)
+  ds = np.zeros((world, nq, k), dtype=np.float32)
+  shards = []
+  for r in range(world):
+    ix = _lib.NativeIndex(a, 1, k, k, shard_rank=r, shard_world=world)
+    shards.append(ix)
+    ids[r], ds[r] = ix.search_batched(q)
+    per = -(-n // world)
+    assert ids[r].min() >= r * per and ids[r].max() < min(n, (r + 1) * per)
+  ri, rd = distributed.merge_topk_reference(ids, ds, k)
+  np.testing.assert_array_equal(ri, fi)
+  np.testing.assert_array_equal(rd.view(np.uint32), fd.view(np.uint32))
+  dev = torch.device("cuda", 0)
+  g_ids = torch.from_numpy(ids.view(np.int32).reshape(world * nq, k)).to(dev)
+  g_ds = torch.from_numpy(ds.reshape(world * nq, k)).to(dev)
+  o_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
+  o_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+  vp = C.c_void_p
+  _lib.check(_lib.lib().scann_b200_merge_topk_device(shards[0]._h, nq, world, k, vp(g_ids.data_ptr()),
+                                                     vp(g_ds.data_ptr()), k, vp(o_i.data_ptr()), vp(o_d.data_ptr()), k))
+  np.testing.assert_array_equal(o_i.cpu().numpy().view(np.uint32), fi)
+  np.testing.assert_array_equal(o_d.cpu().numpy().view(np.uint32), fd.view(np.uint32))

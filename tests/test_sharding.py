@@ -102,3 +102,41 @@ def test_shard_tokens_partitions_every_leaf():
     np.testing.assert_array_equal(merged, dps)
     for r, p in enumerate(parts):
       assert (p[leaf] % 3 == r).all()
+
+
+# ---- row-sharded bf16 brute force (BASELINE.json configs[2] at N > 1) --------------------------------------
+def _bf_worker(rank, world, port, out_dir):
+  os.environ["MASTER_ADDR"] = "127.0.0.1"
+  os.environ["MASTER_PORT"] = str(port)
+  dist.init_process_group("gloo", rank=rank, world_size=world)
+  try:
+    from scann_b200 import index_build
+    rng = np.random.default_rng(31)
+    n, d, nq, k = 3001, 24, 37, 10
+    db = rng.standard_normal((n, d), dtype=np.float32)
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    bits = index_build.bfloat16_quantize(db)
+    per = -(-n // world)                                    # the split of scann_b200_index_create
+    r0, r1 = min(rank * per, n), min((rank + 1) * per, n)
+    li, ld = oracle.bruteforce_bf16(np.ascontiguousarray(bits[r0:r1]), q, k, threads=1)
+    li = (li + np.uint32(r0)).astype(np.uint32)             # global ids
+    g = []
+    for arr, dt in ((li.view(np.int32), torch.int32), (ld, torch.float32)):
+      t = torch.from_numpy(np.ascontiguousarray(arr))
+      o = torch.empty((world * nq, k), dtype=dt)
+      dist.all_gather_into_tensor(o, t)
+      g.append(o.numpy().reshape(world, nq, k))
+    mi, md = sd.merge_topk_reference(g[0].view(np.uint32), g[1], k)
+    fi, fd = oracle.bruteforce_bf16(bits, q, k, threads=1)
+    np.savez(os.path.join(out_dir, f"bf{rank}.npz"), idx=mi, dist=md, full_idx=fi, full_dist=fd)
+  finally:
+    dist.destroy_process_group()
+
+
+def test_two_gloo_ranks_row_sharded_bruteforce(tmp_path):
+  world = 2
+  mp.spawn(_bf_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+  for r in range(world):
+    got = np.load(os.path.join(str(tmp_path), f"bf{r}.npz"))
+    np.testing.assert_array_equal(got["idx"], got["full_idx"])
+    np.testing.assert_array_equal(got["dist"].view(np.uint32), got["full_dist"].view(np.uint32))
