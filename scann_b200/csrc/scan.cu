@@ -747,7 +747,7 @@ __device__ __forceinline__ void compact_one(const ScanWork& w, uint32_t q, int d
   if (tid == 0) *s_dups = 0;
   __syncthreads();
   uint32_t nuniq = n;
-  if (!dedup && n > 1024u && n > w.nover) {
+  if (!dedup && n > max(2u * w.nover, 128u)) {
     // Heavy tail: do not sort thousands of keys to keep N of them.  A bound select finds a key T >= the
     // N-th smallest with only a few more than N keys <= T (exact 8-pass radix select if its bin is
     // crowded); those keys are compacted through the query's own buffer row and only they are sorted.
