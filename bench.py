@@ -542,7 +542,8 @@ def run_bruteforce(args, wl, rank, world, local_rank):
          "gpu_launches": int(agg["kernel_launches"]), "clocks": sampler.summary(),
          "roofline": {"bound": "tensor", "kernel": "bf::gemm_pair_kernel<2, filter>", "achieved": flops / gemm_s / 1e12,
                       "peak": peak, "peak_source": "measured burst" if peaks else "fallback", "unit": "TFLOP/s",
-                      "frac": flops / gemm_s / 1e12 / peak, "traffic": None,
+                      "frac": flops / gemm_s / 1e12 / peak, "traffic": ncu_traffic("r01_gemm_pair_traffic.json"),
+                      "traffic_note": "dram bytes of the largest round's launch (497,664 rows: 764 MB compulsory)",
                       "frac_of_sustained_peak": flops / gemm_s / 1e12 / peak_sustained,
                       "note": "flops count both bf16 query terms (hi + lo); time includes the compactions between rounds",
                       "useful_tflops_f32_equivalent": flops / 2 / gemm_s / 1e12},
