@@ -38,6 +38,11 @@ WORKLOADS = {
                            clusters=8000, normalize=True, seed=3, train_sample=250000),
     # C3: brute-force MIPS over a bf16 database (BASELINE.json configs[2])
     "c3_bruteforce_bf16": dict(kind="bruteforce", n=1_000_000, d=768, k=100, nq=10000, seed=5),
+    # C5 shape family (Deep1B-like: 96-d L2-normalised rows, dot product, SOAR, reorder 200) at a database size
+    # one bench run can build in minutes; BASELINE.json's C5 is 100M rows / 40k leaves on 8 GPUs.  ~2,500 rows
+    # per leaf as in C5; --n / --leaves rescale it.
+    "c5_deep_shape": dict(n=20_000_000, d=96, leaves=8000, probe=80, dpb=2, pre=200, k=10, nq=10000,
+                          clusters=133333, normalize=True, seed=9, train_sample=500000, soar=1.5),
     "c1_synthetic": dict(n=100_000, d=100, leaves=100, probe=10, dpb=2, pre=100, k=10, nq=10000,
                          clusters=400, normalize=False, seed=1, train_sample=100000),
 }
@@ -82,7 +87,7 @@ def build_arrays(wl, db, device):
   from scann_b200 import index_build
   return index_build.build_tree_ah(db, "dot_product", num_leaves=wl["leaves"], dims_per_block=wl["dpb"],
                                    training_sample_size=wl["train_sample"], tree_iters=12, ah_iters=10,
-                                   seed=0, device=device)
+                                   soar_lambda=wl.get("soar"), seed=0, device=device)
 
 
 class ClockSampler(threading.Thread):
@@ -149,6 +154,26 @@ def recall_at_k(found, truth):
   return hit / (found.shape[0] * k)
 
 
+def exact_topk(d_q, db, k, dev, rows=1 << 21):
+  """Exact f32 brute-force top-k ids (dot product) on the GPU, database streamed in chunks of `rows`."""
+  import torch
+  nq = d_q.shape[0]
+  best_v = torch.full((nq, k), -float("inf"), device=dev)
+  best_i = torch.zeros((nq, k), dtype=torch.int64, device=dev)
+  for r0 in range(0, db.shape[0], rows):
+    d_db = torch.from_numpy(db[r0:r0 + rows]).to(dev)
+    for s in range(0, nq, 2000):
+      v, i = torch.topk(d_q[s:s + 2000] @ d_db.T, min(k, d_db.shape[0]), dim=1)
+      cv = torch.cat([best_v[s:s + 2000], v], dim=1)
+      ci = torch.cat([best_i[s:s + 2000], i + r0], dim=1)
+      o = torch.topk(cv, k, dim=1).indices
+      best_v[s:s + 2000] = torch.gather(cv, 1, o)
+      best_i[s:s + 2000] = torch.gather(ci, 1, o)
+    del d_db
+  torch.cuda.empty_cache()
+  return best_i.cpu().numpy()
+
+
 def cpu_reference_run(oracle_index, q, sample, threads, steps, warmup):
   """Times the oracle's AVX2 path on a bounded sample; returns QPS."""
   qs = np.ascontiguousarray(q[:sample])
@@ -169,6 +194,8 @@ def main():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--workload", default="c2_glove_shape", choices=list(WORKLOADS))
   ap.add_argument("--leaves", type=int, default=0, help="override leaves_to_search")
+  ap.add_argument("--clusters", type=int, default=0, help="override the number of mixture components of the synthetic data")
+  ap.add_argument("--n", type=int, default=0, help="override the database size (leaves are rescaled to keep rows per leaf)")
   ap.add_argument("--cpu-sample", type=int, default=2000)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
@@ -178,6 +205,12 @@ def main():
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   wl = dict(WORKLOADS[args.workload])
+  if args.n > 0 and "leaves" in wl:
+    wl["leaves"] = max(16, int(round(wl["leaves"] * args.n / wl["n"])))
+    wl["clusters"] = max(64, int(round(wl["clusters"] * args.n / wl["n"])))
+    wl["n"] = args.n
+  if args.clusters > 0:
+    wl["clusters"] = args.clusters
   if args.leaves > 0:
     wl["probe"] = args.leaves
 
@@ -209,14 +242,17 @@ def main():
     from scann_b200 import index_build
     if rank == 0:
       arrays = build_arrays(wl, db, dev)
+      extra = {"soar_codes": arrays.soar_codes} if arrays.soar else {}
       np.savez(shm, centers=arrays.centers, tokens=arrays.tokens, codes=arrays.codes, codebook=arrays.codebook,
-               block_dims=arrays.block_dims)
+               block_dims=arrays.block_dims, **extra)
     dist.barrier()
     if rank != 0:
       z = np.load(shm)
       arrays = index_build.IndexArrays(distance="dot_product", dataset=db, n=db.shape[0], d=db.shape[1])
       arrays.centers, arrays.tokens, arrays.codes = z["centers"], z["tokens"], z["codes"]
       arrays.codebook, arrays.block_dims, arrays.residual = z["codebook"], z["block_dims"], True
+      if "soar_codes" in z.files:
+        arrays.soar_codes, arrays.soar, arrays.overretrieve = z["soar_codes"], True, 2.0
     dist.barrier()
     if rank == 0:
       os.unlink(shm)
@@ -243,13 +279,7 @@ def main():
   torch.cuda.synchronize()
 
   # ground truth for recall (exact f32 brute force on the GPU)
-  d_db = torch.from_numpy(db).to(dev)
-  truth = torch.empty((nq, k), dtype=torch.int64, device=dev)
-  for s in range(0, nq, 1000):
-    truth[s:s + 1000] = torch.topk(d_q[s:s + 1000] @ d_db.T, k, dim=1).indices
-  truth = truth.cpu().numpy()
-  del d_db
-  torch.cuda.empty_cache()
+  truth = exact_topk(d_q, db, k, dev)
 
   def step_dev():
     ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)

@@ -348,13 +348,15 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   const int nlast = (int)ix.B - 8 * (W - 1);
   const int off128 = 128 * (int)ix.B;
   const uint32_t nover = w.nover;
-  uint64_t* grow = w.buf + (size_t)q * w.cap;  // this query's buffer row doubles as compaction scratch
+  uint64_t* grow = w.buf + (size_t)q * w.cap;  // this query's (still empty) buffer row is the compaction scratch
   build_quad_table(tbl, w.lut + (size_t)q * W * 128, nullptr, nullptr, nullptr, W * 128, tid, kScanThreads);
   if (tid == 0) { s_tau = kKeyMax; s_cnt = 0; }
   const float mult = w.mult[q], inv = w.inv_mult[q];
+  // Sample whole leaves, nearest first, until at least 4 N slots have been scored: the N-th best of
+  // that sample is the pruning threshold of the main scan.  Nothing is published -- the main scan
+  // covers every probed leaf, these too (1-2 % more scan work, and no hand-over of candidates).
   uint32_t seen = 0;
-  uint32_t r = 0;
-  for (; r < w.P; ++r) {
+  for (uint32_t r = 0; r < w.P; ++r) {
     const int leaf = w.leaves[(size_t)q * w.P + r];
     if (leaf < 0) break;
     const float bias = ix.key_by_dp ? 0.f : w.bias[(size_t)q * w.P + r];
@@ -391,8 +393,7 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
       const uint32_t c = s_cnt;
       __syncthreads();  // everyone has read s_cnt before the next round may bump it
       if (c > (uint32_t)(capl - kScanThreads)) {
-        // keep the N smallest: radix-select the N-th key, compact through the global row (no sort:
-        // the compaction after the main scan orders everything anyway).  c > capl-128 >= N here.
+        // buffer full: keep the keys up to a bound T of the N-th smallest (compacted through the global row)
         uint32_t n_le = 0;
         uint64_t T = block_select_bound(scand, c, nover, &s_sel, &n_le);
         if (n_le > (uint32_t)capl / 2) T = block_radix_select(scand, c, nover, &s_sel);  // crowded bin: exact select
@@ -413,32 +414,24 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
       }
     }
     seen += n;
-    if (seen >= nover) { ++r; break; }
+    if (seen >= 4 * nover) break;
   }
   __syncthreads();
-  // publish: every buffered candidate (unsorted, at most capl) and the N-th smallest key as tau
+  // tau: an upper bound of the N-th smallest sampled key, plus one so that the bounding element itself
+  // passes the main scan's strict `key < tau` test.
   const uint32_t c = s_cnt;
   uint64_t tau = kKeyMax;
   if (c >= nover) {
     uint32_t n_le = 0;
     tau = block_select_bound(scand, c, nover, &s_sel, &n_le);
-    if (n_le > w.cap || n_le > 2 * nover + 64) tau = block_radix_select(scand, c, nover, &s_sel);  // crowded bin
+    if (n_le > 2 * nover + 64) tau = block_radix_select(scand, c, nover, &s_sel);  // crowded bin: exact N-th key
+    if (tau != kKeyMax) tau += 1;
   }
-  // only keys <= tau can still matter; the rest of the pilot's buffer is dropped here
-  if (tid == 0) s_cnt = 0;
-  __syncthreads();
-  for (uint32_t i = tid; i < c; i += kScanThreads) {
-    const uint64_t k = scand[i];
-    if (k <= tau) {
-      const uint32_t pos = atomicAdd(&s_cnt, 1u);
-      if (pos < w.cap) grow[pos] = k;
-    }
-  }
-  __syncthreads();
+  const uint32_t r = 0;  // the main scan starts at rank 0
   if (tid == 0) {
-    w.cnt[q] = min(s_cnt, w.cap);
+    w.cnt[q] = 0;
     w.tau[q] = tau;
-    w.pilot_end[q] = (int32_t)r;
+    w.pilot_end[q] = 0;
     w.ovf[q] = 0;
   }
   // Work-list counts of the leaves left to the main scan, and the traffic statistics of all probed
@@ -863,8 +856,8 @@ leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, 
   }
 
 static int pilot_capl(uint32_t nover) {
-  int capl = 1024;  // a whole typical leaf is buffered before the first (and usually only) selection
-  while ((uint32_t)capl < nover + kScanThreads) capl <<= 1;
+  int capl = 1024;  // keys buffered between selections; a typical leaf fits
+  while ((uint32_t)capl < 2 * nover + kScanThreads) capl <<= 1;
   return capl;
 }
 size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover) {
