@@ -42,7 +42,7 @@ WORKLOADS = {
     # one bench run can build in minutes; BASELINE.json's C5 is 100M rows / 40k leaves on 8 GPUs.  ~2,500 rows
     # per leaf as in C5; --n / --leaves rescale it.
     "c5_deep_shape": dict(n=20_000_000, d=96, leaves=8000, probe=80, dpb=2, pre=200, k=10, nq=10000,
-                          clusters=133333, normalize=True, seed=9, train_sample=500000, soar=1.5),
+                          clusters=80000, normalize=True, seed=9, train_sample=500000, soar=1.5),
     "c1_synthetic": dict(n=100_000, d=100, leaves=100, probe=10, dpb=2, pre=100, k=10, nq=10000,
                          clusters=400, normalize=False, seed=1, train_sample=100000),
 }

@@ -6,26 +6,28 @@
 //   FastTopNeighbors<float>                            utils/fast_top_neighbors.h:43-299
 //
 // B200 formulation.  The CPU kernel looks one query's 16-entry uint8 table up with vpshufb
-// for 32 datapoints at a time.  Here the unit of work is a QUAD of four queries that probe
-// the same leaf: their four uint8 tables are interleaved in shared memory into one table of
-// 32-bit entries  T[b][c] = lut0 | lut1 << 8 | lut2 << 16 | lut3 << 24,  so ONE conflict-free
-// LDS.32 (16 distinct entries = 16 distinct banks, equal entries broadcast: a single wavefront
-// per warp) serves four (query, datapoint, block) lookups; a mask and a byte permute split the
-// word into (q0, q2) and (q1, q3) u16 lanes and two 32-bit adds accumulate four u16 sums
-// (B <= 256 => sum <= 65280, no carry between the halves).  Each thread owns one datapoint
-// of a 32-slot group: its B nibbles live in W = ceil(B/8) registers, loaded once per work
-// item with coalesced 128-bit loads and reused for every quad of the item.
+// for 32 datapoints at a time.  Here the unit of work of the main scan is an OCT of eight queries
+// that probe the same leaf: their eight uint8 tables are interleaved in shared memory into one
+// table of 64-bit entries  T[b][c] = {lut0 | lut1 << 8 | lut2 << 16 | lut3 << 24, lut4 | ... | lut7 << 24},
+// so ONE conflict-free LDS.64 (16 distinct entries = 16 distinct bank pairs, equal entries
+// broadcast) serves eight (query, datapoint, block) lookups; masks and byte permutes split the
+// two words into four registers of two u16 lanes and four IMADs accumulate them (B <= 256 =>
+// sum <= 65280, no carry between the halves).  Each thread owns one datapoint of a 32-slot
+// group: its B nibbles live in W = ceil(B/8) registers, loaded once per work item with coalesced
+// 128-bit loads and reused for every oct of the item.  (The pilot and the debug hook score one
+// query at a time through the 32-bit "quad" table of score_quad.)
 //
 // Top-N.  Every query owns a candidate buffer buf[q][cap] in HBM, a count and a threshold
-// key tau[q] (score, global slot).  A PILOT kernel (one CTA per query) scans the nearest
-// leaves until it has seen >= N candidates, keeps the exact N best in shared memory and
-// publishes tau.  The MAIN kernel scans every remaining (query, leaf) pair, grouped by leaf
-// into quads, with an integer pre-filter (sum <= thr, conservative) and an exact 64-bit key
-// comparison; survivors are appended with one warp-aggregated atomic.  COMPACT sorts each
-// buffer and keeps the N smallest keys.  The result is the exact top-N under
-// (float score, leaf, slot) -- the contract of SURVEY.md section 7 hard-part 1 -- regardless of
-// scheduling.  If a buffer overflowed, the host re-scans only the affected queries with the
-// tightened tau (duplicates are removed by key), so no candidate can be lost.
+// key tau[q] (score, global slot).  A PILOT kernel (one CTA per query) scores whole leaves,
+// nearest first, until it has seen >= 4 N slots and sets tau to (a bound of) the N-th best key
+// of that sample + 1; it publishes no candidates.  The MAIN kernel scans every probed (query, leaf)
+// pair, grouped by leaf into octs, with an integer pre-filter (sum <= thr, conservative) and an
+// exact 64-bit key comparison (key < tau); survivors are appended with one warp-aggregated atomic.
+// COMPACT keeps the N smallest keys of each buffer (sort, or bound select + sort for long buffers).
+// The result is the exact top-N under (float score, leaf, slot) -- the contract of SURVEY.md
+// section 7 hard-part 1 -- regardless of scheduling and of how tight tau was.  If a buffer
+// overflowed, the host re-scans only the affected queries with the tightened tau (duplicates are
+// removed by key), so no candidate can be lost.
 #include "common.cuh"
 #include "exact_math.cuh"
 #include "kernels.h"
