@@ -576,11 +576,14 @@ struct ItemMeta {
   uint32_t q[kMaxQPI];
   int thr[kMaxQPI];
   float inv[kMaxQPI], bias[kMaxQPI];
+  // thresholds of an oct packed like its accumulators, (t0,t2) (t1,t3) (t4,t6) (t5,t7) as u16 halves, each
+  // biased by 32768: bit 15 of a half of (thrp - acc) is set iff sum <= thr (sums < 2^15 because B <= 128)
+  uint4 thrp[kMaxQPI / 8];
 };
 
 // Rare path of the main scan: exact key test and warp-aggregated append for one oct.  All 32 lanes call.
 __device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork& w, const ItemMeta* meta, uint32_t qd,
-                                             uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t pm,
+                                             uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, bool valid,
                                              uint32_t gslot, int off128) {
   const int lane = threadIdx.x & 31;
   const int sv[8] = {(int)(a0 & 0xFFFFu), (int)(a1 & 0xFFFFu), (int)(a0 >> 16), (int)(a1 >> 16),
@@ -588,7 +591,7 @@ __device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork&
 #pragma unroll 1
   for (int i = 0; i < 8; ++i) {
     const int qi = qd * 8 + i;
-    bool p = (pm >> i) & 1u;
+    bool p = valid && sv[i] <= meta->thr[qi];
     if (!__any_sync(kFull, p)) continue;
     uint64_t key = 0;
     if (p) {
@@ -674,6 +677,10 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       s_thr[tid] = thr;
     }
     __syncthreads();
+    if (tid < (int)(qpi / 8)) {
+      auto bt = [&](int i) -> uint32_t { return (uint32_t)(min(max(s_thr[tid * 8 + i], -1), 32767) + 32768); };
+      meta.thrp[tid] = make_uint4(bt(0) | (bt(2) << 16), bt(1) | (bt(3) << 16), bt(4) | (bt(6) << 16), bt(5) | (bt(7) << 16));
+    }
     for (uint32_t qd = 0; qd < nquads; ++qd) {
       const uint8_t* lp[8];
 #pragma unroll
@@ -702,12 +709,10 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       // fast path inline (8 compares per oct), candidate push out of line: the scoring loops of the
       // octs are unrolled copies and must stay inside the instruction cache
       auto filter = [&](const uint32_t qd, const uint32_t (&acc)[4]) {
-        const int sv[8] = {(int)(acc[0] & 0xFFFFu), (int)(acc[1] & 0xFFFFu), (int)(acc[0] >> 16), (int)(acc[1] >> 16),
-                           (int)(acc[2] & 0xFFFFu), (int)(acc[3] & 0xFFFFu), (int)(acc[2] >> 16), (int)(acc[3] >> 16)};
-        uint32_t pm = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) pm |= (valid && sv[i] <= s_thr[qd * 8 + i]) ? (1u << i) : 0u;
-        if (__any_sync(kFull, pm != 0)) push_candidates(ix, w, &meta, qd, acc[0], acc[1], acc[2], acc[3], pm, gslot, off128);
+        const uint4 t = meta.thrp[qd];
+        const uint32_t hit = ((t.x - acc[0]) | (t.y - acc[1]) | (t.z - acc[2]) | (t.w - acc[3])) & 0x80008000u;
+        if (__any_sync(kFull, valid && hit != 0))
+          push_candidates(ix, w, &meta, qd, acc[0], acc[1], acc[2], acc[3], valid, gslot, off128);
       };
 #define SB_DO_QUAD(QD)                                       \
   if (QD < nquads) {                                         \
