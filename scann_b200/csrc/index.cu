@@ -80,7 +80,8 @@ size_t word_pos(int W, int j, int m) {
   return (size_t)N4 * 128 + (R >= 2 ? 64 : 0) + m;
 }
 
-enum { EV_START, EV_TOK, EV_LUT, EV_PILOT, EV_WORK, EV_SCAN, EV_COMPACT, EV_FIN, EV_COUNT };
+enum { EV_START, EV_TOK, EV_LUT, EV_PILOT, EV_WORK, EV_SCAN, EV_COMPACT, EV_FIN, EV_COUNT,
+       EV2_WORK = EV_COUNT, EV2_SCAN, EV2_COMPACT, EV_ALL };
 
 }  // namespace
 
@@ -103,13 +104,14 @@ struct scann_b200_index {
   DevBuf tok_a, q, dist, leaves, bias, lut, mult, inv, pilot_end, buf, cnt, tau, ovf, leaf_cnt, leaf_eoff,
       leaf_cur, item_off, entry_q, entry_bias, counters, stats, out_idx, out_dist;
   PinnedBuf h_q, h_idx, h_dist, h_counters;
-  cudaEvent_t ev[EV_COUNT] = {};
+  cudaEvent_t ev[EV_ALL] = {};
   scann_b200_stats last{};
   uint32_t max_chunk = 16384;
   // brute-force (bf16) searcher: database rows as bf16 with a 16-byte aligned pitch
   bool brute = false;
   uint32_t bf_dpitch = 0;
   uint32_t bf_row0 = 0;  // first database row of this shard (row-sharded brute force)
+  uint32_t avg_leaf_slots = 0;  // mean padded slots per leaf (scan phase heuristic)
   DevBuf bf_db, bf_a;
 };
 
@@ -179,6 +181,7 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     }
   }
   const size_t ngroups = goff[L];
+  ix->avg_leaf_slots = (uint32_t)(ngroups * 32 / std::max<uint32_t>(L, 1));
   if (ngroups * 32 > 0xFFFFFFF0ull) return fail(SCANN_B200_UNIMPLEMENTED, "more than 2^32 slots");
   std::vector<uint32_t> slot_dp(ngroups * 32, 0xFFFFFFFFu);
   std::vector<uint32_t> slot_tie(world > 1 ? ngroups * 32 : 0, 0xFFFFFFFFu);
@@ -413,10 +416,18 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   launches += 1;
   CU(cudaGetLastError());
   CU(cudaEventRecord(ix->ev[EV_LUT], s));
+  // Two scan phases when many slots are probed per query (C5-size leaves): the nearest eighth of the
+  // leaves first, a compaction that tightens tau from "N-th best of the pilot's sample" to "N-th best of
+  // those leaves", then the rest.  The pushes of the second phase shrink several-fold (100M x 96, P = 80:
+  // 10.3k -> candidates per query); for C2-size work the extra launches cost more than they save.
+  bool two_phase = p.P >= 16 && (uint64_t)p.P * ix->avg_leaf_slots >= 131072;
+  if (const char* e = getenv("SCANN_B200_TWO_PHASE")) two_phase = e[0] == '1' && p.P >= 2;
+  const uint32_t r1 = two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
+  w.rank_lo = 0; w.rank_hi = r1;
   CU(sb::launch_pilot(v, w, s));
   launches += 1;
   CU(cudaEventRecord(ix->ev[EV_PILOT], s));
-  sb::launch_worklist(v, w, false, s, &launches);
+  sb::launch_worklist(v, w, false, true, s, &launches);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ix->ev[EV_WORK], s));
   CU(sb::launch_scan(v, w, 0, s));
@@ -425,6 +436,19 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(sb::launch_compact(v, w, false, s));
   launches += cap > 1024 ? 2 : 1;
   CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
+  if (two_phase) {
+    w.rank_lo = r1; w.rank_hi = p.P;
+    sb::launch_worklist(v, w, false, false, s, &launches);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ix->ev[EV2_WORK], s));
+    CU(sb::launch_scan(v, w, 0, s));
+    launches += 1; scan_launches += 1;
+    CU(cudaEventRecord(ix->ev[EV2_SCAN], s));
+    CU(sb::launch_compact(v, w, false, s));
+    launches += cap > 1024 ? 2 : 1;
+    CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
+  }
+  w.rank_lo = 0; w.rank_hi = p.P;  // re-scans of overflowed queries cover every probed leaf
   // overflow check: one 32-byte read back per chunk
   uint32_t* hc = ix->h_counters.as<uint32_t>();
   CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
@@ -433,7 +457,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   while (hc[2] != 0) {
     if (++retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
     CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
-    sb::launch_worklist(v, w, true, s, &launches);
+    sb::launch_worklist(v, w, true, false, s, &launches);
     CU(sb::launch_scan(v, w, 0, s));
     CU(sb::launch_compact(v, w, true, s));
     launches += cap > 1024 ? 3 : 2; scan_launches += 1;
@@ -453,7 +477,16 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaMemcpyAsync(hs, w.stats, sizeof hs, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   float ms[EV_COUNT] = {0};
-  for (int i = 1; i < EV_COUNT; ++i) CU(cudaEventElapsedTime(&ms[i], ix->ev[i - 1], ix->ev[i]));
+  for (int i = 1; i < EV_COUNT; ++i) {
+    const int prev = (i == EV_FIN && two_phase) ? EV2_COMPACT : i - 1;
+    CU(cudaEventElapsedTime(&ms[i], ix->ev[prev], ix->ev[i]));
+  }
+  if (two_phase) {
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, ix->ev[EV_COMPACT], ix->ev[EV2_WORK])); ms[EV_WORK] += t;
+    CU(cudaEventElapsedTime(&t, ix->ev[EV2_WORK], ix->ev[EV2_SCAN])); ms[EV_SCAN] += t;
+    CU(cudaEventElapsedTime(&t, ix->ev[EV2_SCAN], ix->ev[EV2_COMPACT])); ms[EV_COMPACT] += t;
+  }
   scann_b200_stats& st = ix->last;
   st.scan_bytes_alg += hs[0];
   st.scan_pairs += hs[1];
@@ -584,7 +617,7 @@ int scann_b200_index_create(const scann_b200_index_desc* desc, scann_b200_index*
   if (rc == 0) {
     cudaError_t se = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
     if (se != cudaSuccess) rc = fail(SCANN_B200_INTERNAL, "cudaStreamCreate: %s", cudaGetErrorString(se));
-    for (int i = 0; i < EV_COUNT && rc == 0; ++i)
+    for (int i = 0; i < EV_ALL && rc == 0; ++i)
       if (cudaEventCreate(&ix->ev[i]) != cudaSuccess) rc = fail(SCANN_B200_INTERNAL, "cudaEventCreate failed");
   }
   if (rc) { delete ix; return rc; }
@@ -599,7 +632,7 @@ void scann_b200_index_destroy(scann_b200_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
   if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
-  for (int i = 0; i < EV_COUNT; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+  for (int i = 0; i < EV_ALL; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
   delete ix;
 }
 

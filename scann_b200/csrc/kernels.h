@@ -46,7 +46,7 @@ struct ScanWork {
   const uint8_t* lut;         // [nq][W*8*16]
   const float* mult;          // [nq]
   const float* inv_mult;      // [nq]
-  int32_t* pilot_end;         // [nq] first rank the pilot did not scan
+  int32_t* pilot_end;         // [nq] unused (the pilot publishes nothing; kept for layout stability)
   uint64_t* buf;              // [nq][cap] candidate keys
   uint32_t* cnt;              // [nq]
   uint64_t* tau;              // [nq] push only keys < tau
@@ -60,6 +60,7 @@ struct ScanWork {
   uint32_t* counters;         // [8]: 0 item counter, 1 n_items, 2 n_ovf, 3 n_entries
   unsigned long long* stats;  // [4]: 0 bytes_alg, 1 pairs, 2 lookups
   uint32_t nq, P, cap, nover, quads_per_item;
+  uint32_t rank_lo, rank_hi;  // ranks [rank_lo, rank_hi) of every query's leaf list go into the next work list
   uint32_t one;               // always 1; a runtime value so the scan's IMAD accumulates stay IMADs
 };
 
@@ -81,7 +82,8 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
 size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover);
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item);
 cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s);
-void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, cudaStream_t s, int* launches);
+// counted = the per-leaf counts of ranks [rank_lo, rank_hi) are already in leaf_cnt (the pilot kernel does that)
+void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, bool counted, cudaStream_t s, int* launches);
 cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s);
 cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s);
 // ---- finalize ----

@@ -369,22 +369,22 @@ constexpr int kRefineMaxCand = 512;
 // map (2 ulp of a value < 2^31), so this is a superset of {a <= a_P + 2 eps}.
 // kSmemRow: u is staged in shared memory once (L <= kRefineSmemL, L % 4 == 0), so the passes touch
 // no global memory; otherwise any L, u recomputed from the row on every pass.
-constexpr int kRefineSmemL = 4096;
-constexpr int kRefineThreads = 128;
+constexpr int kRefineSmemL = 49152;  // 192 KB of shared memory for the row image
 
-template <bool kSmemRow>
+template <bool kSmemRow, int kRefineThreads>
 __global__ void __launch_bounds__(kRefineThreads)
 topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ S, int nq, int P, int Ppow2, int Cp,
                    float eps_rel, int32_t* __restrict__ leaves, float* __restrict__ bias, uint32_t* fallbacks) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ uint32_t hist[256];
-  __shared__ float red_a[4], red_b[4];
+  constexpr int kWarps = kRefineThreads / 32;
+  __shared__ float red_a[kWarps], red_b[kWarps];
   __shared__ uint32_t s_sel[4];  // digit, cum, bucket, candidate counter
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int qi = blockIdx.x;
   const int L = (int)ix.L, D = (int)ix.d, Dp = (D + 3) & ~3;
   const bool sql2 = ix.distance == 1;
-  const int Lp = (L + 511) & ~511;  // whole LDS.128 iterations of the block
+  const int Lp = (L + 4 * kRefineThreads - 1) / (4 * kRefineThreads) * (4 * kRefineThreads);  // whole LDS.128 iterations of the block
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
   float* sq = reinterpret_cast<float*>(smem_raw + (size_t)Cp * 8);
   uint32_t* srow = reinterpret_cast<uint32_t*>(smem_raw + (size_t)Cp * 8 + (size_t)Dp * 4);
@@ -400,7 +400,9 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, o);
   if (lane == 0) red_a[warp] = ssq;
   __syncthreads();
-  ssq = red_a[0] + red_a[1] + red_a[2] + red_a[3];
+  ssq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kWarps; ++i) ssq += red_a[i];
   float qn = 0.f;
   if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
     if (tid == 0) {
@@ -452,8 +454,10 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   }
   if (lane == 0) { red_a[warp] = amin; red_b[warp] = amax; }
   __syncthreads();
-  amin = fminf(fminf(red_a[0], red_a[1]), fminf(red_a[2], red_a[3]));
-  amax = fmaxf(fmaxf(red_b[0], red_b[1]), fmaxf(red_b[2], red_b[3]));
+  amin = red_a[0];
+  amax = red_b[0];
+#pragma unroll
+  for (int i = 1; i < kWarps; ++i) { amin = fminf(amin, red_a[i]); amax = fmaxf(amax, red_b[i]); }
   const float span = __fsub_rn(amax, amin);
   const float scale = (span > 0.f && span < __int_as_float(0x7F800000)) ? __fdiv_rn(2145386496.f, span) : 0.f;
   auto ufn = [&](float a) -> uint32_t {
@@ -478,8 +482,7 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   if (P < L) {
     uint32_t mask = 0, prefix = 0, need = (uint32_t)P, below = 0;
     for (int shift = 23;; ) {
-      hist[tid] = 0;
-      hist[tid + kRefineThreads] = 0;
+      for (int i = tid; i < 256; i += kRefineThreads) hist[i] = 0;
       __syncthreads();
       if (kSmemRow && shift == 23) {
         // first pass: convert the staged distances to u in place (each thread revisits its own slots)
@@ -684,15 +687,20 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   const float eps_rel = (float)ix.tok_kp * 4.76837158e-7f + 3.05175781e-5f;  // K * 2^-21 + 2^-15
   if (cp < 128) cp = 128;  // the in-register sort writes 128 keys back
   const size_t smem = (size_t)cp * 8 + (size_t)((ix.d + 3) & ~3u) * 4;
-#define SB_REFINE(kS, bytes)                                                                                    \
-  do {                                                                                                          \
-    e = cudaFuncSetAttribute(topp_refine_kernel<kS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
-    if (e != cudaSuccess) return e;                                                                             \
-    topp_refine_kernel<kS><<<nq, kRefineThreads, (bytes), s>>>(ix, q, dist, (int)nq, (int)P, pp, cp, eps_rel,   \
-                                                               leaves, bias, fallbacks);                        \
+#define SB_REFINE(kS, kT, bytes)                                                                                  \
+  do {                                                                                                            \
+    e = cudaFuncSetAttribute(topp_refine_kernel<kS, kT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+    if (e != cudaSuccess) return e;                                                                               \
+    topp_refine_kernel<kS, kT><<<nq, kT, (bytes), s>>>(ix, q, dist, (int)nq, (int)P, pp, cp, eps_rel, leaves, bias, \
+                                                       fallbacks);                                                \
   } while (0)
-  if (ix.L <= (uint32_t)kRefineSmemL && (ix.L & 3u) == 0) SB_REFINE(true, smem + (size_t)((ix.L + 511) & ~511u) * 4);
-  else SB_REFINE(false, smem);
+  // more threads per query for longer rows (the row image stays in shared memory up to L = 49152)
+  auto rowbytes = [&](uint32_t threads) { return (size_t)((ix.L + 4 * threads - 1) / (4 * threads) * (4 * threads)) * 4; };
+  const bool smem_row = ix.L <= (uint32_t)kRefineSmemL && (ix.L & 3u) == 0;
+  if (smem_row && ix.L <= 4096) SB_REFINE(true, 128, smem + rowbytes(128));
+  else if (smem_row && ix.L <= 16384) SB_REFINE(true, 256, smem + rowbytes(256));
+  else if (smem_row) SB_REFINE(true, 512, smem + rowbytes(512));
+  else SB_REFINE(false, 256, smem);
 #undef SB_REFINE
   if (launches) *launches += 3;
   return cudaGetLastError();

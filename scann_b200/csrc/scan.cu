@@ -429,7 +429,6 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
     if (n_le > 2 * nover + 64) tau = block_radix_select(scand, c, nover, &s_sel);  // crowded bin: exact N-th key
     if (tau != kKeyMax) tau += 1;
   }
-  const uint32_t r = 0;  // the main scan starts at rank 0
   if (tid == 0) {
     w.cnt[q] = 0;
     w.tau[q] = tau;
@@ -444,7 +443,7 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
     if (leaf >= 0) {
       bytes += (unsigned long long)(ix.leaf_goff[leaf + 1] - ix.leaf_goff[leaf]) * 16ull * ix.B;
       pairs += 1;
-      if (rr >= r) atomicAdd(&w.leaf_cnt[leaf], 1u);
+      if (rr >= w.rank_lo && rr < w.rank_hi) atomicAdd(&w.leaf_cnt[leaf], 1u);
     }
   }
 #pragma unroll
@@ -475,7 +474,7 @@ __global__ void worklist_count_kernel(DevIndex ix, ScanWork w, int only_ovf, int
         bytes = (unsigned long long)ng * 16ull * ix.B;
         pairs = 1;
       }
-      if ((int)r >= w.pilot_end[q] && (!only_ovf || w.ovf[q])) atomicAdd(&w.leaf_cnt[leaf], 1u);
+      if (r >= w.rank_lo && r < w.rank_hi && (!only_ovf || w.ovf[q])) atomicAdd(&w.leaf_cnt[leaf], 1u);
     }
   }
   if (count_stats) {
@@ -546,21 +545,21 @@ __global__ void worklist_scatter_kernel(DevIndex ix, ScanWork w, int only_ovf) {
   const uint32_t q = (uint32_t)(i / w.P), r = (uint32_t)(i % w.P);
   const int leaf = w.leaves[i];
   if (leaf < 0) return;
-  if ((int)r < w.pilot_end[q] || (only_ovf && !w.ovf[q])) return;
+  if (r < w.rank_lo || r >= w.rank_hi || (only_ovf && !w.ovf[q])) return;
   const uint32_t pos = w.leaf_eoff[leaf] + atomicAdd(&w.leaf_cur[leaf], 1u);
   w.entry_q[pos] = q;
   w.entry_bias[pos] = w.bias[i];
 }
 
-// The first work list of a batch is counted by the pilot kernel (launch_pilot zeroes leaf_cnt); the
-// re-scan lists of overflowed queries are counted here.
-void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, cudaStream_t s,
+// The first work list of a batch is counted by the pilot kernel (launch_pilot zeroes leaf_cnt); later
+// ones (second scan phase, re-scans of overflowed queries) are counted here.
+void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, bool counted, cudaStream_t s,
                      int* launches) {
   const size_t total = (size_t)w.nq * w.P;
   const int blocks = (int)((total + 255) / 256);
-  if (only_overflowed) {
+  if (!counted) {
     cudaMemsetAsync(w.leaf_cnt, 0, sizeof(uint32_t) * (ix.L + 1), s);
-    worklist_count_kernel<<<blocks, 256, 0, s>>>(ix, w, 1, 0);
+    worklist_count_kernel<<<blocks, 256, 0, s>>>(ix, w, only_overflowed ? 1 : 0, 0);
     if (launches) *launches += 1;
   }
   worklist_scan_kernel<<<1, 1024, 0, s>>>(ix, w);
@@ -790,7 +789,8 @@ __device__ __forceinline__ void compact_one(const ScanWork& w, uint32_t q, int d
   if (tid == 0) {
     w.cnt[q] = keep;
     w.tau[q] = (keep >= w.nover) ? s[w.nover - 1] : kKeyMax;
-    w.ovf[q] = over ? 1u : 0u;
+    // sticky across the scan phases of a batch; the re-scan (dedup) passes clear it
+    if (over || dedup) w.ovf[q] = over ? 1u : 0u;
     if (over) atomicAdd(&w.counters[2], 1u);
   }
 }

@@ -162,3 +162,24 @@ def test_tokenize_degenerate_queries_fall_back_to_exact(kw, monkeypatch):
   l1, d1 = c.native.tokenize(q)
   np.testing.assert_array_equal(l0, l1)
   np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
+# ---- two scan phases (nearest leaves first, tau tightened in between) must not change anything ----
+@pytest.mark.parametrize("kw", [CASES[0], CASES[5], CASES[6], CASES[7], CASES[8]], ids=["dot", "soar", "tiny", "allprobed", "l2"])
+@pytest.mark.parametrize("cap", [None, "256"])
+def test_two_phase_scan_is_bit_exact(kw, cap, monkeypatch):
+  monkeypatch.setenv("SCANN_B200_TWO_PHASE", "1")
+  if cap:
+    monkeypatch.setenv("SCANN_B200_CAND_CAP", cap)   # overflow in either phase -> re-scan with dedup
+  c = get_case(**kw)
+  a = c.oracle.candidates(c.q)
+  b = c.native.candidates(c.q)
+  np.testing.assert_array_equal(a["count"], b["count"])
+  for i in range(len(c.q)):
+    n = a["count"][i]
+    np.testing.assert_array_equal(a["dp"][i, :n], b["dp"][i, :n])
+    np.testing.assert_array_equal(a["score"][i, :n].view(np.uint32), b["score"][i, :n].view(np.uint32))
+  i0, d0 = c.oracle.search_batched(c.q)
+  i1, d1 = c.native.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
