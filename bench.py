@@ -285,8 +285,16 @@ def main():
     ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)
     return ix.stats()
 
+  # end-to-end leg: the caller's query and result arrays are page-locked host memory (numpy views of
+  # pinned torch tensors), as a serving front end would hold them
+  q_pin_t = torch.from_numpy(q).pin_memory()
+  q_pin = q_pin_t.numpy()
+  oi_t = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+  od_t = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+  out_pin = (oi_t.numpy().view(np.uint32), od_t.numpy())
+
   def step_host():
-    return ix.search_batched(q)
+    return ix.search_batched(q_pin, out=out_pin)
 
   for _ in range(args.warmup):
     step_dev()

@@ -178,11 +178,18 @@ class NativeIndex:
   __del__ = close
 
   # ---- hot path ----
-  def search_batched(self, q, final_nn=-1, pre_nn=-1, leaves=-1):
+  def search_batched(self, q, final_nn=-1, pre_nn=-1, leaves=-1, out=None):
+    """Host buffers in / out.  `out` = (uint32 [nq, k], float32 [nq, k]) reuses caller arrays; page-locked
+    arrays (queries and/or outputs) are copied to / from the device without the staging copy."""
     q = np.ascontiguousarray(q, dtype=np.float32)
     k = final_nn if final_nn > 0 else self.default_final_nn
-    idx = np.empty((q.shape[0], k), dtype=np.uint32)
-    dist = np.empty((q.shape[0], k), dtype=np.float32)
+    if out is not None:
+      idx, dist = out
+      assert idx.dtype == np.uint32 and dist.dtype == np.float32 and idx.shape == dist.shape == (q.shape[0], k)
+      assert idx.flags.c_contiguous and dist.flags.c_contiguous
+    else:
+      idx = np.empty((q.shape[0], k), dtype=np.uint32)
+      dist = np.empty((q.shape[0], k), dtype=np.float32)
     check(lib().scann_b200_search_batched(self._h, ptr(q), q.shape[0], final_nn, pre_nn, leaves,
                                           ptr(idx), ptr(dist), k))
     return idx, dist

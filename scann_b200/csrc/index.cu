@@ -449,33 +449,42 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
     CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
   }
   w.rank_lo = 0; w.rank_hi = p.P;  // re-scans of overflowed queries cover every probed leaf
-  // overflow check: one 32-byte read back per chunk
-  uint32_t* hc = ix->h_counters.as<uint32_t>();
-  CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  const uint32_t tok_fallbacks = hc[5];
-  while (hc[2] != 0) {
-    if (++retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
-    CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
-    sb::launch_worklist(v, w, true, false, s, &launches);
-    CU(sb::launch_scan(v, w, 0, s));
-    CU(sb::launch_compact(v, w, true, s));
-    launches += cap > 1024 ? 3 : 2; scan_launches += 1;
-    CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-  }
-  if (!stop_after_candidates) {
+  // Overflow flag, statistics and the finalize kernel share ONE host round trip: finalize is launched
+  // optimistically; if some buffer overflowed (rare) its output is discarded, the flagged queries are
+  // re-scanned and finalize runs again.
+  uint32_t* hc = ix->h_counters.as<uint32_t>();                        // pinned: [0..7] counters, then 4 x u64 stats
+  unsigned long long* hs = reinterpret_cast<unsigned long long*>(hc + 8);
+  auto finalize = [&]() -> int {
+    if (stop_after_candidates) return 0;
     sb::FinalizeArgs a{};
     a.q = d_q; a.nq = nq; a.npre = p.npre; a.k = p.k; a.out_k = out_k;
     a.out_idx = d_out_idx; a.out_dist = d_out_dist;
     if (part) { a.part_ids = part->ids; a.part_tie = part->tie; a.part_ah = part->ah; a.part_exact = part->exact; a.part_cap = part->cap; }
     CU(sb::launch_finalize(v, w, a, s));
     launches += 1;
-  }
+    return 0;
+  };
+  if (int rc = finalize()) return rc;
   CU(cudaEventRecord(ix->ev[EV_FIN], s));
-  unsigned long long hs[4];
-  CU(cudaMemcpyAsync(hs, w.stats, sizeof hs, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(hs, w.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  const uint32_t tok_fallbacks = hc[5];
+  if (hc[2] != 0) {
+    while (hc[2] != 0) {
+      if (++retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
+      CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
+      sb::launch_worklist(v, w, true, false, s, &launches);
+      CU(sb::launch_scan(v, w, 0, s));
+      CU(sb::launch_compact(v, w, true, s));
+      launches += cap > 1024 ? 3 : 2; scan_launches += 1;
+      CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+    }
+    if (int rc = finalize()) return rc;
+    CU(cudaEventRecord(ix->ev[EV_FIN], s));
+    CU(cudaStreamSynchronize(s));
+  }
   float ms[EV_COUNT] = {0};
   for (int i = 1; i < EV_COUNT; ++i) {
     const int prev = (i == EV_FIN && two_phase) ? EV2_COMPACT : i - 1;
@@ -670,6 +679,12 @@ int scann_b200_search_batched(scann_b200_index* ix, const float* queries, uint32
   CU(cudaSetDevice(ix->device));
   ix->last = scann_b200_stats{};
   const uint32_t D = ix->dev.d;
+  auto pinned = [](const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool q_pinned = pinned(queries), out_pinned = pinned(out_idx) && pinned(out_dist);
   for (uint32_t s0 = 0; s0 < nq; s0 += ix->max_chunk) {
     const uint32_t c = std::min(ix->max_chunk, nq - s0);
     CU(ix->q.ensure(sizeof(float) * (size_t)c * D));
@@ -678,16 +693,25 @@ int scann_b200_search_batched(scann_b200_index* ix, const float* queries, uint32
     CU(ix->h_q.ensure(sizeof(float) * (size_t)c * D));
     CU(ix->h_idx.ensure(sizeof(uint32_t) * (size_t)c * out_k));
     CU(ix->h_dist.ensure(sizeof(float) * (size_t)c * out_k));
-    memcpy(ix->h_q.p, queries + (size_t)s0 * D, sizeof(float) * (size_t)c * D);
-    CU(cudaMemcpyAsync(ix->q.p, ix->h_q.p, sizeof(float) * (size_t)c * D, cudaMemcpyHostToDevice, ix->stream));
+    // page-locked caller memory goes to the device directly; pageable memory through the pinned staging buffer
+    const float* src = queries + (size_t)s0 * D;
+    if (!q_pinned) {
+      memcpy(ix->h_q.p, src, sizeof(float) * (size_t)c * D);
+      src = ix->h_q.as<float>();
+    }
+    CU(cudaMemcpyAsync(ix->q.p, src, sizeof(float) * (size_t)c * D, cudaMemcpyHostToDevice, ix->stream));
     if (int rc = run_chunk(ix, ix->q.as<float>(), c, p, ix->out_idx.as<uint32_t>(), ix->out_dist.as<float>(),
                            (uint32_t)out_k))
       return rc;
-    CU(cudaMemcpyAsync(ix->h_idx.p, ix->out_idx.p, sizeof(uint32_t) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
-    CU(cudaMemcpyAsync(ix->h_dist.p, ix->out_dist.p, sizeof(float) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
+    uint32_t* dst_i = out_pinned ? out_idx + (size_t)s0 * out_k : ix->h_idx.as<uint32_t>();
+    float* dst_d = out_pinned ? out_dist + (size_t)s0 * out_k : ix->h_dist.as<float>();
+    CU(cudaMemcpyAsync(dst_i, ix->out_idx.p, sizeof(uint32_t) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
+    CU(cudaMemcpyAsync(dst_d, ix->out_dist.p, sizeof(float) * (size_t)c * out_k, cudaMemcpyDeviceToHost, ix->stream));
     CU(cudaStreamSynchronize(ix->stream));
-    memcpy(out_idx + (size_t)s0 * out_k, ix->h_idx.p, sizeof(uint32_t) * (size_t)c * out_k);
-    memcpy(out_dist + (size_t)s0 * out_k, ix->h_dist.p, sizeof(float) * (size_t)c * out_k);
+    if (!out_pinned) {
+      memcpy(out_idx + (size_t)s0 * out_k, ix->h_idx.p, sizeof(uint32_t) * (size_t)c * out_k);
+      memcpy(out_dist + (size_t)s0 * out_k, ix->h_dist.p, sizeof(float) * (size_t)c * out_k);
+    }
   }
   return 0;
 }

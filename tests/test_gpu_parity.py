@@ -183,3 +183,20 @@ def test_two_phase_scan_is_bit_exact(kw, cap, monkeypatch):
   i1, d1 = c.native.search_batched(c.q)
   np.testing.assert_array_equal(i0, i1)
   np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
+def test_host_call_with_page_locked_buffers_matches_pageable():
+  """scann_b200_search_batched copies page-locked caller memory to / from the device directly."""
+  import torch
+  c = get_case()
+  i0, d0 = c.native.search_batched(c.q)
+  qp = torch.from_numpy(c.q).pin_memory()
+  oi = torch.empty(i0.shape, dtype=torch.int32).pin_memory()
+  od = torch.empty(d0.shape, dtype=torch.float32).pin_memory()
+  i1, d1 = c.native.search_batched(qp.numpy(), out=(oi.numpy().view(np.uint32), od.numpy()))
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  # mixed: pinned queries, pageable outputs
+  i2, d2 = c.native.search_batched(qp.numpy())
+  np.testing.assert_array_equal(i0, i2)
+  np.testing.assert_array_equal(d0.view(np.uint32), d2.view(np.uint32))
