@@ -34,7 +34,9 @@
 
 // How the main scan accumulates the four u16-lane registers of an oct lookup:
 //   0 = plain adds (ptxas merges pairs into IADD3 on the ALU pipe), 1 = two on ALU + two IMAD on the
-//   FMA pipe, 2 = all four as IMAD.  Measured on B200 (C2): see DESIGN.md.
+//   FMA pipe, 2 = all four as IMAD, 3 = one mask per word + a 64-bit IMAD.WIDE sum of the whole word (fewer
+//   instructions, but IMAD.WIDE issues far below the IMAD rate: 1.94 ms vs 1.45 ms on C2).
+//   Measured on B200 (C2): see DESIGN.md.
 #ifndef SB_SCAN_ACC
 #define SB_SCAN_ACC 2
 #endif
@@ -104,6 +106,25 @@ __device__ __forceinline__ void score_oct_addr(const uint32_t (&ad)[8 * W], int 
                                                uint32_t (&acc)[4]) {
   uint32_t e0 = 0, o0 = 0, e1 = 0, o1 = 0;
   const int nl = NL ? NL : nlast;
+#if SB_SCAN_ACC == 3
+  // One mask per word instead of mask + permute: the even bytes are accumulated as two u16 lanes (IMAD),
+  // the WHOLE word as a 64-bit integer (IMAD.WIDE); sum(word) = E_lo + 2^8 O_lo + 2^16 E_hi + 2^24 O_hi, so the
+  // odd lanes are (S - E) >> 8 at the end.
+  unsigned long long sx = 0, sy = 0;
+#pragma unroll
+  for (int i = 0; i < 8 * W; ++i) {
+    if (i >= 8 * (W - 1) + nl) continue;
+    uint32_t vx, vy;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8));
+    const uint32_t xe = vx & 0x00FF00FFu, ye = vy & 0x00FF00FFu;
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e0) : "r"(xe), "r"(one));
+    asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e1) : "r"(ye), "r"(one));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(sx) : "r"(vx), "r"(one));
+    asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(sy) : "r"(vy), "r"(one));
+  }
+  acc[0] = e0; acc[1] = (uint32_t)((sx - e0) >> 8); acc[2] = e1; acc[3] = (uint32_t)((sy - e1) >> 8);
+  return;
+#endif
 #pragma unroll
   for (int i = 0; i < 8 * W; ++i) {
     if (i >= 8 * (W - 1) + nl) continue;
