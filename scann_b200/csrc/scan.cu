@@ -28,6 +28,8 @@
 // section 7 hard-part 1 -- regardless of scheduling and of how tight tau was.  If a buffer
 // overflowed, the host re-scans only the affected queries with the tightened tau (duplicates are
 // removed by key), so no candidate can be lost.
+#include <utility>
+
 #include "common.cuh"
 #include "exact_math.cuh"
 #include "kernels.h"
@@ -101,35 +103,37 @@ __device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigne
 // so ptxas cannot fold them back into IADD3s) accumulate them: LDS : ALU : FMA = 1 : 4 : 4 per eight
 // lookups.  ad[i] is the shared address of block row i's entry for this slot in oct table 0; oct QD's
 // table is a compile-time displacement away.
+template <int... Is, class F>
+__device__ __forceinline__ void static_for(std::integer_sequence<int, Is...>, F&& f) {
+  (f(std::integral_constant<int, Is>{}), ...);
+}
+
+// One oct (eight queries) against one 32-slot group.  ad[i] = table base | nibble offset of lookup i (the
+// table is 128-byte aligned, so the OR is the add); the row of lookup i (i * 128 bytes) and the oct's table
+// (QD * W * 1024 bytes) are immediate displacements of the load.
 template <int W, int NL, int QD>
 __device__ __forceinline__ void score_oct_addr(const uint32_t (&ad)[8 * W], int nlast, uint32_t one,
                                                uint32_t (&acc)[4]) {
   uint32_t e0 = 0, o0 = 0, e1 = 0, o1 = 0;
   const int nl = NL ? NL : nlast;
 #if SB_SCAN_ACC == 3
-  // One mask per word instead of mask + permute: the even bytes are accumulated as two u16 lanes (IMAD),
-  // the WHOLE word as a 64-bit integer (IMAD.WIDE); sum(word) = E_lo + 2^8 O_lo + 2^16 E_hi + 2^24 O_hi, so the
-  // odd lanes are (S - E) >> 8 at the end.
   unsigned long long sx = 0, sy = 0;
-#pragma unroll
-  for (int i = 0; i < 8 * W; ++i) {
-    if (i >= 8 * (W - 1) + nl) continue;
+#endif
+  static_for(std::make_integer_sequence<int, 8 * W>{}, [&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    if (i >= 8 * (W - 1) + nl) return;
     uint32_t vx, vy;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8));
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8 + i * 128));
+#if SB_SCAN_ACC == 3
+    // One mask per word instead of mask + permute: the even bytes are accumulated as two u16 lanes (IMAD),
+    // the WHOLE word as a 64-bit integer (IMAD.WIDE); sum(word) = E_lo + 2^8 O_lo + 2^16 E_hi + 2^24 O_hi, so
+    // the odd lanes are (S - E) >> 8 at the end.
     const uint32_t xe = vx & 0x00FF00FFu, ye = vy & 0x00FF00FFu;
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e0) : "r"(xe), "r"(one));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e1) : "r"(ye), "r"(one));
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(sx) : "r"(vx), "r"(one));
     asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(sy) : "r"(vy), "r"(one));
-  }
-  acc[0] = e0; acc[1] = (uint32_t)((sx - e0) >> 8); acc[2] = e1; acc[3] = (uint32_t)((sy - e1) >> 8);
-  return;
-#endif
-#pragma unroll
-  for (int i = 0; i < 8 * W; ++i) {
-    if (i >= 8 * (W - 1) + nl) continue;
-    uint32_t vx, vy;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8));
+#else
     const uint32_t xe = vx & 0x00FF00FFu, xo = __byte_perm(vx, 0u, 0x4341);
     const uint32_t ye = vy & 0x00FF00FFu, yo = __byte_perm(vy, 0u, 0x4341);
 #if SB_SCAN_ACC == 0
@@ -145,8 +149,13 @@ __device__ __forceinline__ void score_oct_addr(const uint32_t (&ad)[8 * W], int 
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(e1) : "r"(ye), "r"(one));
     asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(o1) : "r"(yo), "r"(one));
 #endif
-  }
+#endif
+  });
+#if SB_SCAN_ACC == 3
+  acc[0] = e0; acc[1] = (uint32_t)((sx - e0) >> 8); acc[2] = e1; acc[3] = (uint32_t)((sy - e1) >> 8);
+#else
   acc[0] = e0; acc[1] = o0; acc[2] = e1; acc[3] = o1;  // (s0,s2) (s1,s3) (s4,s6) (s5,s7) as u16 lanes
+#endif
 }
 
 // Interleave up to eight uint8 LUTs (8W*16 bytes each, NULL = all zero) into an oct table.
@@ -639,7 +648,8 @@ template <int W, int NL>
 __global__ void __launch_bounds__(kScanThreads)
 scan_main_kernel(DevIndex ix, ScanWork w) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint2* tables = reinterpret_cast<uint2*>(smem);  // [octs per item][W*128] 64-bit entries
+  // [octs per item][W*128] 64-bit entries, 128-byte aligned: the lookup addresses are formed with OR
+  uint2* tables = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~(uintptr_t)127);
   __shared__ ItemMeta meta;
   uint32_t (&s_q)[kMaxQPI] = meta.q;
   int (&s_thr)[kMaxQPI] = meta.thr;
@@ -723,8 +733,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
         for (int j = 0; j < W; ++j)
 #pragma unroll
           for (int k = 0; k < 8; ++k)
-            ad[8 * j + k] = tb32 + (8 * j + k) * 128 +
-                            ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
+            ad[8 * j + k] = tb32 | ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
       }
       // fast path inline (8 compares per oct), candidate push out of line: the scoring loops of the
       // octs are unrolled copies and must stay inside the instruction cache
@@ -892,7 +901,7 @@ size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover) {
   return (size_t)ix.W * 128 * 4 + (size_t)pilot_capl(nover) * 8;
 }
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item) {
-  return (size_t)quads_per_item * ix.W * 128 * 8;
+  return (size_t)quads_per_item * ix.W * 128 * 8 + 128;  // + alignment slack
 }
 
 cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) {
