@@ -39,8 +39,10 @@ typedef struct scann_b200_index scann_b200_index;
  * Everything a searcher is made of, as host pointers in the serialized-asset layouts
  * (scann_ops/cc/scann.cc:105-233 LoadArtifacts).  The library copies
  * what it needs to the device during scann_b200_index_create; the caller keeps ownership.
- *   tree-AH      : centers + tokens + codes (+ soar_codes) + codebook (+ dataset for reordering)
- *   brute force  : dataset (f32) or bf16_dataset, n_leaves = n_blocks = 0
+ *   tree-AH      : centers + tokens + codes (+ soar_codes) + codebook
+ *                  (+ dataset for f32 reordering, or bf16_dataset alone for bfloat16 reordering:
+ *                   Bfloat16ReorderingHelper, utils/reordering_helper.cc:720-757)
+ *   brute force  : bf16_dataset, n_leaves = n_blocks = 0 (Bfloat16BruteForceSearcher)
  */
 typedef struct {
   int32_t distance;            /* SCANN_B200_DOT_PRODUCT | SCANN_B200_SQUARED_L2 */

@@ -716,15 +716,31 @@ static size_t soar_dedup(cand_t* c, size_t n, size_t final_size, uint64_t* keys)
 /* utils/reordering_helper.cc:257-283 -> DenseDistanceOneToMany over the gathered rows.
  * The reference's arithmetic for a row depends on its position in the (unordered) result
  * list (main kernel vs. the n%3 tail); the oracle uses the main kernel for every row. */
+/* utils/bfloat16_helpers.h:30-48 (Bfloat16Decompress): bits << 16. */
+static inline float bf16_to_f32(int16_t b) {
+  uint32_t u = (uint32_t)(uint16_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static float neg_dot_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n);
+static float sql2_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n);
+
+/* bfloat16 reordering (utils/reordering_helper.cc:745-757, Bfloat16ReorderingHelper::ComputeDistancesForReordering
+ * -> DenseDotProductDistanceOneToManyBf16Float / OneToManyBf16FloatSquaredL2): f32 query x bf16 row, f32 FMA. */
 static float exact_distance(const so_index* ix, const float* q, uint32_t dp) {
   const uint32_t D = ix->d.d;
+  if (!ix->d.dataset) {
+    const int16_t* xb = ix->d.bf16_dataset + (size_t)dp * D;
+    return ix->d.distance == SO_DOT_PRODUCT ? neg_dot_bf16_avx2_order(q, xb, D) : sql2_bf16_avx2_order(q, xb, D);
+  }
   const float* x = ix->d.dataset + (size_t)dp * D;
   if (ix->d.distance == SO_DOT_PRODUCT) return D < 8 ? neg_dot_small(q, x, D) : neg_dot_avx2_order(q, x, D);
   return D < 8 ? sql2_small(q, x, D) : sql2_avx2_order(q, x, D);
 }
 
 int so_exact_distances(const so_index* ix, const float* q, const uint32_t* dps, uint32_t n, float* out) {
-  if (!ix->d.dataset) return fail("no dataset");
+  if (!ix->d.dataset && !ix->d.bf16_dataset) return fail("no dataset");
   for (uint32_t i = 0; i < n; ++i) out[i] = exact_distance(ix, q, dps[i]);
   return 0;
 }
@@ -736,7 +752,7 @@ typedef struct {
 static sp_t resolve_params(const so_index* ix, int final_nn, int pre_nn, int leaves) {
   /* scann_ops/cc/scann.cc:406-430 + SetUnspecifiedParametersToDefaults */
   sp_t p;
-  const int has_reorder = ix->d.dataset != NULL && ix->d.n_blocks != 0;
+  const int has_reorder = (ix->d.dataset != NULL || ix->d.bf16_dataset != NULL) && ix->d.n_blocks != 0;
   p.k = final_nn > 0 ? final_nn : ix->d.default_final_nn;
   if (has_reorder) p.npre = pre_nn > 0 ? pre_nn : ix->d.default_pre_nn;
   else p.npre = p.k;
@@ -833,7 +849,7 @@ static void finish_query(const so_index* ix, const float* q, sp_t sp, uint64_t* 
   }
   size_t m = n;
   if (!ix->disjoint) m = soar_dedup(c, n, (size_t)sp.npre, k2);
-  const int has_reorder = ix->d.dataset != NULL;
+  const int has_reorder = ix->d.dataset != NULL || ix->d.bf16_dataset != NULL;
   for (size_t i = 0; i < m; ++i) {
     float dist = has_reorder ? exact_distance(ix, q, c[i].dp) : c[i].score;
     k2[i] = ((uint64_t)f2ord(dist) << 32) | c[i].dp;
@@ -939,13 +955,6 @@ int so_candidates(const so_index* ix, const float* q, uint32_t nq, int pre_nn, i
 /* bfloat16 brute force (config C3)                                           */
 /* ------------------------------------------------------------------------- */
 
-/* utils/bfloat16_helpers.h:30-48 (Bfloat16Decompress): bits << 16. */
-static inline float bf16_to_f32(int16_t b) {
-  uint32_t u = (uint32_t)(uint16_t)b << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
 
 /* brute_force/bfloat16_brute_force.cc:131-147: dist_i = -sum_d q[d] * f32(bf16 x[i][d]) with an f32
  * query and f32 accumulation, over ALL rows, then the k smallest (distance, index).
@@ -970,6 +979,28 @@ static float neg_dot_bf16_avx2_order(const float* q, const int16_t* x, uint32_t 
   }
   float r = (b[0] + b[2]) + (b[1] + b[3]);
   if (j < n) r = fmaf(-q[j], bf16_to_f32(x[j]), r);
+  return r;
+}
+
+/* squared-L2 sibling (FusedMultiplyOp<kIsSquaredL2 = true, int16_t>: diff = q - x; acc = fma(diff, diff, acc)) */
+static float sql2_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n) {
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8)
+    for (int l = 0; l < 8; ++l) { const float t = q[j + l] - bf16_to_f32(x[j + l]); a[l] = fmaf(t, t, a[l]); }
+  float b[4];
+  for (int l = 0; l < 4; ++l) b[l] = a[l + 4] + a[l];
+  if (j + 4 <= n) {
+    for (int l = 0; l < 4; ++l) { const float t = q[j + l] - bf16_to_f32(x[j + l]); b[l] = fmaf(t, t, b[l]); }
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    { const float t = q[j] - bf16_to_f32(x[j]); b[2] = fmaf(t, t, b[2]); }
+    { const float t = q[j + 1] - bf16_to_f32(x[j + 1]); b[3] = fmaf(t, t, b[3]); }
+    j += 2;
+  }
+  float r = (b[0] + b[2]) + (b[1] + b[3]);
+  if (j < n) { const float t = q[j] - bf16_to_f32(x[j]); r = fmaf(t, t, r); }
   return r;
 }
 

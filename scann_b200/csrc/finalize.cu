@@ -22,8 +22,14 @@ constexpr uint32_t kInvalidId = 0xFFFFFFFFu;
 __device__ __forceinline__ float exact_distance(const DevIndex& ix, const float* __restrict__ q,
                                                 uint32_t dp) {
   const uint32_t row = ix.dp_row ? ix.dp_row[dp] : dp;
-  const float* x = ix.dataset + (size_t)row * ix.d;
   auto lq = [&](uint32_t i) { return q[i]; };
+  if (!ix.dataset) {
+    // bfloat16 reordering (utils/reordering_helper.cc:745-757): f32 query x bf16 row, f32 FMA, 8-lane order
+    const uint16_t* xb = ix.dataset_bf16 + (size_t)row * ix.d;
+    auto lb = [&](uint32_t i) { return __uint_as_float((uint32_t)__ldg(xb + i) << 16); };
+    return ix.distance == 0 ? neg_dot_avx2_order(lq, lb, ix.d) : sql2_avx2_order(lq, lb, ix.d);
+  }
+  const float* x = ix.dataset + (size_t)row * ix.d;
   auto lx = [&](uint32_t i) { return __ldg(x + i); };
   if (ix.distance == 0) return ix.d < 8 ? neg_dot_small(lq, lx, ix.d) : neg_dot_avx2_order(lq, lx, ix.d);
   return ix.d < 8 ? sql2_small(lq, lx, ix.d) : sql2_avx2_order(lq, lx, ix.d);
@@ -67,6 +73,47 @@ __device__ __forceinline__ float exact_distance_lanes8(const DevIndex& ix, const
   float r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));        // lane 0: (b0+b2)+(b1+b3)
   if (j < n && l == 0) {
     const float xv = __ldg(x + j), qv = q[j];
+    if (dot) r = __fmaf_rn(-qv, xv, r);
+    else { const float t = __fsub_rn(qv, xv); r = __fmaf_rn(t, t, r); }
+  }
+  return r;
+}
+
+// bf16 rows: the same lane structure with Bfloat16Decompress on every load.
+__device__ __forceinline__ float exact_distance_lanes8_bf16(const DevIndex& ix, const float* __restrict__ q,
+                                                       uint32_t dp, int l) {
+  const uint32_t row = ix.dp_row ? ix.dp_row[dp] : dp;
+  const uint16_t* __restrict__ x = ix.dataset_bf16 + (size_t)row * ix.d;
+  const uint32_t n = ix.d;
+  const bool dot = ix.distance == 0;
+  float a = 0.f;
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8) {
+    const float xv = __uint_as_float((uint32_t)__ldg(x + j + l) << 16), qv = q[j + l];
+    if (dot) a = __fmaf_rn(-qv, xv, a);
+    else { const float t = __fsub_rn(qv, xv); a = __fmaf_rn(t, t, a); }
+  }
+  float b = __fadd_rn(__shfl_down_sync(0xFFFFFFFFu, a, 4, 8), a);  // lanes 0..3: a[l+4] + a[l]
+  if (j + 4 <= n) {
+    if (l < 4) {
+      const float xv = __uint_as_float((uint32_t)__ldg(x + j + l) << 16), qv = q[j + l];
+      if (dot) b = __fmaf_rn(-qv, xv, b);
+      else { const float t = __fsub_rn(qv, xv); b = __fmaf_rn(t, t, b); }
+    }
+    j += 4;
+  }
+  if (j + 2 <= n) {
+    if (l == 2 || l == 3) {
+      const float xv = __uint_as_float((uint32_t)__ldg(x + j + (l - 2)) << 16), qv = q[j + (l - 2)];
+      if (dot) b = __fmaf_rn(-qv, xv, b);
+      else { const float t = __fsub_rn(qv, xv); b = __fmaf_rn(t, t, b); }
+    }
+    j += 2;
+  }
+  const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));   // lanes 0,1: b0+b2, b1+b3
+  float r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));        // lane 0: (b0+b2)+(b1+b3)
+  if (j < n && l == 0) {
+    const float xv = __uint_as_float((uint32_t)__ldg(x + j) << 16), qv = q[j];
     if (dot) r = __fmaf_rn(-qv, xv, r);
     else { const float t = __fsub_rn(qv, xv); r = __fmaf_rn(t, t, r); }
   }
@@ -137,7 +184,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
   const uint32_t q = blockIdx.x;
   const uint32_t n = min(w.cnt[q], w.nover);
   const uint64_t* src = w.buf + (size_t)q * w.cap;
-  const bool reorder = ix.dataset != nullptr;
+  const bool reorder = ix.dataset != nullptr || ix.dataset_bf16 != nullptr;
   for (uint32_t i = tid; i < ix.d; i += kFinThreads) sq[i] = a.q[(size_t)q * ix.d + i];
   if (tid == 0) s_removed = 0;
   __syncthreads();
@@ -171,7 +218,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
         const bool valid = c < n;
         const uint32_t gslot = (uint32_t)src[valid ? c : 0];
         const uint32_t dp = ix.key_by_dp ? gslot : ix.slot_dp[gslot];
-        const float dist = exact_distance_lanes8(ix, sq, dp, l);
+        const float dist = ix.dataset ? exact_distance_lanes8(ix, sq, dp, l) : exact_distance_lanes8_bf16(ix, sq, dp, l);
         if (valid && l == 0) a.part_exact[(size_t)q * a.part_cap + c] = dist;
       }
     }
@@ -217,7 +264,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
       const uint32_t c = c0 + grp;
       const bool valid = c < m;
       const uint32_t dp = (uint32_t)kb[valid ? c : 0];
-      const float dist = exact_distance_lanes8(ix, sq, dp, l);
+      const float dist = ix.dataset ? exact_distance_lanes8(ix, sq, dp, l) : exact_distance_lanes8_bf16(ix, sq, dp, l);
       if (valid && l == 0) ka[c] = make_key(dist, dp);
     }
   } else {

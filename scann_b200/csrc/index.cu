@@ -263,7 +263,25 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     UP(ix->slot_tie, slot_tie.data(), sizeof(uint32_t) * slot_tie.size());
     v.slot_tie = ix->slot_tie.as<uint32_t>();
   }
-  v.dataset = nullptr; v.dp_row = nullptr;
+  v.dataset = nullptr; v.dp_row = nullptr; v.dataset_bf16 = nullptr;
+  if (!d->dataset && d->bf16_dataset) {
+    // bfloat16 reordering (exact_reordering { bfloat16 { enabled: true } }, bfloat16_dataset.npy): half the
+    // reorder gather bytes and device memory of the f32 rows
+    if (world == 1) {
+      UP(ix->dataset, d->bf16_dataset, sizeof(uint16_t) * (size_t)N * D);
+    } else {
+      std::vector<uint32_t> rowmap(N, 0xFFFFFFFFu);
+      size_t rows = 0;
+      for (uint32_t i = rank; i < N; i += world) rowmap[i] = (uint32_t)rows++;
+      CU(ix->dataset.ensure(sizeof(uint16_t) * std::max<size_t>(rows, 1) * D));
+      if (rows)
+        CU(cudaMemcpy2D(ix->dataset.p, sizeof(uint16_t) * D, d->bf16_dataset + (size_t)rank * D,
+                        sizeof(uint16_t) * D * world, sizeof(uint16_t) * D, rows, cudaMemcpyHostToDevice));
+      UP(ix->dp_row, rowmap.data(), sizeof(uint32_t) * N);
+      v.dp_row = ix->dp_row.as<uint32_t>();
+    }
+    v.dataset_bf16 = ix->dataset.as<uint16_t>();
+  }
   if (d->dataset) {
     if (world == 1) {
       UP(ix->dataset, d->dataset, sizeof(float) * (size_t)N * D);
@@ -322,7 +340,7 @@ int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Pa
     p->k = (uint32_t)kb; p->npre = p->k; p->nover = p->k; p->P = 1;
     return 0;
   }
-  const bool has_reorder = ix->dev.dataset != nullptr;
+  const bool has_reorder = ix->dev.dataset != nullptr || ix->dev.dataset_bf16 != nullptr;
   const int k = final_nn > 0 ? final_nn : ix->desc.default_final_nn;
   int npre = has_reorder ? (pre_nn > 0 ? pre_nn : ix->desc.default_pre_nn) : k;
   int P = leaves > 0 ? leaves : ix->desc.default_leaves;

@@ -32,6 +32,7 @@ struct DevIndex {
   const uint32_t* slot_dp;    // [groups*32] datapoint id per slot, 0xFFFFFFFF padding
   const uint32_t* slot_tie;   // [groups*32] slot of the datapoint in the unsharded index (NULL = identity)
   const float* dataset;       // [rows][D] f32 rows for exact reordering (NULL if none)
+  const uint16_t* dataset_bf16;  // [rows][D] bf16 rows (bfloat16 reordering) when `dataset` is NULL
   const uint32_t* dp_row;     // [N] datapoint id -> row of `dataset` (NULL = identity)
   // tensor-core tokenization (prep.cu): centres as the bf16 operand [L][tok_kp] = [hi | hi | lo | 0]
   const void* tok_b;

@@ -67,8 +67,17 @@ class _Plan:
       unimpl("residual squared-L2 tree-AH")
     r = self.reordering
     if r is not None:
-      if cfgmod.as_bool(r.path("fixed_point", "enabled"), False) or cfgmod.as_bool(r.path("bfloat16", "enabled"), False):
-        unimpl("int8 / bfloat16 reordering")
+      if cfgmod.as_bool(r.path("fixed_point", "enabled"), False):
+        unimpl("int8 reordering")
+      if self.bf16_reorder():
+        thr = cfgmod.as_float(r.path("bfloat16", "noise_shaping_threshold"), math.nan)
+        if thr is not None and not math.isnan(thr):
+          unimpl("noise-shaped bfloat16 quantization of the reordering dataset")
+
+  def bf16_reorder(self):
+    """exact_reordering { bfloat16 { enabled: true } } (Bfloat16ReorderingHelper, utils/reordering_helper.cc:720-757)."""
+    r = self.reordering
+    return r is not None and cfgmod.as_bool(r.path("bfloat16", "enabled"), False)
 
   def dims_per_block(self):
     proj = self.ah.get("projection")
@@ -120,6 +129,10 @@ class ScannNumpy:
           soar_lambda=lam, overretrieve=cfgmod.as_float(p.path("database_spilling", "overretrieve_factor"), 2.0),
           spherical=p.get("partitioning_type", "GENERIC") == "SPHERICAL",
           keep_dataset=plan.reordering is not None)
+      if plan.bf16_reorder():
+        # reordering_helper.cc:729-730: the reordering dataset is Bfloat16QuantizeFloatDataset(original)
+        arrays.bf16_dataset = index_build.bfloat16_quantize(db)
+        arrays.dataset = None
       self._finish(arrays, plan)
     except _lib.ScannB200Error as e:
       raise _runtime("Error initializing searcher: ", e)
@@ -200,6 +213,7 @@ class ScannNumpy:
     d.soar_codes = own(a.soar_codes, np.uint8)
     d.codebook = own(a.codebook, np.float32)
     d.dataset = own(a.dataset, np.float32)
+    d.bf16_dataset = own(a.bf16_dataset, np.int16)
     d.overretrieve = a.overretrieve
     buf = C.create_string_buffer(1 << 16)
     rc = L.scann_b200_assets_save(path.encode(), C.byref(d), self._config_text.encode(), 1 if relative_path else 0,
@@ -261,6 +275,7 @@ def _arrays_from_desc(desc, plan):
   n, d, L, B, S = desc.n, desc.d, desc.n_leaves, desc.n_blocks, desc.dims_per_block
   a = index_build.IndexArrays(distance="dot_product" if desc.distance == 0 else "squared_l2", dataset=None, n=n, d=d)
   a.dataset = arr(desc.dataset, (n, d), np.float32)
+  a.bf16_dataset = arr(desc.bf16_dataset, (n, d), np.int16)
   a.centers = arr(desc.centers, (L, d), np.float32)
   a.soar = bool(desc.soar)
   a.tokens = arr(desc.tokens, (n * (2 if a.soar else 1),), np.int32)

@@ -109,3 +109,22 @@ def test_empty_partitions_are_tolerated():
   idx, dist = s.search_batched(q)
   truth = np.take_along_axis(q @ db.T, idx.astype(np.int64), axis=1)
   np.testing.assert_allclose(dist, truth, rtol=1e-5)
+
+
+def test_bfloat16_reordering_through_the_builder(tmp_path):
+  """reorder(N, quantize=ReorderType.BFLOAT16): bfloat16_dataset.npy asset, round trip, distances of the bf16 rows."""
+  from scann_b200 import scann_ops_pybind, scann_builder, index_build
+  db, q = make_data()
+  s = (scann_ops_pybind.builder(db, 10, "dot_product").tree(27, 10, min_partition_size=10).score_ah(2)
+       .reorder(60, quantize=scann_builder.ReorderType.BFLOAT16).build())
+  idx, dist = s.search_batched(q)
+  bits = index_build.bfloat16_quantize(db)
+  x = (bits.view(np.uint16).astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+  truth = np.take_along_axis(q.astype(np.float64) @ x.T, idx.astype(np.int64), axis=1)
+  np.testing.assert_allclose(dist, truth, rtol=1e-5, atol=1e-5)
+  s.serialize(str(tmp_path))
+  assert (tmp_path / "bfloat16_dataset.npy").exists() and not (tmp_path / "dataset.npy").exists()
+  l2 = scann_ops_pybind.load_searcher(str(tmp_path))
+  i2, d2 = l2.search_batched(q)
+  np.testing.assert_array_equal(idx, i2)
+  np.testing.assert_array_equal(dist.view(np.uint32), d2.view(np.uint32))

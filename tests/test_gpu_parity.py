@@ -200,3 +200,35 @@ def test_host_call_with_page_locked_buffers_matches_pageable():
   i2, d2 = c.native.search_batched(qp.numpy())
   np.testing.assert_array_equal(i0, i2)
   np.testing.assert_array_equal(d0.view(np.uint32), d2.view(np.uint32))
+
+
+# ---- bfloat16 reordering (Bfloat16ReorderingHelper) ----
+@pytest.mark.parametrize("kw", [dict(), dict(soar=1.5), dict(dpb=3, d=99, leaves=60, n=9000),
+                                dict(distance="squared_l2", d=64, leaves=50, n=10000),
+                                dict(n=3000, leaves=30, d=6, dpb=2, probe=5, pre=40)],
+                         ids=["dot", "soar", "d99", "l2", "d6"])
+def test_bf16_reordering_is_bit_exact(kw):
+  import copy
+  import oracle
+  from scann_b200 import _lib, index_build, distributed
+  c = get_case(**kw)
+  a = copy.copy(c.arrays)
+  a.bf16_dataset = index_build.bfloat16_quantize(c.db)
+  a.dataset = None
+  o = oracle.OracleIndex(a, c.probe, c.pre, c.k)
+  g = _lib.NativeIndex(a, c.probe, c.pre, c.k)
+  i0, d0 = o.search_batched(c.q)
+  i1, d1 = g.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  # distances are those of the bf16 rows (f32 query), within 1e-5 relative of float64
+  x = (a.bf16_dataset.view(np.uint16).astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+  rows = x[i1.astype(np.int64)]
+  if a.distance == "dot_product":
+    truth = np.einsum("qd,qkd->qk", c.q.astype(np.float64), rows)
+  else:
+    truth = ((c.q.astype(np.float64)[:, None, :] - rows) ** 2).sum(-1)
+  np.testing.assert_allclose(d1, truth, rtol=1e-5, atol=1e-5)
+  # and it differs from f32 reordering somewhere (the bf16 rows really are used)
+  _, df = c.native.search_batched(c.q)
+  assert not np.array_equal(df.view(np.uint32), d1.view(np.uint32))

@@ -66,3 +66,21 @@ def test_sharded_equals_unsharded(kw, world):
   np.testing.assert_array_equal(ref_i[:8], i2[:8])
   i0, d0 = c.oracle.search_batched(c.q)
   np.testing.assert_array_equal(i0, i2)
+
+
+@pytest.mark.parametrize("kw,world", [(dict(), 2), (dict(soar=1.5), 3)])
+def test_sharded_bf16_reordering_equals_unsharded(kw, world):
+  """Shards hold the bf16 rows of their own datapoints (id mod world) for the reordering."""
+  import copy
+  import types
+  from scann_b200 import _lib, index_build
+  c = get_case(**kw)
+  a = copy.copy(c.arrays)
+  a.bf16_dataset = index_build.bfloat16_quantize(c.db)
+  a.dataset = None
+  full = _lib.NativeIndex(a, c.probe, c.pre, c.k)
+  i1, d1 = full.search_batched(c.q)
+  case = types.SimpleNamespace(arrays=a, q=c.q, probe=c.probe, pre=c.pre, k=c.k)
+  i2, d2, _ = run_sharded(case, world)
+  np.testing.assert_array_equal(i1, i2)
+  np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
