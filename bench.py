@@ -38,6 +38,8 @@ WORKLOADS = {
                            clusters=8000, normalize=True, seed=3, train_sample=250000),
     # C3: brute-force MIPS over a bf16 database (BASELINE.json configs[2])
     "c3_bruteforce_bf16": dict(kind="bruteforce", n=1_000_000, d=768, k=100, nq=10000, seed=5),
+    # the float sibling (BruteForceSearcher<float>): f32 rows, 3-term bf16 tcgen05 pre-filter + exact fp32 chain
+    "c3_bruteforce_f32": dict(kind="bruteforce", dtype="f32", n=1_000_000, d=768, k=100, nq=10000, seed=5),
     # C5 shape family (Deep1B-like: 96-d L2-normalised rows, dot product, SOAR, reorder 200) at a database size
     # one bench run can build in minutes; BASELINE.json's C5 is 100M rows / 40k leaves on 8 GPUs.  ~2,500 rows
     # per leaf as in C5; --n / --leaves rescale it.
@@ -450,19 +452,22 @@ def run_bruteforce(args, wl, rank, world, local_rank):
   n, d, nq, k = wl["n"], wl["d"], wl["nq"], wl["k"]
   rng = np.random.default_rng(wl["seed"])
   t0 = time.time()
-  bits = np.empty((n, d), np.int16)
+  f32 = wl.get("dtype") == "f32"
+  bits = np.empty((n, d), np.float32 if f32 else np.int16)
   for s0 in range(0, n, 1 << 16):
-    bits[s0:s0 + (1 << 16)] = index_build.bfloat16_quantize(rng.standard_normal((min(1 << 16, n - s0), d), dtype=np.float32))
+    blk = rng.standard_normal((min(1 << 16, n - s0), d), dtype=np.float32)
+    bits[s0:s0 + (1 << 16)] = blk if f32 else index_build.bfloat16_quantize(blk)
   q = np.random.default_rng(wl["seed"] + 1).standard_normal((nq, d), dtype=np.float32)
   log(f"[bf] data in {time.time() - t0:.1f}s")
-  a = index_build.IndexArrays(distance="dot_product", dataset=None, n=n, d=d)
-  a.bf16_dataset = bits
+  a = index_build.IndexArrays(distance="dot_product", dataset=bits if f32 else None, n=n, d=d)
+  if not f32:
+    a.bf16_dataset = bits
   if args.impl == "reference":
     import oracle
     threads = os.cpu_count() or 1
     sample = max(threads, 16)
     t0 = time.perf_counter()
-    oracle.bruteforce_bf16(bits, q[:sample], k, threads=threads)
+    (oracle.bruteforce_f32 if f32 else oracle.bruteforce_bf16)(bits, q[:sample], k, threads=threads)
     dt = time.perf_counter() - t0
     qps = sample / dt
     emit({"impl": "reference", "metric": "batched QPS, bf16 brute-force MIPS k=100", "value": qps,
@@ -490,7 +495,7 @@ def run_bruteforce(args, wl, rank, world, local_rank):
   for _ in range(args.warmup):
     ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)
   # recall against an f32 GEMM on the decompressed rows (first 512 queries)
-  x = (torch.from_numpy(bits.view(np.uint16).astype(np.int32)).to(dev) << 16).view(torch.float32)
+  x = torch.from_numpy(bits).to(dev) if f32 else (torch.from_numpy(bits.view(np.uint16).astype(np.int32)).to(dev) << 16).view(torch.float32)
   gt = torch.topk(d_q[:512] @ x.T, k, dim=1).indices.cpu().numpy()
   del x
   torch.cuda.empty_cache()
@@ -558,7 +563,7 @@ def run_bruteforce(args, wl, rank, world, local_rank):
     if rank != 0:
       dist.destroy_process_group()
       return 0
-  flops = 2.0 * nq * n * d * 2  # two bf16 split terms per product
+  flops = 2.0 * nq * n * d * (3 if f32 else 2)  # bf16 split terms per product: hi.hi + lo.hi (+ hi.lo for f32 rows)
   gemm_s = agg["ms_scan"] / args.steps * 1e-3
   peaks = {}
   try:
@@ -568,17 +573,18 @@ def run_bruteforce(args, wl, rank, world, local_rank):
   # the GEMM rounds run as ~20 ms bursts between L2 flushes, i.e. "a kernel timed alone": burst peak
   peak = float(peaks.get("bf16_tflops", 1590.0))
   peak_sustained = float(peaks.get("bf16_tflops_sustained", 1400.0))
-  out = {"metric": "batched QPS, bf16 brute-force MIPS k=100", "value": world * nq * args.steps / (ms_total * 1e-3),
+  out = {"metric": f"batched QPS, {'f32' if f32 else 'bf16'} brute-force MIPS k=100", "value": world * nq * args.steps / (ms_total * 1e-3),
          "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
          "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-         "dtype": "bf16 x (bf16 hi + bf16 lo) -> f32 (tcgen05), f32 re-scoring", "data": "synthetic",
+         "dtype": ("(bf16 hi + lo) x (bf16 hi + lo) -> f32 (tcgen05, 3 terms), exact f32 chain re-scoring" if f32 else
+                   "bf16 x (bf16 hi + bf16 lo) -> f32 (tcgen05), f32 re-scoring"), "data": "synthetic",
          "config": {"workload": args.workload, "n": n, "d": d, "k": k, "queries_per_step": nq * world,
                     "recall_at_100_first512": rec, "l2_flush": "256 MiB write between timed steps",
                     "parallelism": f"query-parallel x{world} (one replica and one {nq}-query batch per GPU)"},
          "e2e": {"value": world * nq * e2e_steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(q.nbytes) * world,
                  "d2h_bytes_per_step": int(nq * k * 8) * world, "steps": e2e_steps},
          "gpu_launches": int(agg["kernel_launches"]), "clocks": sampler.summary(),
-         "roofline": {"bound": "tensor", "kernel": "bf::gemm_pair_kernel<2, filter>", "achieved": flops / gemm_s / 1e12,
+         "roofline": {"bound": "tensor", "kernel": "bf::gemm_pair_kernel<1, filter>" if f32 else "bf::gemm_pair_kernel<2, filter>", "achieved": flops / gemm_s / 1e12,
                       "peak": peak, "peak_source": "measured burst" if peaks else "fallback", "unit": "TFLOP/s",
                       "frac": flops / gemm_s / 1e12 / peak, "traffic": ncu_traffic("r01_gemm_pair_traffic.json"),
                       "traffic_note": "dram bytes of the largest round's launch (497,664 rows: 764 MB compulsory)",

@@ -1032,3 +1032,39 @@ int so_bruteforce_bf16(const int16_t* db, uint32_t n, uint32_t d, const float* q
   }
   return 0;
 }
+
+/* Float brute force: BruteForceSearcher<float>::FinishBatchedSearchSimple (brute_force/brute_force.cc:376-393)
+ * -> DenseDistanceManyToManyTopK (distance_measures/many_to_many/many_to_many_floating_point.h:119-130,
+ * many_to_many_impl.inc:522-567): dist = acc after  acc = 0; acc = fnmadd(q[d], x[d], acc)  sequentially in d
+ * (the same kernel as the partitioner's query tokenization), then FastTopNeighbors: the k smallest
+ * (distance, index).  Dot product only; API distances are -dist (scann.cc:364-369). */
+int so_bruteforce_f32(const float* db, uint32_t n, uint32_t d, const float* q, uint32_t nq, int k, uint32_t* out_idx,
+                      float* out_dist, int threads) {
+  if (k <= 0) return fail("k must be positive");
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 1 ? threads : 1)
+#endif
+  for (uint32_t i = 0; i < nq; ++i) {
+    topn_t tn;
+    topn_init(&tn, (size_t)k);
+    const float* qi = q + (size_t)i * d;
+    for (uint32_t r = 0; r < n; ++r) {
+      const float* x = db + (size_t)r * d;
+      float acc = 0.f;
+      for (uint32_t j = 0; j < d; ++j) acc = fmaf(-qi[j], x[j], acc);
+      topn_push(&tn, ((uint64_t)f2ord(acc) << 32) | r);
+    }
+    topn_finish(&tn);
+    for (int j = 0; j < k; ++j) {
+      if ((size_t)j < tn.n) {
+        out_idx[(size_t)i * k + j] = (uint32_t)tn.buf[j];
+        out_dist[(size_t)i * k + j] = -ord2f((uint32_t)(tn.buf[j] >> 32));
+      } else {
+        out_idx[(size_t)i * k + j] = 0;
+        out_dist[(size_t)i * k + j] = NAN;
+      }
+    }
+    free(tn.buf);
+  }
+  return 0;
+}

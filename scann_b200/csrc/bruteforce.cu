@@ -565,6 +565,60 @@ rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db
   }
 }
 
+// Float brute force (BruteForceSearcher<float>::FinishBatchedSearchSimple, brute_force/brute_force.cc:376-393 ->
+// DenseDistanceManyToManyTopK, many_to_many_impl.inc:522-567): exact re-scoring of the k' candidates with the
+// reference's arithmetic, acc = 0; acc = fnmadd(q[d], x[d], acc) sequentially in d.  One thread per candidate.
+__global__ void __launch_bounds__(128)
+rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ db, uint32_t d, const uint64_t* __restrict__ buf,
+                   const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t kprime, uint32_t k, uint32_t out_k,
+                   uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int np2) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
+  float* sq = reinterpret_cast<float*>(ka + np2);
+  const int tid = threadIdx.x;
+  const uint32_t qi = blockIdx.x;
+  const uint32_t m = min(cnt[qi], kprime);
+  const uint64_t* src = buf + (size_t)qi * cap;
+  for (uint32_t i = tid; i < d; i += 128) sq[i] = q[(size_t)qi * d + i];
+  for (int i = tid; i < np2; i += 128) ka[i] = kKeyMax;
+  __syncthreads();
+  for (uint32_t c = tid; c < m; c += 128) {
+    const uint32_t dp = (uint32_t)src[c];
+    const float* x = db + (size_t)dp * d;
+    float acc = 0.f;
+    if ((d & 3u) == 0) {
+      for (uint32_t j = 0; j < d; j += 16) {  // 16 dims in flight before the first FMA of the chunk
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(x + min(j + 4 * u, d - 4)));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t jj = j + 4 * u;
+          if (jj < d) {
+            acc = __fmaf_rn(-sq[jj], v[u].x, acc);
+            acc = __fmaf_rn(-sq[jj + 1], v[u].y, acc);
+            acc = __fmaf_rn(-sq[jj + 2], v[u].z, acc);
+            acc = __fmaf_rn(-sq[jj + 3], v[u].w, acc);
+          }
+        }
+      }
+    } else {
+      for (uint32_t j = 0; j < d; ++j) acc = __fmaf_rn(-sq[j], __ldg(x + j), acc);
+    }
+    ka[c] = make_key(acc, dp);
+  }
+  __syncthreads();
+  block_bitonic_sort(ka, np2);
+  const uint32_t kk = min(k, m);
+  for (uint32_t i = tid; i < out_k; i += 128) {
+    uint32_t id = 0;
+    float dist = __uint_as_float(0x7FC00000u);
+    if (i < kk) { id = (uint32_t)ka[i] + id_base; dist = -ord2f((uint32_t)(ka[i] >> 32)); }
+    out_idx[(size_t)qi * out_k + i] = id;
+    out_dist[(size_t)qi * out_k + i] = dist;
+  }
+}
+
 }  // namespace bf
 
 // ---- host side ------------------------------------------------------------------------------
@@ -663,11 +717,11 @@ static bool use_pair_kernel() {
 
 // One round: database rows [row0, row1) against all queries.
 cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, uint32_t n_total, uint32_t dpitch,
-                          uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s) {
+                          uint32_t row0, uint32_t row1, const ScanWork& w, int splits, cudaStream_t s) {
   const uint32_t m_pad = bf_m_pad(nq);
   const bool pair = use_pair_kernel();
   CUtensorMap tmA, tmB;
-  cudaError_t e = make_tmap(&tmA, a_operand, (uint64_t)bf::kSplits * m_pad, dpitch, dpitch, bf::BM);
+  cudaError_t e = make_tmap(&tmA, a_operand, (uint64_t)splits * m_pad, dpitch, dpitch, bf::BM);
   if (e != cudaSuccess) return e;
   e = make_tmap(&tmB, db, n_total, dpitch, dpitch, pair ? bf::BN / 2 : bf::BN);
   if (e != cudaSuccess) return e;
@@ -677,9 +731,15 @@ cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, ui
   a.num_kb = (dpitch + bf::BK - 1) / bf::BK;
   a.buf = w.buf; a.cnt = w.cnt; a.tau = w.tau; a.ovf = w.ovf; a.cap = w.cap;
   { const char* pe = getenv("SCANN_B200_GEMM_PROFILE"); a.prof = pe && pe[0] == '1'; }
+  if (splits == 1) {  // operands with the hi/lo terms concatenated along K (float brute force)
+    if (pair) return launch_gemm_pair<1, bf::kEpiFilter>(tmA, tmB, a, s);
+    return launch_gemm<1, bf::kEpiFilter>(tmA, tmB, a, s);
+  }
   if (pair) return launch_gemm_pair<bf::kSplits, bf::kEpiFilter>(tmA, tmB, a, s);
   return launch_gemm<bf::kSplits, bf::kEpiFilter>(tmA, tmB, a, s);
 }
+
+uint32_t bf_query_rows_pad(uint32_t nq) { return bf_m_pad(nq); }
 
 // Plain C[a_row][b_row] = sum_k A[a_row][k] * B[b_row][k] (bf16 operands, fp32 accumulate and output): the
 // tokenization pre-filter's GEMM (prep.cu), K = the concatenated hi/lo terms.
@@ -708,6 +768,17 @@ cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, 
   if (e != cudaSuccess) return e;
   bf::rescore_kernel<<<nq, 128, smem, s>>>(q, reinterpret_cast<const __nv_bfloat16*>(db), d, dpitch, w.buf, w.cnt, w.cap,
                                            kprime, k, out_k, id_base, out_idx, out_dist, np2);
+  return cudaGetLastError();
+}
+
+cudaError_t bf_rescore_f32(const float* q, const float* db, uint32_t nq, uint32_t d, const ScanWork& w, uint32_t kprime,
+                           uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s) {
+  int np2 = 2;
+  while ((uint32_t)np2 < kprime) np2 <<= 1;
+  const size_t smem = (size_t)np2 * 8 + (((size_t)d + 3) & ~(size_t)3) * 4;
+  cudaError_t e = cudaFuncSetAttribute(bf::rescore_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  bf::rescore_f32_kernel<<<nq, 128, smem, s>>>(q, db, d, w.buf, w.cnt, w.cap, kprime, k, out_k, id_base, out_idx, out_dist, np2);
   return cudaGetLastError();
 }
 

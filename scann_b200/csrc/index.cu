@@ -109,6 +109,7 @@ struct scann_b200_index {
   uint32_t max_chunk = 16384;
   // brute-force (bf16) searcher: database rows as bf16 with a 16-byte aligned pitch
   bool brute = false;
+  bool bf_f32 = false;  // float brute force: f32 rows in `dataset`, concatenated hi/lo bf16 operand in `bf_db`
   uint32_t bf_dpitch = 0;
   uint32_t bf_row0 = 0;  // first database row of this shard (row-sharded brute force)
   uint32_t avg_leaf_slots = 0;  // mean padded slots per leaf (scan phase heuristic)
@@ -122,9 +123,10 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   if (d->distance != SCANN_B200_DOT_PRODUCT && d->distance != SCANN_B200_SQUARED_L2)
     return fail(SCANN_B200_INVALID_ARGUMENT, "unknown distance measure %d", d->distance);
   if (!L && !B) {
-    // Bfloat16BruteForceSearcher (brute_force/bfloat16_brute_force.cc): bf16 rows, MIPS only
-    if (!d->bf16_dataset) return fail(SCANN_B200_UNIMPLEMENTED, "brute force is implemented for bfloat16 datasets only (bfloat16_dataset.npy)");
-    if (d->distance != SCANN_B200_DOT_PRODUCT) return fail(SCANN_B200_UNIMPLEMENTED, "bfloat16 brute force supports dot product distance only");
+    // Bfloat16BruteForceSearcher (brute_force/bfloat16_brute_force.cc) or BruteForceSearcher<float>
+    // (brute_force/brute_force.cc:376-393): MIPS only
+    if (!d->bf16_dataset && !d->dataset) return fail(SCANN_B200_INVALID_ARGUMENT, "brute force needs dataset or bf16_dataset");
+    if (d->distance != SCANN_B200_DOT_PRODUCT) return fail(SCANN_B200_UNIMPLEMENTED, "brute force supports dot product distance only");
     // row-sharded brute force: rank r keeps the contiguous rows [r * ceil(N / world), ...) and reports global ids
     const int world_bf = d->shard_world > 0 ? d->shard_world : 1;
     const int rank_bf = d->shard_rank;
@@ -137,6 +139,19 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     vb.distance = d->distance; vb.n = nloc; vb.d = D; vb.disjoint = 1;
     ix->brute = true;
     ix->bf_row0 = row0;
+    if (!d->bf16_dataset) {
+      // float rows: kept as they are for the exact re-scoring, plus the bf16 GEMM operand [hi | hi | lo]
+      // (K = 3D padded to 64; the queries are [hi | lo | hi], so one GEMM gives qh.xh + ql.xh + qh.xl)
+      ix->bf_f32 = true;
+      ix->bf_dpitch = sb::tokenize_kpitch(D);
+      CU(ix->dataset.ensure(sizeof(float) * (size_t)std::max<uint32_t>(nloc, 1) * D));
+      if (nloc) CU(cudaMemcpy(ix->dataset.p, d->dataset + (size_t)row0 * D, sizeof(float) * (size_t)nloc * D, cudaMemcpyHostToDevice));
+      CU(ix->bf_db.ensure(sb::tokenize_operand_bytes(std::max<uint32_t>(nloc, 1), D)));
+      CU(sb::build_tokenize_operand(ix->dataset.as<float>(), nloc, D, 2, ix->bf_db.p, 0));
+      CU(cudaStreamSynchronize(0));
+      vb.dataset = ix->dataset.as<float>();
+      return 0;
+    }
     ix->bf_dpitch = (D + 7) / 8 * 8;
     CU(ix->bf_db.ensure((size_t)std::max<uint32_t>(nloc, 1) * ix->bf_dpitch * 2));
     CU(cudaMemset(ix->bf_db.p, 0, (size_t)std::max<uint32_t>(nloc, 1) * ix->bf_dpitch * 2));
@@ -543,7 +558,8 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   const uint32_t kprime = 2 * k + 64;
   if (kprime > 8192) return fail(SCANN_B200_UNIMPLEMENTED, "brute force with k=%u > 4064 is not supported", k);
   const uint32_t cap = pick_cap(kprime);
-  CU(ix->bf_a.ensure(sb::bf_query_operand_bytes(nq, ix->bf_dpitch)));
+  CU(ix->bf_a.ensure(ix->bf_f32 ? (size_t)sb::bf_query_rows_pad(nq) * ix->bf_dpitch * 2 + 256 * (size_t)ix->bf_dpitch * 2
+                                : sb::bf_query_operand_bytes(nq, ix->bf_dpitch)));
   CU(ix->buf.ensure(sizeof(uint64_t) * (size_t)nq * cap));
   CU(ix->cnt.ensure(sizeof(uint32_t) * nq));
   CU(ix->tau.ensure(sizeof(uint64_t) * nq));
@@ -561,7 +577,8 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
   CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
   CU(cudaEventRecord(ix->ev[EV_START], s));
-  CU(sb::bf_split_queries(d_q, nq, v.d, ix->bf_dpitch, ix->bf_a.p, s));
+  if (ix->bf_f32) CU(sb::build_tokenize_operand(d_q, nq, v.d, 1, ix->bf_a.p, s));
+  else CU(sb::bf_split_queries(d_q, nq, v.d, ix->bf_dpitch, ix->bf_a.p, s));
   CU(sb::bf_init_state(nq, w.cnt, w.tau, w.ovf, s));
   launches += 2;
   CU(cudaEventRecord(ix->ev[EV_TOK], s));
@@ -576,7 +593,7 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   const uint32_t growth = 3 * kprime <= 1000 ? 2 : (2 * kprime <= 1000 ? 1 : 2);
   while (row0 < v.n) {
     const uint32_t row1 = (uint64_t)row0 + chunk >= v.n ? v.n : row0 + chunk;
-    CU(sb::bf_gemm_round(ix->bf_a.p, ix->bf_db.p, nq, v.n, ix->bf_dpitch, row0, row1, w, s));
+    CU(sb::bf_gemm_round(ix->bf_a.p, ix->bf_db.p, nq, v.n, ix->bf_dpitch, row0, row1, w, ix->bf_f32 ? 1 : 2, s));
     CU(sb::launch_compact(v, w, false, s));
     launches += 1 + (cap > 1024 ? 2 : 1);
     gemm_launches += 1;
@@ -588,7 +605,10 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   if (hc[2] != 0) return fail(SCANN_B200_INTERNAL, "brute force: candidate buffer overflow (%u queries)", hc[2]);
-  CU(sb::bf_rescore(d_q, ix->bf_db.p, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
+  if (ix->bf_f32)
+    CU(sb::bf_rescore_f32(d_q, v.dataset, nq, v.d, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
+  else
+    CU(sb::bf_rescore(d_q, ix->bf_db.p, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
   launches += 1;
   CU(cudaEventRecord(ix->ev[EV_FIN], s));
   CU(cudaStreamSynchronize(s));

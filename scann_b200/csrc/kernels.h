@@ -107,8 +107,13 @@ cudaError_t launch_merge_topk(int distance, uint32_t nq, int world, int k_in, co
 size_t bf_query_operand_bytes(uint32_t nq, uint32_t dpitch);
 cudaError_t bf_split_queries(const float* q, uint32_t nq, uint32_t d, uint32_t dpitch, void* a_operand, cudaStream_t s);
 cudaError_t bf_init_state(uint32_t nq, uint32_t* cnt, uint64_t* tau, uint32_t* ovf, cudaStream_t s);
+// splits = 2: A holds the hi and lo bf16 terms of the queries as two stacked row blocks (bf16 database);
+// splits = 1: both operands carry their hi/lo terms concatenated along K (float database, see prep.cu)
 cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, uint32_t n_total, uint32_t dpitch,
-                          uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s);
+                          uint32_t row0, uint32_t row1, const ScanWork& w, int splits, cudaStream_t s);
+uint32_t bf_query_rows_pad(uint32_t nq);
+cudaError_t bf_rescore_f32(const float* q, const float* db, uint32_t nq, uint32_t d, const ScanWork& w, uint32_t kprime,
+                           uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s);
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
                        uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist,
                        cudaStream_t s);

@@ -47,8 +47,17 @@ class _Plan:
       raise RuntimeError(f"Error initializing searcher: UNIMPLEMENTED: {what} is outside the scann_b200 hot path")
     if self.autopilot is not None:
       unimpl("autopilot")
+    if self.is_brute_force():
+      # score_brute_force(): BruteForceSearcher<float> / Bfloat16BruteForceSearcher (brute_force/*.cc)
+      if self.distance != "dot_product":
+        unimpl("brute force with a distance other than dot product")
+      if cfgmod.as_bool(self.brute_force.path("fixed_point", "enabled"), False):
+        unimpl("int8 brute force")
+      if self.reordering is not None:
+        unimpl("reordering after brute force")
+      return
     if self.partitioning is None or self.ah is None:
-      unimpl("a searcher without tree() + score_ah()")
+      unimpl("a searcher without tree() + score_ah() or score_brute_force()")
     p, ah = self.partitioning, self.ah
     if p.has("projection") or p.has("bottom_up_top_level_partitioner"):
       unimpl("PCA/truncate projections and upper_tree")
@@ -73,6 +82,12 @@ class _Plan:
         thr = cfgmod.as_float(r.path("bfloat16", "noise_shaping_threshold"), math.nan)
         if thr is not None and not math.isnan(thr):
           unimpl("noise-shaped bfloat16 quantization of the reordering dataset")
+
+  def is_brute_force(self):
+    return self.brute_force is not None and self.partitioning is None and self.ah is None
+
+  def bf16_brute_force(self):
+    return self.is_brute_force() and cfgmod.as_bool(self.brute_force.path("bfloat16", "enabled"), False)
 
   def bf16_reorder(self):
     """exact_reordering { bfloat16 { enabled: true } } (Bfloat16ReorderingHelper, utils/reordering_helper.cc:720-757)."""
@@ -111,6 +126,17 @@ class ScannNumpy:
     plan.check_supported()
     self._config_text = config_text
     db = np.ascontiguousarray(db, dtype=np.float32)
+    if plan.is_brute_force():
+      try:
+        arrays = index_build.IndexArrays(distance=plan.distance, dataset=None, n=db.shape[0], d=db.shape[1])
+        if plan.bf16_brute_force():
+          arrays.bf16_dataset = index_build.bfloat16_quantize(db)   # bfloat16_brute_force.cc:60-75
+        else:
+          arrays.dataset = db
+        self._finish(arrays, plan)
+      except _lib.ScannB200Error as e:
+        raise _runtime("Error initializing searcher: ", e)
+      return
     p, ah = plan.partitioning, plan.ah
     soar = p.path("database_spilling", "spilling_type") in ("TWO_CENTER_ORTHOGONALITY_AMPLIFIED", "SOAR")
     lam = cfgmod.as_float(p.path("database_spilling", "orthogonality_amplification_lambda"), 1.5) if soar else None
@@ -138,8 +164,13 @@ class ScannNumpy:
       raise _runtime("Error initializing searcher: ", e)
 
   def _finish(self, arrays, plan):
-    leaves = cfgmod.as_int(plan.partitioning.path("query_spilling", "max_spill_centers"), arrays.centers.shape[0])
     final_nn = plan.num_neighbors
+    if plan.is_brute_force():
+      self._arrays, self._plan = arrays, plan
+      self._n, self._d = arrays.n, arrays.d
+      self._index = _lib.NativeIndex(arrays, 1, final_nn, final_nn)
+      return
+    leaves = cfgmod.as_int(plan.partitioning.path("query_spilling", "max_spill_centers"), arrays.centers.shape[0])
     pre = cfgmod.as_int(plan.reordering.get("approx_num_neighbors"), final_nn) if plan.reordering is not None else final_nn
     self._arrays = arrays
     self._plan = plan
@@ -204,7 +235,8 @@ class ScannNumpy:
     d = _lib.IndexDesc()
     d.distance = 0 if a.distance == "dot_product" else 1
     d.n, d.d = a.n, a.d
-    d.n_leaves, d.n_blocks, d.dims_per_block = a.centers.shape[0], a.codes.shape[1], a.codebook.shape[2]
+    if a.centers is not None:
+      d.n_leaves, d.n_blocks, d.dims_per_block = a.centers.shape[0], a.codes.shape[1], a.codebook.shape[2]
     d.block_dims = own(a.block_dims, np.int32)
     d.centers = own(a.centers, np.float32)
     d.tokens = own(a.tokens, np.int32)

@@ -97,7 +97,7 @@ def test_docids_and_error_behaviour(tmp_path):
   with pytest.raises(ValueError, match="docid and database size mismatch"):
     scann_ops_pybind.create_searcher(db, "", docids=["a"])
   with pytest.raises(RuntimeError, match="Error initializing searcher: UNIMPLEMENTED"):
-    scann_ops_pybind.builder(db, 5, "dot_product").score_brute_force().build()
+    scann_ops_pybind.builder(db, 5, "squared_l2").score_brute_force().build()   # brute force: dot product only
 
 
 def test_empty_partitions_are_tolerated():

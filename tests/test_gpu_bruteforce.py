@@ -83,3 +83,50 @@ def test_row_sharded_bruteforce_equals_unsharded(world):
                                                      vp(g_ds.data_ptr()), k, vp(o_i.data_ptr()), vp(o_d.data_ptr()), k))
   np.testing.assert_array_equal(o_i.cpu().numpy().view(np.uint32), fi)
   np.testing.assert_array_equal(o_d.cpu().numpy().view(np.uint32), fd.view(np.uint32))
+
+
+# ---- float brute force (BruteForceSearcher<float>, brute_force/brute_force.cc:376-393) ----
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 96, 300, 20), (5000, 768, 130, 100), (700, 40, 5, 10), (30000, 100, 257, 50),
+                                      (3000, 17, 40, 10)])
+def test_float_bruteforce_matches_oracle(n, d, nq, k):
+  import oracle
+  from scann_b200 import _lib, index_build
+  rng = np.random.default_rng(n + d)
+  db = rng.standard_normal((n, d), dtype=np.float32)
+  q = rng.standard_normal((nq, d), dtype=np.float32)
+  a = index_build.IndexArrays(distance="dot_product", dataset=db, n=n, d=d)
+  ix = _lib.NativeIndex(a, 1, k, k)
+  idx, dist = ix.search_batched(q)
+  oi, od = oracle.bruteforce_f32(db, q, k, threads=8)
+  np.testing.assert_array_equal(idx, oi)
+  np.testing.assert_array_equal(dist.view(np.uint32), od.view(np.uint32))
+  truth = np.take_along_axis(q.astype(np.float64) @ db.astype(np.float64).T, idx.astype(np.int64), axis=1)
+  np.testing.assert_allclose(dist, truth, rtol=1e-5, atol=1e-4)
+  gt = np.argsort(-(q.astype(np.float64) @ db.astype(np.float64).T), axis=1)[:, :k]
+  recall = np.mean([len(set(idx[i].tolist()) & set(gt[i].tolist())) / k for i in range(nq)])
+  assert recall > 0.999
+
+
+def test_brute_force_through_the_builder(tmp_path):
+  """score_brute_force() (float) and score_brute_force(ReorderType.BFLOAT16): the reference's own brute-force test
+  (scann_ops_pybind_test.py:79-90,253-264) checks against numpy at rtol 1e-6 / 1e-5."""
+  from scann_b200 import scann_ops_pybind, scann_builder
+  rng = np.random.default_rng(0)
+  db = rng.random((2000, 32), dtype=np.float32)
+  q = rng.random((20, 32), dtype=np.float32)
+  s = scann_ops_pybind.builder(db, 10, "dot_product").score_brute_force().build()
+  idx, dist = s.search_batched(q)
+  full = q.astype(np.float64) @ db.astype(np.float64).T
+  np.testing.assert_array_equal(idx, np.argsort(-full, axis=1)[:, :10].astype(np.uint32))
+  np.testing.assert_allclose(dist, np.take_along_axis(full, idx.astype(np.int64), axis=1), rtol=1e-5)
+  (tmp_path / "f32").mkdir()
+  s.serialize(str(tmp_path / "f32"))
+  assert (tmp_path / "f32" / "dataset.npy").exists()
+  l2 = scann_ops_pybind.load_searcher(str(tmp_path / "f32"))
+  i2, d2 = l2.search_batched(q)
+  np.testing.assert_array_equal(idx, i2)
+  np.testing.assert_array_equal(dist.view(np.uint32), d2.view(np.uint32))
+  b = scann_ops_pybind.builder(db, 10, "dot_product").score_brute_force(scann_builder.ReorderType.BFLOAT16).build()
+  ib, dbf = b.search_batched(q)
+  assert np.mean(ib == idx) > 0.9
+  np.testing.assert_allclose(dbf, np.take_along_axis(full, ib.astype(np.int64), axis=1), rtol=2e-2)
