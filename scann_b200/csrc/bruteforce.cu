@@ -143,6 +143,7 @@ __device__ __forceinline__ void filter_tile(const GemmArgs& a, uint32_t tbase, u
     uint32_t m = (m0 | m1) | (m2 | m3);
     const uint32_t col = n0 + c * 32;  // columns past the end of this round's rows do not exist
     if (col + 32 > a.row1) m &= col < a.row1 ? (0xFFFFFFFFu >> (32 - (a.row1 - col))) : 0u;
+    if (!qvalid) m = 0u;  // padding rows of the A operand: an inf/NaN accumulator must not reserve slots
     masks[c * 128] = m;
     total += __popc(m);
   }

@@ -577,7 +577,13 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
   CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
   CU(cudaEventRecord(ix->ev[EV_START], s));
-  if (ix->bf_f32) CU(sb::build_tokenize_operand(d_q, nq, v.d, 1, ix->bf_a.p, s));
+  if (ix->bf_f32) {
+    // the GEMM walks bf_query_rows_pad(nq) rows; the split kernel writes ceil(nq / 128) * 128 of them
+    const size_t written = (size_t)((nq + 127) / 128 * 128) * ix->bf_dpitch * 2;
+    const size_t walked = (size_t)sb::bf_query_rows_pad(nq) * ix->bf_dpitch * 2;
+    if (walked > written) CU(cudaMemsetAsync(static_cast<char*>(ix->bf_a.p) + written, 0, walked - written, s));
+    CU(sb::build_tokenize_operand(d_q, nq, v.d, 1, ix->bf_a.p, s));
+  }
   else CU(sb::bf_split_queries(d_q, nq, v.d, ix->bf_dpitch, ix->bf_a.p, s));
   CU(sb::bf_init_state(nq, w.cnt, w.tau, w.ovf, s));
   launches += 2;
