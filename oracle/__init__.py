@@ -220,3 +220,78 @@ def bruteforce_f32(db, q, k, threads=1):
   if rc:
     raise RuntimeError(L.so_last_error().decode())
   return idx, dist
+
+
+# ---- index build, deterministic part ----
+
+def assign_primary(x, centers, threads=1):
+  """Database tokenization: nearest centre under squared L2 -> (token [N] i32, distance [N] f32)."""
+  L = lib()
+  L.so_assign_primary.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  c = np.ascontiguousarray(centers, dtype=np.float32)
+  tok = np.empty(x.shape[0], np.int32)
+  dist = np.empty(x.shape[0], np.float32)
+  rc = L.so_assign_primary(_p(x), x.shape[0], x.shape[1], _p(c), c.shape[0], _p(tok), _p(dist), threads)
+  if rc:
+    raise RuntimeError(L.so_last_error().decode())
+  return tok, dist
+
+
+def assign_soar(x, centers, primary, lam, threads=1):
+  """SOAR secondary assignment -> (token [N] i32, cost [N] f32); the token may equal the primary."""
+  L = lib()
+  L.so_assign_soar.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_float,
+                               C.c_void_p, C.c_void_p, C.c_int]
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  c = np.ascontiguousarray(centers, dtype=np.float32)
+  p = np.ascontiguousarray(primary, dtype=np.int32)
+  tok = np.empty(x.shape[0], np.int32)
+  cost = np.empty(x.shape[0], np.float32)
+  rc = L.so_assign_soar(_p(x), x.shape[0], x.shape[1], _p(c), c.shape[0], _p(p), float(lam), _p(tok), _p(cost), threads)
+  if rc:
+    raise RuntimeError(L.so_last_error().decode())
+  return tok, cost
+
+
+def encode(x, codebook, block_dims=None, centers=None, token=None, threshold=float("nan"), threads=1):
+  """AH codes [N, B] u8 of x (centers None) or of x - centers[token]; threshold NaN = plain nearest-centre hash."""
+  L = lib()
+  L.so_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32,
+                          C.c_void_p, C.c_double, C.c_void_p, C.c_int]
+  L.so_last_encode_ties.restype = C.c_uint64
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  cb = np.ascontiguousarray(codebook, dtype=np.float32)
+  bd = None if block_dims is None else np.ascontiguousarray(block_dims, dtype=np.int32)
+  c = None if centers is None else np.ascontiguousarray(centers, dtype=np.float32)
+  t = None if token is None else np.ascontiguousarray(token, dtype=np.int32)
+  out = np.empty((x.shape[0], cb.shape[0]), np.uint8)
+  rc = L.so_encode(_p(x), x.shape[0], x.shape[1], _p(c), _p(t), _p(cb), cb.shape[0], cb.shape[2], _p(bd),
+                   float(threshold), _p(out), threads)
+  if rc:
+    raise RuntimeError(L.so_last_error().decode())
+  return out, int(L.so_last_encode_ties())
+
+
+def encode_database(x, centers, codebook, block_dims=None, residual=True, soar_lambda=None,
+                    threshold=float("nan"), threads=1):
+  """The whole deterministic build stage in the serialized layout (scann_ops/cc/scann.cc:533-566):
+  tokens [N] or [2N] (slot 2i = lower-numbered leaf, 2i+1 = the other leaf or -1), codes, soar_codes."""
+  n = x.shape[0]
+  prim, _ = assign_primary(x, centers, threads)
+  cen = centers if residual else None
+  if soar_lambda is None:
+    codes, _ = encode(x, codebook, block_dims, cen, prim, threshold, threads)
+    return prim, codes, None
+  if not residual:
+    raise ValueError("SOAR is defined for residual (dot product) tree-AH only (scann_builder.py:170-172)")
+  sec, _ = assign_soar(x, centers, prim, soar_lambda, threads)
+  spilled = sec != prim
+  lo = np.where(spilled, np.minimum(prim, sec), prim).astype(np.int32)
+  hi = np.where(spilled, np.maximum(prim, sec), -1).astype(np.int32)
+  tokens = np.empty(2 * n, np.int32)
+  tokens[0::2] = lo
+  tokens[1::2] = hi
+  codes, _ = encode(x, codebook, block_dims, cen, lo, threshold, threads)
+  soar_codes, _ = encode(x, codebook, block_dims, cen, hi, threshold, threads)
+  return tokens, codes, soar_codes

@@ -1068,3 +1068,294 @@ int so_bruteforce_f32(const float* db, uint32_t n, uint32_t d, const float* q, u
   }
   return 0;
 }
+
+/* ========================================================================= */
+/* index build, deterministic part: database             */
+/* tokenization, SOAR secondary assignment, residuals, AH encoding.            */
+/* Given the trained centres and codebook these are pure functions of the      */
+/* inputs; the trainers themselves (k-means, codebooks) are random-initialised */
+/* and out of scope.                                                            */
+/* ========================================================================= */
+
+static __thread uint64_t g_encode_ties;
+uint64_t so_last_encode_ties(void) { return g_encode_ties; }
+
+/* KMeansTreePartitioner::TokenizeDatabaseImplFastPath / TokenForDatapointBatchedImpl
+ * (partitioning/kmeans_tree_partitioner.cc:561-612,903-923) -> DenseDistanceManyToManyTop1 with
+ * SquaredL2Distance (the builder's partitioning distance, scann_builder.py:213-238):
+ * acc = ||c||^2 + ||x||^2, then acc = fnmadd(x[dim], 2 c[dim], acc) sequentially in dim
+ * (many_to_many_impl.inc:236-257,522-567), ManyToManyTop1Callback keeps the first strict minimum
+ * (many_to_many_common.h:176-199) = argmin by (distance, centre index). */
+static void l2_center_distances(const float* x, const float* centers_t, const float* cnorm, uint32_t L, uint32_t D, float* out) {
+  double qn = 0.0;
+  for (uint32_t k = 0; k < D; ++k) qn += (double)x[k] * (double)x[k];
+  const float qnf = (float)qn;
+  for (uint32_t l = 0; l < L; ++l) out[l] = cnorm[l] + qnf;
+  for (uint32_t k = 0; k < D; ++k) {
+    const float nq = -x[k];
+    const float* c = centers_t + (size_t)k * L;
+    for (uint32_t l = 0; l < L; ++l) { float c2 = c[l] * 2.0f; out[l] = fmaf(nq, c2, out[l]); }
+  }
+}
+
+static void transpose_centers(const float* centers, uint32_t L, uint32_t D, float* ct, float* cnorm) {
+  for (uint32_t l = 0; l < L; ++l)
+    for (uint32_t k = 0; k < D; ++k) ct[(size_t)k * L + l] = centers[(size_t)l * D + k];
+  for (uint32_t l = 0; l < L; ++l) {
+    float a = 0.0f;
+    for (uint32_t k = 0; k < D; ++k) { float c = centers[(size_t)l * D + k]; a = fmaf(-c, c, a); }
+    cnorm[l] = a * -1.0f;
+  }
+}
+
+int so_assign_primary(const float* x, uint32_t n, uint32_t d, const float* centers, uint32_t L, int32_t* out_tok,
+                      float* out_dist, int threads) {
+  if (!L || !d) return fail("so_assign_primary: empty centres");
+  float* ct = (float*)malloc(sizeof(float) * (size_t)L * d);
+  float* cn = (float*)malloc(sizeof(float) * L);
+  transpose_centers(centers, L, d, ct, cn);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads > 1 ? threads : 1)
+#endif
+  {
+    float* dist = (float*)malloc(sizeof(float) * L);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (uint32_t i = 0; i < n; ++i) {
+      l2_center_distances(x + (size_t)i * d, ct, cn, L, d, dist);
+      uint32_t best = 0;
+      for (uint32_t l = 1; l < L; ++l) if (dist[l] < dist[best]) best = l;
+      out_tok[i] = (int32_t)best;
+      if (out_dist) out_dist[i] = dist[best];
+    }
+    free(dist);
+  }
+  free(ct); free(cn);
+  return 0;
+}
+
+/* ComputeNormalizedResidual (partitioning/orthogonality_amplification_utils.h:27-46). */
+static void normalized_residual(const float* x, const float* c, uint32_t d, float* out) {
+  double sqnorm = 0.0;
+  for (uint32_t i = 0; i < d; ++i) {
+    out[i] = (float)((double)x[i] - (double)c[i]);
+    sqnorm += (double)out[i] * (double)out[i];
+  }
+  if (sqnorm < 1e-7) { for (uint32_t i = 0; i < d; ++i) out[i] = 0.0f; return; }
+  const float inv_norm = (float)(1.0 / sqrt(sqnorm));
+  for (uint32_t i = 0; i < d; ++i) out[i] = out[i] * inv_norm;
+}
+
+/* KMeansTreePartitioner::OrthogonalityAmplifiedTokenForDatapointBatched
+ * (partitioning/kmeans_tree_partitioner.cc:925-997) -> DenseManyToManyOrthogonalityAmplified
+ * (distance_measures/many_to_many/many_to_many_impl.inc:729-781), float:
+ *   diff = x[dim] - c[dim]; t1 = fma(diff, diff, t1); t2 = fma(diff, rhat[dim], t2)   sequentially in dim
+ *   cost = t1 + (lambda * t2) * t2
+ * over ALL centres (the primary is not excluded; a datapoint whose secondary equals its primary is
+ * simply not spilled, kmeans_tree_partitioner.cc:527-531), first strict minimum. */
+int so_assign_soar(const float* x, uint32_t n, uint32_t d, const float* centers, uint32_t L, const int32_t* primary,
+                   float lambda, int32_t* out_tok, float* out_cost, int threads) {
+  if (!L || !d) return fail("so_assign_soar: empty centres");
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads > 1 ? threads : 1)
+#endif
+  {
+    float* rhat = (float*)malloc(sizeof(float) * d);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (uint32_t i = 0; i < n; ++i) {
+      const float* xi = x + (size_t)i * d;
+      normalized_residual(xi, centers + (size_t)primary[i] * d, d, rhat);
+      uint32_t best = 0;
+      float best_cost = INFINITY;
+      for (uint32_t l = 0; l < L; ++l) {
+        const float* c = centers + (size_t)l * d;
+        float t1 = 0.0f, t2 = 0.0f;
+        for (uint32_t k = 0; k < d; ++k) {
+          const float diff = xi[k] - c[k];
+          t1 = fmaf(diff, diff, t1);
+          t2 = fmaf(diff, rhat[k], t2);
+        }
+        const float lt = lambda * t2;
+        const float q = lt * t2;
+        const float cost = t1 + q;
+        if (cost < best_cost) { best_cost = cost; best = l; }
+      }
+      out_tok[i] = (int32_t)best;
+      if (out_cost) out_cost[i] = best_cost;
+    }
+    free(rhat);
+  }
+  return 0;
+}
+
+/* DenseSingleAccumulate with l2_distance_internal::Square (utils/reduction.h:357-390,
+ * distance_measures/one_to_one/l2_distance.h:57-63,108-111): SquaredL2Norm(DatapointPtr<float>) in double. */
+static double squared_l2_norm_f64(const float* v, uint32_t n) {
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  uint32_t i = 0;
+  for (; i + 4 <= n; i += 4) {
+    r0 += (double)v[i] * (double)v[i];
+    r1 += (double)v[i + 1] * (double)v[i + 1];
+    r2 += (double)v[i + 2] * (double)v[i + 2];
+    r3 += (double)v[i + 3] * (double)v[i + 3];
+  }
+  r2 += r3;
+  if (i + 2 <= n) {
+    r0 += (double)v[i] * (double)v[i];
+    r1 += (double)v[i + 1] * (double)v[i + 1];
+    i += 2;
+  }
+  r1 += r2;
+  if (i < n) r0 += (double)v[i] * (double)v[i];
+  return r0 + r1;
+}
+
+/* One (datapoint, token) pair.
+ *   threshold NaN : Indexer::Hash -> AhImpl::IndexDatapoint (hashes/internal/asymmetric_hashing_impl.cc:199-244):
+ *                   per block DenseDistanceOneToMany(SquaredL2) to the 16 centres, std::min_element (first minimum).
+ *   otherwise     : Indexer::HashWithNoiseShaping -> AhImpl::IndexDatapointNoiseShaped (:434-503) with
+ *                   ComputeResidualStats (:292-340), ComputeParallelCostMultiplier (:258-265),
+ *                   InitializeToMinResidualNorm (:342-355), OptimizeSingleSubspace (:376-412); all in double,
+ *                   compiled without FMA (no -mfma outside the SCANN_AVX2 functions).
+ * `res` is the vector that is hashed (the residual for TreeAHHybridResidual,
+ * tree_ah_hybrid_residual.cc:414-428), `orig` the original datapoint.
+ * The blocks are visited in descending order of their initial residual norm (ZipSortBranchOptimized with
+ * std::greater, :466-476); that sort is not stable, so equal norms (never seen on continuous data; counted in
+ * *ties) are ordered here by ascending block index. */
+static void encode_one(const float* res, const float* orig, uint32_t D, const float* codebook, uint32_t B, uint32_t S,
+                       const int32_t* block_dims, const uint32_t* block_off, double threshold, uint8_t* out,
+                       double* stat_norm, double* stat_par, uint64_t* ties) {
+  if (isnan(threshold)) {
+    float dist[16];
+    for (uint32_t b = 0; b < B; ++b) {
+      one_to_many(SO_SQUARED_L2, res + block_off[b], codebook + (size_t)b * 16 * S, 16, S, (uint32_t)block_dims[b], dist);
+      uint32_t best = 0;
+      for (uint32_t c = 1; c < 16; ++c) if (dist[c] < dist[best]) best = c;
+      out[b] = (uint8_t)best;
+    }
+    return;
+  }
+  /* ComputeResidualStats: chunked norm of the original, then per (block, centre) residual norm and the
+   * component of the quantisation residual parallel to the original. */
+  double chunked_norm = 0.0;
+  for (uint32_t k = 0; k < D; ++k) { const double v = (double)orig[k]; chunked_norm += v * v; }
+  chunked_norm = sqrt(chunked_norm);
+  const double inv_norm = 1.0 / chunked_norm;
+  for (uint32_t b = 0; b < B; ++b) {
+    const uint32_t nd = (uint32_t)block_dims[b];
+    for (uint32_t c = 0; c < 16; ++c) {
+      const float* cen = codebook + ((size_t)b * 16 + c) * S;
+      double rn = 0.0, par = 0.0;
+      for (uint32_t k = 0; k < nd; ++k) {
+        const double rc = (double)res[block_off[b] + k] - (double)cen[k];
+        const double sq = rc * rc;
+        rn += sq;
+        const double p0 = rc * (double)orig[block_off[b] + k];
+        const double p1 = p0 * inv_norm;
+        par += p1;
+      }
+      stat_norm[b * 16 + c] = rn;
+      stat_par[b * 16 + c] = par;
+    }
+  }
+  /* ComputeParallelCostMultiplier(threshold, SquaredL2Norm(original), dims) */
+  const double sqn = squared_l2_norm_f64(orig, D);
+  const double t2 = threshold * threshold;
+  const double parallel_cost = t2 / sqn;
+  const double perpendicular_cost = (1.0 - t2 / sqn) / ((double)D - 1.0);
+  const double mult = parallel_cost / perpendicular_cost;
+  uint8_t code[256];
+  uint16_t order[256];
+  double norm0[256];
+  for (uint32_t b = 0; b < B; ++b) {
+    uint32_t best = 0;
+    for (uint32_t c = 1; c < 16; ++c) if (stat_norm[b * 16 + c] < stat_norm[b * 16 + best]) best = c;
+    code[b] = (uint8_t)best;
+  }
+  double par = 0.0;
+  for (uint32_t b = 0; b < B; ++b) par += stat_par[b * 16 + code[b]];
+  for (uint32_t b = 0; b < B; ++b) { norm0[b] = stat_norm[b * 16 + code[b]]; order[b] = (uint16_t)b; }
+  /* descending norm, ties by ascending block (insertion sort: B <= 256) */
+  int tie = 0;
+  for (uint32_t i = 1; i < B; ++i) {
+    const uint16_t v = order[i];
+    uint32_t j = i;
+    while (j > 0 && norm0[order[j - 1]] < norm0[v]) { order[j] = order[j - 1]; --j; }
+    order[j] = v;
+  }
+  for (uint32_t i = 1; i < B; ++i) if (norm0[order[i]] == norm0[order[i - 1]]) tie = 1;
+  if (tie && ties) ++*ties;
+  int changes = 1;
+  for (int round = 0; changes && round < 10; ++round) {
+    changes = 0;
+    for (uint32_t i = 0; i < B; ++i) {
+      const uint32_t b = order[i];
+      const uint8_t cur = code[b];
+      const double old_norm = stat_norm[b * 16 + cur], old_par = stat_par[b * 16 + cur];
+      uint8_t best = cur;
+      double best_delta = 0.0, best_par = par;
+      for (uint32_t c = 0; c < 16; ++c) {
+        if (c == cur) continue;
+        const double d0 = par - old_par;
+        const double new_par = d0 + stat_par[b * 16 + c];
+        const double a2 = new_par * new_par, b2 = par * par;
+        const double par_delta = a2 - b2;
+        if (par_delta > 0.0) continue;
+        const double norm_delta = stat_norm[b * 16 + c] - old_norm;
+        const double perp_delta = norm_delta - par_delta;
+        const double m0 = mult * par_delta;
+        const double cost_delta = m0 + perp_delta;
+        if (cost_delta < best_delta) { best = (uint8_t)c; best_delta = cost_delta; best_par = new_par; }
+      }
+      if (best != cur) { par = best_par; code[b] = best; changes = 1; }
+    }
+  }
+  for (uint32_t b = 0; b < B; ++b) out[b] = code[b];
+}
+
+/* Codes of n (datapoint, token) pairs: row i hashes x[i] - centers[token[i]] (centers != NULL: residual
+ * quantisation, TreeAHHybridResidual::ComputeResiduals tree_ah_hybrid_residual.cc:189-212, float subtraction)
+ * or x[i] itself (centers == NULL).  out is [n][B], one code per byte. */
+int so_encode(const float* x, uint32_t n, uint32_t d, const float* centers, const int32_t* token, const float* codebook,
+              uint32_t B, uint32_t S, const int32_t* block_dims_in, double threshold, uint8_t* out, int threads) {
+  if (!B || B > 256) return fail("so_encode: 1 <= B <= 256");
+  int32_t* bd = (int32_t*)malloc(sizeof(int32_t) * B);
+  uint32_t* bo = (uint32_t*)malloc(sizeof(uint32_t) * (B + 1));
+  bo[0] = 0;
+  for (uint32_t b = 0; b < B; ++b) { bd[b] = block_dims_in ? block_dims_in[b] : (int32_t)S; bo[b + 1] = bo[b] + (uint32_t)bd[b]; }
+  if (bo[B] != d) {
+    const uint32_t got = bo[B];
+    free(bd); free(bo);
+    return fail("so_encode: block dims sum to %u, expected %u", got, d);
+  }
+  uint64_t ties_total = 0;
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads > 1 ? threads : 1) reduction(+ : ties_total)
+#endif
+  {
+    float* res = (float*)malloc(sizeof(float) * d);
+    double* sn = (double*)malloc(sizeof(double) * B * 16);
+    double* sp = (double*)malloc(sizeof(double) * B * 16);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+    for (uint32_t i = 0; i < n; ++i) {
+      const float* xi = x + (size_t)i * d;
+      const float* r = xi;
+      if (centers && token[i] >= 0) {
+        const float* c = centers + (size_t)token[i] * d;
+        for (uint32_t k = 0; k < d; ++k) res[k] = xi[k] - c[k];
+        r = res;
+      }
+      if (centers && token[i] < 0) { memset(out + (size_t)i * B, 0, B); continue; }
+      encode_one(r, xi, d, codebook, B, S, bd, bo, threshold, out + (size_t)i * B, sn, sp, &ties_total);
+    }
+    free(res); free(sn); free(sp);
+  }
+  g_encode_ties = ties_total;
+  free(bd); free(bo);
+  return 0;
+}
