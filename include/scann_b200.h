@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SCANN_B200_ABI_VERSION 2
+#define SCANN_B200_ABI_VERSION 3
 
 enum { SCANN_B200_DOT_PRODUCT = 0, SCANN_B200_SQUARED_L2 = 1 };
 
@@ -118,6 +118,49 @@ int scann_b200_merge_topk_device(scann_b200_index* index, uint32_t nq, int32_t w
 
 const char* scann_b200_last_error(void);
 int scann_b200_abi_version(void);
+
+/* ---- index construction, deterministic part ---- */
+
+/*
+ * What builder(...).build() does to every datapoint once the partitioner and the AH codebook are trained:
+ *   database tokenization   KMeansTreePartitioner::TokenizeDatabase (partitioning/kmeans_tree_partitioner.cc:475-560)
+ *                           -> DenseDistanceManyToManyTop1 under SquaredL2Distance (scann_builder.py:213-238)
+ *   SOAR secondary leaf     OrthogonalityAmplifiedTokenForDatapointBatched (:925-997),
+ *                           DenseManyToManyOrthogonalityAmplified (distance_measures/many_to_many/many_to_many_impl.inc:729-781)
+ *   residual + AH codes     TreeAHHybridResidual::BuildLeafSearchers (tree_x_hybrid/tree_ah_hybrid_residual.cc:395-428)
+ *                           -> Indexer::Hash / HashWithNoiseShaping (hashes/asymmetric_hashing2/indexing.cc:87-246,
+ *                           hashes/internal/asymmetric_hashing_impl.cc:199-244,434-503)
+ * Host pointers in, host pointers out, in the serialized-asset layouts of scann_b200_index_desc.
+ */
+typedef struct {
+  uint32_t n, d;                   /* datapoints, dimensionality */
+  uint32_t n_leaves;               /* L */
+  uint32_t n_blocks;               /* B <= 256 */
+  uint32_t dims_per_block;         /* row stride of `codebook` */
+  const int32_t* block_dims;       /* [B] real dims per block (must sum to d), NULL => all dims_per_block */
+  const float* dataset;            /* [N][D] */
+  const float* centers;            /* [L][D] trained partition centres */
+  const float* codebook;           /* [B][16][dims_per_block] trained AH centres */
+  int32_t residual;                /* 1: hash x - centre[token] (use_residual_quantization, dot product); 0: hash x */
+  float soar_lambda;               /* orthogonality_amplification_lambda; NaN = no database spilling */
+  double noise_shaping_threshold;  /* AsymmetricHasherConfig.noise_shaping_threshold; NaN = Indexer::Hash */
+  int32_t device;
+} scann_b200_encode_desc;
+
+typedef struct {
+  float ms_tokenize, ms_soar, ms_encode, ms_total; /* CUDA events; ms_total includes the host <-> device copies */
+  uint64_t soar_evaluated;      /* exact SOAR cost evaluations (the reference evaluates N * L) */
+  uint64_t spilled;             /* datapoints whose secondary leaf differs from the primary */
+  uint64_t norm_ties;           /* noise shaping: datapoints whose initial block norms tie (visiting order unspecified in the reference) */
+  uint64_t tokenize_fallbacks;  /* rows whose tensor-core tokenization pre-filter fell back to exact distances */
+  uint32_t chunk_rows;          /* rows processed per pass */
+} scann_b200_encode_stats;
+
+/* tokens_out: [N] i32, or [2N] with SOAR (slot 2i = lower-numbered leaf, 2i + 1 = the other leaf or -1:
+ * scann_ops/cc/scann.cc:533-551); codes_out [N][B] (the code of slot 2i's leaf); soar_codes_out [N][B] (slot 2i + 1,
+ * zero when not spilled; required with SOAR, else ignored).  stats may be NULL. */
+int scann_b200_encode_database(const scann_b200_encode_desc* desc, int32_t* tokens_out, uint8_t* codes_out,
+                               uint8_t* soar_codes_out, scann_b200_encode_stats* stats);
 
 /* ---- serialized assets (the reference's on-disk format) ---- */
 

@@ -276,13 +276,14 @@ def encode(x, codebook, block_dims=None, centers=None, token=None, threshold=flo
 def encode_database(x, centers, codebook, block_dims=None, residual=True, soar_lambda=None,
                     threshold=float("nan"), threads=1):
   """The whole deterministic build stage in the serialized layout (scann_ops/cc/scann.cc:533-566):
-  tokens [N] or [2N] (slot 2i = lower-numbered leaf, 2i+1 = the other leaf or -1), codes, soar_codes."""
+  tokens [N] or [2N] (slot 2i = lower-numbered leaf, 2i+1 = the other leaf or -1), codes, soar_codes, and the number
+  of (datapoint, leaf) pairs whose initial block norms tie (so_last_encode_ties)."""
   n = x.shape[0]
   prim, _ = assign_primary(x, centers, threads)
   cen = centers if residual else None
   if soar_lambda is None:
-    codes, _ = encode(x, codebook, block_dims, cen, prim, threshold, threads)
-    return prim, codes, None
+    codes, ties = encode(x, codebook, block_dims, cen, prim, threshold, threads)
+    return prim, codes, None, ties
   if not residual:
     raise ValueError("SOAR is defined for residual (dot product) tree-AH only (scann_builder.py:170-172)")
   sec, _ = assign_soar(x, centers, prim, soar_lambda, threads)
@@ -292,6 +293,6 @@ def encode_database(x, centers, codebook, block_dims=None, residual=True, soar_l
   tokens = np.empty(2 * n, np.int32)
   tokens[0::2] = lo
   tokens[1::2] = hi
-  codes, _ = encode(x, codebook, block_dims, cen, lo, threshold, threads)
-  soar_codes, _ = encode(x, codebook, block_dims, cen, hi, threshold, threads)
-  return tokens, codes, soar_codes
+  codes, ties0 = encode(x, codebook, block_dims, cen, lo, threshold, threads)
+  soar_codes, ties1 = encode(x, codebook, block_dims, cen, hi, threshold, threads)
+  return tokens, codes, soar_codes, ties0 + ties1

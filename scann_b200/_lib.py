@@ -43,6 +43,26 @@ class Stats(C.Structure):
     return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class EncodeDesc(C.Structure):
+  _fields_ = [
+      ("n", C.c_uint32), ("d", C.c_uint32), ("n_leaves", C.c_uint32), ("n_blocks", C.c_uint32),
+      ("dims_per_block", C.c_uint32), ("block_dims", C.c_void_p), ("dataset", C.c_void_p),
+      ("centers", C.c_void_p), ("codebook", C.c_void_p), ("residual", C.c_int32),
+      ("soar_lambda", C.c_float), ("noise_shaping_threshold", C.c_double), ("device", C.c_int32),
+  ]
+
+
+class EncodeStats(C.Structure):
+  _fields_ = [
+      ("ms_tokenize", C.c_float), ("ms_soar", C.c_float), ("ms_encode", C.c_float), ("ms_total", C.c_float),
+      ("soar_evaluated", C.c_uint64), ("spilled", C.c_uint64), ("norm_ties", C.c_uint64),
+      ("tokenize_fallbacks", C.c_uint64), ("chunk_rows", C.c_uint32),
+  ]
+
+  def as_dict(self):
+    return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 EXPORTS = [
     "scann_b200_index_create", "scann_b200_index_destroy", "scann_b200_search_batched",
     "scann_b200_search_batched_device", "scann_b200_search_partial_device",
@@ -52,7 +72,7 @@ EXPORTS = [
     "scann_b200_debug_candidates", "scann_b200_leaf_size", "scann_b200_last_stats",
     "scann_b200_assets_load", "scann_b200_assets_free", "scann_b200_assets_describe",
     "scann_b200_assets_config", "scann_b200_assets_save", "scann_b200_config_text_to_binary",
-    "scann_b200_config_binary_to_text",
+    "scann_b200_config_binary_to_text", "scann_b200_encode_database",
 ]
 
 
@@ -97,6 +117,7 @@ def lib():
   L.scann_b200_assets_save.argtypes = [C.c_char_p, C.POINTER(IndexDesc), C.c_char_p, C.c_int, C.c_char_p, C.c_size_t]
   L.scann_b200_config_text_to_binary.argtypes = [C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
   L.scann_b200_config_binary_to_text.argtypes = [vp, C.c_size_t, C.c_char_p, C.c_size_t]
+  L.scann_b200_encode_database.argtypes = [C.POINTER(EncodeDesc), vp, vp, vp, C.POINTER(EncodeStats)]
   _LIB = L
   return L
 
@@ -243,3 +264,31 @@ class NativeIndex:
     check(lib().scann_b200_debug_candidates(self._h, ptr(q), nq, pre_nn, leaves, cap, ptr(leaf), ptr(slot),
                                             ptr(dp), ptr(score), ptr(cnt)))
     return dict(leaf=leaf, slot=slot, dp=dp, score=score, count=cnt)
+
+
+def encode_database(dataset, centers, codebook, block_dims=None, residual=True, soar_lambda=None,
+                    noise_shaping_threshold=float("nan"), device=0):
+  """scann_b200_encode_database: database tokenization, SOAR secondary assignment and AH encoding on the GPU.
+
+  Returns (tokens [N] or [2N] i32, codes [N, B] u8, soar_codes [N, B] u8 or None, stats dict) in the
+  serialized-asset layout (datapoint_to_token.npy, hashed_dataset.npy, hashed_dataset_soar.npy)."""
+  x = np.ascontiguousarray(dataset, dtype=np.float32)
+  c = np.ascontiguousarray(centers, dtype=np.float32)
+  cb = np.ascontiguousarray(codebook, dtype=np.float32)
+  bd = None if block_dims is None else np.ascontiguousarray(block_dims, dtype=np.int32)
+  n, d = x.shape
+  nb = cb.shape[0]
+  soar = soar_lambda is not None
+  tokens = np.empty(2 * n if soar else n, np.int32)
+  codes = np.empty((n, nb), np.uint8)
+  soar_codes = np.empty((n, nb), np.uint8) if soar else None
+  desc = EncodeDesc()
+  desc.n, desc.d, desc.n_leaves, desc.n_blocks, desc.dims_per_block = n, d, c.shape[0], nb, cb.shape[2]
+  desc.block_dims, desc.dataset, desc.centers, desc.codebook = ptr(bd), ptr(x), ptr(c), ptr(cb)
+  desc.residual = 1 if residual else 0
+  desc.soar_lambda = float(soar_lambda) if soar else float("nan")
+  desc.noise_shaping_threshold = float(noise_shaping_threshold)
+  desc.device = device
+  st = EncodeStats()
+  check(lib().scann_b200_encode_database(C.byref(desc), ptr(tokens), ptr(codes), ptr(soar_codes), C.byref(st)))
+  return tokens, codes, soar_codes, st.as_dict()

@@ -208,11 +208,21 @@ def bfloat16_quantize(x):
 def build_tree_ah(db, distance="dot_product", num_leaves=100, dims_per_block=2,
                   training_sample_size=100000, tree_iters=12, ah_iters=10,
                   soar_lambda=None, overretrieve=2.0, spherical=False,
-                  seed=0, device=None, keep_dataset=True):
-  """tree().score_ah() index: returns IndexArrays (the serialized asset set)."""
+                  seed=0, device=None, keep_dataset=True, noise_shaping_threshold=float("nan"),
+                  native_encode=None):
+  """tree().score_ah() index: returns IndexArrays (the serialized asset set).
+
+  Training (k-means tree, AH codebooks) is torch; the per-datapoint stage -- database tokenization, SOAR
+  secondary assignment, residuals, AH encoding incl. noise shaping -- runs through the C ABI
+  (`scann_b200_encode_database`, csrc/encode.cu) whenever a CUDA device is present (`native_encode=None`)
+  and reproduces the reference's arithmetic bit for bit.  The torch encoder below it is only what CPU-only
+  test fixtures are generated with: plain nearest-centre codes, primary excluded from the SOAR choice.
+  """
   db = np.ascontiguousarray(db, dtype=np.float32)
   n, d = db.shape
   residual = distance == "dot_product"
+  if soar_lambda is not None and distance != "dot_product":
+    raise ValueError("SOAR requires dot product distance.")
   rng = np.random.default_rng(seed)
   if n > training_sample_size:
     sel = np.sort(rng.choice(n, size=training_sample_size, replace=False))
@@ -222,10 +232,26 @@ def build_tree_ah(db, distance="dot_product", num_leaves=100, dims_per_block=2,
   num_leaves = min(num_leaves, n)
   centers = train_kmeans(sample, num_leaves, iters=tree_iters, seed=seed,
                          spherical=spherical, device=device)
-  tok = tokenize_database(db, centers, device=device)
   arr = IndexArrays(distance=distance, dataset=db if keep_dataset else None, n=n, d=d)
   arr.centers = centers.astype(np.float32)
   arr.residual = residual
+  if native_encode is None:
+    native_encode = torch.cuda.is_available()
+  if native_encode:
+    from scann_b200 import _lib
+    res_s = sample - centers[tokenize_database(sample, centers, device=device)] if residual else sample
+    cb, block_dims = train_ah_codebook(res_s, dims_per_block, iters=ah_iters, seed=seed + 1,
+                                       sample=training_sample_size, device=device)
+    arr.codebook, arr.block_dims = cb, block_dims
+    dev_index = 0 if device is None else (torch.device(device).index or 0)
+    arr.tokens, arr.codes, arr.soar_codes, arr.meta["encode_stats"] = _lib.encode_database(
+        db, arr.centers, cb, block_dims, residual=residual, soar_lambda=soar_lambda,
+        noise_shaping_threshold=noise_shaping_threshold, device=dev_index)
+    if soar_lambda is not None:
+      arr.soar = True
+      arr.overretrieve = float(overretrieve)
+    return arr
+  tok = tokenize_database(db, centers, device=device)
   if residual:
     res = db - centers[tok]
   else:
@@ -235,8 +261,6 @@ def build_tree_ah(db, distance="dot_product", num_leaves=100, dims_per_block=2,
   arr.codebook, arr.block_dims = cb, block_dims
   arr.codes = encode_ah(res, cb, block_dims, device=device)
   if soar_lambda is not None:
-    if distance != "dot_product":
-      raise ValueError("SOAR requires dot product distance.")
     sec = soar_assign(db, centers, tok, lam=soar_lambda, device=device)
     res2 = db - centers[sec]
     arr.soar_codes = encode_ah(res2, cb, block_dims, device=device)

@@ -141,10 +141,9 @@ class ScannNumpy:
     soar = p.path("database_spilling", "spilling_type") in ("TWO_CENTER_ORTHOGONALITY_AMPLIFIED", "SOAR")
     lam = cfgmod.as_float(p.path("database_spilling", "orthogonality_amplification_lambda"), 1.5) if soar else None
     thr = cfgmod.as_float(ah.get("noise_shaping_threshold"), math.nan)
-    if thr is not None and not math.isnan(thr):
-      # anisotropic (noise-shaped) encoding is an index-build feature; the plain
-      # nearest-centre encoder is used and the threshold is recorded in the config only.
-      pass
+    if thr is None:
+      thr = math.nan
+    # the threshold selects Indexer::HashWithNoiseShaping in scann_b200_encode_database (csrc/encode.cu)
     try:
       arrays = index_build.build_tree_ah(
           db, plan.distance, num_leaves=cfgmod.as_int(p.get("num_children")),
@@ -154,7 +153,7 @@ class ScannNumpy:
           ah_iters=cfgmod.as_int(ah.get("max_clustering_iterations"), 10),
           soar_lambda=lam, overretrieve=cfgmod.as_float(p.path("database_spilling", "overretrieve_factor"), 2.0),
           spherical=p.get("partitioning_type", "GENERIC") == "SPHERICAL",
-          keep_dataset=plan.reordering is not None)
+          keep_dataset=plan.reordering is not None, noise_shaping_threshold=thr)
       if plan.bf16_reorder():
         # reordering_helper.cc:729-730: the reordering dataset is Bfloat16QuantizeFloatDataset(original)
         arrays.bf16_dataset = index_build.bfloat16_quantize(db)

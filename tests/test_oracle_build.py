@@ -245,7 +245,7 @@ def test_encode_database_layout_with_soar():
   x, centers = _data(300, 16, 13, 10, noise=1.2)
   bd = np.full(8, 2, np.int32)
   cb = _codebook(8, 2, 11)
-  tokens, codes, soar_codes = oracle.encode_database(x, centers, cb, bd, residual=True, soar_lambda=1.5, threshold=0.2)
+  tokens, codes, soar_codes, _ = oracle.encode_database(x, centers, cb, bd, residual=True, soar_lambda=1.5, threshold=0.2)
   prim, _ = oracle.assign_primary(x, centers)
   sec, _ = oracle.assign_soar(x, centers, prim, 1.5)
   lo, hi = tokens[0::2], tokens[1::2]
