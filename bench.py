@@ -34,8 +34,10 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (n, d, leaves, probe, dims_per_block, reorder, k, nq, generator)
+    # noise = AH noise_shaping_threshold (anisotropic quantization); 0.2 is what the reference documents for
+    # glove-100-angular (docs/example: score_ah(2, anisotropic_quantization_threshold=0.2)).
     "c2_glove_shape": dict(n=1_183_514, d=100, leaves=2000, probe=100, dpb=2, pre=100, k=10, nq=10000,
-                           clusters=8000, normalize=True, seed=3, train_sample=250000),
+                           clusters=8000, normalize=True, seed=3, train_sample=250000, noise=0.2),
     # C3: brute-force MIPS over a bf16 database (BASELINE.json configs[2])
     "c3_bruteforce_bf16": dict(kind="bruteforce", n=1_000_000, d=768, k=100, nq=10000, seed=5),
     # the float sibling (BruteForceSearcher<float>): f32 rows, 3-term bf16 tcgen05 pre-filter + exact fp32 chain
@@ -44,7 +46,7 @@ WORKLOADS = {
     # one bench run can build in minutes; BASELINE.json's C5 is 100M rows / 40k leaves on 8 GPUs.  ~2,500 rows
     # per leaf as in C5; --n / --leaves rescale it.
     "c5_deep_shape": dict(n=20_000_000, d=96, leaves=8000, probe=80, dpb=2, pre=200, k=10, nq=10000,
-                          clusters=80000, normalize=True, seed=9, train_sample=500000, soar=1.5),
+                          clusters=80000, normalize=True, seed=9, train_sample=500000, soar=1.5, noise=0.2),
     "c1_synthetic": dict(n=100_000, d=100, leaves=100, probe=10, dpb=2, pre=100, k=10, nq=10000,
                          clusters=400, normalize=False, seed=1, train_sample=100000),
 }
@@ -89,7 +91,8 @@ def build_arrays(wl, db, device):
   from scann_b200 import index_build
   return index_build.build_tree_ah(db, "dot_product", num_leaves=wl["leaves"], dims_per_block=wl["dpb"],
                                    training_sample_size=wl["train_sample"], tree_iters=12, ah_iters=10,
-                                   soar_lambda=wl.get("soar"), seed=0, device=device)
+                                   soar_lambda=wl.get("soar"), seed=0, device=device,
+                                   noise_shaping_threshold=wl.get("noise", float("nan")))
 
 
 class ClockSampler(threading.Thread):
@@ -198,6 +201,8 @@ def main():
   ap.add_argument("--leaves", type=int, default=0, help="override leaves_to_search")
   ap.add_argument("--clusters", type=int, default=0, help="override the number of mixture components of the synthetic data")
   ap.add_argument("--n", type=int, default=0, help="override the database size (leaves are rescaled to keep rows per leaf)")
+  ap.add_argument("--noise", type=float, default=None,
+                  help="AH noise_shaping_threshold used when the index is built (the reference builder's default is 0.2)")
   ap.add_argument("--cpu-sample", type=int, default=2000)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
@@ -215,6 +220,8 @@ def main():
     wl["clusters"] = args.clusters
   if args.leaves > 0:
     wl["probe"] = args.leaves
+  if args.noise is not None:
+    wl["noise"] = args.noise
 
   import torch
   if wl.get("kind") == "bruteforce":
@@ -381,6 +388,7 @@ def main():
       "config": {"workload": args.workload, "n": wl["n"], "d": wl["d"], "leaves": wl["leaves"],
                  "leaves_to_search": wl["probe"], "ah_blocks": wl["d"] // wl["dpb"], "reorder": wl["pre"],
                  "k": k, "queries_per_step": nq * world, "recall_at_10": rec,
+                 "noise_shaping_threshold": wl.get("noise"),
                  "l2_flush": "256 MiB write between timed steps",
                  "parallelism": f"query-parallel x{world} (one replica and one {nq}-query batch per GPU)",
                  "wall_s_timed_region": wall},

@@ -53,6 +53,8 @@ struct SoarArgs {
   const float* centers;    // [L][D]
   const float* cnorm;      // [L] ||c||^2 (fnmadd chain)
   const float* row;        // [n][L]: x.c (row_is_dot) or squared distances
+  const float* row2;       // [n][L]: rhat.c from the second GEMM, or NULL (no projection pruning)
+  float* rhat;             // [n][D] normalised residuals (written by rhat_kernel, read by soar_kernel)
   const int32_t* near;     // [n][P] nearest centres, sorted by (distance, centre); near[.][0] is the primary
   int32_t* sec;            // [n] out
   unsigned long long* evaluated;  // exact cost evaluations, summed (statistics)
@@ -86,6 +88,28 @@ __device__ __forceinline__ float soar_cost(const float* __restrict__ xs, const f
   return __fadd_rn(t1, __fmul_rn(__fmul_rn(lambda, t2), t2));
 }
 
+// ComputeNormalizedResidual (orthogonality_amplification_utils.h:27-46), one warp per datapoint:
+// out = float(double(x) - double(c)); sqnorm = sequential double sum of out^2; zero if sqnorm < 1e-7, else
+// out *= float(1 / sqrt(sqnorm)).  The rows are the A operand of the second GEMM (rhat . c for every centre).
+__global__ void __launch_bounds__(kSoarThreads)
+rhat_kernel(SoarArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * (kSoarThreads / 32) + warp;
+  if (i >= a.n) return;
+  const float* x = a.x + (size_t)i * a.D;
+  const float* pc = a.centers + (size_t)a.near[(size_t)i * a.P] * a.D;
+  float* out = a.rhat + (size_t)i * a.D;
+  for (uint32_t k = lane; k < a.D; k += 32) out[k] = (float)__dsub_rn((double)x[k], (double)__ldg(pc + k));
+  __syncwarp();
+  double sqnorm = 0.0;
+  if (lane == 0)
+    for (uint32_t k = 0; k < a.D; ++k) sqnorm = __dadd_rn(sqnorm, __dmul_rn((double)out[k], (double)out[k]));
+  sqnorm = __shfl_sync(kFull, sqnorm, 0);
+  const bool degenerate = sqnorm < 1e-7;
+  const float inv_norm = degenerate ? 0.f : (float)(1.0 / sqrt(sqnorm));
+  for (uint32_t k = lane; k < a.D; k += 32) out[k] = degenerate ? 0.f : __fmul_rn(out[k], inv_norm);
+}
+
 __global__ void __launch_bounds__(kSoarThreads)
 soar_kernel(SoarArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -98,30 +122,26 @@ soar_kernel(SoarArgs a) {
   if (i >= a.n) return;
   const float* x = a.x + (size_t)i * a.D;
   const int32_t prim = a.near[(size_t)i * a.P];
-  const float* pc = a.centers + (size_t)prim * a.D;
-  // ComputeNormalizedResidual (orthogonality_amplification_utils.h:27-46)
   float ssq = 0.f;
+  double xr64 = 0.0;  // <x, rhat>: the centre-independent half of the projection <x - c, rhat>
   for (uint32_t k = lane; k < a.D; k += 32) {
-    const float v = x[k];
+    const float v = x[k], r = a.rhat[(size_t)i * a.D + k];
     xs[k] = v;
-    rh[k] = (float)__dsub_rn((double)v, (double)__ldg(pc + k));
+    rh[k] = r;
     ssq = fmaf(v, v, ssq);
+    xr64 = fma((double)v, (double)r, xr64);
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(kFull, ssq, o);
-  __syncwarp();
-  double sqnorm = 0.0, qn64 = 0.0;
-  if (lane == 0) {
-    for (uint32_t k = 0; k < a.D; ++k) sqnorm = __dadd_rn(sqnorm, __dmul_rn((double)rh[k], (double)rh[k]));
-  } else if (lane == 1) {  // ||x||^2 as the tokenizer computes it (sequential double accumulation, narrowed)
-    for (uint32_t k = 0; k < a.D; ++k) qn64 = __dadd_rn(qn64, __dmul_rn((double)xs[k], (double)xs[k]));
+  for (int o = 16; o > 0; o >>= 1) {
+    ssq += __shfl_xor_sync(kFull, ssq, o);
+    xr64 += __shfl_xor_sync(kFull, xr64, o);
   }
-  sqnorm = __shfl_sync(kFull, sqnorm, 0);
-  const float qn = (float)__shfl_sync(kFull, qn64, 1);
-  const bool degenerate = sqnorm < 1e-7;
-  const float inv_norm = degenerate ? 0.f : (float)(1.0 / sqrt(sqnorm));
-  for (uint32_t k = lane; k < a.D; k += 32) rh[k] = degenerate ? 0.f : __fmul_rn(rh[k], inv_norm);
   __syncwarp();
+  double qn64 = 0.0;
+  if (lane == 0)  // ||x||^2 as the tokenizer computes it (sequential double accumulation, narrowed)
+    for (uint32_t k = 0; k < a.D; ++k) qn64 = __dadd_rn(qn64, __dmul_rn((double)xs[k], (double)xs[k]));
+  const float qn = (float)__shfl_sync(kFull, qn64, 0);
+  const float xr = (float)xr64;
 
   float m = __int_as_float(0x7F800000);
   int32_t best = 0x7FFFFFFF;
@@ -144,12 +164,19 @@ soar_kernel(SoarArgs a) {
     evaluate(c);
     evals += np;
   }
-  // bound of |approx - ||x - c||^2| (the tokenization pre-filter's eps, prep.cu, plus the chain's own rounding)
+  // E1 bounds |approx - ||x - c||^2| (the tokenization pre-filter's eps, prep.cu, plus the chains' own rounding);
+  // E2 bounds |(xr - S2) - t2| for the fp32 chain t2 = sum fma(diff, rhat): GEMM error of rhat.c (|rhat| <= 1),
+  // the rounding of xr and of the chain ((D + 2) 2^-24 |x - c| |rhat|).  Then, with p = max(|xr - S2| - E2, 0):
+  //   cost = fl(t1 + fl(fl(lambda t2) t2)) >= ((approx - E1) shrink + lambda p^2 (1 - 2^-22)) (1 - 2^-23).
   const float qnorm = sqrtf(ssq) * 1.001f;
   const float scale = qn + a.cmax * a.cmax + 2.f * qnorm * a.cmax;
-  const float E = 2.f * a.eps_rel * qnorm * a.cmax + 2.f * (float)(a.D + 8) * 1.1920929e-7f * scale;
-  const float shrink = 1.f - (float)(a.D + 8) * 1.1920929e-7f;  // t1 >= ||x - c||^2 * shrink
+  const float ulp = (float)(a.D + 8) * 1.1920929e-7f;
+  const float E1 = 2.f * a.eps_rel * qnorm * a.cmax + 2.f * ulp * scale;
+  const float E2 = 1.5f * a.eps_rel * a.cmax + 2.f * ulp * (qnorm + a.cmax);
+  const float shrink = 1.f - ulp;  // t1 >= ||x - c||^2 * shrink
+  const float lam_lo = a.lambda * (1.f - 4.76837158e-7f);
   const float* row = a.row + (size_t)i * a.L;
+  const float* row2 = a.row2 ? a.row2 + (size_t)i * a.L : nullptr;
   uint32_t ncand = 0;
   for (uint32_t base = 0; base < a.L; base += 32) {
     const uint32_t l = base + lane;
@@ -157,7 +184,11 @@ soar_kernel(SoarArgs a) {
     if (l < a.L) {
       const float v = row[l];
       const float ap = a.row_is_dot ? __fsub_rn(__fadd_rn(__ldg(a.cnorm + l), qn), __fmul_rn(2.f, v)) : v;
-      const float lb = __fmul_rd(__fsub_rd(ap, E), shrink);
+      float lb = __fmul_rd(__fsub_rd(ap, E1), shrink);
+      if (row2) {
+        const float p = fmaxf(__fsub_rd(fabsf(__fsub_rn(xr, row2[l])), E2), 0.f);
+        lb = __fmul_rd(__fadd_rd(lb, __fmul_rd(__fmul_rd(p, p), lam_lo)), 1.f - 1.1920929e-7f);
+      }
       pass = !(lb > m);  // NaN passes
     }
     const uint32_t mask = __ballot_sync(kFull, pass);
@@ -233,10 +264,29 @@ struct EncodeArgs {
 __host__ __device__ __forceinline__ size_t encode_team_bytes(uint32_t D, uint32_t B, bool shaped) {
   const size_t Dp = (D + 3) & ~3u;
   size_t b = 2 * Dp * sizeof(float);                        // res, orig
-  if (shaped) b += (size_t)B * 16 * 2 * sizeof(double)      // norm, par
-                   + (size_t)B * sizeof(double);            // initial norms
+  if (shaped) b += (size_t)B * sizeof(double);              // initial norms
   b += ((size_t)B * 3 + 15) & ~(size_t)15;                  // code u8, order u16
   return (b + 15) & ~(size_t)15;
+}
+
+// u64 image of a double that orders like the double (NaNs at the two ends)
+__device__ __forceinline__ uint64_t d2ord(double v) {
+  const uint64_t u = (uint64_t)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord2d(uint64_t o) {
+  return __longlong_as_double((long long)((o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o));
+}
+// Lowest lane of the team (mask tmask, first lane tbase) that holds the minimum of v; *vmin = that minimum.
+// Two 32-bit REDUX.MIN on the ordered image and one ballot instead of a 4-level shuffle tree of (double, index).
+__device__ __forceinline__ int team_argmin(uint32_t tmask, int tbase, double v, double* vmin) {
+  const uint64_t key = d2ord(v);
+  const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+  const uint32_t mh = __reduce_min_sync(tmask, hi);
+  const uint32_t ml = __reduce_min_sync(tmask, hi == mh ? lo : 0xFFFFFFFFu);
+  const uint32_t win = __ballot_sync(tmask, hi == mh && lo == ml) & tmask;
+  *vmin = ord2d(((uint64_t)mh << 32) | ml);
+  return __ffs(win) - 1 - tbase;
 }
 
 template <bool kShaped>
@@ -245,24 +295,23 @@ encode_kernel(EncodeArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int team = tid / kTeam, c = tid % kTeam;      // lane within the team = codebook centre
+  const int tbase = (tid & 31) & ~(kTeam - 1);        // first lane of the team inside its warp
+  const uint32_t tmask = 0xFFFFu << tbase;
   const uint32_t Dp = (a.D + 3) & ~3u;
   unsigned char* base = smem_raw + (size_t)team * encode_team_bytes(a.D, a.B, kShaped);
   float* res = reinterpret_cast<float*>(base);
   float* orig = res + Dp;
-  double* snorm = reinterpret_cast<double*>(orig + Dp);
-  double* spar = snorm + (kShaped ? (size_t)a.B * 16 : 0);
-  double* n0 = spar + (kShaped ? (size_t)a.B * 16 : 0);
+  double* n0 = reinterpret_cast<double*>(orig + Dp);
   uint8_t* code = reinterpret_cast<uint8_t*>(n0 + (kShaped ? a.B : 0));
   uint16_t* order = reinterpret_cast<uint16_t*>(code + ((a.B + 1) & ~1u));
   const uint64_t pair = (uint64_t)blockIdx.x * (kEncodeThreads / kTeam) + team;
   const bool active = pair < (uint64_t)a.n * a.npd;
-  // inactive teams run the same instruction stream on a dummy pair so that the full-warp shuffles stay converged
+  // inactive teams run the same instruction stream on a dummy pair so that the warp stays converged
   const uint32_t i = active ? (uint32_t)(pair / a.npd) : 0u;
   const uint32_t which = active ? (uint32_t)(pair % a.npd) : 0u;
   const int32_t tok = a.tokens[(size_t)i * a.npd + which];
   uint8_t* out = (which ? a.soar_codes : a.codes) + (size_t)i * a.B;
   if (tok < 0) {  // not spilled: the SOAR row stays zero (CombineLeafDatasets, tree_x_hybrid/internal/utils.h:87-106)
-    // (team-uniform branch; the other team of the warp only meets this team at shuffles, and there are none here)
     if (active) for (uint32_t b = c; b < a.B; b += kTeam) out[b] = 0;
   }
   const bool work = tok >= 0;
@@ -297,11 +346,11 @@ encode_kernel(EncodeArgs a) {
     return;
   } else {
     const uint32_t B = a.B, D = a.D;
-    // ---- ComputeResidualStats: ||orig|| (sequential double sum), then per (block, centre) statistics ----
+    // ---- ||orig|| (sequential double sum) and SquaredL2Norm(orig) (four strided accumulators) ----
     double chunked = 0.0, sqn = 0.0;
     if (c == 0) {
       for (uint32_t k = 0; k < D; ++k) chunked = __dadd_rn(chunked, __dmul_rn((double)orig[k], (double)orig[k]));
-    } else if (c == 1) {  // SquaredL2Norm(original): DenseSingleAccumulate, four strided double accumulators
+    } else if (c == 1) {  // DenseSingleAccumulate (utils/reduction.h:357-390)
       double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
       uint32_t k = 0;
       for (; k + 4 <= D; k += 4) {
@@ -326,7 +375,10 @@ encode_kernel(EncodeArgs a) {
     const double t2 = __dmul_rn(a.threshold, a.threshold);
     const double ratio = __ddiv_rn(t2, sqn);
     const double mult = __ddiv_rn(ratio, __ddiv_rn(__dsub_rn(1.0, ratio), __dsub_rn((double)D, 1.0)));
-    for (uint32_t b = 0; b < B; ++b) {
+    // ComputeResidualStatsForCluster for (block b, this lane's centre).  The statistics are NOT kept: B * 16 pairs of
+    // doubles per team would cap the SM at 8 resident warps; recomputing them costs 6 double operations per dimension
+    // (the same operations in the same order, so the same bits) and keeps the team's footprint at ~1.4 KB.
+    auto stats = [&](uint32_t b, double* rn_out, double* par_out) {
       const uint32_t nd = (uint32_t)a.block_dims[b], off = a.block_off[b];
       const float* cx = a.codebook + ((size_t)b * 16 + c) * a.S;
       double rn = 0.0, par = 0.0;
@@ -335,23 +387,19 @@ encode_kernel(EncodeArgs a) {
         rn = __dadd_rn(rn, __dmul_rn(rc, rc));
         par = __dadd_rn(par, __dmul_rn(__dmul_rn(rc, (double)orig[off + k]), inv_norm));
       }
-      snorm[b * 16 + c] = rn;
-      spar[b * 16 + c] = par;
-      // InitializeToMinResidualNorm: first minimum
-      int idx = c;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        const double on = __shfl_xor_sync(kFull, rn, o, kTeam);
-        const int oi = __shfl_xor_sync(kFull, idx, o, kTeam);
-        if (on < rn || (on == rn && oi < idx)) { rn = on; idx = oi; }
-      }
-      if (c == 0) { code[b] = (uint8_t)idx; n0[b] = rn; }
+      *rn_out = rn;
+      *par_out = par;
+    };
+    // ---- InitializeToMinResidualNorm (first minimum) + ComputeParallelResidualComponent (sequential over blocks) ----
+    double par = 0.0;
+    for (uint32_t b = 0; b < B; ++b) {
+      double rn, pc, nmin;
+      stats(b, &rn, &pc);
+      const int idx = team_argmin(tmask, tbase, rn, &nmin);
+      par = __dadd_rn(par, __shfl_sync(kFull, pc, idx, kTeam));
+      if (c == 0) { code[b] = (uint8_t)idx; n0[b] = nmin; }
     }
     __syncwarp();
-    // ---- ComputeParallelResidualComponent: sequential sum over the blocks ----
-    double par = 0.0;
-    if (c == 0) for (uint32_t b = 0; b < B; ++b) par = __dadd_rn(par, spar[b * 16 + code[b]]);
-    par = __shfl_sync(kFull, par, 0, kTeam);
     // ---- visiting order: descending initial norm, ties by ascending block (rank by counting) ----
     bool tie = false;
     for (uint32_t b = c; b < B; b += kTeam) {
@@ -365,9 +413,9 @@ encode_kernel(EncodeArgs a) {
       order[rank] = (uint16_t)b;
     }
     __syncwarp();
-    if (__ballot_sync(kFull, tie) & (0xFFFFu << (16 * ((tid & 31) / kTeam))))
+    if (__ballot_sync(kFull, tie) & tmask)
       if (c == 0 && active && work) atomicAdd(a.ties, 1ull);
-    // ---- coordinate descent ----
+    // ---- coordinate descent (OptimizeSingleSubspace over the blocks, <= 10 rounds) ----
     bool changes = true;
     for (int round = 0; round < 10; ++round) {
       // the two teams of a warp stay in lockstep: a finished team keeps iterating without effect (a round without
@@ -377,29 +425,24 @@ encode_kernel(EncodeArgs a) {
       for (uint32_t ii = 0; ii < B; ++ii) {
         const uint32_t b = order[ii];
         const int cur = code[b];
-        const double old_norm = snorm[b * 16 + cur], old_par = spar[b * 16 + cur];
-        const double new_par = __dadd_rn(__dsub_rn(par, old_par), spar[b * 16 + c]);
+        double rn, pc;
+        stats(b, &rn, &pc);
+        const double old_norm = __shfl_sync(kFull, rn, cur, kTeam), old_par = __shfl_sync(kFull, pc, cur, kTeam);
+        const double new_par = __dadd_rn(__dsub_rn(par, old_par), pc);
         const double par_delta = __dsub_rn(__dmul_rn(new_par, new_par), __dmul_rn(par, par));
-        const double norm_delta = __dsub_rn(snorm[b * 16 + c], old_norm);
+        const double norm_delta = __dsub_rn(rn, old_norm);
         const double perp_delta = __dsub_rn(norm_delta, par_delta);
         const double cost_delta = __dadd_rn(__dmul_rn(mult, par_delta), perp_delta);
         const bool valid = c != cur && !(par_delta > 0.0) && cost_delta < 0.0;
-        double v = valid ? cost_delta : 0.0;
-        int idx = valid ? c : 255;
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(kFull, v, o, kTeam);
-          const int oi = __shfl_xor_sync(kFull, idx, o, kTeam);
-          if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
-        }
-        const double win_par = __shfl_sync(kFull, new_par, idx & 15, kTeam);
-        if (idx != 255) {
-          par = win_par;
+        if (__ballot_sync(kFull, valid) & tmask) {  // team-uniform
+          double vmin;
+          const int idx = team_argmin(tmask, tbase, valid ? cost_delta : 0.0, &vmin);  // valid lanes are < 0: they win
+          par = __shfl_sync(tmask, new_par, tbase + idx);
           changes = true;
           if (c == 0) code[b] = (uint8_t)idx;
         }
-        __syncwarp();
       }
+      __syncwarp();  // code[] of this round is visible to the next one (a block is visited once per round)
     }
     __syncwarp();
     if (active && work) for (uint32_t b = c; b < B; b += kTeam) out[b] = code[b];
@@ -538,16 +581,25 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
   uint32_t R = 16384;
   { const char* e = getenv("SCANN_B200_ENCODE_CHUNK"); if (e && atoi(e) > 0) R = (uint32_t)atoi(e); }
   R = std::min(R, N);
-  Buf x, dist, tok_a, near, bias, sec, toks, codes, scodes, counters;
-  CU(x.alloc(sizeof(float) * (size_t)R * D));
+  Buf xbuf[2], dist, tok_a, near, bias, sec, toks[2], codes[2], scodes[2], counters, rhat, dist2;
+  for (int b = 0; b < 2; ++b) {
+    CU(xbuf[b].alloc(sizeof(float) * (size_t)R * D));
+    CU(toks[b].alloc(sizeof(int32_t) * (size_t)R * npd));
+    CU(codes[b].alloc((size_t)R * B));
+    CU(scodes[b].alloc((size_t)R * B));
+  }
   CU(dist.alloc(sizeof(float) * (size_t)R * L));
   CU(tok_a.alloc(sb::tokenize_operand_bytes(R, D)));
   CU(near.alloc(sizeof(int32_t) * (size_t)R * P));
   CU(bias.alloc(sizeof(float) * (size_t)R * P));
   CU(sec.alloc(sizeof(int32_t) * R));
-  CU(toks.alloc(sizeof(int32_t) * (size_t)R * npd));
-  CU(codes.alloc((size_t)R * B));
-  CU(scodes.alloc((size_t)R * B));
+  const bool row_is_dot = sb::tokenize_tensor_path(v, P);
+  // SOAR: the projection term is pruned with a second tensor-core GEMM (rhat x centres) when the centre operand
+  // exists; small trees (SIMT tokenization) prune by distance only
+  bool soar_gemm = soar && row_is_dot && d->soar_lambda >= 0.f;
+  { const char* e = getenv("SCANN_B200_SOAR_GEMM"); if (e && e[0] == '0') soar_gemm = false; }
+  if (soar) CU(rhat.alloc(sizeof(float) * (size_t)R * D));
+  if (soar_gemm) CU(dist2.alloc(sizeof(float) * (size_t)R * L));
   CU(counters.alloc(sizeof(unsigned long long) * 4 + sizeof(uint32_t) * 4));
   CU(cudaMemsetAsync(counters.p, 0, sizeof(unsigned long long) * 4 + sizeof(uint32_t) * 4, s));
   unsigned long long* c_evaluated = counters.as<unsigned long long>();
@@ -564,7 +616,6 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
       if (soar) pin_s.pin(soar_codes_out, (size_t)N * B, cudaHostRegisterDefault);
     } }
 
-  const bool row_is_dot = sb::tokenize_tensor_path(v, P);
   const float eps_rel = (float)v.tok_kp * 4.76837158e-7f + 3.05175781e-5f;  // as launch_tokenize_topp
   const size_t team_bytes = sb::encode_team_bytes(D, B, shaped);
   const size_t enc_smem = team_bytes * (sb::kEncodeThreads / sb::kTeam);
@@ -577,34 +628,87 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
     CU(cudaFuncSetAttribute(sb::soar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)soar_smem));
   }
 
+  // ---- chunk pipeline: copy-in, compute and copy-out on three streams, two buffers ----
+  // chunk c uses buffer b = c & 1.  copy-in of c waits for the compute of c - 2 (it overwrites x[b]); compute of c
+  // waits for its copy-in and for the copy-out of c - 2 (it overwrites toks/codes[b]); copy-out of c waits for its
+  // compute.  The host only blocks on the stage times of chunk c - 2.
   float ms[4] = {0, 0, 0, 0};  // tokenize, soar, encode, total
+  Stream st_in, st_out;
+  CU(cudaStreamCreateWithFlags(&st_in.s, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&st_out.s, cudaStreamNonBlocking));
+  struct Slot {
+    cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr, t[4] = {};
+    bool used = false;
+    ~Slot() {
+      for (cudaEvent_t e : {in_done, comp_done, out_done, t[0], t[1], t[2], t[3]}) if (e) cudaEventDestroy(e);
+    }
+  } slot[2];
+  for (auto& sl : slot) {
+    CU(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sl.comp_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    for (auto& e : sl.t) CU(cudaEventCreate(&e));
+  }
+  auto collect = [&](Slot& sl) -> cudaError_t {  // stage times of the chunk that last used this slot
+    cudaError_t e = cudaEventSynchronize(sl.t[3]);
+    float t;
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k) {
+      e = cudaEventElapsedTime(&t, sl.t[k], sl.t[k + 1]);
+      ms[k] += t;
+    }
+    return e;
+  };
+  CU(cudaStreamSynchronize(s));  // centres, operand and codebook are in place before the other streams start
   CU(cudaEventRecord(ev.e[6], s));
-  for (uint64_t r0 = 0; r0 < N; r0 += R) {
+  uint64_t chunk = 0;
+  for (uint64_t r0 = 0; r0 < N; r0 += R, ++chunk) {
     const uint32_t nr = (uint32_t)std::min<uint64_t>(R, N - r0);
-    CU(cudaMemcpyAsync(x.p, d->dataset + r0 * D, sizeof(float) * (size_t)nr * D, cudaMemcpyHostToDevice, s));
-    CU(cudaEventRecord(ev.e[0], s));
+    const int b = (int)(chunk & 1);
+    Slot& sl = slot[b];
+    float* xb = xbuf[b].as<float>();
+    int32_t* tb = toks[b].as<int32_t>();
+    uint8_t* cb = codes[b].as<uint8_t>();
+    uint8_t* sb_ = scodes[b].as<uint8_t>();
+    if (sl.used) {
+      CU(collect(sl));
+      CU(cudaStreamWaitEvent(st_in.s, sl.comp_done, 0));
+      CU(cudaStreamWaitEvent(s, sl.out_done, 0));
+    }
+    CU(cudaMemcpyAsync(xb, d->dataset + r0 * D, sizeof(float) * (size_t)nr * D, cudaMemcpyHostToDevice, st_in.s));
+    CU(cudaEventRecord(sl.in_done, st_in.s));
+    CU(cudaStreamWaitEvent(s, sl.in_done, 0));
+    CU(cudaEventRecord(sl.t[0], s));
     int launches = 0;
-    CU(sb::launch_tokenize_topp(v, x.as<float>(), nr, P, dist.as<float>(), tok_a.p, near.as<int32_t>(), bias.as<float>(),
+    CU(sb::launch_tokenize_topp(v, xb, nr, P, dist.as<float>(), tok_a.p, near.as<int32_t>(), bias.as<float>(),
                                 c_fallbacks, s, &launches));
-    CU(cudaEventRecord(ev.e[1], s));
+    CU(cudaEventRecord(sl.t[1], s));
     if (soar) {
       sb::SoarArgs a{};
-      a.x = x.as<float>(); a.centers = v.centers; a.cnorm = v.center_sqnorm; a.row = dist.as<float>();
+      a.x = xb; a.centers = v.centers; a.cnorm = v.center_sqnorm; a.row = dist.as<float>();
       a.near = near.as<int32_t>(); a.sec = sec.as<int32_t>(); a.evaluated = c_evaluated;
       a.n = nr; a.L = L; a.D = D; a.P = P; a.row_is_dot = row_is_dot ? 1 : 0;
       a.lambda = d->soar_lambda; a.eps_rel = eps_rel; a.cmax = v.center_max_norm;
-      sb::soar_kernel<<<(nr + sb::kSoarThreads / 32 - 1) / (sb::kSoarThreads / 32), sb::kSoarThreads, soar_smem, s>>>(a);
+      a.rhat = rhat.as<float>();
+      const unsigned wgrid = (nr + sb::kSoarThreads / 32 - 1) / (sb::kSoarThreads / 32);
+      sb::rhat_kernel<<<wgrid, sb::kSoarThreads, 0, s>>>(a);
+      CU(cudaGetLastError());
+      if (soar_gemm) {  // the tokenization's A operand is free again: reuse it for rhat
+        CU(sb::build_tokenize_operand(a.rhat, nr, D, 1, tok_a.p, s));
+        CU(sb::gemm_bf16_nt(tok_a.p, nr, (nr + 127) / 128 * 128, v.tok_b, L, v.tok_kp, dist2.as<float>(), L, s));
+        a.row2 = dist2.as<float>();
+      }
+      sb::soar_kernel<<<wgrid, sb::kSoarThreads, soar_smem, s>>>(a);
       CU(cudaGetLastError());
     }
-    sb::tokens_kernel<<<(nr + 255) / 256, 256, 0, s>>>(near.as<int32_t>(), P, soar ? sec.as<int32_t>() : nullptr, nr,
-                                                       toks.as<int32_t>(), c_spilled);
+    sb::tokens_kernel<<<(nr + 255) / 256, 256, 0, s>>>(near.as<int32_t>(), P, soar ? sec.as<int32_t>() : nullptr, nr, tb,
+                                                       c_spilled);
     CU(cudaGetLastError());
-    CU(cudaEventRecord(ev.e[2], s));
+    CU(cudaEventRecord(sl.t[2], s));
     {
       sb::EncodeArgs a{};
-      a.x = x.as<float>(); a.centers = d->residual ? v.centers : nullptr; a.tokens = toks.as<int32_t>();
+      a.x = xb; a.centers = d->residual ? v.centers : nullptr; a.tokens = tb;
       a.codebook = codebook.as<float>(); a.block_dims = block_dims.as<int32_t>(); a.block_off = block_off.as<uint32_t>();
-      a.codes = codes.as<uint8_t>(); a.soar_codes = scodes.as<uint8_t>(); a.ties = c_ties;
+      a.codes = cb; a.soar_codes = sb_; a.ties = c_ties;
       a.n = nr; a.D = D; a.B = B; a.S = S; a.npd = npd; a.threshold = d->noise_shaping_threshold;
       const uint64_t pairs = (uint64_t)nr * npd;
       const unsigned grid = (unsigned)((pairs + sb::kEncodeThreads / sb::kTeam - 1) / (sb::kEncodeThreads / sb::kTeam));
@@ -612,18 +716,23 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
       else sb::encode_kernel<false><<<grid, sb::kEncodeThreads, enc_smem, s>>>(a);
       CU(cudaGetLastError());
     }
-    CU(cudaEventRecord(ev.e[3], s));
-    CU(cudaMemcpyAsync(tokens_out + r0 * npd, toks.p, sizeof(int32_t) * (size_t)nr * npd, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(codes_out + r0 * B, codes.p, (size_t)nr * B, cudaMemcpyDeviceToHost, s));
-    if (soar) CU(cudaMemcpyAsync(soar_codes_out + r0 * B, scodes.p, (size_t)nr * B, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    float t;
-    CU(cudaEventElapsedTime(&t, ev.e[0], ev.e[1])); ms[0] += t;
-    CU(cudaEventElapsedTime(&t, ev.e[1], ev.e[2])); ms[1] += t;
-    CU(cudaEventElapsedTime(&t, ev.e[2], ev.e[3])); ms[2] += t;
+    CU(cudaEventRecord(sl.t[3], s));
+    CU(cudaEventRecord(sl.comp_done, s));
+    CU(cudaStreamWaitEvent(st_out.s, sl.comp_done, 0));
+    CU(cudaMemcpyAsync(tokens_out + r0 * npd, tb, sizeof(int32_t) * (size_t)nr * npd, cudaMemcpyDeviceToHost, st_out.s));
+    CU(cudaMemcpyAsync(codes_out + r0 * B, cb, (size_t)nr * B, cudaMemcpyDeviceToHost, st_out.s));
+    if (soar) CU(cudaMemcpyAsync(soar_codes_out + r0 * B, sb_, (size_t)nr * B, cudaMemcpyDeviceToHost, st_out.s));
+    CU(cudaEventRecord(sl.out_done, st_out.s));
+    sl.used = true;
+  }
+  for (auto& sl : slot) {
+    if (!sl.used) continue;
+    CU(collect(sl));
+    CU(cudaStreamWaitEvent(s, sl.out_done, 0));
   }
   CU(cudaEventRecord(ev.e[7], s));
   CU(cudaStreamSynchronize(s));
+  CU(cudaStreamSynchronize(st_out.s));
   CU(cudaEventElapsedTime(&ms[3], ev.e[6], ev.e[7]));
   if (stats_out) {
     unsigned long long hc[4];
