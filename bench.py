@@ -47,6 +47,11 @@ WORKLOADS = {
     # per leaf as in C5; --n / --leaves rescale it.
     "c5_deep_shape": dict(n=20_000_000, d=96, leaves=8000, probe=80, dpb=2, pre=200, k=10, nq=10000,
                           clusters=80000, normalize=True, seed=9, train_sample=500000, soar=1.5, noise=0.2),
+    # C4 shape (BASELINE.json configs[3]: sift 10M x 128 squared L2, k = 10): integer-valued SIFT-like rows (0..218)
+    # drawn from a clustered mixture, TreeXHybridSMMD semantics (AH codes of the raw vector, no residual, no SOAR:
+    # the reference's builder rejects SOAR for squared L2, scann_builder.py:200-201).  Fits one GPU (5.1 GB of rows).
+    "c4_sift_shape": dict(n=10_000_000, d=128, leaves=4000, probe=64, dpb=2, pre=100, k=10, nq=10000,
+                          clusters=16000, normalize=False, seed=7, train_sample=500000, distance="squared_l2", gen="sift"),
     "c1_synthetic": dict(n=100_000, d=100, leaves=100, probe=10, dpb=2, pre=100, k=10, nq=10000,
                          clusters=400, normalize=False, seed=1, train_sample=100000),
 }
@@ -84,12 +89,18 @@ def make_data(wl):
                           normalize=wl["normalize"])
   q = datasets.clustered(wl["nq"], wl["d"], wl["clusters"], seed=wl["seed"] + 1, centers_seed=100 + wl["seed"],
                          normalize=wl["normalize"])
+  if wl.get("gen") == "sift":  # SIFT-like: non-negative integers up to 218 stored as f32
+    for a in (db, q):
+      np.abs(a, out=a)
+      a *= 40.0
+      np.clip(a, 0.0, 218.0, out=a)
+      np.round(a, out=a)
   return db, q
 
 
 def build_arrays(wl, db, device):
   from scann_b200 import index_build
-  return index_build.build_tree_ah(db, "dot_product", num_leaves=wl["leaves"], dims_per_block=wl["dpb"],
+  return index_build.build_tree_ah(db, wl.get("distance", "dot_product"), num_leaves=wl["leaves"], dims_per_block=wl["dpb"],
                                    training_sample_size=wl["train_sample"], tree_iters=12, ah_iters=10,
                                    soar_lambda=wl.get("soar"), seed=0, device=device,
                                    noise_shaping_threshold=wl.get("noise", float("nan")))
@@ -159,16 +170,21 @@ def recall_at_k(found, truth):
   return hit / (found.shape[0] * k)
 
 
-def exact_topk(d_q, db, k, dev, rows=1 << 21):
-  """Exact f32 brute-force top-k ids (dot product) on the GPU, database streamed in chunks of `rows`."""
+def exact_topk(d_q, db, k, dev, rows=1 << 21, l2=False):
+  """Exact f32 brute-force top-k ids on the GPU, database streamed in chunks of `rows`; dot product, or squared L2
+  as argmax of <q, x> - |x|^2 / 2."""
   import torch
   nq = d_q.shape[0]
   best_v = torch.full((nq, k), -float("inf"), device=dev)
   best_i = torch.zeros((nq, k), dtype=torch.int64, device=dev)
   for r0 in range(0, db.shape[0], rows):
     d_db = torch.from_numpy(db[r0:r0 + rows]).to(dev)
+    half = 0.5 * (d_db.double() ** 2).sum(1).float() if l2 else None
     for s in range(0, nq, 2000):
-      v, i = torch.topk(d_q[s:s + 2000] @ d_db.T, min(k, d_db.shape[0]), dim=1)
+      sc = d_q[s:s + 2000] @ d_db.T
+      if l2:
+        sc -= half[None, :]
+      v, i = torch.topk(sc, min(k, d_db.shape[0]), dim=1)
       cv = torch.cat([best_v[s:s + 2000], v], dim=1)
       ci = torch.cat([best_i[s:s + 2000], i + r0], dim=1)
       o = torch.topk(cv, k, dim=1).indices
@@ -203,6 +219,8 @@ def main():
   ap.add_argument("--n", type=int, default=0, help="override the database size (leaves are rescaled to keep rows per leaf)")
   ap.add_argument("--noise", type=float, default=None,
                   help="AH noise_shaping_threshold used when the index is built (the reference builder's default is 0.2)")
+  ap.add_argument("--sweep-leaves", default="",
+                  help="comma-separated leaves_to_search values measured after the headline run (recall / QPS trade-off)")
   ap.add_argument("--cpu-sample", type=int, default=2000)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   args = ap.parse_args()
@@ -257,9 +275,10 @@ def main():
     dist.barrier()
     if rank != 0:
       z = np.load(shm)
-      arrays = index_build.IndexArrays(distance="dot_product", dataset=db, n=db.shape[0], d=db.shape[1])
+      arrays = index_build.IndexArrays(distance=wl.get("distance", "dot_product"), dataset=db, n=db.shape[0], d=db.shape[1])
       arrays.centers, arrays.tokens, arrays.codes = z["centers"], z["tokens"], z["codes"]
-      arrays.codebook, arrays.block_dims, arrays.residual = z["codebook"], z["block_dims"], True
+      arrays.codebook, arrays.block_dims = z["codebook"], z["block_dims"]
+      arrays.residual = arrays.distance == "dot_product"
       if "soar_codes" in z.files:
         arrays.soar_codes, arrays.soar, arrays.overretrieve = z["soar_codes"], True, 2.0
     dist.barrier()
@@ -288,7 +307,7 @@ def main():
   torch.cuda.synchronize()
 
   # ground truth for recall (exact f32 brute force on the GPU)
-  truth = exact_topk(d_q, db, k, dev)
+  truth = exact_topk(d_q, db, k, dev, l2=wl.get("distance") == "squared_l2")
 
   def step_dev():
     ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k)
@@ -342,6 +361,24 @@ def main():
   if dist is not None:
     dist.barrier()
   e2e_s = (time.perf_counter() - e0)
+  sweep = []
+  if args.sweep_leaves and world == 1:
+    for p_ in [int(v) for v in args.sweep_leaves.split(",") if v]:
+      def step_p():
+        ix.search_batched_device(d_q.data_ptr(), nq, d_idx.data_ptr(), d_dist.data_ptr(), k, leaves=p_)
+        return ix.stats()
+      for _ in range(3):
+        step_p()
+      rec_p = recall_at_k(d_idx.cpu().numpy().view(np.uint32), truth)
+      ms_p, scan_p, n_p = 0.0, 0.0, max(3, min(args.steps, 5))
+      for _ in range(n_p):
+        flush.zero_()
+        torch.cuda.synchronize()
+        st = step_p()
+        ms_p += st["ms_total"]
+        scan_p += st["ms_scan"]
+      sweep.append({"leaves_to_search": p_, "recall_at_10": rec_p, "qps": nq * n_p / (ms_p / 1e3),
+                    "ms_per_step": ms_p / n_p, "ms_scan": scan_p / n_p})
   db_sharded = None
   if searcher is not None:
     sh_dev, _ = make_sharded_steps(searcher, wl, q, d_q, d_idx, d_dist)
@@ -385,7 +422,8 @@ def main():
       "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
       "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "u8 LUT / int16 accumulate (scan), f32 (tokenize, reorder)", "data": "synthetic",
-      "config": {"workload": args.workload, "n": wl["n"], "d": wl["d"], "leaves": wl["leaves"],
+      "config": {"workload": args.workload, "distance": wl.get("distance", "dot_product"), "n": wl["n"], "d": wl["d"],
+                 "leaves": wl["leaves"], "soar_lambda": wl.get("soar"),
                  "leaves_to_search": wl["probe"], "ah_blocks": wl["d"] // wl["dpb"], "reorder": wl["pre"],
                  "k": k, "queries_per_step": nq * world, "recall_at_10": rec,
                  "noise_shaping_threshold": wl.get("noise"),
@@ -396,6 +434,7 @@ def main():
               "d2h_bytes_per_step": int(nq * k * 8) * world, "steps": e2e_steps},
       "gpu_launches": int(agg.get("kernel_launches", 0)),
       "clocks": sampler.summary(),
+      **({"probe_sweep": sweep} if sweep else {}),
       "roofline": {"bound": "hbm", "kernel": "scan_main_kernel<W>", "achieved": achieved, "peak": peak,
                    "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak if peak else None,
                    "traffic": ncu_traffic("r01_scan_main_traffic.json") if args.workload == "c2_glove_shape" else None,

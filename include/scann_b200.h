@@ -42,7 +42,9 @@ typedef struct scann_b200_index scann_b200_index;
  *   tree-AH      : centers + tokens + codes (+ soar_codes) + codebook
  *                  (+ dataset for f32 reordering, or bf16_dataset alone for bfloat16 reordering:
  *                   Bfloat16ReorderingHelper, utils/reordering_helper.cc:720-757)
- *   brute force  : bf16_dataset, n_leaves = n_blocks = 0 (Bfloat16BruteForceSearcher)
+ *   brute force  : n_leaves = n_blocks = 0 and bf16_dataset (Bfloat16BruteForceSearcher,
+ *                  brute_force/bfloat16_brute_force.cc:101-152) or dataset (BruteForceSearcher<float>,
+ *                  brute_force/brute_force.cc:376-393); dot product only
  */
 typedef struct {
   int32_t distance;            /* SCANN_B200_DOT_PRODUCT | SCANN_B200_SQUARED_L2 */
