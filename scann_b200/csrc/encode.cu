@@ -490,6 +490,9 @@ struct HostPin {  // pins the caller's arrays for the duration of the call so th
   void* p = nullptr;
   ~HostPin() { if (p) cudaHostUnregister(p); }
   void pin(const void* q, size_t bytes, unsigned flags) {
+    // Only large arrays: that is where DMA from the caller's pages pays, and a large numpy / malloc block is its own
+    // mapping.  Small arrays share pages with unrelated heap objects; page-locking and unlocking those is avoided.
+    if (bytes < ((size_t)32 << 20)) return;
     if (cudaHostRegister(const_cast<void*>(q), bytes, flags) == cudaSuccess) { p = const_cast<void*>(q); return; }
     (void)cudaGetLastError();
     if (flags != cudaHostRegisterDefault && cudaHostRegister(const_cast<void*>(q), bytes, cudaHostRegisterDefault) == cudaSuccess) {

@@ -436,6 +436,10 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   w.entry_q = ix->entry_q.as<uint32_t>(); w.entry_bias = ix->entry_bias.as<float>();
   w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
   w.nq = nq; w.P = p.P; w.cap = cap; w.nover = p.nover; w.quads_per_item = 2; w.one = 1;  // 2 octs = 16 queries per work item
+  // large leaves (C5 shape: ~20 candidates per (query, item)): stage candidates in shared memory, one global atomic
+  // per (query, item); small leaves (C2: ~1.4) append directly
+  w.stage = ix->avg_leaf_slots >= 2048 ? 1u : 0u;
+  if (const char* e = getenv("SCANN_B200_SCAN_STAGE")) w.stage = e[0] == '1' ? 1u : 0u;
   int launches = 0;
   uint32_t scan_launches = 0, retries = 0;
 
@@ -453,7 +457,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   // leaves first, a compaction that tightens tau from "N-th best of the pilot's sample" to "N-th best of
   // those leaves", then the rest.  The pushes of the second phase shrink several-fold (100M x 96, P = 80:
   // 10.3k -> candidates per query); for C2-size work the extra launches cost more than they save.
-  bool two_phase = p.P >= 16 && (uint64_t)p.P * ix->avg_leaf_slots >= 131072;
+  bool two_phase = p.P >= 16 && (uint64_t)p.P * ix->avg_leaf_slots >= 98304;
   if (const char* e = getenv("SCANN_B200_TWO_PHASE")) two_phase = e[0] == '1' && p.P >= 2;
   const uint32_t r1 = two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
   w.rank_lo = 0; w.rank_hi = r1;

@@ -63,6 +63,7 @@ struct ScanWork {
   uint32_t nq, P, cap, nover, quads_per_item;
   uint32_t rank_lo, rank_hi;  // ranks [rank_lo, rank_hi) of every query's leaf list go into the next work list
   uint32_t one;               // always 1; a runtime value so the scan's IMAD accumulates stay IMADs
+  uint32_t stage;             // 1: the main scan stages candidates per item in shared memory (large leaves)
 };
 
 // ---- query preparation ----

@@ -608,10 +608,17 @@ struct ItemMeta {
   // thresholds of an oct packed like its accumulators, (t0,t2) (t1,t3) (t4,t6) (t5,t7) as u16 halves, each
   // biased by 32768: bit 15 of a half of (thrp - acc) is set iff sum <= thr (sums < 2^15 because B <= 128)
   uint4 thrp[kMaxQPI / 8];
+  // per-item staging of the candidates of each query: the scan appends here with shared-memory atomics and the item's
+  // epilogue publishes a query's keys with ONE global atomicAdd (one lane per staged key).  Where a few slots of almost
+  // every 32-slot group pass the threshold (C5-size leaves: ~20 candidates per (query, item)) the global atomic and its
+  // round trip leave the scoring loop; a full stage spills to the direct path below.
+  uint32_t scnt[kMaxQPI];
+  uint64_t sbuf[kMaxQPI][32];
 };
+constexpr uint32_t kStage = 32;
 
 // Rare path of the main scan: exact key test and warp-aggregated append for one oct.  All 32 lanes call.
-__device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork& w, const ItemMeta* meta, uint32_t qd,
+__device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork& w, ItemMeta* meta, uint32_t qd,
                                              uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, bool valid,
                                              uint32_t gslot, int off128) {
   const int lane = threadIdx.x & 31;
@@ -628,17 +635,29 @@ __device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork&
                      ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
       p = key < meta->tau[qi];
     }
-    const uint32_t m = __ballot_sync(kFull, p);
+    uint32_t m = __ballot_sync(kFull, p);
     if (m) {
-      const uint32_t qq = meta->q[qi];
-      const int leader = __ffs(m) - 1;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(&w.cnt[qq], (uint32_t)__popc(m));
-      base = __shfl_sync(kFull, base, leader);
-      if (p) {
-        const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-        if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = key;
-        else w.ovf[qq] = 1u;
+      // stage in shared memory; the part of the group that does not fit goes to the query's buffer directly
+      int leader = __ffs(m) - 1;
+      uint32_t sbase = 0;
+      if (w.stage) {
+        if (lane == leader) sbase = atomicAdd(&meta->scnt[qi], (uint32_t)__popc(m));
+        sbase = __shfl_sync(kFull, sbase, leader);
+        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+        if (p && sbase + rank < kStage) { meta->sbuf[qi][sbase + rank] = key; p = false; }
+        m = __ballot_sync(kFull, p);
+      }
+      if (m) {
+        const uint32_t qq = meta->q[qi];
+        leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&w.cnt[qq], (uint32_t)__popc(m));
+        base = __shfl_sync(kFull, base, leader);
+        if (p) {
+          const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+          if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = key;
+          else w.ovf[qq] = 1u;
+        }
       }
     }
   }
@@ -705,6 +724,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       }
       s_q[tid] = qq;
       s_thr[tid] = thr;
+      meta.scnt[tid] = 0;
     }
     __syncthreads();
     if (tid < (int)(qpi / 8)) {
@@ -751,6 +771,22 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
   }
       SB_DO_QUAD(0) SB_DO_QUAD(1)
 #undef SB_DO_QUAD
+    }
+    // item epilogue: publish the staged candidates, one warp per query, one global atomicAdd per (query, item)
+    if (!w.stage) continue;
+    __syncthreads();
+    for (uint32_t qi = warp; qi < ecount; qi += kScanWarps) {
+      const uint32_t c = min(meta.scnt[qi], kStage);
+      if (c == 0) continue;
+      const uint32_t qq = s_q[qi];
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&w.cnt[qq], c);
+      base = __shfl_sync(kFull, base, 0);
+      if ((uint32_t)lane < c) {
+        const uint32_t pos = base + lane;
+        if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = meta.sbuf[qi][lane];
+        else w.ovf[qq] = 1u;
+      }
     }
   }
 }

@@ -185,6 +185,28 @@ def test_two_phase_scan_is_bit_exact(kw, cap, monkeypatch):
   np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
 
 
+# ---- per-item candidate staging in shared memory (the large-leaf mode of the main scan) must not change anything ----
+@pytest.mark.parametrize("kw", [CASES[0], CASES[5], CASES[7], CASES[8]], ids=["dot", "soar", "allprobed", "l2"])
+@pytest.mark.parametrize("mode", ["single", "two_phase", "overflow"])
+def test_staged_candidate_push_is_bit_exact(kw, mode, monkeypatch):
+  monkeypatch.setenv("SCANN_B200_SCAN_STAGE", "1")
+  monkeypatch.setenv("SCANN_B200_TWO_PHASE", "1" if mode != "single" else "0")
+  if mode == "overflow":
+    monkeypatch.setenv("SCANN_B200_CAND_CAP", "256")
+  c = get_case(**kw)
+  a = c.oracle.candidates(c.q)
+  b = c.native.candidates(c.q)
+  np.testing.assert_array_equal(a["count"], b["count"])
+  for i in range(len(c.q)):
+    n = a["count"][i]
+    np.testing.assert_array_equal(a["dp"][i, :n], b["dp"][i, :n])
+    np.testing.assert_array_equal(a["score"][i, :n].view(np.uint32), b["score"][i, :n].view(np.uint32))
+  i0, d0 = c.oracle.search_batched(c.q)
+  i1, d1 = c.native.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
 def test_host_call_with_page_locked_buffers_matches_pageable():
   """scann_b200_search_batched copies page-locked caller memory to / from the device directly."""
   import torch
