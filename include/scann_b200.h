@@ -41,7 +41,8 @@ typedef struct scann_b200_index scann_b200_index;
  * what it needs to the device during scann_b200_index_create; the caller keeps ownership.
  *   tree-AH      : centers + tokens + codes (+ soar_codes) + codebook
  *                  (+ dataset for f32 reordering, or bf16_dataset alone for bfloat16 reordering:
- *                   Bfloat16ReorderingHelper, utils/reordering_helper.cc:720-757)
+ *                   Bfloat16ReorderingHelper, utils/reordering_helper.cc:720-757, or int8_dataset +
+ *                   int8_multipliers (+ dp_norms) for fixed-point reordering)
  *   brute force  : n_leaves = n_blocks = 0 and bf16_dataset (Bfloat16BruteForceSearcher,
  *                  brute_force/bfloat16_brute_force.cc:101-152) or dataset (BruteForceSearcher<float>,
  *                  brute_force/brute_force.cc:376-393); dot product only
@@ -69,6 +70,11 @@ typedef struct {
   int32_t device;              /* CUDA device ordinal */
   int32_t shard_rank;          /* this index holds datapoints with id % shard_world == shard_rank */
   int32_t shard_world;         /* 1 = unsharded */
+  /* int8 (fixed point) reordering, used when dataset and bf16_dataset are NULL
+   * (FixedPointFloatDense{DotProduct,SquaredL2}ReorderingHelper, utils/reordering_helper.cc:384-441,581-618) */
+  const int8_t* int8_dataset;      /* int8_dataset.npy [N][D] */
+  const float* int8_multipliers;   /* int8_multipliers.npy [D]: multiplier_by_dimension */
+  const float* dp_norms;           /* dp_norms.npy [N]: squared L2 norms of the original rows (squared L2 only) */
 } scann_b200_index_desc;
 
 /* Replaces ScannInterface::Initialize(ScannArtifacts) (scann_ops/cc/scann.cc:355-381) and the
@@ -172,7 +178,8 @@ typedef struct scann_b200_assets scann_b200_assets;
  * scann_config.pb from `artifacts_dir` and every asset listed in the text-format ScannAssets
  * manifest (`assets_pbtxt` = contents of scann_assets.pbtxt; relative paths are re-rooted at
  * artifacts_dir): serialized_partitioner.pb, ah_codebook.pb, datapoint_to_token.npy,
- * hashed_dataset[_soar].npy, dataset.npy, bfloat16_dataset.npy.  The handle owns the host copies. */
+ * hashed_dataset[_soar].npy, dataset.npy, bfloat16_dataset.npy, int8_dataset.npy + int8_multipliers.npy +
+ * dp_norms.npy.  The handle owns the host copies. */
 int scann_b200_assets_load(const char* artifacts_dir, const char* assets_pbtxt, scann_b200_assets** out);
 void scann_b200_assets_free(scann_b200_assets* assets);
 /* Fills an index descriptor whose pointers alias the handle's memory (valid until _free) and whose

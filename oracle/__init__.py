@@ -23,6 +23,7 @@ class _Desc(C.Structure):
       ("codebook", C.c_void_p), ("dataset", C.c_void_p), ("bf16_dataset", C.c_void_p),
       ("overretrieve", C.c_float), ("default_leaves", C.c_int32),
       ("default_pre_nn", C.c_int32), ("default_final_nn", C.c_int32),
+      ("int8_dataset", C.c_void_p), ("int8_multipliers", C.c_void_p), ("dp_norms", C.c_void_p),
   ]
 
 
@@ -98,6 +99,9 @@ class OracleIndex:
     d.codebook = _p(own(a.codebook, np.float32))
     d.dataset = _p(own(a.dataset, np.float32))
     d.bf16_dataset = _p(own(a.bf16_dataset, np.int16))
+    d.int8_dataset = _p(own(getattr(a, "int8_dataset", None), np.int8))
+    d.int8_multipliers = _p(own(getattr(a, "int8_multipliers", None), np.float32))
+    d.dp_norms = _p(own(getattr(a, "dp_norms", None), np.float32))
     d.overretrieve = a.overretrieve
     d.default_leaves = leaves_to_search
     d.default_pre_nn = pre_reorder_nn

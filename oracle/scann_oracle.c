@@ -725,11 +725,52 @@ static inline float bf16_to_f32(int16_t b) {
 }
 static float neg_dot_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n);
 static float sql2_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n);
+static double squared_l2_norm_f64(const float* v, uint32_t n);
+
+/* int8 (fixed point) reordering: FixedPointFloatDense{DotProduct,SquaredL2}ReorderingHelper::
+ * ComputeDistancesForReordering (utils/reordering_helper.cc:430-441,610-618):
+ *   q'[d] = (1.0f / multiplier[d]) * q[d]     (PrepareForAsymmetricScalarQuantizedDotProduct,
+ *                                              utils/scalar_quantization_helpers.cc:341-351; the inverse is formed
+ *                                              once in the helper's constructor, reordering_helper.cc:407-412)
+ *   val = -<q', float(x)> in the order of OneToManyAsymmetricTemplate<.., int8_t> on AVX2
+ *         (distance_measures/one_to_many/one_to_many_asymmetric_impl.inc:296-353): eight fnmadd lanes over whole
+ *         groups of 8 dims (HandleXDims<16> is two such steps), one 4-wide step into lanes 0..3, HorizontalSum3X
+ *         = ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)) (utils/intrinsics/horizontal_sum.h:170-182), then the remaining
+ *         dims one by one with fnmadd on the scalar.
+ *   dot product: val.  squared L2: (|q|^2 + dp_norms[id]) + 2.0f * val  (SetSquaredL2DistanceFunctor,
+ *   reordering_helper.cc:108-131; |q|^2 = float(SquaredL2Norm(q))).
+ * As for the float kernel, the reference sends the last n mod 3 rows of a list through a one-to-one kernel with
+ * another summation order; the list order is unspecified there, so every row uses the main kernel here. */
+static float neg_dot_i8_order(const float* qp, const int8_t* x, uint32_t n) {
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8)
+    for (int l = 0; l < 8; ++l) a[l] = fmaf(-qp[j + l], (float)x[j + l], a[l]);
+  if (j + 4 <= n) {
+    for (int l = 0; l < 4; ++l) a[l] = fmaf(-qp[j + l], (float)x[j + l], a[l]);
+    j += 4;
+  }
+  float r = ((a[0] + a[4]) + (a[2] + a[6])) + ((a[1] + a[5]) + (a[3] + a[7]));
+  for (; j < n; ++j) r = fmaf(-qp[j], (float)x[j], r);
+  return r;
+}
+static float exact_distance_i8(const so_index* ix, const float* q, uint32_t dp) {
+  const uint32_t D = ix->d.d;
+  float qp[D];
+  for (uint32_t j = 0; j < D; ++j) { const float inv = 1.0f / ix->d.int8_multipliers[j]; qp[j] = inv * q[j]; }
+  const float val = neg_dot_i8_order(qp, ix->d.int8_dataset + (size_t)dp * D, D);
+  if (ix->d.distance == SO_DOT_PRODUCT) return val;
+  const float qn = (float)squared_l2_norm_f64(q, D);
+  const float s = qn + ix->d.dp_norms[dp];
+  const float t = 2.0f * val;
+  return s + t;
+}
 
 /* bfloat16 reordering (utils/reordering_helper.cc:745-757, Bfloat16ReorderingHelper::ComputeDistancesForReordering
  * -> DenseDotProductDistanceOneToManyBf16Float / OneToManyBf16FloatSquaredL2): f32 query x bf16 row, f32 FMA. */
 static float exact_distance(const so_index* ix, const float* q, uint32_t dp) {
   const uint32_t D = ix->d.d;
+  if (!ix->d.dataset && !ix->d.bf16_dataset) return exact_distance_i8(ix, q, dp);
   if (!ix->d.dataset) {
     const int16_t* xb = ix->d.bf16_dataset + (size_t)dp * D;
     return ix->d.distance == SO_DOT_PRODUCT ? neg_dot_bf16_avx2_order(q, xb, D) : sql2_bf16_avx2_order(q, xb, D);
@@ -740,7 +781,7 @@ static float exact_distance(const so_index* ix, const float* q, uint32_t dp) {
 }
 
 int so_exact_distances(const so_index* ix, const float* q, const uint32_t* dps, uint32_t n, float* out) {
-  if (!ix->d.dataset && !ix->d.bf16_dataset) return fail("no dataset");
+  if (!ix->d.dataset && !ix->d.bf16_dataset && !ix->d.int8_dataset) return fail("no dataset");
   for (uint32_t i = 0; i < n; ++i) out[i] = exact_distance(ix, q, dps[i]);
   return 0;
 }
@@ -752,7 +793,7 @@ typedef struct {
 static sp_t resolve_params(const so_index* ix, int final_nn, int pre_nn, int leaves) {
   /* scann_ops/cc/scann.cc:406-430 + SetUnspecifiedParametersToDefaults */
   sp_t p;
-  const int has_reorder = (ix->d.dataset != NULL || ix->d.bf16_dataset != NULL) && ix->d.n_blocks != 0;
+  const int has_reorder = (ix->d.dataset != NULL || ix->d.bf16_dataset != NULL || ix->d.int8_dataset != NULL) && ix->d.n_blocks != 0;
   p.k = final_nn > 0 ? final_nn : ix->d.default_final_nn;
   if (has_reorder) p.npre = pre_nn > 0 ? pre_nn : ix->d.default_pre_nn;
   else p.npre = p.k;
@@ -849,7 +890,7 @@ static void finish_query(const so_index* ix, const float* q, sp_t sp, uint64_t* 
   }
   size_t m = n;
   if (!ix->disjoint) m = soar_dedup(c, n, (size_t)sp.npre, k2);
-  const int has_reorder = ix->d.dataset != NULL || ix->d.bf16_dataset != NULL;
+  const int has_reorder = ix->d.dataset != NULL || ix->d.bf16_dataset != NULL || ix->d.int8_dataset != NULL;
   for (size_t i = 0; i < m; ++i) {
     float dist = has_reorder ? exact_distance(ix, q, c[i].dp) : c[i].score;
     k2[i] = ((uint64_t)f2ord(dist) << 32) | c[i].dp;

@@ -25,6 +25,7 @@ class IndexDesc(C.Structure):
       ("overretrieve", C.c_float), ("default_leaves", C.c_int32),
       ("default_pre_nn", C.c_int32), ("default_final_nn", C.c_int32),
       ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
+      ("int8_dataset", C.c_void_p), ("int8_multipliers", C.c_void_p), ("dp_norms", C.c_void_p),
   ]
 
 
@@ -173,6 +174,9 @@ class NativeIndex:
     d.codebook = ptr(own(a.codebook, np.float32))
     d.dataset = ptr(own(a.dataset, np.float32))
     d.bf16_dataset = ptr(own(a.bf16_dataset, np.int16))
+    d.int8_dataset = ptr(own(getattr(a, "int8_dataset", None), np.int8))
+    d.int8_multipliers = ptr(own(getattr(a, "int8_multipliers", None), np.float32))
+    d.dp_norms = ptr(own(getattr(a, "dp_norms", None), np.float32))
     d.overretrieve = a.overretrieve
     d.default_leaves = leaves_to_search
     d.default_pre_nn = pre_reorder_nn

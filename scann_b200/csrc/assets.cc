@@ -554,9 +554,10 @@ struct Assets {
   Node config;
   std::vector<float> centers, codebook, dataset_own;
   std::vector<int32_t> block_dims;
-  NpyArray tokens, codes, soar_codes, dataset, bf16;
+  NpyArray tokens, codes, soar_codes, dataset, bf16, int8, int8_mult, dp_norms;
   uint32_t n_leaves = 0, n_blocks = 0, dpb = 0, d = 0, n = 0;
   bool has_tokens = false, has_codes = false, has_soar = false, has_dataset = false, has_bf16 = false;
+  bool has_int8 = false, has_int8_mult = false, has_dp_norms = false;
 };
 
 static double node_num(const Node* n, double dflt) {
@@ -732,6 +733,18 @@ int load(const char* dir, const char* assets_pbtxt, Assets** out) {
         if (int rc = read_npy(path, &a->bf16)) return rc;
         if (a->bf16.elem != 2 || a->bf16.shape.size() != 2) return afail(SCANN_B200_INVALID_ARGUMENT, "bfloat16_dataset.npy must be 2-D int16");
         a->has_bf16 = true;
+      } else if (t == "INT8_DATASET_NPY" || t == "10") {
+        if (int rc = read_npy(path, &a->int8)) return rc;
+        if (a->int8.elem != 1 || a->int8.shape.size() != 2) return afail(SCANN_B200_INVALID_ARGUMENT, "int8_dataset.npy must be 2-D int8");
+        a->has_int8 = true;
+      } else if (t == "INT8_MULTIPLIERS_NPY" || t == "13") {
+        if (int rc = read_npy(path, &a->int8_mult)) return rc;
+        if (a->int8_mult.descr != "<f4" || a->int8_mult.shape.size() != 1) return afail(SCANN_B200_INVALID_ARGUMENT, "int8_multipliers.npy must be 1-D float32");
+        a->has_int8_mult = true;
+      } else if (t == "INT8_NORMS_NPY" || t == "14") {
+        if (int rc = read_npy(path, &a->dp_norms)) return rc;
+        if (a->dp_norms.descr != "<f4" || a->dp_norms.shape.size() != 1) return afail(SCANN_B200_INVALID_ARGUMENT, "dp_norms.npy must be 1-D float32");
+        a->has_dp_norms = true;
       } else {
         return afail(SCANN_B200_UNIMPLEMENTED, "asset type %s is not supported by scann_b200", t.c_str());
       }
@@ -740,6 +753,13 @@ int load(const char* dir, const char* assets_pbtxt, Assets** out) {
   if (a->has_dataset) { a->n = (uint32_t)a->dataset.shape[0]; a->d = (uint32_t)a->dataset.shape[1]; }
   else if (a->has_codes) a->n = (uint32_t)a->codes.shape[0];
   else if (a->has_bf16) { a->n = (uint32_t)a->bf16.shape[0]; a->d = (uint32_t)a->bf16.shape[1]; }
+  if (a->has_int8) {
+    if (!a->has_dataset && !a->has_bf16) { a->n = (uint32_t)a->int8.shape[0]; a->d = (uint32_t)a->int8.shape[1]; }
+    if (!a->has_int8_mult || a->int8_mult.shape[0] != a->int8.shape[1])
+      return afail(SCANN_B200_INVALID_ARGUMENT, "int8_dataset.npy needs int8_multipliers.npy with one entry per dimension");
+    if (a->has_dp_norms && a->dp_norms.shape[0] != a->int8.shape[0])
+      return afail(SCANN_B200_INVALID_ARGUMENT, "dp_norms.npy has %zu entries, int8_dataset.npy has %zu rows", a->dp_norms.shape[0], a->int8.shape[0]);
+  }
   if (a->has_codes && a->n_blocks && a->codes.shape[1] != a->n_blocks)
     return afail(SCANN_B200_INVALID_ARGUMENT, "hashed_dataset.npy has %zu blocks, codebook has %u", a->codes.shape[1], a->n_blocks);
   if (a->has_tokens) {
@@ -770,6 +790,9 @@ int describe(const Assets* a, scann_b200_index_desc* d) {
   d->codebook = a->codebook.empty() ? nullptr : a->codebook.data();
   d->dataset = a->has_dataset ? reinterpret_cast<const float*>(a->dataset.bytes.data() + a->dataset.data_off) : nullptr;
   d->bf16_dataset = a->has_bf16 ? reinterpret_cast<const int16_t*>(a->bf16.bytes.data() + a->bf16.data_off) : nullptr;
+  d->int8_dataset = a->has_int8 ? reinterpret_cast<const int8_t*>(a->int8.bytes.data() + a->int8.data_off) : nullptr;
+  d->int8_multipliers = a->has_int8_mult ? reinterpret_cast<const float*>(a->int8_mult.bytes.data() + a->int8_mult.data_off) : nullptr;
+  d->dp_norms = a->has_dp_norms ? reinterpret_cast<const float*>(a->dp_norms.bytes.data() + a->dp_norms.data_off) : nullptr;
   d->overretrieve = (float)node_num(c.path({"partitioning", "database_spilling", "overretrieve_factor"}), 2.0);
   d->default_leaves = (int32_t)node_num(c.path({"partitioning", "query_spilling", "max_spill_centers"}), (double)a->n_leaves);
   d->default_final_nn = (int32_t)node_num(c.find("num_neighbors"), 1);
@@ -857,6 +880,18 @@ int save(const char* dir, const scann_b200_index_desc* d, const char* config_tex
   if (d->bf16_dataset) {
     if (int rc = write_npy(base + "/bfloat16_dataset.npy", "<i2", d->bf16_dataset, 2, d->n, d->d)) return rc;
     add("BF16_DATASET_NPY", "bfloat16_dataset.npy");
+  }
+  if (d->int8_dataset) {  // scann.cc:568-593 (pre_quantized_fixed_point)
+    if (int rc = write_npy(base + "/int8_dataset.npy", "<i1", d->int8_dataset, 1, d->n, d->d)) return rc;
+    add("INT8_DATASET_NPY", "int8_dataset.npy");
+    if (d->int8_multipliers) {
+      if (int rc = write_npy(base + "/int8_multipliers.npy", "<f4", d->int8_multipliers, 4, d->d, -1)) return rc;
+      add("INT8_MULTIPLIERS_NPY", "int8_multipliers.npy");
+    }
+    if (d->dp_norms) {
+      if (int rc = write_npy(base + "/dp_norms.npy", "<f4", d->dp_norms, 4, d->n, -1)) return rc;
+      add("INT8_NORMS_NPY", "dp_norms.npy");
+    }
   }
   if (d->dataset) {
     if (int rc = write_npy(base + "/dataset.npy", "<f4", d->dataset, 4, d->n, d->d)) return rc;

@@ -19,6 +19,35 @@ namespace sb {
 constexpr int kFinThreads = 128;
 constexpr uint32_t kInvalidId = 0xFFFFFFFFu;
 
+// int8 (fixed point) reordering: FixedPointFloatDense{DotProduct,SquaredL2}ReorderingHelper
+// (utils/reordering_helper.cc:430-441,610-618).  `qp` = the query scaled by the inverse multipliers
+// (PrepareForAsymmetricScalarQuantizedDotProduct), val = -<qp, float(x)> in the order of
+// OneToManyAsymmetricTemplate<.., int8_t> on AVX2 (one_to_many_asymmetric_impl.inc:296-353): eight fnmadd lanes over
+// whole groups of 8 dims, one 4-wide step into lanes 0..3, HorizontalSum3X = ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)),
+// the remaining dims one by one on the scalar.  Squared L2: (|q|^2 + dp_norm) + 2 val (SetSquaredL2DistanceFunctor).
+__device__ __forceinline__ float exact_distance_i8(const DevIndex& ix, const float* __restrict__ qp, float qnorm,
+                                                   uint32_t dp) {
+  const uint32_t row = ix.dp_row ? ix.dp_row[dp] : dp;
+  const int8_t* __restrict__ x = ix.dataset_i8 + (size_t)row * ix.d;
+  const uint32_t n = ix.d;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a[l] = __fmaf_rn(-qp[j + l], (float)__ldg(x + j + l), a[l]);
+  }
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[l] = __fmaf_rn(-qp[j + l], (float)__ldg(x + j + l), a[l]);
+    j += 4;
+  }
+  float r = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])),
+                      __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
+  for (; j < n; ++j) r = __fmaf_rn(-qp[j], (float)__ldg(x + j), r);
+  if (ix.distance == 0) return r;
+  return __fadd_rn(__fadd_rn(qnorm, ix.i8_dp_norm[dp]), __fmul_rn(2.0f, r));
+}
+
 __device__ __forceinline__ float exact_distance(const DevIndex& ix, const float* __restrict__ q,
                                                 uint32_t dp) {
   const uint32_t row = ix.dp_row ? ix.dp_row[dp] : dp;
@@ -184,10 +213,40 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
   const uint32_t q = blockIdx.x;
   const uint32_t n = min(w.cnt[q], w.nover);
   const uint64_t* src = w.buf + (size_t)q * w.cap;
-  const bool reorder = ix.dataset != nullptr || ix.dataset_bf16 != nullptr;
-  for (uint32_t i = tid; i < ix.d; i += kFinThreads) sq[i] = a.q[(size_t)q * ix.d + i];
+  const bool i8 = ix.dataset_i8 != nullptr;
+  const bool reorder = ix.dataset != nullptr || ix.dataset_bf16 != nullptr || i8;
+  float* sqp = sq + ((ix.d + 3) & ~3u);               // [D] int8 reordering: the query scaled by the inverse multipliers
+  __shared__ float s_qnorm;
+  for (uint32_t i = tid; i < ix.d; i += kFinThreads) {
+    const float v = a.q[(size_t)q * ix.d + i];
+    sq[i] = v;
+    if (i8) sqp[i] = __fmul_rn(ix.i8_inv_mult[i], v);
+  }
   if (tid == 0) s_removed = 0;
   __syncthreads();
+  if (i8 && ix.distance != 0 && tid == 0) {
+    // float(SquaredL2Norm(query)): DenseSingleAccumulate, four strided double accumulators (utils/reduction.h:357-390)
+    double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+    uint32_t k = 0;
+    const uint32_t D = ix.d;
+    for (; k + 4 <= D; k += 4) {
+      r0 = __dadd_rn(r0, __dmul_rn((double)sq[k], (double)sq[k]));
+      r1 = __dadd_rn(r1, __dmul_rn((double)sq[k + 1], (double)sq[k + 1]));
+      r2 = __dadd_rn(r2, __dmul_rn((double)sq[k + 2], (double)sq[k + 2]));
+      r3 = __dadd_rn(r3, __dmul_rn((double)sq[k + 3], (double)sq[k + 3]));
+    }
+    r2 = __dadd_rn(r2, r3);
+    if (k + 2 <= D) {
+      r0 = __dadd_rn(r0, __dmul_rn((double)sq[k], (double)sq[k]));
+      r1 = __dadd_rn(r1, __dmul_rn((double)sq[k + 1], (double)sq[k + 1]));
+      k += 2;
+    }
+    r1 = __dadd_rn(r1, r2);
+    if (k < D) r0 = __dadd_rn(r0, __dmul_rn((double)sq[k], (double)sq[k]));
+    s_qnorm = (float)__dadd_rn(r0, r1);
+  }
+  if (i8) __syncthreads();
+  const float qnorm = (i8 && ix.distance != 0) ? s_qnorm : 0.f;
 
   if (a.part_ids) {
     // Sharded mode: emit the raw over-retrieved candidates (before SOAR de-duplication, which is
@@ -203,6 +262,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
                                      : ((s & 0xFFFFFFFF00000000ull) | (ix.slot_tie ? ix.slot_tie[gslot] : gslot));
         a.part_ah[o] = ord2f((uint32_t)(s >> 32));
         if (!reorder) a.part_exact[o] = ord2f((uint32_t)(s >> 32));
+        else if (i8) a.part_exact[o] = exact_distance_i8(ix, sqp, qnorm, dp);
         else if (ix.d < 8) a.part_exact[o] = exact_distance(ix, sq, dp);
       } else {
         a.part_ids[o] = kInvalidId;
@@ -211,7 +271,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
         a.part_exact[o] = INFINITY;
       }
     }
-    if (reorder && ix.d >= 8) {
+    if (reorder && ix.d >= 8 && !i8) {
       const int l = tid & 7, grp = tid >> 3;
       for (uint32_t c0 = 0; c0 < n; c0 += kFinThreads / 8) {
         const uint32_t c = c0 + grp;
@@ -257,7 +317,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
   }
   for (int i = tid; i < np2; i += kFinThreads) ka[i] = kKeyMax;
   __syncthreads();
-  if (reorder && ix.d >= 8) {
+  if (reorder && ix.d >= 8 && !i8) {
     // 8 lanes per candidate row, 16 rows per pass
     const int l = tid & 7, grp = tid >> 3;
     for (uint32_t c0 = 0; c0 < m; c0 += kFinThreads / 8) {
@@ -271,7 +331,8 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
     for (uint32_t i = tid; i < m; i += kFinThreads) {
       const uint64_t c = kb[i];
       const uint32_t dp = (uint32_t)c;
-      const float dist = reorder ? exact_distance(ix, sq, dp) : ord2f((uint32_t)(c >> 32));
+      const float dist = i8 ? exact_distance_i8(ix, sqp, qnorm, dp)
+                            : (reorder ? exact_distance(ix, sq, dp) : ord2f((uint32_t)(c >> 32)));
       ka[i] = make_key(dist, dp);
     }
   }
@@ -294,7 +355,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
 cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const FinalizeArgs& a, cudaStream_t s) {
   int np2 = 2;
   while ((uint32_t)np2 < w.nover) np2 <<= 1;
-  const size_t smem = (size_t)np2 * 16 + (((size_t)ix.d + 3) & ~(size_t)3) * 4;
+  const size_t smem = (size_t)np2 * 16 + (((size_t)ix.d + 3) & ~(size_t)3) * 4 * (ix.dataset_i8 ? 2 : 1);
   cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   finalize_kernel<<<w.nq, kFinThreads, smem, s>>>(ix, w, a, np2);

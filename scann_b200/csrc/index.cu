@@ -98,6 +98,7 @@ struct scann_b200_index {
   std::mutex mu;
   std::vector<uint32_t> h_leaf_size;
   // persistent device arrays
+  DevBuf i8_inv, i8_norm;
   DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
       codes, slot_dp, slot_tie, dataset, dp_row, tok_b;
   // workspace
@@ -279,6 +280,36 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     v.slot_tie = ix->slot_tie.as<uint32_t>();
   }
   v.dataset = nullptr; v.dp_row = nullptr; v.dataset_bf16 = nullptr;
+  v.dataset_i8 = nullptr; v.i8_inv_mult = nullptr; v.i8_dp_norm = nullptr;
+  if (!d->dataset && !d->bf16_dataset && d->int8_dataset) {
+    // int8 reordering (exact_reordering { fixed_point { enabled: true } }; int8_dataset.npy + int8_multipliers.npy
+    // + dp_norms.npy): a quarter of the reorder gather bytes and device memory of the f32 rows
+    if (!d->int8_multipliers) return fail(SCANN_B200_INVALID_ARGUMENT, "int8_dataset needs int8_multipliers");
+    if (d->distance == SCANN_B200_SQUARED_L2 && !d->dp_norms)
+      return fail(SCANN_B200_INVALID_ARGUMENT, "int8 reordering under squared L2 needs dp_norms");
+    if (world == 1) {
+      UP(ix->dataset, d->int8_dataset, (size_t)N * D);
+    } else {
+      std::vector<uint32_t> rowmap(N, 0xFFFFFFFFu);
+      size_t rows = 0;
+      for (uint32_t i = rank; i < N; i += world) rowmap[i] = (uint32_t)rows++;
+      CU(ix->dataset.ensure(std::max<size_t>(rows, 1) * D));
+      if (rows)
+        CU(cudaMemcpy2D(ix->dataset.p, D, d->int8_dataset + (size_t)rank * D, (size_t)D * world, D, rows,
+                        cudaMemcpyHostToDevice));
+      UP(ix->dp_row, rowmap.data(), sizeof(uint32_t) * N);
+      v.dp_row = ix->dp_row.as<uint32_t>();
+    }
+    v.dataset_i8 = ix->dataset.as<int8_t>();
+    std::vector<float> inv(D);
+    for (uint32_t j = 0; j < D; ++j) inv[j] = 1.0f / d->int8_multipliers[j];  // reordering_helper.cc:407-412
+    UP(ix->i8_inv, inv.data(), sizeof(float) * D);
+    v.i8_inv_mult = ix->i8_inv.as<float>();
+    if (d->dp_norms) {
+      UP(ix->i8_norm, d->dp_norms, sizeof(float) * (size_t)N);
+      v.i8_dp_norm = ix->i8_norm.as<float>();
+    }
+  }
   if (!d->dataset && d->bf16_dataset) {
     // bfloat16 reordering (exact_reordering { bfloat16 { enabled: true } }, bfloat16_dataset.npy): half the
     // reorder gather bytes and device memory of the f32 rows
@@ -355,7 +386,7 @@ int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Pa
     p->k = (uint32_t)kb; p->npre = p->k; p->nover = p->k; p->P = 1;
     return 0;
   }
-  const bool has_reorder = ix->dev.dataset != nullptr || ix->dev.dataset_bf16 != nullptr;
+  const bool has_reorder = ix->dev.dataset != nullptr || ix->dev.dataset_bf16 != nullptr || ix->dev.dataset_i8 != nullptr;
   const int k = final_nn > 0 ? final_nn : ix->desc.default_final_nn;
   int npre = has_reorder ? (pre_nn > 0 ? pre_nn : ix->desc.default_pre_nn) : k;
   int P = leaves > 0 ? leaves : ix->desc.default_leaves;
@@ -680,7 +711,8 @@ int scann_b200_index_create(const scann_b200_index_desc* desc, scann_b200_index*
   if (rc) { delete ix; return rc; }
   // host pointers must not outlive this call
   ix->desc.centers = nullptr; ix->desc.tokens = nullptr; ix->desc.codes = nullptr; ix->desc.soar_codes = nullptr;
-  ix->desc.codebook = nullptr; ix->desc.dataset = nullptr; ix->desc.bf16_dataset = nullptr; ix->desc.block_dims = nullptr;
+  ix->desc.codebook = nullptr; ix->desc.dataset = nullptr; ix->desc.bf16_dataset = nullptr; ix->desc.int8_dataset = nullptr;
+  ix->desc.int8_multipliers = nullptr; ix->desc.dp_norms = nullptr; ix->desc.block_dims = nullptr;
   *out = ix;
   return 0;
 }

@@ -34,6 +34,10 @@ struct DevIndex {
   const float* dataset;       // [rows][D] f32 rows for exact reordering (NULL if none)
   const uint16_t* dataset_bf16;  // [rows][D] bf16 rows (bfloat16 reordering) when `dataset` is NULL
   const uint32_t* dp_row;     // [N] datapoint id -> row of `dataset` (NULL = identity)
+  // int8 (fixed point) reordering when `dataset` and `dataset_bf16` are NULL
+  const int8_t* dataset_i8;   // [rows][D]
+  const float* i8_inv_mult;   // [D] 1.0f / multiplier_by_dimension
+  const float* i8_dp_norm;    // [N] squared L2 norm of the original row, by datapoint id (squared L2 only)
   // tensor-core tokenization (prep.cu): centres as the bf16 operand [L][tok_kp] = [hi | hi | lo | 0]
   const void* tok_b;
   uint32_t tok_kp;

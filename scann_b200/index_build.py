@@ -35,6 +35,9 @@ class IndexArrays:
   codebook: Optional[np.ndarray] = None       # [B, 16, dpb] f32, zero padded (ah_codebook.pb)
   block_dims: Optional[np.ndarray] = None     # [B] i32 real dims of each block
   bf16_dataset: Optional[np.ndarray] = None   # [N, D] i16 (bfloat16_dataset.npy)
+  int8_dataset: Optional[np.ndarray] = None   # [N, D] i8 (int8_dataset.npy): fixed-point reordering
+  int8_multipliers: Optional[np.ndarray] = None  # [D] f32 (int8_multipliers.npy)
+  dp_norms: Optional[np.ndarray] = None       # [N] f32 (dp_norms.npy), squared L2 only
   n: int = 0
   d: int = 0
   residual: bool = False
@@ -203,6 +206,47 @@ def bfloat16_quantize(x):
   was_finite = ((bits >> 23) & 0xFF) != 0xFF
   r = np.where(exp_all_ones & was_finite, r - 1, r)
   return r.astype(np.uint16).view(np.int16)
+
+
+def int8_quantize(x, chunk=1 << 18):
+  """`ScalarQuantizeFloatDataset` with multiplier quantile 1.0 (`utils/scalar_quantization_helpers.cc:39-63,94-145`):
+  multiplier[d] = 127 / max|x[:, d]| (1 where the column is zero), value = clamp(round_half_away(x * multiplier)).
+  Returns (int8 [N, D], multipliers [D] f32)."""
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  mx = np.zeros(x.shape[1], np.float32)
+  for s in range(0, x.shape[0], chunk):
+    np.maximum(mx, np.abs(x[s:s + chunk]).max(0), out=mx)
+  mult = np.where(mx == 0, np.float32(1.0), np.float32(127.0) / np.where(mx == 0, np.float32(1.0), mx)).astype(np.float32)
+  out = np.empty(x.shape, np.int8)
+  for s in range(0, x.shape[0], chunk):
+    v = x[s:s + chunk] * mult[None, :]                       # f32 product, as Int8Quantize receives it
+    r = np.trunc(v)
+    r += np.where(np.abs(v - r) >= np.float32(0.5), np.sign(v), np.float32(0)).astype(np.float32)   # std::round
+    out[s:s + chunk] = np.clip(r, -128, 127).astype(np.int8)
+  return out, mult
+
+
+def squared_l2_norms(x, chunk=1 << 18):
+  """float(SquaredL2Norm(row)) with DenseSingleAccumulate's four strided double accumulators
+  (`utils/reduction.h:357-390`): what dp_norms.npy holds (`utils/reordering_helper.cc:586-591`)."""
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  n, d = x.shape
+  out = np.empty(n, np.float32)
+  d4 = d - d % 4
+  for s in range(0, n, chunk):
+    sq = x[s:s + chunk].astype(np.float64) ** 2
+    r = [np.cumsum(sq[:, l:d4:4], axis=1)[:, -1] if d4 else np.zeros(sq.shape[0]) for l in range(4)]
+    i = d4
+    r[2] = r[2] + r[3]
+    if i + 2 <= d:
+      r[0] = r[0] + sq[:, i]
+      r[1] = r[1] + sq[:, i + 1]
+      i += 2
+    r[1] = r[1] + r[2]
+    if i < d:
+      r[0] = r[0] + sq[:, i]
+    out[s:s + chunk] = (r[0] + r[1]).astype(np.float32)
+  return out
 
 
 def build_tree_ah(db, distance="dot_product", num_leaves=100, dims_per_block=2,

@@ -76,8 +76,13 @@ class _Plan:
       unimpl("residual squared-L2 tree-AH")
     r = self.reordering
     if r is not None:
-      if cfgmod.as_bool(r.path("fixed_point", "enabled"), False):
-        unimpl("int8 reordering")
+      if self.int8_reorder():
+        thr = cfgmod.as_float(r.path("fixed_point", "noise_shaping_threshold"), math.nan)
+        if thr is not None and not math.isnan(thr):
+          unimpl("noise-shaped int8 quantization of the reordering dataset")
+        quantile = cfgmod.as_float(r.path("fixed_point", "fixed_point_multiplier_quantile"), 1.0)
+        if quantile is not None and abs(quantile - 1.0) >= 0.001:
+          unimpl("fixed_point_multiplier_quantile != 1")
       if self.bf16_reorder():
         thr = cfgmod.as_float(r.path("bfloat16", "noise_shaping_threshold"), math.nan)
         if thr is not None and not math.isnan(thr):
@@ -93,6 +98,12 @@ class _Plan:
     """exact_reordering { bfloat16 { enabled: true } } (Bfloat16ReorderingHelper, utils/reordering_helper.cc:720-757)."""
     r = self.reordering
     return r is not None and cfgmod.as_bool(r.path("bfloat16", "enabled"), False)
+
+  def int8_reorder(self):
+    """exact_reordering { fixed_point { enabled: true } } (FixedPointFloatDense*ReorderingHelper,
+    utils/reordering_helper.cc:384-441,581-618; base/reordering_helper_factory.cc:106-175)."""
+    r = self.reordering
+    return r is not None and cfgmod.as_bool(r.path("fixed_point", "enabled"), False)
 
   def dims_per_block(self):
     proj = self.ah.get("projection")
@@ -157,6 +168,12 @@ class ScannNumpy:
       if plan.bf16_reorder():
         # reordering_helper.cc:729-730: the reordering dataset is Bfloat16QuantizeFloatDataset(original)
         arrays.bf16_dataset = index_build.bfloat16_quantize(db)
+        arrays.dataset = None
+      elif plan.int8_reorder():
+        # reordering_helper.cc:384-397,581-595: ScalarQuantizeFloatDataset(original, quantile 1.0) (+ row norms for L2)
+        arrays.int8_dataset, arrays.int8_multipliers = index_build.int8_quantize(db)
+        if plan.distance == "squared_l2":
+          arrays.dp_norms = index_build.squared_l2_norms(db)
         arrays.dataset = None
       self._finish(arrays, plan)
     except _lib.ScannB200Error as e:
@@ -245,6 +262,9 @@ class ScannNumpy:
     d.codebook = own(a.codebook, np.float32)
     d.dataset = own(a.dataset, np.float32)
     d.bf16_dataset = own(a.bf16_dataset, np.int16)
+    d.int8_dataset = own(a.int8_dataset, np.int8)
+    d.int8_multipliers = own(a.int8_multipliers, np.float32)
+    d.dp_norms = own(a.dp_norms, np.float32)
     d.overretrieve = a.overretrieve
     buf = C.create_string_buffer(1 << 16)
     rc = L.scann_b200_assets_save(path.encode(), C.byref(d), self._config_text.encode(), 1 if relative_path else 0,
@@ -307,6 +327,9 @@ def _arrays_from_desc(desc, plan):
   a = index_build.IndexArrays(distance="dot_product" if desc.distance == 0 else "squared_l2", dataset=None, n=n, d=d)
   a.dataset = arr(desc.dataset, (n, d), np.float32)
   a.bf16_dataset = arr(desc.bf16_dataset, (n, d), np.int16)
+  a.int8_dataset = arr(desc.int8_dataset, (n, d), np.int8)
+  a.int8_multipliers = arr(desc.int8_multipliers, (d,), np.float32)
+  a.dp_norms = arr(desc.dp_norms, (n,), np.float32)
   a.centers = arr(desc.centers, (L, d), np.float32)
   a.soar = bool(desc.soar)
   a.tokens = arr(desc.tokens, (n * (2 if a.soar else 1),), np.int32)

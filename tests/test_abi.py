@@ -27,8 +27,12 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
   from scann_b200 import _lib
-  # 6 u32/i32, 3 pointers, i32 (+pad), 5 pointers, float + 6 i32
-  assert ctypes.sizeof(_lib.IndexDesc) == 24 + 24 + 8 + 40 + 28 + 4
+  # 6 u32/i32, 3 pointers, i32 (+pad), 5 pointers, float + 6 i32 (+pad), 3 pointers (int8 reordering)
+  assert ctypes.sizeof(_lib.IndexDesc) == 24 + 24 + 8 + 40 + 28 + 4 + 24
+  # 5 u32 (+pad), 4 pointers, i32, float, double, i32 (+pad)
+  assert ctypes.sizeof(_lib.EncodeDesc) == 24 + 32 + 8 + 8 + 8
+  # 4 floats, 4 u64, u32 (+pad)
+  assert ctypes.sizeof(_lib.EncodeStats) == 16 + 32 + 8
   assert ctypes.sizeof(_lib.Stats) == 24 + 8 + 32 + 4 + 4 + 16 + 8
 
 

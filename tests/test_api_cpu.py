@@ -202,3 +202,51 @@ def test_load_errors_are_reported_not_fatal(tmp_path):
     scann_ops_pybind.load_searcher(str(tmp_path / "missing"))
   with pytest.raises(ValueError, match="No scann_assets.pbtxt"):
     scann_ops_pybind.load_searcher(str(tmp_path))
+
+
+def test_int8_reordering_assets_round_trip(tmp_path):
+  """int8_dataset.npy / int8_multipliers.npy / dp_norms.npy (scann.cc:568-593): names, dtypes, manifest, load."""
+  from scann_b200 import index_build
+  a, z = load_golden("l2_b16")
+  q8, mult = index_build.int8_quantize(a.dataset)
+  norms = index_build.squared_l2_norms(a.dataset)
+  L = _lib.lib()
+  keep = []
+
+  def own(x, dt):
+    y = np.ascontiguousarray(x, dtype=dt)
+    keep.append(y)
+    return _lib.ptr(y)
+
+  d = _lib.IndexDesc()
+  d.distance, d.n, d.d = 1, a.n, a.d
+  d.n_leaves, d.n_blocks, d.dims_per_block = a.centers.shape[0], a.codes.shape[1], a.codebook.shape[2]
+  d.block_dims, d.centers, d.tokens = own(a.block_dims, np.int32), own(a.centers, np.float32), own(a.tokens, np.int32)
+  d.codes, d.codebook = own(a.codes, np.uint8), own(a.codebook, np.float32)
+  d.int8_dataset, d.int8_multipliers, d.dp_norms = own(q8, np.int8), own(mult, np.float32), own(norms, np.float32)
+  cfg = scann_builder.ScannBuilder(a.dataset, 10, "squared_l2").tree(a.centers.shape[0], 5).score_ah(2).reorder(
+      50, quantize=scann_builder.ReorderType.INT8).create_config()
+  assert "fixed_point" in cfg
+  buf = C.create_string_buffer(1 << 16)
+  assert L.scann_b200_assets_save(str(tmp_path).encode(), C.byref(d), cfg.encode(), 1, buf, len(buf)) == 0, L.scann_b200_last_error()
+  manifest = buf.value.decode()
+  for t in ("INT8_DATASET_NPY", "INT8_MULTIPLIERS_NPY", "INT8_NORMS_NPY"):
+    assert t in manifest
+  assert not (tmp_path / "dataset.npy").exists()
+  f8 = np.load(tmp_path / "int8_dataset.npy")
+  assert f8.dtype == np.int8 and np.array_equal(f8, q8)
+  assert np.array_equal(np.load(tmp_path / "int8_multipliers.npy"), mult)
+  assert np.array_equal(np.load(tmp_path / "dp_norms.npy"), norms)
+  h = C.c_void_p()
+  assert L.scann_b200_assets_load(str(tmp_path).encode(), manifest.encode(), C.byref(h)) == 0, L.scann_b200_last_error()
+  d2 = _lib.IndexDesc()
+  assert L.scann_b200_assets_describe(h, C.byref(d2)) == 0
+  from scann_b200.scann_pybind import _Plan, _arrays_from_desc
+  plan = _Plan(L.scann_b200_assets_config(h).decode())
+  assert plan.int8_reorder()
+  b2 = _arrays_from_desc(d2, plan)
+  L.scann_b200_assets_free(h)
+  assert (d2.n, d2.d) == (a.n, a.d) and b2.dataset is None
+  np.testing.assert_array_equal(b2.int8_dataset, q8)
+  np.testing.assert_array_equal(b2.int8_multipliers, mult)
+  np.testing.assert_array_equal(b2.dp_norms, norms)

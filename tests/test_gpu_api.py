@@ -128,3 +128,31 @@ def test_bfloat16_reordering_through_the_builder(tmp_path):
   i2, d2 = l2.search_batched(q)
   np.testing.assert_array_equal(idx, i2)
   np.testing.assert_array_equal(dist.view(np.uint32), d2.view(np.uint32))
+
+
+def test_int8_reordering_through_the_builder(tmp_path):
+  """reorder(N, quantize=ReorderType.INT8): int8 assets, round trip, distances of the dequantized rows."""
+  from scann_b200 import scann_ops_pybind, scann_builder, index_build
+  db, q = make_data()
+  for dist in ("dot_product", "squared_l2"):
+    out = tmp_path / dist
+    out.mkdir()
+    s = (scann_ops_pybind.builder(db, 10, dist).tree(27, 10, min_partition_size=10).score_ah(2)
+         .reorder(60, quantize=scann_builder.ReorderType.INT8).build())
+    idx, dist_v = s.search_batched(q)
+    q8, mult = index_build.int8_quantize(db)
+    deq = q8.astype(np.float64) / mult.astype(np.float64)[None, :]
+    rows = deq[idx.astype(np.int64)]
+    if dist == "dot_product":
+      truth = np.einsum("qd,qkd->qk", q.astype(np.float64), rows)
+    else:
+      truth = ((q.astype(np.float64) ** 2).sum(1)[:, None] + (db.astype(np.float64) ** 2).sum(1)[idx.astype(np.int64)]
+               - 2 * np.einsum("qd,qkd->qk", q.astype(np.float64), rows))
+    np.testing.assert_allclose(dist_v, truth, rtol=1e-4, atol=1e-3)
+    s.serialize(str(out))
+    assert (out / "int8_dataset.npy").exists() and (out / "int8_multipliers.npy").exists()
+    assert (out / "dp_norms.npy").exists() == (dist == "squared_l2") and not (out / "dataset.npy").exists()
+    l2 = scann_ops_pybind.load_searcher(str(out))
+    i2, d2 = l2.search_batched(q)
+    np.testing.assert_array_equal(idx, i2)
+    np.testing.assert_array_equal(dist_v.view(np.uint32), d2.view(np.uint32))

@@ -254,3 +254,37 @@ def test_bf16_reordering_is_bit_exact(kw):
   # and it differs from f32 reordering somewhere (the bf16 rows really are used)
   _, df = c.native.search_batched(c.q)
   assert not np.array_equal(df.view(np.uint32), d1.view(np.uint32))
+
+
+# ---- int8 (fixed point) reordering (FixedPointFloatDense*ReorderingHelper) ----
+@pytest.mark.parametrize("kw", [dict(), dict(soar=1.5), dict(dpb=3, d=99, leaves=60, n=9000),
+                                dict(distance="squared_l2", d=64, leaves=50, n=10000),
+                                dict(n=3000, leaves=30, d=6, dpb=2, probe=5, pre=40)],
+                         ids=["dot", "soar", "d99", "l2", "d6"])
+def test_int8_reordering_is_bit_exact(kw):
+  import copy
+  import oracle
+  from scann_b200 import _lib, index_build
+  c = get_case(**kw)
+  a = copy.copy(c.arrays)
+  a.int8_dataset, a.int8_multipliers = index_build.int8_quantize(c.db)
+  if a.distance == "squared_l2":
+    a.dp_norms = index_build.squared_l2_norms(c.db)
+  a.dataset = None
+  o = oracle.OracleIndex(a, c.probe, c.pre, c.k)
+  g = _lib.NativeIndex(a, c.probe, c.pre, c.k)
+  i0, d0 = o.search_batched(c.q)
+  i1, d1 = g.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  # distances are those of the dequantized rows, close to the f32 reordering
+  _, df = c.native.search_batched(c.q)
+  assert not np.array_equal(df.view(np.uint32), d1.view(np.uint32))
+  deq = a.int8_dataset.astype(np.float64) / a.int8_multipliers.astype(np.float64)[None, :]
+  rows = deq[i1.astype(np.int64)]
+  qq = c.q.astype(np.float64)
+  if a.distance == "dot_product":
+    truth = np.einsum("qd,qkd->qk", qq, rows)
+  else:
+    truth = (qq ** 2).sum(1)[:, None] + a.dp_norms[i1.astype(np.int64)].astype(np.float64) - 2 * np.einsum("qd,qkd->qk", qq, rows)
+  np.testing.assert_allclose(d1, truth, rtol=1e-4, atol=1e-3)

@@ -84,3 +84,23 @@ def test_sharded_bf16_reordering_equals_unsharded(kw, world):
   i2, d2, _ = run_sharded(case, world)
   np.testing.assert_array_equal(i1, i2)
   np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw,world", [(dict(), 2), (dict(distance="squared_l2", d=64, leaves=50, n=10000), 3)])
+def test_sharded_int8_reordering_equals_unsharded(kw, world):
+  """Shards hold the int8 rows of their own datapoints; multipliers and row norms are replicated."""
+  import copy
+  import types
+  from scann_b200 import _lib, index_build
+  c = get_case(**kw)
+  a = copy.copy(c.arrays)
+  a.int8_dataset, a.int8_multipliers = index_build.int8_quantize(c.db)
+  if a.distance == "squared_l2":
+    a.dp_norms = index_build.squared_l2_norms(c.db)
+  a.dataset = None
+  full = _lib.NativeIndex(a, c.probe, c.pre, c.k)
+  i1, d1 = full.search_batched(c.q)
+  case = types.SimpleNamespace(arrays=a, q=c.q, probe=c.probe, pre=c.pre, k=c.k)
+  i2, d2, _ = run_sharded(case, world)
+  np.testing.assert_array_equal(i1, i2)
+  np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))

@@ -107,3 +107,67 @@ def test_padding_when_fewer_candidates_than_k():
   oi = oracle.OracleIndex(a, 1, 5, 10)
   idx, dist = oi.search_batched(z["queries"][:3], final_nn=10, pre_nn=5, leaves=1)
   assert np.isnan(dist[:, 5:]).all() and (idx[:, 5:] == 0).all() and not np.isnan(dist[:, :5]).any()
+
+
+# ---- int8 (fixed point) reordering: FixedPointFloatDense*ReorderingHelper ----
+def _np_int8_distance(q, x8, mult, dot, norms=None):
+  """Independent numpy restatement: q' = (1/mult) * q, eight fnmadd lanes, 4-wide step, HorizontalSum3X, scalar tail."""
+  from helpers import f32, fma32
+  inv = f32(np.float32(1.0) / mult)
+  qp = f32(inv * q)
+  n = len(q)
+  xf = x8.astype(np.float32)                      # [rows, D]
+  a = np.zeros((xf.shape[0], 8), np.float32)
+  j = 0
+  while j + 8 <= n:
+    a = fma32(np.broadcast_to(-qp[None, j:j + 8], a.shape), xf[:, j:j + 8], a)
+    j += 8
+  if j + 4 <= n:
+    a[:, :4] = fma32(np.broadcast_to(-qp[None, j:j + 4], (xf.shape[0], 4)), xf[:, j:j + 4], a[:, :4])
+    j += 4
+  r = f32(f32(f32(a[:, 0] + a[:, 4]) + f32(a[:, 2] + a[:, 6])) + f32(f32(a[:, 1] + a[:, 5]) + f32(a[:, 3] + a[:, 7])))
+  while j < n:
+    r = fma32(np.full_like(r, -qp[j]), xf[:, j], r)
+    j += 1
+  if dot:
+    return r
+  qn = np.float32((q.astype(np.float64) ** 2).sum())
+  return f32(f32(qn + norms) + f32(np.float32(2.0) * r))
+
+
+@pytest.mark.parametrize("name", ["dot_b16", "l2_b16"])
+def test_int8_reordering_matches_numpy_and_f64(name):
+  import copy
+  from scann_b200 import index_build
+  a, z = load_golden(name)
+  a = copy.copy(a)
+  db = a.dataset
+  a.int8_dataset, a.int8_multipliers = index_build.int8_quantize(db)
+  dot = a.distance == "dot_product"
+  if not dot:
+    a.dp_norms = index_build.squared_l2_norms(db)
+  a.dataset = None
+  # quantization: |x * mult - q| <= 0.5, the extreme value of every column maps to +-127
+  v = db * a.int8_multipliers[None, :]
+  assert np.abs(v - a.int8_dataset).max() <= 0.5 + 1e-4
+  assert (np.abs(a.int8_dataset).max(0) == 127).all()
+  oi = oracle.OracleIndex(a, int(z["probe"]), int(z["pre"]), int(z["k"]))
+  q = z["queries"][:6]
+  dps = np.arange(0, a.n, 7, dtype=np.uint32)
+  for qi in q:
+    got = oi.exact_distances(qi, dps)
+    ref = _np_int8_distance(qi, a.int8_dataset[dps], a.int8_multipliers, dot, None if dot else a.dp_norms[dps])
+    # the float64 emulation of the f32 fma double-rounds in rare cases: allow isolated 1-ulp differences
+    same = got.view(np.uint32) == ref.view(np.uint32)
+    assert same.mean() > 0.999
+    np.testing.assert_allclose(got, ref, rtol=3e-7, atol=1e-6)
+    deq = a.int8_dataset[dps].astype(np.float64) / a.int8_multipliers.astype(np.float64)[None, :]
+    if dot:
+      truth = -(deq @ qi.astype(np.float64))
+    else:  # the reference's formula: |q|^2 + |x|^2 (original row) - 2 <q, dequantized x>
+      truth = (qi.astype(np.float64) ** 2).sum() + a.dp_norms[dps].astype(np.float64) - 2.0 * (deq @ qi.astype(np.float64))
+    np.testing.assert_allclose(got, truth, rtol=1e-4, atol=1e-3)
+  idx, dist = oi.search_batched(z["queries"])
+  f = oracle.OracleIndex(load_golden(name)[0], int(z["probe"]), int(z["pre"]), int(z["k"]))
+  fidx, _ = f.search_batched(z["queries"])
+  assert np.mean([len(set(idx[i].tolist()) & set(fidx[i].tolist())) / idx.shape[1] for i in range(len(idx))]) > 0.9
