@@ -54,6 +54,7 @@ struct SoarArgs {
   const float* cnorm;      // [L] ||c||^2 (fnmadd chain)
   const float* row;        // [n][L]: x.c (row_is_dot) or squared distances
   const float* row2;       // [n][L]: rhat.c from the second GEMM, or NULL (no projection pruning)
+  const uint8_t* row_exact; // [n] or NULL: 1 = this row of `row` holds exact squared distances (tokenizer fallback)
   float* rhat;             // [n][D] normalised residuals (written by rhat_kernel, read by soar_kernel)
   const int32_t* near;     // [n][P] nearest centres, sorted by (distance, centre); near[.][0] is the primary
   int32_t* sec;            // [n] out
@@ -177,13 +178,14 @@ soar_kernel(SoarArgs a) {
   const float lam_lo = a.lambda * (1.f - 4.76837158e-7f);
   const float* row = a.row + (size_t)i * a.L;
   const float* row2 = a.row2 ? a.row2 + (size_t)i * a.L : nullptr;
+  const bool is_dot = a.row_is_dot && !(a.row_exact && a.row_exact[i]);
   uint32_t ncand = 0;
   for (uint32_t base = 0; base < a.L; base += 32) {
     const uint32_t l = base + lane;
     bool pass = false;
     if (l < a.L) {
       const float v = row[l];
-      const float ap = a.row_is_dot ? __fsub_rn(__fadd_rn(__ldg(a.cnorm + l), qn), __fmul_rn(2.f, v)) : v;
+      const float ap = is_dot ? __fsub_rn(__fadd_rn(__ldg(a.cnorm + l), qn), __fmul_rn(2.f, v)) : v;
       float lb = __fmul_rd(__fsub_rd(ap, E1), shrink);
       if (row2) {
         const float p = fmaxf(__fsub_rd(fabsf(__fsub_rn(xr, row2[l])), E2), 0.f);
@@ -584,7 +586,7 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
   uint32_t R = 16384;
   { const char* e = getenv("SCANN_B200_ENCODE_CHUNK"); if (e && atoi(e) > 0) R = (uint32_t)atoi(e); }
   R = std::min(R, N);
-  Buf xbuf[2], dist, tok_a, near, bias, sec, toks[2], codes[2], scodes[2], counters, rhat, dist2;
+  Buf xbuf[2], dist, tok_a, near, bias, sec, toks[2], codes[2], scodes[2], counters, rhat, dist2, fbflag;
   for (int b = 0; b < 2; ++b) {
     CU(xbuf[b].alloc(sizeof(float) * (size_t)R * D));
     CU(toks[b].alloc(sizeof(int32_t) * (size_t)R * npd));
@@ -596,6 +598,8 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
   CU(near.alloc(sizeof(int32_t) * (size_t)R * P));
   CU(bias.alloc(sizeof(float) * (size_t)R * P));
   CU(sec.alloc(sizeof(int32_t) * R));
+  CU(fbflag.alloc(R));
+  v.tok_fallback_flag = fbflag.as<uint8_t>();
   const bool row_is_dot = sb::tokenize_tensor_path(v, P);
   // SOAR: the projection term is pruned with a second tensor-core GEMM (rhat x centres) when the centre operand
   // exists; small trees (SIMT tokenization) prune by distance only
@@ -681,6 +685,7 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
     CU(cudaEventRecord(sl.in_done, st_in.s));
     CU(cudaStreamWaitEvent(s, sl.in_done, 0));
     CU(cudaEventRecord(sl.t[0], s));
+    CU(cudaMemsetAsync(fbflag.p, 0, nr, s));
     int launches = 0;
     CU(sb::launch_tokenize_topp(v, xb, nr, P, dist.as<float>(), tok_a.p, near.as<int32_t>(), bias.as<float>(),
                                 c_fallbacks, s, &launches));
@@ -692,6 +697,7 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
       a.n = nr; a.L = L; a.D = D; a.P = P; a.row_is_dot = row_is_dot ? 1 : 0;
       a.lambda = d->soar_lambda; a.eps_rel = eps_rel; a.cmax = v.center_max_norm;
       a.rhat = rhat.as<float>();
+      a.row_exact = fbflag.as<uint8_t>();
       const unsigned wgrid = (nr + sb::kSoarThreads / 32 - 1) / (sb::kSoarThreads / 32);
       sb::rhat_kernel<<<wgrid, sb::kSoarThreads, 0, s>>>(a);
       CU(cudaGetLastError());

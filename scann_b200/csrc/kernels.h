@@ -42,6 +42,9 @@ struct DevIndex {
   const void* tok_b;
   uint32_t tok_kp;
   float center_max_norm;      // >= max_l ||c_l||
+  // optional [nq] bytes: set to 1 for rows whose tensor-core pre-filter fell back to exact distances (the row of
+  // the distance matrix then holds exact distances instead of dot products); only the index-build stage reads it
+  uint8_t* tok_fallback_flag;
 };
 
 struct ScanWork {

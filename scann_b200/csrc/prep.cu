@@ -654,9 +654,162 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
     }
   } else {
     if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1u);
+    if (tid == 0 && ix.tok_fallback_flag) ix.tok_fallback_flag[qi] = 1;
     for (int i = tid; i < L; i += kRefineThreads) row[i] = exact(i);
     __syncthreads();
     if (warp == 0) warp_topp_exact(row, L, P, Ppow2, hist, skeys, lane, lout, bout);
+  }
+}
+
+// Streaming refinement for long rows and P <= 128: one warp per query, two coalesced passes over the row instead of a
+// radix select on a shared-memory image of it.  Pass 1 keeps the minimum of 128 strided sub-rows (4 per lane); the
+// P-th smallest of those minima is an upper bound U of the P-th smallest approximate distance (P different sub-rows
+// each hold an element <= U).  Pass 2 collects the centres with approx <= U + 2 eps -- a superset of the exact top P,
+// see above -- which get the exact chain and a sort by (distance, leaf).  More than kStreamCand candidates (degenerate
+// rows) fall back to exact distances for all centres.
+// MEASURED AND REJECTED as the default (kept behind SCANN_B200_TOKENIZE=stream, bit-exact, tested): with one warp per
+// query the two passes are a serial chain of L / 256 round trips to HBM per warp; 10k queries x 40k centres take
+// 3.2 ms against 2.65 ms for the radix refinement (CTA per query, row staged in shared memory), 8000 centres 0.71
+// against 0.38 ms, and the index-build stage's tokenization 1.24 s against 0.75 s per 20M rows.
+constexpr int kStreamCand = 256;
+__global__ void __launch_bounds__(256)
+topp_stream_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ S, int nq, int P, int Ppow2,
+                   float eps_rel, int32_t* __restrict__ leaves, float* __restrict__ bias, uint32_t* fallbacks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= nq) return;
+  const int L = (int)ix.L, D = (int)ix.d, Dp = (D + 3) & ~3;
+  unsigned char* base = smem_raw + (size_t)warp * ((size_t)kStreamCand * 8 + 1024 + (size_t)Dp * 4);
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(base);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base + (size_t)kStreamCand * 8);
+  float* mins = reinterpret_cast<float*>(hist);  // 128 floats; dead before `hist` is used
+  float* sq = reinterpret_cast<float*>(base + (size_t)kStreamCand * 8 + 1024);
+  float* row = S + (size_t)qi * L;
+  const bool sql2 = ix.distance == 1;
+  const uint32_t lt = (1u << lane) - 1u;
+
+  float ssq = 0.f;
+  for (int k = lane; k < Dp; k += 32) {
+    const float v = k < D ? q[(size_t)qi * D + k] : 0.f;
+    sq[k] = v;
+    ssq = fmaf(v, v, ssq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, o);
+  __syncwarp();
+  float qn = 0.f;
+  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
+    double acc = 0.0;
+    if (lane == 0) for (int k = 0; k < D; ++k) acc += (double)sq[k] * (double)sq[k];
+    qn = (float)__shfl_sync(0xFFFFFFFFu, acc, 0);
+  }
+  const float qnorm = sqrtf(ssq) * 1.001f, cmax = ix.center_max_norm;
+  float eps = eps_rel * qnorm * cmax;
+  if (sql2) eps = 2.f * eps + (float)(D + 8) * 1.1920929e-7f * (qn + cmax * cmax + 2.f * qnorm * cmax);
+  auto approx = [&](int i) -> float {
+    const float sdot = row[i];
+    return sql2 ? __fsub_rn(__fadd_rn(__ldg(ix.center_sqnorm + i), qn), __fmul_rn(2.f, sdot)) : -sdot;
+  };
+  // ---- pass 1: minima of 128 strided sub-rows ----
+  const float inf = __int_as_float(0x7F800000);
+  float m[4] = {inf, inf, inf, inf};
+  for (int i0 = 0; i0 < L; i0 += 256) {  // eight independent loads in flight per lane
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + 32 * j + lane;
+      v[j] = i < L ? approx(i) : inf;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j & 3] = fminf(m[j & 3], v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mins[4 * lane + j] = m[j];
+  __syncwarp();
+  float U = inf;
+  {
+    int rank[4] = {0, 0, 0, 0};
+    for (int t = 0; t < 128; ++t) {
+      const float w = mins[t];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rank[j] += (w < m[j] || (w == m[j] && t < 4 * lane + j)) ? 1 : 0;
+    }
+    float val = inf;
+    bool has = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (rank[j] == P - 1) { has = true; val = m[j]; }
+    const uint32_t hm = __ballot_sync(0xFFFFFFFFu, has);
+    if (hm) U = __shfl_sync(0xFFFFFFFFu, val, __ffs(hm) - 1);
+  }
+  __syncwarp();
+  const float thr = __fadd_ru(U, __fmul_ru(2.f, eps));
+  // ---- pass 2: candidates ----
+  uint32_t count = 0;
+  for (int i0 = 0; i0 < L; i0 += 256) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + 32 * j + lane;
+      v[j] = i < L ? approx(i) : inf;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + 32 * j + lane;
+      const bool c = i < L && !(v[j] > thr);  // NaN is a candidate
+      const uint32_t mk = __ballot_sync(0xFFFFFFFFu, c);
+      if (mk) {
+        if (c) {
+          const uint32_t pos = count + __popc(mk & lt);
+          if (pos < (uint32_t)kStreamCand) skeys[pos] = (uint64_t)(uint32_t)i;
+        }
+        count += __popc(mk);
+      }
+    }
+  }
+  __syncwarp();
+  auto exact = [&](int idx) -> float {
+    const float* c = ix.centers + (size_t)idx * D;
+    float acc = sql2 ? __fadd_rn(ix.center_sqnorm[idx], qn) : 0.f;
+    const float scale2 = sql2 ? 2.0f : 1.0f;
+    if ((D & 3) == 0) {
+      for (int k = 0; k < D; k += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(c + k));
+        acc = __fmaf_rn(-sq[k], __fmul_rn(v.x, scale2), acc);
+        acc = __fmaf_rn(-sq[k + 1], __fmul_rn(v.y, scale2), acc);
+        acc = __fmaf_rn(-sq[k + 2], __fmul_rn(v.z, scale2), acc);
+        acc = __fmaf_rn(-sq[k + 3], __fmul_rn(v.w, scale2), acc);
+      }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < D; ++k) acc = __fmaf_rn(-sq[k], __fmul_rn(__ldg(c + k), scale2), acc);
+    }
+    return acc;
+  };
+  int32_t* lout = leaves + (size_t)qi * P;
+  float* bout = bias + (size_t)qi * P;
+  if (count <= (uint32_t)kStreamCand) {
+    int ns = 2;
+    while ((uint32_t)ns < count) ns <<= 1;
+    for (int j = lane; j < ns; j += 32) {
+      const bool live = (uint32_t)j < count;
+      const uint32_t idx = live ? (uint32_t)skeys[j] : 0u;
+      const float e = live ? exact((int)idx) : 0.f;
+      skeys[j] = live ? (((uint64_t)f2ord(e) << 32) | idx) : kKeyMax;
+    }
+    __syncwarp();
+    warp_bitonic_sort(skeys, ns, lane);
+    for (int i = lane; i < P; i += 32) {
+      const uint64_t k = i < ns ? skeys[i] : kKeyMax;
+      lout[i] = (k == kKeyMax) ? -1 : (int32_t)(uint32_t)k;
+      bout[i] = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
+    }
+  } else {
+    if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1u);
+    if (lane == 0 && ix.tok_fallback_flag) ix.tok_fallback_flag[qi] = 1;
+    for (int i = lane; i < L; i += 32) row[i] = exact(i);
+    __syncwarp();
+    warp_topp_exact(row, L, P, Ppow2, hist, skeys, lane, lout, bout);
   }
 }
 
@@ -664,7 +817,7 @@ bool tokenize_tensor_path(const DevIndex& ix, uint32_t P) {
   if (!ix.tok_b || P + 32 > (uint32_t)kRefineMaxCand || ix.d > 2048) return false;
   const char* e = getenv("SCANN_B200_TOKENIZE");
   if (e && !strcmp(e, "simt")) return false;
-  if (e && !strcmp(e, "tcgen05")) return true;
+  if (e && (!strcmp(e, "tcgen05") || !strcmp(e, "stream"))) return true;
   return ix.L >= 256;  // below that the SIMT GEMM is already negligible
 }
 
@@ -685,6 +838,23 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   while (cp < (int)P + 32) cp <<= 1;
   if (cp < pp) cp = pp;
   const float eps_rel = (float)ix.tok_kp * 4.76837158e-7f + 3.05175781e-5f;  // K * 2^-21 + 2^-15
+  {
+    // SCANN_B200_TOKENIZE=stream: the streaming refinement (P <= 128)
+    const char* env = getenv("SCANN_B200_TOKENIZE");
+    const bool force_stream = env && !strcmp(env, "stream"), force_radix = env && !strcmp(env, "tcgen05");
+    (void)force_radix;
+    if (P <= 128 && force_stream) {  // measured slower than the radix refinement (see the kernel's comment): opt-in only
+      int sp = 2;
+      while (sp < (int)P) sp <<= 1;
+      const size_t per_warp = (size_t)kStreamCand * 8 + 1024 + (size_t)((ix.d + 3) & ~3u) * 4;
+      const size_t bytes = per_warp * 8;
+      e = cudaFuncSetAttribute(topp_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+      topp_stream_kernel<<<(nq + 7) / 8, 256, bytes, s>>>(ix, q, dist, (int)nq, (int)P, sp, eps_rel, leaves, bias, fallbacks);
+      if (launches) *launches += 3;
+      return cudaGetLastError();
+    }
+  }
   if (cp < 128) cp = 128;  // the in-register sort writes 128 keys back
   const size_t smem = (size_t)cp * 8 + (size_t)((ix.d + 3) & ~3u) * 4;
 #define SB_REFINE(kS, kT, bytes)                                                                                  \

@@ -103,6 +103,26 @@ def test_encode_chunking_and_degenerate_rows(monkeypatch):
   assert (tokens[1:600:2] == -1).all() and not (tokens == 17).any()
 
 
+@pytest.mark.parametrize("mode", ["stream", "tcgen05"])
+def test_encode_with_streaming_tokenizer_and_fallback_rows(mode, monkeypatch):
+  """The streaming top-P refinement (opt-in) under the encoder, incl. rows that fall back to exact
+  distances (zero vectors, many equal centres): the SOAR pruning must then read that row as distances."""
+  import oracle
+  from scann_b200 import _lib
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", mode)
+  x, centers = _mixture(3000, 48, 400, 17, 1.0, True)
+  centers[100:140] = centers[99]               # 41 equal centres: a crowded tie window
+  x[:50] = 0.0                                 # zero rows: every centre ties in the pre-filter
+  x[50:90] = centers[99] * 1.0001
+  cb, bd = _codebook(x[100:], centers, 2, 9)
+  tokens, codes, soar_codes, st = _lib.encode_database(x, centers, cb, bd, soar_lambda=1.5)
+  assert st["tokenize_fallbacks"] > 0
+  o_tokens, o_codes, o_soar, _ = oracle.encode_database(x, centers, cb, bd, soar_lambda=1.5, threads=8)
+  np.testing.assert_array_equal(tokens, o_tokens)
+  np.testing.assert_array_equal(codes, o_codes)
+  np.testing.assert_array_equal(soar_codes, o_soar)
+
+
 def test_encode_rejects_bad_arguments():
   from scann_b200 import _lib
   x, centers = _mixture(100, 16, 8, 1, 1.0, False)

@@ -128,7 +128,7 @@ TOK_CASES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["tcgen05", "simt"])
+@pytest.mark.parametrize("mode", ["tcgen05", "simt", "stream"])
 @pytest.mark.parametrize("kw", TOK_CASES, ids=[str(i) for i in range(len(TOK_CASES))])
 def test_tokenize_modes_bit_exact(kw, mode, monkeypatch):
   monkeypatch.setenv("SCANN_B200_TOKENIZE", mode)
@@ -145,10 +145,11 @@ def test_tokenize_modes_bit_exact(kw, mode, monkeypatch):
 
 @pytest.mark.parametrize("kw", [dict(n=6000, leaves=300, probe=40, pre=50, d=32),
                                 dict(distance="squared_l2", d=64, leaves=50, n=10000)], ids=["dot", "l2"])
-def test_tokenize_degenerate_queries_fall_back_to_exact(kw, monkeypatch):
+@pytest.mark.parametrize("mode", ["tcgen05", "stream"])
+def test_tokenize_degenerate_queries_fall_back_to_exact(kw, mode, monkeypatch):
   """Zero / tiny / huge / duplicated queries: the candidate window of the pre-filter degenerates (every centre ties),
   the kernel must fall back to exact distances and still match the oracle bit for bit."""
-  monkeypatch.setenv("SCANN_B200_TOKENIZE", "tcgen05")
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", mode)
   c = get_case(**kw)
   q = c.q[:64].copy()
   q[0] = 0.0

@@ -22,6 +22,8 @@ def main():
   ap.add_argument("--n", type=int, default=20_000_000)
   ap.add_argument("--cases", default="10000:24:auto,10000:24:1")
   ap.add_argument("--steps", type=int, default=5)
+  ap.add_argument("--leaves-total", type=int, default=0, help="override the number of leaves of the index")
+  ap.add_argument("--env", default="", help="comma-separated NAME=VALUE pairs set before each case list pass")
   args = ap.parse_args()
   import torch
   import bench
@@ -31,6 +33,11 @@ def main():
     wl["leaves"] = max(16, int(round(wl["leaves"] * args.n / wl["n"])))
     wl["clusters"] = max(64, int(round(wl["clusters"] * args.n / wl["n"])))
     wl["n"] = args.n
+  if args.leaves_total:
+    wl["leaves"] = args.leaves_total
+  for kv in [e for e in args.env.split(",") if e]:
+    name, val = kv.split("=")
+    os.environ[name] = val
   dev = torch.device("cuda", 0)
   db, q = bench.make_data(wl)
   arrays = bench.build_arrays(wl, db, dev)
@@ -40,8 +47,13 @@ def main():
   truth = bench.exact_topk(d_q, db, k, dev, l2=wl.get("distance") == "squared_l2")
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
   for case in args.cases.split(","):
-    nq_s, p_s, tp = case.split(":")
+    parts = case.split(":")
+    nq_s, p_s, tp = parts[:3]
     nq, p = int(nq_s), int(p_s)
+    if len(parts) > 3:
+      os.environ["SCANN_B200_TOKENIZE"] = parts[3]
+    else:
+      os.environ.pop("SCANN_B200_TOKENIZE", None)
     if tp == "auto":
       os.environ.pop("SCANN_B200_TWO_PHASE", None)
     else:
@@ -64,7 +76,8 @@ def main():
         agg[key] = agg.get(key, 0) + val
     s = args.steps
     print(json.dumps({
-        "nq": nq, "leaves_to_search": p, "two_phase": tp, "recall_at_10": round(rec, 4),
+        "nq": nq, "leaves_to_search": p, "two_phase": tp, "tokenize": os.environ.get("SCANN_B200_TOKENIZE", "auto"),
+        "leaves": wl["leaves"], "recall_at_10": round(rec, 4),
         "ms_total": agg["ms_total"] / s, "ms_scan": agg["ms_scan"] / s, "ms_compact": agg["ms_compact"] / s,
         "ms_pilot": agg["ms_pilot"] / s, "ms_finalize": agg["ms_finalize"] / s, "ms_tokenize": agg["ms_tokenize"] / s,
         "qps": nq * s / (agg["ms_total"] / 1e3), "cand_per_query": agg["cand_sum"] / s / nq,
