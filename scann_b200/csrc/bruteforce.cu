@@ -107,8 +107,11 @@ struct GemmArgs {
   uint32_t num_kb;               // ceil(K / 64)
   // kEpiFilter: candidate buffers
   uint64_t* buf; uint32_t* cnt; const uint64_t* tau; uint32_t* ovf; uint32_t cap;
-  // kEpiStore: raw accumulators, out[a_row * ld + b_row]
+  // kEpiStore: raw accumulators, out[a_row * ld + b_row]; optionally the maximum of every 32-column chunk,
+  // cmax[a_row * ld_c + b_row / 32] (the chunk pre-selection of the tokenizer, prep.cu)
   float* out; uint32_t ld;
+  float* cmax; uint32_t ld_c;
+  const float* cbias;  // with cmax: per-column bias b; the chunk statistic becomes -min_j(b[j] - 2 acc[j]) (squared L2)
   int prof;   // debug: CTA 0 prints where its MMA thread waited (SCANN_B200_GEMM_PROFILE=1)
 };
 
@@ -290,6 +293,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)(c * 32), v);
           const uint32_t col = n0 + c * 32;
+          if (qvalid && a.cmax && col < a.row1) {
+            float mx = __int_as_float(0xFF800000);
+            if (!a.cbias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < a.row1) mx = fmaxf(mx, __uint_as_float(v[j]));
+            } else if (col + 32 <= a.row1) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(a.cbias + col + j));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j])), b.x));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j + 1])), b.y));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j + 2])), b.z));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j + 3])), b.w));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < a.row1) mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j])), __ldg(a.cbias + col + j)));
+            }
+            a.cmax[(size_t)q * a.ld_c + (col >> 5)] = mx;
+          }
           if (qvalid) {
             if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
 #pragma unroll
@@ -475,6 +500,28 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t v[32];
           tmem_ld32(tbase + (uint32_t)(c * 32), v);
           const uint32_t col = n0 + c * 32;
+          if (qvalid && a.cmax && col < a.row1) {
+            float mx = __int_as_float(0xFF800000);
+            if (!a.cbias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < a.row1) mx = fmaxf(mx, __uint_as_float(v[j]));
+            } else if (col + 32 <= a.row1) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(a.cbias + col + j));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j])), b.x));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j + 1])), b.y));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j + 2])), b.z));
+                mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j + 3])), b.w));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < a.row1) mx = fmaxf(mx, __fsub_rn(__fmul_rn(2.f, __uint_as_float(v[j])), __ldg(a.cbias + col + j)));
+            }
+            a.cmax[(size_t)q * a.ld_c + (col >> 5)] = mx;
+          }
           if (qvalid) {
             if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
 #pragma unroll
@@ -745,7 +792,8 @@ uint32_t bf_query_rows_pad(uint32_t nq) { return bf_m_pad(nq); }
 // Plain C[a_row][b_row] = sum_k A[a_row][k] * B[b_row][k] (bf16 operands, fp32 accumulate and output): the
 // tokenization pre-filter's GEMM (prep.cu), K = the concatenated hi/lo terms.
 cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows_pad, const void* b_operand,
-                         uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s) {
+                         uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s, float* cmax,
+                         uint32_t ld_c, const float* cbias) {
   CUtensorMap tmA, tmB;
   cudaError_t e = make_tmap(&tmA, a_operand, a_rows_pad, kpitch, kpitch, bf::BM);
   if (e != cudaSuccess) return e;
@@ -756,6 +804,7 @@ cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows
   a.mt = a_rows_pad / bf::BM; a.nt = (b_rows + bf::BN - 1) / bf::BN;
   a.num_kb = (kpitch + bf::BK - 1) / bf::BK;
   a.out = out; a.ld = ld;
+  a.cmax = cmax; a.ld_c = ld_c; a.cbias = cbias;
   return launch_gemm<1, bf::kEpiStore>(tmA, tmB, a, s);
 }
 

@@ -586,7 +586,7 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
   uint32_t R = 16384;
   { const char* e = getenv("SCANN_B200_ENCODE_CHUNK"); if (e && atoi(e) > 0) R = (uint32_t)atoi(e); }
   R = std::min(R, N);
-  Buf xbuf[2], dist, tok_a, near, bias, sec, toks[2], codes[2], scodes[2], counters, rhat, dist2, fbflag;
+  Buf xbuf[2], dist, tok_a, near, bias, sec, toks[2], codes[2], scodes[2], counters, rhat, dist2, fbflag, tok_cmax;
   for (int b = 0; b < 2; ++b) {
     CU(xbuf[b].alloc(sizeof(float) * (size_t)R * D));
     CU(toks[b].alloc(sizeof(int32_t) * (size_t)R * npd));
@@ -600,6 +600,8 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
   CU(sec.alloc(sizeof(int32_t) * R));
   CU(fbflag.alloc(R));
   v.tok_fallback_flag = fbflag.as<uint8_t>();
+  CU(tok_cmax.alloc(sizeof(float) * (size_t)R * ((L + 31) / 32)));
+  v.tok_cmax_ws = tok_cmax.as<float>();
   const bool row_is_dot = sb::tokenize_tensor_path(v, P);
   // SOAR: the projection term is pruned with a second tensor-core GEMM (rhat x centres) when the centre operand
   // exists; small trees (SIMT tokenization) prune by distance only

@@ -98,7 +98,7 @@ struct scann_b200_index {
   std::mutex mu;
   std::vector<uint32_t> h_leaf_size;
   // persistent device arrays
-  DevBuf i8_inv, i8_norm;
+  DevBuf i8_inv, i8_norm, tok_cmax;
   DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
       codes, slot_dp, slot_tie, dataset, dp_row, tok_b;
   // workspace
@@ -423,6 +423,8 @@ int ensure_workspace(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_
   CU(ix->q.ensure(sizeof(float) * (size_t)nq * v.d));
   CU(ix->dist.ensure(sizeof(float) * (size_t)nq * v.L));
   CU(ix->tok_a.ensure(sb::tokenize_operand_bytes(nq, v.d)));
+  CU(ix->tok_cmax.ensure(sizeof(float) * (size_t)nq * ((v.L + 31) / 32)));
+  ix->dev.tok_cmax_ws = ix->tok_cmax.as<float>();
   CU(ix->leaves.ensure(sizeof(int32_t) * (size_t)nq * p.P));
   CU(ix->bias.ensure(sizeof(float) * (size_t)nq * p.P));
   CU(ix->lut.ensure((size_t)nq * v.W * 128));

@@ -45,6 +45,8 @@ struct DevIndex {
   // optional [nq] bytes: set to 1 for rows whose tensor-core pre-filter fell back to exact distances (the row of
   // the distance matrix then holds exact distances instead of dot products); only the index-build stage reads it
   uint8_t* tok_fallback_flag;
+  // optional workspace [nq][ceil(L / 32)] floats: enables the chunk pre-selection of the tokenizer (prep.cu)
+  float* tok_cmax_ws;
 };
 
 struct ScanWork {
@@ -127,8 +129,11 @@ cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, 
                        cudaStream_t s);
 // out[a_row * ld + b_row] = sum_k A[a_row][k] * B[b_row][k]; bf16 operands with row pitch kpitch (multiple of 64),
 // a_rows_pad a multiple of 128 (padding rows readable), fp32 accumulate on tcgen05.
+// cmax (optional): cmax[a_row * ld_c + b_row / 32] = max over that row's 32-column chunk of out (cbias == NULL) or of
+// 2 * out - cbias[b_row] (squared L2: minus the smallest "||c||^2 - 2 <q, c>" of the chunk).
 cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows_pad, const void* b_operand,
-                         uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s);
+                         uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s,
+                         float* cmax = nullptr, uint32_t ld_c = 0, const float* cbias = nullptr);
 // ---- debug ----
 void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s);
 

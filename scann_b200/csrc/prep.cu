@@ -813,11 +813,132 @@ topp_stream_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   }
 }
 
+// Chunk pre-selection for long rows (P <= 128, L / 32 >= 2 P): the GEMM's store epilogue also writes the maximum of
+// every 32-centre chunk of the row (of 2 S - ||c||^2 for squared L2), so the refinement reads L / 32 values instead of L.  The P-th smallest
+// chunk minimum U (= -chunk maximum; exact, by the warp radix select) is an upper bound of the P-th smallest
+// approximate distance -- P different chunks each hold an element <= U -- and only chunks whose minimum is <= U + 2 eps
+// can hold a candidate.  Those chunks (about P of them) are read back, 128 bytes each, their elements <= U + 2 eps get
+// the exact chain and the sort by (distance, leaf): the same superset argument and the same result as the radix
+// refinement, with 5 KB + ~P * 128 B read per query instead of 160 KB at L = 40k, one warp per query and no row image.
+constexpr int kChunkMaxChunks = 2048;  // L <= 65536
+__global__ void __launch_bounds__(256)
+topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ S, const float* __restrict__ cmax_ws,
+                  int nq, int P, int Ppow2, float eps_rel, int32_t* __restrict__ leaves, float* __restrict__ bias,
+                  uint32_t* fallbacks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x * 8 + warp;
+  if (qi >= nq) return;
+  const int L = (int)ix.L, D = (int)ix.d, Dp = (D + 3) & ~3, Lc = (L + 31) >> 5, Lcp = (Lc + 3) & ~3;
+  unsigned char* base = smem_raw + (size_t)warp * ((size_t)kStreamCand * 8 + 1024 + (size_t)Dp * 4 + (size_t)Lcp * 4);
+  uint64_t* skeys = reinterpret_cast<uint64_t*>(base);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(base + (size_t)kStreamCand * 8);
+  float* sq = reinterpret_cast<float*>(base + (size_t)kStreamCand * 8 + 1024);
+  float* cm = sq + Dp;  // [Lc] chunk minima of the approximate distance
+  float* row = S + (size_t)qi * L;
+  const uint32_t lt = (1u << lane) - 1u;
+
+  const bool sql2 = ix.distance == 1;
+  float ssq = 0.f;
+  for (int k = lane; k < Dp; k += 32) {
+    const float v = k < D ? q[(size_t)qi * D + k] : 0.f;
+    sq[k] = v;
+    ssq = fmaf(v, v, ssq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, o);
+  __syncwarp();
+  float qn = 0.f;
+  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
+    double acc = 0.0;
+    if (lane == 0) for (int k = 0; k < D; ++k) acc += (double)sq[k] * (double)sq[k];
+    qn = (float)__shfl_sync(0xFFFFFFFFu, acc, 0);
+  }
+  // chunk minima of the approximate distance: -max(S) (dot product), -max(2 S - ||c||^2) + ||q||^2 (squared L2)
+  const float* cmr = cmax_ws + (size_t)qi * Lc;
+  for (int j = lane; j < Lc; j += 32) cm[j] = sql2 ? __fadd_rn(-cmr[j], qn) : -cmr[j];
+  __syncwarp();
+  const float qnorm = sqrtf(ssq) * 1.001f, cmaxn = ix.center_max_norm;
+  float eps = eps_rel * qnorm * cmaxn;
+  // squared L2: as the radix refinement, plus the few ulps by which "(b - 2S) + |q|^2" of the chunk statistic and
+  // "(b + |q|^2) - 2S" of the element test may differ
+  if (sql2) eps = 2.f * eps + (float)(D + 16) * 1.1920929e-7f * (qn + cmaxn * cmaxn + 2.f * qnorm * cmaxn);
+  auto approx = [&](int i) -> float {
+    const float sdot = row[i];
+    return sql2 ? __fsub_rn(__fadd_rn(__ldg(ix.center_sqnorm + i), qn), __fmul_rn(2.f, sdot)) : -sdot;
+  };
+  uint32_t need = 0;
+  const uint32_t prefix = warp_radix_select([&](int j) { return f2ord(cm[j]); }, Lc, (uint32_t)P, hist, lane, need);
+  const float U = ord2f(prefix);
+  const float thr = __fadd_ru(U, __fmul_ru(2.f, eps));
+  uint32_t count = 0;
+  for (int j0 = 0; j0 < Lc; j0 += 32) {
+    const int j = j0 + lane;
+    uint32_t hits = __ballot_sync(0xFFFFFFFFu, j < Lc && !(cm[j] > thr));
+    while (hits) {
+      const int jj = j0 + __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int i = jj * 32 + lane;
+      const bool c = i < L && !(approx(i) > thr);
+      const uint32_t mk = __ballot_sync(0xFFFFFFFFu, c);
+      if (c) {
+        const uint32_t pos = count + __popc(mk & lt);
+        if (pos < (uint32_t)kStreamCand) skeys[pos] = (uint64_t)(uint32_t)i;
+      }
+      count += __popc(mk);
+    }
+  }
+  __syncwarp();
+  auto exact = [&](int idx) -> float {  // the reference's sequential fnmadd chain (tokenize_kernel)
+    const float* c = ix.centers + (size_t)idx * D;
+    float acc = sql2 ? __fadd_rn(ix.center_sqnorm[idx], qn) : 0.f;
+    const float scale2 = sql2 ? 2.0f : 1.0f;
+    if ((D & 3) == 0) {
+      for (int k = 0; k < D; k += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(c + k));
+        acc = __fmaf_rn(-sq[k], __fmul_rn(v.x, scale2), acc);
+        acc = __fmaf_rn(-sq[k + 1], __fmul_rn(v.y, scale2), acc);
+        acc = __fmaf_rn(-sq[k + 2], __fmul_rn(v.z, scale2), acc);
+        acc = __fmaf_rn(-sq[k + 3], __fmul_rn(v.w, scale2), acc);
+      }
+    } else {
+#pragma unroll 4
+      for (int k = 0; k < D; ++k) acc = __fmaf_rn(-sq[k], __fmul_rn(__ldg(c + k), scale2), acc);
+    }
+    return acc;
+  };
+  int32_t* lout = leaves + (size_t)qi * P;
+  float* bout = bias + (size_t)qi * P;
+  if (count <= (uint32_t)kStreamCand) {
+    int ns = 2;
+    while ((uint32_t)ns < count) ns <<= 1;
+    for (int j = lane; j < ns; j += 32) {
+      const bool live = (uint32_t)j < count;
+      const uint32_t idx = live ? (uint32_t)skeys[j] : 0u;
+      const float e = live ? exact((int)idx) : 0.f;
+      skeys[j] = live ? (((uint64_t)f2ord(e) << 32) | idx) : kKeyMax;
+    }
+    __syncwarp();
+    warp_bitonic_sort(skeys, ns, lane);
+    for (int i = lane; i < P; i += 32) {
+      const uint64_t k = i < ns ? skeys[i] : kKeyMax;
+      lout[i] = (k == kKeyMax) ? -1 : (int32_t)(uint32_t)k;
+      bout[i] = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
+    }
+  } else {
+    if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1u);
+    if (lane == 0 && ix.tok_fallback_flag) ix.tok_fallback_flag[qi] = 1;
+    for (int i = lane; i < L; i += 32) row[i] = exact(i);
+    __syncwarp();
+    warp_topp_exact(row, L, P, Ppow2, hist, skeys, lane, lout, bout);
+  }
+}
+
 bool tokenize_tensor_path(const DevIndex& ix, uint32_t P) {
   if (!ix.tok_b || P + 32 > (uint32_t)kRefineMaxCand || ix.d > 2048) return false;
   const char* e = getenv("SCANN_B200_TOKENIZE");
   if (e && !strcmp(e, "simt")) return false;
-  if (e && (!strcmp(e, "tcgen05") || !strcmp(e, "stream"))) return true;
+  if (e && (!strcmp(e, "tcgen05") || !strcmp(e, "stream") || !strcmp(e, "chunk"))) return true;
   return ix.L >= 256;  // below that the SIMT GEMM is already negligible
 }
 
@@ -831,8 +952,31 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   }
   cudaError_t e = build_tokenize_operand(q, nq, ix.d, 1, a_ws, s);
   if (e != cudaSuccess) return e;
-  e = gemm_bf16_nt(a_ws, nq, (nq + 127) / 128 * 128, ix.tok_b, ix.L, ix.tok_kp, dist, ix.L, s);
+  // chunk pre-selection: P <= 128, at least 2 P chunks; default from 4096 centres
+  // (SCANN_B200_TOKENIZE=chunk forces it where it applies, =tcgen05 the radix refinement)
+  const uint32_t n_chunks = (ix.L + 31) / 32;
+  bool chunked = ix.tok_cmax_ws && P <= 128 && n_chunks >= 2 * P && n_chunks <= (uint32_t)kChunkMaxChunks;
+  {
+    const char* env = getenv("SCANN_B200_TOKENIZE");
+    if (env && (!strcmp(env, "tcgen05") || !strcmp(env, "stream"))) chunked = false;
+    else if (!(env && !strcmp(env, "chunk")) && ix.L < 4096) chunked = false;
+  }
+  e = gemm_bf16_nt(a_ws, nq, (nq + 127) / 128 * 128, ix.tok_b, ix.L, ix.tok_kp, dist, ix.L, s,
+                   chunked ? ix.tok_cmax_ws : nullptr, n_chunks, ix.distance == 1 ? ix.center_sqnorm : nullptr);
   if (e != cudaSuccess) return e;
+  if (chunked) {
+    int sp = 2;
+    while (sp < (int)P) sp <<= 1;
+    const float er = (float)ix.tok_kp * 4.76837158e-7f + 3.05175781e-5f;  // K * 2^-21 + 2^-15
+    const size_t per_warp = (size_t)kStreamCand * 8 + 1024 + (size_t)((ix.d + 3) & ~3u) * 4 + (size_t)((n_chunks + 3) & ~3u) * 4;
+    const size_t bytes = per_warp * 8;
+    e = cudaFuncSetAttribute(topp_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    topp_chunk_kernel<<<(nq + 7) / 8, 256, bytes, s>>>(ix, q, dist, ix.tok_cmax_ws, (int)nq, (int)P, sp, er, leaves, bias,
+                                                       fallbacks);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+  }
   int pp = 2, cp = 64;
   while (pp < (int)P) pp <<= 1;
   while (cp < (int)P + 32) cp <<= 1;

@@ -123,6 +123,24 @@ def test_encode_with_streaming_tokenizer_and_fallback_rows(mode, monkeypatch):
   np.testing.assert_array_equal(soar_codes, o_soar)
 
 
+@pytest.mark.parametrize("soar", [None, 1.5])
+def test_encode_with_chunk_preselection(soar, monkeypatch):
+  """The tokenizer's chunk pre-selection under squared L2 (default from 4,096 leaves; forced here on 1,024)."""
+  import oracle
+  from scann_b200 import _lib
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", "chunk")
+  x, centers = _mixture(5000, 40, 1024, 23, 0.7, False)
+  centers[300:330] = centers[299]              # equal centres inside and across chunks
+  x[:20] = 0.0
+  cb, bd = _codebook(x[100:], centers, 2, 4)
+  tokens, codes, soar_codes, st = _lib.encode_database(x, centers, cb, bd, soar_lambda=soar, noise_shaping_threshold=0.2)
+  o_tokens, o_codes, o_soar, _ = oracle.encode_database(x, centers, cb, bd, soar_lambda=soar, threshold=0.2, threads=8)
+  np.testing.assert_array_equal(tokens, o_tokens)
+  np.testing.assert_array_equal(codes, o_codes)
+  if soar is not None:
+    np.testing.assert_array_equal(soar_codes, o_soar)
+
+
 def test_encode_rejects_bad_arguments():
   from scann_b200 import _lib
   x, centers = _mixture(100, 16, 8, 1, 1.0, False)
@@ -150,3 +168,27 @@ def test_built_index_searches_like_the_oracle():
   o_idx, o_dist = oi.search_batched(q, impl=1, threads=8)
   np.testing.assert_array_equal(idx, o_idx)
   np.testing.assert_array_equal(dist.view(np.uint32), o_dist.view(np.uint32))
+
+
+def _build_golden_names():
+  import glob
+  import os
+  d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "build")
+  return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(d, "*.npz")))
+
+
+@pytest.mark.parametrize("name", _build_golden_names())
+def test_encode_database_matches_committed_golden(name):
+  """No oracle in the loop: the GPU encoder against the committed fixtures (oracle/gen_golden_build.py)."""
+  import os
+  from scann_b200 import _lib
+  z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "build", name + ".npz"))
+  soar = None if np.isnan(z["soar_lambda"]) else float(z["soar_lambda"])
+  tokens, codes, soar_codes, st = _lib.encode_database(z["x"], z["centers"], z["codebook"], z["block_dims"],
+                                                       residual=bool(z["residual"]), soar_lambda=soar,
+                                                       noise_shaping_threshold=float(z["threshold"]))
+  np.testing.assert_array_equal(tokens, z["exp_tokens"])
+  np.testing.assert_array_equal(codes, z["exp_codes"])
+  if soar is not None:
+    np.testing.assert_array_equal(soar_codes, z["exp_soar_codes"])
+  assert st["norm_ties"] == int(z["exp_ties"])

@@ -125,10 +125,13 @@ TOK_CASES = [
     dict(distance="squared_l2", d=30, dpb=4, leaves=300, n=6000, probe=64, pre=64),
     dict(dpb=3, d=100, leaves=700, n=15000, probe=37),     # D % 4 == 0 but 3D not a multiple of 64; odd P
     dict(dpb=3, d=99, leaves=300, n=8000, probe=33),       # D % 4 != 0: scalar centre loads
+    dict(n=12000, leaves=3000, probe=24, pre=60, d=32),    # 94 chunks of 32 centres >= 2 P: the chunk pre-selection applies
+    dict(n=9000, leaves=2500, probe=7, pre=40, d=50, dpb=2),  # ... with L % 32 != 0 and D % 4 != 0
+    dict(distance="squared_l2", n=9000, leaves=2100, probe=9, pre=40, d=32),  # ... squared L2: chunk minima of ||c||^2 - 2 <q, c>
 ]
 
 
-@pytest.mark.parametrize("mode", ["tcgen05", "simt", "stream"])
+@pytest.mark.parametrize("mode", ["tcgen05", "simt", "stream", "chunk"])
 @pytest.mark.parametrize("kw", TOK_CASES, ids=[str(i) for i in range(len(TOK_CASES))])
 def test_tokenize_modes_bit_exact(kw, mode, monkeypatch):
   monkeypatch.setenv("SCANN_B200_TOKENIZE", mode)
@@ -145,7 +148,7 @@ def test_tokenize_modes_bit_exact(kw, mode, monkeypatch):
 
 @pytest.mark.parametrize("kw", [dict(n=6000, leaves=300, probe=40, pre=50, d=32),
                                 dict(distance="squared_l2", d=64, leaves=50, n=10000)], ids=["dot", "l2"])
-@pytest.mark.parametrize("mode", ["tcgen05", "stream"])
+@pytest.mark.parametrize("mode", ["tcgen05", "stream", "chunk"])
 def test_tokenize_degenerate_queries_fall_back_to_exact(kw, mode, monkeypatch):
   """Zero / tiny / huge / duplicated queries: the candidate window of the pre-filter degenerates (every centre ties),
   the kernel must fall back to exact distances and still match the oracle bit for bit."""

@@ -256,3 +256,30 @@ def test_encode_database_layout_with_soar():
   assert (soar_codes[~spilled] == 0).all()
   c_lo, _ = oracle.encode(x, cb, bd, centers=centers, token=lo, threshold=0.2)
   np.testing.assert_array_equal(codes, c_lo)
+
+
+# ---- committed fixtures (tests/golden/build/, generator oracle/gen_golden_build.py) ----
+def build_golden_names():
+  import glob
+  import os
+  d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "build")
+  return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(d, "*.npz")))
+
+
+def load_build_golden(name):
+  import os
+  return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "build", name + ".npz"))
+
+
+@pytest.mark.parametrize("name", build_golden_names())
+def test_oracle_reproduces_build_golden(name):
+  z = load_build_golden(name)
+  soar = None if np.isnan(z["soar_lambda"]) else float(z["soar_lambda"])
+  tokens, codes, soar_codes, ties = oracle.encode_database(z["x"], z["centers"], z["codebook"], z["block_dims"],
+                                                          residual=bool(z["residual"]), soar_lambda=soar,
+                                                          threshold=float(z["threshold"]), threads=2)
+  np.testing.assert_array_equal(tokens, z["exp_tokens"])
+  np.testing.assert_array_equal(codes, z["exp_codes"])
+  if soar is not None:
+    np.testing.assert_array_equal(soar_codes, z["exp_soar_codes"])
+  assert ties == int(z["exp_ties"])
