@@ -180,32 +180,45 @@ soar_kernel(SoarArgs a) {
   const float* row2 = a.row2 ? a.row2 + (size_t)i * a.L : nullptr;
   const bool is_dot = a.row_is_dot && !(a.row_exact && a.row_exact[i]);
   uint32_t ncand = 0;
-  for (uint32_t base = 0; base < a.L; base += 32) {
-    const uint32_t l = base + lane;
-    bool pass = false;
-    if (l < a.L) {
-      const float v = row[l];
-      const float ap = is_dot ? __fsub_rn(__fadd_rn(__ldg(a.cnorm + l), qn), __fmul_rn(2.f, v)) : v;
-      float lb = __fmul_rd(__fsub_rd(ap, E1), shrink);
-      if (row2) {
-        const float p = fmaxf(__fsub_rd(fabsf(__fsub_rn(xr, row2[l])), E2), 0.f);
-        lb = __fmul_rd(__fadd_rd(lb, __fmul_rd(__fmul_rd(p, p), lam_lo)), 1.f - 1.1920929e-7f);
-      }
-      pass = !(lb > m);  // NaN passes
+  // four 32-centre groups per iteration: the loads of all of them are in flight before the first test (the scan is a
+  // serial chain of round trips per warp otherwise: issue 48 %, DRAM 17 % in the first capture)
+  for (uint32_t base = 0; base < a.L; base += 128) {
+    float v[4], w[4], cn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t l = base + 32 * u + lane;
+      const bool in = l < a.L;
+      v[u] = in ? row[l] : 0.f;
+      w[u] = (in && row2) ? row2[l] : 0.f;
+      cn[u] = (in && is_dot) ? __ldg(a.cnorm + l) : 0.f;
     }
-    const uint32_t mask = __ballot_sync(kFull, pass);
-    if (mask) {
-      if (pass) cand[ncand + __popc(mask & ((1u << lane) - 1u))] = (int32_t)l;
-      ncand += __popc(mask);
-      __syncwarp();
-      if (ncand >= 32) {
-        evaluate(cand[lane]);
-        evals += 32;
-        const int32_t carry = (uint32_t)lane + 32 < ncand ? cand[lane + 32] : -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t l = base + 32 * u + lane;
+      bool pass = false;
+      if (l < a.L) {
+        const float ap = is_dot ? __fsub_rn(__fadd_rn(cn[u], qn), __fmul_rn(2.f, v[u])) : v[u];
+        float lb = __fmul_rd(__fsub_rd(ap, E1), shrink);
+        if (row2) {
+          const float p = fmaxf(__fsub_rd(fabsf(__fsub_rn(xr, w[u])), E2), 0.f);
+          lb = __fmul_rd(__fadd_rd(lb, __fmul_rd(__fmul_rd(p, p), lam_lo)), 1.f - 1.1920929e-7f);
+        }
+        pass = !(lb > m);  // NaN passes
+      }
+      const uint32_t mask = __ballot_sync(kFull, pass);
+      if (mask) {
+        if (pass) cand[ncand + __popc(mask & ((1u << lane) - 1u))] = (int32_t)l;
+        ncand += __popc(mask);
         __syncwarp();
-        ncand -= 32;
-        if ((uint32_t)lane < ncand) cand[lane] = carry;
-        __syncwarp();
+        if (ncand >= 32) {
+          evaluate(cand[lane]);
+          evals += 32;
+          const int32_t carry = (uint32_t)lane + 32 < ncand ? cand[lane + 32] : -1;
+          __syncwarp();
+          ncand -= 32;
+          if ((uint32_t)lane < ncand) cand[lane] = carry;
+          __syncwarp();
+        }
       }
     }
   }
@@ -266,7 +279,8 @@ struct EncodeArgs {
 __host__ __device__ __forceinline__ size_t encode_team_bytes(uint32_t D, uint32_t B, bool shaped) {
   const size_t Dp = (D + 3) & ~3u;
   size_t b = 2 * Dp * sizeof(float);                        // res, orig
-  if (shaped) b += (size_t)B * sizeof(double);              // initial norms
+  if (shaped) b += (size_t)B * sizeof(double)               // initial norms
+                   + 2 * Dp * sizeof(double);               // res, orig widened once (the descent re-reads them)
   b += ((size_t)B * 3 + 15) & ~(size_t)15;                  // code u8, order u16
   return (b + 15) & ~(size_t)15;
 }
@@ -304,7 +318,9 @@ encode_kernel(EncodeArgs a) {
   float* res = reinterpret_cast<float*>(base);
   float* orig = res + Dp;
   double* n0 = reinterpret_cast<double*>(orig + Dp);
-  uint8_t* code = reinterpret_cast<uint8_t*>(n0 + (kShaped ? a.B : 0));
+  double* dres = n0 + (kShaped ? a.B : 0);
+  double* dorig = dres + (kShaped ? Dp : 0);
+  uint8_t* code = reinterpret_cast<uint8_t*>(dorig + (kShaped ? Dp : 0));
   uint16_t* order = reinterpret_cast<uint16_t*>(code + ((a.B + 1) & ~1u));
   const uint64_t pair = (uint64_t)blockIdx.x * (kEncodeThreads / kTeam) + team;
   const bool active = pair < (uint64_t)a.n * a.npd;
@@ -322,7 +338,9 @@ encode_kernel(EncodeArgs a) {
   for (uint32_t k = c; k < a.D; k += kTeam) {
     const float v = x[k];
     orig[k] = v;
-    res[k] = cen ? __fsub_rn(v, __ldg(cen + k)) : v;   // ComputeResiduals: float subtraction
+    const float r = cen ? __fsub_rn(v, __ldg(cen + k)) : v;   // ComputeResiduals: float subtraction
+    res[k] = r;
+    if constexpr (kShaped) { dres[k] = (double)r; dorig[k] = (double)v; }
   }
   __syncwarp();
 
@@ -385,9 +403,9 @@ encode_kernel(EncodeArgs a) {
       const float* cx = a.codebook + ((size_t)b * 16 + c) * a.S;
       double rn = 0.0, par = 0.0;
       for (uint32_t k = 0; k < nd; ++k) {
-        const double rc = __dsub_rn((double)res[off + k], (double)__ldg(cx + k));
+        const double rc = __dsub_rn(dres[off + k], (double)__ldg(cx + k));
         rn = __dadd_rn(rn, __dmul_rn(rc, rc));
-        par = __dadd_rn(par, __dmul_rn(__dmul_rn(rc, (double)orig[off + k]), inv_norm));
+        par = __dadd_rn(par, __dmul_rn(__dmul_rn(rc, dorig[off + k]), inv_norm));
       }
       *rn_out = rn;
       *par_out = par;
