@@ -192,3 +192,40 @@ def test_encode_database_matches_committed_golden(name):
   if soar is not None:
     np.testing.assert_array_equal(soar_codes, z["exp_soar_codes"])
   assert st["norm_ties"] == int(z["exp_ties"])
+
+
+@pytest.mark.parametrize("n,d,L,dpb,soar,thr", [
+    (1, 8, 5, 2, 1.5, 0.2),          # a single datapoint
+    (33, 2, 3, 2, 1.5, float("nan")),  # one AH block
+    (40, 6, 1, 2, 1.5, 0.2),         # one leaf: the secondary can only be the primary, nothing is spilled
+    (257, 5, 9, 1, None, 0.5),       # dims_per_block 1, odd D
+    (64, 16, 300, 4, 2.5, 0.2),      # more leaves than datapoints (tensor-core tokenization with empty leaves)
+])
+def test_encode_edge_shapes(n, d, L, dpb, soar, thr):
+  import oracle
+  from scann_b200 import _lib
+  rng = np.random.default_rng(n * 7 + d)
+  x = rng.standard_normal((n, d)).astype(np.float32)
+  centers = rng.standard_normal((L, d)).astype(np.float32)
+  full, part = divmod(d, dpb)
+  bd = np.asarray([dpb] * full + ([part] if part else []), np.int32)
+  cb = (0.5 * rng.standard_normal((len(bd), 16, dpb))).astype(np.float32)
+  for b in range(len(bd)):
+    cb[b, :, bd[b]:] = 0
+  tokens, codes, soar_codes, st = _lib.encode_database(x, centers, cb, bd, soar_lambda=soar, noise_shaping_threshold=thr)
+  o_tokens, o_codes, o_soar, _ = oracle.encode_database(x, centers, cb, bd, soar_lambda=soar, threshold=thr, threads=2)
+  np.testing.assert_array_equal(tokens, o_tokens)
+  np.testing.assert_array_equal(codes, o_codes)
+  if soar is not None:
+    np.testing.assert_array_equal(soar_codes, o_soar)
+    if L == 1:
+      assert (tokens[1::2] == -1).all() and st["spilled"] == 0
+
+
+def test_encode_empty_database():
+  from scann_b200 import _lib
+  x = np.zeros((0, 8), np.float32)
+  centers = np.ones((4, 8), np.float32)
+  cb = np.zeros((4, 16, 2), np.float32)
+  tokens, codes, soar_codes, st = _lib.encode_database(x, centers, cb)
+  assert tokens.shape == (0,) and codes.shape == (0, 4) and soar_codes is None
