@@ -473,6 +473,15 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   // per (query, item); small leaves (C2: ~1.4) append directly
   w.stage = ix->avg_leaf_slots >= 2048 ? 1u : 0u;
   if (const char* e = getenv("SCANN_B200_SCAN_STAGE")) w.stage = e[0] == '1' ? 1u : 0u;
+  // pilot sample: 4 N' slots; whole leaves for large leaves (a looser tau costs pushes there), for small leaves the
+  // pilot stops inside the leaf once the target is reached (SCANN_B200_PILOT="<factor>[p]" overrides, tests / tuning)
+  w.pilot_target = 4 * p.nover;
+  w.pilot_partial = 0;
+  if (const char* e = getenv("SCANN_B200_PILOT")) {
+    const int f = atoi(e);
+    if (f > 0) w.pilot_target = (uint32_t)f * p.nover;
+    w.pilot_partial = strchr(e, 'p') ? 1u : 0u;
+  }
   int launches = 0;
   uint32_t scan_launches = 0, retries = 0;
 

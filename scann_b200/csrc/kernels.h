@@ -73,6 +73,8 @@ struct ScanWork {
   uint32_t rank_lo, rank_hi;  // ranks [rank_lo, rank_hi) of every query's leaf list go into the next work list
   uint32_t one;               // always 1; a runtime value so the scan's IMAD accumulates stay IMADs
   uint32_t stage;             // 1: the main scan stages candidates per item in shared memory (large leaves)
+  uint32_t pilot_target;      // slots the pilot samples per query before it fixes tau (4 N')
+  uint32_t pilot_partial;     // 1: the pilot may stop inside a leaf once the target is reached (small leaves)
 };
 
 // ---- query preparation ----

@@ -95,6 +95,25 @@ __device__ __forceinline__ void score_quad(const uint32_t (&w)[W], const unsigne
   a23 = __byte_perm(ae, ao, 0x7632);
 }
 
+// Pilot scoring: ONE query, its u8 LUT as it is ([8W][16] bytes).  One LDS.U8 and one add per lookup (the 16 bytes of a
+// block row lie in four adjacent banks: no conflicts) instead of the quad table's load + mask + permute + two adds.
+template <int W, int NL = 0>
+__device__ __forceinline__ int score_one(const uint32_t (&w)[W], const unsigned char* tbl, int nlast) {
+  uint32_t s0 = 0, s1 = 0;
+  const int nl = NL ? NL : nlast;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (j == W - 1 && k >= nl) continue;
+      const uint32_t nib = (w[j] >> (4 * k)) & 0xFu;
+      const uint32_t v = tbl[(8 * j + k) * 16 + nib];
+      if (k & 1) s1 += v; else s0 += v;
+    }
+  }
+  return (int)(s0 + s1);
+}
+
 // Main-scan scoring.  An OCT of eight queries shares one table of 64-bit entries
 //   T[b][c] = { lut0 | lut1 << 8 | lut2 << 16 | lut3 << 24,  lut4 | lut5 << 8 | lut6 << 16 | lut7 << 24 },
 // so one LDS.64 (the LSU issues about one warp-wide shared load per two cycles whatever its width)
@@ -381,7 +400,10 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   const int off128 = 128 * (int)ix.B;
   const uint32_t nover = w.nover;
   uint64_t* grow = w.buf + (size_t)q * w.cap;  // this query's (still empty) buffer row is the compaction scratch
-  build_quad_table(tbl, w.lut + (size_t)q * W * 128, nullptr, nullptr, nullptr, W * 128, tid, kScanThreads);
+  {  // the query's own u8 LUT, [8W][16] bytes
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(w.lut + (size_t)q * W * 128);
+    for (int t = tid; t < W * 32; t += kScanThreads) tbl[t] = src[t];
+  }
   if (tid == 0) { s_tau = kKeyMax; s_cnt = 0; }
   const float mult = w.mult[q], inv = w.inv_mult[q];
   // Sample whole leaves, nearest first, until at least 4 N slots have been scored: the N-th best of
@@ -398,13 +420,12 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
     if (tid == 0) s_thr = acc_threshold(s_tau, mult, inv, bias) + off128;
     __syncthreads();
     for (uint32_t g0 = 0; g0 < ng; g0 += kScanWarps) {
+      if (w.pilot_partial && seen + g0 * 32 >= w.pilot_target) break;  // enough slots sampled (slot order = id order)
       const uint32_t g = g0 + warp;
       if (g < ng) {
         uint32_t cw[W];
         load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
-        uint32_t a01, a23;
-        score_quad<W>(cw, reinterpret_cast<const unsigned char*>(tbl), nlast, a01, a23);
-        const int s0 = (int)(a01 & 0xFFFFu);
+        const int s0 = score_one<W>(cw, reinterpret_cast<const unsigned char*>(tbl), nlast);
         bool p = (g * 32 + lane < n) && s0 <= s_thr;
         uint64_t key = 0;
         if (p) {
@@ -446,7 +467,7 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
       }
     }
     seen += n;
-    if (seen >= 4 * nover) break;
+    if (seen >= w.pilot_target) break;
   }
   __syncthreads();
   // tau: an upper bound of the N-th smallest sampled key, plus one so that the bounding element itself
