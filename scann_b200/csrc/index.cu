@@ -98,7 +98,7 @@ struct scann_b200_index {
   std::mutex mu;
   std::vector<uint32_t> h_leaf_size;
   // persistent device arrays
-  DevBuf i8_inv, i8_norm, tok_cmax;
+  DevBuf i8_inv, i8_norm, tok_cmax, pair_pos;
   DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
       codes, slot_dp, slot_tie, dataset, dp_row, tok_b;
   // workspace
@@ -440,6 +440,7 @@ int ensure_workspace(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_
   CU(ix->leaf_cur.ensure(sizeof(uint32_t) * (v.L + 1)));
   CU(ix->item_off.ensure(sizeof(uint32_t) * (v.L + 1)));
   CU(ix->entry_q.ensure(sizeof(uint32_t) * (size_t)nq * p.P));
+  CU(ix->pair_pos.ensure(sizeof(uint32_t) * (size_t)nq * p.P));
   CU(ix->entry_bias.ensure(sizeof(float) * (size_t)nq * p.P));
   CU(ix->counters.ensure(sizeof(uint32_t) * 8));
   CU(ix->stats.ensure(sizeof(unsigned long long) * 4));
@@ -466,7 +467,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   w.buf = ix->buf.as<uint64_t>(); w.cnt = ix->cnt.as<uint32_t>(); w.tau = ix->tau.as<uint64_t>();
   w.ovf = ix->ovf.as<uint32_t>(); w.leaf_cnt = ix->leaf_cnt.as<uint32_t>(); w.leaf_eoff = ix->leaf_eoff.as<uint32_t>();
   w.leaf_cur = ix->leaf_cur.as<uint32_t>(); w.item_off = ix->item_off.as<uint32_t>();
-  w.entry_q = ix->entry_q.as<uint32_t>(); w.entry_bias = ix->entry_bias.as<float>();
+  w.entry_q = ix->entry_q.as<uint32_t>(); w.entry_bias = ix->entry_bias.as<float>(); w.pair_pos = ix->pair_pos.as<uint32_t>();
   w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
   w.nq = nq; w.P = p.P; w.cap = cap; w.nover = p.nover; w.quads_per_item = 2; w.one = 1;  // 2 octs = 16 queries per work item
   // large leaves (C5 shape: ~20 candidates per (query, item)): stage candidates in shared memory, one global atomic

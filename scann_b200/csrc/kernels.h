@@ -65,6 +65,7 @@ struct ScanWork {
   uint32_t* leaf_eoff;        // [L+1]
   uint32_t* leaf_cur;         // [L]
   uint32_t* item_off;         // [L+1]
+  uint32_t* pair_pos;         // [nq*P] position of the (query, rank) pair inside its leaf's entry list (set when counted)
   uint32_t* entry_q;          // [nq*P]
   float* entry_bias;          // [nq*P]
   uint32_t* counters;         // [8]: 0 item counter, 1 n_items, 2 n_ovf, 3 n_entries

@@ -494,7 +494,8 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
     if (leaf >= 0) {
       bytes += (unsigned long long)(ix.leaf_goff[leaf + 1] - ix.leaf_goff[leaf]) * 16ull * ix.B;
       pairs += 1;
-      if (rr >= w.rank_lo && rr < w.rank_hi) atomicAdd(&w.leaf_cnt[leaf], 1u);
+      // the count IS the pair's position in its leaf's entry list: the scatter pass needs no second atomic
+      if (rr >= w.rank_lo && rr < w.rank_hi) w.pair_pos[(size_t)q * w.P + rr] = atomicAdd(&w.leaf_cnt[leaf], 1u);
     }
   }
 #pragma unroll
@@ -525,7 +526,7 @@ __global__ void worklist_count_kernel(DevIndex ix, ScanWork w, int only_ovf, int
         bytes = (unsigned long long)ng * 16ull * ix.B;
         pairs = 1;
       }
-      if (r >= w.rank_lo && r < w.rank_hi && (!only_ovf || w.ovf[q])) atomicAdd(&w.leaf_cnt[leaf], 1u);
+      if (r >= w.rank_lo && r < w.rank_hi && (!only_ovf || w.ovf[q])) w.pair_pos[i] = atomicAdd(&w.leaf_cnt[leaf], 1u);
     }
   }
   if (count_stats) {
@@ -597,7 +598,7 @@ __global__ void worklist_scatter_kernel(DevIndex ix, ScanWork w, int only_ovf) {
   const int leaf = w.leaves[i];
   if (leaf < 0) return;
   if (r < w.rank_lo || r >= w.rank_hi || (only_ovf && !w.ovf[q])) return;
-  const uint32_t pos = w.leaf_eoff[leaf] + atomicAdd(&w.leaf_cur[leaf], 1u);
+  const uint32_t pos = w.leaf_eoff[leaf] + w.pair_pos[i];
   w.entry_q[pos] = q;
   w.entry_bias[pos] = w.bias[i];
 }
