@@ -492,9 +492,16 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(sb::launch_tokenize_topp(v, d_q, nq, p.P, ix->dist.as<float>(), ix->tok_a.p, ix->leaves.as<int32_t>(),
                               ix->bias.as<float>(), w.counters + 5, s, &launches));
   CU(cudaEventRecord(ix->ev[EV_TOK], s));
-  sb::launch_lut(v, d_q, nq, ix->lut.as<uint8_t>(), ix->mult.as<float>(), ix->inv.as<float>(), s);
-  launches += 1;
-  CU(cudaGetLastError());
+  // LUT build: fused into the pilot kernel when the raw table fits its candidate buffer (every BASELINE.json
+  // configuration; SCANN_B200_FUSE_LUT=0 keeps the separate lut_kernel)
+  bool fuse_lut = sb::pilot_can_build_lut(v, p.nover);
+  if (const char* e = getenv("SCANN_B200_FUSE_LUT")) fuse_lut = fuse_lut && e[0] != '0';
+  w.q_for_lut = fuse_lut ? d_q : nullptr;
+  if (!fuse_lut) {
+    sb::launch_lut(v, d_q, nq, ix->lut.as<uint8_t>(), ix->mult.as<float>(), ix->inv.as<float>(), s);
+    launches += 1;
+    CU(cudaGetLastError());
+  }
   CU(cudaEventRecord(ix->ev[EV_LUT], s));
   // Two scan phases when many slots are probed per query (C5-size leaves): the nearest eighth of the
   // leaves first, a compaction that tightens tau from "N-th best of the pilot's sample" to "N-th best of

@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "exact_math.cuh"
 #include "kernels.h"
+#include "lut.cuh"
 
 namespace sb {
 
@@ -1045,20 +1046,7 @@ lut_kernel(DevIndex ix, const float* __restrict__ q, uint8_t* __restrict__ lut,
   const uint32_t ne = ix.B * 16;
   float mx = 0.f;
   for (uint32_t e = tid; e < ne; e += kLutThreads) {
-    const uint32_t b = e >> 4, c = e & 15;
-    const uint32_t n = (uint32_t)ix.block_dims[b];
-    const float* qb = sq + ix.block_off[b];
-    const float* cx = ix.codebook + ((size_t)b * 16 + c) * ix.dpb;
-    auto lq = [&](uint32_t i) { return qb[i]; };
-    auto lx = [&](uint32_t i) { return cx[i]; };
-    float r;
-    if (ix.distance == 0) {
-      if (c < 15) r = n < 8 ? neg_dot_small(lq, lx, n) : neg_dot_avx2_order(lq, lx, n);
-      else r = -dot_sse4_order(lq, lx, n);
-    } else {
-      if (c < 15) r = n < 8 ? sql2_small(lq, lx, n) : sql2_avx2_order(lq, lx, n);
-      else r = sql2_sse4_order(lq, lx, n);
-    }
+    const float r = lut_raw_entry(ix, sq, e);
     raw[e] = r;
     mx = fmaxf(mx, fabsf(r));
   }
@@ -1069,13 +1057,10 @@ lut_kernel(DevIndex ix, const float* __restrict__ q, uint8_t* __restrict__ lut,
   if (tid == 0) {
     float m = 0.f;
     for (int w = 0; w < kLutThreads / 32; ++w) m = fmaxf(m, red[w]);
-    const float floor_ = __fsqrt_rn(FLT_EPSILON);
-    const float denom = m > floor_ ? m : floor_;
-    const float mult = __fdiv_rn(127.0f, denom);
+    const float mult = lut_multiplier(m);
     s_mult = mult;
     mult_out[qi] = mult;
-    // lut16_avx2.inc:429 (dot, double division) vs querying.h:450 (squared L2, 1.0f / mult)
-    inv_out[qi] = ix.key_by_dp ? __fdiv_rn(1.0f, mult) : (float)(1.0 / (double)mult);
+    inv_out[qi] = lut_inverse_multiplier(ix, mult);
   }
   __syncthreads();
   const float mult = s_mult;
@@ -1083,10 +1068,7 @@ lut_kernel(DevIndex ix, const float* __restrict__ q, uint8_t* __restrict__ lut,
   const uint32_t npad = ix.W * 8 * 16;
   for (uint32_t e = tid; e < npad; e += kLutThreads) {
     uint8_t v = 0;
-    if (e < ne) {
-      const float f = __fadd_rn(roundf(__fmul_rn(raw[e], mult)), 128.0f);
-      v = (uint8_t)(int)f;
-    }
+    if (e < ne) v = (uint8_t)lut_quantize(raw[e], mult);
     out[e] = v;
   }
 }

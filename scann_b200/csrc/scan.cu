@@ -33,6 +33,7 @@
 #include "common.cuh"
 #include "exact_math.cuh"
 #include "kernels.h"
+#include "lut.cuh"
 
 // How the main scan accumulates the four u16-lane registers of an oct lookup:
 //   0 = plain adds (ptxas merges pairs into IADD3 on the ALU pipe), 1 = two on ALU + two IMAD on the
@@ -400,12 +401,57 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   const int off128 = 128 * (int)ix.B;
   const uint32_t nover = w.nover;
   uint64_t* grow = w.buf + (size_t)q * w.cap;  // this query's (still empty) buffer row is the compaction scratch
-  {  // the query's own u8 LUT, [8W][16] bytes
+  float mult, inv;
+  if (w.q_for_lut) {
+    // Fused LUT build (lut_kernel's arithmetic, lut.cuh): raw table in the still unused candidate buffer, block
+    // maximum, multiplier, then the u8 table goes to shared memory for this kernel and to global memory for the
+    // main scan -- one launch and one re-read of the table less per batch.
+    __shared__ float s_red[kScanThreads / 32];
+    __shared__ float s_mi[2];
+    float* sq = reinterpret_cast<float*>(scand);
+    float* raw = sq + ((ix.d + 3) & ~3u);
+    for (uint32_t k = tid; k < ix.d; k += kScanThreads) sq[k] = w.q_for_lut[(size_t)q * ix.d + k];
+    __syncthreads();
+    const uint32_t ne = ix.B * 16;
+    float mx = 0.f;
+    for (uint32_t e = tid; e < ne; e += kScanThreads) {
+      const float r = lut_raw_entry(ix, sq, e);
+      raw[e] = r;
+      mx = fmaxf(mx, fabsf(r));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    if (tid == 0) {
+      float m = 0.f;
+      for (int i = 0; i < kScanThreads / 32; ++i) m = fmaxf(m, s_red[i]);
+      const float mu = lut_multiplier(m);
+      const float iv = lut_inverse_multiplier(ix, mu);
+      s_mi[0] = mu; s_mi[1] = iv;
+      const_cast<float*>(w.mult)[q] = mu;
+      const_cast<float*>(w.inv_mult)[q] = iv;
+    }
+    __syncthreads();
+    mult = s_mi[0]; inv = s_mi[1];
+    uint32_t* gl = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(w.lut) + (size_t)q * W * 128);
+    for (int t = tid; t < W * 32; t += kScanThreads) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t e = 4 * t + j;
+        if (e < ne) word |= lut_quantize(raw[e], mult) << (8 * j);
+      }
+      tbl[t] = word;
+      gl[t] = word;
+    }
+    __syncthreads();  // raw / sq alias the candidate buffer
+  } else {  // the query's own u8 LUT, [8W][16] bytes
     const uint32_t* src = reinterpret_cast<const uint32_t*>(w.lut + (size_t)q * W * 128);
     for (int t = tid; t < W * 32; t += kScanThreads) tbl[t] = src[t];
+    mult = w.mult[q]; inv = w.inv_mult[q];
   }
   if (tid == 0) { s_tau = kKeyMax; s_cnt = 0; }
-  const float mult = w.mult[q], inv = w.inv_mult[q];
   // Sample whole leaves, nearest first, until at least 4 N slots have been scored: the N-th best of
   // that sample is the pruning threshold of the main scan.  Nothing is published -- the main scan
   // covers every probed leaf, these too (1-2 % more scan work, and no hand-over of candidates).
@@ -957,6 +1003,10 @@ static int pilot_capl(uint32_t nover) {
 }
 size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover) {
   return (size_t)ix.W * 128 * 4 + (size_t)pilot_capl(nover) * 8;
+}
+// the fused LUT build keeps the query and the raw table in the pilot's candidate buffer
+bool pilot_can_build_lut(const DevIndex& ix, uint32_t nover) {
+  return ((size_t)((ix.d + 3) & ~3u) + (size_t)ix.B * 16) * 4 <= (size_t)pilot_capl(nover) * 8;
 }
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item) {
   return (size_t)quads_per_item * ix.W * 128 * 8 + 128;  // + alignment slack

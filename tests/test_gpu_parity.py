@@ -292,3 +292,21 @@ def test_int8_reordering_is_bit_exact(kw):
   else:
     truth = (qq ** 2).sum(1)[:, None] + a.dp_norms[i1.astype(np.int64)].astype(np.float64) - 2 * np.einsum("qd,qkd->qk", qq, rows)
   np.testing.assert_allclose(d1, truth, rtol=1e-4, atol=1e-3)
+
+
+# ---- LUT build fused into the pilot kernel vs the separate lut_kernel: same table, same results ----
+@pytest.mark.parametrize("kw", [CASES[0], CASES[5], CASES[8]], ids=["dot", "soar", "l2"])
+def test_fused_and_separate_lut_build_agree(kw, monkeypatch):
+  c = get_case(**kw)
+  i0, d0 = c.oracle.search_batched(c.q)
+  for fuse in ("1", "0"):
+    monkeypatch.setenv("SCANN_B200_FUSE_LUT", fuse)
+    i1, d1 = c.native.search_batched(c.q)
+    np.testing.assert_array_equal(i0, i1)
+    np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    a = c.oracle.candidates(c.q)
+    b = c.native.candidates(c.q)
+    np.testing.assert_array_equal(a["count"], b["count"])
+    for i in range(len(c.q)):
+      n = a["count"][i]
+      np.testing.assert_array_equal(a["score"][i, :n].view(np.uint32), b["score"][i, :n].view(np.uint32))
