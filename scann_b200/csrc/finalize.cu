@@ -76,6 +76,18 @@ __device__ __forceinline__ float exact_distance_lanes8(const DevIndex& ix, const
   const bool dot = ix.distance == 0;
   float a = 0.f;
   uint32_t j = 0;
+  // four 32-byte sectors of the gathered row in flight per 8-lane group before the first FMA needs one
+  for (; j + 32 <= n; j += 32) {
+    float xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xv[u] = __ldg(x + j + 8 * u + l);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float qv = q[j + 8 * u + l];
+      if (dot) a = __fmaf_rn(-qv, xv[u], a);
+      else { const float t = __fsub_rn(qv, xv[u]); a = __fmaf_rn(t, t, a); }
+    }
+  }
   for (; j + 8 <= n; j += 8) {
     const float xv = __ldg(x + j + l), qv = q[j + l];
     if (dot) a = __fmaf_rn(-qv, xv, a);
