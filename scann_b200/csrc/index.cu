@@ -520,8 +520,9 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(sb::launch_scan(v, w, 0, s));
   launches += 1; scan_launches += 1;
   CU(cudaEventRecord(ix->ev[EV_SCAN], s));
-  CU(sb::launch_compact(v, w, false, s));
-  launches += cap > 1024 ? 2 : 1;
+  int ncl = 0;
+  CU(sb::launch_compact(v, w, false, s, &ncl));
+  launches += ncl;
   CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
   if (two_phase) {
     w.rank_lo = r1; w.rank_hi = p.P;
@@ -531,8 +532,8 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
     CU(sb::launch_scan(v, w, 0, s));
     launches += 1; scan_launches += 1;
     CU(cudaEventRecord(ix->ev[EV2_SCAN], s));
-    CU(sb::launch_compact(v, w, false, s));
-    launches += cap > 1024 ? 2 : 1;
+    CU(sb::launch_compact(v, w, false, s, &ncl));
+    launches += ncl;
     CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
   }
   w.rank_lo = 0; w.rank_hi = p.P;  // re-scans of overflowed queries cover every probed leaf
@@ -563,8 +564,8 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
       CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
       sb::launch_worklist(v, w, true, false, s, &launches);
       CU(sb::launch_scan(v, w, 0, s));
-      CU(sb::launch_compact(v, w, true, s));
-      launches += cap > 1024 ? 3 : 2; scan_launches += 1;
+      CU(sb::launch_compact(v, w, true, s, &ncl));
+      launches += 1 + ncl; scan_launches += 1;
       CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
     }
@@ -654,8 +655,9 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
   while (row0 < v.n) {
     const uint32_t row1 = (uint64_t)row0 + chunk >= v.n ? v.n : row0 + chunk;
     CU(sb::bf_gemm_round(ix->bf_a.p, ix->bf_db.p, nq, v.n, ix->bf_dpitch, row0, row1, w, ix->bf_f32 ? 1 : 2, s));
-    CU(sb::launch_compact(v, w, false, s));
-    launches += 1 + (cap > 1024 ? 2 : 1);
+    int ncl = 0;
+    CU(sb::launch_compact(v, w, false, s, &ncl));
+    launches += 1 + (uint32_t)ncl;
     gemm_launches += 1;
     row0 = row1;
     chunk = (uint32_t)std::min<uint64_t>((uint64_t)row1 * growth, 0x40000000ull);

@@ -101,7 +101,8 @@ cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s);
 // counted = the per-leaf counts of ranks [rank_lo, rank_hi) are already in leaf_cnt (the pilot kernel does that)
 void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, bool counted, cudaStream_t s, int* launches);
 cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s);
-cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s);
+// *n_launched (optional) receives the number of kernels launched (1-3: small, medium, heavy-tail class)
+cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s, int* n_launched = nullptr);
 // ---- finalize ----
 struct FinalizeArgs {
   const float* q;         // [nq][D]

@@ -933,7 +933,7 @@ __device__ __forceinline__ void compact_one(const ScanWork& w, uint32_t q, int d
 // with more buffered candidates are appended to a list (w.entry_q is free after the scan) and
 // handled by compact_big_kernel with a handful of large-shared-memory CTAs.
 __global__ void __launch_bounds__(kScanThreads)
-compact_small_kernel(ScanWork w, int dedup, uint32_t hi) {
+compact_small_kernel(ScanWork w, int dedup, uint32_t hi, uint32_t mid) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint32_t s_dups;
   const uint32_t q = blockIdx.x;
@@ -943,19 +943,26 @@ compact_small_kernel(ScanWork w, int dedup, uint32_t hi) {
     atomicMax(&w.stats[3], (unsigned long long)nraw);
   }
   if (min(nraw, w.cap) > hi) {
-    if (threadIdx.x == 0) w.entry_q[atomicAdd(&w.counters[4], 1u)] = q;
+    // two size classes behind the common case: up to `mid` keys (32 KB of shared memory, several CTAs per SM: the
+    // typical C5-shape query buffers 1-3k keys) and the heavy tail (one CTA per SM).  The lists share entry_q: the
+    // big one grows from the front, the medium one from the back (together at most nq entries).
+    if (threadIdx.x == 0) {
+      if (min(nraw, w.cap) > mid) w.entry_q[atomicAdd(&w.counters[4], 1u)] = q;
+      else w.entry_q[(size_t)w.nq * (w.P ? w.P : 1u) - 1 - atomicAdd(&w.counters[6], 1u)] = q;  // P = 0: brute force
+    }
     return;
   }
   compact_one(w, q, dedup, reinterpret_cast<uint64_t*>(smem), &s_dups);
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-compact_big_kernel(ScanWork w, int dedup) {
+compact_big_kernel(ScanWork w, int dedup, int medium) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ uint32_t s_dups;
-  const uint32_t nbig = w.counters[4];
-  for (uint32_t i = blockIdx.x; i < nbig; i += gridDim.x) {
-    compact_one(w, w.entry_q[i], dedup, reinterpret_cast<uint64_t*>(smem), &s_dups);
+  const uint32_t nlist = w.counters[medium ? 6 : 4];
+  const size_t last = (size_t)w.nq * (w.P ? w.P : 1u) - 1;
+  for (uint32_t i = blockIdx.x; i < nlist; i += gridDim.x) {
+    compact_one(w, w.entry_q[medium ? last - i : i], dedup, reinterpret_cast<uint64_t*>(smem), &s_dups);
     __syncthreads();
   }
 }
@@ -1054,19 +1061,28 @@ cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStr
   return cudaGetLastError();
 }
 
-cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s) {
+cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s, int* n_launched) {
   (void)ix;
   int np2 = 2;
   while ((uint32_t)np2 < w.cap) np2 <<= 1;
   const uint32_t small = (uint32_t)np2 < 1024u ? (uint32_t)np2 : 1024u;
+  // the medium class pays where many queries buffer 1-4k keys (large leaves, brute-force rounds); on C2-size work
+  // its extra launch costs more than the heavy-tail kernel loses (0.077 -> 0.096 ms), so it is off there
+  const bool use_mid = w.stage != 0 || w.P == 0;
+  const uint32_t mid = !use_mid ? small : ((uint32_t)np2 < 4096u ? (uint32_t)np2 : 4096u);
   cudaError_t e = cudaMemsetAsync(w.counters + 4, 0, sizeof(uint32_t), s);
   if (e != cudaSuccess) return e;
-  compact_small_kernel<<<w.nq, kScanThreads, (size_t)small * 8, s>>>(w, dedup ? 1 : 0, small);
+  e = cudaMemsetAsync(w.counters + 6, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return e;
+  compact_small_kernel<<<w.nq, kScanThreads, (size_t)small * 8, s>>>(w, dedup ? 1 : 0, small, mid);
   if ((uint32_t)np2 > small) {
-    const size_t smem = (size_t)np2 * 8;
-    e = cudaFuncSetAttribute(compact_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(compact_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)np2 * 8));
     if (e != cudaSuccess) return e;
-    compact_big_kernel<<<296, kScanThreads, smem, s>>>(w, dedup ? 1 : 0);
+    if (mid > small) compact_big_kernel<<<148 * 6, kScanThreads, (size_t)mid * 8, s>>>(w, dedup ? 1 : 0, 1);
+    if ((uint32_t)np2 > mid) compact_big_kernel<<<296, kScanThreads, (size_t)np2 * 8, s>>>(w, dedup ? 1 : 0, 0);
+    if (n_launched) *n_launched = 1 + (mid > small ? 1 : 0) + ((uint32_t)np2 > mid ? 1 : 0);
+  } else if (n_launched) {
+    *n_launched = 1;
   }
   return cudaGetLastError();
 }
