@@ -494,7 +494,12 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaEventRecord(ix->ev[EV_TOK], s));
   // LUT build: fused into the pilot kernel when the raw table fits its candidate buffer (every BASELINE.json
   // configuration; SCANN_B200_FUSE_LUT=0 keeps the separate lut_kernel)
-  bool fuse_lut = sb::pilot_can_build_lut(v, p.nover);
+  // pilot buffer: the default (1024 keys or 2 N' + 128) selects every ~900 buffered keys, which also tightens the
+  // pilot's own threshold early; buffering a whole large leaf and selecting once was measured and rejected
+  // (20M x 96: pilot 0.72 -> 1.47 ms).  SCANN_B200_PILOT_CAP overrides (tests).
+  w.pilot_cap = 0;
+  if (const char* e = getenv("SCANN_B200_PILOT_CAP")) w.pilot_cap = (uint32_t)atoi(e);
+  bool fuse_lut = sb::pilot_can_build_lut(v, w);
   if (const char* e = getenv("SCANN_B200_FUSE_LUT")) fuse_lut = fuse_lut && e[0] != '0';
   w.q_for_lut = fuse_lut ? d_q : nullptr;
   if (!fuse_lut) {

@@ -75,6 +75,7 @@ struct ScanWork {
   uint32_t one;               // always 1; a runtime value so the scan's IMAD accumulates stay IMADs
   uint32_t stage;             // 1: the main scan stages candidates per item in shared memory (large leaves)
   const float* q_for_lut;     // [nq][D] queries: non-NULL = the pilot builds lut / mult / inv_mult itself (fused LUT build)
+  uint32_t pilot_cap;         // keys the pilot buffers between selections (0 = the default, 1024 or 2 N' + 128)
   uint32_t pilot_target;      // slots the pilot samples per query before it fixes tau (4 N')
   uint32_t pilot_partial;     // 1: the pilot may stop inside a leaf once the target is reached (small leaves)
 };
@@ -94,8 +95,8 @@ bool tokenize_tensor_path(const DevIndex& ix, uint32_t P);
 cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq, uint32_t P, float* dist, void* a_ws,
                                  int32_t* leaves, float* bias, uint32_t* fallbacks, cudaStream_t s, int* launches);
 // ---- scan ----
-size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover);
-bool pilot_can_build_lut(const DevIndex& ix, uint32_t nover);
+size_t pilot_smem_bytes(const DevIndex& ix, const ScanWork& w);
+bool pilot_can_build_lut(const DevIndex& ix, const ScanWork& w);
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item);
 cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s);
 // counted = the per-leaf counts of ranks [rank_lo, rank_hi) are already in leaf_cnt (the pilot kernel does that)

@@ -1003,27 +1003,29 @@ leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, 
     default: return cudaErrorInvalidValue;                                               \
   }
 
-static int pilot_capl(uint32_t nover) {
-  int capl = 1024;  // keys buffered between selections; a typical leaf fits
-  while ((uint32_t)capl < 2 * nover + kScanThreads) capl <<= 1;
+static int pilot_capl(const ScanWork& w) {
+  int capl = 1024;  // keys buffered between selections; a typical C2 leaf fits
+  while ((uint32_t)capl < 2 * w.nover + kScanThreads) capl <<= 1;
+  // large leaves: hold a whole leaf, so the pilot selects once at the end instead of every ~900 keys
+  while ((uint32_t)capl < w.pilot_cap && capl < 8192) capl <<= 1;
   return capl;
 }
-size_t pilot_smem_bytes(const DevIndex& ix, uint32_t nover) {
-  return (size_t)ix.W * 128 * 4 + (size_t)pilot_capl(nover) * 8;
+size_t pilot_smem_bytes(const DevIndex& ix, const ScanWork& w) {
+  return (size_t)ix.W * 128 * 4 + (size_t)pilot_capl(w) * 8;
 }
 // the fused LUT build keeps the query and the raw table in the pilot's candidate buffer
-bool pilot_can_build_lut(const DevIndex& ix, uint32_t nover) {
-  return ((size_t)((ix.d + 3) & ~3u) + (size_t)ix.B * 16) * 4 <= (size_t)pilot_capl(nover) * 8;
+bool pilot_can_build_lut(const DevIndex& ix, const ScanWork& w) {
+  return ((size_t)((ix.d + 3) & ~3u) + (size_t)ix.B * 16) * 4 <= (size_t)pilot_capl(w) * 8;
 }
 size_t scan_smem_bytes(const DevIndex& ix, uint32_t quads_per_item) {
   return (size_t)quads_per_item * ix.W * 128 * 8 + 128;  // + alignment slack
 }
 
 cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) {
-  const int capl = pilot_capl(w.nover);
+  const int capl = pilot_capl(w);
   cudaError_t em = cudaMemsetAsync(w.leaf_cnt, 0, sizeof(uint32_t) * (ix.L + 1), s);
   if (em != cudaSuccess) return em;
-  const size_t smem = pilot_smem_bytes(ix, w.nover);
+  const size_t smem = pilot_smem_bytes(ix, w);
   SB_DISPATCH_W(ix.W, {
     cudaError_t e = cudaFuncSetAttribute(pilot_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

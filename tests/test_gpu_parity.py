@@ -194,6 +194,7 @@ def test_two_phase_scan_is_bit_exact(kw, cap, monkeypatch):
 @pytest.mark.parametrize("mode", ["single", "two_phase", "overflow"])
 def test_staged_candidate_push_is_bit_exact(kw, mode, monkeypatch):
   monkeypatch.setenv("SCANN_B200_SCAN_STAGE", "1")
+  monkeypatch.setenv("SCANN_B200_PILOT_CAP", "4096")     # the large-leaf pilot buffer as well
   monkeypatch.setenv("SCANN_B200_TWO_PHASE", "1" if mode != "single" else "0")
   if mode == "overflow":
     monkeypatch.setenv("SCANN_B200_CAND_CAP", "256")
