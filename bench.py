@@ -669,9 +669,12 @@ def run_reference(args, wl):
       "unit": "queries/s", "n_gpus": args.gpus, "steps": steps_run, "warmup": min(warmup, 1),
       "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "u8 LUT / int16 accumulate (AVX2)", "data": "synthetic",
-      "config": {"workload": args.workload, "n": wl["n"], "d": wl["d"], "leaves": wl["leaves"],
-                 "leaves_to_search": wl["probe"], "reorder": wl["pre"], "k": wl["k"],
-                 "queries_per_step": sample},
+      "config": {"workload": args.workload, "distance": wl.get("distance", "dot_product"), "n": wl["n"], "d": wl["d"],
+                 "leaves": wl["leaves"], "soar_lambda": wl.get("soar"), "leaves_to_search": wl["probe"],
+                 "ah_blocks": wl["d"] // wl["dpb"], "reorder": wl["pre"], "k": wl["k"],
+                 "noise_shaping_threshold": wl.get("noise"),
+                 "queries_per_step": sample,
+                 "sample_note": f"bounded sample: the first {sample} of the workload's {wl['nq']} queries per step"},
       "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
                        "sample": f"{sample} queries per step, batches of 256 over {threads} threads"},
       "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
