@@ -1,6 +1,7 @@
 /*
  * scann_oracle.c -- CPU restatement of ScaNN's batched query hot path
- * (tokenize -> AH LUT -> LUT16 scan -> top-N -> SOAR dedup -> exact reorder -> sort).
+ * (tokenize -> AH LUT -> LUT16 scan -> top-N -> SOAR dedup -> exact reorder -> sort), of bf16 / float brute force,
+ * and of the per-datapoint stage of index construction (database tokenization, SOAR assignment, AH encoding).
  *
  * TEST INFRASTRUCTURE ONLY -- see scann_oracle.h.  "parity unpinned" with
  * respect to the reference binary (it cannot be built here and ships no golden
