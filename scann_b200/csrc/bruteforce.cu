@@ -315,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             a.cmax[(size_t)q * a.ld_c + (col >> 5)] = mx;
           }
-          if (qvalid) {
+          if (qvalid && a.out) {
             if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -522,7 +522,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             a.cmax[(size_t)q * a.ld_c + (col >> 5)] = mx;
           }
-          if (qvalid) {
+          if (qvalid && a.out) {
             if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)

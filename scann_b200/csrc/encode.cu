@@ -620,6 +620,7 @@ extern "C" int scann_b200_encode_database(const scann_b200_encode_desc* d, int32
   v.tok_fallback_flag = fbflag.as<uint8_t>();
   CU(tok_cmax.alloc(sizeof(float) * (size_t)R * ((L + 31) / 32)));
   v.tok_cmax_ws = tok_cmax.as<float>();
+  v.tok_need_rows = soar ? 1 : 0;  // the SOAR pruning reads the distance matrix
   const bool row_is_dot = sb::tokenize_tensor_path(v, P);
   // SOAR: the projection term is pruned with a second tensor-core GEMM (rhat x centres) when the centre operand
   // exists; small trees (SIMT tokenization) prune by distance only

@@ -47,6 +47,9 @@ struct DevIndex {
   uint8_t* tok_fallback_flag;
   // optional workspace [nq][ceil(L / 32)] floats: enables the chunk pre-selection of the tokenizer (prep.cu)
   float* tok_cmax_ws;
+  // 1: callers read the [nq][L] matrix of the tokenization GEMM afterwards (the SOAR pruning of the index-build
+  // stage); 0: the chunk pre-selection may skip storing it and evaluate the exact chain for whole candidate chunks
+  int tok_need_rows;
 };
 
 struct ScanWork {

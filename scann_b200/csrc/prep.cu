@@ -825,7 +825,7 @@ constexpr int kChunkMaxChunks = 2048;  // L <= 65536
 __global__ void __launch_bounds__(256)
 topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ S, const float* __restrict__ cmax_ws,
                   int nq, int P, int Ppow2, float eps_rel, int32_t* __restrict__ leaves, float* __restrict__ bias,
-                  uint32_t* fallbacks) {
+                  uint32_t* fallbacks, int have_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int qi = blockIdx.x * 8 + warp;
@@ -872,24 +872,6 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
   const uint32_t prefix = warp_radix_select([&](int j) { return f2ord(cm[j]); }, Lc, (uint32_t)P, hist, lane, need);
   const float U = ord2f(prefix);
   const float thr = __fadd_ru(U, __fmul_ru(2.f, eps));
-  uint32_t count = 0;
-  for (int j0 = 0; j0 < Lc; j0 += 32) {
-    const int j = j0 + lane;
-    uint32_t hits = __ballot_sync(0xFFFFFFFFu, j < Lc && !(cm[j] > thr));
-    while (hits) {
-      const int jj = j0 + __ffs(hits) - 1;
-      hits &= hits - 1;
-      const int i = jj * 32 + lane;
-      const bool c = i < L && !(approx(i) > thr);
-      const uint32_t mk = __ballot_sync(0xFFFFFFFFu, c);
-      if (c) {
-        const uint32_t pos = count + __popc(mk & lt);
-        if (pos < (uint32_t)kStreamCand) skeys[pos] = (uint64_t)(uint32_t)i;
-      }
-      count += __popc(mk);
-    }
-  }
-  __syncwarp();
   auto exact = [&](int idx) -> float {  // the reference's sequential fnmadd chain (tokenize_kernel)
     const float* c = ix.centers + (size_t)idx * D;
     float acc = sql2 ? __fadd_rn(ix.center_sqnorm[idx], qn) : 0.f;
@@ -908,6 +890,38 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
     }
     return acc;
   };
+  // Without the stored matrix (have_rows == 0: the GEMM only wrote the chunk maxima) the element test runs on the
+  // exact chain itself: every centre of a candidate chunk is evaluated (32 consecutive centre rows, one per lane) and
+  // kept if exact <= U + eps -- an element of the exact top P has chain <= T* <= U + eps, T* being the P-th smallest
+  // chain distance, because the P chunks with minimum <= U each hold an element with chain <= U + eps.  The keys carry
+  // the exact distance already (bit 63 of the buffered key marks them).
+  const float thr_exact = __fadd_ru(U, eps);
+  uint32_t count = 0;
+  for (int j0 = 0; j0 < Lc; j0 += 32) {
+    const int j = j0 + lane;
+    uint32_t hits = __ballot_sync(0xFFFFFFFFu, j < Lc && !(cm[j] > thr));
+    while (hits) {
+      const int jj = j0 + __ffs(hits) - 1;
+      hits &= hits - 1;
+      const int i = jj * 32 + lane;
+      float e = 0.f;
+      bool c;
+      if (have_rows) {
+        c = i < L && !(approx(i) > thr);
+      } else {
+        if (i < L) e = exact(i);
+        c = i < L && !(e > thr_exact);
+      }
+      const uint32_t mk = __ballot_sync(0xFFFFFFFFu, c);
+      if (c) {
+        const uint32_t pos = count + __popc(mk & lt);
+        if (pos < (uint32_t)kStreamCand)
+          skeys[pos] = have_rows ? (uint64_t)(uint32_t)i : (((uint64_t)f2ord(e) << 32) | (uint32_t)i);
+      }
+      count += __popc(mk);
+    }
+  }
+  __syncwarp();
   int32_t* lout = leaves + (size_t)qi * P;
   float* bout = bias + (size_t)qi * P;
   if (count <= (uint32_t)kStreamCand) {
@@ -915,9 +929,13 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
     while ((uint32_t)ns < count) ns <<= 1;
     for (int j = lane; j < ns; j += 32) {
       const bool live = (uint32_t)j < count;
-      const uint32_t idx = live ? (uint32_t)skeys[j] : 0u;
-      const float e = live ? exact((int)idx) : 0.f;
-      skeys[j] = live ? (((uint64_t)f2ord(e) << 32) | idx) : kKeyMax;
+      if (have_rows) {
+        const uint32_t idx = live ? (uint32_t)skeys[j] : 0u;
+        const float e = live ? exact((int)idx) : 0.f;
+        skeys[j] = live ? (((uint64_t)f2ord(e) << 32) | idx) : kKeyMax;
+      } else if (!live) {
+        skeys[j] = kKeyMax;
+      }
     }
     __syncwarp();
     warp_bitonic_sort(skeys, ns, lane);
@@ -962,7 +980,14 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
     if (env && (!strcmp(env, "tcgen05") || !strcmp(env, "stream"))) chunked = false;
     else if (!(env && !strcmp(env, "chunk")) && ix.L < 4096) chunked = false;
   }
-  e = gemm_bf16_nt(a_ws, nq, (nq + 127) / 128 * 128, ix.tok_b, ix.L, ix.tok_kp, dist, ix.L, s,
+  // SCANN_B200_TOKENIZE_ROWS=0: do not store the matrix when nobody else reads it (chunk pre-selection without
+  // tok_need_rows); the element test then evaluates the exact chain for whole candidate chunks.  Measured and rejected
+  // as the default: at 40k centres the GEMM is bound by its operand traffic from L2, not by the store (1.19 -> 1.11 ms
+  // at P = 24), and the 32 exact chains per candidate chunk cost more than the stored row saves (1.40 -> 3.08 ms at
+  // P = 80).
+  bool store_rows = true;
+  if (const char* env = getenv("SCANN_B200_TOKENIZE_ROWS")) store_rows = !(env[0] == '0' && chunked && ix.tok_need_rows == 0);
+  e = gemm_bf16_nt(a_ws, nq, (nq + 127) / 128 * 128, ix.tok_b, ix.L, ix.tok_kp, store_rows ? dist : nullptr, ix.L, s,
                    chunked ? ix.tok_cmax_ws : nullptr, n_chunks, ix.distance == 1 ? ix.center_sqnorm : nullptr);
   if (e != cudaSuccess) return e;
   if (chunked) {
@@ -974,7 +999,7 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
     e = cudaFuncSetAttribute(topp_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     topp_chunk_kernel<<<(nq + 7) / 8, 256, bytes, s>>>(ix, q, dist, ix.tok_cmax_ws, (int)nq, (int)P, sp, er, leaves, bias,
-                                                       fallbacks);
+                                                       fallbacks, store_rows ? 1 : 0);
     if (launches) *launches += 3;
     return cudaGetLastError();
   }

@@ -295,6 +295,18 @@ def test_int8_reordering_is_bit_exact(kw):
   np.testing.assert_allclose(d1, truth, rtol=1e-4, atol=1e-3)
 
 
+# ---- chunk pre-selection without the stored distance matrix (exact chain for whole candidate chunks) ----
+@pytest.mark.parametrize("kw", [TOK_CASES[8], TOK_CASES[9], TOK_CASES[10]], ids=["dot", "odd", "l2"])
+def test_chunk_preselection_without_stored_rows(kw, monkeypatch):
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", "chunk")
+  monkeypatch.setenv("SCANN_B200_TOKENIZE_ROWS", "0")
+  c = get_case(**kw)
+  l0, d0 = c.oracle.tokenize(c.q)
+  l1, d1 = c.native.tokenize(c.q)
+  np.testing.assert_array_equal(l0, l1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
 # ---- LUT build fused into the pilot kernel vs the separate lut_kernel: same table, same results ----
 @pytest.mark.parametrize("kw", [CASES[0], CASES[5], CASES[8]], ids=["dot", "soar", "l2"])
 def test_fused_and_separate_lut_build_agree(kw, monkeypatch):
