@@ -794,10 +794,14 @@ uint32_t bf_query_rows_pad(uint32_t nq) { return bf_m_pad(nq); }
 cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows_pad, const void* b_operand,
                          uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s, float* cmax,
                          uint32_t ld_c, const float* cbias) {
+  // SCANN_B200_TOK_GEMM=pair: the CTA-pair kernel (each CTA loads half of the B tile) for this GEMM too; at K = 320
+  // the one-CTA kernel is bound by its operand traffic from L2 (tokenization)
+  bool pair = false;
+  { const char* pe = getenv("SCANN_B200_TOK_GEMM"); pair = pe && !strcmp(pe, "pair"); }
   CUtensorMap tmA, tmB;
   cudaError_t e = make_tmap(&tmA, a_operand, a_rows_pad, kpitch, kpitch, bf::BM);
   if (e != cudaSuccess) return e;
-  e = make_tmap(&tmB, b_operand, b_rows, kpitch, kpitch, bf::BN);
+  e = make_tmap(&tmB, b_operand, b_rows, kpitch, kpitch, pair ? bf::BN / 2 : bf::BN);
   if (e != cudaSuccess) return e;
   bf::GemmArgs a{};
   a.nq = a_rows; a.m_pad = a_rows_pad; a.row0 = 0; a.row1 = b_rows;
@@ -805,6 +809,7 @@ cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows
   a.num_kb = (kpitch + bf::BK - 1) / bf::BK;
   a.out = out; a.ld = ld;
   a.cmax = cmax; a.ld_c = ld_c; a.cbias = cbias;
+  if (pair) return launch_gemm_pair<1, bf::kEpiStore>(tmA, tmB, a, s);
   return launch_gemm<1, bf::kEpiStore>(tmA, tmB, a, s);
 }
 
