@@ -250,3 +250,44 @@ def test_int8_reordering_assets_round_trip(tmp_path):
   np.testing.assert_array_equal(b2.int8_dataset, q8)
   np.testing.assert_array_equal(b2.int8_multipliers, mult)
   np.testing.assert_array_equal(b2.dp_norms, norms)
+
+
+def test_plan_reads_reordering_and_noise_shaping_options():
+  """Host logic of ScannNumpy(db, config, threads): which searcher / reordering helper / encoder the config selects
+  (base/reordering_helper_factory.cc:106-200, tree_ah_hybrid_residual.cc:414-428)."""
+  from scann_b200.scann_pybind import _Plan
+  import math
+  db = np.zeros((10, 8), np.float32)
+  R = scann_builder.ReorderType
+  mk = lambda **kw: scann_builder.ScannBuilder(db, 5, kw.pop("dist", "dot_product")).tree(4, 2).score_ah(2, **kw)
+  p = _Plan(mk(anisotropic_quantization_threshold=0.2).reorder(30).create_config())
+  p.check_supported()
+  assert not p.int8_reorder() and not p.bf16_reorder() and not p.is_brute_force()
+  assert abs(cfgmod.as_float(p.ah.get("noise_shaping_threshold"), math.nan) - 0.2) < 1e-12
+  p = _Plan(mk().reorder(30, quantize=R.INT8).create_config())
+  p.check_supported()
+  assert p.int8_reorder() and not p.bf16_reorder()
+  assert math.isnan(cfgmod.as_float(p.ah.get("noise_shaping_threshold"), math.nan))
+  p = _Plan(mk(dist="squared_l2").reorder(30, quantize=R.BFLOAT16).create_config())
+  p.check_supported()
+  assert p.bf16_reorder() and not p.int8_reorder() and p.distance == "squared_l2"
+  # noise-shaped quantization of the REORDERING rows is not built: rejected loudly, not ignored
+  with pytest.raises(Exception, match="noise-shaped"):
+    _Plan(mk().reorder(30, quantize=R.INT8, anisotropic_quantization_threshold=0.2).create_config()).check_supported()
+  bf = _Plan(scann_builder.ScannBuilder(db, 5, "dot_product").score_brute_force(R.BFLOAT16).create_config())
+  assert bf.is_brute_force() and bf.bf16_brute_force()
+
+
+def test_int8_quantizer_semantics():
+  """ScalarQuantizeFloatDataset at quantile 1.0 (utils/scalar_quantization_helpers.cc:39-63, .h:40-50)."""
+  from scann_b200 import index_build
+  x = np.array([[0.5, -2.0, 0.0, 1.0], [-0.25, 1.0, 0.0, 0.996], [0.0019685, 0.0, 0.0, -1.0]], np.float32)
+  q, m = index_build.int8_quantize(x)
+  np.testing.assert_array_equal(m, np.array([254.0, 63.5, 1.0, 127.0], np.float32))   # 127 / max|column|, 1 for a zero column
+  # 0.5 * 254 = 127; -0.25 * 254 = -63.5 -> -64 (round half away from zero); 0.0019685 * 254 = 0.49999 -> 0
+  np.testing.assert_array_equal(q[:, 0], np.array([127, -64, 0], np.int8))
+  np.testing.assert_array_equal(q[:, 1], np.array([-127, 64, 0], np.int8))             # 1.0 * 63.5 = 63.5 -> 64
+  np.testing.assert_array_equal(q[:, 2], np.zeros(3, np.int8))
+  np.testing.assert_array_equal(q[:, 3], np.array([127, 126, -127], np.int8))          # 0.996 * 127 = 126.49 -> 126
+  n = index_build.squared_l2_norms(x)
+  np.testing.assert_allclose(n, (x.astype(np.float64) ** 2).sum(1), rtol=1e-7)
