@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SCANN_B200_ABI_VERSION 3
+#define SCANN_B200_ABI_VERSION 4
 
 enum { SCANN_B200_DOT_PRODUCT = 0, SCANN_B200_SQUARED_L2 = 1 };
 
@@ -75,7 +75,14 @@ typedef struct {
   const int8_t* int8_dataset;      /* int8_dataset.npy [N][D] */
   const float* int8_multipliers;   /* int8_multipliers.npy [D]: multiplier_by_dimension */
   const float* dp_norms;           /* dp_norms.npy [N]: squared L2 norms of the original rows (squared L2 only) */
+  /* how a tree-AH database is split over shard_world ranks:
+   *   SCANN_B200_SHARD_BY_ID   every leaf is split, this rank holds datapoints with id % shard_world == shard_rank
+   *   SCANN_B200_SHARD_BY_LEAF whole leaves (incl. their SOAR copies) are dealt out, this rank holds the leaves with
+   *                            leaf % shard_world == shard_rank and the rows of the datapoints stored in them */
+  int32_t shard_mode;
 } scann_b200_index_desc;
+
+enum { SCANN_B200_SHARD_BY_ID = 0, SCANN_B200_SHARD_BY_LEAF = 1 };
 
 /* Replaces ScannInterface::Initialize(ScannArtifacts) (scann_ops/cc/scann.cc:355-381) and the
  * per-leaf asymmetric_hashing2::Searcher construction incl. CreatePackedDataset
@@ -113,6 +120,36 @@ int scann_b200_merge_partials_device(scann_b200_index* index, uint32_t nq, int32
                                      const uint64_t* d_tiebreak, const float* d_ah_score,
                                      const float* d_exact, int32_t pre_reorder_nn, int32_t final_nn,
                                      uint32_t* d_out_idx, float* d_out_dist, int32_t out_k);
+
+/*
+ * Database-sharded search, one process per GPU (the reference has no multi-device searcher:
+ * the single-device semantics are those of scann_b200_search_batched_device, and the result is bit-identical to it).
+ *   scann_b200_comm_unique_id   rank 0 creates the 128-byte NCCL id; the caller distributes it (any side channel)
+ *   scann_b200_comm_init        every rank joins; `index` must have been created with the same shard_rank / shard_world
+ *   scann_b200_search_sharded_device   every rank calls it with the SAME queries (device buffers, [nq][D]); every rank
+ *                               receives the full result ([nq][out_k] device buffers).
+ * Per batch, on the index's stream, with NCCL over NVLink as the only exchange:
+ *   1. each rank tokenizes nq / world queries; all-gather of the (leaf, centre distance) lists          8 B x P per query
+ *   2. the rank that owns a query's nearest leaf fixes the pruning threshold tau; all-reduce(min)         8 B per query
+ *   3. LUT16 scan of the rank's own leaves / datapoints, local top-N', exact distances of those candidates
+ *   4. all-to-all: the 16-byte records (tie-break key, id, exact distance) of query q go to rank q / ceil(nq / world)
+ *   5. that rank merges world sorted lists: global top-N' -> SOAR dedup -> top-k by (distance, id)
+ *   6. all-gather of the k results                                                                       8 B x k per query
+ * light != 0 selects the north star's light protocol instead of 4-6: every rank finishes its local top-k and one
+ * all-gather of (id, distance) x k per query per rank is merged (duplicates by id removed).  The light result
+ * reorders a superset of the single-GPU candidates, so it is NOT bit-identical (recall >= the parity mode's).
+ */
+int scann_b200_comm_unique_id(void* out_id128);
+int scann_b200_comm_init(scann_b200_index* index, int32_t rank, int32_t world, const void* id128);
+int scann_b200_search_sharded_device(scann_b200_index* index, const float* d_queries, uint32_t nq, int32_t final_nn,
+                                     int32_t pre_reorder_nn, int32_t leaves, int32_t light, uint32_t* d_out_idx,
+                                     float* d_out_dist, int32_t out_k);
+/* The same protocol with all `world` shards living in THIS process (indexes created with shard_rank 0..world-1, on
+ * one device or several): the exchanges are device copies.  Used by the tests to run world-size 2/3/4/8 searches on
+ * one GPU; the result is written once. */
+int scann_b200_search_sharded_local(scann_b200_index* const* shards, int32_t world, const float* d_queries, uint32_t nq,
+                                    int32_t final_nn, int32_t pre_reorder_nn, int32_t leaves, int32_t light,
+                                    uint32_t* d_out_idx, float* d_out_dist, int32_t out_k);
 
 /* Row-sharded brute force (the reference has no multi-device searcher, the single
  * device semantics are Bfloat16BruteForceSearcher::FindNeighborsImpl, brute_force/bfloat16_brute_force.cc:101-152).
@@ -234,6 +271,11 @@ typedef struct {
   uint64_t cand_sum;          /* candidates buffered per query after the main scan, summed */
   uint64_t cand_max;          /* ... and the maximum over queries */
   uint64_t tokenize_fallbacks; /* queries whose tensor-core tokenization pre-filter fell back to exact distances */
+  /* sharded search: collectives (all of them, CUDA events around the NCCL calls) and the owner-side merge */
+  float ms_exchange, ms_merge;
+  uint64_t exchange_bytes;     /* bytes this rank sent in the last call */
+  uint32_t bf_widenings;       /* brute force: re-runs with a wider candidate window / safe rounds (0 in the common case) */
+  uint32_t bf_exact_fallbacks; /* brute force: queries finished by the exact all-rows kernel */
 } scann_b200_stats;
 /* Timing (CUDA events on the index's stream) and traffic figures of the last search call. */
 int scann_b200_last_stats(scann_b200_index* index, scann_b200_stats* out);

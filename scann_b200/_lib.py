@@ -26,6 +26,7 @@ class IndexDesc(C.Structure):
       ("default_pre_nn", C.c_int32), ("default_final_nn", C.c_int32),
       ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
       ("int8_dataset", C.c_void_p), ("int8_multipliers", C.c_void_p), ("dp_norms", C.c_void_p),
+      ("shard_mode", C.c_int32),
   ]
 
 
@@ -38,6 +39,8 @@ class Stats(C.Structure):
       ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("scan_kernel_count", C.c_uint32),
       ("cand_sum", C.c_uint64), ("cand_max", C.c_uint64),
       ("tokenize_fallbacks", C.c_uint64),
+      ("ms_exchange", C.c_float), ("ms_merge", C.c_float), ("exchange_bytes", C.c_uint64),
+      ("bf_widenings", C.c_uint32), ("bf_exact_fallbacks", C.c_uint32),
   ]
 
   def as_dict(self):
@@ -68,6 +71,8 @@ EXPORTS = [
     "scann_b200_index_create", "scann_b200_index_destroy", "scann_b200_search_batched",
     "scann_b200_search_batched_device", "scann_b200_search_partial_device",
     "scann_b200_merge_partials_device", "scann_b200_merge_topk_device", "scann_b200_last_error",
+    "scann_b200_comm_unique_id", "scann_b200_comm_init", "scann_b200_search_sharded_device",
+    "scann_b200_search_sharded_local",
     "scann_b200_abi_version",
     "scann_b200_debug_tokenize", "scann_b200_debug_lut", "scann_b200_debug_leaf_scores",
     "scann_b200_debug_candidates", "scann_b200_leaf_size", "scann_b200_last_stats",
@@ -100,6 +105,10 @@ def lib():
   L.scann_b200_search_partial_device.argtypes = [vp, vp, u32, i32, i32, vp, vp, vp, vp, i32]
   L.scann_b200_merge_partials_device.argtypes = [vp, u32, i32, i32, vp, vp, vp, vp, i32, i32, vp, vp, i32]
   L.scann_b200_merge_topk_device.argtypes = [vp, u32, i32, i32, vp, vp, i32, vp, vp, i32]
+  L.scann_b200_comm_unique_id.argtypes = [vp]
+  L.scann_b200_comm_init.argtypes = [vp, i32, i32, vp]
+  L.scann_b200_search_sharded_device.argtypes = [vp, vp, u32, i32, i32, i32, i32, vp, vp, i32]
+  L.scann_b200_search_sharded_local.argtypes = [C.POINTER(vp), i32, vp, u32, i32, i32, i32, i32, vp, vp, i32]
   L.scann_b200_last_error.restype = C.c_char_p
   L.scann_b200_abi_version.restype = C.c_int
   L.scann_b200_debug_tokenize.argtypes = [vp, vp, u32, i32, vp, vp]
@@ -147,7 +156,7 @@ class NativeIndex:
   """Owns one scann_b200_index handle built from IndexArrays."""
 
   def __init__(self, arrays, leaves_to_search, pre_reorder_nn, final_nn, device=0, shard_rank=0,
-               shard_world=1):
+               shard_world=1, shard_mode=0):
     L = lib()
     a = arrays
     keep = []
@@ -184,6 +193,7 @@ class NativeIndex:
     d.device = device
     d.shard_rank = shard_rank
     d.shard_world = shard_world
+    d.shard_mode = shard_mode
     h = C.c_void_p()
     check(L.scann_b200_index_create(C.byref(d), C.byref(h)))
     self._h = h

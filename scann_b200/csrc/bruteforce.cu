@@ -27,6 +27,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -567,13 +569,50 @@ __global__ void init_topk_state_kernel(uint32_t nq, uint32_t* cnt, uint64_t* tau
   if (i < nq) { cnt[i] = 0; tau[i] = kKeyMax; ovf[i] = 0; }
 }
 
+// Is the candidate window wide enough?  The k' kept rows are the k' smallest APPROXIMATE keys (split-bf16 tensor-core
+// scores), so every row outside has approximate distance >= a_last, the largest kept one, and exact distance
+// >= a_last - eps with eps = eps_rel * ||q|| * max_i ||x_i|| bounding |approximate - exact| (dropped split terms
+// <= 2^-15, fp32 accumulation of K products <= K * 2^-21 including the exact chain's own rounding, all relative to
+// sum |q_d x_d| <= ||q|| ||x||; the same bound as the tokenization pre-filter).  If the k-th
+// exact distance is strictly below that, no outside row can enter or tie into the top k.  Otherwise the query is
+// flagged and the host widens the window (or finishes the query with the exact all-rows kernel).  Called by all
+// threads after the final sort; sq = the query in shared memory.
+struct SafetyArgs {
+  float eps_rel, max_row_norm;
+  uint32_t* unsafe;    // [nq] flag per query
+  uint32_t* n_unsafe;  // counter
+};
+__device__ __forceinline__ void check_window(const SafetyArgs& sa, uint32_t qi, const float* sq, uint32_t d, uint32_t m,
+                                             uint32_t kprime, uint32_t kk, const uint64_t* src, const uint64_t* ka) {
+  if (!sa.unsafe) return;
+  __shared__ float s_part[4];
+  float a = 0.f;
+  for (uint32_t i = threadIdx.x; i < d; i += 128) a = fmaf(sq[i], sq[i], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float qn = sqrtf((s_part[0] + s_part[1]) + (s_part[2] + s_part[3])) * 1.0001f;
+    bool bad = false;
+    if (m == kprime && kk > 0 && qn > 0.f) {  // fewer than k' candidates = every row is one; zero query: all keys exact
+      const float a_last = ord2f((uint32_t)(src[m - 1] >> 32));  // the buffer is sorted by the last compaction
+      const float e_k = ord2f((uint32_t)(ka[kk - 1] >> 32));
+      const float eps = sa.eps_rel * qn * sa.max_row_norm;
+      bad = !(e_k < a_last - eps);
+    }
+    sa.unsafe[qi] = bad ? 1u : 0u;
+    if (bad) atomicAdd(sa.n_unsafe, 1u);
+  }
+}
+
 // Exact re-scoring of the k' candidates (f32 query x bf16 row, the oracle's 8-lane FMA order),
 // final top-k by (distance, id), output.
 __global__ void __launch_bounds__(128)
 rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db, uint32_t d, uint32_t dpitch,
                const uint64_t* __restrict__ buf, const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t kprime,
                uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist,
-               int np2) {
+               int np2, SafetyArgs sa) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
   float* sq = reinterpret_cast<float*>(ka + np2);
@@ -604,6 +643,7 @@ rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db
   __syncthreads();
   block_bitonic_sort(ka, np2);
   const uint32_t kk = min(k, m);
+  check_window(sa, qi, sq, d, m, kprime, kk, src, ka);
   for (uint32_t i = tid; i < out_k; i += 128) {
     uint32_t id = 0;
     float dist = __uint_as_float(0x7FC00000u);
@@ -619,7 +659,7 @@ rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db
 __global__ void __launch_bounds__(128)
 rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ db, uint32_t d, const uint64_t* __restrict__ buf,
                    const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t kprime, uint32_t k, uint32_t out_k,
-                   uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int np2) {
+                   uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int np2, SafetyArgs sa) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
   float* sq = reinterpret_cast<float*>(ka + np2);
@@ -658,10 +698,106 @@ rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ db, ui
   __syncthreads();
   block_bitonic_sort(ka, np2);
   const uint32_t kk = min(k, m);
+  check_window(sa, qi, sq, d, m, kprime, kk, src, ka);
   for (uint32_t i = tid; i < out_k; i += 128) {
     uint32_t id = 0;
     float dist = __uint_as_float(0x7FC00000u);
     if (i < kk) { id = (uint32_t)ka[i] + id_base; dist = -ord2f((uint32_t)(ka[i] >> 32)); }
+    out_idx[(size_t)qi * out_k + i] = id;
+    out_dist[(size_t)qi * out_k + i] = dist;
+  }
+}
+
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+// max_i ||x_i||^2 over the database rows (bf16 or f32), as the bits of a non-negative float (atomicMax on u32).
+template <typename T>
+__global__ void max_row_norm_kernel(const T* __restrict__ db, uint32_t n, uint32_t d, uint32_t pitch, uint32_t* out_bits) {
+  const uint32_t row = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  float a = 0.f;
+  if (row < n) {
+    const T* x = db + (size_t)row * pitch;
+    for (uint32_t j = lane; j < d; j += 32) { const float v = to_float(x[j]); a = fmaf(v, v, a); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+  if (lane == 0 && row < n) atomicMax(out_bits, __float_as_uint(a));
+}
+
+// Exact all-rows fallback for the queries whose candidate window could not be proven wide enough even at the largest
+// k' (thousands of near-ties at the k-th score).  One round = rows [row0, row1) against the flagged queries: eight
+// lanes per row evaluate the reference's exact arithmetic, keys below the query's tau go to its candidate buffer; the
+// host compacts (keep k) between rounds and sizes the rounds so that the buffer cannot overflow.
+template <bool kF32>
+__global__ void __launch_bounds__(128)
+exact_round_kernel(const float* __restrict__ q, const void* __restrict__ dbv, uint32_t d, uint32_t dpitch,
+                   const uint32_t* __restrict__ flagged, uint32_t row0, uint32_t row1, uint64_t* __restrict__ buf,
+                   uint32_t* __restrict__ cnt, const uint64_t* __restrict__ tau, uint32_t* __restrict__ ovf, uint32_t cap) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float* sq = reinterpret_cast<float*>(smem);
+  const int tid = threadIdx.x;
+  const uint32_t qi = flagged[blockIdx.y];
+  for (uint32_t i = tid; i < d; i += 128) sq[i] = q[(size_t)qi * d + i];
+  __syncthreads();
+  const uint64_t t = tau[qi];
+  const int l = tid & 7, grp = tid >> 3;
+  const uint32_t per_cta = (row1 - row0 + gridDim.x - 1) / gridDim.x;
+  const uint32_t r_begin = row0 + blockIdx.x * per_cta, r_end = min(row1, r_begin + per_cta);
+  for (uint32_t r0 = r_begin; r0 < r_end; r0 += 16) {
+    const uint32_t row = r0 + grp;
+    const bool valid = row < r_end;
+    float r = 0.f;
+    if (kF32) {
+      // BruteForceSearcher<float>: acc = fnmadd(q[d], x[d], acc) sequentially in d -- one lane walks the row
+      if (valid && l == 0) {
+        const float* x = static_cast<const float*>(dbv) + (size_t)row * d;
+        for (uint32_t j = 0; j < d; ++j) r = __fmaf_rn(-sq[j], __ldg(x + j), r);
+      }
+    } else {
+      const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(dbv) + (size_t)(valid ? row : row0) * dpitch;
+      float acc = 0.f;
+      uint32_t j = 0;
+      for (; j + 8 <= d; j += 8) acc = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), acc);
+      float b = __fadd_rn(__shfl_down_sync(0xFFFFFFFFu, acc, 4, 8), acc);
+      if (j + 4 <= d) { if (l < 4) b = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), b); j += 4; }
+      if (j + 2 <= d) { if (l == 2 || l == 3) b = __fmaf_rn(-sq[j + l - 2], __bfloat162float(x[j + l - 2]), b); j += 2; }
+      const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));
+      r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));
+      if (j < d && l == 0) r = __fmaf_rn(-sq[j], __bfloat162float(x[j]), r);
+    }
+    if (valid && l == 0) {
+      const uint64_t key = make_key(r, row);
+      if (key < t) {
+        const uint32_t pos = atomicAdd(&cnt[qi], 1u);
+        if (pos < cap) buf[(size_t)qi * cap + pos] = key;
+        else ovf[qi] = 1u;
+      }
+    }
+  }
+}
+
+// flagged queries: reset the candidate state; all others: park (cnt = 0, so the compactions skip them)
+__global__ void exact_prepare_kernel(uint32_t nq, const uint32_t* __restrict__ unsafe, uint32_t* cnt, uint64_t* tau,
+                                     uint32_t* ovf, uint32_t* flagged, uint32_t* n_flagged) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq) return;
+  cnt[i] = 0; ovf[i] = 0; tau[i] = kKeyMax;
+  if (unsafe[i]) flagged[atomicAdd(n_flagged, 1u)] = i;
+}
+
+__global__ void exact_emit_kernel(const uint32_t* __restrict__ flagged, const uint64_t* __restrict__ buf,
+                                  const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t k, uint32_t out_k,
+                                  uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+  const uint32_t qi = flagged[blockIdx.x];
+  const uint32_t kk = min(k, cnt[qi]);
+  for (uint32_t i = threadIdx.x; i < out_k; i += blockDim.x) {
+    uint32_t id = 0;
+    float dist = __uint_as_float(0x7FC00000u);
+    if (i < kk) {
+      const uint64_t key = buf[(size_t)qi * cap + i];  // sorted by the last compaction
+      id = (uint32_t)key + id_base; dist = -ord2f((uint32_t)(key >> 32));
+    }
     out_idx[(size_t)qi * out_k + i] = id;
     out_dist[(size_t)qi * out_k + i] = dist;
   }
@@ -813,27 +949,83 @@ cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows
   return launch_gemm<1, bf::kEpiStore>(tmA, tmB, a, s);
 }
 
+cudaError_t bf_max_row_norm(const void* db, bool f32, uint32_t n, uint32_t d, uint32_t pitch, float* out, cudaStream_t s) {
+  uint32_t* bits = nullptr;
+  cudaError_t e = cudaMalloc(&bits, 4);
+  if (e != cudaSuccess) return e;
+  cudaMemsetAsync(bits, 0, 4, s);
+  if (n) {
+    if (f32) bf::max_row_norm_kernel<float><<<(n + 7) / 8, 256, 0, s>>>(static_cast<const float*>(db), n, d, pitch, bits);
+    else bf::max_row_norm_kernel<__nv_bfloat16><<<(n + 7) / 8, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(db), n, d, pitch, bits);
+  }
+  float sq = 0.f;
+  e = cudaMemcpyAsync(&sq, bits, 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(bits);
+  if (e != cudaSuccess) return e;
+  *out = sqrtf(sq) * 1.0001f;
+  return cudaGetLastError();
+}
+
+cudaError_t bf_exact_prepare(uint32_t nq, const uint32_t* unsafe, const ScanWork& w, uint32_t* flagged, uint32_t* n_flagged,
+                             cudaStream_t s) {
+  cudaError_t e = cudaMemsetAsync(n_flagged, 0, 4, s);
+  if (e != cudaSuccess) return e;
+  bf::exact_prepare_kernel<<<(nq + 255) / 256, 256, 0, s>>>(nq, unsafe, w.cnt, w.tau, w.ovf, flagged, n_flagged);
+  return cudaGetLastError();
+}
+
+cudaError_t bf_exact_round(const float* q, const void* db, bool f32, uint32_t d, uint32_t dpitch, const uint32_t* flagged,
+                           uint32_t n_flagged, uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s) {
+  if (!n_flagged || row1 <= row0) return cudaSuccess;
+  const size_t smem = (((size_t)d + 3) & ~(size_t)3) * 4;
+  const uint32_t ctas = std::min<uint32_t>(std::max<uint32_t>(1u, (row1 - row0 + 1023) / 1024), 1024u);
+  dim3 grid(ctas, n_flagged);
+  if (f32) {
+    cudaError_t e = cudaFuncSetAttribute(bf::exact_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bf::exact_round_kernel<true><<<grid, 128, smem, s>>>(q, db, d, dpitch, flagged, row0, row1, w.buf, w.cnt, w.tau, w.ovf, w.cap);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(bf::exact_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bf::exact_round_kernel<false><<<grid, 128, smem, s>>>(q, db, d, dpitch, flagged, row0, row1, w.buf, w.cnt, w.tau, w.ovf, w.cap);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t bf_exact_emit(const uint32_t* flagged, uint32_t n_flagged, const ScanWork& w, uint32_t k, uint32_t out_k,
+                          uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s) {
+  if (!n_flagged) return cudaSuccess;
+  bf::exact_emit_kernel<<<n_flagged, 128, 0, s>>>(flagged, w.buf, w.cnt, w.cap, k, out_k, id_base, out_idx, out_dist);
+  return cudaGetLastError();
+}
+
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
                        uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist,
-                       cudaStream_t s) {
+                       cudaStream_t s, const BfSafety* safety) {
+  bf::SafetyArgs sa{};
+  if (safety) sa = bf::SafetyArgs{safety->eps_rel, safety->max_row_norm, safety->unsafe, safety->n_unsafe};
   int np2 = 2;
   while ((uint32_t)np2 < kprime) np2 <<= 1;
   const size_t smem = (size_t)np2 * 8 + (((size_t)d + 3) & ~(size_t)3) * 4;
   cudaError_t e = cudaFuncSetAttribute(bf::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   bf::rescore_kernel<<<nq, 128, smem, s>>>(q, reinterpret_cast<const __nv_bfloat16*>(db), d, dpitch, w.buf, w.cnt, w.cap,
-                                           kprime, k, out_k, id_base, out_idx, out_dist, np2);
+                                           kprime, k, out_k, id_base, out_idx, out_dist, np2, sa);
   return cudaGetLastError();
 }
 
 cudaError_t bf_rescore_f32(const float* q, const float* db, uint32_t nq, uint32_t d, const ScanWork& w, uint32_t kprime,
-                           uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s) {
+                           uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s,
+                           const BfSafety* safety) {
+  bf::SafetyArgs sa{};
+  if (safety) sa = bf::SafetyArgs{safety->eps_rel, safety->max_row_norm, safety->unsafe, safety->n_unsafe};
   int np2 = 2;
   while ((uint32_t)np2 < kprime) np2 <<= 1;
   const size_t smem = (size_t)np2 * 8 + (((size_t)d + 3) & ~(size_t)3) * 4;
   cudaError_t e = cudaFuncSetAttribute(bf::rescore_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  bf::rescore_f32_kernel<<<nq, 128, smem, s>>>(q, db, d, w.buf, w.cnt, w.cap, kprime, k, out_k, id_base, out_idx, out_dist, np2);
+  bf::rescore_f32_kernel<<<nq, 128, smem, s>>>(q, db, d, w.buf, w.cnt, w.cap, kprime, k, out_k, id_base, out_idx, out_dist, np2, sa);
   return cudaGetLastError();
 }
 

@@ -260,30 +260,34 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
   if (i8) __syncthreads();
   const float qnorm = (i8 && ix.distance != 0) ? s_qnorm : 0.f;
 
-  if (a.part_ids) {
+  if (a.part_ids || a.part_rec) {
     // Sharded mode: emit the raw over-retrieved candidates (before SOAR de-duplication, which is
-    // only exact on the global top list) with their exact distances.
+    // only exact on the global top list) with their exact distances: four arrays, or packed 16-byte records
+    // {tie-break key, id, exact distance}.
+    const bool packed = a.part_ids == nullptr;
     for (uint32_t i = tid; i < a.part_cap; i += kFinThreads) {
       const size_t o = (size_t)q * a.part_cap + i;
+      uint32_t id = kInvalidId;
+      uint64_t tie = kKeyMax;
+      float ah = INFINITY, ex = INFINITY;
       if (i < n) {
         const uint64_t s = src[i];
         const uint32_t gslot = (uint32_t)s;
-        const uint32_t dp = ix.key_by_dp ? gslot : ix.slot_dp[gslot];
-        a.part_ids[o] = dp;
-        a.part_tie[o] = ix.key_by_dp ? s
-                                     : ((s & 0xFFFFFFFF00000000ull) | (ix.slot_tie ? ix.slot_tie[gslot] : gslot));
-        a.part_ah[o] = ord2f((uint32_t)(s >> 32));
-        if (!reorder) a.part_exact[o] = ord2f((uint32_t)(s >> 32));
-        else if (i8) a.part_exact[o] = exact_distance_i8(ix, sqp, qnorm, dp);
-        else if (ix.d < 8) a.part_exact[o] = exact_distance(ix, sq, dp);
+        id = ix.key_by_dp ? gslot : ix.slot_dp[gslot];
+        tie = ix.key_by_dp ? s : ((s & 0xFFFFFFFF00000000ull) | (ix.slot_tie ? ix.slot_tie[gslot] : gslot));
+        ah = ord2f((uint32_t)(s >> 32));
+        if (!reorder) ex = ah;
+        else if (i8) ex = exact_distance_i8(ix, sqp, qnorm, id);
+        else if (ix.d < 8) ex = exact_distance(ix, sq, id);
+      }
+      if (packed) {
+        a.part_rec[o] = make_uint4((uint32_t)tie, (uint32_t)(tie >> 32), id, __float_as_uint(ex));
       } else {
-        a.part_ids[o] = kInvalidId;
-        a.part_tie[o] = kKeyMax;
-        a.part_ah[o] = INFINITY;
-        a.part_exact[o] = INFINITY;
+        a.part_ids[o] = id; a.part_tie[o] = tie; a.part_ah[o] = ah; a.part_exact[o] = ex;
       }
     }
     if (reorder && ix.d >= 8 && !i8) {
+      if (packed) __syncthreads();  // the exact distance is patched into the records written above
       const int l = tid & 7, grp = tid >> 3;
       for (uint32_t c0 = 0; c0 < n; c0 += kFinThreads / 8) {
         const uint32_t c = c0 + grp;
@@ -291,7 +295,10 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
         const uint32_t gslot = (uint32_t)src[valid ? c : 0];
         const uint32_t dp = ix.key_by_dp ? gslot : ix.slot_dp[gslot];
         const float dist = ix.dataset ? exact_distance_lanes8(ix, sq, dp, l) : exact_distance_lanes8_bf16(ix, sq, dp, l);
-        if (valid && l == 0) a.part_exact[(size_t)q * a.part_cap + c] = dist;
+        if (valid && l == 0) {
+          if (packed) reinterpret_cast<float*>(a.part_rec + (size_t)q * a.part_cap + c)[3] = dist;
+          else a.part_exact[(size_t)q * a.part_cap + c] = dist;
+        }
       }
     }
     return;
@@ -374,13 +381,20 @@ cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const Finaliz
   return cudaGetLastError();
 }
 
-// Merge `world` all-gathered partial lists ([world][nq][n_cand]): global top-nover by the
-// (AH score, unsharded slot) key, SOAR de-duplication, top-npre by (score, id), then top-k by
-// (exact distance, id).  Reproduces the single-GPU result exactly.
+// Merge `world` partial lists of one query: global top-nover by the (AH score, unsharded slot) key, SOAR
+// de-duplication, top-npre by (score, id), then top-k by (exact distance, id).  Reproduces the single-GPU result
+// exactly.  Two record sources: the four all-gathered arrays [world][nq][n_cand] (kPacked =
+// false, every rank merges every query) or packed records [world][nq_slice][n_cand] of the queries this rank owns.
+struct MergeSrc {
+  const uint32_t* ids; const uint64_t* tie; const float* exact;  // arrays
+  const uint4* rec;                                              // packed
+  uint32_t nq_stride;                                            // queries per rank block
+  int n_cand;
+};
+template <bool kPacked>
 __global__ void __launch_bounds__(kFinThreads)
-merge_partials_kernel(int distance, int disjoint, uint32_t nq, int world, int n_cand,
-                      const uint32_t* __restrict__ ids, const uint64_t* __restrict__ tie,
-                      const float* __restrict__ exact, uint32_t nover, uint32_t npre, uint32_t k,
+merge_partials_kernel(int distance, int disjoint, MergeSrc src, int world,
+                      uint32_t nover, uint32_t npre, uint32_t k,
                       uint32_t* out_idx, float* out_dist, uint32_t out_k, int np2) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* ka = reinterpret_cast<uint64_t*>(smem);        // [np2]
@@ -390,8 +404,15 @@ merge_partials_kernel(int distance, int disjoint, uint32_t nq, int world, int n_
   __shared__ uint32_t s_removed, s_valid;
   const int tid = threadIdx.x;
   const uint32_t q = blockIdx.x;
+  const int n_cand = src.n_cand;
   const int total = world * n_cand;
-  auto rec = [&](int i) { return ((size_t)(i / n_cand) * nq + q) * n_cand + (i % n_cand); };
+  auto rec = [&](int i) { return ((size_t)(i / n_cand) * src.nq_stride + q) * n_cand + (i % n_cand); };
+  auto rec_id = [&](size_t o) -> uint32_t { return kPacked ? src.rec[o].z : src.ids[o]; };
+  auto rec_tie = [&](size_t o) -> uint64_t {
+    if (kPacked) { const uint4 r = src.rec[o]; return ((uint64_t)r.y << 32) | r.x; }
+    return src.tie[o];
+  };
+  auto rec_exact = [&](size_t o) -> float { return kPacked ? __uint_as_float(src.rec[o].w) : src.exact[o]; };
   if (tid == 0) { s_removed = 0; s_valid = 0; }
   __syncthreads();
   uint32_t nvalid = 0;
@@ -399,7 +420,7 @@ merge_partials_kernel(int distance, int disjoint, uint32_t nq, int world, int n_
     uint64_t key = kKeyMax;
     if (i < total) {
       const size_t o = rec(i);
-      if (ids[o] != kInvalidId) { key = tie[o]; ++nvalid; }
+      if (rec_id(o) != kInvalidId) { key = rec_tie(o); ++nvalid; }
     }
     ka[i] = key;
     pa[i] = (uint32_t)i;
@@ -412,7 +433,7 @@ merge_partials_kernel(int distance, int disjoint, uint32_t nq, int world, int n_
   if (disjoint) {
     for (int i = tid; i < np2; i += kFinThreads) {
       uint64_t key = kKeyMax;
-      if ((uint32_t)i < n) key = (ka[i] & 0xFFFFFFFF00000000ull) | ids[rec((int)pa[i])];
+      if ((uint32_t)i < n) key = (ka[i] & 0xFFFFFFFF00000000ull) | rec_id(rec((int)pa[i]));
       kb[i] = key;
       pb[i] = pa[i];
     }
@@ -424,7 +445,7 @@ merge_partials_kernel(int distance, int disjoint, uint32_t nq, int world, int n_
     for (int i = tid; i < np2; i += kFinThreads) {
       uint64_t key = kKeyMax;
       uint32_t p = pa[i];
-      if ((uint32_t)i < n) key = ((uint64_t)ids[rec((int)p)] << 32) | (ka[i] >> 32);
+      if ((uint32_t)i < n) key = ((uint64_t)rec_id(rec((int)p)) << 32) | (ka[i] >> 32);
       kb[i] = key;
       pb[i] = p;
     }
@@ -439,7 +460,7 @@ merge_partials_kernel(int distance, int disjoint, uint32_t nq, int world, int n_
   }
   for (int i = tid; i < np2; i += kFinThreads) {
     uint64_t key = kKeyMax;
-    if ((uint32_t)i < m) key = make_key(exact[rec((int)pb[i])], (uint32_t)kb[i]);
+    if ((uint32_t)i < m) key = make_key(rec_exact(rec((int)pb[i])), (uint32_t)kb[i]);
     ka[i] = key;
   }
   __syncthreads();
@@ -462,10 +483,26 @@ cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, in
   int np2 = 2;
   while (np2 < world * n_cand) np2 <<= 1;
   const size_t smem = (size_t)np2 * 24;
-  cudaError_t e = cudaFuncSetAttribute(merge_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(merge_partials_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  merge_partials_kernel<<<nq, kFinThreads, smem, s>>>(ix.distance, ix.disjoint, nq, world, n_cand, ids, tie, exact,
-                                                      nover, npre, k, out_idx, out_dist, out_k, np2);
+  MergeSrc src{ids, tie, exact, nullptr, nq, n_cand};
+  merge_partials_kernel<false><<<nq, kFinThreads, smem, s>>>(ix.distance, ix.disjoint, src, world,
+                                                             nover, npre, k, out_idx, out_dist, out_k, np2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_merge_records(const DevIndex& ix, uint32_t nq_valid, uint32_t nq_slice, int world, int n_cand,
+                                 const uint4* rec, uint32_t nover, uint32_t npre, uint32_t k, uint32_t* out_idx,
+                                 float* out_dist, uint32_t out_k, cudaStream_t s) {
+  if (nq_valid == 0) return cudaSuccess;
+  int np2 = 2;
+  while (np2 < world * n_cand) np2 <<= 1;
+  const size_t smem = (size_t)np2 * 24;
+  cudaError_t e = cudaFuncSetAttribute(merge_partials_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  MergeSrc src{nullptr, nullptr, nullptr, rec, nq_slice, n_cand};
+  merge_partials_kernel<true><<<nq_valid, kFinThreads, smem, s>>>(ix.distance, ix.disjoint, src, world,
+                                                                  nover, npre, k, out_idx, out_dist, out_k, np2);
   return cudaGetLastError();
 }
 
@@ -476,7 +513,7 @@ cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, in
 __global__ void __launch_bounds__(kFinThreads)
 merge_topk_kernel(int distance, uint32_t nq, int world, int k_in, const uint32_t* __restrict__ ids,
                   const float* __restrict__ dists, uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k,
-                  int np2) {
+                  int np2, int dedup_ids) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
   const int tid = threadIdx.x;
@@ -494,6 +531,19 @@ merge_topk_kernel(int distance, uint32_t nq, int world, int k_in, const uint32_t
   }
   __syncthreads();
   block_bitonic_sort(ka, np2);
+  if (dedup_ids) {
+    // light sharded protocol: the two SOAR copies of a datapoint may reach the top-k of two ranks; both carry the
+    // same exact distance, so they are neighbours after the sort -- drop the second and sort again
+    bool any = false;
+    for (int i0 = 0; i0 < np2; i0 += kFinThreads) {
+      const int i = i0 + tid;
+      const bool dup = i > 0 && i < np2 && ka[i] != kKeyMax && ka[i] == ka[i - 1];
+      __syncthreads();
+      if (dup) { ka[i] = kKeyMax; any = true; }
+      __syncthreads();
+    }
+    if (__syncthreads_or(any)) block_bitonic_sort(ka, np2);
+  }
   for (uint32_t i = tid; i < out_k; i += kFinThreads) {
     uint32_t id = 0;
     float dist = __uint_as_float(0x7FC00000u);
@@ -504,13 +554,15 @@ merge_topk_kernel(int distance, uint32_t nq, int world, int k_in, const uint32_t
 }
 
 cudaError_t launch_merge_topk(int distance, uint32_t nq, int world, int k_in, const uint32_t* ids, const float* dists,
-                              uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k, cudaStream_t s) {
+                              uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k, cudaStream_t s,
+                              bool dedup_ids) {
   int np2 = 2;
   while (np2 < world * k_in) np2 <<= 1;
   const size_t smem = (size_t)np2 * 8;
   cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  merge_topk_kernel<<<nq, kFinThreads, smem, s>>>(distance, nq, world, k_in, ids, dists, k, out_idx, out_dist, out_k, np2);
+  merge_topk_kernel<<<nq, kFinThreads, smem, s>>>(distance, nq, world, k_in, ids, dists, k, out_idx, out_dist, out_k, np2,
+                                                  dedup_ids ? 1 : 0);
   return cudaGetLastError();
 }
 

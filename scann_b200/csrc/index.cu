@@ -18,59 +18,11 @@
 #include <string>
 #include <vector>
 
-#include "../../include/scann_b200.h"
-#include "kernels.h"
+#include "index_internal.h"
 
 namespace {
 
 thread_local std::string g_err;
-
-int fail(int code, const char* fmt, ...) {
-  char buf[1024];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof buf, fmt, ap);
-  va_end(ap);
-  g_err = buf;
-  return code;
-}
-
-#define CU(expr)                                                                              \
-  do {                                                                                        \
-    cudaError_t _e = (expr);                                                                  \
-    if (_e != cudaSuccess)                                                                    \
-      return fail(SCANN_B200_INTERNAL, "CUDA error %s at %s:%d: %s", cudaGetErrorName(_e),    \
-                  __FILE__, __LINE__, cudaGetErrorString(_e));                                \
-  } while (0)
-
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t ensure(size_t n) {
-    if (n <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; bytes = 0;
-    cudaError_t e = cudaMalloc(&p, n);
-    if (e == cudaSuccess) bytes = n;
-    return e;
-  }
-  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-struct PinnedBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  ~PinnedBuf() { if (p) cudaFreeHost(p); }
-  cudaError_t ensure(size_t n) {
-    if (n <= bytes) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; bytes = 0;
-    cudaError_t e = cudaMallocHost(&p, n);
-    if (e == cudaSuccess) bytes = n;
-    return e;
-  }
-  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
-};
 
 size_t word_pos(int W, int j, int m) {
   const int N4 = W / 4, R = W % 4;
@@ -80,42 +32,24 @@ size_t word_pos(int W, int j, int m) {
   return (size_t)N4 * 128 + (R >= 2 ? 64 : 0) + m;
 }
 
-enum { EV_START, EV_TOK, EV_LUT, EV_PILOT, EV_WORK, EV_SCAN, EV_COMPACT, EV_FIN, EV_COUNT,
-       EV2_WORK = EV_COUNT, EV2_SCAN, EV2_COMPACT, EV_ALL };
-
 }  // namespace
+
+namespace sbi {
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+}  // namespace sbi
+using namespace sbi;
 
 namespace sb {
 void set_last_error(const char* msg) { g_err = msg ? msg : ""; }  // used by assets.cc
 }  // namespace sb
-
-struct scann_b200_index {
-  sb::DevIndex dev{};
-  scann_b200_index_desc desc{};
-  int device = 0;
-  int sm_count = 148;
-  cudaStream_t stream = nullptr;
-  std::mutex mu;
-  std::vector<uint32_t> h_leaf_size;
-  // persistent device arrays
-  DevBuf i8_inv, i8_norm, tok_cmax, pair_pos;
-  DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
-      codes, slot_dp, slot_tie, dataset, dp_row, tok_b;
-  // workspace
-  DevBuf tok_a, q, dist, leaves, bias, lut, mult, inv, pilot_end, buf, cnt, tau, ovf, leaf_cnt, leaf_eoff,
-      leaf_cur, item_off, entry_q, entry_bias, counters, stats, out_idx, out_dist;
-  PinnedBuf h_q, h_idx, h_dist, h_counters;
-  cudaEvent_t ev[EV_ALL] = {};
-  scann_b200_stats last{};
-  uint32_t max_chunk = 16384;
-  // brute-force (bf16) searcher: database rows as bf16 with a 16-byte aligned pitch
-  bool brute = false;
-  bool bf_f32 = false;  // float brute force: f32 rows in `dataset`, concatenated hi/lo bf16 operand in `bf_db`
-  uint32_t bf_dpitch = 0;
-  uint32_t bf_row0 = 0;  // first database row of this shard (row-sharded brute force)
-  uint32_t avg_leaf_slots = 0;  // mean padded slots per leaf (scan phase heuristic)
-  DevBuf bf_db, bf_a;
-};
 
 namespace {
 
@@ -151,6 +85,7 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
       CU(sb::build_tokenize_operand(ix->dataset.as<float>(), nloc, D, 2, ix->bf_db.p, 0));
       CU(cudaStreamSynchronize(0));
       vb.dataset = ix->dataset.as<float>();
+      CU(sb::bf_max_row_norm(ix->dataset.p, true, nloc, D, D, &ix->bf_max_row_norm, 0));
       return 0;
     }
     ix->bf_dpitch = (D + 7) / 8 * 8;
@@ -158,6 +93,7 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     CU(cudaMemset(ix->bf_db.p, 0, (size_t)std::max<uint32_t>(nloc, 1) * ix->bf_dpitch * 2));
     if (nloc) CU(cudaMemcpy2D(ix->bf_db.p, (size_t)ix->bf_dpitch * 2, d->bf16_dataset + (size_t)row0 * D, (size_t)D * 2,
                               (size_t)D * 2, nloc, cudaMemcpyHostToDevice));
+    CU(sb::bf_max_row_norm(ix->bf_db.p, false, nloc, D, ix->bf_dpitch, &ix->bf_max_row_norm, 0));
     return 0;
   }
   if (!L || !B) return fail(SCANN_B200_UNIMPLEMENTED, "only tree-AH and bf16 brute-force indexes are implemented (n_leaves=%u, n_blocks=%u)", L, B);
@@ -167,6 +103,14 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   if (d->soar && !d->soar_codes) return fail(SCANN_B200_INVALID_ARGUMENT, "SOAR index without soar_codes");
   const int world = d->shard_world > 0 ? d->shard_world : 1, rank = d->shard_rank;
   if (rank < 0 || rank >= world) return fail(SCANN_B200_INVALID_ARGUMENT, "bad shard rank %d/%d", rank, world);
+  if (d->shard_mode != SCANN_B200_SHARD_BY_ID && d->shard_mode != SCANN_B200_SHARD_BY_LEAF)
+    return fail(SCANN_B200_INVALID_ARGUMENT, "unknown shard_mode %d", d->shard_mode);
+  const bool by_leaf = world > 1 && d->shard_mode == SCANN_B200_SHARD_BY_LEAF;
+  ix->shard_rank = rank; ix->shard_world = world; ix->shard_mode = d->shard_mode;
+  // which (datapoint, leaf) pairs this rank stores: a residue class of the ids inside every leaf, or whole leaves
+  auto mine = [&](uint32_t i, int32_t t) -> bool {
+    return by_leaf ? ((uint32_t)t % (uint32_t)world == (uint32_t)rank) : (i % (uint32_t)world == (uint32_t)rank);
+  };
   sb::DevIndex& v = ix->dev;
   v.distance = d->distance; v.n = N; v.d = D; v.L = L; v.B = B; v.W = (B + 7) / 8; v.dpb = d->dims_per_block;
   const int W = (int)v.W;
@@ -180,7 +124,7 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     if (t < 0) continue;
     if ((uint32_t)t >= L) return fail(SCANN_B200_INVALID_ARGUMENT, "token %d out of range [0,%u)", t, L);
     lsize_full[t]++;
-    if ((j / mult) % world != (size_t)rank) continue;
+    if (!mine((uint32_t)(j / mult), t)) continue;
     lsize[t]++;
   }
   // unsharded group offsets: the tie-break half of a candidate key must be the slot the
@@ -197,7 +141,11 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     }
   }
   const size_t ngroups = goff[L];
-  ix->avg_leaf_slots = (uint32_t)(ngroups * 32 / std::max<uint32_t>(L, 1));
+  {
+    uint32_t nonempty = 0;  // a leaf-sharded rank holds L / world leaves; the rest are empty here
+    for (uint32_t l = 0; l < L; ++l) nonempty += lsize[l] ? 1u : 0u;
+    ix->avg_leaf_slots = (uint32_t)(ngroups * 32 / std::max<uint32_t>(by_leaf ? nonempty : L, 1));
+  }
   if (ngroups * 32 > 0xFFFFFFF0ull) return fail(SCANN_B200_UNIMPLEMENTED, "more than 2^32 slots");
   std::vector<uint32_t> slot_dp(ngroups * 32, 0xFFFFFFFFu);
   std::vector<uint32_t> slot_tie(world > 1 ? ngroups * 32 : 0, 0xFFFFFFFFu);
@@ -211,7 +159,7 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
       const uint32_t i = (uint32_t)(j / mult);
       if (d->soar && (j & 1) && d->tokens[j - 1] >= 0) disjoint = 0;
       const uint32_t s_full = cur_full[t]++;
-      if (i % world != (uint32_t)rank) continue;
+      if (!mine(i, t)) continue;
       const uint32_t s = cur[t]++;
       const size_t g = goff[t] + s / 32;
       const int m = (int)(s % 32);
@@ -247,7 +195,7 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
       return fail(SCANN_B200_INVALID_ARGUMENT, "block %u has %d dims (stride %u)", b, bdims[b], d->dims_per_block);
     boff[b + 1] = boff[b] + (uint32_t)bdims[b];
   }
-  if (boff[B] > D) return fail(SCANN_B200_INVALID_ARGUMENT, "AH blocks cover %u dims > dimensionality %u", boff[B], D);
+  if (boff[B] != D) return fail(SCANN_B200_INVALID_ARGUMENT, "AH blocks cover %u dims, dimensionality is %u", boff[B], D);
 
 #define UP(buf, ptr, bytes_)                                                        \
   do {                                                                              \
@@ -281,25 +229,57 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   }
   v.dataset = nullptr; v.dp_row = nullptr; v.dataset_bf16 = nullptr;
   v.dataset_i8 = nullptr; v.i8_inv_mult = nullptr; v.i8_dp_norm = nullptr;
+  // Reordering rows of this shard (f32, bf16 or int8): all rows when unsharded; the rows of the rank's residue class
+  // (id sharding: a pitched copy of the strided host rows); or the rows of the datapoints stored in the rank's leaves
+  // (leaf sharding: gathered through a staging buffer).  dp_row maps a datapoint id to its row on this rank.
+  auto upload_rows = [&](const void* src, size_t row_bytes) -> int {
+    const char* base = static_cast<const char*>(src);
+    if (world == 1) {
+      UP(ix->dataset, src, row_bytes * (size_t)N);
+      return 0;
+    }
+    std::vector<uint32_t> rowmap(N, 0xFFFFFFFFu);
+    size_t rows = 0;
+    if (!by_leaf) {
+      for (uint32_t i = rank; i < N; i += world) rowmap[i] = (uint32_t)rows++;
+      CU(ix->dataset.ensure(std::max<size_t>(rows, 1) * row_bytes));
+      if (rows)
+        CU(cudaMemcpy2D(ix->dataset.p, row_bytes, base + (size_t)rank * row_bytes, row_bytes * world, row_bytes, rows,
+                        cudaMemcpyHostToDevice));
+    } else {
+      for (uint32_t i = 0; i < N; ++i) {
+        bool here = false;
+        for (uint32_t c = 0; c < mult && !here; ++c) {
+          const int32_t t = d->tokens[(size_t)i * mult + c];
+          here = t >= 0 && mine(i, t);
+        }
+        if (here) rowmap[i] = (uint32_t)rows++;
+      }
+      CU(ix->dataset.ensure(std::max<size_t>(rows, 1) * row_bytes));
+      const size_t stage_rows = std::max<size_t>(1, (64u << 20) / row_bytes);
+      std::vector<char> stage(stage_rows * row_bytes);
+      size_t filled = 0, done = 0;
+      for (uint32_t i = 0; i < N; ++i) {
+        if (rowmap[i] == 0xFFFFFFFFu) continue;
+        memcpy(stage.data() + filled * row_bytes, base + (size_t)i * row_bytes, row_bytes);
+        if (++filled == stage_rows) {
+          CU(cudaMemcpy(static_cast<char*>(ix->dataset.p) + done * row_bytes, stage.data(), filled * row_bytes, cudaMemcpyHostToDevice));
+          done += filled; filled = 0;
+        }
+      }
+      if (filled) CU(cudaMemcpy(static_cast<char*>(ix->dataset.p) + done * row_bytes, stage.data(), filled * row_bytes, cudaMemcpyHostToDevice));
+    }
+    UP(ix->dp_row, rowmap.data(), sizeof(uint32_t) * (size_t)N);
+    v.dp_row = ix->dp_row.as<uint32_t>();
+    return 0;
+  };
   if (!d->dataset && !d->bf16_dataset && d->int8_dataset) {
     // int8 reordering (exact_reordering { fixed_point { enabled: true } }; int8_dataset.npy + int8_multipliers.npy
     // + dp_norms.npy): a quarter of the reorder gather bytes and device memory of the f32 rows
     if (!d->int8_multipliers) return fail(SCANN_B200_INVALID_ARGUMENT, "int8_dataset needs int8_multipliers");
     if (d->distance == SCANN_B200_SQUARED_L2 && !d->dp_norms)
       return fail(SCANN_B200_INVALID_ARGUMENT, "int8 reordering under squared L2 needs dp_norms");
-    if (world == 1) {
-      UP(ix->dataset, d->int8_dataset, (size_t)N * D);
-    } else {
-      std::vector<uint32_t> rowmap(N, 0xFFFFFFFFu);
-      size_t rows = 0;
-      for (uint32_t i = rank; i < N; i += world) rowmap[i] = (uint32_t)rows++;
-      CU(ix->dataset.ensure(std::max<size_t>(rows, 1) * D));
-      if (rows)
-        CU(cudaMemcpy2D(ix->dataset.p, D, d->int8_dataset + (size_t)rank * D, (size_t)D * world, D, rows,
-                        cudaMemcpyHostToDevice));
-      UP(ix->dp_row, rowmap.data(), sizeof(uint32_t) * N);
-      v.dp_row = ix->dp_row.as<uint32_t>();
-    }
+    if (int rc = upload_rows(d->int8_dataset, (size_t)D)) return rc;
     v.dataset_i8 = ix->dataset.as<int8_t>();
     std::vector<float> inv(D);
     for (uint32_t j = 0; j < D; ++j) inv[j] = 1.0f / d->int8_multipliers[j];  // reordering_helper.cc:407-412
@@ -313,36 +293,11 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   if (!d->dataset && d->bf16_dataset) {
     // bfloat16 reordering (exact_reordering { bfloat16 { enabled: true } }, bfloat16_dataset.npy): half the
     // reorder gather bytes and device memory of the f32 rows
-    if (world == 1) {
-      UP(ix->dataset, d->bf16_dataset, sizeof(uint16_t) * (size_t)N * D);
-    } else {
-      std::vector<uint32_t> rowmap(N, 0xFFFFFFFFu);
-      size_t rows = 0;
-      for (uint32_t i = rank; i < N; i += world) rowmap[i] = (uint32_t)rows++;
-      CU(ix->dataset.ensure(sizeof(uint16_t) * std::max<size_t>(rows, 1) * D));
-      if (rows)
-        CU(cudaMemcpy2D(ix->dataset.p, sizeof(uint16_t) * D, d->bf16_dataset + (size_t)rank * D,
-                        sizeof(uint16_t) * D * world, sizeof(uint16_t) * D, rows, cudaMemcpyHostToDevice));
-      UP(ix->dp_row, rowmap.data(), sizeof(uint32_t) * N);
-      v.dp_row = ix->dp_row.as<uint32_t>();
-    }
+    if (int rc = upload_rows(d->bf16_dataset, sizeof(uint16_t) * (size_t)D)) return rc;
     v.dataset_bf16 = ix->dataset.as<uint16_t>();
   }
   if (d->dataset) {
-    if (world == 1) {
-      UP(ix->dataset, d->dataset, sizeof(float) * (size_t)N * D);
-    } else {
-      std::vector<uint32_t> rowmap(N, 0xFFFFFFFFu);
-      size_t rows = 0;
-      for (uint32_t i = rank; i < N; i += world) rowmap[i] = (uint32_t)rows++;
-      CU(ix->dataset.ensure(sizeof(float) * std::max<size_t>(rows, 1) * D));
-      // rows of this shard are strided in the host array: copy with a pitched memcpy
-      if (rows)
-        CU(cudaMemcpy2D(ix->dataset.p, sizeof(float) * D, d->dataset + (size_t)rank * D,
-                        sizeof(float) * D * world, sizeof(float) * D, rows, cudaMemcpyHostToDevice));
-      UP(ix->dp_row, rowmap.data(), sizeof(uint32_t) * N);
-      v.dp_row = ix->dp_row.as<uint32_t>();
-    }
+    if (int rc = upload_rows(d->dataset, sizeof(float) * (size_t)D)) return rc;
     v.dataset = ix->dataset.as<float>();
   }
 #undef UP
@@ -376,7 +331,9 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   return 0;
 }
 
-struct Params { uint32_t k, npre, nover, P; };
+}  // namespace
+
+namespace sbi {
 
 int resolve(const scann_b200_index* ix, int final_nn, int pre_nn, int leaves, Params* p) {
   // scann_ops/cc/scann.cc:406-430 + SetUnspecifiedParametersToDefaults
@@ -450,18 +407,9 @@ int ensure_workspace(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_
   return 0;
 }
 
-struct PartialOut { uint32_t* ids; uint64_t* tie; float* ah; float* exact; uint32_t cap; };
-
-// One chunk of queries, everything on the device.  d_q [nq][D]; outputs may be null when
-// only partial (sharded) records are wanted.
-int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Params& p,
-                 uint32_t* d_out_idx, float* d_out_dist, uint32_t out_k, const PartialOut* part,
-                 bool stop_after_candidates) {
-  const sb::DevIndex& v = ix->dev;
-  cudaStream_t s = ix->stream;
-  const uint32_t cap = pick_cap(p.nover);
-  if (int rc = ensure_workspace(ix, nq, p, out_k ? out_k : 1, cap)) return rc;
-  sb::ScanWork w{};
+void fill_scan_work(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_t cap, sb::ScanWork* wp) {
+  sb::ScanWork& w = *wp;
+  w = sb::ScanWork{};
   w.leaves = ix->leaves.as<int32_t>(); w.bias = ix->bias.as<float>(); w.lut = ix->lut.as<uint8_t>();
   w.mult = ix->mult.as<float>(); w.inv_mult = ix->inv.as<float>(); w.pilot_end = ix->pilot_end.as<int32_t>();
   w.buf = ix->buf.as<uint64_t>(); w.cnt = ix->cnt.as<uint32_t>(); w.tau = ix->tau.as<uint64_t>();
@@ -483,6 +431,30 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
     if (f > 0) w.pilot_target = (uint32_t)f * p.nover;
     w.pilot_partial = strchr(e, 'p') ? 1u : 0u;
   }
+  // pilot buffer: the default (1024 keys or 2 N' + 128) selects every ~900 buffered keys, which also tightens the
+  // pilot's own threshold early; buffering a whole large leaf and selecting once was measured and rejected
+  // (20M x 96: pilot 0.72 -> 1.47 ms).  SCANN_B200_PILOT_CAP overrides (tests).
+  w.pilot_cap = 0;
+  if (const char* e = getenv("SCANN_B200_PILOT_CAP")) w.pilot_cap = (uint32_t)atoi(e);
+}
+
+}  // namespace sbi
+
+namespace {
+
+struct PartialOut { uint32_t* ids; uint64_t* tie; float* ah; float* exact; uint32_t cap; };
+
+// One chunk of queries, everything on the device.  d_q [nq][D]; outputs may be null when
+// only partial (sharded) records are wanted.
+int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Params& p,
+                 uint32_t* d_out_idx, float* d_out_dist, uint32_t out_k, const PartialOut* part,
+                 bool stop_after_candidates) {
+  const sb::DevIndex& v = ix->dev;
+  cudaStream_t s = ix->stream;
+  const uint32_t cap = pick_cap(p.nover);
+  if (int rc = ensure_workspace(ix, nq, p, out_k ? out_k : 1, cap)) return rc;
+  sb::ScanWork w{};
+  fill_scan_work(ix, nq, p, cap, &w);
   int launches = 0;
   uint32_t scan_launches = 0, retries = 0;
 
@@ -494,11 +466,6 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaEventRecord(ix->ev[EV_TOK], s));
   // LUT build: fused into the pilot kernel when the raw table fits its candidate buffer (every BASELINE.json
   // configuration; SCANN_B200_FUSE_LUT=0 keeps the separate lut_kernel)
-  // pilot buffer: the default (1024 keys or 2 N' + 128) selects every ~900 buffered keys, which also tightens the
-  // pilot's own threshold early; buffering a whole large leaf and selecting once was measured and rejected
-  // (20M x 96: pilot 0.72 -> 1.47 ms).  SCANN_B200_PILOT_CAP overrides (tests).
-  w.pilot_cap = 0;
-  if (const char* e = getenv("SCANN_B200_PILOT_CAP")) w.pilot_cap = (uint32_t)atoi(e);
   bool fuse_lut = sb::pilot_can_build_lut(v, w);
   if (const char* e = getenv("SCANN_B200_FUSE_LUT")) fuse_lut = fuse_lut && e[0] != '0';
   w.q_for_lut = fuse_lut ? d_q : nullptr;
@@ -611,31 +578,36 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
 // Brute force (bf16): geometric rounds of [tcgen05 GEMM + threshold filter] -> compaction, then an
 // exact re-scoring of the k' best.  Mirrors Bfloat16BruteForceSearcher::FindNeighborsImpl
 // (brute_force/bfloat16_brute_force.cc:101-152) for a whole batch of queries.
+//
+// The result is the exact top-k by (exact distance, id) on every input:
+//  * the pre-filter keeps the k' = 2k + 64 smallest approximate keys; the re-scoring kernel proves per query that the
+//    window was wide enough (check_window, bruteforce.cu) and the batch is re-run with a 4x wider window while any query
+//    fails the proof; at k' = 8192 the remaining queries (thousands of near-ties at the k-th score) are finished by the
+//    exact all-rows kernel;
+//  * the geometric rounds assume rows arrive in no particular order; on an ordered database (rows sorted by score for
+//    some query) a round can push more keys than a candidate buffer holds.  The overflow is detected and the batch is
+//    re-run with rounds of at most cap - k' rows, which cannot overflow by construction.
 int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_t k, uint32_t* d_out_idx,
                     float* d_out_dist, uint32_t out_k) {
   const sb::DevIndex& v = ix->dev;
   cudaStream_t s = ix->stream;
-  const uint32_t kprime = 2 * k + 64;
-  if (kprime > 8192) return fail(SCANN_B200_UNIMPLEMENTED, "brute force with k=%u > 4064 is not supported", k);
-  const uint32_t cap = pick_cap(kprime);
+  if (2 * k + 64 > 8192) return fail(SCANN_B200_UNIMPLEMENTED, "brute force with k=%u > 4064 is not supported", k);
   CU(ix->bf_a.ensure(ix->bf_f32 ? (size_t)sb::bf_query_rows_pad(nq) * ix->bf_dpitch * 2 + 256 * (size_t)ix->bf_dpitch * 2
                                 : sb::bf_query_operand_bytes(nq, ix->bf_dpitch)));
-  CU(ix->buf.ensure(sizeof(uint64_t) * (size_t)nq * cap));
   CU(ix->cnt.ensure(sizeof(uint32_t) * nq));
   CU(ix->tau.ensure(sizeof(uint64_t) * nq));
   CU(ix->ovf.ensure(sizeof(uint32_t) * nq));
   CU(ix->entry_q.ensure(sizeof(uint32_t) * (size_t)nq));
+  CU(ix->bf_flags.ensure(sizeof(uint32_t) * (2 * (size_t)nq + 4)));  // [nq] unsafe flags, [nq] flagged list, counters
   CU(ix->counters.ensure(sizeof(uint32_t) * 8));
   CU(ix->stats.ensure(sizeof(unsigned long long) * 4));
   CU(ix->h_counters.ensure(64));
-  sb::ScanWork w{};
-  w.buf = ix->buf.as<uint64_t>(); w.cnt = ix->cnt.as<uint32_t>(); w.tau = ix->tau.as<uint64_t>();
-  w.ovf = ix->ovf.as<uint32_t>(); w.entry_q = ix->entry_q.as<uint32_t>();
-  w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
-  w.nq = nq; w.cap = cap; w.nover = kprime;
-  uint32_t launches = 0, gemm_launches = 0;
-  CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
-  CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
+  uint32_t* d_unsafe = ix->bf_flags.as<uint32_t>();
+  uint32_t* d_flagged = d_unsafe + nq;
+  uint32_t* d_nflag = d_flagged + nq;   // [0] queries that failed the window proof, [1] length of the flagged list
+  uint32_t* hc = ix->h_counters.as<uint32_t>();
+  uint32_t launches = 0, gemm_launches = 0, widenings = 0, exact_fallbacks = 0;
+  const void* db = ix->bf_db.p;
   CU(cudaEventRecord(ix->ev[EV_START], s));
   if (ix->bf_f32) {
     // the GEMM walks bf_query_rows_pad(nq) rows; the split kernel writes ceil(nq / 128) * 128 of them
@@ -645,51 +617,108 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
     CU(sb::build_tokenize_operand(d_q, nq, v.d, 1, ix->bf_a.p, s));
   }
   else CU(sb::bf_split_queries(d_q, nq, v.d, ix->bf_dpitch, ix->bf_a.p, s));
-  CU(sb::bf_init_state(nq, w.cnt, w.tau, w.ovf, s));
-  launches += 2;
-  CU(cudaEventRecord(ix->ev[EV_TOK], s));
-  // rounds: the first one must hold >= k' rows (everything passes an infinite threshold) and fit
-  // the candidate buffers; afterwards the inflow per round is ~ k' * growth
-  // (every row seen so far has a 1-in-rows chance per kept slot, so a round over g x the rows seen
-  // pushes ~ g * k' keys).  Rounds are sized so that k' * (1 + g) stays within the 1024 keys the
-  // one-CTA-per-query compaction sorts in shared memory.
-  uint32_t row0 = 0;
-  uint32_t chunk = std::max<uint32_t>(1024, (kprime + 255) / 256 * 256);
-  chunk = std::min(chunk, cap / 2);
-  const uint32_t growth = 3 * kprime <= 1000 ? 2 : (2 * kprime <= 1000 ? 1 : 2);
-  while (row0 < v.n) {
-    const uint32_t row1 = (uint64_t)row0 + chunk >= v.n ? v.n : row0 + chunk;
-    CU(sb::bf_gemm_round(ix->bf_a.p, ix->bf_db.p, nq, v.n, ix->bf_dpitch, row0, row1, w, ix->bf_f32 ? 1 : 2, s));
-    int ncl = 0;
-    CU(sb::launch_compact(v, w, false, s, &ncl));
-    launches += 1 + (uint32_t)ncl;
-    gemm_launches += 1;
-    row0 = row1;
-    chunk = (uint32_t)std::min<uint64_t>((uint64_t)row1 * growth, 0x40000000ull);
-  }
-  CU(cudaEventRecord(ix->ev[EV_SCAN], s));
-  uint32_t* hc = ix->h_counters.as<uint32_t>();
-  CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
-  if (hc[2] != 0) return fail(SCANN_B200_INTERNAL, "brute force: candidate buffer overflow (%u queries)", hc[2]);
-  if (ix->bf_f32)
-    CU(sb::bf_rescore_f32(d_q, v.dataset, nq, v.d, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
-  else
-    CU(sb::bf_rescore(d_q, ix->bf_db.p, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
   launches += 1;
-  CU(cudaEventRecord(ix->ev[EV_FIN], s));
-  CU(cudaStreamSynchronize(s));
+  CU(cudaEventRecord(ix->ev[EV_TOK], s));
+  // |approximate - exact| <= eps_rel * ||q|| * max ||x||: K * 2^-21 + 2^-15 with K the accumulated products per score
+  const uint32_t kacc = ix->bf_f32 ? ix->bf_dpitch : 2 * ix->bf_dpitch;
+  const float eps_rel = (float)kacc * 4.76837158e-7f + 3.05175781e-5f;
+  uint32_t kprime = 2 * k + 64;
+  if (const char* e = getenv("SCANN_B200_BF_KPRIME")) {  // tests: start from a narrow window
+    const long t = strtol(e, nullptr, 10);
+    if (t >= (long)k && t <= 8192) kprime = (uint32_t)t;
+  }
+  bool safe_rounds = false;
+  sb::ScanWork w{};
+  for (;;) {
+    const uint32_t cap = pick_cap(kprime);
+    CU(ix->buf.ensure(sizeof(uint64_t) * (size_t)nq * cap));
+    w = sb::ScanWork{};
+    w.buf = ix->buf.as<uint64_t>(); w.cnt = ix->cnt.as<uint32_t>(); w.tau = ix->tau.as<uint64_t>();
+    w.ovf = ix->ovf.as<uint32_t>(); w.entry_q = ix->entry_q.as<uint32_t>();
+    w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
+    w.nq = nq; w.cap = cap; w.nover = kprime;
+    CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
+    CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
+    CU(cudaMemsetAsync(d_nflag, 0, sizeof(uint32_t) * 2, s));
+    CU(sb::bf_init_state(nq, w.cnt, w.tau, w.ovf, s));
+    launches += 1;
+    // rounds: the first one must hold >= k' rows (everything passes an infinite threshold) and fit
+    // the candidate buffers; afterwards the inflow per round is ~ k' * growth
+    // (every row seen so far has a 1-in-rows chance per kept slot, so a round over g x the rows seen
+    // pushes ~ g * k' keys).  Rounds are sized so that k' * (1 + g) stays within the 1024 keys the
+    // one-CTA-per-query compaction sorts in shared memory.  Safe rounds: at most cap - k' rows each.
+    uint32_t row0 = 0;
+    uint32_t chunk = std::max<uint32_t>(1024, (kprime + 255) / 256 * 256);
+    chunk = std::min(chunk, cap / 2);
+    const uint32_t safe_chunk = std::max<uint32_t>(256, (cap - kprime) / 256 * 256);
+    if (safe_rounds) chunk = safe_chunk;
+    const uint32_t growth = 3 * kprime <= 1000 ? 2 : (2 * kprime <= 1000 ? 1 : 2);
+    while (row0 < v.n) {
+      const uint32_t row1 = (uint64_t)row0 + chunk >= v.n ? v.n : row0 + chunk;
+      CU(sb::bf_gemm_round(ix->bf_a.p, db, nq, v.n, ix->bf_dpitch, row0, row1, w, ix->bf_f32 ? 1 : 2, s));
+      int ncl = 0;
+      CU(sb::launch_compact(v, w, false, s, &ncl));
+      launches += 1 + (uint32_t)ncl;
+      gemm_launches += 1;
+      row0 = row1;
+      chunk = safe_rounds ? safe_chunk : (uint32_t)std::min<uint64_t>((uint64_t)row1 * growth, 0x40000000ull);
+    }
+    CU(cudaEventRecord(ix->ev[EV_SCAN], s));
+    // optimistic: the re-scoring is launched before the overflow counter is known (one host round trip)
+    sb::BfSafety safety{eps_rel, ix->bf_max_row_norm, d_unsafe, d_nflag};
+    if (ix->bf_f32)
+      CU(sb::bf_rescore_f32(d_q, v.dataset, nq, v.d, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s, &safety));
+    else
+      CU(sb::bf_rescore(d_q, db, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s, &safety));
+    launches += 1;
+    CU(cudaEventRecord(ix->ev[EV_FIN], s));
+    CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(hc + 8, d_nflag, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (hc[2] != 0) {
+      if (safe_rounds) return fail(SCANN_B200_INTERNAL, "brute force: candidate buffer overflow in safe rounds (%u queries)", hc[2]);
+      safe_rounds = true;
+      ++widenings;
+      continue;
+    }
+    if (hc[8] == 0) break;
+    if (kprime < 8192) {
+      kprime = std::min<uint32_t>(8192, kprime * 4);
+      ++widenings;
+      continue;
+    }
+    // exact all-rows fallback for the flagged queries: keys are exact, keep k
+    exact_fallbacks = hc[8];
+    w.nover = k;
+    CU(sb::bf_exact_prepare(nq, d_unsafe, w, d_flagged, d_nflag + 1, s));
+    const uint32_t rows_per_round = std::max<uint32_t>(256, cap - k);
+    const void* rows = ix->bf_f32 ? static_cast<const void*>(v.dataset) : db;
+    for (uint32_t r0 = 0; r0 < v.n; r0 += rows_per_round) {
+      const uint32_t r1 = (uint32_t)std::min<uint64_t>((uint64_t)r0 + rows_per_round, v.n);
+      CU(sb::bf_exact_round(d_q, rows, ix->bf_f32, v.d, ix->bf_dpitch, d_flagged, exact_fallbacks, r0, r1, w, s));
+      int ncl = 0;
+      CU(sb::launch_compact(v, w, false, s, &ncl));
+      launches += 1 + (uint32_t)ncl;
+    }
+    CU(sb::bf_exact_emit(d_flagged, exact_fallbacks, w, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
+    launches += 2;
+    CU(cudaEventRecord(ix->ev[EV_FIN], s));
+    CU(cudaStreamSynchronize(s));
+    break;
+  }
   float ms_prep = 0, ms_gemm = 0, ms_fin = 0, tot = 0;
   CU(cudaEventElapsedTime(&ms_prep, ix->ev[EV_START], ix->ev[EV_TOK]));
-  CU(cudaEventElapsedTime(&ms_gemm, ix->ev[EV_TOK], ix->ev[EV_SCAN]));
   CU(cudaEventElapsedTime(&ms_fin, ix->ev[EV_SCAN], ix->ev[EV_FIN]));
   CU(cudaEventElapsedTime(&tot, ix->ev[EV_START], ix->ev[EV_FIN]));
+  ms_gemm = tot - ms_prep - ms_fin;  // all GEMM rounds, including those of a re-run
   scann_b200_stats& st = ix->last;
   st.kernel_launches += launches;
   st.scan_kernel_count += gemm_launches;
   st.ms_tokenize += ms_prep; st.ms_scan += ms_gemm; st.ms_finalize += ms_fin; st.ms_total += tot;
   st.scan_pairs += (uint64_t)nq * v.n;
   st.scan_bytes_alg += (uint64_t)v.n * ix->bf_dpitch * 2;  // compulsory database bytes of one pass
+  st.bf_widenings += widenings;
+  st.bf_exact_fallbacks += exact_fallbacks;
   return 0;
 }
 
@@ -748,6 +777,7 @@ void scann_b200_index_destroy(scann_b200_index* ix) {
   cudaSetDevice(ix->device);
   if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
   for (int i = 0; i < EV_ALL; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
+  if (ix->comm) comm_destroy(ix->comm);
   delete ix;
 }
 

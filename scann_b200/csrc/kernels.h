@@ -81,6 +81,11 @@ struct ScanWork {
   uint32_t pilot_cap;         // keys the pilot buffers between selections (0 = the default, 1024 or 2 N' + 128)
   uint32_t pilot_target;      // slots the pilot samples per query before it fixes tau (4 N')
   uint32_t pilot_partial;     // 1: the pilot may stop inside a leaf once the target is reached (small leaves)
+  // leaf-sharded search: only the rank that owns a query's nearest leaf (leaf % pilot_world == pilot_rank) samples for
+  // tau, the others leave tau = max and the ranks all-reduce(min) it afterwards.  pilot_world <= 1: every query.
+  uint32_t pilot_world, pilot_rank;
+  uint32_t max_gpt;           // groups per work item of the main scan (0 = kMaxGroupsPerTile)
+  uint32_t* item_leaf;        // [n_items] leaf of each work item (written by the work-list pass)
 };
 
 // ---- query preparation ----
@@ -115,6 +120,9 @@ struct FinalizeArgs {
   float* out_dist;        // [nq][out_k]
   // partial (sharded) outputs, optional
   uint32_t* part_ids; uint64_t* part_tie; float* part_ah; float* part_exact; uint32_t part_cap;
+  // packed partial records {tie-break key u64, id u32, exact distance f32} [nq][part_cap] (sharded.cu); used when
+  // part_ids is NULL
+  uint4* part_rec;
 };
 cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const FinalizeArgs& a, cudaStream_t s);
 cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, int n_cand,
@@ -122,7 +130,13 @@ cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, in
                                   uint32_t nover, uint32_t npre, uint32_t k, uint32_t* out_idx,
                                   float* out_dist, uint32_t out_k, cudaStream_t s);
 cudaError_t launch_merge_topk(int distance, uint32_t nq, int world, int k_in, const uint32_t* ids, const float* dists,
-                              uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k, cudaStream_t s);
+                              uint32_t k, uint32_t* out_idx, float* out_dist, uint32_t out_k, cudaStream_t s,
+                              bool dedup_ids = false);
+// Owner-side merge of the sharded search: rec = [world][nq_slice][n_cand] packed records (each list sorted by key,
+// padded with id 0xFFFFFFFF) of the nq_valid queries this rank owns; writes rows [0, nq_valid) of out_idx / out_dist.
+cudaError_t launch_merge_records(const DevIndex& ix, uint32_t nq_valid, uint32_t nq_slice, int world, int n_cand,
+                                 const uint4* rec, uint32_t nover, uint32_t npre, uint32_t k, uint32_t* out_idx,
+                                 float* out_dist, uint32_t out_k, cudaStream_t s);
 // ---- bf16 brute force (tcgen05 GEMM + fused top-k pre-filter), bruteforce.cu ----
 size_t bf_query_operand_bytes(uint32_t nq, uint32_t dpitch);
 cudaError_t bf_split_queries(const float* q, uint32_t nq, uint32_t d, uint32_t dpitch, void* a_operand, cudaStream_t s);
@@ -132,11 +146,23 @@ cudaError_t bf_init_state(uint32_t nq, uint32_t* cnt, uint64_t* tau, uint32_t* o
 cudaError_t bf_gemm_round(const void* a_operand, const void* db, uint32_t nq, uint32_t n_total, uint32_t dpitch,
                           uint32_t row0, uint32_t row1, const ScanWork& w, int splits, cudaStream_t s);
 uint32_t bf_query_rows_pad(uint32_t nq);
+// window check of the exact re-scoring (bruteforce.cu check_window): flags queries whose k-th exact distance does not
+// clear "largest kept approximate distance - eps"
+struct BfSafety { float eps_rel, max_row_norm; uint32_t* unsafe; uint32_t* n_unsafe; };
 cudaError_t bf_rescore_f32(const float* q, const float* db, uint32_t nq, uint32_t d, const ScanWork& w, uint32_t kprime,
-                           uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s);
+                           uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s,
+                           const BfSafety* safety = nullptr);
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
                        uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist,
-                       cudaStream_t s);
+                       cudaStream_t s, const BfSafety* safety = nullptr);
+cudaError_t bf_max_row_norm(const void* db, bool f32, uint32_t n, uint32_t d, uint32_t pitch, float* out, cudaStream_t s);
+// exact all-rows fallback for flagged queries (see bruteforce.cu)
+cudaError_t bf_exact_prepare(uint32_t nq, const uint32_t* unsafe, const ScanWork& w, uint32_t* flagged, uint32_t* n_flagged,
+                             cudaStream_t s);
+cudaError_t bf_exact_round(const float* q, const void* db, bool f32, uint32_t d, uint32_t dpitch, const uint32_t* flagged,
+                           uint32_t n_flagged, uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s);
+cudaError_t bf_exact_emit(const uint32_t* flagged, uint32_t n_flagged, const ScanWork& w, uint32_t k, uint32_t out_k,
+                          uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s);
 // out[a_row * ld + b_row] = sum_k A[a_row][k] * B[b_row][k]; bf16 operands with row pitch kpitch (multiple of 64),
 // a_rows_pad a multiple of 128 (padding rows readable), fp32 accumulate on tcgen05.
 // cmax (optional): cmax[a_row * ld_c + b_row / 32] = max over that row's 32-column chunk of out (cbias == NULL) or of

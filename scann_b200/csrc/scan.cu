@@ -455,8 +455,11 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
   // Sample whole leaves, nearest first, until at least 4 N slots have been scored: the N-th best of
   // that sample is the pruning threshold of the main scan.  Nothing is published -- the main scan
   // covers every probed leaf, these too (1-2 % more scan work, and no hand-over of candidates).
+  // Leaf-sharded search: only the owner of the query's nearest leaf samples (its own leaves, nearest first).
   uint32_t seen = 0;
-  for (uint32_t r = 0; r < w.P; ++r) {
+  const int leaf0 = w.leaves[(size_t)q * w.P];
+  const bool sampler = w.pilot_world <= 1 || (leaf0 >= 0 && (uint32_t)leaf0 % w.pilot_world == w.pilot_rank);
+  for (uint32_t r = 0; sampler && r < w.P; ++r) {
     const int leaf = w.leaves[(size_t)q * w.P + r];
     if (leaf < 0) break;
     const float bias = ix.key_by_dp ? 0.f : w.bias[(size_t)q * w.P + r];
@@ -922,7 +925,9 @@ __device__ __forceinline__ void compact_one(const ScanWork& w, uint32_t q, int d
   for (uint32_t i = tid; i < keep; i += kScanThreads) w.buf[(size_t)q * w.cap + i] = s[i];
   if (tid == 0) {
     w.cnt[q] = keep;
-    w.tau[q] = (keep >= w.nover) ? s[w.nover - 1] : kKeyMax;
+    // fewer than N keys passed the current tau: it stays (it is an upper bound of the N-th best key that came from
+    // elsewhere -- another rank's pilot in the sharded search; on one GPU it can only be kKeyMax here)
+    if (keep >= w.nover) w.tau[q] = s[w.nover - 1];
     // sticky across the scan phases of a batch; the re-scan (dedup) passes clear it
     if (over || dedup) w.ovf[q] = over ? 1u : 0u;
     if (over) atomicAdd(&w.counters[2], 1u);

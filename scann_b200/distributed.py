@@ -1,6 +1,13 @@
 """Sharded search over the GPUs of one box.
 
-The database shards by datapoint id (`id % world == rank`) inside every leaf; centres, AH
+Two generations live here.  `ShardedIndex` is the one to use: the whole protocol (sliced tokenization, threshold
+all-reduce, scan of the rank's own leaves, all-to-all of 16-byte records to the query's owner, merge, all-gather of
+the k results) runs inside the C++ library on the index's stream, NCCL called from C++ (`csrc/sharded.cu`);
+torch.distributed only carries the 128-byte NCCL id to the ranks.  `ShardedSearcher` below is the round-1 form
+(three torch all-gathers of every rank's candidates, every rank merges every query); it is kept because the tests
+state the merge rule on its records.
+
+Round-1 form: the database shards by datapoint id (`id % world == rank`) inside every leaf; centres, AH
 codebook, tokenization and LUT build are replicated, so no query-side exchange is needed.
 Each rank produces its local over-retrieved pre-reorder candidates with exact distances
 (`scann_b200_search_partial_device`), ONE all-gather exchanges them (records of
@@ -80,6 +87,75 @@ def merge_partials_reference(ids, tie, exact, nover, npre, k, disjoint, dot_prod
     out_i[j] = dp
     out_d[j] = -ex if dot_product else ex
   return out_i, out_d
+
+
+SHARD_BY_ID, SHARD_BY_LEAF = 0, 1
+
+
+class ShardedIndex:
+  """One rank (one process, one GPU) of a database-sharded tree-AH searcher.
+
+  `group` is a torch.distributed process group; it is used ONCE, to broadcast the NCCL unique id that rank 0 gets
+  from the library.  All exchanges of a search are NCCL calls issued by the library itself.
+  """
+
+  def __init__(self, arrays, leaves_to_search, pre_reorder_nn, final_nn, rank, world, device, group=None,
+               shard_mode=SHARD_BY_LEAF):
+    import torch
+    import torch.distributed as dist
+    self.torch = torch
+    self.rank, self.world = rank, world
+    self.dev = torch.device("cuda", device)
+    self.k = final_nn
+    self.index = _lib.NativeIndex(arrays, leaves_to_search, pre_reorder_nn, final_nn, device=device,
+                                  shard_rank=rank, shard_world=world, shard_mode=shard_mode)
+    if world > 1:
+      L = _lib.lib()
+      uid = torch.zeros(128, dtype=torch.uint8)
+      if rank == 0:
+        buf = (C.c_uint8 * 128)()
+        _lib.check(L.scann_b200_comm_unique_id(buf))
+        uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+      backend = dist.get_backend(group)
+      t = uid.to(self.dev) if backend == "nccl" else uid
+      dist.broadcast(t, src=0, group=group)
+      raw = bytes(t.cpu().numpy().tobytes())
+      _lib.check(L.scann_b200_comm_init(self.index._h, rank, world, raw))
+
+  def search_batched_device(self, d_q, d_idx, d_dist, light=False, leaves=-1):
+    """d_q [nq, D] f32 cuda tensor (the same on every rank); d_idx [nq, k] int32, d_dist [nq, k] f32 outputs, filled
+    on every rank.  Returns this rank's stats (CUDA-event times incl. ms_exchange / ms_merge)."""
+    vp = C.c_void_p
+    # the library's stream does not wait for torch's: the caller's tensors must be complete
+    _lib.check(_lib.lib().scann_b200_search_sharded_device(self.index._h, vp(d_q.data_ptr()), d_q.shape[0], -1, -1,
+                                                           leaves, 1 if light else 0, vp(d_idx.data_ptr()),
+                                                           vp(d_dist.data_ptr()), d_idx.shape[1]))
+    return self.index.stats()
+
+  def search_batched(self, q, light=False):
+    t = self.torch
+    d_q = t.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(self.dev)
+    d_idx = t.empty((q.shape[0], self.k), dtype=t.int32, device=self.dev)
+    d_dist = t.empty((q.shape[0], self.k), dtype=t.float32, device=self.dev)
+    t.cuda.synchronize()
+    self.search_batched_device(d_q, d_idx, d_dist, light=light)
+    return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy()
+
+
+def search_sharded_local(shards, q, k, light=False, leaves=-1):
+  """All `world` shards (NativeIndex objects with shard_rank 0..world-1) in this process on one device: the library
+  runs the same protocol with device copies instead of NCCL.  Test vehicle; returns (ids, distances, stats of rank 0)."""
+  import torch
+  dev = torch.device("cuda", shards[0].device)
+  d_q = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(dev)
+  d_idx = torch.empty((q.shape[0], k), dtype=torch.int32, device=dev)
+  d_dist = torch.empty((q.shape[0], k), dtype=torch.float32, device=dev)
+  torch.cuda.synchronize()
+  hs = (C.c_void_p * len(shards))(*[s._h for s in shards])
+  vp = C.c_void_p
+  _lib.check(_lib.lib().scann_b200_search_sharded_local(hs, len(shards), vp(d_q.data_ptr()), q.shape[0], -1, -1, leaves,
+                                                        1 if light else 0, vp(d_idx.data_ptr()), vp(d_dist.data_ptr()), k))
+  return d_idx.cpu().numpy().view(np.uint32), d_dist.cpu().numpy(), [s.stats() for s in shards]
 
 
 class ShardedSearcher:

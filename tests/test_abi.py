@@ -22,18 +22,19 @@ def test_library_exports_every_declared_symbol():
   for n in names:
     assert hasattr(lib, n), f"{n} declared in include/scann_b200.h but not exported"
   assert sorted(_lib.EXPORTS) == names
-  assert lib.scann_b200_abi_version() == 3
+  assert lib.scann_b200_abi_version() == 4
 
 
 def test_struct_layouts_match_header():
   from scann_b200 import _lib
-  # 6 u32/i32, 3 pointers, i32 (+pad), 5 pointers, float + 6 i32 (+pad), 3 pointers (int8 reordering)
-  assert ctypes.sizeof(_lib.IndexDesc) == 24 + 24 + 8 + 40 + 28 + 4 + 24
+  # 6 u32/i32, 3 pointers, i32 (+pad), 5 pointers, float + 6 i32 (+pad), 3 pointers (int8 reordering), shard_mode (+pad)
+  assert ctypes.sizeof(_lib.IndexDesc) == 24 + 24 + 8 + 40 + 28 + 4 + 24 + 8
   # 5 u32 (+pad), 4 pointers, i32, float, double, i32 (+pad)
   assert ctypes.sizeof(_lib.EncodeDesc) == 24 + 32 + 8 + 8 + 8
   # 4 floats, 4 u64, u32 (+pad)
   assert ctypes.sizeof(_lib.EncodeStats) == 16 + 32 + 8
-  assert ctypes.sizeof(_lib.Stats) == 24 + 8 + 32 + 4 + 4 + 16 + 8
+  # ... + ms_exchange, ms_merge, exchange_bytes, bf_widenings, bf_exact_fallbacks
+  assert ctypes.sizeof(_lib.Stats) == 24 + 8 + 32 + 4 + 4 + 16 + 8 + 8 + 8 + 8
 
 
 def test_create_fails_loudly_without_gpu_or_arguments():

@@ -104,3 +104,97 @@ def test_sharded_int8_reordering_equals_unsharded(kw, world):
   i2, d2, _ = run_sharded(case, world)
   np.testing.assert_array_equal(i1, i2)
   np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
+
+
+# ---- the C++ protocol (csrc/sharded.cu): sliced tokenization, threshold all-reduce, owner-side merge -----------------
+
+def _local_world(a, probe, pre, k, world, mode):
+  from scann_b200 import _lib
+  return [_lib.NativeIndex(a, probe, pre, k, device=0, shard_rank=r, shard_world=world, shard_mode=mode)
+          for r in range(world)]
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["by_id", "by_leaf"])
+@pytest.mark.parametrize("kw,world", [(dict(), 2), (dict(), 3), (dict(soar=1.5), 2), (dict(soar=1.5), 4),
+                                      (dict(soar=1.5), 8), (dict(n=3000, leaves=300, probe=40, pre=150), 8),
+                                      (dict(distance="squared_l2", d=64, leaves=50, n=10000), 3)])
+def test_sharded_protocol_equals_unsharded(kw, world, mode):
+  """world shards on one device, exchanges as device copies: ids and distance bits of the unsharded searcher."""
+  from scann_b200 import distributed as sd
+  c = get_case(**kw)
+  i1, d1 = c.native.search_batched(c.q)
+  shards = _local_world(c.arrays, c.probe, c.pre, c.k, world, mode)
+  i2, d2, st = sd.search_sharded_local(shards, c.q, c.k)
+  np.testing.assert_array_equal(i1, i2)
+  np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
+  i0, _ = c.oracle.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i2)
+  assert all(s["exchange_bytes"] > 0 and s["kernel_launches"] >= 8 for s in st)
+  if mode == 1:  # whole leaves are dealt out: the ranks' scan work adds up to the unsharded scan work
+    c.native.search_batched(c.q)
+    assert sum(s["scan_bytes_alg"] for s in st) == c.native.stats()["scan_bytes_alg"]
+  for s in shards:
+    s.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["by_id", "by_leaf"])
+def test_sharded_protocol_ragged_batches_and_overflow(mode, monkeypatch):
+  """nq not divisible by the world size, fewer queries than ranks, forced candidate-buffer overflows, two scan phases."""
+  from scann_b200 import distributed as sd
+  c = get_case(soar=1.5)
+  shards = _local_world(c.arrays, c.probe, c.pre, c.k, 4, mode)
+  for nq in (1, 3, 37):
+    i1, d1 = c.native.search_batched(c.q[:nq])
+    i2, d2, _ = sd.search_sharded_local(shards, c.q[:nq], c.k)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
+  i1, d1 = c.native.search_batched(c.q)
+  monkeypatch.setenv("SCANN_B200_CAND_CAP", "256")
+  monkeypatch.setenv("SCANN_B200_TWO_PHASE", "1")
+  i2, d2, st = sd.search_sharded_local(shards, c.q, c.k)
+  np.testing.assert_array_equal(i1, i2)
+  np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
+  for s in shards:
+    s.close()
+
+
+def test_sharded_protocol_reordering_variants_by_leaf():
+  """Leaf-sharded ranks hold the bf16 / int8 rows of the datapoints stored in their leaves."""
+  import copy
+  from scann_b200 import _lib, index_build, distributed as sd
+  c = get_case(soar=1.5)
+  for kind in ("bf16", "int8"):
+    a = copy.copy(c.arrays)
+    if kind == "bf16":
+      a.bf16_dataset = index_build.bfloat16_quantize(c.db)
+    else:
+      a.int8_dataset, a.int8_multipliers = index_build.int8_quantize(c.db)
+    a.dataset = None
+    full = _lib.NativeIndex(a, c.probe, c.pre, c.k)
+    i1, d1 = full.search_batched(c.q)
+    shards = _local_world(a, c.probe, c.pre, c.k, 3, 1)
+    i2, d2, _ = sd.search_sharded_local(shards, c.q, c.k)
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(d1.view(np.uint32), d2.view(np.uint32))
+    for s in shards:
+      s.close()
+    full.close()
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["by_id", "by_leaf"])
+def test_sharded_light_protocol(mode):
+  """Light protocol (local top-k + one all-gather): not bit-identical by design; every returned neighbour carries its
+  exact distance, rows are sorted, no id repeats, and the result is at least as good as the parity mode's."""
+  from scann_b200 import distributed as sd
+  c = get_case(soar=1.5)
+  shards = _local_world(c.arrays, c.probe, c.pre, c.k, 4, mode)
+  i1, d1 = c.native.search_batched(c.q)
+  i2, d2, _ = sd.search_sharded_local(shards, c.q, c.k, light=True)
+  for r in range(c.q.shape[0]):
+    assert len(set(i2[r].tolist())) == c.k
+    exact = c.db[i2[r]].astype(np.float64) @ c.q[r].astype(np.float64)
+    np.testing.assert_allclose(d2[r], exact, rtol=1e-5, atol=1e-6)
+    assert np.all(np.diff(d2[r]) <= 0)          # dot product: descending similarity
+    assert d2[r][-1] >= d1[r][-1] - 1e-6         # k-th neighbour no worse than the parity result's
+  for s in shards:
+    s.close()
