@@ -1,0 +1,105 @@
+"""ctypes binding of oracle/_ref/libscann_ref.so: pieces of the REFERENCE'S OWN code (its AVX2 LUT16 kernel, the LUT
+fixed-point conversion, the code packing, bfloat16 helpers) compiled from /root/reference by oracle/Makefile.
+
+Test infrastructure: it pins oracle/scann_oracle.c (and, in the -m gpu tests, the CUDA kernels) to reference code
+instead of to restatements.  The library is built in the container that has /root/reference and travels to the GPU box
+as a prebuilt file; `available()` is False where neither exists.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libscann_ref.so")
+_LIB = None
+
+
+def available():
+  return os.path.exists(LIB_PATH)
+
+
+def lib():
+  global _LIB
+  if _LIB is None:
+    L = C.CDLL(LIB_PATH)
+    L.ref_pack_dataset.restype = C.c_uint64
+    L.ref_pack_dataset.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]
+    L.ref_lut16_int16.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int, C.c_void_p]
+    L.ref_lut16_top_float.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                      C.c_int]
+    L.ref_lut_to_fixed_point.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
+    L.ref_bf16_quantize.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    L.ref_bf16_decompress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    _LIB = L
+  return _LIB
+
+
+def _p(a):
+  return a.ctypes.data_as(C.c_void_p)
+
+
+def pack_dataset(codes):
+  """CreatePackedDataset (asymmetric_hashing_impl.cc:690-737): codes [n, B] u8 -> packed bytes."""
+  codes = np.ascontiguousarray(codes, dtype=np.uint8)
+  n, b = codes.shape
+  out = np.zeros(((n + 31) // 32) * b * 16, np.uint8)
+  size = lib().ref_pack_dataset(_p(codes), n, b, _p(out), out.size)
+  assert size == out.size, (size, out.size)
+  return out
+
+
+def _ptr_array(arrs):
+  return (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+
+
+def lut16_int16(packed, n, num_blocks, luts):
+  """LUT16Avx2<len(luts)>::GetInt16Distances: int16 scores [len(luts), 32 * ceil(n / 32)]."""
+  n32 = (n + 31) // 32
+  luts = [np.ascontiguousarray(l, dtype=np.uint8).reshape(-1) for l in luts]
+  outs = [np.zeros(32 * n32, np.int16) for _ in luts]
+  rc = lib().ref_lut16_int16(_p(packed), n32, num_blocks, _ptr_array(luts), len(luts), _ptr_array(outs))
+  assert rc == 0
+  return np.stack(outs)
+
+
+def lut16_top_float(packed, n, num_blocks, luts, biases, mults, epsilon=np.inf, first_dp_index=0, seq_prefetch=False):
+  """LUT16Avx2<len(luts)>::GetTopFloatDistances with a top-N that keeps every push: per query (indices, float scores)
+  of the datapoints whose int16 sum passes the reference's pre-filter `acc < trunc((epsilon - bias) * mult)`."""
+  n32 = (n + 31) // 32
+  nq = len(luts)
+  luts = [np.ascontiguousarray(l, dtype=np.uint8).reshape(-1) for l in luts]
+  idx = [np.zeros(32 * n32, np.uint32) for _ in range(nq)]
+  dist = [np.zeros(32 * n32, np.float32) for _ in range(nq)]
+  cnt = np.zeros(nq, np.uint32)
+  b = np.ascontiguousarray(biases, dtype=np.float32)
+  m = np.ascontiguousarray(mults, dtype=np.float32)
+  rc = lib().ref_lut16_top_float(_p(packed), n32, num_blocks, n, _ptr_array(luts), nq, _p(b), _p(m),
+                                 C.c_float(float(epsilon)), first_dp_index, _ptr_array(idx), _ptr_array(dist), 32 * n32,
+                                 _p(cnt), 1 if seq_prefetch else 0)
+  assert rc == 0, rc
+  return [(idx[j][:cnt[j]].copy(), dist[j][:cnt[j]].copy()) for j in range(nq)]
+
+
+def lut_to_fixed_point(raw, truncate=False):
+  """ConvertLookupToFixedPoint<uint8_t> (asymmetric_hashing_impl.cc:571-645): (u8 table, multiplier)."""
+  raw = np.ascontiguousarray(raw, dtype=np.float32).reshape(-1)
+  out = np.zeros(raw.size, np.uint8)
+  mult = np.zeros(1, np.float32)
+  lib().ref_lut_to_fixed_point(_p(raw), raw.size, 1 if truncate else 0, _p(out), _p(mult))
+  return out, mult[0]
+
+
+def bf16_quantize(x):
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  out = np.zeros(x.shape, np.int16)
+  lib().ref_bf16_quantize(_p(x), x.size, _p(out))
+  return out
+
+
+def bf16_decompress(x):
+  x = np.ascontiguousarray(x, dtype=np.int16)
+  out = np.zeros(x.shape, np.float32)
+  lib().ref_bf16_decompress(_p(x), x.size, _p(out))
+  return out

@@ -456,22 +456,26 @@ int so_tokenize(const so_index* ix, const float* q, uint32_t nq, int leaves, int
  * one-to-many path because 16-centre models never build block-transposed centres,
  * hashes/asymmetric_hashing2/training_model.cc:157-159), :572-587 (multiplier, quantile 1.0),
  * :589-645 (ConvertLookupToFixedPoint<uint8_t>, ROUND): lut = u8(round(raw*mult) + 128). */
-static void lut_one(const so_index* ix, const float* q, uint8_t* lut, float* mult_out, float* raw) {
-  const uint32_t B = ix->d.n_blocks, S = ix->d.dims_per_block;
-  for (uint32_t b = 0; b < B; ++b)
-    one_to_many(ix->d.distance, q + ix->block_off[b], ix->d.codebook + (size_t)b * 16 * S, 16, S,
-                (uint32_t)ix->block_dims[b], raw + b * 16);
+void so_lut_quantize(const float* raw, uint64_t n, uint8_t* lut, float* mult_out) {
   float maxabs = 0.0f;
-  for (uint32_t i = 0; i < B * 16; ++i) { float a = fabsf(raw[i]); if (a > maxabs) maxabs = a; }
+  for (uint64_t i = 0; i < n; ++i) { float a = fabsf(raw[i]); if (a > maxabs) maxabs = a; }
   const float floor_ = sqrtf(FLT_EPSILON);
   const float denom = maxabs > floor_ ? maxabs : floor_;
   const float mult = 127 / denom;
-  for (uint32_t i = 0; i < B * 16; ++i) {
+  for (uint64_t i = 0; i < n; ++i) {
     float v = raw[i] * mult;
     float r = roundf(v) + 128;
     lut[i] = (uint8_t)r;
   }
   *mult_out = mult;
+}
+
+static void lut_one(const so_index* ix, const float* q, uint8_t* lut, float* mult_out, float* raw) {
+  const uint32_t B = ix->d.n_blocks, S = ix->d.dims_per_block;
+  for (uint32_t b = 0; b < B; ++b)
+    one_to_many(ix->d.distance, q + ix->block_off[b], ix->d.codebook + (size_t)b * 16 * S, 16, S,
+                (uint32_t)ix->block_dims[b], raw + b * 16);
+  so_lut_quantize(raw, (uint64_t)B * 16, lut, mult_out);
 }
 
 int so_lut(const so_index* ix, const float* q, uint32_t nq, uint8_t* out_lut, float* out_mult) {

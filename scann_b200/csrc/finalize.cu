@@ -401,11 +401,12 @@ merge_partials_kernel(int distance, int disjoint, MergeSrc src, int world,
   uint64_t* kb = ka + np2;                                  // [np2]
   uint32_t* pa = reinterpret_cast<uint32_t*>(kb + np2);     // [np2] payload: record offset
   uint32_t* pb = pa + np2;                                  // [np2]
+  uint64_t* ks = reinterpret_cast<uint64_t*>(pb + np2);     // [world][ml] the lists' keys (ml = min(n_cand, nover))
   __shared__ uint32_t s_removed, s_valid;
   const int tid = threadIdx.x;
   const uint32_t q = blockIdx.x;
   const int n_cand = src.n_cand;
-  const int total = world * n_cand;
+  const int ml = min(n_cand, (int)nover);  // a list's entries past its nover-th cannot be among the global nover best
   auto rec = [&](int i) { return ((size_t)(i / n_cand) * src.nq_stride + q) * n_cand + (i % n_cand); };
   auto rec_id = [&](size_t o) -> uint32_t { return kPacked ? src.rec[o].z : src.ids[o]; };
   auto rec_tie = [&](size_t o) -> uint64_t {
@@ -414,20 +415,39 @@ merge_partials_kernel(int distance, int disjoint, MergeSrc src, int world,
   };
   auto rec_exact = [&](size_t o) -> float { return kPacked ? __uint_as_float(src.rec[o].w) : src.exact[o]; };
   if (tid == 0) { s_removed = 0; s_valid = 0; }
+  for (int i = tid; i < np2; i += kFinThreads) { ka[i] = kKeyMax; pa[i] = 0; }
   __syncthreads();
+  // Every list arrives sorted by key (keys are unique: (score, unsharded slot)), so the global rank of an element is
+  // its position in its own list plus, for every other list, the number of keys below it (a binary search in shared
+  // memory).  Elements of rank < nover drop straight into their place: a `world`-way merge without a sort.
   uint32_t nvalid = 0;
-  for (int i = tid; i < np2; i += kFinThreads) {
-    uint64_t key = kKeyMax;
-    if (i < total) {
-      const size_t o = rec(i);
-      if (rec_id(o) != kInvalidId) { key = rec_tie(o); ++nvalid; }
-    }
-    ka[i] = key;
-    pa[i] = (uint32_t)i;
+  for (int e = tid; e < world * ml; e += kFinThreads) {
+    const int r = e / ml, i = e - r * ml;
+    const size_t o = rec(r * n_cand + i);
+    const bool ok = rec_id(o) != kInvalidId;
+    ks[e] = ok ? rec_tie(o) : kKeyMax;
+    nvalid += ok ? 1u : 0u;
   }
   if (nvalid) atomicAdd(&s_valid, nvalid);
   __syncthreads();
-  block_bitonic_sort_kv(ka, pa, np2);
+  for (int e = tid; e < world * ml; e += kFinThreads) {
+    const uint64_t key = ks[e];
+    if (key == kKeyMax) continue;
+    const int r = e / ml;
+    uint32_t rank = (uint32_t)(e - r * ml);
+    for (int r2 = 0; r2 < world && rank < nover; ++r2) {
+      if (r2 == r) continue;
+      const uint64_t* l = ks + r2 * ml;
+      int lo = 0, hi = ml;  // first index with l[idx] > key
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (l[mid] < key) lo = mid + 1; else hi = mid;
+      }
+      rank += (uint32_t)lo;
+    }
+    if (rank < nover) { ka[rank] = key; pa[rank] = (uint32_t)(r * n_cand + (e - r * ml)); }
+  }
+  __syncthreads();
   const uint32_t n = min(s_valid, nover);  // global over-retrieved candidate list
   uint32_t m;
   if (disjoint) {
@@ -476,13 +496,20 @@ merge_partials_kernel(int distance, int disjoint, MergeSrc src, int world,
   }
 }
 
+static size_t merge_smem_bytes(int world, int n_cand, uint32_t nover, int* np2_out) {
+  int np2 = 2;
+  while ((uint32_t)np2 < nover) np2 <<= 1;
+  *np2_out = np2;
+  const int m = n_cand < (int)nover ? n_cand : (int)nover;
+  return (size_t)np2 * 24 + (size_t)world * m * 8;
+}
+
 cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, int n_cand,
                                   const uint32_t* ids, const uint64_t* tie, const float* exact,
                                   uint32_t nover, uint32_t npre, uint32_t k, uint32_t* out_idx,
                                   float* out_dist, uint32_t out_k, cudaStream_t s) {
   int np2 = 2;
-  while (np2 < world * n_cand) np2 <<= 1;
-  const size_t smem = (size_t)np2 * 24;
+  const size_t smem = merge_smem_bytes(world, n_cand, nover, &np2);
   cudaError_t e = cudaFuncSetAttribute(merge_partials_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   MergeSrc src{ids, tie, exact, nullptr, nq, n_cand};
@@ -496,8 +523,7 @@ cudaError_t launch_merge_records(const DevIndex& ix, uint32_t nq_valid, uint32_t
                                  float* out_dist, uint32_t out_k, cudaStream_t s) {
   if (nq_valid == 0) return cudaSuccess;
   int np2 = 2;
-  while (np2 < world * n_cand) np2 <<= 1;
-  const size_t smem = (size_t)np2 * 24;
+  const size_t smem = merge_smem_bytes(world, n_cand, nover, &np2);
   cudaError_t e = cudaFuncSetAttribute(merge_partials_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   MergeSrc src{nullptr, nullptr, nullptr, rec, nq_slice, n_cand};

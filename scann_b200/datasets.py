@@ -7,16 +7,35 @@ import numpy as np
 
 
 def clustered(n, d, n_clusters, sigma=0.35, seed=0, normalize=False, chunk=1 << 18,
-              centers_seed=None):
+              centers_seed=None, threads=1):
   """Gaussian mixture: n_clusters means ~ N(0, I), point = mean + sigma * N(0, I).
 
   `centers_seed` pins the mixture means so database and queries (different
-  `seed`) are drawn from the same mixture.
+  `seed`) are drawn from the same mixture.  threads > 1 draws every chunk from its own stream
+  (seed, chunk index) on a thread pool -- a different, equally deterministic dataset, for the large bench shapes.
   """
   crng = np.random.default_rng(seed if centers_seed is None else centers_seed)
   means = crng.standard_normal((n_clusters, d), dtype=np.float32)
-  rng = np.random.default_rng([seed, 0x5ca77])
   out = np.empty((n, d), dtype=np.float32)
+  if threads > 1:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def fill(ci):
+      s = ci * chunk
+      e = min(n, s + chunk)
+      rng = np.random.default_rng([seed, 0x5ca77, ci])
+      which = rng.integers(0, n_clusters, size=e - s)
+      blk = rng.standard_normal((e - s, d), dtype=np.float32)
+      blk *= sigma
+      blk += means[which]
+      if normalize:
+        blk /= np.maximum(np.linalg.norm(blk, axis=1, keepdims=True), 1e-12)
+      out[s:e] = blk
+
+    with ThreadPoolExecutor(threads) as ex:
+      list(ex.map(fill, range((n + chunk - 1) // chunk)))
+    return out
+  rng = np.random.default_rng([seed, 0x5ca77])
   for s in range(0, n, chunk):
     e = min(n, s + chunk)
     which = rng.integers(0, n_clusters, size=e - s)

@@ -1,0 +1,167 @@
+"""The oracle against the REFERENCE'S OWN CODE (oracle/_ref/libscann_ref.so, built by oracle/Makefile from
+/root/reference: the AVX2 LUT16 kernel of hashes/internal/lut16_avx2.inc with the reference's SIMD wrappers, the LUT
+fixed-point conversion and the code packing of hashes/internal/asymmetric_hashing_impl.cc, utils/bfloat16_helpers.h).
+
+This is what pins oracle/scann_oracle.c to the reference for the integer / byte part of the path: packed codes, u8 LUT,
+int16 scores, the float score (two roundings), the candidate contract.  Skipped where the library is absent (a checkout
+without /root/reference and without the prebuilt file).
+"""
+import numpy as np
+import pytest
+
+from conftest import get_case
+from oracle import ref
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libscann_ref.so not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("n,B", [(1, 1), (31, 2), (32, 3), (33, 16), (77, 25), (500, 48), (1000, 50), (257, 64),
+                                 (96, 127), (64, 128), (40, 200), (33, 256)])
+def test_reference_int16_scores_equal_the_lookup_sum(n, B):
+  """LUT16Avx2<1..3>::GetInt16Distances on CreatePackedDataset's layout == sum_b lut[b][code_b] - 128 B, the statement
+  the oracle's score_slot and the CUDA kernels implement (odd B exercises the SSE tail of the bottom loop, n % 32 the
+  padded last group)."""
+  rng = np.random.default_rng(n * 1000 + B)
+  codes = rng.integers(0, 16, (n, B), dtype=np.uint8)
+  packed = ref.pack_dataset(codes)
+  for nq in (1, 2, 3):
+    luts = [rng.integers(0, 256, (B, 16), dtype=np.uint8) for _ in range(nq)]
+    if B > 128:  # keep the int16 accumulator exact as CanUseInt16Accumulator demands (asymmetric_hashing_impl.cc:656-688)
+      luts = [(l.astype(np.int32) // 2 + 64).astype(np.uint8) for l in luts]
+    got = ref.lut16_int16(packed, n, B, luts)[:, :n].astype(np.int32)
+    want = np.stack([l[np.arange(B)[None, :], codes].astype(np.int32).sum(1) - 128 * B for l in luts])
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(dpb=1, d=64), dict(dpb=3, d=50, leaves=40), dict(distance="squared_l2", d=64, leaves=50, n=10000)],
+                         ids=["dot_b50", "dot_b64", "dot_varchunk_b17", "l2_b32"])
+def test_oracle_leaf_scores_equal_the_reference_kernel(kw):
+  """Whole leaves of a real index: the oracle's int16 scores == the reference kernel's, on the reference's packing of
+  the same codes, under the oracle's own u8 LUTs."""
+  c = get_case(**kw)
+  lut, _ = c.oracle.lut(c.q[:6])
+  for leaf in range(0, c.oracle.L, max(1, c.oracle.L // 7)):
+    dps = c.oracle.leaf_datapoints(leaf)
+    if len(dps) == 0:
+      continue
+    codes = c.arrays.codes[dps]
+    packed = ref.pack_dataset(codes)
+    got = ref.lut16_int16(packed, len(dps), codes.shape[1], [lut[0], lut[1], lut[2]])
+    for j in range(3):
+      np.testing.assert_array_equal(got[j, :len(dps)], c.oracle.leaf_scores(lut[j], leaf))
+
+
+def test_lut_fixed_point_conversion_equals_the_reference():
+  """so_lut_quantize == ConvertLookupToFixedPoint<uint8_t> (quantile 1.0, ROUND): bytes and multiplier bits, incl. the
+  sqrt(FLT_EPSILON) floor, exact .5 products and the +-127 ends."""
+  import ctypes as C
+  import oracle
+  L = oracle.lib()
+  L.so_lut_quantize.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+  L.so_lut_quantize.restype = None
+  rng = np.random.default_rng(3)
+  tables = [rng.standard_normal(800).astype(np.float32), (rng.standard_normal(400) * 1e-6).astype(np.float32),
+            np.zeros(32, np.float32), np.linspace(-2, 2, 255 * 2 + 1).astype(np.float32),
+            (rng.integers(-254, 255, 1600) / 254.0).astype(np.float32), np.array([1e30, -1e30, 3.0], np.float32)]
+  for raw in tables:
+    want, wm = ref.lut_to_fixed_point(raw)
+    got = np.zeros(raw.size, np.uint8)
+    gm = np.zeros(1, np.float32)
+    L.so_lut_quantize(raw.ctypes.data_as(C.c_void_p), raw.size, got.ctypes.data_as(C.c_void_p), gm.ctypes.data_as(C.c_void_p))
+    np.testing.assert_array_equal(got, want)
+    assert gm.view(np.uint32)[0] == np.float32(wm).view(np.uint32)
+
+
+def test_oracle_luts_equal_the_reference_conversion_of_their_raw_tables():
+  """The oracle's u8 LUT of real queries, re-derived through the reference's conversion from a float64-accurate raw
+  table: the multiplier differs by at most the raw table's own rounding, and wherever the raw entries agree the bytes do
+  (the raw table's arithmetic -- the one-to-many kernel -- is pinned by tests/test_oracle.py)."""
+  c = get_case()
+  lut, mult = c.oracle.lut(c.q[:8])
+  a = c.arrays
+  for i in range(8):
+    qb = c.q[i].reshape(a.codebook.shape[0], -1)
+    raw = -np.einsum("bd,bcd->bc", qb.astype(np.float64), a.codebook.astype(np.float64)).astype(np.float32)
+    want, wm = ref.lut_to_fixed_point(raw)
+    assert abs(wm - mult[i]) <= 2e-6 * abs(wm)
+    assert np.mean(want.reshape(lut[i].shape) == lut[i]) > 0.97
+    assert np.max(np.abs(want.reshape(lut[i].shape).astype(int) - lut[i].astype(int))) <= 1
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(soar=1.5)], ids=["dot", "dot_soar"])
+def test_oracle_candidates_equal_topn_of_the_reference_float_scores(kw):
+  """The pre-reorder candidate list, end to end on reference arithmetic: for every probed leaf the reference kernel
+  (GetTopFloatDistances, epsilon = +inf so that nothing is pruned) gives float(acc) * float(1 / mult) + bias for every
+  datapoint; the N' smallest (score, leaf, slot) of those are exactly the oracle's candidates, score bits included."""
+  c = get_case(**kw)
+  nq = 6
+  q = c.q[:nq]
+  leaves, bias = c.oracle.tokenize(q)
+  lut, mult = c.oracle.lut(q)
+  cand = c.oracle.candidates(q)
+  tokens = c.arrays.tokens
+  for i in range(nq):
+    rows = []
+    for r in range(leaves.shape[1]):
+      leaf = int(leaves[i, r])
+      dps = c.oracle.leaf_datapoints(leaf)
+      if len(dps) == 0:
+        continue
+      codes = c.arrays.codes[dps]
+      if c.arrays.soar:  # the SOAR code row iff the leaf is the datapoint's second token
+        second = tokens[2 * dps.astype(np.int64) + 1] == leaf
+        codes = np.where(second[:, None], c.arrays.soar_codes[dps], codes)
+      packed = ref.pack_dataset(codes)
+      (idx, dist), = ref.lut16_top_float(packed, len(dps), codes.shape[1], [lut[i]], [bias[i, r]], [mult[i]])
+      assert len(idx) == len(dps)  # nothing pruned: every real datapoint exactly once (the padded tail is masked)
+      order = np.argsort(idx)
+      for s, d in zip(idx[order], dist[order]):
+        rows.append((np.float32(d), leaf, int(s)))
+    # ascending (score, leaf, slot); -0.0 == +0.0 as in DistanceComparator
+    rows.sort(key=lambda t: (float(t[0]), t[1], t[2]))
+    n = int(cand["count"][i])
+    want = rows[:n]
+    np.testing.assert_array_equal(np.asarray([w[0] for w in want], np.float32).view(np.uint32),
+                                  cand["score"][i, :n].view(np.uint32))
+    np.testing.assert_array_equal([w[1] for w in want], cand["leaf"][i, :n])
+    np.testing.assert_array_equal([w[2] for w in want], cand["slot"][i, :n])
+
+
+def test_reference_prefilter_band_is_what_the_contract_says():
+  """The reference's own candidate filter `acc < trunc((epsilon - bias) * mult)` (lut16_avx2.inc:432-438), run with the
+  epsilon the exact contract ends at: everything it keeps has score <= epsilon + one quantum, and everything strictly
+  better than epsilon minus one quantum is kept -- the band DESIGN.md section 2 describes, measured on reference code."""
+  c = get_case()
+  q = c.q[:4]
+  leaves, bias = c.oracle.tokenize(q)
+  lut, mult = c.oracle.lut(q)
+  cand = c.oracle.candidates(q)
+  for i in range(4):
+    n = int(cand["count"][i])
+    eps = float(cand["score"][i, n - 1])
+    quantum = float(np.float32(1.0) / mult[i])
+    for r in range(leaves.shape[1]):
+      leaf = int(leaves[i, r])
+      dps = c.oracle.leaf_datapoints(leaf)
+      if len(dps) == 0:
+        continue
+      packed = ref.pack_dataset(c.arrays.codes[dps])
+      (aidx, adist), = ref.lut16_top_float(packed, len(dps), c.arrays.codes.shape[1], [lut[i]], [bias[i, r]], [mult[i]])
+      (kidx, kdist), = ref.lut16_top_float(packed, len(dps), c.arrays.codes.shape[1], [lut[i]], [bias[i, r]], [mult[i]], epsilon=eps)
+      assert np.all(kdist <= eps + quantum * 1.001)
+      kept = set(kidx.tolist())
+      must = aidx[adist < eps - quantum * 1.001]
+      assert set(must.tolist()) <= kept
+
+
+def test_bfloat16_helpers_equal_the_reference():
+  from scann_b200 import index_build
+  rng = np.random.default_rng(5)
+  x = np.concatenate([rng.standard_normal(100000).astype(np.float32) * 10.0 ** rng.integers(-30, 30, 100000).astype(np.float32),
+                      np.array([0.0, -0.0, np.inf, -np.inf, 3.4028235e38, -3.4028235e38, 3.39e38, 1e-45, -1e-45, 1.00390625,
+                                1.01171875, 65280.0, 65536.0], np.float32)])
+  np.testing.assert_array_equal(index_build.bfloat16_quantize(x), ref.bf16_quantize(x))
+  bits = rng.integers(-32768, 32768, 50000).astype(np.int16)
+  want = ref.bf16_decompress(bits)
+  got = (bits.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+  np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
