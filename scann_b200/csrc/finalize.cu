@@ -223,7 +223,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
   __shared__ uint32_t s_removed;
   const int tid = threadIdx.x;
   const uint32_t q = blockIdx.x;
-  const uint32_t n = min(w.cnt[q], w.nover);
+  uint32_t n = min(w.cnt[q], w.nover);
   const uint64_t* src = w.buf + (size_t)q * w.cap;
   const bool i8 = ix.dataset_i8 != nullptr;
   const bool reorder = ix.dataset != nullptr || ix.dataset_bf16 != nullptr || i8;
@@ -260,6 +260,16 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
   if (i8) __syncthreads();
   const float qnorm = (i8 && ix.distance != 0) ? s_qnorm : 0.f;
 
+  if ((a.part_ids || a.part_rec) && a.part_limit) {
+    // sampled global threshold (sharded.cu): local candidates whose score exceeds it cannot be among the global N' best
+    const uint32_t lim = a.part_limit[q];
+    uint32_t lo = 0, hi = n;  // first index whose score word is > lim (src is sorted)
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if ((uint32_t)(src[mid] >> 32) <= lim) lo = mid + 1; else hi = mid;
+    }
+    n = lo;
+  }
   if (a.part_ids || a.part_rec) {
     // Sharded mode: emit the raw over-retrieved candidates (before SOAR de-duplication, which is
     // only exact on the global top list) with their exact distances: four arrays, or packed 16-byte records
@@ -318,22 +328,54 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
     m = min(n, a.npre);
     __syncthreads();
   } else {
-    // sort by (dp, score) so the two SOAR copies of a datapoint are adjacent
+    // SOAR de-duplication (DeduplicateDatabaseSpilledResults, tree_x_hybrid/internal/utils.cc:135-156) without sorting by
+    // datapoint: the two copies of a datapoint find each other through a hash table on the id; the copy that comes
+    // first in (score, slot) order survives with 0.5 a + 0.5 b, the other is dropped.  One sort by (score', id) follows.
+    uint32_t* tab = reinterpret_cast<uint32_t*>(sq + 2 * ((ix.d + 3) & ~3u));  // [2 np2] slot -> list position + 1
+    uint32_t* dpv = tab + 2 * np2;                                              // [np2] datapoint id
+    int* partner = reinterpret_cast<int*>(dpv + np2);                           // [np2] position of the other copy or -1
+    const uint32_t hmask = 2u * (uint32_t)np2 - 1u;
+    for (int i = tid; i < 2 * np2; i += kFinThreads) tab[i] = 0u;
+    for (int i = tid; i < np2; i += kFinThreads) {
+      dpv[i] = (uint32_t)i < n ? ix.slot_dp[(uint32_t)src[i]] : kInvalidId;
+      partner[i] = -1;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += kFinThreads) {
+      const uint32_t dp = dpv[i];
+      uint32_t h = (dp * 2654435761u) & hmask;
+      for (;;) {
+        const uint32_t old = atomicCAS(&tab[h], 0u, i + 1u);
+        if (old == 0u) break;
+        if (dpv[old - 1u] == dp) { partner[i] = (int)(old - 1u); partner[old - 1u] = (int)i; break; }
+        h = (h + 1u) & hmask;
+      }
+    }
+    __syncthreads();
+    uint32_t removed = 0;
     for (int i = tid; i < np2; i += kFinThreads) {
       uint64_t k = kKeyMax;
       if ((uint32_t)i < n) {
-        const uint64_t s = src[i];
-        k = ((uint64_t)ix.slot_dp[(uint32_t)s] << 32) | (s >> 32);
+        const int j = partner[i];
+        if (j >= 0 && j < i) {
+          ++removed;
+        } else {
+          float sc = ord2f((uint32_t)(src[i] >> 32));
+          if (j > i) sc = __fadd_rn(__fmul_rn(0.5f, sc), __fmul_rn(0.5f, ord2f((uint32_t)(src[j] >> 32))));
+          k = make_key(sc, dpv[i]);
+        }
       }
-      ka[i] = k;
+      kb[i] = k;
     }
-    __syncthreads();
-    block_bitonic_sort(ka, np2);
-    soar_merge_sorted(ka, kb, nullptr, nullptr, n, np2, &s_removed);
+    if (removed) atomicAdd(&s_removed, removed);
     __syncthreads();
     block_bitonic_sort(kb, np2);
     m = min(n - s_removed, a.npre);
   }
+  // the final sort covers the m reordered candidates only
+  int np2k = 2;
+  while ((uint32_t)np2k < m) np2k <<= 1;
+  if (np2k > np2) np2k = np2;
   for (int i = tid; i < np2; i += kFinThreads) ka[i] = kKeyMax;
   __syncthreads();
   if (reorder && ix.d >= 8 && !i8) {
@@ -356,7 +398,7 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
     }
   }
   __syncthreads();
-  block_bitonic_sort(ka, np2);
+  block_bitonic_sort(ka, np2k);
   const uint32_t kk = min(a.k, m);
   const float mulr = ix.distance == 0 ? -1.0f : 1.0f;  // scann.cc:364-369
   for (uint32_t i = tid; i < a.out_k; i += kFinThreads) {
@@ -374,10 +416,70 @@ finalize_kernel(DevIndex ix, ScanWork w, FinalizeArgs a, int np2) {
 cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const FinalizeArgs& a, cudaStream_t s) {
   int np2 = 2;
   while ((uint32_t)np2 < w.nover) np2 <<= 1;
-  const size_t smem = (size_t)np2 * 16 + (((size_t)ix.d + 3) & ~(size_t)3) * 4 * (ix.dataset_i8 ? 2 : 1);
+  // ka, kb; the query (twice: int8 reordering keeps a scaled copy); hash table [2 np2] + ids [np2] + partners [np2]
+  const size_t smem = (size_t)np2 * 16 + (((size_t)ix.d + 3) & ~(size_t)3) * 4 * 2 + (size_t)np2 * 16;
   cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   finalize_kernel<<<w.nq, kFinThreads, smem, s>>>(ix, w, a, np2);
+  return cudaGetLastError();
+}
+
+// Sampled global threshold of the sharded search.  Every rank publishes, per query, the score word of every 16th key of
+// its sorted local candidate list (positions 15, 31, ...).  If m of a rank's samples are <= x, that rank holds at
+// least 16 m candidates with score <= x; so with `need` = ceil(N' / 16), the need-th smallest sample over all ranks is
+// an upper bound of the global N'-th best score, and at most N' + 15 * world (+ ties) candidates lie below it.  Ranks
+// then reorder and send only those, instead of their whole local top-N' (world x N' in total).
+__global__ void sample_scores_kernel(const uint64_t* __restrict__ buf, const uint32_t* __restrict__ cnt, uint32_t cap,
+                                     uint32_t nover, uint32_t nq, uint32_t S, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq * S) return;
+  const uint32_t q = i / S, j = i - q * S;
+  const uint32_t pos = 16 * (j + 1) - 1;
+  const uint32_t n = min(cnt[q], nover);
+  out[i] = pos < n ? (uint32_t)(buf[(size_t)q * cap + pos] >> 32) : 0xFFFFFFFFu;
+}
+
+__global__ void __launch_bounds__(kFinThreads)
+sample_threshold_kernel(const uint32_t* __restrict__ samples, int world, uint32_t nq, uint32_t S, uint32_t need,
+                        uint32_t* __restrict__ limit, int np2) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  uint32_t* v = reinterpret_cast<uint32_t*>(smem);
+  const uint32_t q = blockIdx.x;
+  const int total = world * (int)S;
+  for (int i = threadIdx.x; i < np2; i += kFinThreads)
+    v[i] = i < total ? samples[((size_t)(i / S) * nq + q) * S + (i % S)] : 0xFFFFFFFFu;
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < (np2 >> 1); t += kFinThreads) {
+        const int l = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int r = l | j;
+        const uint32_t a = v[l], b = v[r];
+        const bool up = (l & k) == 0;
+        if ((a > b) == up) { v[l] = b; v[r] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) limit[q] = (need >= 1 && (int)need <= total) ? v[need - 1] : 0xFFFFFFFFu;
+}
+
+cudaError_t launch_sample_scores(const ScanWork& w, uint32_t S, uint32_t* out, cudaStream_t s) {
+  const uint32_t total = w.nq * S;
+  if (!total) return cudaSuccess;
+  sample_scores_kernel<<<(total + 255) / 256, 256, 0, s>>>(w.buf, w.cnt, w.cap, w.nover, w.nq, S, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample_threshold(const uint32_t* samples, int world, uint32_t nq, uint32_t S, uint32_t nover,
+                                    uint32_t* limit, cudaStream_t s) {
+  if (!nq) return cudaSuccess;
+  int np2 = 2;
+  while (np2 < world * (int)S) np2 <<= 1;
+  const size_t smem = (size_t)np2 * 4;
+  cudaError_t e = cudaFuncSetAttribute(sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  sample_threshold_kernel<<<nq, kFinThreads, smem, s>>>(samples, world, nq, S, (nover + 15) / 16, limit, np2);
   return cudaGetLastError();
 }
 
@@ -460,31 +562,62 @@ merge_partials_kernel(int distance, int disjoint, MergeSrc src, int world,
     m = min(n, npre);
     __syncthreads();
   } else {
-    __syncthreads();
-    // (dp, score) keys, payload = record
+    // SOAR de-duplication (DeduplicateDatabaseSpilledResults, tree_x_hybrid/internal/utils.cc:135-156) without sorting by
+    // datapoint: the two copies of a datapoint find each other through a hash table on the id; the copy that comes
+    // first in (score, slot) order survives with 0.5 a + 0.5 b, the other is dropped.  One sort by (score', id) follows.
+    uint32_t* tab = reinterpret_cast<uint32_t*>(ks + (size_t)world * ml);  // [2 np2] slot -> list position + 1
+    uint32_t* dpv = tab + 2 * np2;                                          // [np2] datapoint id
+    int* partner = reinterpret_cast<int*>(dpv + np2);                       // [np2] position of the other copy or -1
+    const uint32_t hmask = 2u * (uint32_t)np2 - 1u;
+    for (int i = tid; i < 2 * np2; i += kFinThreads) tab[i] = 0u;
     for (int i = tid; i < np2; i += kFinThreads) {
-      uint64_t key = kKeyMax;
-      uint32_t p = pa[i];
-      if ((uint32_t)i < n) key = ((uint64_t)rec_id(rec((int)p)) << 32) | (ka[i] >> 32);
-      kb[i] = key;
-      pb[i] = p;
+      dpv[i] = (uint32_t)i < n ? rec_id(rec((int)pa[i])) : kInvalidId;
+      partner[i] = -1;
     }
     __syncthreads();
+    for (uint32_t i = tid; i < n; i += kFinThreads) {
+      const uint32_t dp = dpv[i];
+      uint32_t h = (dp * 2654435761u) & hmask;
+      for (;;) {
+        const uint32_t old = atomicCAS(&tab[h], 0u, i + 1u);
+        if (old == 0u) break;
+        if (dpv[old - 1u] == dp) { partner[i] = (int)(old - 1u); partner[old - 1u] = (int)i; break; }
+        h = (h + 1u) & hmask;
+      }
+    }
+    __syncthreads();
+    uint32_t removed = 0;
+    for (int i = tid; i < np2; i += kFinThreads) {
+      uint64_t key = kKeyMax;
+      if ((uint32_t)i < n) {
+        const int j = partner[i];
+        if (j >= 0 && j < i) {
+          ++removed;
+        } else {
+          float sc = ord2f((uint32_t)(ka[i] >> 32));
+          if (j > i) sc = __fadd_rn(__fmul_rn(0.5f, sc), __fmul_rn(0.5f, ord2f((uint32_t)(ka[j] >> 32))));
+          key = make_key(sc, dpv[i]);
+        }
+      }
+      kb[i] = key;
+      pb[i] = pa[i];
+    }
+    if (removed) atomicAdd(&s_removed, removed);
+    __syncthreads();
     block_bitonic_sort_kv(kb, pb, np2);
-    soar_merge_sorted(kb, ka, pb, pa, n, np2, &s_removed);
-    __syncthreads();
-    block_bitonic_sort_kv(ka, pa, np2);
     m = min(n - s_removed, npre);
-    for (int i = tid; i < np2; i += kFinThreads) { kb[i] = ka[i]; pb[i] = pa[i]; }
-    __syncthreads();
   }
-  for (int i = tid; i < np2; i += kFinThreads) {
+  // top-k by (exact distance, id) of the m candidates that go to "reordering"; only np2k >= m keys are sorted
+  int np2k = 2;
+  while ((uint32_t)np2k < m) np2k <<= 1;
+  if (np2k > np2) np2k = np2;
+  for (int i = tid; i < np2k; i += kFinThreads) {
     uint64_t key = kKeyMax;
     if ((uint32_t)i < m) key = make_key(rec_exact(rec((int)pb[i])), (uint32_t)kb[i]);
     ka[i] = key;
   }
   __syncthreads();
-  block_bitonic_sort(ka, np2);
+  block_bitonic_sort(ka, np2k);
   const uint32_t kk = min(k, m);
   const float mulr = distance == 0 ? -1.0f : 1.0f;
   for (uint32_t i = tid; i < out_k; i += kFinThreads) {
@@ -501,7 +634,8 @@ static size_t merge_smem_bytes(int world, int n_cand, uint32_t nover, int* np2_o
   while ((uint32_t)np2 < nover) np2 <<= 1;
   *np2_out = np2;
   const int m = n_cand < (int)nover ? n_cand : (int)nover;
-  return (size_t)np2 * 24 + (size_t)world * m * 8;
+  // ka, kb (u64) + pa, pb (u32) + the lists' keys + hash table [2 np2] + ids [np2] + partners [np2]
+  return (size_t)np2 * 24 + (size_t)world * m * 8 + (size_t)np2 * 16;
 }
 
 cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, int n_cand,

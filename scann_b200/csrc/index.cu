@@ -145,6 +145,7 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     uint32_t nonempty = 0;  // a leaf-sharded rank holds L / world leaves; the rest are empty here
     for (uint32_t l = 0; l < L; ++l) nonempty += lsize[l] ? 1u : 0u;
     ix->avg_leaf_slots = (uint32_t)(ngroups * 32 / std::max<uint32_t>(by_leaf ? nonempty : L, 1));
+    ix->nonempty_leaves = nonempty;
   }
   if (ngroups * 32 > 0xFFFFFFF0ull) return fail(SCANN_B200_UNIMPLEMENTED, "more than 2^32 slots");
   std::vector<uint32_t> slot_dp(ngroups * 32, 0xFFFFFFFFu);
@@ -396,6 +397,7 @@ int ensure_workspace(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_
   CU(ix->leaf_eoff.ensure(sizeof(uint32_t) * (v.L + 1)));
   CU(ix->leaf_cur.ensure(sizeof(uint32_t) * (v.L + 1)));
   CU(ix->item_off.ensure(sizeof(uint32_t) * (v.L + 1)));
+  CU(ix->item_leaf.ensure(sizeof(uint32_t) * std::min<size_t>((size_t)nq * p.P * 4 + v.L + 1024, (size_t)8 << 20)));
   CU(ix->entry_q.ensure(sizeof(uint32_t) * (size_t)nq * p.P));
   CU(ix->pair_pos.ensure(sizeof(uint32_t) * (size_t)nq * p.P));
   CU(ix->entry_bias.ensure(sizeof(float) * (size_t)nq * p.P));
@@ -418,6 +420,26 @@ void fill_scan_work(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_t
   w.entry_q = ix->entry_q.as<uint32_t>(); w.entry_bias = ix->entry_bias.as<float>(); w.pair_pos = ix->pair_pos.as<uint32_t>();
   w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
   w.nq = nq; w.P = p.P; w.cap = cap; w.nover = p.nover; w.quads_per_item = 2; w.one = 1;  // 2 octs = 16 queries per work item
+  w.item_leaf = ix->item_leaf.as<uint32_t>();
+  w.item_leaf_cap = (uint32_t)(ix->item_leaf.bytes / sizeof(uint32_t));
+  // Groups per work item.  An item costs a fixed set-up (oct tables, thresholds, a few dependent loads); with many more
+  // items than resident CTAs (740) larger tiles amortise it, with few items small tiles balance the load.  Expected
+  // items at g groups per tile: (leaves hit) x ceil(queries per leaf / 16) x ceil(groups per leaf / g).
+  {
+    const double leaves = std::max<double>(1.0, ix->nonempty_leaves);
+    const double qpl = (double)nq * p.P * (ix->shard_mode == SCANN_B200_SHARD_BY_LEAF ? 1.0 / ix->shard_world : 1.0) / leaves;
+    const double hit = leaves * (1.0 - exp(-qpl));
+    const double chunks = std::max(1.0, ceil(qpl / 16.0));
+    const double groups = std::max(1.0, ix->avg_leaf_slots / 32.0);
+    uint32_t g = (uint32_t)sb::kMaxGroupsPerTile;
+    for (uint32_t cand = 256; cand > (uint32_t)sb::kMaxGroupsPerTile; cand >>= 1)
+      if (hit * chunks * ceil(groups / cand) >= 16.0 * 740.0) { g = cand; break; }
+    w.max_gpt = g;
+    if (const char* e = getenv("SCANN_B200_SCAN_GPT")) {
+      const int t = atoi(e);
+      if (t >= 1 && t <= 4096) w.max_gpt = (uint32_t)t;
+    }
+  }
   // large leaves (C5 shape: ~20 candidates per (query, item)): stage candidates in shared memory, one global atomic
   // per (query, item); small leaves (C2: ~1.4) append directly
   w.stage = ix->avg_leaf_slots >= 2048 ? 1u : 0u;
@@ -736,6 +758,72 @@ int check_query_args(scann_b200_index* ix, const void* q, uint32_t nq) {
 
 }  // namespace
 
+namespace sbi {
+
+static scann_b200_index* make_lane(scann_b200_index* root) {
+  scann_b200_index* c = new scann_b200_index();
+  c->dev = root->dev; c->desc = root->desc; c->device = root->device; c->sm_count = root->sm_count;
+  c->h_leaf_size = root->h_leaf_size; c->max_chunk = root->max_chunk;
+  c->brute = root->brute; c->bf_f32 = root->bf_f32; c->bf_dpitch = root->bf_dpitch; c->bf_row0 = root->bf_row0;
+  c->avg_leaf_slots = root->avg_leaf_slots; c->nonempty_leaves = root->nonempty_leaves;
+  c->bf_max_row_norm = root->bf_max_row_norm;
+  c->shard_rank = root->shard_rank; c->shard_world = root->shard_world; c->shard_mode = root->shard_mode;
+  c->parent = root;
+  // the index arrays a search path reaches through DevBuf members rather than through `dev`
+  auto alias = [](DevBuf& dst, const DevBuf& src) { dst.p = src.p; dst.bytes = src.bytes; dst.own = false; };
+  alias(c->bf_db, root->bf_db); alias(c->dataset, root->dataset); alias(c->leaf_goff, root->leaf_goff);
+  alias(c->slot_dp, root->slot_dp);
+  bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < EV_ALL && ok; ++i) ok = cudaEventCreate(&c->ev[i]) == cudaSuccess;
+  if (!ok) {
+    fail(SCANN_B200_INTERNAL, "could not create a search lane (stream / events)");
+    if (c->stream) cudaStreamDestroy(c->stream);
+    for (int i = 0; i < EV_ALL; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+LaneGuard::LaneGuard(scann_b200_index* root) : root_(root) {
+  std::unique_lock<std::mutex> lk(root->pool_mu);
+  if (root->lane_busy.empty()) root->lane_busy.assign(1, 0);
+  for (;;) {
+    for (size_t i = 0; i < root->lane_busy.size(); ++i)
+      if (!root->lane_busy[i]) { slot_ = (int)i; break; }
+    if (slot_ >= 0) break;
+    if ((int)root->lane_busy.size() < scann_b200_index::kMaxLanes) {
+      cudaSetDevice(root->device);
+      scann_b200_index* c = make_lane(root);
+      if (!c) return;
+      root->lanes.push_back(c);
+      root->lane_busy.push_back(0);
+      slot_ = (int)root->lane_busy.size() - 1;
+      break;
+    }
+    root->pool_cv.wait(lk);
+  }
+  root->lane_busy[slot_] = 1;
+  ix = slot_ == 0 ? root : root->lanes[slot_ - 1];
+  lk.unlock();
+  ix->mu.lock();
+}
+
+LaneGuard::~LaneGuard() {
+  if (!ix) return;
+  const scann_b200_stats st = ix->last;
+  ix->mu.unlock();
+  {
+    std::lock_guard<std::mutex> lk(root_->pool_mu);
+    root_->lane_busy[slot_] = 0;
+    root_->last_any = st;  // scann_b200_last_stats: the most recently finished call
+    root_->last_any_valid = true;
+  }
+  root_->pool_cv.notify_one();
+}
+
+}  // namespace sbi
+
 extern "C" {
 
 const char* scann_b200_last_error(void) { return g_err.c_str(); }
@@ -775,6 +863,12 @@ int scann_b200_index_create(const scann_b200_index_desc* desc, scann_b200_index*
 void scann_b200_index_destroy(scann_b200_index* ix) {
   if (!ix) return;
   cudaSetDevice(ix->device);
+  for (scann_b200_index* c : ix->lanes) {
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    for (int i = 0; i < EV_ALL; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    delete c;
+  }
+  ix->lanes.clear();
   if (ix->stream) { cudaStreamSynchronize(ix->stream); cudaStreamDestroy(ix->stream); }
   for (int i = 0; i < EV_ALL; ++i) if (ix->ev[i]) cudaEventDestroy(ix->ev[i]);
   if (ix->comm) comm_destroy(ix->comm);
@@ -792,7 +886,9 @@ int scann_b200_search_batched_device(scann_b200_index* ix, const float* d_querie
   Params p;
   if (int rc = resolve(ix, final_nn, pre_nn, leaves, &p)) return rc;
   if (out_k <= 0 || !d_out_idx || !d_out_dist) return fail(SCANN_B200_INVALID_ARGUMENT, "bad output buffers");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  LaneGuard lane(ix);
+  if (!lane.ix) return SCANN_B200_INTERNAL;
+  ix = lane.ix;
   CU(cudaSetDevice(ix->device));
   ix->last = scann_b200_stats{};
   for (uint32_t s0 = 0; s0 < nq; s0 += ix->max_chunk) {
@@ -811,7 +907,9 @@ int scann_b200_search_batched(scann_b200_index* ix, const float* queries, uint32
   Params p;
   if (int rc = resolve(ix, final_nn, pre_nn, leaves, &p)) return rc;
   if (out_k <= 0 || !out_idx || !out_dist) return fail(SCANN_B200_INVALID_ARGUMENT, "bad output buffers");
-  std::lock_guard<std::mutex> lock(ix->mu);
+  LaneGuard lane(ix);  // concurrent callers run on different lanes: one batch's copies overlap another's kernels
+  if (!lane.ix) return SCANN_B200_INTERNAL;
+  ix = lane.ix;
   CU(cudaSetDevice(ix->device));
   ix->last = scann_b200_stats{};
   const uint32_t D = ix->dev.d;
@@ -862,6 +960,7 @@ int scann_b200_search_partial_device(scann_b200_index* ix, const float* d_querie
     return fail(SCANN_B200_INVALID_ARGUMENT, "partial buffers too small: n_cand=%d < %u", n_cand, p.nover);
   std::lock_guard<std::mutex> lock(ix->mu);
   CU(cudaSetDevice(ix->device));
+  { std::lock_guard<std::mutex> lk(ix->pool_mu); ix->last_any_valid = false; }
   ix->last = scann_b200_stats{};
   for (uint32_t s0 = 0; s0 < nq; s0 += ix->max_chunk) {
     const uint32_t c = std::min(ix->max_chunk, nq - s0);
@@ -907,6 +1006,10 @@ int scann_b200_merge_topk_device(scann_b200_index* ix, uint32_t nq, int32_t worl
 
 int scann_b200_last_stats(scann_b200_index* ix, scann_b200_stats* out) {
   if (!ix || !out) return fail(SCANN_B200_INVALID_ARGUMENT, "null argument");
+  {
+    std::lock_guard<std::mutex> lk(ix->pool_mu);
+    if (ix->last_any_valid) { *out = ix->last_any; return 0; }
+  }
   std::lock_guard<std::mutex> lock(ix->mu);
   *out = ix->last;
   return 0;
@@ -965,8 +1068,7 @@ int scann_b200_debug_leaf_scores(scann_b200_index* ix, const uint8_t* lut, uint3
   CU(dout.ensure(sizeof(int16_t) * n));
   CU(cudaMemsetAsync(dl.p, 0, (size_t)v.W * 128, ix->stream));
   CU(cudaMemcpyAsync(dl.p, lut, (size_t)v.B * 16, cudaMemcpyHostToDevice, ix->stream));
-  sb::launch_leaf_scores(v, dl.as<uint8_t>(), leaf, dout.as<int16_t>(), ix->stream);
-  CU(cudaGetLastError());
+  CU(sb::launch_leaf_scores(v, dl.as<uint8_t>(), leaf, dout.as<int16_t>(), ix->stream));
   CU(cudaMemcpyAsync(out, dout.p, sizeof(int16_t) * n, cudaMemcpyDeviceToHost, ix->stream));
   CU(cudaStreamSynchronize(ix->stream));
   return 0;
@@ -982,6 +1084,7 @@ int scann_b200_debug_candidates(scann_b200_index* ix, const float* queries, uint
   std::lock_guard<std::mutex> lock(ix->mu);
   CU(cudaSetDevice(ix->device));
   const sb::DevIndex& v = ix->dev;
+  { std::lock_guard<std::mutex> lk(ix->pool_mu); ix->last_any_valid = false; }
   ix->last = scann_b200_stats{};
   CU(ix->q.ensure(sizeof(float) * (size_t)nq * v.d));
   CU(cudaMemcpyAsync(ix->q.p, queries, sizeof(float) * (size_t)nq * v.d, cudaMemcpyHostToDevice, ix->stream));

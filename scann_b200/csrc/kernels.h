@@ -85,7 +85,8 @@ struct ScanWork {
   // tau, the others leave tau = max and the ranks all-reduce(min) it afterwards.  pilot_world <= 1: every query.
   uint32_t pilot_world, pilot_rank;
   uint32_t max_gpt;           // groups per work item of the main scan (0 = kMaxGroupsPerTile)
-  uint32_t* item_leaf;        // [n_items] leaf of each work item (written by the work-list pass)
+  uint32_t* item_leaf;        // [item_leaf_cap] leaf of each work item (written by the work-list pass; NULL = none)
+  uint32_t item_leaf_cap;
 };
 
 // ---- query preparation ----
@@ -123,7 +124,14 @@ struct FinalizeArgs {
   // packed partial records {tie-break key u64, id u32, exact distance f32} [nq][part_cap] (sharded.cu); used when
   // part_ids is NULL
   uint4* part_rec;
+  // optional [nq] score words (f2ord): partial candidates above it are dropped (sampled global threshold, sharded.cu)
+  const uint32_t* part_limit;
 };
+// sampled global threshold (finalize.cu): every 16th score of the sorted local lists -> [nq][S]; the threshold kernel
+// reads the all-gathered [world][nq][S] samples
+cudaError_t launch_sample_scores(const ScanWork& w, uint32_t S, uint32_t* out, cudaStream_t s);
+cudaError_t launch_sample_threshold(const uint32_t* samples, int world, uint32_t nq, uint32_t S, uint32_t nover,
+                                    uint32_t* limit, cudaStream_t s);
 cudaError_t launch_finalize(const DevIndex& ix, const ScanWork& w, const FinalizeArgs& a, cudaStream_t s);
 cudaError_t launch_merge_partials(const DevIndex& ix, uint32_t nq, int world, int n_cand,
                                   const uint32_t* ids, const uint64_t* tie, const float* exact,
@@ -171,6 +179,6 @@ cudaError_t gemm_bf16_nt(const void* a_operand, uint32_t a_rows, uint32_t a_rows
                          uint32_t b_rows, uint32_t kpitch, float* out, uint32_t ld, cudaStream_t s,
                          float* cmax = nullptr, uint32_t ld_c = 0, const float* cbias = nullptr);
 // ---- debug ----
-void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s);
+cudaError_t launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s);
 
 }  // namespace sb

@@ -47,6 +47,15 @@
 namespace sb {
 
 constexpr uint32_t kInvalidQuery = 0xFFFFFFFFu;
+
+// Work tiling of a leaf of `ng` 32-slot groups: tiles of at most `max_gpt` groups, evenly sized.  max_gpt is a per-batch
+// choice of the host (launch heuristics in index.cu): 32 keeps items small where there are few of them, larger tiles
+// amortise the per-item set-up (oct tables, thresholds) where a batch has many more items than resident CTAs.
+__device__ __forceinline__ void leaf_tiling(uint32_t ng, uint32_t max_gpt, uint32_t* ntiles, uint32_t* gpt) {
+  const uint32_t nt = ng ? (ng + max_gpt - 1) / max_gpt : 0u;
+  *ntiles = nt;
+  *gpt = nt ? (ng + nt - 1) / nt : 0u;
+}
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kMaxQPI = 32;  // queries per work item (4 octs of 8 queries)
 
@@ -603,7 +612,9 @@ __global__ void __launch_bounds__(1024) worklist_scan_kernel(DevIndex ix, ScanWo
     if (l < ix.L) {
       ce = w.leaf_cnt[l];
       const uint32_t qpi = w.quads_per_item * kQueriesPerQuad;
-      ci = ((ce + qpi - 1) / qpi) * ix.leaf_ntiles[l];
+      uint32_t nt, gp;
+      leaf_tiling(ix.leaf_goff[l + 1] - ix.leaf_goff[l], w.max_gpt, &nt, &gp);
+      ci = ((ce + qpi - 1) / qpi) * nt;
     }
     uint32_t se = ce, si = ci;  // inclusive warp scan
 #pragma unroll
@@ -625,7 +636,12 @@ __global__ void __launch_bounds__(1024) worklist_scan_kernel(DevIndex ix, ScanWo
     __syncthreads();
     const uint32_t pe = carry_e + (warp ? wsum_e[warp - 1] : 0u) + se - ce;
     const uint32_t pi = carry_i + (warp ? wsum_i[warp - 1] : 0u) + si - ci;
-    if (l < ix.L) { w.leaf_eoff[l] = pe; w.item_off[l] = pi; w.leaf_cur[l] = 0; }
+    if (l < ix.L) {
+      w.leaf_eoff[l] = pe; w.item_off[l] = pi; w.leaf_cur[l] = 0;
+      // item -> leaf table (the scan kernel's alternative to a binary search over item_off per item)
+      if (w.item_leaf)
+        for (uint32_t j = 0; j < ci && pi + j < w.item_leaf_cap; ++j) w.item_leaf[pi + j] = l;
+    }
     __syncthreads();
     if (tid == 0) { carry_e += wsum_e[31]; carry_i += wsum_i[31]; }
     __syncthreads();
@@ -688,21 +704,28 @@ struct ItemMeta {
 };
 constexpr uint32_t kStage = 32;
 
-// Rare path of the main scan: exact key test and warp-aggregated append for one oct.  All 32 lanes call.
+// Push path of the main scan: exact key test and warp-aggregated append for one oct.  All 32 lanes call.  `hit` holds
+// the lane's packed threshold test (bit 15 / 31 of word j set iff the sum in that half passed); one warp-wide OR finds
+// the queries of the oct with any passing slot and only those are visited.
 __device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork& w, ItemMeta* meta, uint32_t qd,
-                                             uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, bool valid,
-                                             uint32_t gslot, int off128) {
+                                             uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t h0, uint32_t h1,
+                                             uint32_t h2, uint32_t h3, bool valid, uint32_t gslot, int off128) {
   const int lane = threadIdx.x & 31;
-  const int sv[8] = {(int)(a0 & 0xFFFFu), (int)(a1 & 0xFFFFu), (int)(a0 >> 16), (int)(a1 >> 16),
-                     (int)(a2 & 0xFFFFu), (int)(a3 & 0xFFFFu), (int)(a2 >> 16), (int)(a3 >> 16)};
-#pragma unroll 1
-  for (int i = 0; i < 8; ++i) {
+  // query i of the oct: sums (s0,s2) (s1,s3) (s4,s6) (s5,s7) sit in a0..a3 as u16 halves
+  uint32_t m8 = ((h0 >> 15) & 1u) | ((h1 >> 14) & 2u) | ((h0 >> 29) & 4u) | ((h1 >> 28) & 8u) |
+                ((h2 >> 11) & 16u) | ((h3 >> 10) & 32u) | ((h2 >> 25) & 64u) | ((h3 >> 24) & 128u);
+  if (!valid) m8 = 0u;
+  uint32_t any8 = __reduce_or_sync(kFull, m8);
+  while (any8) {
+    const int i = __ffs(any8) - 1;
+    any8 &= any8 - 1;
     const int qi = qd * 8 + i;
-    bool p = valid && sv[i] <= meta->thr[qi];
-    if (!__any_sync(kFull, p)) continue;
+    bool p = (m8 >> i) & 1u;
     uint64_t key = 0;
     if (p) {
-      key = make_key(ah_float_score(sv[i] - off128, meta->inv[qi], meta->bias[qi]),
+      const uint32_t word = (i & 4) ? ((i & 1) ? a3 : a2) : ((i & 1) ? a1 : a0);
+      const int sv = (int)((i & 2) ? (word >> 16) : (word & 0xFFFFu));
+      key = make_key(ah_float_score(sv - off128, meta->inv[qi], meta->bias[qi]),
                      ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
       p = key < meta->tau[qi];
     }
@@ -746,35 +769,38 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
   uint64_t (&s_tau)[kMaxQPI] = meta.tau;
   float (&s_inv)[kMaxQPI] = meta.inv;
   float (&s_bias)[kMaxQPI] = meta.bias;
-  __shared__ uint32_t s_item, s_leaf;
+  __shared__ uint32_t s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nlast = (int)ix.B - 8 * (W - 1);
   const int off128 = 128 * (int)ix.B;
   const uint32_t n_items = w.counters[1];
   const uint32_t qpi = w.quads_per_item * kQueriesPerQuad;
   constexpr int kTblEntries = W * 128;
+  // Items are claimed one ahead: the atomic for item i + 1 is issued when item i starts and its result is only needed
+  // when item i is done, so its round trip (and the item -> leaf lookup) overlaps the scoring.
+  if (tid == 0) s_item = atomicAdd(&w.counters[0], 1u);
   for (;;) {
-    __syncthreads();  // previous item's tables are no longer read
-    if (tid == 0) {
-      const uint32_t item = atomicAdd(&w.counters[0], 1u);
-      s_item = item;
-      if (item < n_items) {  // leaf = upper_bound(item_off, item) - 1
-        uint32_t lo = 0, hi = ix.L;
-        while (lo < hi) {
-          const uint32_t mid = (lo + hi) >> 1;
-          if (w.item_off[mid + 1] <= item) lo = mid + 1; else hi = mid;
-        }
-        s_leaf = lo;
-      }
-    }
-    __syncthreads();
+    __syncthreads();  // previous item's tables are no longer read; s_item is visible
     const uint32_t item = s_item;
     if (item >= n_items) break;
-    const uint32_t leaf = s_leaf;
+    uint32_t next_item = 0;
+    if (tid == 0) next_item = atomicAdd(&w.counters[0], 1u);
+    uint32_t leaf;
+    if (w.item_leaf && item < w.item_leaf_cap) {
+      leaf = w.item_leaf[item];
+    } else {  // leaf = upper_bound(item_off, item) - 1
+      uint32_t lo = 0, hi = ix.L;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (w.item_off[mid + 1] <= item) lo = mid + 1; else hi = mid;
+      }
+      leaf = lo;
+    }
     const uint32_t local = item - w.item_off[leaf];
-    const uint32_t ntiles = ix.leaf_ntiles[leaf];
+    const uint32_t gbeg_t = ix.leaf_goff[leaf], ng_t = ix.leaf_goff[leaf + 1] - gbeg_t;
+    uint32_t ntiles, gpt;
+    leaf_tiling(ng_t, w.max_gpt, &ntiles, &gpt);
     const uint32_t chunk = local / ntiles, tile = local - chunk * ntiles;
-    const uint32_t gpt = ix.leaf_gpt[leaf];
     const uint32_t gbeg = ix.leaf_goff[leaf], ng = ix.leaf_goff[leaf + 1] - gbeg;
     const uint32_t g0 = tile * gpt, g1 = min(g0 + gpt, ng);
     const uint32_t nleaf = ix.leaf_size[leaf];
@@ -830,9 +856,10 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       // octs are unrolled copies and must stay inside the instruction cache
       auto filter = [&](const uint32_t qd, const uint32_t (&acc)[4]) {
         const uint4 t = meta.thrp[qd];
-        const uint32_t hit = ((t.x - acc[0]) | (t.y - acc[1]) | (t.z - acc[2]) | (t.w - acc[3])) & 0x80008000u;
+        const uint32_t h0 = t.x - acc[0], h1 = t.y - acc[1], h2 = t.z - acc[2], h3 = t.w - acc[3];
+        const uint32_t hit = (h0 | h1 | h2 | h3) & 0x80008000u;
         if (__any_sync(kFull, valid && hit != 0))
-          push_candidates(ix, w, &meta, qd, acc[0], acc[1], acc[2], acc[3], valid, gslot, off128);
+          push_candidates(ix, w, &meta, qd, acc[0], acc[1], acc[2], acc[3], h0, h1, h2, h3, valid, gslot, off128);
       };
 #define SB_DO_QUAD(QD)                                       \
   if (QD < nquads) {                                         \
@@ -844,21 +871,24 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
 #undef SB_DO_QUAD
     }
     // item epilogue: publish the staged candidates, one warp per query, one global atomicAdd per (query, item)
-    if (!w.stage) continue;
-    __syncthreads();
-    for (uint32_t qi = warp; qi < ecount; qi += kScanWarps) {
-      const uint32_t c = min(meta.scnt[qi], kStage);
-      if (c == 0) continue;
-      const uint32_t qq = s_q[qi];
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&w.cnt[qq], c);
-      base = __shfl_sync(kFull, base, 0);
-      if ((uint32_t)lane < c) {
-        const uint32_t pos = base + lane;
-        if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = meta.sbuf[qi][lane];
-        else w.ovf[qq] = 1u;
+    if (w.stage) {
+      __syncthreads();
+      for (uint32_t qi = warp; qi < ecount; qi += kScanWarps) {
+        const uint32_t c = min(meta.scnt[qi], kStage);
+        if (c == 0) continue;
+        const uint32_t qq = s_q[qi];
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&w.cnt[qq], c);
+        base = __shfl_sync(kFull, base, 0);
+        if ((uint32_t)lane < c) {
+          const uint32_t pos = base + lane;
+          if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = meta.sbuf[qi][lane];
+          else w.ovf[qq] = 1u;
+        }
       }
     }
+    // hand the pre-claimed item to the next iteration (every thread read s_item before the first barrier of the body)
+    if (tid == 0) s_item = next_item;
   }
 }
 
@@ -973,13 +1003,20 @@ compact_big_kernel(ScanWork w, int dedup, int medium) {
 }
 
 // ---- debug: int16 scores of one leaf under one uint8 LUT ---------------------------------
-template <int W>
+// Runs the MAIN scan's scoring path (oct table, score_oct_addr<W, NL, 0>, the same (W, NL) instantiation launch_scan
+// picks): the LUT sits in oct lane `lane_q` (the other seven tables are zero), so calls with different lanes cover all
+// eight u16 accumulator positions.
+template <int W, int NL>
 __global__ void __launch_bounds__(kScanThreads)
-leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, int16_t* __restrict__ out) {
+leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, int lane_q, uint32_t one,
+                   int16_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);
+  uint2* tables = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(smem) + 127) & ~(uintptr_t)127);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  build_quad_table(tbl, lut, nullptr, nullptr, nullptr, W * 128, tid, kScanThreads);
+  const uint8_t* lp[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) lp[i] = (i == lane_q) ? lut : nullptr;
+  build_oct_table(tables, lp, W * 128, tid, kScanThreads);
   __syncthreads();
   const int nlast = (int)ix.B - 8 * (W - 1);
   const uint32_t gbeg = ix.leaf_goff[leaf], ng = ix.leaf_goff[leaf + 1] - gbeg;
@@ -987,10 +1024,20 @@ leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, 
   for (uint32_t g = blockIdx.x * kScanWarps + warp; g < ng; g += gridDim.x * kScanWarps) {
     uint32_t cw[W];
     load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
-    uint32_t a01, a23;
-    score_quad<W>(cw, reinterpret_cast<const unsigned char*>(tbl), nlast, a01, a23);
+    uint32_t ad[8 * W];
+    const uint32_t tb32 = (uint32_t)__cvta_generic_to_shared(tables);
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        ad[8 * j + k] = tb32 | ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
+    uint32_t acc[4];
+    score_oct_addr<W, NL, 0>(ad, nlast, one, acc);
+    // (s0,s2) (s1,s3) (s4,s6) (s5,s7) as u16 lanes
+    const uint32_t word = acc[((lane_q >> 2) << 1) | (lane_q & 1)];
+    const uint32_t sum = ((lane_q >> 1) & 1) ? (word >> 16) : (word & 0xFFFFu);
     const uint32_t slot = g * 32 + lane;
-    if (slot < n) out[slot] = (int16_t)((int)(a01 & 0xFFFFu) - 128 * (int)ix.B);
+    if (slot < n) out[slot] = (int16_t)((int)sum - 128 * (int)ix.B);
   }
 }
 
@@ -1094,16 +1141,26 @@ cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cu
   return cudaGetLastError();
 }
 
-void launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s) {
-  const size_t smem = (size_t)ix.W * 128 * 4;
-  auto run = [&]() -> cudaError_t {
-    SB_DISPATCH_W(ix.W, {
-      cudaFuncSetAttribute(leaf_scores_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      leaf_scores_kernel<W><<<8, kScanThreads, smem, s>>>(ix, lut, leaf, out);
-    });
-    return cudaSuccess;
-  };
-  run();
+template <int W, int NL>
+static cudaError_t launch_leaf_scores_t(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int lane_q, int16_t* out,
+                                        cudaStream_t s) {
+  const size_t smem = scan_smem_bytes(ix, 1);
+  cudaError_t e = cudaFuncSetAttribute(leaf_scores_kernel<W, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  leaf_scores_kernel<W, NL><<<8, kScanThreads, smem, s>>>(ix, lut, leaf, lane_q, 1u, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s) {
+  const int nlast = (int)ix.B - 8 * ((int)ix.W - 1);
+  const int lane_q = (int)(leaf & 7u);
+  SB_DISPATCH_W(ix.W, {
+    if (nlast == 8) return launch_leaf_scores_t<W, 8>(ix, lut, leaf, lane_q, out, s);
+    if (nlast == 2) return launch_leaf_scores_t<W, 2>(ix, lut, leaf, lane_q, out, s);
+    if (nlast == 4) return launch_leaf_scores_t<W, 4>(ix, lut, leaf, lane_q, out, s);
+    return launch_leaf_scores_t<W, 0>(ix, lut, leaf, lane_q, out, s);
+  });
+  return cudaGetLastError();
 }
 
 }  // namespace sb

@@ -179,11 +179,15 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
   const uint32_t slice = (nq + G - 1) / G, nq_pad = slice * (uint32_t)G;
   const uint32_t cap = pick_cap(p.nover);
   const uint32_t ncand = p.nover;
-  std::vector<RankState> S(R.size());
+  // sampled global threshold: SCANN_B200_SHARD_SAMPLE=0 sends every rank's whole local top-N' instead
+  bool sampled = !light && G > 1;
+  if (const char* e = getenv("SCANN_B200_SHARD_SAMPLE")) sampled = sampled && e[0] != '0';
+  const uint32_t S = (p.nover + 15) / 16;
+  std::vector<RankState> RS(R.size());
   auto each = [&](auto&& f) -> int {
     for (size_t r = 0; r < R.size(); ++r) {
       CU(cudaSetDevice(R[r]->device));
-      if (int rc = f(R[r], S[r], r)) return rc;
+      if (int rc = f(R[r], RS[r], r)) return rc;
     }
     return 0;
   };
@@ -199,6 +203,8 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
         const size_t gk = light ? (size_t)G * nq * out_k : (size_t)nq_pad * out_k;
         CU(ix->sh_idx.ensure(sizeof(uint32_t) * gk));
         CU(ix->sh_dist.ensure(sizeof(float) * gk));
+        CU(ix->sh_samples.ensure(sizeof(uint32_t) * ((size_t)G * nq * S + 4)));
+        CU(ix->sh_limit.ensure(sizeof(uint32_t) * ((size_t)nq + 4)));
         fill_scan_work(ix, nq, p, cap, &st.w);
         sb::ScanWork& w = st.w;
         w.pilot_world = (G > 1 && ix->shard_mode == SCANN_B200_SHARD_BY_LEAF) ? (uint32_t)G : 1u;
@@ -230,7 +236,9 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
         st.launches += 1;
         CU(cudaGetLastError());
         CU(cudaEventRecord(ix->ev[EV_LUT], s));
-        st.two_phase = p.P >= 16 && (uint64_t)p.P * ix->avg_leaf_slots >= 98304;
+        // two scan phases only where this RANK probes many slots per query (leaf sharding: P / world leaves)
+        const uint64_t volume = (uint64_t)p.P * ix->avg_leaf_slots / (w.pilot_world > 1 ? (uint64_t)G : 1ull);
+        st.two_phase = p.P >= 16 && volume >= 49152;
         if (const char* e = getenv("SCANN_B200_TWO_PHASE")) st.two_phase = e[0] == '1' && p.P >= 2;
         const uint32_t r1 = st.two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
         w.rank_lo = 0; w.rank_hi = r1;
@@ -275,48 +283,61 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
           CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
         }
         w.rank_lo = 0; w.rank_hi = p.P;
-        auto finalize = [&]() -> int {
-          sb::FinalizeArgs a{};
-          a.q = d_q[r]; a.nq = nq; a.npre = p.npre; a.k = p.k; a.out_k = out_k;
-          if (light) {
-            a.out_idx = ix->sh_idx.as<uint32_t>() + (size_t)ix->shard_rank * nq * out_k;
-            a.out_dist = ix->sh_dist.as<float>() + (size_t)ix->shard_rank * nq * out_k;
-          } else {
-            a.part_rec = ix->sh_send.as<uint4>();
-            a.part_cap = ncand;
-          }
-          CU(sb::launch_finalize(v, w, a, s));
-          st.launches += 1;
-          return 0;
-        };
-        if (!light && nq_pad > nq)  // records of the padding queries: invalid ids
-          CU(cudaMemsetAsync(ix->sh_send.as<uint4>() + (size_t)nq * ncand, 0xFF, sizeof(uint4) * (size_t)(nq_pad - nq) * ncand, s));
-        if (int rc = finalize()) return rc;
-        CU(cudaEventRecord(ix->ev[EV_FIN], s));
         uint32_t* hc = ix->h_counters.as<uint32_t>();
         unsigned long long* hs = reinterpret_cast<unsigned long long*>(hc + 8);
         CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(hs, w.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         const uint32_t tok_fallbacks = hc[5];
-        if (hc[2] != 0) {  // candidate-buffer overflow: re-scan the flagged queries (local, no collective involved)
-          while (hc[2] != 0) {
-            if (++st.retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
-            CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
-            sb::launch_worklist(v, w, true, false, s, &st.launches);
-            CU(sb::launch_scan(v, w, 0, s));
-            CU(sb::launch_compact(v, w, true, s, &ncl));
-            st.launches += 1 + ncl; st.scan_launches += 1;
-            CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
-            CU(cudaStreamSynchronize(s));
-          }
-          if (int rc = finalize()) return rc;
-          CU(cudaEventRecord(ix->ev[EV_FIN], s));
+        while (hc[2] != 0) {  // candidate-buffer overflow: re-scan the flagged queries (local, no collective involved)
+          if (++st.retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
+          CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));
+          sb::launch_worklist(v, w, true, false, s, &st.launches);
+          CU(sb::launch_scan(v, w, 0, s));
+          CU(sb::launch_compact(v, w, true, s, &ncl));
+          st.launches += 1 + ncl; st.scan_launches += 1;
+          CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+          CU(cudaStreamSynchronize(s));
         }
+        if (sampled) {
+          CU(sb::launch_sample_scores(w, S, ix->sh_samples.as<uint32_t>() + (size_t)ix->shard_rank * nq * S, s));
+          st.launches += 1;
+        }
+        CU(cudaEventRecord(ix->ev[EV_S0], s));
         scann_b200_stats& ls = ix->last;
         ls.scan_bytes_alg += hs[0]; ls.scan_pairs += hs[1]; ls.scan_lookups += hs[0] * 2;
         ls.cand_sum += hs[2]; ls.cand_max = std::max<uint64_t>(ls.cand_max, hs[3]);
         ls.tokenize_fallbacks += tok_fallbacks;
+        return 0;
+      })) return rc;
+
+  // 3b. sampled global threshold (parity mode, world > 1): all-gather every 16th local score, threshold per query
+  if (int rc = mark(EV_C8)) return rc;
+  if (sampled)
+    if (int rc = coll.allgather(ptrs([](scann_b200_index* ix) { return ix->sh_samples.p; }), sizeof(uint32_t) * (size_t)nq * S)) return rc;
+  if (int rc = mark(EV_C9)) return rc;
+  if (int rc = each([&](scann_b200_index* ix, RankState& st, size_t r) -> int {
+        sb::ScanWork& w = st.w;
+        cudaStream_t s = ix->stream;
+        sb::FinalizeArgs a{};
+        a.q = d_q[r]; a.nq = nq; a.npre = p.npre; a.k = p.k; a.out_k = out_k;
+        if (light) {
+          a.out_idx = ix->sh_idx.as<uint32_t>() + (size_t)ix->shard_rank * nq * out_k;
+          a.out_dist = ix->sh_dist.as<float>() + (size_t)ix->shard_rank * nq * out_k;
+        } else {
+          a.part_rec = ix->sh_send.as<uint4>();
+          a.part_cap = ncand;
+          if (sampled) {
+            CU(sb::launch_sample_threshold(ix->sh_samples.as<uint32_t>(), G, nq, S, p.nover, ix->sh_limit.as<uint32_t>(), s));
+            st.launches += 1;
+            a.part_limit = ix->sh_limit.as<uint32_t>();
+          }
+          if (nq_pad > nq)  // records of the padding queries: invalid ids
+            CU(cudaMemsetAsync(ix->sh_send.as<uint4>() + (size_t)nq * ncand, 0xFF, sizeof(uint4) * (size_t)(nq_pad - nq) * ncand, s));
+        }
+        CU(sb::launch_finalize(ix->dev, w, a, s));
+        st.launches += 1;
+        CU(cudaEventRecord(ix->ev[EV_FIN], s));
         return 0;
       })) return rc;
 
@@ -383,10 +404,8 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
       if (int rc = el(EV2_WORK, EV2_SCAN, &t)) return rc; ls.ms_scan += t;
       if (int rc = el(EV2_SCAN, EV2_COMPACT, &t)) return rc; ls.ms_compact += t;
     }
-    if (st.retries == 0) {  // a re-scan re-records EV_FIN; its time goes to the total only
-      if (int rc = el(st.two_phase ? EV2_COMPACT : EV_COMPACT, EV_FIN, &t)) return rc; ls.ms_finalize += t;
-    }
-    for (int c = 0; c < 4; ++c) { if (int rc = el(EV_C0 + 2 * c, EV_C0 + 2 * c + 1, &t)) return rc; x += t; }
+    if (int rc = el(EV_C9, EV_FIN, &t)) return rc; ls.ms_finalize += t;
+    for (int c = 0; c < 5; ++c) { if (int rc = el(EV_C0 + 2 * c, EV_C0 + 2 * c + 1, &t)) return rc; x += t; }
     if (int rc = el(EV_M0, EV_M1, &t)) return rc;
     ls.ms_merge += t;
     ls.ms_exchange += x;
@@ -426,7 +445,12 @@ int sharded_search(std::vector<scann_b200_index*>& R, bool local, const float* d
   if ((long long)G * p.nover > 8192 && !light)
     return fail(SCANN_B200_UNIMPLEMENTED, "merge of %d x %u candidates too large", G, p.nover);
   std::vector<std::unique_lock<std::mutex>> locks;
-  for (auto* ix : R) { locks.emplace_back(ix->mu); ix->last = scann_b200_stats{}; }
+  for (auto* ix : R) {
+    locks.emplace_back(ix->mu);
+    ix->last = scann_b200_stats{};
+    std::lock_guard<std::mutex> lk(ix->pool_mu);
+    ix->last_any_valid = false;
+  }
   const uint32_t D = R[0]->dev.d;
   std::vector<uint32_t*> oi(R.size(), nullptr);
   std::vector<float*> od(R.size(), nullptr);

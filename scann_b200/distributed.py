@@ -92,6 +92,31 @@ def merge_partials_reference(ids, tie, exact, nover, npre, k, disjoint, dot_prod
 SHARD_BY_ID, SHARD_BY_LEAF = 0, 1
 
 
+def sampled_threshold_reference(rank_scores, nover):
+  """Host statement of the sampled global threshold (csrc/finalize.cu sample_scores_kernel / sample_threshold_kernel).
+
+  rank_scores: one ascending array of score words (f2ord of the AH score) per rank = that rank's local candidate list.
+  Every rank samples positions 15, 31, ... of its list (at most nover entries); the ceil(nover / 16)-th smallest sample
+  over all ranks bounds the global nover-th best score from above.  Returns that bound (0xFFFFFFFF: no pruning)."""
+  need = (nover + 15) // 16
+  samples = []
+  for s in rank_scores:
+    s = np.asarray(s, dtype=np.uint32)[:nover]
+    samples.extend(s[15::16].tolist())
+  samples.sort()
+  return samples[need - 1] if len(samples) >= need else 0xFFFFFFFF
+
+
+def owner_of_query(q, nq, world):
+  """Rank that tokenizes and merges query q of a batch of nq (contiguous slices of ceil(nq / world) queries)."""
+  return q // (-(-nq // world))
+
+
+def leaf_owner(leaf, world):
+  """Leaf sharding: the rank that stores (and scans) a leaf."""
+  return leaf % world
+
+
 class ShardedIndex:
   """One rank (one process, one GPU) of a database-sharded tree-AH searcher.
 

@@ -156,3 +156,32 @@ def test_int8_reordering_through_the_builder(tmp_path):
     i2, d2 = l2.search_batched(q)
     np.testing.assert_array_equal(idx, i2)
     np.testing.assert_array_equal(dist_v.view(np.uint32), d2.view(np.uint32))
+
+
+def test_concurrent_search_batched_on_one_handle():
+  """ScannInterface::SearchBatched may be called from several threads (scann_ops/cc/scann.cc:478-501): concurrent calls on
+  one handle run on separate lanes (own stream + workspace) and return exactly what serial calls return."""
+  import threading
+  from conftest import get_case
+  c = get_case(soar=1.5)
+  want_i, want_d = c.native.search_batched(c.q)
+  results = {}
+
+  def worker(t):
+    out = []
+    for rep in range(6):
+      lo = (t * 7 + rep * 3) % 40
+      out.append((lo, c.native.search_batched(c.q[lo:lo + 24])))
+    results[t] = out
+
+  threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]   # more threads than lanes: some wait
+  for th in threads:
+    th.start()
+  for th in threads:
+    th.join()
+  assert len(results) == 6
+  for t, out in results.items():
+    for lo, (i, d) in out:
+      np.testing.assert_array_equal(i, want_i[lo:lo + 24])
+      np.testing.assert_array_equal(d.view(np.uint32), want_d[lo:lo + 24].view(np.uint32))
+  assert c.native.stats()["kernel_launches"] >= 8

@@ -99,3 +99,81 @@ def test_c2_index_build_properties_and_oracle_sample(monkeypatch):
   n_p, p_p = err(cp)
   n_s, p_s = err(cs)
   assert n_s >= n_p and p_s < p_p
+
+
+# ---- the other BASELINE.json configurations at their own sizes (only C2 had a full-size oracle check) ------
+
+def _tree_ah_fullsize(name, n_oracle_queries, overrides=None):
+  """Builds the bench workload `name` exactly as bench.py does, searches all its queries on the GPU, and compares an
+  oracle run on the first n_oracle_queries bit for bit."""
+  import bench
+  import oracle
+  from scann_b200 import _lib
+  wl = dict(bench.WORKLOADS[name])
+  wl.update(overrides or {})
+  db, q = bench.make_data(wl)
+  arrays = bench.build_arrays(wl, db, "cuda:0")
+  ix = _lib.NativeIndex(arrays, wl["probe"], wl["pre"], wl["k"])
+  idx, dist = ix.search_batched(q)
+  st = ix.stats()
+  oi = oracle.OracleIndex(arrays, wl["probe"], wl["pre"], wl["k"])
+  m = min(n_oracle_queries, wl["nq"])
+  oidx, odist = oi.search_batched(q[:m], impl=1, threads=16)
+  np.testing.assert_array_equal(idx[:m], oidx)
+  np.testing.assert_array_equal(dist[:m].view(np.uint32), odist.view(np.uint32))
+  # the scalar oracle path (impl 0) on a few queries as well: the AVX2 path is itself only a restatement
+  o2, d2 = oi.search_batched(q[:8], impl=0)
+  np.testing.assert_array_equal(idx[:8], o2)
+  np.testing.assert_array_equal(dist[:8].view(np.uint32), d2.view(np.uint32))
+  assert not np.isnan(dist).any() and all(len(set(r.tolist())) == wl["k"] for r in idx[:1000])
+  # reported distances against float64 on the rows themselves (tolerance of the north star: 1e-5 relative)
+  sel = np.arange(0, wl["nq"], 50)
+  rows = db[idx[sel].astype(np.int64)].astype(np.float64)
+  if wl.get("distance") == "squared_l2":
+    truth = ((rows - q[sel].astype(np.float64)[:, None, :]) ** 2).sum(2)
+    assert (np.diff(dist, axis=1) >= 0).all()
+  else:
+    truth = np.einsum("qd,qkd->qk", q[sel].astype(np.float64), rows)
+    assert (np.diff(dist, axis=1) <= 0).all()
+  np.testing.assert_allclose(dist[sel], truth, rtol=1e-5, atol=1e-5 * float(np.abs(truth).max()))
+  ix.close()
+  return wl, st
+
+
+def test_c1_all_queries_against_the_oracle():
+  """BASELINE.json configs[0]: 100k x 100, 100 leaves, reorder 100, k = 10 -- every one of the 10,000 queries."""
+  wl, st = _tree_ah_fullsize("c1_synthetic", 10000)
+  assert st["overflow_retries"] == 0
+
+
+def test_c4_sift_shape_against_the_oracle():
+  """BASELINE.json configs[3] shape: 10M x 128 squared L2 (TreeXHybridSMMD semantics), 4000 leaves, 64 probed."""
+  wl, st = _tree_ah_fullsize("c4_sift_shape", 64)
+  assert st["scan_bytes_alg"] > 0
+
+
+def test_c5_deep_shape_against_the_oracle():
+  """BASELINE.json configs[4] shape at 20M rows: 96-d, SOAR, reorder 200 (400 over-retrieved), 24 of 8000 leaves: the
+  two-phase scan and the per-item candidate staging are active at this size."""
+  wl, st = _tree_ah_fullsize("c5_deep_shape", 64)
+  assert st["scan_kernel_count"] >= 2     # two scan phases
+  assert st["cand_sum"] / wl["nq"] > 400  # more candidates buffered than kept: the compaction classes are exercised
+
+
+def test_c3_bruteforce_bf16_against_the_oracle():
+  """BASELINE.json configs[2]: 1M x 768 bf16 rows, k = 100: 32 queries against the oracle's exact f32 x bf16 scan, all
+  10,000 for the invariants (sorted, unique ids, no widening needed on i.i.d. data)."""
+  import bench
+  import oracle
+  from scann_b200 import _lib
+  wl = dict(bench.WORKLOADS["c3_bruteforce_bf16"])
+  a, bits, q = bench.bruteforce_data(wl, 16)
+  ix = _lib.NativeIndex(a, 1, wl["k"], wl["k"])
+  idx, dist = ix.search_batched(q)
+  st = ix.stats()
+  oi, od = oracle.bruteforce_bf16(bits, q[:32], wl["k"], threads=16)
+  np.testing.assert_array_equal(idx[:32], oi)
+  np.testing.assert_array_equal(dist[:32].view(np.uint32), od.view(np.uint32))
+  assert (np.diff(dist, axis=1) <= 0).all() and all(len(set(r.tolist())) == wl["k"] for r in idx[:500])
+  assert st["bf_widenings"] == 0 and st["bf_exact_fallbacks"] == 0
+  ix.close()

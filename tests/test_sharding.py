@@ -140,3 +140,55 @@ def test_two_gloo_ranks_row_sharded_bruteforce(tmp_path):
     got = np.load(os.path.join(str(tmp_path), f"bf{r}.npz"))
     np.testing.assert_array_equal(got["idx"], got["full_idx"])
     np.testing.assert_array_equal(got["dist"].view(np.uint32), got["full_dist"].view(np.uint32))
+
+
+# ---- host logic of the C++ sharded protocol (csrc/sharded.cu), no GPU needed ----------------------------------------------
+
+@pytest.mark.parametrize("world,nover", [(2, 400), (8, 400), (3, 100), (8, 17), (4, 16), (5, 1)])
+def test_sampled_threshold_is_a_valid_and_tight_bound(world, nover):
+  """The ceil(N'/16)-th smallest of the ranks' every-16th scores is >= the global N'-th best score (nothing needed is
+  dropped) and at most N' + 15 world candidates (+ ties) lie at or below it (little is sent in vain)."""
+  rng = np.random.default_rng(world * 1000 + nover)
+  for trial in range(50):
+    sizes = rng.integers(0, 3 * nover, world)
+    if trial % 7 == 0:
+      sizes[rng.integers(0, world)] = 4 * nover      # everything on one rank
+    if trial % 11 == 0:
+      sizes[:] = rng.integers(0, 8, world)           # fewer than N' candidates in total
+    lists = [np.sort(rng.integers(0, 1 << (10 if trial % 3 else 28), int(n)).astype(np.uint32)) for n in sizes]
+    t = sd.sampled_threshold_reference(lists, nover)
+    allv = np.sort(np.concatenate(lists)) if sum(sizes) else np.empty(0, np.uint32)
+    if len(allv) >= nover and t != 0xFFFFFFFF:
+      assert allv[nover - 1] <= t                    # the global N'-th best survives
+      kept = sum(int(np.searchsorted(l[:nover], t, side="right")) for l in lists)
+      ties = int((allv == t).sum())
+      assert kept <= nover + 15 * world + ties
+    if t == 0xFFFFFFFF:
+      # no pruning only when the samples cannot prove N' candidates exist
+      assert sum(len(l[:nover]) // 16 for l in lists) < (nover + 15) // 16
+
+
+def test_query_and_leaf_ownership_cover_everything_once():
+  for world in (1, 2, 3, 8):
+    for nq in (1, 2, 7, 64, 10000):
+      owners = [sd.owner_of_query(q, nq, world) for q in range(nq)]
+      assert min(owners) >= 0 and max(owners) < world and owners == sorted(owners)
+      sl = -(-nq // world)
+      assert all(owners.count(r) <= sl for r in range(world))
+    assert sorted(set(sd.leaf_owner(l, world) for l in range(100))) == list(range(min(world, 100)))
+
+
+def test_sharded_protocol_symbols_and_nccl_id():
+  """The C ABI exports the sharded entry points; the NCCL id call works without a GPU (it only loads libnccl)."""
+  import ctypes as C
+  from scann_b200 import _lib
+  L = _lib.lib()
+  for name in ("scann_b200_comm_unique_id", "scann_b200_comm_init", "scann_b200_search_sharded_device",
+               "scann_b200_search_sharded_local"):
+    assert hasattr(L, name)
+  buf = (C.c_uint8 * 128)()
+  rc = L.scann_b200_comm_unique_id(buf)
+  assert rc in (0, 9)                                # 9: libnccl.so.2 not loadable on this host
+  if rc == 0:
+    assert any(buf)
+  assert L.scann_b200_comm_init(None, 0, 1, None) == 3
