@@ -207,6 +207,35 @@ typedef struct {
 int scann_b200_encode_database(const scann_b200_encode_desc* desc, int32_t* tokens_out, uint8_t* codes_out,
                                uint8_t* soar_codes_out, scann_b200_encode_stats* stats);
 
+/* ---- index construction, training ---- */
+
+/*
+ * Lloyd iterations of the k-means trainers: KMeansTreePartitioner::TrainKMeans (partitioning/kmeans_tree_partitioner.cc:
+ * 424-441) -> GmmUtils::GenericKmeans (utils/gmm_utils.cc:846-915: assignment with UnbalancedFloat32PartitionAssignment,
+ * RecomputeCentroidsSimple :1052-1132), and the 16-centre AH codebooks per block (hashes/internal/
+ * asymmetric_hashing_impl.cc:41-197).  Deterministic: the result is a function of (data, init_centers, iterations).
+ * The caller supplies the initial centres (the reference draws them from an unseeded generator); a cluster that ends an
+ * iteration empty keeps its centre (the reference re-initialises small clusters randomly).  Host pointers in / out.
+ */
+typedef struct {
+  uint32_t n, d, k;            /* training points, dimensionality, clusters (k <= n) */
+  const float* data;           /* [n][d] */
+  const float* init_centers;   /* [k][d] */
+  int32_t iterations;          /* centroid recomputations (GmmUtils::Options::max_iterations) */
+  int32_t device;
+} scann_b200_kmeans_desc;
+
+typedef struct {
+  float ms_assign, ms_update, ms_total;  /* CUDA events */
+  uint32_t iterations;
+  uint32_t empty_clusters;     /* clusters that were empty in the last recomputation */
+  double mean_sq_distance;     /* mean squared distance of the final assignment (0 when assign_out is NULL) */
+} scann_b200_kmeans_stats;
+
+/* centers_out [k][d]; assign_out [n] (the final partition: nearest centre of every point) or NULL; stats may be NULL. */
+int scann_b200_train_kmeans(const scann_b200_kmeans_desc* desc, float* centers_out, int32_t* assign_out,
+                            scann_b200_kmeans_stats* stats);
+
 /* ---- serialized assets (the reference's on-disk format) ---- */
 
 typedef struct scann_b200_assets scann_b200_assets;

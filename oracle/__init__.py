@@ -300,3 +300,18 @@ def encode_database(x, centers, codebook, block_dims=None, residual=True, soar_l
   codes, ties0 = encode(x, codebook, block_dims, cen, lo, threshold, threads)
   soar_codes, ties1 = encode(x, codebook, block_dims, cen, hi, threshold, threads)
   return tokens, codes, soar_codes, ties0 + ties1
+
+
+def kmeans(x, init_centers, iterations, threads=1, want_assignment=True):
+  """so_kmeans: (centers [k, d] f32, assignment [n] i32 or None, empty clusters of the last iteration)."""
+  L = lib()
+  L.so_kmeans.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  c = np.array(init_centers, dtype=np.float32, copy=True, order="C")
+  assign = np.empty(x.shape[0], np.int32) if want_assignment else None
+  empty = np.zeros(1, np.uint32)
+  rc = L.so_kmeans(_p(x), x.shape[0], x.shape[1], _p(c), c.shape[0], int(iterations), _p(assign) if assign is not None else None,
+                   _p(empty), threads)
+  if rc:
+    raise RuntimeError(L.so_last_error().decode())
+  return c, assign, int(empty[0])

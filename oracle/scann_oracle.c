@@ -1405,3 +1405,54 @@ int so_encode(const float* x, uint32_t n, uint32_t d, const float* centers, cons
   free(bd); free(bo);
   return 0;
 }
+
+
+/* ------------------------------------------------------------------------- */
+/* k-means training: Lloyd iterations                    */
+/* ------------------------------------------------------------------------- */
+
+/* GmmUtils main loop (utils/gmm_utils.cc:846-915) with UNBALANCED_FLOAT32 assignment and
+ * RecomputeCentroidsSimple (:1052-1132): assignment = first minimum of the float many-to-many squared-L2 chain
+ * (so_assign_primary); centroid = double sums over the members in index order inside kParallelAggregate = 4 contiguous
+ * slices of the training set (one slice when n < 8 k, :1064-1065), slice sums added in slice order into a zeroed
+ * accumulator, times double(1.0 / count) (NormalizeCentroid :1038-1048), stored as float for the next assignment.
+ * An empty cluster keeps its centre (the reference re-initialises it randomly; see csrc/train.cu).
+ * centers: [k][d] in / out; assign_out [n] = the final partition (may be NULL). */
+int so_kmeans(const float* x, uint32_t n, uint32_t d, float* centers, uint32_t k, int iterations, int32_t* assign_out,
+              uint32_t* empty_out, int threads) {
+  if (!n || !d || !k || k > n) return fail("so_kmeans: bad sizes");
+  int32_t* assign = (int32_t*)malloc(sizeof(int32_t) * n);
+  const uint32_t slices = ((uint64_t)n >= (uint64_t)k * 8) ? 4u : 1u;
+  const uint32_t per = (n + slices - 1) / slices;
+  double* part = (double*)malloc(sizeof(double) * (size_t)slices * k * d);
+  uint32_t* cnt = (uint32_t*)malloc(sizeof(uint32_t) * k);
+  uint32_t empty = 0;
+  for (int it = 0; it < iterations; ++it) {
+    so_assign_primary(x, n, d, centers, k, assign, NULL, threads);
+    memset(part, 0, sizeof(double) * (size_t)slices * k * d);
+    memset(cnt, 0, sizeof(uint32_t) * k);
+    for (uint32_t t = 0; t < slices; ++t) {
+      const uint32_t lo = t * per, hi = (lo + per < n) ? lo + per : n;
+      for (uint32_t i = lo; i < hi; ++i) {
+        double* acc = part + ((size_t)t * k + (uint32_t)assign[i]) * d;
+        const float* row = x + (size_t)i * d;
+        for (uint32_t j = 0; j < d; ++j) acc[j] += (double)row[j];
+        cnt[assign[i]]++;
+      }
+    }
+    empty = 0;
+    for (uint32_t c = 0; c < k; ++c) {
+      if (!cnt[c]) { ++empty; continue; }
+      const double mult = 1.0 / (double)cnt[c];
+      for (uint32_t j = 0; j < d; ++j) {
+        double sum = 0.0;
+        for (uint32_t t = 0; t < slices; ++t) sum += part[((size_t)t * k + c) * d + j];
+        centers[(size_t)c * d + j] = (float)(sum * mult);
+      }
+    }
+  }
+  if (assign_out) so_assign_primary(x, n, d, centers, k, assign_out, NULL, threads);
+  if (empty_out) *empty_out = empty;
+  free(assign); free(part); free(cnt);
+  return 0;
+}

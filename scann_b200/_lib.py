@@ -67,6 +67,19 @@ class EncodeStats(C.Structure):
     return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class KMeansDesc(C.Structure):
+  _fields_ = [("n", C.c_uint32), ("d", C.c_uint32), ("k", C.c_uint32), ("data", C.c_void_p), ("init_centers", C.c_void_p),
+              ("iterations", C.c_int32), ("device", C.c_int32)]
+
+
+class KMeansStats(C.Structure):
+  _fields_ = [("ms_assign", C.c_float), ("ms_update", C.c_float), ("ms_total", C.c_float), ("iterations", C.c_uint32),
+              ("empty_clusters", C.c_uint32), ("mean_sq_distance", C.c_double)]
+
+  def as_dict(self):
+    return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 EXPORTS = [
     "scann_b200_index_create", "scann_b200_index_destroy", "scann_b200_search_batched",
     "scann_b200_search_batched_device", "scann_b200_search_partial_device",
@@ -78,7 +91,7 @@ EXPORTS = [
     "scann_b200_debug_candidates", "scann_b200_leaf_size", "scann_b200_last_stats",
     "scann_b200_assets_load", "scann_b200_assets_free", "scann_b200_assets_describe",
     "scann_b200_assets_config", "scann_b200_assets_save", "scann_b200_config_text_to_binary",
-    "scann_b200_config_binary_to_text", "scann_b200_encode_database",
+    "scann_b200_config_binary_to_text", "scann_b200_encode_database", "scann_b200_train_kmeans",
 ]
 
 
@@ -128,6 +141,7 @@ def lib():
   L.scann_b200_config_text_to_binary.argtypes = [C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
   L.scann_b200_config_binary_to_text.argtypes = [vp, C.c_size_t, C.c_char_p, C.c_size_t]
   L.scann_b200_encode_database.argtypes = [C.POINTER(EncodeDesc), vp, vp, vp, C.POINTER(EncodeStats)]
+  L.scann_b200_train_kmeans.argtypes = [C.POINTER(KMeansDesc), vp, vp, C.POINTER(KMeansStats)]
   _LIB = L
   return L
 
@@ -306,3 +320,20 @@ def encode_database(dataset, centers, codebook, block_dims=None, residual=True, 
   st = EncodeStats()
   check(lib().scann_b200_encode_database(C.byref(desc), ptr(tokens), ptr(codes), ptr(soar_codes), C.byref(st)))
   return tokens, codes, soar_codes, st.as_dict()
+
+
+def train_kmeans(data, init_centers, iterations, device=0, want_assignment=True):
+  """scann_b200_train_kmeans: Lloyd iterations on the GPU (assignment = the tokenizer with P = 1, centroid update in the
+  reference's double arithmetic, deterministic).  Returns (centers [k, d] f32, assignment [n] i32 or None, stats)."""
+  x = np.ascontiguousarray(data, dtype=np.float32)
+  c0 = np.ascontiguousarray(init_centers, dtype=np.float32)
+  n, d = x.shape
+  k = c0.shape[0]
+  desc = KMeansDesc()
+  desc.n, desc.d, desc.k, desc.data, desc.init_centers = n, d, k, ptr(x), ptr(c0)
+  desc.iterations, desc.device = int(iterations), device
+  centers = np.empty((k, d), np.float32)
+  assign = np.empty(n, np.int32) if want_assignment else None
+  st = KMeansStats()
+  check(lib().scann_b200_train_kmeans(C.byref(desc), ptr(centers), ptr(assign), C.byref(st)))
+  return centers, assign, st.as_dict()

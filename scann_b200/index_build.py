@@ -3,8 +3,8 @@
 This is the part of `builder(...).build()` that sits *before* the hot path
 (SURVEY.md §3.2, §8f rank 1): it only has to produce assets in the reference's
 format so that the query path has something to search.  It is written with
-torch so that the same code runs on the CPU here and on `cuda:0` on the GPU box
-(index build is not the product of this repository; the query path is).
+torch so that CPU-only test fixtures can be generated here; on a CUDA device the trainers
+(`scann_b200_train_kmeans`) and the per-datapoint stage (`scann_b200_encode_database`) run in the library.
 
 What it mirrors in the reference (behaviour, not code):
   * k-means partitioner with SquaredL2 partitioning distance
@@ -70,12 +70,55 @@ def _sqdist_argmin(x, centers, c_norms=None, chunk=65536, exclude=None, return_d
   return (out, dist) if return_dist else out
 
 
+def _use_native_trainer(device, spherical=False):
+  """The library's trainer (csrc/train.cu) runs whenever a CUDA device is the target; torch only serves CPU-only
+  fixtures (device="cpu") and spherical k-means (the library does not normalise centroids)."""
+  return (not spherical) and torch.cuda.is_available() and _dev(device).type == "cuda"
+
+
+def _reseed_empty(x, centers, assign, device_index, extra_iters=2, rounds=4):
+  """The library keeps an empty cluster's centre (the reference re-initialises it from an unseeded generator,
+  `utils/gmm_utils.cc:1204-1330`); here empty clusters restart from the points farthest from their centre, followed by
+  `extra_iters` more Lloyd iterations, so every leaf ends up non-empty when N >= k."""
+  from scann_b200 import _lib
+  k = centers.shape[0]
+  for _ in range(rounds):
+    empty = np.flatnonzero(np.bincount(assign, minlength=k) == 0)
+    if not len(empty):
+      break
+    diff = x - centers[assign]
+    far = np.argsort(-np.einsum("ij,ij->i", diff, diff), kind="stable")[:len(empty)]
+    centers = centers.copy()
+    centers[empty] = x[far]
+    centers, assign, _ = _lib.train_kmeans(x, centers, extra_iters, device=device_index)
+  return centers, assign
+
+
+def train_kmeans_native(x, k, iters=12, seed=0, device=None):
+  """`scann_b200_train_kmeans` (csrc/train.cu): tensor-core assignment + the reference's double-precision centroid
+  update; initial centres = a seeded sample of the data (the reference's k-means++ draws from an unseeded generator)."""
+  from scann_b200 import _lib
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  n = x.shape[0]
+  if k > n:
+    raise ValueError(f"k={k} > n={n}")
+  dev_index = _dev(device).index or 0
+  g = torch.Generator(device="cpu").manual_seed(seed)
+  init = x[torch.randperm(n, generator=g)[:k].numpy()]
+  centers, assign, _ = _lib.train_kmeans(x, init, iters, device=dev_index)
+  centers, _ = _reseed_empty(x, centers, assign, dev_index)
+  return centers
+
+
 def train_kmeans(x, k, iters=12, seed=0, spherical=False, device=None):
-  """Plain Lloyd iterations, random initialisation from the data.
+  """Lloyd iterations, random initialisation from the data: the library's trainer on a CUDA device, plain torch
+  otherwise (CPU-only test fixtures, spherical k-means).
 
   Empty clusters are re-seeded from the points currently farthest from their
   centre, so every leaf ends up non-empty when N >= k.
   """
+  if _use_native_trainer(device, spherical):
+    return train_kmeans_native(x, k, iters=iters, seed=seed, device=device)
   dev = _dev(device)
   x = torch.as_tensor(x, device=dev, dtype=torch.float32)
   n = x.shape[0]
@@ -152,8 +195,36 @@ def _to_blocks(x, block_dims, dpb):
   return x.view(n, b, dpb).permute(1, 0, 2).contiguous()
 
 
+def train_ah_codebook_native(x, dims_per_block, iters=10, seed=0, sample=100000, device=None):
+  """One `scann_b200_train_kmeans` call per block (16 centres over the block's real dims,
+  `hashes/internal/asymmetric_hashing_impl.cc:41-197`) -> ([B, 16, dpb] f32 zero padded, block_dims)."""
+  from scann_b200 import _lib
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  n, d = x.shape
+  block_dims = block_layout(d, dims_per_block)
+  g = np.random.default_rng(seed)
+  xs = x[np.sort(g.choice(n, size=sample, replace=False))] if n > sample else x
+  ns = xs.shape[0]
+  init = g.choice(ns, size=16, replace=ns < 16)
+  dev_index = _dev(device).index or 0
+  cb = np.zeros((len(block_dims), 16, dims_per_block), np.float32)
+  off = 0
+  for b, bd in enumerate(block_dims):
+    sub = np.ascontiguousarray(xs[:, off:off + bd])
+    if ns >= 16:
+      c, a, _ = _lib.train_kmeans(sub, sub[init], iters, device=dev_index)
+      c, _ = _reseed_empty(sub, c, a, dev_index)
+    else:
+      c = sub[init]
+    cb[b, :, :bd] = c
+    off += bd
+  return cb, block_dims
+
+
 def train_ah_codebook(x, dims_per_block, iters=10, seed=0, sample=100000, device=None):
   """16-centre k-means per block on (residual) sub-vectors -> [B, 16, dpb] f32."""
+  if _use_native_trainer(device):
+    return train_ah_codebook_native(x, dims_per_block, iters=iters, seed=seed, sample=sample, device=device)
   dev = _dev(device)
   n, d = x.shape
   block_dims = block_layout(d, dims_per_block)
@@ -256,7 +327,9 @@ def build_tree_ah(db, distance="dot_product", num_leaves=100, dims_per_block=2,
                   native_encode=None):
   """tree().score_ah() index: returns IndexArrays (the serialized asset set).
 
-  Training (k-means tree, AH codebooks) is torch; the per-datapoint stage -- database tokenization, SOAR
+  Training (k-means tree, AH codebooks) runs through the C ABI on a CUDA device (`scann_b200_train_kmeans`,
+  csrc/train.cu; torch Lloyd iterations only for device="cpu" fixtures and spherical k-means); the per-datapoint
+  stage -- database tokenization, SOAR
   secondary assignment, residuals, AH encoding incl. noise shaping -- runs through the C ABI
   (`scann_b200_encode_database`, csrc/encode.cu) whenever a CUDA device is present (`native_encode=None`)
   and reproduces the reference's arithmetic bit for bit.  The torch encoder below it is only what CPU-only
@@ -278,6 +351,7 @@ def build_tree_ah(db, distance="dot_product", num_leaves=100, dims_per_block=2,
                          spherical=spherical, device=device)
   arr = IndexArrays(distance=distance, dataset=db if keep_dataset else None, n=n, d=d)
   arr.centers = centers.astype(np.float32)
+  arr.meta["trainer"] = "scann_b200_train_kmeans" if _use_native_trainer(device, spherical) else "torch"
   arr.residual = residual
   if native_encode is None:
     native_encode = torch.cuda.is_available()

@@ -283,3 +283,48 @@ def test_oracle_reproduces_build_golden(name):
   if soar is not None:
     np.testing.assert_array_equal(soar_codes, z["exp_soar_codes"])
   assert ties == int(z["exp_ties"])
+
+
+def _kmeans_numpy(x, centers, iterations):
+  """GmmUtils' loop restated with numpy: float32 first-minimum assignment through oracle.assign_primary, then double
+  sums in index order inside 4 contiguous slices (1 when n < 8 k), slice sums added in slice order, times 1.0 / count."""
+  import oracle
+  n, d = x.shape
+  k = centers.shape[0]
+  c = centers.copy()
+  slices = 4 if n >= 8 * k else 1
+  per = (n + slices - 1) // slices
+  for _ in range(iterations):
+    a, _ = oracle.assign_primary(x, c, threads=2)
+    for j in range(k):
+      total = np.zeros(d, np.float64)
+      cnt = 0
+      for t in range(slices):
+        lo, hi = t * per, min(n, (t + 1) * per)
+        m = np.flatnonzero(a[lo:hi] == j) + lo
+        part = np.zeros(d, np.float64)
+        for i in m:                      # index order, one add at a time
+          part += x[i].astype(np.float64)
+        total += part
+        cnt += len(m)
+      if cnt:
+        c[j] = (total * (1.0 / cnt)).astype(np.float32)
+  a, _ = oracle.assign_primary(x, c, threads=2)
+  return c, a
+
+
+@pytest.mark.parametrize("n,d,k,iters", [(600, 6, 16, 3), (100, 5, 16, 2), (900, 33, 40, 2)])
+def test_kmeans_matches_numpy_restatement(n, d, k, iters):
+  import oracle
+  rng = np.random.default_rng(n + k)
+  means = rng.standard_normal((k, d)).astype(np.float32)
+  x = (means[rng.integers(0, k, n)] + 0.5 * rng.standard_normal((n, d))).astype(np.float32)
+  init = x[np.sort(rng.choice(n, k, replace=False))].copy()
+  c, a, empty = oracle.kmeans(x, init, iters, threads=2)
+  c_ref, a_ref = _kmeans_numpy(x, init, iters)
+  assert np.array_equal(c.view(np.uint32), c_ref.view(np.uint32))
+  assert np.array_equal(a, a_ref)
+  # Lloyd iterations never raise the distortion
+  d0 = ((x - init[oracle.assign_primary(x, init)[0]]) ** 2).sum()
+  d1 = ((x - c[a]) ** 2).sum()
+  assert d1 <= d0
