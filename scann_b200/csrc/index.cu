@@ -428,6 +428,7 @@ void fill_scan_work(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_t
   {
     const double leaves = std::max<double>(1.0, ix->nonempty_leaves);
     const double qpl = (double)nq * p.P * (ix->shard_mode == SCANN_B200_SHARD_BY_LEAF ? 1.0 / ix->shard_world : 1.0) / leaves;
+    w.qpl_per_rank = (float)(qpl / std::max<uint32_t>(1u, p.P));
     const double hit = leaves * (1.0 - exp(-qpl));
     const double chunks = std::max(1.0, ceil(qpl / 16.0));
     const double groups = std::max(1.0, ix->avg_leaf_slots / 32.0);
@@ -503,8 +504,10 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   // 10.3k -> candidates per query); for C2-size work the extra launches cost more than they save.
   bool two_phase = p.P >= 16 && (uint64_t)p.P * ix->avg_leaf_slots >= 98304;
   if (const char* e = getenv("SCANN_B200_TWO_PHASE")) two_phase = e[0] == '1' && p.P >= 2;
-  const uint32_t r1 = two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
+  uint32_t r1 = two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
+  if (const char* e = getenv("SCANN_B200_PHASE1_RANKS")) { const int t = atoi(e); if (two_phase && t >= 1 && (uint32_t)t < p.P) r1 = (uint32_t)t; }
   w.rank_lo = 0; w.rank_hi = r1;
+  sb::scan_prepare_phase(&w);
   CU(sb::launch_pilot(v, w, s));
   launches += 1;
   CU(cudaEventRecord(ix->ev[EV_PILOT], s));
@@ -520,6 +523,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
   if (two_phase) {
     w.rank_lo = r1; w.rank_hi = p.P;
+    sb::scan_prepare_phase(&w);
     sb::launch_worklist(v, w, false, false, s, &launches);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ix->ev[EV2_WORK], s));
@@ -531,6 +535,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
     CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
   }
   w.rank_lo = 0; w.rank_hi = p.P;  // re-scans of overflowed queries cover every probed leaf
+  sb::scan_prepare_phase(&w);
   // Overflow flag, statistics and the finalize kernel share ONE host round trip: finalize is launched
   // optimistically; if some buffer overflowed (rare) its output is discarded, the flagged queries are
   // re-scanned and finalize runs again.

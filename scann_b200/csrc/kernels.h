@@ -87,6 +87,8 @@ struct ScanWork {
   uint32_t max_gpt;           // groups per work item of the main scan (0 = kMaxGroupsPerTile)
   uint32_t* item_leaf;        // [item_leaf_cap] leaf of each work item (written by the work-list pass; NULL = none)
   uint32_t item_leaf_cap;
+  // expected queries of the batch per (non-empty leaf, probed rank): launch_scan's choice between octs and wide quads
+  float qpl_per_rank;
 };
 
 // ---- query preparation ----
@@ -111,6 +113,8 @@ cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s);
 // counted = the per-leaf counts of ranks [rank_lo, rank_hi) are already in leaf_cnt (the pilot kernel does that)
 void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, bool counted, cudaStream_t s, int* launches);
 cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s);
+bool scan_uses_wide(const ScanWork& w);
+void scan_prepare_phase(ScanWork* w);
 // *n_launched (optional) receives the number of kernels launched (1-3: small, medium, heavy-tail class)
 cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s, int* n_launched = nullptr);
 // ---- finalize ----

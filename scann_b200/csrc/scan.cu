@@ -43,6 +43,15 @@
 #ifndef SB_SCAN_ACC
 #define SB_SCAN_ACC 2
 #endif
+// Accumulation of a wide-quad lookup (two registers of two u16 lanes): 0 = plain adds, 1 = one add + one IMAD,
+// 2 = two IMADs.
+// resident CTAs per SM the main scan is compiled for (5 x 128 threads => at most 96 registers)
+#ifndef SB_SCAN_MIN_CTAS
+#define SB_SCAN_MIN_CTAS 5
+#endif
+#ifndef SB_SCAN_WACC
+#define SB_SCAN_WACC 1
+#endif
 
 namespace sb {
 
@@ -209,6 +218,62 @@ __device__ __forceinline__ void build_oct_table(uint2* __restrict__ tbl, const u
     }
     reinterpret_cast<uint4*>(tbl)[2 * t] = make_uint4(x[0], y[0], x[1], y[1]);
     reinterpret_cast<uint4*>(tbl)[2 * t + 1] = make_uint4(x[2], y[2], x[3], y[3]);
+  }
+}
+
+// ---- wide quads (sparse batches) -----------------------------------------------------------
+// Where a leaf is probed by only a few queries of the batch (C5 shape: 10k queries over 40k leaves, ~6 per leaf and
+// fewer per scan phase) most lanes of an oct are empty and its mask / permute / accumulate work is wasted.  A WIDE QUAD
+// serves four queries from a table of 64-bit entries that already hold u16 lanes,
+//   T[b][c] = { lut0 | lut1 << 16,  lut2 | lut3 << 16 },
+// so a lookup is one LDS.64 and two adds (3 issue slots per four lookups instead of 9 per eight) and the unit of wasted
+// work is four queries instead of eight.  It moves twice the shared-memory bytes per lookup (64 lookups / clk / SM at
+// the LDS limit instead of 128), so dense batches keep the octs; launch_scan picks per launch.
+template <int W, int NL, int QD>
+__device__ __forceinline__ void score_wquad_addr(const uint32_t (&ad)[8 * W], int nlast, uint32_t one,
+                                                 uint32_t (&acc)[2]) {
+  uint32_t x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  const int nl = NL ? NL : nlast;
+  static_for(std::make_integer_sequence<int, 8 * W>{}, [&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    if (i >= 8 * (W - 1) + nl) return;
+    uint32_t vx, vy;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(vx), "=r"(vy) : "r"(ad[i]), "n"(QD * W * 128 * 8 + i * 128));
+#if SB_SCAN_WACC == 0
+    (void)one;
+    if (i & 1) { x1 += vx; y1 += vy; } else { x0 += vx; y0 += vy; }
+#elif SB_SCAN_WACC == 1
+    if (i & 1) { x1 += vx; asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y1) : "r"(vy), "r"(one)); }
+    else { x0 += vx; asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y0) : "r"(vy), "r"(one)); }
+#else
+    if (i & 1) {
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x1) : "r"(vx), "r"(one));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y1) : "r"(vy), "r"(one));
+    } else {
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x0) : "r"(vx), "r"(one));
+      asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(y0) : "r"(vy), "r"(one));
+    }
+#endif
+  });
+  acc[0] = x0 + x1;  // s0 | s1 << 16
+  acc[1] = y0 + y1;  // s2 | s3 << 16
+}
+
+// Widen up to four uint8 LUTs (8W*16 bytes each, NULL = all zero) into a wide-quad table.
+__device__ __forceinline__ void build_wquad_table(uint2* __restrict__ tbl, const uint8_t* const (&l)[4],
+                                                  int n_entries, int tid, int nthreads) {
+  for (int t = tid; t < n_entries / 4; t += nthreads) {
+    uint32_t v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = l[i] ? reinterpret_cast<const uint32_t*>(l[i])[t] : 0u;
+    // entry e: x = byte e of v0 | byte e of v1 << 16, y likewise for v2, v3
+    uint2 o[4];
+    o[0] = make_uint2(__byte_perm(v[0], v[1], 0x4440) & 0x00FF00FFu, __byte_perm(v[2], v[3], 0x4440) & 0x00FF00FFu);
+    o[1] = make_uint2(__byte_perm(v[0], v[1], 0x5551) & 0x00FF00FFu, __byte_perm(v[2], v[3], 0x5551) & 0x00FF00FFu);
+    o[2] = make_uint2(__byte_perm(v[0], v[1], 0x6662) & 0x00FF00FFu, __byte_perm(v[2], v[3], 0x6662) & 0x00FF00FFu);
+    o[3] = make_uint2(__byte_perm(v[0], v[1], 0x7773) & 0x00FF00FFu, __byte_perm(v[2], v[3], 0x7773) & 0x00FF00FFu);
+    reinterpret_cast<uint4*>(tbl)[2 * t] = make_uint4(o[0].x, o[0].y, o[1].x, o[1].y);
+    reinterpret_cast<uint4*>(tbl)[2 * t + 1] = make_uint4(o[2].x, o[2].y, o[3].x, o[3].y);
   }
 }
 
@@ -695,36 +760,42 @@ struct ItemMeta {
   // thresholds of an oct packed like its accumulators, (t0,t2) (t1,t3) (t4,t6) (t5,t7) as u16 halves, each
   // biased by 32768: bit 15 of a half of (thrp - acc) is set iff sum <= thr (sums < 2^15 because B <= 128)
   uint4 thrp[kMaxQPI / 8];
+  // the same for a wide quad: (t0,t1) (t2,t3)
+  uint2 thrpw[kMaxQPI / 4];
   // per-item staging of the candidates of each query: the scan appends here with shared-memory atomics and the item's
   // epilogue publishes a query's keys with ONE global atomicAdd (one lane per staged key).  Where a few slots of almost
   // every 32-slot group pass the threshold (C5-size leaves: ~20 candidates per (query, item)) the global atomic and its
   // round trip leave the scoring loop; a full stage spills to the direct path below.
   uint32_t scnt[kMaxQPI];
-  uint64_t sbuf[kMaxQPI][32];
+  uint64_t sbuf[kMaxQPI * 32];  // [queries per item][stage entries]: 32 per query at 32 queries per item, 64 at 16
 };
-constexpr uint32_t kStage = 32;
+constexpr uint32_t kStageKeys = kMaxQPI * 32;
 
 // Push path of the main scan: exact key test and warp-aggregated append for one oct.  All 32 lanes call.  `hit` holds
 // the lane's packed threshold test (bit 15 / 31 of word j set iff the sum in that half passed); one warp-wide OR finds
 // the queries of the oct with any passing slot and only those are visited.
+// WIDE = 1: a wide quad -- a0 = s0 | s1 << 16, a1 = s2 | s3 << 16 (a2, a3, h2, h3 unused).
+template <int WIDE>
 __device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork& w, ItemMeta* meta, uint32_t qd,
                                              uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t h0, uint32_t h1,
                                              uint32_t h2, uint32_t h3, bool valid, uint32_t gslot, int off128) {
   const int lane = threadIdx.x & 31;
+  const uint32_t kstage = kStageKeys / (w.quads_per_item * kQueriesPerQuad);
   // query i of the oct: sums (s0,s2) (s1,s3) (s4,s6) (s5,s7) sit in a0..a3 as u16 halves
-  uint32_t m8 = ((h0 >> 15) & 1u) | ((h1 >> 14) & 2u) | ((h0 >> 29) & 4u) | ((h1 >> 28) & 8u) |
-                ((h2 >> 11) & 16u) | ((h3 >> 10) & 32u) | ((h2 >> 25) & 64u) | ((h3 >> 24) & 128u);
+  uint32_t m8 = WIDE ? (((h0 >> 15) & 1u) | ((h0 >> 30) & 2u) | ((h1 >> 13) & 4u) | ((h1 >> 28) & 8u))
+                     : (((h0 >> 15) & 1u) | ((h1 >> 14) & 2u) | ((h0 >> 29) & 4u) | ((h1 >> 28) & 8u) |
+                        ((h2 >> 11) & 16u) | ((h3 >> 10) & 32u) | ((h2 >> 25) & 64u) | ((h3 >> 24) & 128u));
   if (!valid) m8 = 0u;
   uint32_t any8 = __reduce_or_sync(kFull, m8);
   while (any8) {
     const int i = __ffs(any8) - 1;
     any8 &= any8 - 1;
-    const int qi = qd * 8 + i;
+    const int qi = qd * (WIDE ? 4 : 8) + i;
     bool p = (m8 >> i) & 1u;
     uint64_t key = 0;
     if (p) {
-      const uint32_t word = (i & 4) ? ((i & 1) ? a3 : a2) : ((i & 1) ? a1 : a0);
-      const int sv = (int)((i & 2) ? (word >> 16) : (word & 0xFFFFu));
+      const uint32_t word = WIDE ? ((i & 2) ? a1 : a0) : ((i & 4) ? ((i & 1) ? a3 : a2) : ((i & 1) ? a1 : a0));
+      const int sv = (int)(((WIDE ? (i & 1) : (i & 2)) != 0) ? (word >> 16) : (word & 0xFFFFu));
       key = make_key(ah_float_score(sv - off128, meta->inv[qi], meta->bias[qi]),
                      ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
       p = key < meta->tau[qi];
@@ -738,7 +809,7 @@ __device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork&
         if (lane == leader) sbase = atomicAdd(&meta->scnt[qi], (uint32_t)__popc(m));
         sbase = __shfl_sync(kFull, sbase, leader);
         const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-        if (p && sbase + rank < kStage) { meta->sbuf[qi][sbase + rank] = key; p = false; }
+        if (p && sbase + rank < kstage) { meta->sbuf[qi * kstage + sbase + rank] = key; p = false; }
         m = __ballot_sync(kFull, p);
       }
       if (m) {
@@ -757,8 +828,37 @@ __device__ __noinline__ void push_candidates(const DevIndex& ix, const ScanWork&
   }
 }
 
-template <int W, int NL>
-__global__ void __launch_bounds__(kScanThreads)
+// Push path of a wide quad with per-item staging: every lane appends its own passing (query, slot) pairs with a
+// shared-memory atomic -- no warp-wide loop over the queries, no ballots: with a handful of passing pairs per warp,
+// mostly on different lanes, the divergent loop runs once or twice.  A full stage spills to the query's buffer.
+__device__ __forceinline__ void push_lane_staged(const DevIndex& ix, const ScanWork& w, ItemMeta* meta, uint32_t qd,
+                                                 uint32_t a0, uint32_t a1, uint32_t h0, uint32_t h1, uint32_t gslot,
+                                                 int off128, uint32_t kstage) {
+  uint32_t m = ((h0 >> 15) & 1u) | ((h0 >> 30) & 2u) | ((h1 >> 13) & 4u) | ((h1 >> 28) & 8u);
+  const uint32_t tie = ix.key_by_dp ? ix.slot_dp[gslot] : gslot;
+  while (m) {
+    const int i = __ffs(m) - 1;
+    m &= m - 1;
+    const uint32_t qi = qd * 4 + i;
+    const uint32_t word = (i & 2) ? a1 : a0;
+    const int sv = (int)((i & 1) ? (word >> 16) : (word & 0xFFFFu));
+    const uint64_t key = make_key(ah_float_score(sv - off128, meta->inv[qi], meta->bias[qi]), tie);
+    if (key < meta->tau[qi]) {
+      const uint32_t pos = atomicAdd(&meta->scnt[qi], 1u);
+      if (pos < kstage) {
+        meta->sbuf[qi * kstage + pos] = key;
+      } else {
+        const uint32_t qq = meta->q[qi];
+        const uint32_t gpos = atomicAdd(&w.cnt[qq], 1u);
+        if (gpos < w.cap) w.buf[(size_t)qq * w.cap + gpos] = key;
+        else w.ovf[qq] = 1u;
+      }
+    }
+  }
+}
+
+template <int W, int NL, int WIDE>
+__global__ void __launch_bounds__(kScanThreads, SB_SCAN_MIN_CTAS)
 scan_main_kernel(DevIndex ix, ScanWork w) {
   extern __shared__ __align__(16) unsigned char smem[];
   // [octs per item][W*128] 64-bit entries, 128-byte aligned: the lookup addresses are formed with OR
@@ -806,7 +906,8 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
     const uint32_t nleaf = ix.leaf_size[leaf];
     const uint32_t ebase = w.leaf_eoff[leaf] + chunk * qpi;
     const uint32_t ecount = min(qpi, w.leaf_eoff[leaf + 1] - ebase);
-    const uint32_t nquads = (ecount + kQueriesPerQuad - 1) / kQueriesPerQuad;  // octs in this item
+    constexpr uint32_t kQPT = WIDE ? 4u : (uint32_t)kQueriesPerQuad;  // queries per table
+    const uint32_t nquads = (ecount + kQPT - 1) / kQPT;  // octs (wide quads) in this item
     if (tid < (int)qpi) {
       uint32_t qq = kInvalidQuery;
       int thr = -1;
@@ -824,23 +925,27 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       meta.scnt[tid] = 0;
     }
     __syncthreads();
-    if (tid < (int)(qpi / 8)) {
-      auto bt = [&](int i) -> uint32_t { return (uint32_t)(min(max(s_thr[tid * 8 + i], -1), 32767) + 32768); };
-      meta.thrp[tid] = make_uint4(bt(0) | (bt(2) << 16), bt(1) | (bt(3) << 16), bt(4) | (bt(6) << 16), bt(5) | (bt(7) << 16));
+    if (tid < (int)(qpi / kQPT)) {
+      auto bt = [&](int i) -> uint32_t { return (uint32_t)(min(max(s_thr[tid * kQPT + i], -1), 32767) + 32768); };
+      if constexpr (WIDE) meta.thrpw[tid] = make_uint2(bt(0) | (bt(1) << 16), bt(2) | (bt(3) << 16));
+      else meta.thrp[tid] = make_uint4(bt(0) | (bt(2) << 16), bt(1) | (bt(3) << 16), bt(4) | (bt(6) << 16), bt(5) | (bt(7) << 16));
     }
     for (uint32_t qd = 0; qd < nquads; ++qd) {
-      const uint8_t* lp[8];
+      const uint8_t* lp[kQPT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const uint32_t qq = s_q[qd * 8 + i];
+      for (int i = 0; i < (int)kQPT; ++i) {
+        const uint32_t qq = s_q[qd * kQPT + i];
         lp[i] = (qq == kInvalidQuery) ? nullptr : w.lut + (size_t)qq * kTblEntries;
       }
-      build_oct_table(tables + (size_t)qd * kTblEntries, lp, kTblEntries, tid, kScanThreads);
+      if constexpr (WIDE) build_wquad_table(tables + (size_t)qd * kTblEntries, lp, kTblEntries, tid, kScanThreads);
+      else build_oct_table(tables + (size_t)qd * kTblEntries, lp, kTblEntries, tid, kScanThreads);
     }
     __syncthreads();
+    // The code words of the warp's next group are requested as soon as the current group's lookup addresses have been
+    // formed from them (the registers are free again), so their DRAM latency overlaps the scoring of the current group.
+    uint32_t cw[W];
+    if (g0 + warp < g1) load_codes<W>(ix.codes + (size_t)(gbeg + g0 + warp) * W * 32, lane, cw);
     for (uint32_t g = g0 + warp; g < g1; g += kScanWarps) {
-      uint32_t cw[W];
-      load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
       const bool valid = g * 32 + lane < nleaf;
       const uint32_t gslot = (gbeg + g) * 32 + lane;
       uint32_t ad[8 * W];
@@ -852,37 +957,60 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
           for (int k = 0; k < 8; ++k)
             ad[8 * j + k] = tb32 | ((k == 0) ? ((cw[j] << 3) & 0x78u) : ((cw[j] >> (4 * k - 3)) & 0x78u));
       }
+      if (g + kScanWarps < g1) load_codes<W>(ix.codes + (size_t)(gbeg + g + kScanWarps) * W * 32, lane, cw);
       // fast path inline (8 compares per oct), candidate push out of line: the scoring loops of the
       // octs are unrolled copies and must stay inside the instruction cache
-      auto filter = [&](const uint32_t qd, const uint32_t (&acc)[4]) {
-        const uint4 t = meta.thrp[qd];
-        const uint32_t h0 = t.x - acc[0], h1 = t.y - acc[1], h2 = t.z - acc[2], h3 = t.w - acc[3];
-        const uint32_t hit = (h0 | h1 | h2 | h3) & 0x80008000u;
-        if (__any_sync(kFull, valid && hit != 0))
-          push_candidates(ix, w, &meta, qd, acc[0], acc[1], acc[2], acc[3], h0, h1, h2, h3, valid, gslot, off128);
-      };
+      if constexpr (WIDE) {
+        auto filter = [&](const uint32_t qd, const uint32_t (&acc)[2]) {
+          const uint2 t = meta.thrpw[qd];
+          const uint32_t h0 = t.x - acc[0], h1 = t.y - acc[1];
+          const uint32_t hit = (h0 | h1) & 0x80008000u;
+          if (w.stage) {
+            if (valid && hit != 0) push_lane_staged(ix, w, &meta, qd, acc[0], acc[1], h0, h1, gslot, off128, kStageKeys / qpi);
+          } else if (__any_sync(kFull, valid && hit != 0)) {
+            push_candidates<1>(ix, w, &meta, qd, acc[0], acc[1], 0u, 0u, h0, h1, 0u, 0u, valid, gslot, off128);
+          }
+        };
+#define SB_DO_WQUAD(QD)                                      \
+  if (QD < nquads) {                                         \
+    uint32_t acc[2];                                         \
+    score_wquad_addr<W, NL, QD>(ad, nlast, w.one, acc);      \
+    filter(QD, acc);                                         \
+  }
+        SB_DO_WQUAD(0) SB_DO_WQUAD(1) SB_DO_WQUAD(2) SB_DO_WQUAD(3)
+#undef SB_DO_WQUAD
+      } else {
+        auto filter = [&](const uint32_t qd, const uint32_t (&acc)[4]) {
+          const uint4 t = meta.thrp[qd];
+          const uint32_t h0 = t.x - acc[0], h1 = t.y - acc[1], h2 = t.z - acc[2], h3 = t.w - acc[3];
+          const uint32_t hit = (h0 | h1 | h2 | h3) & 0x80008000u;
+          if (__any_sync(kFull, valid && hit != 0))
+            push_candidates<0>(ix, w, &meta, qd, acc[0], acc[1], acc[2], acc[3], h0, h1, h2, h3, valid, gslot, off128);
+        };
 #define SB_DO_QUAD(QD)                                       \
   if (QD < nquads) {                                         \
     uint32_t acc[4];                                         \
     score_oct_addr<W, NL, QD>(ad, nlast, w.one, acc);        \
     filter(QD, acc);                                         \
   }
-      SB_DO_QUAD(0) SB_DO_QUAD(1)
+        SB_DO_QUAD(0) SB_DO_QUAD(1)
 #undef SB_DO_QUAD
+      }
     }
     // item epilogue: publish the staged candidates, one warp per query, one global atomicAdd per (query, item)
     if (w.stage) {
       __syncthreads();
+      const uint32_t kstage = kStageKeys / qpi;
       for (uint32_t qi = warp; qi < ecount; qi += kScanWarps) {
-        const uint32_t c = min(meta.scnt[qi], kStage);
+        const uint32_t c = min(meta.scnt[qi], kstage);
         if (c == 0) continue;
         const uint32_t qq = s_q[qi];
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(&w.cnt[qq], c);
         base = __shfl_sync(kFull, base, 0);
-        if ((uint32_t)lane < c) {
-          const uint32_t pos = base + lane;
-          if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = meta.sbuf[qi][lane];
+        for (uint32_t j = lane; j < c; j += 32) {
+          const uint32_t pos = base + j;
+          if (pos < w.cap) w.buf[(size_t)qq * w.cap + pos] = meta.sbuf[qi * kstage + j];
           else w.ovf[qq] = 1u;
         }
       }
@@ -1042,6 +1170,13 @@ leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, 
 }
 
 // ---- launchers ---------------------------------------------------------------------------
+#ifdef SB_DEV_W  // development builds (make DEVW=1): only the block counts of the bench shapes, minutes less of ptxas
+#define SB_DISPATCH_W(Wv, ...)                                                         \
+  switch (Wv) {                                                                          \
+    case 6: { constexpr int W = 6; __VA_ARGS__; } break;   case 7: { constexpr int W = 7; __VA_ARGS__; } break;   \
+    default: return cudaErrorInvalidValue;                                               \
+  }
+#else
 #define SB_DISPATCH_W(Wv, ...)                                                         \
   switch (Wv) {                                                                          \
     case 1: { constexpr int W = 1; __VA_ARGS__; } break;   case 2: { constexpr int W = 2; __VA_ARGS__; } break;   \
@@ -1054,6 +1189,7 @@ leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, 
     case 15: { constexpr int W = 15; __VA_ARGS__; } break; case 16: { constexpr int W = 16; __VA_ARGS__; } break; \
     default: return cudaErrorInvalidValue;                                               \
   }
+#endif
 
 static int pilot_capl(const ScanWork& w) {
   int capl = 1024;  // keys buffered between selections; a typical C2 leaf fits
@@ -1086,31 +1222,59 @@ cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) 
   return cudaGetLastError();
 }
 
-template <int W, int NL>
+template <int W, int NL, int WIDE>
 static cudaError_t launch_scan_t(const DevIndex& ix, const ScanWork& w, int grid, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(scan_main_kernel<W, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(scan_main_kernel<W, NL, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (grid <= 0) {  // persistent: exactly as many CTAs as can be resident
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_main_kernel<W, NL>, kScanThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_main_kernel<W, NL, WIDE>, kScanThreads, smem);
     if (e != cudaSuccess) return e;
     grid = sms * (per_sm > 0 ? per_sm : 1);
   }
-  scan_main_kernel<W, NL><<<grid, kScanThreads, smem, s>>>(ix, w);
+  scan_main_kernel<W, NL, WIDE><<<grid, kScanThreads, smem, s>>>(ix, w);
   return cudaGetLastError();
 }
 
+// Octs or wide quads for this launch.  Wide quads cost 3 issue slots per four lookups (octs: 9 per eight) but twice
+// the shared-memory bytes, and their unit of padding is four queries instead of eight: they win where the leaves of
+// this work list hold few queries each (expected queries per leaf = qpl_per_rank x ranks in the list), the octs win
+// where the tables are full and the LDS pipe is the limit.  SCANN_B200_SCAN_WIDE=0|1 overrides.
+bool scan_uses_wide(const ScanWork& w) {
+  const char* e = getenv("SCANN_B200_SCAN_WIDE");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  const char* t = getenv("SCANN_B200_SCAN_WIDE_QPL");
+  const float limit = t ? (float)atof(t) : 45.f;
+  const uint32_t ranks = w.rank_hi > w.rank_lo ? w.rank_hi - w.rank_lo : w.P;
+  return w.qpl_per_rank > 0.f && w.qpl_per_rank * (float)ranks <= limit;
+}
+
+// Queries per work item of the next work list (call after rank_lo / rank_hi are set, before launch_worklist): sixteen
+// (two octs) for dense lists, eight (two wide quads) for sparse ones -- few leaves hold more there, the tables take
+// half the shared memory and the per-item candidate stage has 128 entries per query instead of 64.
+void scan_prepare_phase(ScanWork* w) { w->quads_per_item = scan_uses_wide(*w) ? 1u : 2u; }
+
 cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s) {
-  const size_t smem = scan_smem_bytes(ix, w.quads_per_item);
+  const bool wide = scan_uses_wide(w);
+  const size_t smem = scan_smem_bytes(ix, w.quads_per_item * (wide ? 2u : 1u));
   // the common block counts (B % 8 == 0, 2, 4) get a kernel without padded lookups
   const int nlast = (int)ix.B - 8 * ((int)ix.W - 1);
+  if (wide) {
+    SB_DISPATCH_W(ix.W, {
+      if (nlast == 8) return launch_scan_t<W, 8, 1>(ix, w, grid, smem, s);
+      if (nlast == 2) return launch_scan_t<W, 2, 1>(ix, w, grid, smem, s);
+      if (nlast == 4) return launch_scan_t<W, 4, 1>(ix, w, grid, smem, s);
+      return launch_scan_t<W, 0, 1>(ix, w, grid, smem, s);
+    });
+    return cudaGetLastError();
+  }
   SB_DISPATCH_W(ix.W, {
-    if (nlast == 8) return launch_scan_t<W, 8>(ix, w, grid, smem, s);
-    if (nlast == 2) return launch_scan_t<W, 2>(ix, w, grid, smem, s);
-    if (nlast == 4) return launch_scan_t<W, 4>(ix, w, grid, smem, s);
-    return launch_scan_t<W, 0>(ix, w, grid, smem, s);
+    if (nlast == 8) return launch_scan_t<W, 8, 0>(ix, w, grid, smem, s);
+    if (nlast == 2) return launch_scan_t<W, 2, 0>(ix, w, grid, smem, s);
+    if (nlast == 4) return launch_scan_t<W, 4, 0>(ix, w, grid, smem, s);
+    return launch_scan_t<W, 0, 0>(ix, w, grid, smem, s);
   });
   return cudaGetLastError();
 }

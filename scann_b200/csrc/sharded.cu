@@ -240,8 +240,10 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
         const uint64_t volume = (uint64_t)p.P * ix->avg_leaf_slots / (w.pilot_world > 1 ? (uint64_t)G : 1ull);
         st.two_phase = p.P >= 16 && volume >= 49152;
         if (const char* e = getenv("SCANN_B200_TWO_PHASE")) st.two_phase = e[0] == '1' && p.P >= 2;
-        const uint32_t r1 = st.two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
+        uint32_t r1 = st.two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
+        if (const char* e = getenv("SCANN_B200_PHASE1_RANKS")) { const int t = atoi(e); if (st.two_phase && t >= 1 && (uint32_t)t < p.P) r1 = (uint32_t)t; }
         w.rank_lo = 0; w.rank_hi = r1;
+        sb::scan_prepare_phase(&w);
         CU(sb::launch_pilot(ix->dev, w, s));
         st.launches += 1;
         CU(cudaEventRecord(ix->ev[EV_PILOT], s));
@@ -272,6 +274,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
         CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
         if (st.two_phase) {
           w.rank_lo = w.rank_hi; w.rank_hi = p.P;
+          sb::scan_prepare_phase(&w);
           sb::launch_worklist(v, w, false, false, s, &st.launches);
           CU(cudaGetLastError());
           CU(cudaEventRecord(ix->ev[EV2_WORK], s));
@@ -283,6 +286,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
           CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
         }
         w.rank_lo = 0; w.rank_hi = p.P;
+        sb::scan_prepare_phase(&w);
         uint32_t* hc = ix->h_counters.as<uint32_t>();
         unsigned long long* hs = reinterpret_cast<unsigned long long*>(hc + 8);
         CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));

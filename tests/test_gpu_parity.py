@@ -212,6 +212,44 @@ def test_staged_candidate_push_is_bit_exact(kw, mode, monkeypatch):
   np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
 
 
+# ---- wide quads (the sparse-batch mode of the main scan: u16-lane tables, four queries per LDS.64) ----
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+@pytest.mark.parametrize("mode", ["plain", "staged_two_phase", "overflow"])
+def test_wide_quad_scan_is_bit_exact(kw, mode, monkeypatch):
+  monkeypatch.setenv("SCANN_B200_SCAN_WIDE", "1")
+  if mode != "plain":
+    monkeypatch.setenv("SCANN_B200_SCAN_STAGE", "1")
+    monkeypatch.setenv("SCANN_B200_TWO_PHASE", "1")
+  if mode == "overflow":
+    monkeypatch.setenv("SCANN_B200_CAND_CAP", "256")
+  c = get_case(**kw)
+  a = c.oracle.candidates(c.q)
+  b = c.native.candidates(c.q)
+  np.testing.assert_array_equal(a["count"], b["count"])
+  for i in range(len(c.q)):
+    n = a["count"][i]
+    np.testing.assert_array_equal(a["leaf"][i, :n], b["leaf"][i, :n])
+    np.testing.assert_array_equal(a["slot"][i, :n], b["slot"][i, :n])
+    np.testing.assert_array_equal(a["score"][i, :n].view(np.uint32), b["score"][i, :n].view(np.uint32))
+  i0, d0 = c.oracle.search_batched(c.q)
+  i1, d1 = c.native.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
+def test_wide_quad_and_oct_scans_agree_on_a_sparse_batch(monkeypatch):
+  """Few queries per leaf (the regime the wide quads are for): 48 queries over 1,000 leaves, both modes, same bits."""
+  c = get_case(n=20000, leaves=1000, probe=24, pre=80, d=96, dpb=2, nq=48)
+  out = {}
+  for wide in ("0", "1"):
+    monkeypatch.setenv("SCANN_B200_SCAN_WIDE", wide)
+    out[wide] = c.native.search_batched(c.q)
+  np.testing.assert_array_equal(out["0"][0], out["1"][0])
+  np.testing.assert_array_equal(out["0"][1].view(np.uint32), out["1"][1].view(np.uint32))
+  i0, d0 = c.oracle.search_batched(c.q)
+  np.testing.assert_array_equal(i0, out["1"][0])
+
+
 def test_host_call_with_page_locked_buffers_matches_pageable():
   """scann_b200_search_batched copies page-locked caller memory to / from the device directly."""
   import torch

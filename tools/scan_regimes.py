@@ -46,7 +46,14 @@ def main():
   d_q = torch.from_numpy(q).to(dev)
   truth = bench.exact_topk(d_q, db, k, dev, l2=wl.get("distance") == "squared_l2")
   flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+  base_env = {n for n in os.environ if n.startswith("SCANN_B200_")}
   for case in args.cases.split(","):
+    case, *envs = case.split(";")  # nq:P:two_phase[:tokenize][;NAME=VALUE...]: per-case environment (tuning knobs)
+    for name in [n for n in os.environ if n.startswith("SCANN_B200_") and n not in base_env]:
+      os.environ.pop(name)
+    for kv in envs:
+      name, val = kv.split("=")
+      os.environ[name] = val
     parts = case.split(":")
     nq_s, p_s, tp = parts[:3]
     nq, p = int(nq_s), int(p_s)
@@ -76,7 +83,7 @@ def main():
         agg[key] = agg.get(key, 0) + val
     s = args.steps
     print(json.dumps({
-        "nq": nq, "leaves_to_search": p, "two_phase": tp, "tokenize": os.environ.get("SCANN_B200_TOKENIZE", "auto"),
+        "nq": nq, "leaves_to_search": p, "two_phase": tp, "env": envs, "tokenize": os.environ.get("SCANN_B200_TOKENIZE", "auto"),
         "leaves": wl["leaves"], "recall_at_10": round(rec, 4),
         "ms_total": agg["ms_total"] / s, "ms_scan": agg["ms_scan"] / s, "ms_compact": agg["ms_compact"] / s,
         "ms_pilot": agg["ms_pilot"] / s, "ms_finalize": agg["ms_finalize"] / s, "ms_tokenize": agg["ms_tokenize"] / s,
