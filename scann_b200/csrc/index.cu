@@ -386,6 +386,7 @@ int ensure_workspace(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_
   CU(ix->leaves.ensure(sizeof(int32_t) * (size_t)nq * p.P));
   CU(ix->bias.ensure(sizeof(float) * (size_t)nq * p.P));
   CU(ix->lut.ensure((size_t)nq * v.W * 128));
+  if (sb::scan_tc_supported(v)) CU(ix->lut_e4m3.ensure((size_t)nq * v.W * 128 * 2));
   CU(ix->mult.ensure(sizeof(float) * nq));
   CU(ix->inv.ensure(sizeof(float) * nq));
   CU(ix->pilot_end.ensure(sizeof(int32_t) * nq));
@@ -421,6 +422,7 @@ void fill_scan_work(scann_b200_index* ix, uint32_t nq, const Params& p, uint32_t
   w.counters = ix->counters.as<uint32_t>(); w.stats = ix->stats.as<unsigned long long>();
   w.nq = nq; w.P = p.P; w.cap = cap; w.nover = p.nover; w.quads_per_item = 2; w.one = 1;  // 2 octs = 16 queries per work item
   w.item_leaf = ix->item_leaf.as<uint32_t>();
+  w.lut_e4m3 = ix->lut_e4m3.as<uint8_t>();
   w.item_leaf_cap = (uint32_t)(ix->item_leaf.bytes / sizeof(uint32_t));
   // Groups per work item.  An item costs a fixed set-up (oct tables, thresholds, a few dependent loads); with many more
   // items than resident CTAs (740) larger tiles amortise it, with few items small tiles balance the load.  Expected
@@ -507,7 +509,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   uint32_t r1 = two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
   if (const char* e = getenv("SCANN_B200_PHASE1_RANKS")) { const int t = atoi(e); if (two_phase && t >= 1 && (uint32_t)t < p.P) r1 = (uint32_t)t; }
   w.rank_lo = 0; w.rank_hi = r1;
-  sb::scan_prepare_phase(&w);
+  sb::scan_prepare_phase(v, &w);
   CU(sb::launch_pilot(v, w, s));
   launches += 1;
   CU(cudaEventRecord(ix->ev[EV_PILOT], s));
@@ -523,7 +525,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
   if (two_phase) {
     w.rank_lo = r1; w.rank_hi = p.P;
-    sb::scan_prepare_phase(&w);
+    sb::scan_prepare_phase(v, &w);
     sb::launch_worklist(v, w, false, false, s, &launches);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ix->ev[EV2_WORK], s));
@@ -535,7 +537,8 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
     CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
   }
   w.rank_lo = 0; w.rank_hi = p.P;  // re-scans of overflowed queries cover every probed leaf
-  sb::scan_prepare_phase(&w);
+  w.rescan = 1;
+  sb::scan_prepare_phase(v, &w);
   // Overflow flag, statistics and the finalize kernel share ONE host round trip: finalize is launched
   // optimistically; if some buffer overflowed (rare) its output is discarded, the flagged queries are
   // re-scanned and finalize runs again.
@@ -557,6 +560,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaMemcpyAsync(hs, w.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   const uint32_t tok_fallbacks = hc[5];
+  if (hc[7] != 0) return fail(SCANN_B200_INTERNAL, "tensor-core scan: a pipeline barrier timed out (watchdog)");
   if (hc[2] != 0) {
     while (hc[2] != 0) {
       if (++retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");

@@ -77,6 +77,7 @@ struct scann_b200_index {
   sbi::DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
       codes, slot_dp, slot_tie, dataset, dp_row, tok_b;
   // workspace
+  sbi::DevBuf lut_e4m3;  // tensor-core scan: the e4m3 (hi nibble x 16, lo nibble) planes of the batch's LUTs
   sbi::DevBuf tok_a, q, dist, leaves, bias, lut, mult, inv, pilot_end, buf, cnt, tau, ovf, leaf_cnt, leaf_eoff,
       leaf_cur, item_off, item_leaf, entry_q, entry_bias, counters, stats, out_idx, out_dist;
   sbi::PinnedBuf h_q, h_idx, h_dist, h_counters;

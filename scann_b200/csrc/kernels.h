@@ -87,8 +87,13 @@ struct ScanWork {
   uint32_t max_gpt;           // groups per work item of the main scan (0 = kMaxGroupsPerTile)
   uint32_t* item_leaf;        // [item_leaf_cap] leaf of each work item (written by the work-list pass; NULL = none)
   uint32_t item_leaf_cap;
-  // expected queries of the batch per (non-empty leaf, probed rank): launch_scan's choice between octs and wide quads
+  // expected queries of the batch per (non-empty leaf, probed rank): scan_prepare_phase's choice of the scan kernel
   float qpl_per_rank;
+  // set by scan_prepare_phase for the next work list: 0 = octs, 1 = wide quads (scan.cu), 2 = tensor cores (scan_tc.cu)
+  uint32_t scan_mode;
+  uint32_t max_gpt_simt;      // the SIMT kernels' groups per item (max_gpt is overwritten for the tensor-core items)
+  uint32_t rescan;            // 1: the work list holds only the queries whose buffer overflowed (sparse whatever the batch)
+  uint8_t* lut_e4m3;          // [2][nq][W*128] workspace of the tensor-core scan (NULL: that path is unavailable)
 };
 
 // ---- query preparation ----
@@ -113,8 +118,12 @@ cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s);
 // counted = the per-leaf counts of ranks [rank_lo, rank_hi) are already in leaf_cnt (the pilot kernel does that)
 void launch_worklist(const DevIndex& ix, const ScanWork& w, bool only_overflowed, bool counted, cudaStream_t s, int* launches);
 cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s);
-bool scan_uses_wide(const ScanWork& w);
-void scan_prepare_phase(ScanWork* w);
+// Picks the kernel of the next work list and sets scan_mode / quads_per_item / max_gpt accordingly: call after rank_lo,
+// rank_hi (and rescan) are set and before launch_worklist; launch_scan follows the choice.
+void scan_prepare_phase(const DevIndex& ix, ScanWork* w);
+// ---- tensor-core scan (scan_tc.cu) ----
+bool scan_tc_supported(const DevIndex& ix);
+cudaError_t launch_scan_tc(const DevIndex& ix, const ScanWork& w, cudaStream_t s);
 // *n_launched (optional) receives the number of kernels launched (1-3: small, medium, heavy-tail class)
 cudaError_t launch_compact(const DevIndex& ix, const ScanWork& w, bool dedup, cudaStream_t s, int* n_launched = nullptr);
 // ---- finalize ----

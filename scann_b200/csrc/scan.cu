@@ -34,6 +34,7 @@
 #include "exact_math.cuh"
 #include "kernels.h"
 #include "lut.cuh"
+#include "scan_common.cuh"
 
 // How the main scan accumulates the four u16-lane registers of an oct lookup:
 //   0 = plain adds (ptxas merges pairs into IADD3 on the ALU pipe), 1 = two on ALU + two IMAD on the
@@ -67,28 +68,6 @@ __device__ __forceinline__ void leaf_tiling(uint32_t ng, uint32_t max_gpt, uint3
 }
 constexpr uint32_t kFull = 0xFFFFFFFFu;
 constexpr int kMaxQPI = 32;  // queries per work item (4 octs of 8 queries)
-
-// ---- packed code layout -------------------------------------------------------------------
-// Per 32-slot group: W 32-bit words per slot (nibble k of word j = code of block 8j+k), stored
-// as planes so that a warp's loads are contiguous: floor(W/4) uint4 planes (512 B each), then
-// one uint2 plane if W%4 >= 2, then one u32 plane if W is odd.  W*128 bytes per group.
-template <int W>
-__device__ __forceinline__ void load_codes(const uint32_t* __restrict__ gbase, int lane,
-                                           uint32_t (&w)[W]) {
-  constexpr int N4 = W / 4, R = W % 4;
-#pragma unroll
-  for (int p = 0; p < N4; ++p) {
-    const uint4 v = ldg_stream_v4(gbase + p * 128 + lane * 4);
-    w[4 * p + 0] = v.x; w[4 * p + 1] = v.y; w[4 * p + 2] = v.z; w[4 * p + 3] = v.w;
-  }
-  if constexpr (R >= 2) {
-    const uint2 v = ldg_stream_v2(gbase + N4 * 128 + lane * 2);
-    w[4 * N4 + 0] = v.x; w[4 * N4 + 1] = v.y;
-  }
-  if constexpr (R & 1) {
-    w[W - 1] = ldg_stream_u32(gbase + N4 * 128 + ((R >= 2) ? 64 : 0) + lane);
-  }
-}
 
 // Four queries' u16 sums for one datapoint: a01 = s0 | s1 << 16, a23 = s2 | s3 << 16.
 // NL = number of real blocks in the last word: 1..8 compile-time (the padded lookups vanish from
@@ -297,24 +276,6 @@ __device__ __forceinline__ void build_quad_table(uint32_t* __restrict__ tbl, con
     o.w = __byte_perm(ab23, cd23, 0x7632);
     reinterpret_cast<uint4*>(tbl)[t] = o;
   }
-}
-
-// Largest accumulator value whose float score is <= the score of `tau` (conservative integer
-// pre-filter; the reference's trunc((eps - bias) * mult) of lut16_avx2.inc:432-438 may drop a
-// candidate that is strictly better than eps, this one never does).
-__device__ int acc_threshold(uint64_t tau, float mult, float inv, float bias) {
-  if (tau == kKeyMax) return 40000;
-  const float ts = ord2f((uint32_t)(tau >> 32));
-  const float est = __fmul_rn(__fsub_rn(ts, bias), mult);
-  int t;
-  if (!(est < 40000.f)) t = 32767;
-  else if (!(est > -40000.f)) t = -32769;
-  else t = (int)floorf(est);
-  t = min(t, 32767);
-  t = max(t, -32769);
-  while (t < 32767 && ah_float_score(t + 1, inv, bias) <= ts) ++t;
-  while (t >= -32768 && ah_float_score(t, inv, bias) > ts) --t;
-  return t;
 }
 
 // K-th smallest (1-based) of n UNIQUE u64 keys in shared memory: 8-pass MSB radix select.
@@ -1238,26 +1199,41 @@ static cudaError_t launch_scan_t(const DevIndex& ix, const ScanWork& w, int grid
   return cudaGetLastError();
 }
 
-// Octs or wide quads for this launch.  Wide quads cost 3 issue slots per four lookups (octs: 9 per eight) but twice
-// the shared-memory bytes, and their unit of padding is four queries instead of eight: they win where the leaves of
-// this work list hold few queries each (expected queries per leaf = qpl_per_rank x ranks in the list), the octs win
-// where the tables are full and the LDS pipe is the limit.  SCANN_B200_SCAN_WIDE=0|1 overrides.
-bool scan_uses_wide(const ScanWork& w) {
-  const char* e = getenv("SCANN_B200_SCAN_WIDE");
-  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-  const char* t = getenv("SCANN_B200_SCAN_WIDE_QPL");
-  const float limit = t ? (float)atof(t) : 45.f;
-  const uint32_t ranks = w.rank_hi > w.rank_lo ? w.rank_hi - w.rank_lo : w.P;
-  return w.qpl_per_rank > 0.f && w.qpl_per_rank * (float)ranks <= limit;
+// The kernel of the next work list, by the expected number of queries per leaf in it (qpl_per_rank x ranks):
+//  * wide quads (3 issue slots per four lookups, padding unit four queries, twice the shared-memory bytes per lookup)
+//    where leaves hold few queries -- measured cross-over with the octs near 45 queries per leaf (20M x 96, B = 48);
+//  * octs (9 issue slots per eight lookups, 128 lookups / clk / SM at the LDS limit) above that;
+//  * the tensor-core scan (scan_tc.cu: blocks of 64 queries per leaf) where the blocks fill.
+// SCANN_B200_SCAN_WIDE=0|1, SCANN_B200_SCAN_TC=0|1 force a path; *_QPL move the thresholds (tests, tuning).
+void scan_prepare_phase(const DevIndex& ix, ScanWork* w) {
+  const uint32_t ranks = w->rank_hi > w->rank_lo ? w->rank_hi - w->rank_lo : w->P;
+  const float qpl = w->rescan ? 0.f : w->qpl_per_rank * (float)ranks;
+  const char* ew = getenv("SCANN_B200_SCAN_WIDE");
+  const char* et = getenv("SCANN_B200_SCAN_TC");
+  const char* lw = getenv("SCANN_B200_SCAN_WIDE_QPL");
+  const char* lt = getenv("SCANN_B200_SCAN_TC_QPL");
+  const float wide_limit = lw ? (float)atof(lw) : 45.f;
+  // the tensor-core scan is opt-in: bit-exact, but at its current 1.5 ms per C2 batch not faster than the octs (1.41 ms)
+  const float tc_limit = lt ? (float)atof(lt) : 3.0e38f;
+  const bool tc_ok = scan_tc_supported(ix) && w->lut_e4m3 != nullptr;
+  bool tc = tc_ok && !w->rescan && qpl >= tc_limit;
+  if (et && (et[0] == '0' || et[0] == '1')) tc = et[0] == '1' && tc_ok;
+  bool wide = w->qpl_per_rank > 0.f && qpl <= wide_limit;
+  if (ew && (ew[0] == '0' || ew[0] == '1')) wide = ew[0] == '1';
+  if (w->max_gpt_simt == 0) w->max_gpt_simt = w->max_gpt;
+  if (tc) {
+    // items = (leaf, block of 64 queries): eight "octs" per item, the whole leaf in one tile
+    w->scan_mode = 2; w->quads_per_item = 8; w->max_gpt = 0x7FFFFFFFu;
+  } else {
+    // sixteen queries (two octs) per item for dense lists, eight (two wide quads) for sparse ones -- few leaves hold
+    // more there, the tables take half the shared memory and the per-item candidate stage has 128 entries per query
+    w->scan_mode = wide ? 1u : 0u; w->quads_per_item = wide ? 1u : 2u; w->max_gpt = w->max_gpt_simt;
+  }
 }
 
-// Queries per work item of the next work list (call after rank_lo / rank_hi are set, before launch_worklist): sixteen
-// (two octs) for dense lists, eight (two wide quads) for sparse ones -- few leaves hold more there, the tables take
-// half the shared memory and the per-item candidate stage has 128 entries per query instead of 64.
-void scan_prepare_phase(ScanWork* w) { w->quads_per_item = scan_uses_wide(*w) ? 1u : 2u; }
-
 cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStream_t s) {
-  const bool wide = scan_uses_wide(w);
+  if (w.scan_mode == 2) return launch_scan_tc(ix, w, s);
+  const bool wide = w.scan_mode == 1;
   const size_t smem = scan_smem_bytes(ix, w.quads_per_item * (wide ? 2u : 1u));
   // the common block counts (B % 8 == 0, 2, 4) get a kernel without padded lookups
   const int nlast = (int)ix.B - 8 * ((int)ix.W - 1);

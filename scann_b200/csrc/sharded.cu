@@ -243,7 +243,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
         uint32_t r1 = st.two_phase ? std::max<uint32_t>(1, p.P / 8) : p.P;
         if (const char* e = getenv("SCANN_B200_PHASE1_RANKS")) { const int t = atoi(e); if (st.two_phase && t >= 1 && (uint32_t)t < p.P) r1 = (uint32_t)t; }
         w.rank_lo = 0; w.rank_hi = r1;
-        sb::scan_prepare_phase(&w);
+        sb::scan_prepare_phase(ix->dev, &w);
         CU(sb::launch_pilot(ix->dev, w, s));
         st.launches += 1;
         CU(cudaEventRecord(ix->ev[EV_PILOT], s));
@@ -274,7 +274,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
         CU(cudaEventRecord(ix->ev[EV_COMPACT], s));
         if (st.two_phase) {
           w.rank_lo = w.rank_hi; w.rank_hi = p.P;
-          sb::scan_prepare_phase(&w);
+          sb::scan_prepare_phase(v, &w);
           sb::launch_worklist(v, w, false, false, s, &st.launches);
           CU(cudaGetLastError());
           CU(cudaEventRecord(ix->ev[EV2_WORK], s));
@@ -286,13 +286,15 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
           CU(cudaEventRecord(ix->ev[EV2_COMPACT], s));
         }
         w.rank_lo = 0; w.rank_hi = p.P;
-        sb::scan_prepare_phase(&w);
+        w.rescan = 1;
+        sb::scan_prepare_phase(v, &w);
         uint32_t* hc = ix->h_counters.as<uint32_t>();
         unsigned long long* hs = reinterpret_cast<unsigned long long*>(hc + 8);
         CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
         CU(cudaMemcpyAsync(hs, w.stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost, s));
         CU(cudaStreamSynchronize(s));
         const uint32_t tok_fallbacks = hc[5];
+        if (hc[7] != 0) return fail(SCANN_B200_INTERNAL, "tensor-core scan: a pipeline barrier timed out (watchdog)");
         while (hc[2] != 0) {  // candidate-buffer overflow: re-scan the flagged queries (local, no collective involved)
           if (++st.retries > 256) return fail(SCANN_B200_INTERNAL, "candidate buffer overflow did not converge");
           CU(cudaMemsetAsync(w.counters + 2, 0, sizeof(uint32_t), s));

@@ -250,6 +250,49 @@ def test_wide_quad_and_oct_scans_agree_on_a_sparse_batch(monkeypatch):
   np.testing.assert_array_equal(i0, out["1"][0])
 
 
+# ---- tensor-core scan (scan_tc.cu: e4m3 nibble planes of the u8 LUT x one-hot codes on tcgen05 kind::f8f6f4, exact f32 sums) ----
+@pytest.mark.parametrize("kw", CASES, ids=[str(i) for i in range(len(CASES))])
+@pytest.mark.parametrize("mode", ["plain", "two_phase", "overflow"])
+def test_tensor_core_scan_is_bit_exact(kw, mode, monkeypatch):
+  monkeypatch.setenv("SCANN_B200_SCAN_TC", "1")
+  if mode != "plain":
+    monkeypatch.setenv("SCANN_B200_TWO_PHASE", "1")
+  if mode == "overflow":
+    monkeypatch.setenv("SCANN_B200_CAND_CAP", "256")   # overflowed queries are re-scanned by the SIMT kernel
+  c = get_case(**kw)
+  a = c.oracle.candidates(c.q)
+  b = c.native.candidates(c.q)
+  np.testing.assert_array_equal(a["count"], b["count"])
+  for i in range(len(c.q)):
+    n = a["count"][i]
+    np.testing.assert_array_equal(a["leaf"][i, :n], b["leaf"][i, :n])
+    np.testing.assert_array_equal(a["slot"][i, :n], b["slot"][i, :n])
+    np.testing.assert_array_equal(a["score"][i, :n].view(np.uint32), b["score"][i, :n].view(np.uint32))
+  i0, d0 = c.oracle.search_batched(c.q)
+  i1, d1 = c.native.search_batched(c.q)
+  np.testing.assert_array_equal(i0, i1)
+  np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
+@pytest.mark.parametrize("kw", [dict(nq=700), dict(nq=700, soar=1.5), dict(nq=500, distance="squared_l2", d=64, leaves=50, n=10000),
+                                dict(nq=300, leaves=30)],   # ~670 slots per leaf: three 256-slot tiles, the last one ragged
+                         ids=["dot", "soar", "l2", "tiles"])
+def test_tensor_core_scan_with_several_query_blocks_per_leaf(kw, monkeypatch):
+  """Hundreds of queries per leaf: several 64-query blocks (the last one ragged) per leaf, several items per CTA;
+  the tensor-core scan, the octs and the oracle agree bit for bit."""
+  c = get_case(**kw)
+  out = {}
+  for tc in ("0", "1"):
+    monkeypatch.setenv("SCANN_B200_SCAN_TC", tc)
+    out[tc] = c.native.search_batched(c.q, leaves=40)
+    assert c.native.stats()["overflow_retries"] == 0
+  np.testing.assert_array_equal(out["0"][0], out["1"][0])
+  np.testing.assert_array_equal(out["0"][1].view(np.uint32), out["1"][1].view(np.uint32))
+  i0, d0 = c.oracle.search_batched(c.q, leaves=40, impl=1)
+  np.testing.assert_array_equal(i0, out["1"][0])
+  np.testing.assert_array_equal(d0.view(np.uint32), out["1"][1].view(np.uint32))
+
+
 def test_host_call_with_page_locked_buffers_matches_pageable():
   """scann_b200_search_batched copies page-locked caller memory to / from the device directly."""
   import torch
