@@ -74,6 +74,10 @@ WORKLOADS = {
 # (9 slots per 256 lookups -> 113.8 lookups), ALU pipe 64 lanes (4 warp instructions = 8 SMSP-clocks per 256 lookups per
 # SMSP -> 128), shared memory 128 B (one LDS.64 = 256 B -> 128).
 ONCHIP = {"issue_slots": 4.0 / 9.0 * 256.0, "alu_pipe": 128.0, "lds_bandwidth": 128.0}
+# Wide quads (sparse work lists, scan.cu score_wquad_addr): 1 LDS.64 + 2 adds = 3 issue slots per 4 queries x 32 slots
+# = 128 lookups -> 170.7; one LDS.64 = 256 B of shared-memory bandwidth per 128 lookups -> 64.  Both at FULL tables:
+# a leaf probed by q queries costs ceil(q / 4) quads, and `achieved` counts the useful lookups only.
+ONCHIP_WIDE = {"issue_slots": 4.0 / 3.0 * 128.0, "lds_bandwidth": 64.0}
 
 
 def log(*a):
@@ -305,16 +309,23 @@ def scan_roofline(agg, peaks, peak_src, clocks, traffic_file=None):
   lookups_per_s = 2 * achieved * 1e9
   mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
   per_clk_sm = lookups_per_s / (148.0 * mhz * 1e6) if mhz else None
-  ceil = min(ONCHIP.values())
-  return {"bound": "hbm", "kernel": "scan_main_kernel<W, NL>", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+  wide = agg.get("scan_wide_launches", 0) > agg.get("scan_oct_launches", 0)
+  tc = agg.get("scan_tc_launches", 0) > 0
+  ceilings = ONCHIP_WIDE if wide else ONCHIP
+  ceil = min(ceilings.values())
+  kernel = "tc::scan_tc_kernel<W>" if tc else ("scan_main_kernel<W, NL, wide quads>" if wide else "scan_main_kernel<W, NL, octs>")
+  note = ("the codes are read from DRAM about once per batch (traffic << algorithmic bytes), so the kernel is bound on "
+          "chip: " + ("3 issue slots and one 256-byte shared-memory access per warp-wide wide-quad lookup (4 queries)" if wide
+                      else "9 issue slots per warp-wide oct lookup (8 queries)"))
+  return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "peak_source": peak_src,
           "unit": "GB/s", "frac": achieved / peak if peak else None,
           "traffic": ncu_traffic(traffic_file) if traffic_file else None,
           "alg_bytes_per_launch": bytes_per_launch, "ms_per_launch": ms_per_launch, "lookups_per_s": lookups_per_s,
-          "onchip": {"unit": "(query, slot, block) lookups per clock per SM", "ceilings": ONCHIP,
-                     "binding": min(ONCHIP, key=ONCHIP.get), "achieved": per_clk_sm, "sm_mhz_used": mhz,
-                     "frac": per_clk_sm / ceil if per_clk_sm else None,
-                     "note": "the codes are read from DRAM about once per batch (traffic << algorithmic bytes), so "
-                             "the kernel is bound on chip: 9 issue slots per warp-wide oct lookup"}}
+          "scan_launches": {"octs": int(agg.get("scan_oct_launches", 0)), "wide_quads": int(agg.get("scan_wide_launches", 0)),
+                            "tensor_cores": int(agg.get("scan_tc_launches", 0))},
+          "onchip": {"unit": "(query, slot, block) lookups per clock per SM", "ceilings": ceilings,
+                     "binding": min(ceilings, key=ceilings.get), "achieved": per_clk_sm, "sm_mhz_used": mhz,
+                     "frac": per_clk_sm / ceil if per_clk_sm else None, "note": note}}
 
 
 def e2e_host_run(ix, q_pin, nq, k, steps, callers):
@@ -490,7 +501,10 @@ def c5_section(args, rank, world, local_rank, dev, dist, flush, peaks, peak_src)
                 "stage_ms_per_step": {s_: agg[s_] / steps for s_ in STAGES if s_ in agg},
                 "scan_GBps_alg": agg["scan_bytes_alg"] / steps / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None,
                 "scan_frac_of_hbm_peak": agg["scan_bytes_alg"] / steps / (scan_ms * 1e-3) / 1e9 / float(peaks["hbm_gbs"]) if scan_ms > 0 else None,
-                "candidates_per_query": agg["cand_sum"] / steps / nq}
+                "candidates_per_query": agg["cand_sum"] / steps / nq,
+                "queries_per_probed_leaf": nq * wl["probe"] / wl["leaves"],
+                "scan_roofline": scan_roofline(agg, peaks, peak_src, None,
+                                               "r02_scan_c5sparse_traffic.json" if nq * wl["probe"] / wl["leaves"] <= 8 else None)}
       # host buffers end to end
       hq = torch.from_numpy(q).pin_memory().numpy()
       oi = torch.empty((nq, k), dtype=torch.int32).pin_memory()

@@ -305,6 +305,9 @@ typedef struct {
   uint64_t exchange_bytes;     /* bytes this rank sent in the last call */
   uint32_t bf_widenings;       /* brute force: re-runs with a wider candidate window / safe rounds (0 in the common case) */
   uint32_t bf_exact_fallbacks; /* brute force: queries finished by the exact all-rows kernel */
+  /* main-scan launches by kernel: octs (dense work lists), wide quads (sparse ones), tensor cores (opt-in) */
+  uint32_t scan_oct_launches, scan_wide_launches, scan_tc_launches;
+  uint32_t reserved0;
 } scann_b200_stats;
 /* Timing (CUDA events on the index's stream) and traffic figures of the last search call. */
 int scann_b200_last_stats(scann_b200_index* index, scann_b200_stats* out);

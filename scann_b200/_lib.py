@@ -41,6 +41,8 @@ class Stats(C.Structure):
       ("tokenize_fallbacks", C.c_uint64),
       ("ms_exchange", C.c_float), ("ms_merge", C.c_float), ("exchange_bytes", C.c_uint64),
       ("bf_widenings", C.c_uint32), ("bf_exact_fallbacks", C.c_uint32),
+      ("scan_oct_launches", C.c_uint32), ("scan_wide_launches", C.c_uint32), ("scan_tc_launches", C.c_uint32),
+      ("reserved0", C.c_uint32),
   ]
 
   def as_dict(self):

@@ -482,6 +482,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   fill_scan_work(ix, nq, p, cap, &w);
   int launches = 0;
   uint32_t scan_launches = 0, retries = 0;
+  uint32_t mode_launches[3] = {0, 0, 0};
 
   CU(cudaMemsetAsync(w.counters, 0, sizeof(uint32_t) * 8, s));
   CU(cudaMemsetAsync(w.stats, 0, sizeof(unsigned long long) * 4, s));
@@ -517,7 +518,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   CU(cudaGetLastError());
   CU(cudaEventRecord(ix->ev[EV_WORK], s));
   CU(sb::launch_scan(v, w, 0, s));
-  launches += 1; scan_launches += 1;
+  launches += 1; scan_launches += 1; mode_launches[w.scan_mode < 3 ? w.scan_mode : 0] += 1;
   CU(cudaEventRecord(ix->ev[EV_SCAN], s));
   int ncl = 0;
   CU(sb::launch_compact(v, w, false, s, &ncl));
@@ -530,7 +531,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
     CU(cudaGetLastError());
     CU(cudaEventRecord(ix->ev[EV2_WORK], s));
     CU(sb::launch_scan(v, w, 0, s));
-    launches += 1; scan_launches += 1;
+    launches += 1; scan_launches += 1; mode_launches[w.scan_mode < 3 ? w.scan_mode : 0] += 1;
     CU(cudaEventRecord(ix->ev[EV2_SCAN], s));
     CU(sb::launch_compact(v, w, false, s, &ncl));
     launches += ncl;
@@ -568,7 +569,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
       sb::launch_worklist(v, w, true, false, s, &launches);
       CU(sb::launch_scan(v, w, 0, s));
       CU(sb::launch_compact(v, w, true, s, &ncl));
-      launches += 1 + ncl; scan_launches += 1;
+      launches += 1 + ncl; scan_launches += 1; mode_launches[w.scan_mode < 3 ? w.scan_mode : 0] += 1;
       CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
     }
@@ -597,6 +598,7 @@ int search_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, const Para
   st.kernel_launches += (uint32_t)launches;
   st.overflow_retries += retries;
   st.scan_kernel_count += scan_launches;
+  st.scan_oct_launches += mode_launches[0]; st.scan_wide_launches += mode_launches[1]; st.scan_tc_launches += mode_launches[2];
   st.ms_tokenize += ms[EV_TOK]; st.ms_lut += ms[EV_LUT]; st.ms_pilot += ms[EV_PILOT];
   st.ms_worklist += ms[EV_WORK]; st.ms_scan += ms[EV_SCAN]; st.ms_compact += ms[EV_COMPACT];
   st.ms_finalize += ms[EV_FIN];

@@ -168,6 +168,7 @@ struct RankState {
   sb::ScanWork w{};
   int launches = 0;
   uint32_t scan_launches = 0, retries = 0;
+  uint32_t mode_launches[3] = {0, 0, 0};
   bool two_phase = false;
 };
 
@@ -267,7 +268,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
         CU(cudaGetLastError());
         CU(cudaEventRecord(ix->ev[EV_WORK], s));
         CU(sb::launch_scan(v, w, 0, s));
-        st.launches += 1; st.scan_launches += 1;
+        st.launches += 1; st.scan_launches += 1; st.mode_launches[w.scan_mode < 3 ? w.scan_mode : 0] += 1;
         CU(cudaEventRecord(ix->ev[EV_SCAN], s));
         CU(sb::launch_compact(v, w, false, s, &ncl));
         st.launches += ncl;
@@ -279,7 +280,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
           CU(cudaGetLastError());
           CU(cudaEventRecord(ix->ev[EV2_WORK], s));
           CU(sb::launch_scan(v, w, 0, s));
-          st.launches += 1; st.scan_launches += 1;
+          st.launches += 1; st.scan_launches += 1; st.mode_launches[w.scan_mode < 3 ? w.scan_mode : 0] += 1;
           CU(cudaEventRecord(ix->ev[EV2_SCAN], s));
           CU(sb::launch_compact(v, w, false, s, &ncl));
           st.launches += ncl;
@@ -301,7 +302,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
           sb::launch_worklist(v, w, true, false, s, &st.launches);
           CU(sb::launch_scan(v, w, 0, s));
           CU(sb::launch_compact(v, w, true, s, &ncl));
-          st.launches += 1 + ncl; st.scan_launches += 1;
+          st.launches += 1 + ncl; st.scan_launches += 1; st.mode_launches[w.scan_mode < 3 ? w.scan_mode : 0] += 1;
           CU(cudaMemcpyAsync(hc, w.counters, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
           CU(cudaStreamSynchronize(s));
         }
@@ -420,6 +421,7 @@ int sharded_chunk(Coll& coll, const std::vector<const float*>& d_q, uint32_t nq,
     ls.kernel_launches += (uint32_t)st.launches;
     ls.overflow_retries += st.retries;
     ls.scan_kernel_count += st.scan_launches;
+    ls.scan_oct_launches += st.mode_launches[0]; ls.scan_wide_launches += st.mode_launches[1]; ls.scan_tc_launches += st.mode_launches[2];
     return 0;
   });
 }
