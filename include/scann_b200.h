@@ -100,7 +100,11 @@ int scann_b200_search_batched(scann_b200_index* index, const float* queries, uin
 
 /* Same computation with every buffer already resident on the index's device
  * (queries [nq][D] f32, outputs [nq][out_k]); enqueued on the index's stream and
- * synchronised before returning.  This is the kernel-side throughput leg of bench.py. */
+ * synchronised before returning.  This is the kernel-side throughput leg of bench.py.
+ * Stream ordering: the index's streams are non-blocking and do NOT wait for the caller's streams.  The
+ * producer of d_queries (and of any other device input of the *_device entry points) must have COMPLETED
+ * -- cudaStreamSynchronize / cudaEventSynchronize on the caller's side -- before the call; the outputs are
+ * complete when the call returns. */
 int scann_b200_search_batched_device(scann_b200_index* index, const float* d_queries, uint32_t nq,
                                      int32_t final_nn, int32_t pre_reorder_nn, int32_t leaves,
                                      uint32_t* d_out_idx, float* d_out_dist, int32_t out_k);

@@ -692,7 +692,11 @@ int load(const char* dir, const char* assets_pbtxt, Assets** out) {
   std::string err;
   if (!parse_text(a->config_text, &a->config, &err)) return afail(SCANN_B200_INTERNAL, "config round trip failed: %s", err.c_str());
   Node assets;
-  if (!parse_text(assets_pbtxt ? assets_pbtxt : "", &assets, &err)) return afail(SCANN_B200_INVALID_ARGUMENT, "Failed to parse scann_assets.pbtxt: %s", err.c_str());
+  // scann.cc LoadArtifacts(artifacts_dir) reads <artifacts_dir>/scann_assets.pbtxt itself when it is handed no text
+  std::string assets_text = assets_pbtxt ? assets_pbtxt : "";
+  if (assets_text.find_first_not_of(" \t\r\n") == std::string::npos)
+    if (int rc = read_file(std::string(dir) + "/scann_assets.pbtxt", &assets_text)) return rc;
+  if (!parse_text(assets_text.c_str(), &assets, &err)) return afail(SCANN_B200_INVALID_ARGUMENT, "Failed to parse scann_assets.pbtxt: %s", err.c_str());
   // dependency order of scann.cc:105-233: partitioner, then tokenization, then the rest
   for (int pass = 0; pass < 3; ++pass) {
     for (const Node& as : assets.kids) {
@@ -757,6 +761,7 @@ int load(const char* dir, const char* assets_pbtxt, Assets** out) {
     if (!a->has_dataset && !a->has_bf16) { a->n = (uint32_t)a->int8.shape[0]; a->d = (uint32_t)a->int8.shape[1]; }
     if (!a->has_int8_mult || a->int8_mult.shape[0] != a->int8.shape[1])
       return afail(SCANN_B200_INVALID_ARGUMENT, "int8_dataset.npy needs int8_multipliers.npy with one entry per dimension");
+    if (a->has_dp_norms && a->dp_norms.shape[0] == 0) a->has_dp_norms = false;  // dot product: the reference may write an empty norms file
     if (a->has_dp_norms && a->dp_norms.shape[0] != a->int8.shape[0])
       return afail(SCANN_B200_INVALID_ARGUMENT, "dp_norms.npy has %zu entries, int8_dataset.npy has %zu rows", a->dp_norms.shape[0], a->int8.shape[0]);
   }

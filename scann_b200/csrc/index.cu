@@ -99,7 +99,9 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   if (!L || !B) return fail(SCANN_B200_UNIMPLEMENTED, "only tree-AH and bf16 brute-force indexes are implemented (n_leaves=%u, n_blocks=%u)", L, B);
   if (!d->centers || !d->tokens || !d->codes || !d->codebook)
     return fail(SCANN_B200_INVALID_ARGUMENT, "tree-AH index needs centers, tokens, codes and codebook");
-  if (B > 128) return fail(SCANN_B200_UNIMPLEMENTED, "n_blocks=%u > 128 not supported yet", B);
+  // B <= 256: the reference's int16 accumulator covers it (CanUseInt16Accumulator, asymmetric_hashing_impl.cc:656-688);
+  // above that it switches to 32-bit sums, which this path does not restate
+  if (B > 256) return fail(SCANN_B200_UNIMPLEMENTED, "n_blocks=%u > 256 not supported", B);
   if (d->soar && !d->soar_codes) return fail(SCANN_B200_INVALID_ARGUMENT, "SOAR index without soar_codes");
   const int world = d->shard_world > 0 ? d->shard_world : 1, rank = d->shard_rank;
   if (rank < 0 || rank >= world) return fail(SCANN_B200_INVALID_ARGUMENT, "bad shard rank %d/%d", rank, world);

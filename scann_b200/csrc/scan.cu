@@ -112,6 +112,24 @@ __device__ __forceinline__ int score_one(const uint32_t (&w)[W], const unsigned 
   return (int)(s0 + s1);
 }
 
+// Runtime-W pilot scoring (generic kernels): the code words come straight from global memory, one at a time.
+__device__ __forceinline__ int score_one_rt(const uint32_t* __restrict__ gbase, int lane, int W, const unsigned char* tbl, int nlast) {
+  uint32_t s0 = 0, s1 = 0;
+#pragma unroll 1
+  for (int j = 0; j < W; ++j) {
+    const uint32_t word = load_code_word(gbase, lane, W, j);
+    const int nk = j == W - 1 ? nlast : 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (k < nk) {
+        const uint32_t v = tbl[(8 * j + k) * 16 + ((word >> (4 * k)) & 0xFu)];
+        if (k & 1) s1 += v; else s0 += v;
+      }
+    }
+  }
+  return (int)(s0 + s1);
+}
+
 // Main-scan scoring.  An OCT of eight queries shares one table of 64-bit entries
 //   T[b][c] = { lut0 | lut1 << 8 | lut2 << 16 | lut3 << 24,  lut4 | lut5 << 8 | lut6 << 16 | lut7 << 24 },
 // so one LDS.64 (the LSU issues about one warp-wide shared load per two cycles whatever its width)
@@ -420,9 +438,12 @@ __device__ __forceinline__ uint64_t block_select_bound(const uint64_t* s, uint32
 // ---------------------------------------------------------------------------------------
 // Pilot: one CTA per query, nearest leaves first, exact top-N threshold in shared memory.
 // ---------------------------------------------------------------------------------------
-template <int W>
+// W = 0: the generic instantiation for 16 < ix.W <= 32 (128 < B <= 256 blocks, asymmetric_hashing_impl.cc:656-688:
+// still the int16 accumulator): the word count is a runtime value and the code words are loaded one at a time.
+template <int WT>
 __global__ void __launch_bounds__(kScanThreads)
 pilot_kernel(DevIndex ix, ScanWork w, int capl) {
+  const int W = WT ? WT : (int)ix.W;
   extern __shared__ __align__(16) unsigned char smem[];
   uint32_t* tbl = reinterpret_cast<uint32_t*>(smem);                  // [W*128]
   uint64_t* scand = reinterpret_cast<uint64_t*>(smem + W * 128 * 4);  // [capl]
@@ -507,9 +528,14 @@ pilot_kernel(DevIndex ix, ScanWork w, int capl) {
       if (w.pilot_partial && seen + g0 * 32 >= w.pilot_target) break;  // enough slots sampled (slot order = id order)
       const uint32_t g = g0 + warp;
       if (g < ng) {
-        uint32_t cw[W];
-        load_codes<W>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
-        const int s0 = score_one<W>(cw, reinterpret_cast<const unsigned char*>(tbl), nlast);
+        int s0;
+        if constexpr (WT != 0) {
+          uint32_t cw[WT ? WT : 1];
+          load_codes<(WT ? WT : 1)>(ix.codes + (size_t)(gbeg + g) * W * 32, lane, cw);
+          s0 = score_one<(WT ? WT : 1)>(cw, reinterpret_cast<const unsigned char*>(tbl), nlast);
+        } else {
+          s0 = score_one_rt(ix.codes + (size_t)(gbeg + g) * W * 32, lane, W, reinterpret_cast<const unsigned char*>(tbl), nlast);
+        }
         bool p = (g * 32 + lane < n) && s0 <= s_thr;
         uint64_t key = 0;
         if (p) {
@@ -832,11 +858,12 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
   float (&s_bias)[kMaxQPI] = meta.bias;
   __shared__ uint32_t s_item;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nlast = (int)ix.B - 8 * (W - 1);
+  const int Wr = W ? W : (int)ix.W;  // W = 0: the generic instantiation (16 < ix.W <= 32), wide quads only
+  const int nlast = (int)ix.B - 8 * (Wr - 1);
   const int off128 = 128 * (int)ix.B;
   const uint32_t n_items = w.counters[1];
   const uint32_t qpi = w.quads_per_item * kQueriesPerQuad;
-  constexpr int kTblEntries = W * 128;
+  const int kTblEntries = Wr * 128;
   // Items are claimed one ahead: the atomic for item i + 1 is issued when item i starts and its result is only needed
   // when item i is done, so its round trip (and the item -> leaf lookup) overlaps the scoring.
   if (tid == 0) s_item = atomicAdd(&w.counters[0], 1u);
@@ -902,10 +929,69 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
       else build_oct_table(tables + (size_t)qd * kTblEntries, lp, kTblEntries, tid, kScanThreads);
     }
     __syncthreads();
+    if constexpr (W == 0) {
+      // Generic path (128 < B <= 256): one code word at a time, the nibbles of a word against up to four wide quads;
+      // the u16 lanes hold sums up to 256 * 255 = 65280, so the threshold test unpacks them (the packed test of the
+      // specialised kernels needs sums below 2^15).
+      static_assert(WIDE == 1, "the generic scan kernel uses wide quads");
+      const uint32_t tb32 = (uint32_t)__cvta_generic_to_shared(tables);
+      const uint32_t kstage = kStageKeys / qpi;
+      for (uint32_t g = g0 + warp; g < g1; g += kScanWarps) {
+        const bool valid = g * 32 + lane < nleaf;
+        const uint32_t gslot = (gbeg + g) * 32 + lane;
+        const uint32_t* gbase = ix.codes + (size_t)(gbeg + g) * Wr * 32;
+        uint32_t ax[4] = {0u, 0u, 0u, 0u}, ay[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int j = 0; j < Wr; ++j) {
+          const uint32_t word = load_code_word(gbase, lane, Wr, j);
+          const int nk = j == Wr - 1 ? nlast : 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (k < nk) {
+              const uint32_t a = tb32 + (uint32_t)((8 * j + k) * 128) + (((word >> (4 * k)) & 0xFu) << 3);
+#pragma unroll
+              for (int qd = 0; qd < 4; ++qd) {
+                if ((uint32_t)qd < nquads) {
+                  uint32_t vx, vy;
+                  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vx), "=r"(vy) : "r"(a + (uint32_t)qd * (uint32_t)kTblEntries * 8u));
+                  ax[qd] += vx; ay[qd] += vy;
+                }
+              }
+            }
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            if ((uint32_t)qd >= nquads) break;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t wv = (i & 2) ? ay[qd] : ax[qd];
+              const int sv = (int)((i & 1) ? (wv >> 16) : (wv & 0xFFFFu));
+              const uint32_t qi = (uint32_t)qd * 4u + (uint32_t)i;
+              if (sv <= s_thr[qi]) {
+                const uint64_t key = make_key(ah_float_score(sv - off128, s_inv[qi], s_bias[qi]), ix.key_by_dp ? ix.slot_dp[gslot] : gslot);
+                if (key < s_tau[qi]) {
+                  uint32_t pos = w.stage ? atomicAdd(&meta.scnt[qi], 1u) : kstage;
+                  if (pos < kstage) {
+                    meta.sbuf[qi * kstage + pos] = key;
+                  } else {
+                    const uint32_t qq = s_q[qi];
+                    const uint32_t gpos = atomicAdd(&w.cnt[qq], 1u);
+                    if (gpos < w.cap) w.buf[(size_t)qq * w.cap + gpos] = key;
+                    else w.ovf[qq] = 1u;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    } else {
     // The code words of the warp's next group are requested as soon as the current group's lookup addresses have been
     // formed from them (the registers are free again), so their DRAM latency overlaps the scoring of the current group.
-    uint32_t cw[W];
-    if (g0 + warp < g1) load_codes<W>(ix.codes + (size_t)(gbeg + g0 + warp) * W * 32, lane, cw);
+    uint32_t cw[W ? W : 1];
+    if (g0 + warp < g1) load_codes<(W ? W : 1)>(ix.codes + (size_t)(gbeg + g0 + warp) * W * 32, lane, cw);
     for (uint32_t g = g0 + warp; g < g1; g += kScanWarps) {
       const bool valid = g * 32 + lane < nleaf;
       const uint32_t gslot = (gbeg + g) * 32 + lane;
@@ -958,6 +1044,7 @@ scan_main_kernel(DevIndex ix, ScanWork w) {
 #undef SB_DO_QUAD
       }
     }
+    }  // W != 0
     // item epilogue: publish the staged candidates, one warp per query, one global atomicAdd per (query, item)
     if (w.stage) {
       __syncthreads();
@@ -1095,6 +1182,24 @@ compact_big_kernel(ScanWork w, int dedup, int medium) {
 // Runs the MAIN scan's scoring path (oct table, score_oct_addr<W, NL, 0>, the same (W, NL) instantiation launch_scan
 // picks): the LUT sits in oct lane `lane_q` (the other seven tables are zero), so calls with different lanes cover all
 // eight u16 accumulator positions.
+// generic instantiation (16 < W <= 32): the pilot's runtime-W scoring over the plain u8 LUT
+__global__ void __launch_bounds__(kScanThreads)
+leaf_scores_generic_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, int16_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = (int)ix.W;
+  for (int t = tid; t < W * 32; t += kScanThreads) reinterpret_cast<uint32_t*>(smem)[t] = reinterpret_cast<const uint32_t*>(lut)[t];
+  __syncthreads();
+  const int nlast = (int)ix.B - 8 * (W - 1);
+  const uint32_t gbeg = ix.leaf_goff[leaf], ng = ix.leaf_goff[leaf + 1] - gbeg;
+  const uint32_t n = ix.leaf_size[leaf];
+  for (uint32_t g = blockIdx.x * kScanWarps + warp; g < ng; g += gridDim.x * kScanWarps) {
+    const int sum = score_one_rt(ix.codes + (size_t)(gbeg + g) * W * 32, lane, W, smem, nlast);
+    const uint32_t slot = g * 32 + lane;
+    if (slot < n) out[slot] = (int16_t)(sum - 128 * (int)ix.B);
+  }
+}
+
 template <int W, int NL>
 __global__ void __launch_bounds__(kScanThreads)
 leaf_scores_kernel(DevIndex ix, const uint8_t* __restrict__ lut, uint32_t leaf, int lane_q, uint32_t one,
@@ -1175,6 +1280,12 @@ cudaError_t launch_pilot(const DevIndex& ix, const ScanWork& w, cudaStream_t s) 
   cudaError_t em = cudaMemsetAsync(w.leaf_cnt, 0, sizeof(uint32_t) * (ix.L + 1), s);
   if (em != cudaSuccess) return em;
   const size_t smem = pilot_smem_bytes(ix, w);
+  if (ix.W > 16 && ix.W <= 32) {  // generic instantiation
+    cudaError_t e = cudaFuncSetAttribute(pilot_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    pilot_kernel<0><<<w.nq, kScanThreads, smem, s>>>(ix, w, capl);
+    return cudaGetLastError();
+  }
   SB_DISPATCH_W(ix.W, {
     cudaError_t e = cudaFuncSetAttribute(pilot_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1220,6 +1331,7 @@ void scan_prepare_phase(const DevIndex& ix, ScanWork* w) {
   if (et && (et[0] == '0' || et[0] == '1')) tc = et[0] == '1' && tc_ok;
   bool wide = w->qpl_per_rank > 0.f && qpl <= wide_limit;
   if (ew && (ew[0] == '0' || ew[0] == '1')) wide = ew[0] == '1';
+  if (ix.W > 16) { tc = false; wide = true; }  // 128 < B <= 256: the generic kernel (wide quads, unpacked thresholds)
   if (w->max_gpt_simt == 0) w->max_gpt_simt = w->max_gpt;
   if (tc) {
     // items = (leaf, block of 64 queries): eight "octs" per item, the whole leaf in one tile
@@ -1235,6 +1347,10 @@ cudaError_t launch_scan(const DevIndex& ix, const ScanWork& w, int grid, cudaStr
   if (w.scan_mode == 2) return launch_scan_tc(ix, w, s);
   const bool wide = w.scan_mode == 1;
   const size_t smem = scan_smem_bytes(ix, w.quads_per_item * (wide ? 2u : 1u));
+  if (ix.W > 16 && ix.W <= 32) {  // generic instantiation, wide quads only (scan_prepare_phase)
+    if (!wide) return cudaErrorInvalidValue;
+    return launch_scan_t<0, 0, 1>(ix, w, grid, smem, s);
+  }
   // the common block counts (B % 8 == 0, 2, 4) get a kernel without padded lookups
   const int nlast = (int)ix.B - 8 * ((int)ix.W - 1);
   if (wide) {
@@ -1292,6 +1408,10 @@ static cudaError_t launch_leaf_scores_t(const DevIndex& ix, const uint8_t* lut, 
 }
 
 cudaError_t launch_leaf_scores(const DevIndex& ix, const uint8_t* lut, uint32_t leaf, int16_t* out, cudaStream_t s) {
+  if (ix.W > 16 && ix.W <= 32) {
+    leaf_scores_generic_kernel<<<8, kScanThreads, (size_t)ix.W * 128, s>>>(ix, lut, leaf, out);
+    return cudaGetLastError();
+  }
   const int nlast = (int)ix.B - 8 * ((int)ix.W - 1);
   const int lane_q = (int)(leaf & 7u);
   SB_DISPATCH_W(ix.W, {

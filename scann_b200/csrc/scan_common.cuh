@@ -27,6 +27,14 @@ __device__ __forceinline__ void load_codes(const uint32_t* __restrict__ gbase, i
   }
 }
 
+// Runtime-W variant (the generic kernels for 16 < W <= 32, i.e. 128 < B <= 256 blocks): word j of this lane.
+__device__ __forceinline__ uint32_t load_code_word(const uint32_t* __restrict__ gbase, int lane, int W, int j) {
+  const int N4 = W / 4, R = W % 4;
+  if (j < 4 * N4) return __ldg(gbase + (j >> 2) * 128 + lane * 4 + (j & 3));
+  if (R >= 2 && j < 4 * N4 + 2) return __ldg(gbase + N4 * 128 + lane * 2 + (j - 4 * N4));
+  return __ldg(gbase + N4 * 128 + ((R >= 2) ? 64 : 0) + lane);
+}
+
 // Largest accumulator value whose float score is <= the score of `tau` (conservative integer
 // pre-filter; the reference's trunc((eps - bias) * mult) of lut16_avx2.inc:432-438 may drop a
 // candidate that is strictly better than eps, this one never does).

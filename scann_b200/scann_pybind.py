@@ -63,6 +63,13 @@ class _Plan:
       unimpl("PCA/truncate projections and upper_tree")
     if p.get("query_tokenization_type", "FLOAT") != "FLOAT":
       unimpl("quantized centroids")
+    # training options the GPU trainer does not honour are refused, not dropped (a user who asks for anisotropic
+    # centroids must not get plain k-means silently)
+    avq = cfgmod.as_float(p.get("avq"), math.nan)
+    if avq is not None and not math.isnan(avq):
+      unimpl("anisotropic (AVQ) partitioning")
+    if p.get("single_machine_center_initialization", "RANDOM_INITIALIZATION") != "RANDOM_INITIALIZATION":
+      unimpl("k-means centre initialisation other than RANDOM_INITIALIZATION")
     if p.path("query_spilling", "spilling_type") not in ("FIXED_NUMBER_OF_CENTERS",):
       unimpl("query spilling other than FIXED_NUMBER_OF_CENTERS")
     if ah.get("lookup_type") != "INT8_LUT16" or cfgmod.as_int(ah.get("num_clusters_per_block"), 256) != 16:

@@ -33,8 +33,8 @@ def test_struct_layouts_match_header():
   assert ctypes.sizeof(_lib.EncodeDesc) == 24 + 32 + 8 + 8 + 8
   # 4 floats, 4 u64, u32 (+pad)
   assert ctypes.sizeof(_lib.EncodeStats) == 16 + 32 + 8
-  # ... + ms_exchange, ms_merge, exchange_bytes, bf_widenings, bf_exact_fallbacks
-  assert ctypes.sizeof(_lib.Stats) == 24 + 8 + 32 + 4 + 4 + 16 + 8 + 8 + 8 + 8
+  # ... + ms_exchange, ms_merge, exchange_bytes, bf_widenings, bf_exact_fallbacks, 3 scan-launch counters + reserved
+  assert ctypes.sizeof(_lib.Stats) == 24 + 8 + 32 + 4 + 4 + 16 + 8 + 8 + 8 + 8 + 16
 
 
 def test_create_fails_loudly_without_gpu_or_arguments():

@@ -17,6 +17,10 @@ CASES = [
     dict(n=6000, leaves=300, probe=300, pre=50, d=32),               # every leaf probed (P > 256: block top-P path)
     dict(distance="squared_l2", d=64, leaves=50, n=10000),           # TreeXHybridSMMD semantics (C4 shape family)
     dict(distance="squared_l2", d=30, dpb=4, leaves=20, n=5000, probe=6, pre=64),
+    # 128 < B <= 256 (still the reference's int16 accumulator, asymmetric_hashing_impl.cc:656-688): the generic kernels
+    dict(dpb=1, d=130, leaves=40, n=6000),          # B=130 (W=17, two blocks in the last word)
+    dict(dpb=2, d=512, leaves=30, n=4000, soar=1.5),  # B=256 (W=32): sums up to 65280 in the u16 lanes
+    dict(distance="squared_l2", dpb=1, d=200, leaves=25, n=5000),  # B=200 (W=25)
 ]
 
 
