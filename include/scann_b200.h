@@ -45,7 +45,9 @@ typedef struct scann_b200_index scann_b200_index;
  *                   int8_multipliers (+ dp_norms) for fixed-point reordering)
  *   brute force  : n_leaves = n_blocks = 0 and bf16_dataset (Bfloat16BruteForceSearcher,
  *                  brute_force/bfloat16_brute_force.cc:101-152) or dataset (BruteForceSearcher<float>,
- *                  brute_force/brute_force.cc:376-393); dot product only
+ *                  brute_force/brute_force.cc:376-393); bf16: dot product only (as the reference), float rows:
+ *                  dot product or squared L2
+ *   n_blocks     : up to 256 (the reference's int16-accumulator range, asymmetric_hashing_impl.cc:656-688)
  */
 typedef struct {
   int32_t distance;            /* SCANN_B200_DOT_PRODUCT | SCANN_B200_SQUARED_L2 */

@@ -211,16 +211,17 @@ def bruteforce_bf16(db_bf16, q, k, threads=1):
   return idx, dist
 
 
-def bruteforce_f32(db, q, k, threads=1):
-  """Exact float brute force on the CPU (sequential fnmadd chain): db [N, D] f32, q [nq, D] f32."""
+def bruteforce_f32(db, q, k, threads=1, distance="dot_product"):
+  """Exact float brute force on the CPU (sequential fnmadd chain): db [N, D] f32, q [nq, D] f32; dot product or
+  squared L2 (the many-to-many kernel's ||x||^2 + ||q||^2 - 2 <q, x> chain)."""
   L = lib()
-  L.so_bruteforce_f32.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
-                                  C.c_void_p, C.c_void_p, C.c_int]
+  fn = L.so_bruteforce_f32 if distance == "dot_product" else L.so_bruteforce_f32_l2
+  fn.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
   db = np.ascontiguousarray(db, dtype=np.float32)
   q = np.ascontiguousarray(q, dtype=np.float32)
   idx = np.empty((q.shape[0], k), dtype=np.uint32)
   dist = np.empty((q.shape[0], k), dtype=np.float32)
-  rc = L.so_bruteforce_f32(_p(db), db.shape[0], db.shape[1], _p(q), q.shape[0], k, _p(idx), _p(dist), threads)
+  rc = fn(_p(db), db.shape[0], db.shape[1], _p(q), q.shape[0], k, _p(idx), _p(dist), threads)
   if rc:
     raise RuntimeError(L.so_last_error().decode())
   return idx, dist

@@ -1115,6 +1115,53 @@ int so_bruteforce_f32(const float* db, uint32_t n, uint32_t d, const float* q, u
   return 0;
 }
 
+/* Float brute force, squared L2: the same searcher with SquaredL2Distance (brute_force/brute_force.cc:376-393 ->
+ * DenseDistanceManyToManyTopK<kIsSquaredL2>): database norms from the transposer, norm = fnmadd(x, x, norm) in
+ * dimension order, times -1, and the rows doubled (AugmentWithL2Norms, many_to_many_impl.inc:236-257); query norms
+ * from SquaredL2Norm (:417-426, double accumulation); acc = ||x||^2 + ||q||^2, then acc = fnmadd(q[d], 2 x[d], acc)
+ * sequentially in d (:527-567).  The distance is acc itself; k smallest (distance, index). */
+int so_bruteforce_f32_l2(const float* db, uint32_t n, uint32_t d, const float* q, uint32_t nq, int k, uint32_t* out_idx,
+                         float* out_dist, int threads) {
+  if (k <= 0) return fail("k must be positive");
+  float* xn = (float*)malloc(sizeof(float) * (n ? n : 1));
+  for (uint32_t r = 0; r < n; ++r) {
+    const float* x = db + (size_t)r * d;
+    float a = 0.0f;
+    for (uint32_t j = 0; j < d; ++j) a = fmaf(-x[j], x[j], a);
+    xn[r] = a * -1.0f;
+  }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 1 ? threads : 1)
+#endif
+  for (uint32_t i = 0; i < nq; ++i) {
+    topn_t tn;
+    topn_init(&tn, (size_t)k);
+    const float* qi = q + (size_t)i * d;
+    double qn = 0.0;
+    for (uint32_t j = 0; j < d; ++j) qn += (double)qi[j] * (double)qi[j];
+    const float qnf = (float)qn;
+    for (uint32_t r = 0; r < n; ++r) {
+      const float* x = db + (size_t)r * d;
+      float acc = xn[r] + qnf;
+      for (uint32_t j = 0; j < d; ++j) { const float x2 = x[j] * 2.0f; acc = fmaf(-qi[j], x2, acc); }
+      topn_push(&tn, ((uint64_t)f2ord(acc) << 32) | r);
+    }
+    topn_finish(&tn);
+    for (int j = 0; j < k; ++j) {
+      if ((size_t)j < tn.n) {
+        out_idx[(size_t)i * k + j] = (uint32_t)tn.buf[j];
+        out_dist[(size_t)i * k + j] = ord2f((uint32_t)(tn.buf[j] >> 32));
+      } else {
+        out_idx[(size_t)i * k + j] = 0;
+        out_dist[(size_t)i * k + j] = NAN;
+      }
+    }
+    free(tn.buf);
+  }
+  free(xn);
+  return 0;
+}
+
 /* ========================================================================= */
 /* index build, deterministic part: database             */
 /* tokenization, SOAR secondary assignment, residuals, AH encoding.            */

@@ -581,7 +581,17 @@ struct SafetyArgs {
   float eps_rel, max_row_norm;
   uint32_t* unsafe;    // [nq] flag per query
   uint32_t* n_unsafe;  // counter
+  // squared L2 (float brute force): the approximate keys live in the AUGMENTED dot-product space x' = [x, -||x||^2 / 2],
+  // q' = [q, 1] (t = ||x||^2 / 2 - <q, x> = (L2 - ||q||^2) / 2), the exact keys are squared-L2 chain values
+  int l2;
 };
+// ||q||^2 as SquaredL2Norm computes it for the many-to-many kernel (many_to_many_impl.inc:417-426): double accumulation
+// in dimension order, narrowed once
+__device__ __forceinline__ float query_sqnorm_ref(const float* sq, uint32_t d) {
+  double a = 0.0;
+  for (uint32_t i = 0; i < d; ++i) a += (double)sq[i] * (double)sq[i];
+  return (float)a;
+}
 __device__ __forceinline__ void check_window(const SafetyArgs& sa, uint32_t qi, const float* sq, uint32_t d, uint32_t m,
                                              uint32_t kprime, uint32_t kk, const uint64_t* src, const uint64_t* ka) {
   if (!sa.unsafe) return;
@@ -597,8 +607,15 @@ __device__ __forceinline__ void check_window(const SafetyArgs& sa, uint32_t qi, 
     bool bad = false;
     if (m == kprime && kk > 0 && qn > 0.f) {  // fewer than k' candidates = every row is one; zero query: all keys exact
       const float a_last = ord2f((uint32_t)(src[m - 1] >> 32));  // the buffer is sorted by the last compaction
-      const float e_k = ord2f((uint32_t)(ka[kk - 1] >> 32));
-      const float eps = sa.eps_rel * qn * sa.max_row_norm;
+      float e_k = ord2f((uint32_t)(ka[kk - 1] >> 32));
+      float eps = sa.eps_rel * qn * sa.max_row_norm;
+      if (sa.l2) {
+        // augmented query norm sqrt(||q||^2 + 1); the exact key back in the augmented scale; plus the rounding of the
+        // squared-L2 chain itself, (d + 4) ulps of (||q|| + ||x||)^2 (||x|| <= ||x'|| = max_row_norm)
+        const float qa = sqrtf(qn * qn + 1.0f) * 1.0001f;
+        eps = sa.eps_rel * qa * sa.max_row_norm + (float)(d + 4) * 1.2e-7f * (qn + sa.max_row_norm) * (qn + sa.max_row_norm);
+        e_k = 0.5f * (e_k - qn * qn * 0.9998f);
+      }
       bad = !(e_k < a_last - eps);
     }
     sa.unsafe[qi] = bad ? 1u : 0u;
@@ -656,13 +673,17 @@ rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db
 // Float brute force (BruteForceSearcher<float>::FinishBatchedSearchSimple, brute_force/brute_force.cc:376-393 ->
 // DenseDistanceManyToManyTopK, many_to_many_impl.inc:522-567): exact re-scoring of the k' candidates with the
 // reference's arithmetic, acc = 0; acc = fnmadd(q[d], x[d], acc) sequentially in d.  One thread per candidate.
+// xnorm != NULL: squared L2 (brute_force.cc:376-393 with SquaredL2Distance -> many_to_many_impl.inc:236-257,522-567):
+// acc = ||x||^2 + ||q||^2, then acc = fnmadd(q[d], 2 x[d], acc) sequentially in d; the distance is acc itself.
 __global__ void __launch_bounds__(128)
 rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ db, uint32_t d, const uint64_t* __restrict__ buf,
                    const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t kprime, uint32_t k, uint32_t out_k,
-                   uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int np2, SafetyArgs sa) {
+                   uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int np2, SafetyArgs sa,
+                   const float* __restrict__ xnorm) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint64_t* ka = reinterpret_cast<uint64_t*>(smem);
   float* sq = reinterpret_cast<float*>(ka + np2);
+  __shared__ float s_qn;
   const int tid = threadIdx.x;
   const uint32_t qi = blockIdx.x;
   const uint32_t m = min(cnt[qi], kprime);
@@ -670,10 +691,13 @@ rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ db, ui
   for (uint32_t i = tid; i < d; i += 128) sq[i] = q[(size_t)qi * d + i];
   for (int i = tid; i < np2; i += 128) ka[i] = kKeyMax;
   __syncthreads();
+  if (xnorm && tid == 0) s_qn = query_sqnorm_ref(sq, d);
+  __syncthreads();
+  const float two = xnorm ? 2.0f : 1.0f;  // 2 x is exact
   for (uint32_t c = tid; c < m; c += 128) {
     const uint32_t dp = (uint32_t)src[c];
     const float* x = db + (size_t)dp * d;
-    float acc = 0.f;
+    float acc = xnorm ? __fadd_rn(xnorm[dp], s_qn) : 0.f;
     if ((d & 3u) == 0) {
       for (uint32_t j = 0; j < d; j += 16) {  // 16 dims in flight before the first FMA of the chunk
         float4 v[4];
@@ -683,15 +707,15 @@ rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ db, ui
         for (int u = 0; u < 4; ++u) {
           const uint32_t jj = j + 4 * u;
           if (jj < d) {
-            acc = __fmaf_rn(-sq[jj], v[u].x, acc);
-            acc = __fmaf_rn(-sq[jj + 1], v[u].y, acc);
-            acc = __fmaf_rn(-sq[jj + 2], v[u].z, acc);
-            acc = __fmaf_rn(-sq[jj + 3], v[u].w, acc);
+            acc = __fmaf_rn(-sq[jj], __fmul_rn(v[u].x, two), acc);
+            acc = __fmaf_rn(-sq[jj + 1], __fmul_rn(v[u].y, two), acc);
+            acc = __fmaf_rn(-sq[jj + 2], __fmul_rn(v[u].z, two), acc);
+            acc = __fmaf_rn(-sq[jj + 3], __fmul_rn(v[u].w, two), acc);
           }
         }
       }
     } else {
-      for (uint32_t j = 0; j < d; ++j) acc = __fmaf_rn(-sq[j], __ldg(x + j), acc);
+      for (uint32_t j = 0; j < d; ++j) acc = __fmaf_rn(-sq[j], __fmul_rn(__ldg(x + j), two), acc);
     }
     ka[c] = make_key(acc, dp);
   }
@@ -702,7 +726,7 @@ rescore_f32_kernel(const float* __restrict__ q, const float* __restrict__ db, ui
   for (uint32_t i = tid; i < out_k; i += 128) {
     uint32_t id = 0;
     float dist = __uint_as_float(0x7FC00000u);
-    if (i < kk) { id = (uint32_t)ka[i] + id_base; dist = -ord2f((uint32_t)(ka[i] >> 32)); }
+    if (i < kk) { id = (uint32_t)ka[i] + id_base; dist = xnorm ? ord2f((uint32_t)(ka[i] >> 32)) : -ord2f((uint32_t)(ka[i] >> 32)); }
     out_idx[(size_t)qi * out_k + i] = id;
     out_dist[(size_t)qi * out_k + i] = dist;
   }
@@ -733,12 +757,16 @@ template <bool kF32>
 __global__ void __launch_bounds__(128)
 exact_round_kernel(const float* __restrict__ q, const void* __restrict__ dbv, uint32_t d, uint32_t dpitch,
                    const uint32_t* __restrict__ flagged, uint32_t row0, uint32_t row1, uint64_t* __restrict__ buf,
-                   uint32_t* __restrict__ cnt, const uint64_t* __restrict__ tau, uint32_t* __restrict__ ovf, uint32_t cap) {
+                   uint32_t* __restrict__ cnt, const uint64_t* __restrict__ tau, uint32_t* __restrict__ ovf, uint32_t cap,
+                   const float* __restrict__ xnorm) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* sq = reinterpret_cast<float*>(smem);
+  __shared__ float s_qn;
   const int tid = threadIdx.x;
   const uint32_t qi = flagged[blockIdx.y];
   for (uint32_t i = tid; i < d; i += 128) sq[i] = q[(size_t)qi * d + i];
+  __syncthreads();
+  if (kF32 && xnorm && tid == 0) s_qn = query_sqnorm_ref(sq, d);
   __syncthreads();
   const uint64_t t = tau[qi];
   const int l = tid & 7, grp = tid >> 3;
@@ -752,7 +780,12 @@ exact_round_kernel(const float* __restrict__ q, const void* __restrict__ dbv, ui
       // BruteForceSearcher<float>: acc = fnmadd(q[d], x[d], acc) sequentially in d -- one lane walks the row
       if (valid && l == 0) {
         const float* x = static_cast<const float*>(dbv) + (size_t)row * d;
-        for (uint32_t j = 0; j < d; ++j) r = __fmaf_rn(-sq[j], __ldg(x + j), r);
+        if (xnorm) {  // squared L2: ||x||^2 + ||q||^2, then fnmadd(q, 2 x)
+          r = __fadd_rn(xnorm[row], s_qn);
+          for (uint32_t j = 0; j < d; ++j) r = __fmaf_rn(-sq[j], __fmul_rn(__ldg(x + j), 2.0f), r);
+        } else {
+          for (uint32_t j = 0; j < d; ++j) r = __fmaf_rn(-sq[j], __ldg(x + j), r);
+        }
       }
     } else {
       const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(dbv) + (size_t)(valid ? row : row0) * dpitch;
@@ -788,7 +821,7 @@ __global__ void exact_prepare_kernel(uint32_t nq, const uint32_t* __restrict__ u
 
 __global__ void exact_emit_kernel(const uint32_t* __restrict__ flagged, const uint64_t* __restrict__ buf,
                                   const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t k, uint32_t out_k,
-                                  uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist) {
+                                  uint32_t id_base, uint32_t* __restrict__ out_idx, float* __restrict__ out_dist, int l2) {
   const uint32_t qi = flagged[blockIdx.x];
   const uint32_t kk = min(k, cnt[qi]);
   for (uint32_t i = threadIdx.x; i < out_k; i += blockDim.x) {
@@ -796,11 +829,33 @@ __global__ void exact_emit_kernel(const uint32_t* __restrict__ flagged, const ui
     float dist = __uint_as_float(0x7FC00000u);
     if (i < kk) {
       const uint64_t key = buf[(size_t)qi * cap + i];  // sorted by the last compaction
-      id = (uint32_t)key + id_base; dist = -ord2f((uint32_t)(key >> 32));
+      id = (uint32_t)key + id_base; dist = l2 ? ord2f((uint32_t)(key >> 32)) : -ord2f((uint32_t)(key >> 32));
     }
     out_idx[(size_t)qi * out_k + i] = id;
     out_dist[(size_t)qi * out_k + i] = dist;
   }
+}
+
+// ---- squared-L2 float brute force: row norms and the augmented rows of the pre-filter ----
+// ||x||^2 as the many-to-many transposer computes it (AugmentWithL2Norms, many_to_many_impl.inc:236-257):
+// norm = fnmadd(x, x, norm) in dimension order, times -1.
+__global__ void row_sqnorm_ref_kernel(const float* __restrict__ x, uint32_t n, uint32_t d, float* __restrict__ out) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const float* p = x + (size_t)r * d;
+  float a = 0.f;
+  for (uint32_t j = 0; j < d; ++j) { const float v = __ldg(p + j); a = __fmaf_rn(-v, v, a); }
+  out[r] = __fmul_rn(a, -1.0f);
+}
+// out [n][d + 1]: the row, then `last` (queries: 1) or -norm[r] / 2 (database rows)
+__global__ void augment_rows_kernel(const float* __restrict__ x, const float* __restrict__ norm, float last, uint32_t n,
+                                    uint32_t d, float* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)n * (d + 1);
+  if (i >= total) return;
+  const size_t r = i / (d + 1);
+  const uint32_t c = (uint32_t)(i - r * (d + 1));
+  out[i] = c < d ? x[r * d + c] : (norm ? -0.5f * norm[r] : last);
 }
 
 }  // namespace bf
@@ -975,8 +1030,21 @@ cudaError_t bf_exact_prepare(uint32_t nq, const uint32_t* unsafe, const ScanWork
   return cudaGetLastError();
 }
 
+cudaError_t bf_row_sqnorms(const float* x, uint32_t n, uint32_t d, float* out, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  bf::row_sqnorm_ref_kernel<<<(n + 127) / 128, 128, 0, s>>>(x, n, d, out);
+  return cudaGetLastError();
+}
+cudaError_t bf_augment_rows(const float* x, const float* norm, float last, uint32_t n, uint32_t d, float* out, cudaStream_t s) {
+  if (!n) return cudaSuccess;
+  const size_t total = (size_t)n * (d + 1);
+  bf::augment_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, norm, last, n, d, out);
+  return cudaGetLastError();
+}
+
 cudaError_t bf_exact_round(const float* q, const void* db, bool f32, uint32_t d, uint32_t dpitch, const uint32_t* flagged,
-                           uint32_t n_flagged, uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s) {
+                           uint32_t n_flagged, uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s,
+                           const float* xnorm) {
   if (!n_flagged || row1 <= row0) return cudaSuccess;
   const size_t smem = (((size_t)d + 3) & ~(size_t)3) * 4;
   const uint32_t ctas = std::min<uint32_t>(std::max<uint32_t>(1u, (row1 - row0 + 1023) / 1024), 1024u);
@@ -984,19 +1052,19 @@ cudaError_t bf_exact_round(const float* q, const void* db, bool f32, uint32_t d,
   if (f32) {
     cudaError_t e = cudaFuncSetAttribute(bf::exact_round_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bf::exact_round_kernel<true><<<grid, 128, smem, s>>>(q, db, d, dpitch, flagged, row0, row1, w.buf, w.cnt, w.tau, w.ovf, w.cap);
+    bf::exact_round_kernel<true><<<grid, 128, smem, s>>>(q, db, d, dpitch, flagged, row0, row1, w.buf, w.cnt, w.tau, w.ovf, w.cap, xnorm);
   } else {
     cudaError_t e = cudaFuncSetAttribute(bf::exact_round_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bf::exact_round_kernel<false><<<grid, 128, smem, s>>>(q, db, d, dpitch, flagged, row0, row1, w.buf, w.cnt, w.tau, w.ovf, w.cap);
+    bf::exact_round_kernel<false><<<grid, 128, smem, s>>>(q, db, d, dpitch, flagged, row0, row1, w.buf, w.cnt, w.tau, w.ovf, w.cap, nullptr);
   }
   return cudaGetLastError();
 }
 
 cudaError_t bf_exact_emit(const uint32_t* flagged, uint32_t n_flagged, const ScanWork& w, uint32_t k, uint32_t out_k,
-                          uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s) {
+                          uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s, bool l2) {
   if (!n_flagged) return cudaSuccess;
-  bf::exact_emit_kernel<<<n_flagged, 128, 0, s>>>(flagged, w.buf, w.cnt, w.cap, k, out_k, id_base, out_idx, out_dist);
+  bf::exact_emit_kernel<<<n_flagged, 128, 0, s>>>(flagged, w.buf, w.cnt, w.cap, k, out_k, id_base, out_idx, out_dist, l2 ? 1 : 0);
   return cudaGetLastError();
 }
 
@@ -1004,7 +1072,7 @@ cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, 
                        uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist,
                        cudaStream_t s, const BfSafety* safety) {
   bf::SafetyArgs sa{};
-  if (safety) sa = bf::SafetyArgs{safety->eps_rel, safety->max_row_norm, safety->unsafe, safety->n_unsafe};
+  if (safety) sa = bf::SafetyArgs{safety->eps_rel, safety->max_row_norm, safety->unsafe, safety->n_unsafe, 0};
   int np2 = 2;
   while ((uint32_t)np2 < kprime) np2 <<= 1;
   const size_t smem = (size_t)np2 * 8 + (((size_t)d + 3) & ~(size_t)3) * 4;
@@ -1017,15 +1085,15 @@ cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, 
 
 cudaError_t bf_rescore_f32(const float* q, const float* db, uint32_t nq, uint32_t d, const ScanWork& w, uint32_t kprime,
                            uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s,
-                           const BfSafety* safety) {
+                           const BfSafety* safety, const float* xnorm) {
   bf::SafetyArgs sa{};
-  if (safety) sa = bf::SafetyArgs{safety->eps_rel, safety->max_row_norm, safety->unsafe, safety->n_unsafe};
+  if (safety) sa = bf::SafetyArgs{safety->eps_rel, safety->max_row_norm, safety->unsafe, safety->n_unsafe, xnorm ? 1 : 0};
   int np2 = 2;
   while ((uint32_t)np2 < kprime) np2 <<= 1;
   const size_t smem = (size_t)np2 * 8 + (((size_t)d + 3) & ~(size_t)3) * 4;
   cudaError_t e = cudaFuncSetAttribute(bf::rescore_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  bf::rescore_f32_kernel<<<nq, 128, smem, s>>>(q, db, d, w.buf, w.cnt, w.cap, kprime, k, out_k, id_base, out_idx, out_dist, np2, sa);
+  bf::rescore_f32_kernel<<<nq, 128, smem, s>>>(q, db, d, w.buf, w.cnt, w.cap, kprime, k, out_k, id_base, out_idx, out_dist, np2, sa, xnorm);
   return cudaGetLastError();
 }
 

@@ -61,7 +61,9 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     // Bfloat16BruteForceSearcher (brute_force/bfloat16_brute_force.cc) or BruteForceSearcher<float>
     // (brute_force/brute_force.cc:376-393): MIPS only
     if (!d->bf16_dataset && !d->dataset) return fail(SCANN_B200_INVALID_ARGUMENT, "brute force needs dataset or bf16_dataset");
-    if (d->distance != SCANN_B200_DOT_PRODUCT) return fail(SCANN_B200_UNIMPLEMENTED, "brute force supports dot product distance only");
+    // squared L2: BruteForceSearcher<float> only (Bfloat16BruteForceSearcher is MIPS-only, bfloat16_brute_force.cc:60-75)
+    if (d->distance != SCANN_B200_DOT_PRODUCT && d->bf16_dataset)
+      return fail(SCANN_B200_UNIMPLEMENTED, "bfloat16 brute force supports dot product distance only");
     // row-sharded brute force: rank r keeps the contiguous rows [r * ceil(N / world), ...) and reports global ids
     const int world_bf = d->shard_world > 0 ? d->shard_world : 1;
     const int rank_bf = d->shard_rank;
@@ -78,13 +80,31 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
       // float rows: kept as they are for the exact re-scoring, plus the bf16 GEMM operand [hi | hi | lo]
       // (K = 3D padded to 64; the queries are [hi | lo | hi], so one GEMM gives qh.xh + ql.xh + qh.xl)
       ix->bf_f32 = true;
-      ix->bf_dpitch = sb::tokenize_kpitch(D);
       CU(ix->dataset.ensure(sizeof(float) * (size_t)std::max<uint32_t>(nloc, 1) * D));
       if (nloc) CU(cudaMemcpy(ix->dataset.p, d->dataset + (size_t)row0 * D, sizeof(float) * (size_t)nloc * D, cudaMemcpyHostToDevice));
+      vb.dataset = ix->dataset.as<float>();
+      if (d->distance == SCANN_B200_SQUARED_L2) {
+        // Squared L2 (brute_force.cc:376-393 with SquaredL2Distance): ||q - x||^2 orders like -(<q, x> - ||x||^2 / 2), the
+        // dot product of the AUGMENTED vectors x' = [x, -||x||^2 / 2], q' = [q, 1].  The tensor-core pre-filter runs on
+        // the augmented operands (D + 1 dimensions); the re-scoring evaluates the reference's squared-L2 chain on the
+        // original rows with the row norms kept here.
+        ix->bf_l2 = true;
+        ix->bf_dpitch = sb::tokenize_kpitch(D + 1);
+        CU(ix->bf_xnorm.ensure(sizeof(float) * std::max<uint32_t>(nloc, 1)));
+        CU(sb::bf_row_sqnorms(ix->dataset.as<float>(), nloc, D, ix->bf_xnorm.as<float>(), 0));
+        sbi::DevBuf aug;
+        CU(aug.ensure(sizeof(float) * (size_t)std::max<uint32_t>(nloc, 1) * (D + 1)));
+        CU(sb::bf_augment_rows(ix->dataset.as<float>(), ix->bf_xnorm.as<float>(), 0.f, nloc, D, aug.as<float>(), 0));
+        CU(ix->bf_db.ensure(sb::tokenize_operand_bytes(std::max<uint32_t>(nloc, 1), D + 1)));
+        CU(sb::build_tokenize_operand(aug.as<float>(), nloc, D + 1, 2, ix->bf_db.p, 0));
+        CU(cudaStreamSynchronize(0));
+        CU(sb::bf_max_row_norm(aug.p, true, nloc, D + 1, D + 1, &ix->bf_max_row_norm, 0));
+        return 0;
+      }
+      ix->bf_dpitch = sb::tokenize_kpitch(D);
       CU(ix->bf_db.ensure(sb::tokenize_operand_bytes(std::max<uint32_t>(nloc, 1), D)));
       CU(sb::build_tokenize_operand(ix->dataset.as<float>(), nloc, D, 2, ix->bf_db.p, 0));
       CU(cudaStreamSynchronize(0));
-      vb.dataset = ix->dataset.as<float>();
       CU(sb::bf_max_row_norm(ix->dataset.p, true, nloc, D, D, &ix->bf_max_row_norm, 0));
       return 0;
     }
@@ -649,7 +669,14 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
     const size_t written = (size_t)((nq + 127) / 128 * 128) * ix->bf_dpitch * 2;
     const size_t walked = (size_t)sb::bf_query_rows_pad(nq) * ix->bf_dpitch * 2;
     if (walked > written) CU(cudaMemsetAsync(static_cast<char*>(ix->bf_a.p) + written, 0, walked - written, s));
-    CU(sb::build_tokenize_operand(d_q, nq, v.d, 1, ix->bf_a.p, s));
+    if (ix->bf_l2) {  // q' = [q, 1]
+      CU(ix->bf_qaug.ensure(sizeof(float) * (size_t)nq * (v.d + 1)));
+      CU(sb::bf_augment_rows(d_q, nullptr, 1.0f, nq, v.d, ix->bf_qaug.as<float>(), s));
+      CU(sb::build_tokenize_operand(ix->bf_qaug.as<float>(), nq, v.d + 1, 1, ix->bf_a.p, s));
+      launches += 1;
+    } else {
+      CU(sb::build_tokenize_operand(d_q, nq, v.d, 1, ix->bf_a.p, s));
+    }
   }
   else CU(sb::bf_split_queries(d_q, nq, v.d, ix->bf_dpitch, ix->bf_a.p, s));
   launches += 1;
@@ -702,7 +729,8 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
     // optimistic: the re-scoring is launched before the overflow counter is known (one host round trip)
     sb::BfSafety safety{eps_rel, ix->bf_max_row_norm, d_unsafe, d_nflag};
     if (ix->bf_f32)
-      CU(sb::bf_rescore_f32(d_q, v.dataset, nq, v.d, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s, &safety));
+      CU(sb::bf_rescore_f32(d_q, v.dataset, nq, v.d, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s, &safety,
+                            ix->bf_l2 ? ix->bf_xnorm.as<float>() : nullptr));
     else
       CU(sb::bf_rescore(d_q, db, nq, v.d, ix->bf_dpitch, w, kprime, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s, &safety));
     launches += 1;
@@ -730,12 +758,13 @@ int search_bf_chunk(scann_b200_index* ix, const float* d_q, uint32_t nq, uint32_
     const void* rows = ix->bf_f32 ? static_cast<const void*>(v.dataset) : db;
     for (uint32_t r0 = 0; r0 < v.n; r0 += rows_per_round) {
       const uint32_t r1 = (uint32_t)std::min<uint64_t>((uint64_t)r0 + rows_per_round, v.n);
-      CU(sb::bf_exact_round(d_q, rows, ix->bf_f32, v.d, ix->bf_dpitch, d_flagged, exact_fallbacks, r0, r1, w, s));
+      CU(sb::bf_exact_round(d_q, rows, ix->bf_f32, v.d, ix->bf_dpitch, d_flagged, exact_fallbacks, r0, r1, w, s,
+                            ix->bf_l2 ? ix->bf_xnorm.as<float>() : nullptr));
       int ncl = 0;
       CU(sb::launch_compact(v, w, false, s, &ncl));
       launches += 1 + (uint32_t)ncl;
     }
-    CU(sb::bf_exact_emit(d_flagged, exact_fallbacks, w, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s));
+    CU(sb::bf_exact_emit(d_flagged, exact_fallbacks, w, k, out_k, ix->bf_row0, d_out_idx, d_out_dist, s, ix->bf_l2));
     launches += 2;
     CU(cudaEventRecord(ix->ev[EV_FIN], s));
     CU(cudaStreamSynchronize(s));
@@ -780,10 +809,12 @@ static scann_b200_index* make_lane(scann_b200_index* root) {
   c->brute = root->brute; c->bf_f32 = root->bf_f32; c->bf_dpitch = root->bf_dpitch; c->bf_row0 = root->bf_row0;
   c->avg_leaf_slots = root->avg_leaf_slots; c->nonempty_leaves = root->nonempty_leaves;
   c->bf_max_row_norm = root->bf_max_row_norm;
+  c->bf_l2 = root->bf_l2;
   c->shard_rank = root->shard_rank; c->shard_world = root->shard_world; c->shard_mode = root->shard_mode;
   c->parent = root;
   // the index arrays a search path reaches through DevBuf members rather than through `dev`
   auto alias = [](DevBuf& dst, const DevBuf& src) { dst.p = src.p; dst.bytes = src.bytes; dst.own = false; };
+  alias(c->bf_xnorm, root->bf_xnorm);
   alias(c->bf_db, root->bf_db); alias(c->dataset, root->dataset); alias(c->leaf_goff, root->leaf_goff);
   alias(c->slot_dp, root->slot_dp);
   bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess;

@@ -95,6 +95,8 @@ struct scann_b200_index {
   uint32_t nonempty_leaves = 0;
   float bf_max_row_norm = 0.f;  // >= max_i ||x_i|| (error bound of the brute-force pre-filter)
   sbi::DevBuf bf_db, bf_a, bf_flags;
+  sbi::DevBuf bf_xnorm, bf_qaug;  // squared-L2 float brute force: row norms (reference arithmetic), augmented queries
+  bool bf_l2 = false;
   // Search lanes: ScannInterface::SearchBatched may be called concurrently on one searcher (scann_ops/cc/scann.cc:478-501
   // runs batches on a thread pool).  The handle itself is lane 0; further lanes are shallow clones -- the same index
   // arrays on the device, their own stream, events and workspace -- created on demand (at most kMaxLanes), so that

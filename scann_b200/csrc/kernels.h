@@ -170,9 +170,14 @@ uint32_t bf_query_rows_pad(uint32_t nq);
 // window check of the exact re-scoring (bruteforce.cu check_window): flags queries whose k-th exact distance does not
 // clear "largest kept approximate distance - eps"
 struct BfSafety { float eps_rel, max_row_norm; uint32_t* unsafe; uint32_t* n_unsafe; };
+// xnorm != NULL: squared L2 (the candidates' keys come from the augmented dot-product pre-filter, see index.cu)
 cudaError_t bf_rescore_f32(const float* q, const float* db, uint32_t nq, uint32_t d, const ScanWork& w, uint32_t kprime,
                            uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s,
-                           const BfSafety* safety = nullptr);
+                           const BfSafety* safety = nullptr, const float* xnorm = nullptr);
+// squared-L2 float brute force: ||x||^2 per row in the reference's arithmetic; rows augmented with one more column
+// (database: -||x||^2 / 2, queries: `last` = 1), out [n][d + 1]
+cudaError_t bf_row_sqnorms(const float* x, uint32_t n, uint32_t d, float* out, cudaStream_t s);
+cudaError_t bf_augment_rows(const float* x, const float* norm, float last, uint32_t n, uint32_t d, float* out, cudaStream_t s);
 cudaError_t bf_rescore(const float* q, const void* db, uint32_t nq, uint32_t d, uint32_t dpitch, const ScanWork& w,
                        uint32_t kprime, uint32_t k, uint32_t out_k, uint32_t id_base, uint32_t* out_idx, float* out_dist,
                        cudaStream_t s, const BfSafety* safety = nullptr);
@@ -181,9 +186,10 @@ cudaError_t bf_max_row_norm(const void* db, bool f32, uint32_t n, uint32_t d, ui
 cudaError_t bf_exact_prepare(uint32_t nq, const uint32_t* unsafe, const ScanWork& w, uint32_t* flagged, uint32_t* n_flagged,
                              cudaStream_t s);
 cudaError_t bf_exact_round(const float* q, const void* db, bool f32, uint32_t d, uint32_t dpitch, const uint32_t* flagged,
-                           uint32_t n_flagged, uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s);
+                           uint32_t n_flagged, uint32_t row0, uint32_t row1, const ScanWork& w, cudaStream_t s,
+                           const float* xnorm = nullptr);
 cudaError_t bf_exact_emit(const uint32_t* flagged, uint32_t n_flagged, const ScanWork& w, uint32_t k, uint32_t out_k,
-                          uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s);
+                          uint32_t id_base, uint32_t* out_idx, float* out_dist, cudaStream_t s, bool l2 = false);
 // out[a_row * ld + b_row] = sum_k A[a_row][k] * B[b_row][k]; bf16 operands with row pitch kpitch (multiple of 64),
 // a_rows_pad a multiple of 128 (padding rows readable), fp32 accumulate on tcgen05.
 // cmax (optional): cmax[a_row * ld_c + b_row / 32] = max over that row's 32-column chunk of out (cbias == NULL) or of

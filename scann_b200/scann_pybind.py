@@ -49,8 +49,8 @@ class _Plan:
       unimpl("autopilot")
     if self.is_brute_force():
       # score_brute_force(): BruteForceSearcher<float> / Bfloat16BruteForceSearcher (brute_force/*.cc)
-      if self.distance != "dot_product":
-        unimpl("brute force with a distance other than dot product")
+      if self.distance != "dot_product" and self.bf16_brute_force():
+        unimpl("bfloat16 brute force with a distance other than dot product")  # bfloat16_brute_force.cc:60-75: MIPS only
       if cfgmod.as_bool(self.brute_force.path("fixed_point", "enabled"), False):
         unimpl("int8 brute force")
       if self.reordering is not None:

@@ -224,3 +224,81 @@ def test_f32_bruteforce_sorted_rows_and_ties():
   oi, od = oracle.bruteforce_f32(db, q, k, threads=8)
   np.testing.assert_array_equal(idx, oi)
   np.testing.assert_array_equal(dist.view(np.uint32), od.view(np.uint32))
+
+
+# ---- squared-L2 float brute force (BruteForceSearcher<float> with SquaredL2Distance, brute_force.cc:376-393) ----
+@pytest.mark.parametrize("n,d,nq,k", [(20000, 96, 300, 20), (5000, 768, 130, 100), (700, 40, 5, 10), (30000, 100, 257, 50),
+                                      (3000, 17, 40, 10)])
+def test_float_bruteforce_squared_l2_matches_oracle(n, d, nq, k):
+  import oracle
+  from scann_b200 import _lib, index_build
+  rng = np.random.default_rng(n + d + 1)
+  db = rng.standard_normal((n, d), dtype=np.float32) * rng.uniform(0.5, 2.0, (n, 1)).astype(np.float32)   # norms vary 4x
+  q = rng.standard_normal((nq, d), dtype=np.float32)
+  a = index_build.IndexArrays(distance="squared_l2", dataset=db, n=n, d=d)
+  ix = _lib.NativeIndex(a, 1, k, k)
+  idx, dist = ix.search_batched(q)
+  oi, od = oracle.bruteforce_f32(db, q, k, threads=8, distance="squared_l2")
+  np.testing.assert_array_equal(idx, oi)
+  np.testing.assert_array_equal(dist.view(np.uint32), od.view(np.uint32))
+  full = ((q.astype(np.float64)[:, None, :] - db.astype(np.float64)[None, :, :]) ** 2).sum(-1) if n * nq * d < 4e8 else None
+  if full is not None:
+    np.testing.assert_allclose(dist, np.take_along_axis(full, idx.astype(np.int64), axis=1), rtol=1e-5, atol=1e-4)
+    gt = np.argsort(full, axis=1)[:, :k]
+    recall = np.mean([len(set(idx[i].tolist()) & set(gt[i].tolist())) / k for i in range(nq)])
+    assert recall > 0.999
+
+
+def test_squared_l2_bruteforce_adversarial_and_sharded(monkeypatch):
+  """Rows sorted by distance to one query, a block of exact duplicates, a narrow start window that has to widen, and the
+  row-sharded form (local top-k with global ids, merge by (distance, id)) against the unsharded index."""
+  import ctypes as C
+  import oracle
+  import torch
+  from scann_b200 import _lib, index_build
+  rng = np.random.default_rng(23)
+  n, d, nq, k = 40000, 48, 24, 25
+  db = rng.standard_normal((n, d), dtype=np.float32)
+  q = rng.standard_normal((nq, d), dtype=np.float32)
+  db = np.ascontiguousarray(db[np.argsort(((db - q[2]) ** 2).sum(1), kind="stable")[::-1]])   # best rows of query 2 come last
+  db[500:560] = db[499]
+  a = index_build.IndexArrays(distance="squared_l2", dataset=db, n=n, d=d)
+  oi, od = oracle.bruteforce_f32(db, q, k, threads=8, distance="squared_l2")
+  ix = _lib.NativeIndex(a, 1, k, k)
+  idx, dist = ix.search_batched(q)
+  np.testing.assert_array_equal(idx, oi)
+  np.testing.assert_array_equal(dist.view(np.uint32), od.view(np.uint32))
+  monkeypatch.setenv("SCANN_B200_BF_KPRIME", str(k))
+  idx2, dist2 = ix.search_batched(q)
+  assert ix.stats()["bf_widenings"] >= 1
+  np.testing.assert_array_equal(idx2, oi)
+  np.testing.assert_array_equal(dist2.view(np.uint32), od.view(np.uint32))
+  monkeypatch.delenv("SCANN_B200_BF_KPRIME")
+  # row-sharded: three shards on this GPU, the all-gather replaced by a concatenation
+  world = 3
+  dev = torch.device("cuda", 0)
+  d_q = torch.from_numpy(q).to(dev)
+  ids = torch.empty((world, nq, k), dtype=torch.int32, device=dev)
+  dists = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+  shards = [_lib.NativeIndex(a, 1, k, k, shard_rank=r, shard_world=world) for r in range(world)]
+  for r, sh in enumerate(shards):
+    sh.search_batched_device(d_q.data_ptr(), nq, ids[r].data_ptr(), dists[r].data_ptr(), k)
+  out_i = torch.empty((nq, k), dtype=torch.int32, device=dev)
+  out_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+  _lib.check(_lib.lib().scann_b200_merge_topk_device(shards[0]._h, nq, world, k, C.c_void_p(ids.data_ptr()), C.c_void_p(dists.data_ptr()),
+                                                     k, C.c_void_p(out_i.data_ptr()), C.c_void_p(out_d.data_ptr()), k))
+  np.testing.assert_array_equal(out_i.cpu().numpy().view(np.uint32), oi)
+  np.testing.assert_array_equal(out_d.cpu().numpy().view(np.uint32), od.view(np.uint32))
+
+
+def test_squared_l2_brute_force_through_the_builder():
+  """scann_ops_pybind_test.py:245-264 (test_squared_l2): score_brute_force() with squared_l2 against numpy at rtol 1e-5."""
+  from scann_b200 import scann_ops_pybind
+  rng = np.random.default_rng(3)
+  db = rng.random((2000, 32), dtype=np.float32)
+  q = rng.random((20, 32), dtype=np.float32)
+  s = scann_ops_pybind.builder(db, 10, "squared_l2").score_brute_force().build()
+  idx, dist = s.search_batched(q)
+  full = ((q.astype(np.float64)[:, None, :] - db.astype(np.float64)[None, :, :]) ** 2).sum(-1)
+  np.testing.assert_array_equal(idx, np.argsort(full, axis=1)[:, :10].astype(np.uint32))
+  np.testing.assert_allclose(dist, np.take_along_axis(full, idx.astype(np.int64), axis=1), rtol=1e-5)

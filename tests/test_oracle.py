@@ -171,3 +171,51 @@ def test_int8_reordering_matches_numpy_and_f64(name):
   f = oracle.OracleIndex(load_golden(name)[0], int(z["probe"]), int(z["pre"]), int(z["k"]))
   fidx, _ = f.search_batched(z["queries"])
   assert np.mean([len(set(idx[i].tolist()) & set(fidx[i].tolist())) / idx.shape[1] for i in range(len(idx))]) > 0.9
+
+
+def test_float_bruteforce_oracles_against_numpy_restatements():
+  """so_bruteforce_f32 / so_bruteforce_f32_l2 against a numpy restatement of the many-to-many chains
+  (many_to_many_impl.inc:236-257,417-426,522-567) -- bit-exact -- and against float64."""
+  rng = np.random.default_rng(5)
+  n, d, nq, k = 400, 37, 9, 7
+  db = (rng.standard_normal((n, d)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+  q = rng.standard_normal((nq, d)).astype(np.float32)
+
+  def fma(a, b, c):  # one rounding: exact product in float64 (24 x 24 bits), sum rounded once to float32 ...
+    # ... float64 addition of an exact product and a float32 is not always exact; use Python's exact rationals
+    from fractions import Fraction
+    out = np.empty(a.shape, np.float32)
+    for i in range(a.size):
+      out.flat[i] = np.float32(float(Fraction(float(a.flat[i])) * Fraction(float(b.flat[i])) + Fraction(float(c.flat[i]))))
+    return out
+
+  # dot product: acc = 0; acc = fnmadd(q[j], x[j], acc)
+  acc = np.zeros((nq, n), np.float32)
+  for j in range(d):
+    acc = fma(np.broadcast_to(-q[:, j:j + 1], (nq, n)).copy(), np.broadcast_to(db[None, :, j], (nq, n)).copy(), acc)
+  idx, dist = oracle.bruteforce_f32(db, q, k)
+  order = np.lexsort((np.broadcast_to(np.arange(n), (nq, n)), acc), axis=1)[:, :k]
+  np.testing.assert_array_equal(idx, order.astype(np.uint32))
+  np.testing.assert_array_equal(dist.view(np.uint32), (-np.take_along_axis(acc, order, axis=1)).view(np.uint32))
+
+  # squared L2: ||x||^2 by fnmadd chain times -1, ||q||^2 in double, then fnmadd(q[j], 2 x[j], acc)
+  xn = np.zeros(n, np.float32)
+  for j in range(d):
+    xn = fma(-db[:, j], db[:, j], xn)
+  xn = xn * np.float32(-1.0)
+  # ||q||^2: sequential double accumulation in dimension order
+  qnf = np.empty(nq, np.float32)
+  for i in range(nq):
+    a = 0.0
+    for j in range(d):
+      a += float(q[i, j]) * float(q[i, j])
+    qnf[i] = np.float32(a)
+  acc = (xn[None, :] + qnf[:, None]).astype(np.float32)
+  for j in range(d):
+    acc = fma(np.broadcast_to(-q[:, j:j + 1], (nq, n)).copy(), np.broadcast_to((db[:, j] * np.float32(2.0))[None, :], (nq, n)).copy(), acc)
+  idx, dist = oracle.bruteforce_f32(db, q, k, distance="squared_l2")
+  order = np.lexsort((np.broadcast_to(np.arange(n), (nq, n)), acc), axis=1)[:, :k]
+  np.testing.assert_array_equal(idx, order.astype(np.uint32))
+  np.testing.assert_array_equal(dist.view(np.uint32), np.take_along_axis(acc, order, axis=1).view(np.uint32))
+  d2 = ((q.astype(np.float64)[:, None, :] - db.astype(np.float64)[None, :, :]) ** 2).sum(-1)
+  np.testing.assert_allclose(dist, np.take_along_axis(d2, idx.astype(np.int64), axis=1), rtol=1e-5)
