@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SCANN_B200_ABI_VERSION 4
+#define SCANN_B200_ABI_VERSION 5
 
 enum { SCANN_B200_DOT_PRODUCT = 0, SCANN_B200_SQUARED_L2 = 1 };
 

@@ -97,7 +97,9 @@ def test_docids_and_error_behaviour(tmp_path):
   with pytest.raises(ValueError, match="docid and database size mismatch"):
     scann_ops_pybind.create_searcher(db, "", docids=["a"])
   with pytest.raises(RuntimeError, match="Error initializing searcher: UNIMPLEMENTED"):
-    scann_ops_pybind.builder(db, 5, "squared_l2").score_brute_force().build()   # brute force: dot product only
+    # bfloat16 brute force is MIPS-only, like the reference's (bfloat16_brute_force.cc:60-75); float rows take squared L2
+    from scann_b200 import scann_builder
+    scann_ops_pybind.builder(db, 5, "squared_l2").score_brute_force(scann_builder.ReorderType.BFLOAT16).build()
 
 
 def test_empty_partitions_are_tolerated():
