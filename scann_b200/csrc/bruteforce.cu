@@ -182,11 +182,15 @@ __device__ __forceinline__ void filter_tile(const GemmArgs& a, uint32_t tbase, u
 
 constexpr int kEpiFilter = 0, kEpiStore = 1;
 
-template <int kSplitsT>
+// The store epilogue transposes its 32 x 32 blocks through shared memory (below): one stage less, 8 x 4.5 KB of blocks.
+constexpr int kTrRowBytes = 144;                 // 32 floats + 16 bytes of padding: 16-byte aligned rows, conflict-free
+constexpr int kTrBlockBytes = 32 * kTrRowBytes;  // per epilogue warp
+template <int kSplitsT, int kEpi = 0>
 struct StageLayout {
   static constexpr int kBytes = kSplitsT * kABytes + kBBytes;
-  static constexpr int kStagesT = kSplitsT == 1 ? 4 : 3;
-  static constexpr size_t kSmem = (size_t)kStagesT * kBytes + 1024;
+  static constexpr int kStagesT = kSplitsT == 1 ? (kEpi == 1 ? 3 : 4) : 3;
+  static constexpr int kTrBytes = kEpi == 1 ? kEpiWarps * kTrBlockBytes : 0;
+  static constexpr size_t kSmem = (size_t)kStagesT * kBytes + kTrBytes + 1024;
 };
 
 // Persistent GEMM: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the A
@@ -197,7 +201,7 @@ struct StageLayout {
 template <int kSplitsT, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs a) {
-  using SL = StageLayout<kSplitsT>;
+  using SL = StageLayout<kSplitsT, kEpi>;
   constexpr int kSt = SL::kStagesT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -317,7 +321,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             a.cmax[(size_t)q * a.ld_c + (col >> 5)] = mx;
           }
-          if (qvalid && a.out) {
+          if (a.out && col + 32 <= a.row1 && (a.ld & 3u) == 0) {
+            // A TMEM lane is an output ROW: stored straight from the registers, every instruction would write 16 bytes
+            // into each of 32 rows (32 half-used sectors, the LSU queue was the limiter of the 40k-centre tokenization).
+            // The warp's 32 x 32 block goes through shared memory instead and leaves as whole 128-byte row segments,
+            // four rows per instruction.
+            const uint32_t blk = smem_u32(smem + (size_t)kSt * SL::kBytes) + (uint32_t)(warp - 4) * kTrBlockBytes;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (uint32_t)lane * kTrRowBytes + (uint32_t)j * 4u),
+                           "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+            __syncwarp();
+            const uint32_t r0 = m0 + (uint32_t)quad * 32u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t rr = (uint32_t)i * 4u + ((uint32_t)lane >> 3);
+              uint4 x;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                           : "r"(blk + rr * kTrRowBytes + ((uint32_t)lane & 7u) * 16u));
+              if (r0 + rr < a.nq)
+                *reinterpret_cast<uint4*>(a.out + (size_t)(r0 + rr) * a.ld + col + ((uint32_t)lane & 7u) * 4u) = x;
+            }
+          } else if (qvalid && a.out) {
             if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -524,7 +550,29 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             a.cmax[(size_t)q * a.ld_c + (col >> 5)] = mx;
           }
-          if (qvalid && a.out) {
+          if (a.out && col + 32 <= a.row1 && (a.ld & 3u) == 0) {
+            // A TMEM lane is an output ROW: stored straight from the registers, every instruction would write 16 bytes
+            // into each of 32 rows (32 half-used sectors, the LSU queue was the limiter of the 40k-centre tokenization).
+            // The warp's 32 x 32 block goes through shared memory instead and leaves as whole 128-byte row segments,
+            // four rows per instruction.
+            const uint32_t blk = smem_u32(smem + (size_t)kSt * SL::kBytes) + (uint32_t)(warp - 4) * kTrBlockBytes;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(blk + (uint32_t)lane * kTrRowBytes + (uint32_t)j * 4u),
+                           "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3]) : "memory");
+            __syncwarp();
+            const uint32_t r0 = m0 + (uint32_t)quad * 32u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t rr = (uint32_t)i * 4u + ((uint32_t)lane >> 3);
+              uint4 x;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w)
+                           : "r"(blk + rr * kTrRowBytes + ((uint32_t)lane & 7u) * 16u));
+              if (r0 + rr < a.nq)
+                *reinterpret_cast<uint4*>(a.out + (size_t)(r0 + rr) * a.ld + col + ((uint32_t)lane & 7u) * 4u) = x;
+            }
+          } else if (qvalid && a.out) {
             if (col + 32 <= a.row1 && (a.ld & 3u) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -924,7 +972,7 @@ static int sm_count() {
 
 template <int kSplitsT, int kEpi>
 static cudaError_t launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const bf::GemmArgs& a, cudaStream_t s) {
-  using SL = bf::StageLayout<kSplitsT>;
+  using SL = bf::StageLayout<kSplitsT, kEpi>;
   cudaError_t e = cudaFuncSetAttribute(bf::gemm_kernel<kSplitsT, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)SL::kSmem);
   if (e != cudaSuccess) return e;
