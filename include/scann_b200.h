@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define SCANN_B200_ABI_VERSION 5
+#define SCANN_B200_ABI_VERSION 6
 
 enum { SCANN_B200_DOT_PRODUCT = 0, SCANN_B200_SQUARED_L2 = 1 };
 
@@ -82,9 +82,17 @@ typedef struct {
    *   SCANN_B200_SHARD_BY_LEAF whole leaves (incl. their SOAR copies) are dealt out, this rank holds the leaves with
    *                            leaf % shard_world == shard_rank and the rows of the datapoints stored in them */
   int32_t shard_mode;
+  /* PartitioningConfig.query_tokenization_type (tree(quantize_centroids=True) in scann_builder.py:231):
+   *   SCANN_B200_TOKENIZE_FLOAT             the batched float path (kmeans_tree_partitioner.cc:642-730)
+   *   SCANN_B200_TOKENIZE_FIXED_POINT_INT8  KMeansTreeNode::GetAllDistancesInt8 (trees/kmeans_tree/kmeans_tree_node.h:
+   *       222-256) on the centres KMeansTreeNode::CreateFixedPointCenters (kmeans_tree_node.cc:267-281) derives from
+   *       `centers` at load time -- the library derives them the same way, nothing extra is serialized.  The leaf
+   *       bias of the AH scores is then the int8 distance, as in the reference.  Tree-AH only. */
+  int32_t query_tokenization_type;
 } scann_b200_index_desc;
 
 enum { SCANN_B200_SHARD_BY_ID = 0, SCANN_B200_SHARD_BY_LEAF = 1 };
+enum { SCANN_B200_TOKENIZE_FLOAT = 0, SCANN_B200_TOKENIZE_FIXED_POINT_INT8 = 1 };
 
 /* Replaces ScannInterface::Initialize(ScannArtifacts) (scann_ops/cc/scann.cc:355-381) and the
  * per-leaf asymmetric_hashing2::Searcher construction incl. CreatePackedDataset

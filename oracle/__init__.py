@@ -24,6 +24,7 @@ class _Desc(C.Structure):
       ("overretrieve", C.c_float), ("default_leaves", C.c_int32),
       ("default_pre_nn", C.c_int32), ("default_final_nn", C.c_int32),
       ("int8_dataset", C.c_void_p), ("int8_multipliers", C.c_void_p), ("dp_norms", C.c_void_p),
+      ("centers_i8", C.c_void_p), ("centers_inv_mult", C.c_void_p), ("centers_sqnorm", C.c_void_p),
   ]
 
 
@@ -58,6 +59,7 @@ def lib():
     L.so_leaf_datapoints.restype = C.POINTER(C.c_uint32)
     L.so_leaf_datapoints.argtypes = [C.c_void_p, C.c_uint32]
     L.so_disjoint.argtypes = [C.c_void_p]
+    L.so_quantize_centers.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.so_last_scan_bytes.restype = C.c_uint64
     L.so_last_boundary_band.restype = C.c_uint64
     _LIB = L
@@ -66,6 +68,16 @@ def lib():
 
 def _p(a):
   return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def quantize_centers(centers):
+  """so_quantize_centers: (int8 centres [L, D], inverse multipliers [D], squared norms of the float centres [L])."""
+  c = np.ascontiguousarray(centers, dtype=np.float32)
+  L, D = c.shape
+  ci8, inv, sqn = np.empty((L, D), np.int8), np.empty(D, np.float32), np.empty(L, np.float32)
+  if lib().so_quantize_centers(_p(c), L, D, _p(ci8), _p(inv), _p(sqn)):
+    raise RuntimeError(lib().so_last_error().decode())
+  return ci8, inv, sqn
 
 
 class OracleIndex:
@@ -102,6 +114,10 @@ class OracleIndex:
     d.int8_dataset = _p(own(getattr(a, "int8_dataset", None), np.int8))
     d.int8_multipliers = _p(own(getattr(a, "int8_multipliers", None), np.float32))
     d.dp_norms = _p(own(getattr(a, "dp_norms", None), np.float32))
+    if getattr(a, "int8_tokenization", False):
+      # query_tokenization_type FIXED_POINT_INT8: the fixed-point centres are derived here from the float centres
+      ci8, inv, sqn = quantize_centers(a.centers)
+      d.centers_i8, d.centers_inv_mult, d.centers_sqnorm = _p(own(ci8, np.int8)), _p(own(inv, np.float32)), _p(own(sqn, np.float32))
     d.overretrieve = a.overretrieve
     d.default_leaves = leaves_to_search
     d.default_pre_nn = pre_reorder_nn

@@ -342,8 +342,97 @@ static void one_to_many(int distance, const float* q, const float* rows, uint32_
  * (DoAccumulationTransposedTemplate): dot: acc = 0; for dim: acc = fnmadd(q[dim], c[dim], acc).
  * squared L2: acc = ||c||^2 + ||q||^2 with ||c||^2 = -(fnmadd chain) (:236-257) and
  * acc = fnmadd(q[dim], 2*c[dim], acc).  Sequential in dim. */
+static float neg_dot_i8_order(const float* qp, const int8_t* x, uint32_t n);
+static double squared_l2_norm_f64(const float* v, uint32_t n);
+/* One-to-one int8 x float dot product, DenseDotProductInt8FloatAvxImpl<AvxFunctionsAvx2Fma>
+ * (distance_measures/one_to_one/dot_product_impl.inc:3-54): two 8-lane fmadd accumulators over whole groups of 16 dims
+ * (lanes 0-7 -> acc0, 8-15 -> acc1), one 8-wide fmadd step into acc0, one 4-wide step as a rounded product ADDED into
+ * lanes 0..3 of acc0 (mul_ps + add_ps, not fused), Sum8(acc0 + acc1) = ((x0+x4)+(x2+x6)) + ((x1+x5)+(x3+x7))
+ * (utils/internal/avx2_funcs.h:56-63), the last < 4 dims as `acc += float(a) * b` (inside an AVX2+FMA target function:
+ * assumed to contract, as the other scalar tails of this file). */
+static float dot_i8_one_to_one(const float* qp, const int8_t* x, uint32_t n) {
+  float a0[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint32_t j = 0;
+  for (; j + 16 <= n; j += 16)
+    for (int l = 0; l < 8; ++l) {
+      a0[l] = fmaf((float)x[j + l], qp[j + l], a0[l]);
+      a1[l] = fmaf((float)x[j + 8 + l], qp[j + 8 + l], a1[l]);
+    }
+  if (j + 8 <= n) {
+    for (int l = 0; l < 8; ++l) a0[l] = fmaf((float)x[j + l], qp[j + l], a0[l]);
+    j += 8;
+  }
+  if (j + 4 <= n) {
+    for (int l = 0; l < 4; ++l) { const float p = (float)x[j + l] * qp[j + l]; a0[l] = a0[l] + p; }
+    j += 4;
+  }
+  float v[8];
+  for (int l = 0; l < 8; ++l) v[l] = a0[l] + a1[l];
+  float r = ((v[0] + v[4]) + (v[2] + v[6])) + ((v[1] + v[5]) + (v[3] + v[7]));
+  for (; j < n; ++j) r = fmaf((float)x[j], qp[j], r);
+  return r;
+}
+
+/* Int8 centres (query_tokenization_type FIXED_POINT_INT8).  A non-FLOAT tokenization type leaves the batched path
+ * (KMeansTreePartitioner::SupportsLowLevelQueryBatching, partitioning/kmeans_tree_partitioner.h:230-236): every query
+ * goes through KMeansTree::Tokenize -> KMeansTreeNode::FindChildrenWithSpilling<float, int8_t> ->
+ * GetAllDistancesInt8 (trees/kmeans_tree/kmeans_tree_node.h:222-256): the query is scaled by the inverse multipliers
+ * (times 2 for squared L2: `q *= inv_mult * 2`), distances = DenseDotProductDistanceOneToManyInt8Float over ALL
+ * centres = OneToManyAsymmetricTemplate<dims, 3, no indices, dot product, int8_t>
+ * (distance_measures/one_to_many/one_to_many_asymmetric_impl.inc:531-671): centres [0, 3 * (L / 3)) through the
+ * three-at-a-time kernel (-<q', float(c)> in the order of neg_dot_i8_order, the kernel of the int8 reordering), the
+ * last L mod 3 centres through ComputeOneToOneScore<0, false> = -DenseDotProductAvx2(int8, float) (:629-639,223-258),
+ * which sums in another order.  Squared L2 adds (SquaredL2Norm(q) + SquaredL2Norm(float centre)) to each.  The top-P
+ * selection (PostprocessDistancesForSpilling, kmeans_tree_node.cc:128-159: FastTopNeighbors(max_centers), PushBlock)
+ * is the exact (distance, index) selection of the float path. */
+static void center_distances_i8(const so_index* ix, const float* q, float* out) {
+  const uint32_t L = ix->d.n_leaves, D = ix->d.d;
+  float qp[D];
+  const int l2 = ix->d.distance != SO_DOT_PRODUCT;
+  for (uint32_t j = 0; j < D; ++j) {
+    const float inv = ix->d.centers_inv_mult[j];
+    qp[j] = l2 ? q[j] * (inv * 2.0f) : q[j] * inv;
+  }
+  const float qn = l2 ? (float)squared_l2_norm_f64(q, D) : 0.0f;
+  const uint32_t L3 = L / 3 * 3;
+  for (uint32_t l = 0; l < L; ++l) {
+    const int8_t* c = ix->d.centers_i8 + (size_t)l * D;
+    const float val = l < L3 ? neg_dot_i8_order(qp, c, D) : -dot_i8_one_to_one(qp, c, D);
+    out[l] = l2 ? val + (qn + ix->d.centers_sqnorm[l]) : val;
+  }
+}
+
+/* KMeansTreeNode::CreateFixedPointCenters (trees/kmeans_tree/kmeans_tree_node.cc:267-281):
+ * ScalarQuantizeFloatDataset(float_centers, 1.0, NaN) (utils/scalar_quantization_helpers.cc:39-63,94-145):
+ * multiplier[d] = 127 / max_l |c[l][d]| (1 for an all-zero column), value = Int8Quantize(c * multiplier) =
+ * clamp(std::round(.), -128, 127) (scalar_quantization_helpers.h:40-50), inverse multiplier = 1.0f / multiplier;
+ * sqnorm[l] = float(SquaredL2Norm(float centre)). */
+int so_quantize_centers(const float* centers, uint32_t L, uint32_t D, int8_t* out_i8, float* out_inv_mult,
+                        float* out_sqnorm) {
+  float* mult = (float*)malloc(sizeof(float) * (D ? D : 1));
+  if (!mult) return fail("out of memory");
+  for (uint32_t j = 0; j < D; ++j) mult[j] = 0.0f;
+  for (uint32_t l = 0; l < L; ++l)
+    for (uint32_t j = 0; j < D; ++j) {
+      const float a = fabsf(centers[(size_t)l * D + j]);
+      if (a > mult[j]) mult[j] = a;
+    }
+  for (uint32_t j = 0; j < D; ++j) mult[j] = mult[j] == 0.0f ? 1.0f : 127.0f / mult[j];
+  for (uint32_t l = 0; l < L; ++l) {
+    for (uint32_t j = 0; j < D; ++j) {
+      const float r = roundf(centers[(size_t)l * D + j] * mult[j]);
+      out_i8[(size_t)l * D + j] = (int8_t)(r > 127.0f ? 127.0f : (r < -128.0f ? -128.0f : r));
+    }
+    out_sqnorm[l] = (float)squared_l2_norm_f64(centers + (size_t)l * D, D);
+  }
+  for (uint32_t j = 0; j < D; ++j) out_inv_mult[j] = 1.0f / mult[j];
+  free(mult);
+  return 0;
+}
+
 static void center_distances(const so_index* ix, const float* q, float* out) {
   const uint32_t L = ix->d.n_leaves, D = ix->d.d;
+  if (ix->d.centers_i8) { center_distances_i8(ix, q, out); return; }
   if (ix->d.distance == SO_DOT_PRODUCT) {
     for (uint32_t l = 0; l < L; ++l) out[l] = 0.0f;
     for (uint32_t k = 0; k < D; ++k) {

@@ -27,6 +27,7 @@ class IndexDesc(C.Structure):
       ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
       ("int8_dataset", C.c_void_p), ("int8_multipliers", C.c_void_p), ("dp_norms", C.c_void_p),
       ("shard_mode", C.c_int32),
+      ("query_tokenization_type", C.c_int32),
   ]
 
 
@@ -202,6 +203,7 @@ class NativeIndex:
     d.int8_dataset = ptr(own(getattr(a, "int8_dataset", None), np.int8))
     d.int8_multipliers = ptr(own(getattr(a, "int8_multipliers", None), np.float32))
     d.dp_norms = ptr(own(getattr(a, "dp_norms", None), np.float32))
+    d.query_tokenization_type = 1 if getattr(a, "int8_tokenization", False) else 0
     d.overretrieve = a.overretrieve
     d.default_leaves = leaves_to_search
     d.default_pre_nn = pre_reorder_nn

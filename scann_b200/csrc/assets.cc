@@ -803,6 +803,11 @@ int describe(const Assets* a, scann_b200_index_desc* d) {
   d->default_final_nn = (int32_t)node_num(c.find("num_neighbors"), 1);
   d->default_pre_nn = (int32_t)node_num(c.path({"exact_reordering", "approx_num_neighbors"}), (double)d->default_final_nn);
   d->shard_world = 1;
+  // partitioning { query_tokenization_type: FIXED_POINT_INT8 } (partitioning/partitioner_factory.cc:95-98)
+  if (const Node* t = c.path({"partitioning", "query_tokenization_type"})) {
+    if (t->scalar == "FIXED_POINT_INT8" || t->scalar == "2") d->query_tokenization_type = SCANN_B200_TOKENIZE_FIXED_POINT_INT8;
+    else if (t->scalar != "FLOAT" && t->scalar != "1") return afail(SCANN_B200_UNIMPLEMENTED, "query_tokenization_type %s is not supported", t->scalar.c_str());
+  }
   return 0;
 }
 

@@ -122,6 +122,8 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
   // B <= 256: the reference's int16 accumulator covers it (CanUseInt16Accumulator, asymmetric_hashing_impl.cc:656-688);
   // above that it switches to 32-bit sums, which this path does not restate
   if (B > 256) return fail(SCANN_B200_UNIMPLEMENTED, "n_blocks=%u > 256 not supported", B);
+  if (d->query_tokenization_type != SCANN_B200_TOKENIZE_FLOAT && d->query_tokenization_type != SCANN_B200_TOKENIZE_FIXED_POINT_INT8)
+    return fail(SCANN_B200_INVALID_ARGUMENT, "unknown query_tokenization_type %d", d->query_tokenization_type);
   if (d->soar && !d->soar_codes) return fail(SCANN_B200_INVALID_ARGUMENT, "SOAR index without soar_codes");
   const int world = d->shard_world > 0 ? d->shard_world : 1, rank = d->shard_rank;
   if (rank < 0 || rank >= world) return fail(SCANN_B200_INVALID_ARGUMENT, "bad shard rank %d/%d", rank, world);
@@ -339,6 +341,54 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     CU(sb::build_tokenize_operand(v.centers, L, D, 2, ix->tok_b.p, 0));
     CU(cudaStreamSynchronize(0));
     v.tok_b = ix->tok_b.p;
+  }
+  if (d->query_tokenization_type == SCANN_B200_TOKENIZE_FIXED_POINT_INT8) {
+    // KMeansTreeNode::CreateFixedPointCenters (trees/kmeans_tree/kmeans_tree_node.cc:267-281), run when the tree is
+    // loaded: ScalarQuantizeFloatDataset(float_centers, 1.0, NaN) (utils/scalar_quantization_helpers.cc:39-63,94-145)
+    // -- multiplier[k] = 127 / max_l |c[l][k]| (1 for an all-zero column), Int8Quantize = clamp(std::round(c * m)) --
+    // its inverse multipliers 1.0f / m, and float(SquaredL2Norm(float centre)) with DenseSingleAccumulate's four
+    // strided double accumulators (utils/reduction.h:357-390)
+    std::vector<float> mult(D, 0.0f), inv(D), sqn(L);
+    std::vector<int8_t> ci8((size_t)L * D);
+    for (uint32_t l = 0; l < L; ++l)
+      for (uint32_t k = 0; k < D; ++k) mult[k] = std::max(mult[k], std::fabs(d->centers[(size_t)l * D + k]));
+    for (uint32_t k = 0; k < D; ++k) {
+      mult[k] = mult[k] == 0.0f ? 1.0f : 127.0f / mult[k];
+      inv[k] = 1.0f / mult[k];
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+      const float* c = d->centers + (size_t)l * D;
+      for (uint32_t k = 0; k < D; ++k) {
+        const float r = std::round(c[k] * mult[k]);
+        ci8[(size_t)l * D + k] = (int8_t)(r > 127.0f ? 127.0f : (r < -128.0f ? -128.0f : r));
+      }
+      double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      uint32_t k = 0;
+      for (; k + 4 <= D; k += 4) {
+        r0 += (double)c[k] * (double)c[k];
+        r1 += (double)c[k + 1] * (double)c[k + 1];
+        r2 += (double)c[k + 2] * (double)c[k + 2];
+        r3 += (double)c[k + 3] * (double)c[k + 3];
+      }
+      r2 += r3;
+      if (k + 2 <= D) {
+        r0 += (double)c[k] * (double)c[k];
+        r1 += (double)c[k + 1] * (double)c[k + 1];
+        k += 2;
+      }
+      r1 += r2;
+      if (k < D) r0 += (double)c[k] * (double)c[k];
+      sqn[l] = (float)(r0 + r1);
+    }
+    CU(ix->cen_i8.ensure(ci8.size() ? ci8.size() : 16));
+    CU(cudaMemcpy(ix->cen_i8.p, ci8.data(), ci8.size(), cudaMemcpyHostToDevice));
+    CU(ix->cen_inv.ensure(sizeof(float) * D));
+    CU(cudaMemcpy(ix->cen_inv.p, inv.data(), sizeof(float) * D, cudaMemcpyHostToDevice));
+    CU(ix->cen_sqn.ensure(sizeof(float) * L));
+    CU(cudaMemcpy(ix->cen_sqn.p, sqn.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
+    v.centers_i8 = ix->cen_i8.as<int8_t>();
+    v.cen_inv_mult = ix->cen_inv.as<float>();
+    v.cen_sqnorm = ix->cen_sqn.as<float>();
   }
   v.centers_t = nullptr;
   v.center_sqnorm = ix->cnorm.as<float>();

@@ -38,6 +38,11 @@ struct DevIndex {
   const int8_t* dataset_i8;   // [rows][D]
   const float* i8_inv_mult;   // [D] 1.0f / multiplier_by_dimension
   const float* i8_dp_norm;    // [N] squared L2 norm of the original row, by datapoint id (squared L2 only)
+  // int8 (fixed point) query tokenization (query_tokenization_type FIXED_POINT_INT8, prep.cu tokenize_i8_kernel):
+  // non-NULL centers_i8 switches launch_tokenize / launch_tokenize_topp to it
+  const int8_t* centers_i8;   // [L][D] ScalarQuantizeFloatDataset(centres, 1.0, NaN)
+  const float* cen_inv_mult;  // [D] 1.0f / multiplier_by_dimension
+  const float* cen_sqnorm;    // [L] float(SquaredL2Norm(float centre)) (squared L2 only)
   // tensor-core tokenization (prep.cu): centres as the bf16 operand [L][tok_kp] = [hi | hi | lo | 0]
   const void* tok_b;
   uint32_t tok_kp;

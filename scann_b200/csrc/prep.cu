@@ -95,7 +95,196 @@ tokenize_kernel(const float* __restrict__ q, const float* __restrict__ c,
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Int8 (fixed point) tokenization: query_tokenization_type FIXED_POINT_INT8.  The reference leaves its batched GEMM
+// path for this type (KMeansTreePartitioner::SupportsLowLevelQueryBatching, partitioning/kmeans_tree_partitioner.h:
+// 230-236) and runs KMeansTreeNode::GetAllDistancesInt8 per query (trees/kmeans_tree/kmeans_tree_node.h:222-256):
+//   q'[k] = q[k] * inv_mult[k]  (squared L2: q[k] * (inv_mult[k] * 2))
+//   val[l] = DenseDotProductDistanceOneToManyInt8Float(q', int8 centres)[l]
+//   dot product: val[l];  squared L2: val[l] + (float(SquaredL2Norm(q)) + float(SquaredL2Norm(float centre l)))
+// val is OneToManyAsymmetricTemplate<dims, 3, .., int8_t> (one_to_many_asymmetric_impl.inc:531-671): centres
+// [0, 3 (L / 3)) in the three-at-a-time AVX2 order -- eight fnmadd lanes over whole groups of 8 dims, one 4-wide step
+// into lanes 0..3, ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), the remaining dims on the scalar -- and the last L mod 3
+// centres through the one-to-one kernel (tokenize_i8_tail_kernel).  Here: a 64-query x 32-centre SIMT tile, four
+// queries x two centres per thread, the eight lane accumulators of every (query, centre) pair in registers, so each
+// lane sees its dims in the reference's order whatever the tiling over k.
+// ---------------------------------------------------------------------------------------
+constexpr int I8M = 64, I8N = 32, I8K = 16, I8PAD = 4;
+
+// float(SquaredL2Norm(q)): DenseSingleAccumulate, four strided double accumulators (utils/reduction.h:357-390)
+__device__ __forceinline__ float squared_l2_norm_strided(const float* __restrict__ v, uint32_t D) {
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  uint32_t k = 0;
+  for (; k + 4 <= D; k += 4) {
+    r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
+    r1 = __dadd_rn(r1, __dmul_rn((double)v[k + 1], (double)v[k + 1]));
+    r2 = __dadd_rn(r2, __dmul_rn((double)v[k + 2], (double)v[k + 2]));
+    r3 = __dadd_rn(r3, __dmul_rn((double)v[k + 3], (double)v[k + 3]));
+  }
+  r2 = __dadd_rn(r2, r3);
+  if (k + 2 <= D) {
+    r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
+    r1 = __dadd_rn(r1, __dmul_rn((double)v[k + 1], (double)v[k + 1]));
+    k += 2;
+  }
+  r1 = __dadd_rn(r1, r2);
+  if (k < D) r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
+  return (float)__dadd_rn(r0, r1);
+}
+
+__device__ __forceinline__ float i8_scaled_query(float q, float inv, int sql2) {
+  return __fmul_rn(q, sql2 ? __fmul_rn(inv, 2.0f) : inv);
+}
+
+__global__ void __launch_bounds__(256)
+tokenize_i8_kernel(const float* __restrict__ q, const float* __restrict__ inv_mult, const int8_t* __restrict__ c,
+                   const float* __restrict__ csq, float* __restrict__ out, int nq, int L, int D, int sql2) {
+  __shared__ __align__(16) float As[I8K][I8M + I8PAD];  // -q'
+  __shared__ __align__(16) float Bs[I8K][I8N + I8PAD];  // float(centre)
+  __shared__ float qn[I8M];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * I8M, n0 = blockIdx.x * I8N;
+  if (sql2 && tid < I8M) {
+    const int r = m0 + tid;
+    qn[tid] = r < nq ? squared_l2_norm_strided(q + (size_t)r * D, (uint32_t)D) : 0.f;
+  }
+  float acc[4][2][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[i][j][l] = 0.f;
+  const int D8 = D & ~7;
+  // stages dims [k0, k0 + I8K) that are < klim (zeros elsewhere)
+  auto stage = [&](int k0, int klim) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int row = idx >> 4, kk = idx & 15;
+      const int gr = m0 + row, gk = k0 + kk;
+      As[kk][row] = (gr < nq && gk < klim) ? -i8_scaled_query(q[(size_t)gr * D + gk], inv_mult[gk], sql2) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * 256;
+      const int row = idx >> 4, kk = idx & 15;
+      const int gc = n0 + row, gk = k0 + kk;
+      Bs[kk][row] = (gc < L && gk < klim) ? (float)c[(size_t)gc * D + gk] : 0.f;
+    }
+  };
+  for (int k0 = 0; k0 < D8; k0 += I8K) {
+    stage(k0, D8);
+    __syncthreads();
+    const int groups = min(2, (D8 - k0) >> 3);
+    for (int g = 0; g < groups; ++g) {
+#pragma unroll
+      for (int l = 0; l < 8; ++l) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[g * 8 + l][ty * 4]);
+        const float2 b = *reinterpret_cast<const float2*>(&Bs[g * 8 + l][tx * 2]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const float bv[2] = {b.x, b.y};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) acc[i][j][l] = __fmaf_rn(av[i], bv[j], acc[i][j][l]);
+      }
+    }
+    __syncthreads();
+  }
+  // the last D mod 8 dims: a 4-wide step into lanes 0..3 when at least four are left, the rest after the lane sum
+  const int rem = D - D8;
+  if (rem) stage(D8, D);
+  __syncthreads();  // also orders qn[]
+  int t = 0;
+  if (rem >= 4) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[l][ty * 4]);
+      const float2 b = *reinterpret_cast<const float2*>(&Bs[l][tx * 2]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[2] = {b.x, b.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][l] = __fmaf_rn(av[i], bv[j], acc[i][j][l]);
+    }
+    t = 4;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = m0 + ty * 4 + i;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float* a = acc[i][j];
+      float v = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])),
+                          __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
+      for (int kk = t; kk < rem; ++kk) v = __fmaf_rn(As[kk][ty * 4 + i], Bs[kk][tx * 2 + j], v);
+      const int col = n0 + tx * 2 + j;
+      if (r < nq && col < L) out[(size_t)r * L + col] = sql2 ? __fadd_rn(v, __fadd_rn(qn[ty * 4 + i], csq[col])) : v;
+    }
+  }
+}
+
+// The last L mod 3 centres: ComputeOneToOneScore<0, false> = -DenseDotProductInt8FloatAvxImpl (one_to_many_asymmetric_
+// impl.inc:629-639,223-258; distance_measures/one_to_one/dot_product_impl.inc:3-54): two 8-lane fmadd accumulators over
+// whole groups of 16 dims, one 8-wide fmadd step into the first, one 4-wide step as a rounded product ADDED to lanes
+// 0..3 of the first, Sum8(acc0 + acc1) = ((x0+x4)+(x2+x6)) + ((x1+x5)+(x3+x7)), the last < 4 dims fused on the scalar.
+// One thread per (query, tail centre).
+__global__ void __launch_bounds__(128)
+tokenize_i8_tail_kernel(const float* __restrict__ q, const float* __restrict__ inv_mult, const int8_t* __restrict__ c,
+                        const float* __restrict__ csq, float* __restrict__ out, int nq, int L, int D, int sql2, int L3) {
+  const int nt = L - L3;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nq * nt) return;
+  const int r = g / nt, col = L3 + g % nt;
+  const float* qr = q + (size_t)r * D;
+  const int8_t* x = c + (size_t)col * D;
+  auto qp = [&](int k) { return i8_scaled_query(qr[k], inv_mult[k], sql2); };
+  float a0[8], a1[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) a0[l] = a1[l] = 0.f;
+  int j = 0;
+  for (; j + 16 <= D; j += 16) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      a0[l] = __fmaf_rn((float)x[j + l], qp(j + l), a0[l]);
+      a1[l] = __fmaf_rn((float)x[j + 8 + l], qp(j + 8 + l), a1[l]);
+    }
+  }
+  if (j + 8 <= D) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a0[l] = __fmaf_rn((float)x[j + l], qp(j + l), a0[l]);
+    j += 8;
+  }
+  if (j + 4 <= D) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a0[l] = __fadd_rn(a0[l], __fmul_rn((float)x[j + l], qp(j + l)));
+    j += 4;
+  }
+  float v[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) v[l] = __fadd_rn(a0[l], a1[l]);
+  float s = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[4]), __fadd_rn(v[2], v[6])),
+                      __fadd_rn(__fadd_rn(v[1], v[5]), __fadd_rn(v[3], v[7])));
+  for (; j < D; ++j) s = __fmaf_rn((float)x[j], qp(j), s);
+  const float val = -s;
+  out[(size_t)r * L + col] = sql2 ? __fadd_rn(val, __fadd_rn(squared_l2_norm_strided(qr, (uint32_t)D), csq[col])) : val;
+}
+
 void launch_tokenize(const DevIndex& ix, const float* q, uint32_t nq, float* dist, cudaStream_t s) {
+  if (ix.centers_i8) {
+    const int sql2 = ix.distance == 1;
+    dim3 grid((ix.L + I8N - 1) / I8N, (nq + I8M - 1) / I8M);
+    tokenize_i8_kernel<<<grid, 256, 0, s>>>(q, ix.cen_inv_mult, ix.centers_i8, ix.cen_sqnorm, dist, (int)nq, (int)ix.L,
+                                            (int)ix.d, sql2);
+    const int L3 = (int)(ix.L / 3 * 3), nt = (int)ix.L - L3;
+    if (nt)
+      tokenize_i8_tail_kernel<<<((int)nq * nt + 127) / 128, 128, 0, s>>>(q, ix.cen_inv_mult, ix.centers_i8, ix.cen_sqnorm,
+                                                                         dist, (int)nq, (int)ix.L, (int)ix.d, sql2, L3);
+    return;
+  }
   dim3 grid((ix.L + TN - 1) / TN, (nq + TM - 1) / TM);
   tokenize_kernel<<<grid, 256, 0, s>>>(q, ix.centers, ix.center_sqnorm, dist, (int)nq, (int)ix.L,
                                        (int)ix.d, ix.distance == 1);
@@ -954,6 +1143,7 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
 }
 
 bool tokenize_tensor_path(const DevIndex& ix, uint32_t P) {
+  if (ix.centers_i8) return false;  // int8 tokenization: its own exact SIMT kernels (launch_tokenize)
   if (!ix.tok_b || P + 32 > (uint32_t)kRefineMaxCand || ix.d > 2048) return false;
   const char* e = getenv("SCANN_B200_TOKENIZE");
   if (e && !strcmp(e, "simt")) return false;
@@ -966,7 +1156,7 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   if (!tokenize_tensor_path(ix, P)) {
     launch_tokenize(ix, q, nq, dist, s);
     launch_topp(ix, dist, nq, P, leaves, bias, s);
-    if (launches) *launches += 2;
+    if (launches) *launches += (ix.centers_i8 && ix.L % 3) ? 3 : 2;
     return cudaGetLastError();
   }
   cudaError_t e = build_tokenize_operand(q, nq, ix.d, 1, a_ws, s);

@@ -38,6 +38,9 @@ class IndexArrays:
   int8_dataset: Optional[np.ndarray] = None   # [N, D] i8 (int8_dataset.npy): fixed-point reordering
   int8_multipliers: Optional[np.ndarray] = None  # [D] f32 (int8_multipliers.npy)
   dp_norms: Optional[np.ndarray] = None       # [N] f32 (dp_norms.npy), squared L2 only
+  # query_tokenization_type FIXED_POINT_INT8 (tree(quantize_centroids=True)): the searcher tokenizes queries against
+  # the fixed-point image of `centers` (derived at load time, as KMeansTreeNode::CreateFixedPointCenters does)
+  int8_tokenization: bool = False
   n: int = 0
   d: int = 0
   residual: bool = False
@@ -295,6 +298,17 @@ def int8_quantize(x, chunk=1 << 18):
     r += np.where(np.abs(v - r) >= np.float32(0.5), np.sign(v), np.float32(0)).astype(np.float32)   # std::round
     out[s:s + chunk] = np.clip(r, -128, 127).astype(np.int8)
   return out, mult
+
+
+def quantize_centers(centers):
+  """Fixed-point centres of int8 query tokenization: `KMeansTreeNode::CreateFixedPointCenters`
+  (trees/kmeans_tree/kmeans_tree_node.cc:267-281) = `ScalarQuantizeFloatDataset(float_centers, 1.0, NaN)`, its
+  `inverse_multiplier_by_dimension` (1.0f / multiplier, scalar_quantization_helpers.cc:133-136) and the squared norms
+  of the FLOAT centres.  Returns (int8 [L, D], inverse multipliers [D] f32, squared norms [L] f32).  The library derives
+  the same arrays in C++ (csrc/index.cu); this numpy restatement feeds the oracle and the tests."""
+  c = np.ascontiguousarray(centers, dtype=np.float32)
+  ci8, mult = int8_quantize(c)
+  return ci8, (np.float32(1.0) / mult).astype(np.float32), squared_l2_norms(c)
 
 
 def squared_l2_norms(x, chunk=1 << 18):

@@ -61,8 +61,11 @@ class _Plan:
     p, ah = self.partitioning, self.ah
     if p.has("projection") or p.has("bottom_up_top_level_partitioner"):
       unimpl("PCA/truncate projections and upper_tree")
-    if p.get("query_tokenization_type", "FLOAT") != "FLOAT":
-      unimpl("quantized centroids")
+    # tree(quantize_centroids=True): FIXED_POINT_INT8 query tokenization (csrc/prep.cu tokenize_i8_kernel)
+    if p.get("query_tokenization_type", "FLOAT") not in ("FLOAT", "FIXED_POINT_INT8"):
+      unimpl("query_tokenization_type " + str(p.get("query_tokenization_type")))
+    if p.get("database_tokenization_type", "FLOAT") != "FLOAT":
+      unimpl("database_tokenization_type other than FLOAT")
     # training options the GPU trainer does not honour are refused, not dropped (a user who asks for anisotropic
     # centroids must not get plain k-means silently)
     avq = cfgmod.as_float(p.get("avq"), math.nan)
@@ -111,6 +114,11 @@ class _Plan:
     utils/reordering_helper.cc:384-441,581-618; base/reordering_helper_factory.cc:106-175)."""
     r = self.reordering
     return r is not None and cfgmod.as_bool(r.path("fixed_point", "enabled"), False)
+
+  def int8_tokenization(self):
+    """partitioning { query_tokenization_type: FIXED_POINT_INT8 } (scann_builder.py:231, partitioner_factory.cc:95-98)."""
+    p = self.partitioning
+    return p is not None and p.get("query_tokenization_type", "FLOAT") == "FIXED_POINT_INT8"
 
   def dims_per_block(self):
     proj = self.ah.get("projection")
@@ -193,6 +201,7 @@ class ScannNumpy:
       self._n, self._d = arrays.n, arrays.d
       self._index = _lib.NativeIndex(arrays, 1, final_nn, final_nn)
       return
+    arrays.int8_tokenization = plan.int8_tokenization()
     leaves = cfgmod.as_int(plan.partitioning.path("query_spilling", "max_spill_centers"), arrays.centers.shape[0])
     pre = cfgmod.as_int(plan.reordering.get("approx_num_neighbors"), final_nn) if plan.reordering is not None else final_nn
     self._arrays = arrays

@@ -34,7 +34,7 @@ class Case:
   """A small tree-AH index + queries + oracle, shared by the parity tests."""
 
   def __init__(self, n=20000, d=100, leaves=100, dpb=2, nq=64, soar=None, distance="dot_product",
-               probe=10, pre=100, k=10, seed=1):
+               probe=10, pre=100, k=10, seed=1, int8_tok=False):
     from scann_b200 import datasets, index_build
     import oracle
     self.db = datasets.clustered(n, d, 4 * leaves, seed=seed, centers_seed=100 + seed)
@@ -42,6 +42,8 @@ class Case:
     self.arrays = index_build.build_tree_ah(self.db, distance, num_leaves=leaves, dims_per_block=dpb,
                                             training_sample_size=min(n, 20000), soar_lambda=soar,
                                             tree_iters=6, ah_iters=5, device="cpu")
+    # tree(quantize_centroids=True): queries are tokenized against the fixed-point centres
+    self.arrays.int8_tokenization = bool(int8_tok)
     self.probe, self.pre, self.k = probe, pre, k
     self.oracle = oracle.OracleIndex(self.arrays, probe, pre, k)
     self._native = None

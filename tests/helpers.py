@@ -43,6 +43,87 @@ def np_center_distances(q, centers):
   return acc
 
 
+def np_center_distances_i8(q, centers, distance):
+  """KMeansTreeNode::GetAllDistancesInt8 (trees/kmeans_tree/kmeans_tree_node.h:222-256), an independent numpy
+  restatement: fixed-point centres as CreateFixedPointCenters derives them, the three-at-a-time AVX2 order of
+  OneToManyAsymmetricTemplate<.., int8_t> for centres [0, 3 (L / 3)) and the one-to-one order of
+  DenseDotProductInt8FloatAvxImpl (dot_product_impl.inc:3-54) for the last L mod 3."""
+  from scann_b200 import index_build
+  ci8, inv, sqn = index_build.quantize_centers(centers)
+  l2 = distance != "dot_product"
+  scale = f32(inv * np.float32(2.0)) if l2 else inv
+  qp = f32(q * scale[None, :])                                # [nq, D]
+  c = ci8.astype(np.float32)                                  # [L, D]
+  nq, D = q.shape
+  L = c.shape[0]
+  L3 = L // 3 * 3
+  out = np.empty((nq, L), np.float32)
+  # main kernel: eight fnmadd lanes
+  a = np.zeros((8, nq, L), np.float32)
+  j = 0
+  while j + 8 <= D:
+    for l in range(8):
+      a[l] = fma32(-qp[:, j + l, None], c[None, :, j + l], a[l])
+    j += 8
+  if j + 4 <= D:
+    for l in range(4):
+      a[l] = fma32(-qp[:, j + l, None], c[None, :, j + l], a[l])
+    j += 4
+  r = f32(f32(f32(a[0] + a[4]) + f32(a[2] + a[6])) + f32(f32(a[1] + a[5]) + f32(a[3] + a[7])))
+  while j < D:
+    r = fma32(-qp[:, j, None], c[None, :, j], r)
+    j += 1
+  out[:] = r
+  # tail rows: one-to-one kernel, two accumulators over 16 dims, rounded product added in the 4-wide step
+  if L3 < L:
+    ct = c[L3:]
+    a0 = np.zeros((8, nq, L - L3), np.float32)
+    a1 = np.zeros((8, nq, L - L3), np.float32)
+    j = 0
+    while j + 16 <= D:
+      for l in range(8):
+        a0[l] = fma32(ct[None, :, j + l], qp[:, j + l, None], a0[l])
+        a1[l] = fma32(ct[None, :, j + 8 + l], qp[:, j + 8 + l, None], a1[l])
+      j += 16
+    if j + 8 <= D:
+      for l in range(8):
+        a0[l] = fma32(ct[None, :, j + l], qp[:, j + l, None], a0[l])
+      j += 8
+    if j + 4 <= D:
+      for l in range(4):
+        a0[l] = f32(a0[l] + f32(ct[None, :, j + l] * qp[:, j + l, None]))
+      j += 4
+    v = f32(a0 + a1)
+    s = f32(f32(f32(v[0] + v[4]) + f32(v[2] + v[6])) + f32(f32(v[1] + v[5]) + f32(v[3] + v[7])))
+    while j < D:
+      s = fma32(ct[None, :, j], qp[:, j, None], s)
+      j += 1
+    out[:, L3:] = -s
+  if l2:
+    qn = index_build.squared_l2_norms(q)
+    out = f32(out + f32(qn[:, None] + sqn[None, :]))
+  return out
+
+
+def i8_tok_arrays(L, D, distance, seed=0):
+  """A minimal tree-AH asset set whose only interesting part is the centres (the tokenizer reads nothing else)."""
+  from scann_b200 import index_build
+  rng = np.random.default_rng(seed)
+  n = max(4 * L, 64)
+  db = rng.standard_normal((n, D)).astype(np.float32)
+  a = index_build.IndexArrays(distance=distance, dataset=db, n=n, d=D)
+  a.centers = (rng.standard_normal((L, D)) * rng.uniform(0.2, 3.0, D)[None, :]).astype(np.float32)
+  if D > 2:
+    a.centers[:, 1] = 0.0                                    # an all-zero column: multiplier 1
+  a.tokens = (np.arange(n) % L).astype(np.int32)
+  a.codes = rng.integers(0, 16, (n, D), dtype=np.uint8)       # one dim per block
+  a.codebook = rng.standard_normal((D, 16, 1)).astype(np.float32)
+  a.block_dims = np.ones(D, np.int32)
+  a.soar, a.soar_codes, a.overretrieve, a.residual = False, None, 2.0, distance == "dot_product"
+  a.int8_tokenization = True
+  return a, rng.standard_normal((9, D)).astype(np.float32)
+
+
 def np_lut_dpb2(q, codebook):
   """asymmetric_hashing_impl.cc:505-645 for dims_per_block == 2 (two products, one add, no FMA)."""
   nq, B = q.shape[0], codebook.shape[0]

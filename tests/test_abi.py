@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
   for n in names:
     assert hasattr(lib, n), f"{n} declared in include/scann_b200.h but not exported"
   assert sorted(_lib.EXPORTS) == names
-  assert lib.scann_b200_abi_version() == 5
+  assert lib.scann_b200_abi_version() == 6
 
 
 def test_struct_layouts_match_header():

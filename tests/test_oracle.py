@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import golden_names, load_golden, np_center_distances, np_lut_dpb2, np_search, np_slots
+from helpers import golden_names, i8_tok_arrays as _i8_tok_arrays, load_golden, np_center_distances, np_lut_dpb2, np_search, np_slots
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -219,3 +219,45 @@ def test_float_bruteforce_oracles_against_numpy_restatements():
   np.testing.assert_array_equal(dist.view(np.uint32), np.take_along_axis(acc, order, axis=1).view(np.uint32))
   d2 = ((q.astype(np.float64)[:, None, :] - db.astype(np.float64)[None, :, :]) ** 2).sum(-1)
   np.testing.assert_allclose(dist, np.take_along_axis(d2, idx.astype(np.int64), axis=1), rtol=1e-5)
+
+
+# ---- int8 (FIXED_POINT_INT8) query tokenization: tree(quantize_centroids=True) -------------------------------------
+
+def test_fixed_point_centers_two_restatements_agree():
+  """KMeansTreeNode::CreateFixedPointCenters: the oracle's C restatement against the numpy one."""
+  from scann_b200 import index_build
+  for L, D in [(7, 5), (100, 100), (33, 17), (64, 128), (1, 3)]:
+    a, _ = _i8_tok_arrays(L, D, "dot_product", seed=L)
+    got = oracle.quantize_centers(a.centers)
+    want = index_build.quantize_centers(a.centers)
+    for g, w in zip(got, want):
+      np.testing.assert_array_equal(g.view(np.uint8 if g.dtype == np.int8 else np.uint32),
+                                    w.view(np.uint8 if w.dtype == np.int8 else np.uint32))
+    assert got[0].min() >= -127 and got[0].max() <= 127 and np.all(got[1][1] == 1.0)
+
+
+# L mod 3 = 0 / 1 / 2 (the last L mod 3 centres take the one-to-one kernel); D covers every tail of both kernels:
+# 100 = 6 x 16 + 4, 17 = 16 + 1, 23 = 16 + 4 + 3, 31 = 16 + 8 + 4 + 3, 12 = 8 + 4, 7 = 4 + 3, 3, 128, 64
+@pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
+@pytest.mark.parametrize("L,D", [(99, 100), (100, 100), (101, 17), (32, 23), (40, 31), (20, 12), (11, 7), (5, 3),
+                                 (64, 128), (50, 64), (2, 24), (1, 40)])
+def test_int8_tokenization_matches_numpy_restatement(L, D, distance):
+  from helpers import np_center_distances_i8
+  a, q = _i8_tok_arrays(L, D, distance, seed=L * 1000 + D)
+  P = min(L, 7)
+  oi = oracle.OracleIndex(a, P, 10, 5)
+  leaf, cdist = oi.tokenize(q, leaves=L)                     # every centre: the full distance row
+  want = np_center_distances_i8(q, a.centers, distance)
+  for i in range(len(q)):
+    np.testing.assert_array_equal(cdist[i].view(np.uint32), want[i, leaf[i]].view(np.uint32))
+    np.testing.assert_array_equal(leaf[i], np.lexsort((np.arange(L), want[i])))
+  # and it is not the float tokenization: distances differ (quantization error), the nearest centre mostly agrees
+  a.int8_tokenization = False
+  of = oracle.OracleIndex(a, P, 10, 5)
+  leaf_f, cdist_f = of.tokenize(q, leaves=L)
+  if D >= 12:
+    assert not np.array_equal(cdist_f, cdist)
+    order_f = np.argsort(leaf_f, axis=1)
+    order_i = np.argsort(leaf, axis=1)
+    df, di = np.take_along_axis(cdist_f, order_f, 1), np.take_along_axis(cdist, order_i, 1)
+    np.testing.assert_allclose(di, df, rtol=0.1, atol=0.05 * np.abs(df).max())
