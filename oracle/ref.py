@@ -1,5 +1,6 @@
 """ctypes binding of oracle/_ref/libscann_ref.so: pieces of the REFERENCE'S OWN code (its AVX2 LUT16 kernel, the LUT
-fixed-point conversion, the code packing, bfloat16 helpers) compiled from /root/reference by oracle/Makefile.
+fixed-point conversion, the code packing, bfloat16 helpers, the f32 x int8 / bf16 one-to-many kernels) compiled from
+/root/reference by oracle/Makefile.
 
 Test infrastructure: it pins oracle/scann_oracle.c (and, in the -m gpu tests, the CUDA kernels) to reference code
 instead of to restatements.  The library is built in the container that has /root/reference and travels to the GPU box
@@ -32,6 +33,10 @@ def lib():
     L.ref_lut_to_fixed_point.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_void_p]
     L.ref_bf16_quantize.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     L.ref_bf16_decompress.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    if hasattr(L, "ref_one_to_many_int8_float"):
+      L.ref_one_to_many_int8_float.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+      L.ref_one_to_many_int8_float_indexed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+      L.ref_one_to_many_bf16_float.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
     _LIB = L
   return _LIB
 
@@ -102,4 +107,33 @@ def bf16_decompress(x):
   x = np.ascontiguousarray(x, dtype=np.int16)
   out = np.zeros(x.shape, np.float32)
   lib().ref_bf16_decompress(_p(x), x.size, _p(out))
+  return out
+
+
+def has_asymmetric():
+  """True when the library carries the asymmetric one-to-many kernels (ref_glue_asym.cc)."""
+  return available() and hasattr(lib(), "ref_one_to_many_int8_float")
+
+
+def one_to_many_int8_float(query, rows, indices=None):
+  """DenseDotProductDistanceOneToManyInt8Float (one_to_many_asymmetric.cc:44-49, :79-86 with an index list):
+  -<query, float(row)> per row; the last n mod 3 results come from the reference's one-to-one kernel."""
+  query = np.ascontiguousarray(query, dtype=np.float32)
+  rows = np.ascontiguousarray(rows, dtype=np.int8)
+  if indices is None:
+    out = np.zeros(rows.shape[0], np.float32)
+    lib().ref_one_to_many_int8_float(_p(query), _p(rows), rows.shape[0], rows.shape[1], _p(out))
+    return out
+  indices = np.ascontiguousarray(indices, dtype=np.uint32)
+  out = np.zeros(indices.shape[0], np.float32)
+  lib().ref_one_to_many_int8_float_indexed(_p(query), _p(rows), rows.shape[1], _p(indices), indices.shape[0], _p(out))
+  return out
+
+
+def one_to_many_bf16_float(query, rows, squared_l2=False):
+  """DenseDotProductDistanceOneToManyBf16Float / OneToManyBf16FloatSquaredL2 over all rows (bf16 bits as int16)."""
+  query = np.ascontiguousarray(query, dtype=np.float32)
+  rows = np.ascontiguousarray(rows, dtype=np.int16)
+  out = np.zeros(rows.shape[0], np.float32)
+  lib().ref_one_to_many_bf16_float(_p(query), _p(rows), rows.shape[0], rows.shape[1], 1 if squared_l2 else 0, _p(out))
   return out

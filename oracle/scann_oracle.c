@@ -1093,27 +1093,25 @@ int so_candidates(const so_index* ix, const float* q, uint32_t nq, int pre_nn, i
 
 /* brute_force/bfloat16_brute_force.cc:131-147: dist_i = -sum_d q[d] * f32(bf16 x[i][d]) with an f32
  * query and f32 accumulation, over ALL rows, then the k smallest (distance, index).
- * The lane order of OneToManyBf16FloatImpl (one_to_many_asymmetric_impl.inc) is not part of the
- * contract (the north star states recall@k equality for bf16 brute force); the oracle uses the
- * same 8-lane FMA order as the float reorder kernel so that the GPU re-scoring can be bit-exact. */
+ * DenseDotProductDistanceOneToManyBf16Float = OneToManyAsymmetricTemplate<dims, 3, .., int16_t> on AVX2
+ * (distance_measures/one_to_many/one_to_many_asymmetric_impl.inc:296-353,697-721), the kernel of the int8 path with
+ * Bfloat16Decompress on the loads: eight fnmadd lanes over whole groups of 8 dims (HandleXDims<16> is two such steps),
+ * one 4-wide step into lanes 0..3, HorizontalSum3X = ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), the remaining dims one by
+ * one with fnmadd on the scalar.  Pinned to the reference's compiled kernel by tests/test_oracle_ref.py.  (The last
+ * n mod 3 rows of a call go through ComputeOneToOneScore, :260-289 -- 16-wide groups only, a horizontal sum, every
+ * remaining dim on the scalar -- which can differ in the last bit when dims is not a multiple of 16; which rows of a
+ * candidate list those are is unspecified, so every row uses the main kernel.) */
 static float neg_dot_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n) {
   float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint32_t j = 0;
   for (; j + 8 <= n; j += 8)
     for (int l = 0; l < 8; ++l) a[l] = fmaf(-q[j + l], bf16_to_f32(x[j + l]), a[l]);
-  float b[4];
-  for (int l = 0; l < 4; ++l) b[l] = a[l + 4] + a[l];
   if (j + 4 <= n) {
-    for (int l = 0; l < 4; ++l) b[l] = fmaf(-q[j + l], bf16_to_f32(x[j + l]), b[l]);
+    for (int l = 0; l < 4; ++l) a[l] = fmaf(-q[j + l], bf16_to_f32(x[j + l]), a[l]);
     j += 4;
   }
-  if (j + 2 <= n) {
-    b[2] = fmaf(-q[j], bf16_to_f32(x[j]), b[2]);
-    b[3] = fmaf(-q[j + 1], bf16_to_f32(x[j + 1]), b[3]);
-    j += 2;
-  }
-  float r = (b[0] + b[2]) + (b[1] + b[3]);
-  if (j < n) r = fmaf(-q[j], bf16_to_f32(x[j]), r);
+  float r = ((a[0] + a[4]) + (a[2] + a[6])) + ((a[1] + a[5]) + (a[3] + a[7]));
+  for (; j < n; ++j) r = fmaf(-q[j], bf16_to_f32(x[j]), r);
   return r;
 }
 
@@ -1123,19 +1121,12 @@ static float sql2_bf16_avx2_order(const float* q, const int16_t* x, uint32_t n) 
   uint32_t j = 0;
   for (; j + 8 <= n; j += 8)
     for (int l = 0; l < 8; ++l) { const float t = q[j + l] - bf16_to_f32(x[j + l]); a[l] = fmaf(t, t, a[l]); }
-  float b[4];
-  for (int l = 0; l < 4; ++l) b[l] = a[l + 4] + a[l];
   if (j + 4 <= n) {
-    for (int l = 0; l < 4; ++l) { const float t = q[j + l] - bf16_to_f32(x[j + l]); b[l] = fmaf(t, t, b[l]); }
+    for (int l = 0; l < 4; ++l) { const float t = q[j + l] - bf16_to_f32(x[j + l]); a[l] = fmaf(t, t, a[l]); }
     j += 4;
   }
-  if (j + 2 <= n) {
-    { const float t = q[j] - bf16_to_f32(x[j]); b[2] = fmaf(t, t, b[2]); }
-    { const float t = q[j + 1] - bf16_to_f32(x[j + 1]); b[3] = fmaf(t, t, b[3]); }
-    j += 2;
-  }
-  float r = (b[0] + b[2]) + (b[1] + b[3]);
-  if (j < n) { const float t = q[j] - bf16_to_f32(x[j]); r = fmaf(t, t, r); }
+  float r = ((a[0] + a[4]) + (a[2] + a[6])) + ((a[1] + a[5]) + (a[3] + a[7]));
+  for (; j < n; ++j) { const float t = q[j] - bf16_to_f32(x[j]); r = fmaf(t, t, r); }
   return r;
 }
 

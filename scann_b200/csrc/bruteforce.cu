@@ -697,12 +697,12 @@ rescore_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ db
     float acc = 0.f;
     uint32_t j = 0;
     for (; j + 8 <= d; j += 8) acc = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), acc);
-    float b = __fadd_rn(__shfl_down_sync(0xFFFFFFFFu, acc, 4, 8), acc);
-    if (j + 4 <= d) { if (l < 4) b = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), b); j += 4; }
-    if (j + 2 <= d) { if (l == 2 || l == 3) b = __fmaf_rn(-sq[j + l - 2], __bfloat162float(x[j + l - 2]), b); j += 2; }
+    // the reference's asymmetric kernel (exact_math.cuh neg_dot_asym_order): 4-wide step into lanes 0..3 before the sum
+    if (j + 4 <= d) { if (l < 4) acc = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), acc); j += 4; }
+    const float b = __fadd_rn(acc, __shfl_down_sync(0xFFFFFFFFu, acc, 4, 8));
     const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));
     float r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));
-    if (j < d && l == 0) r = __fmaf_rn(-sq[j], __bfloat162float(x[j]), r);
+    if (l == 0) for (; j < d; ++j) r = __fmaf_rn(-sq[j], __bfloat162float(x[j]), r);
     if (valid && l == 0) ka[c] = make_key(r, dp);
   }
   __syncthreads();
@@ -840,12 +840,11 @@ exact_round_kernel(const float* __restrict__ q, const void* __restrict__ dbv, ui
       float acc = 0.f;
       uint32_t j = 0;
       for (; j + 8 <= d; j += 8) acc = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), acc);
-      float b = __fadd_rn(__shfl_down_sync(0xFFFFFFFFu, acc, 4, 8), acc);
-      if (j + 4 <= d) { if (l < 4) b = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), b); j += 4; }
-      if (j + 2 <= d) { if (l == 2 || l == 3) b = __fmaf_rn(-sq[j + l - 2], __bfloat162float(x[j + l - 2]), b); j += 2; }
+      if (j + 4 <= d) { if (l < 4) acc = __fmaf_rn(-sq[j + l], __bfloat162float(x[j + l]), acc); j += 4; }
+      const float b = __fadd_rn(acc, __shfl_down_sync(0xFFFFFFFFu, acc, 4, 8));
       const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));
       r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));
-      if (j < d && l == 0) r = __fmaf_rn(-sq[j], __bfloat162float(x[j]), r);
+      if (l == 0) for (; j < d; ++j) r = __fmaf_rn(-sq[j], __bfloat162float(x[j]), r);
     }
     if (valid && l == 0) {
       const uint64_t key = make_key(r, row);

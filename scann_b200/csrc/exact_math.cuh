@@ -41,6 +41,58 @@ __device__ __forceinline__ float neg_dot_avx2_order(LoadQ q, LoadX x, uint32_t n
   return r;
 }
 
+// distance_measures/one_to_many/one_to_many_asymmetric_impl.inc:296-353 (OneToManyAsymmetricTemplate<.., int16_t> /
+// <.., int8_t> on AVX2: f32 query x bf16 or int8 row): eight fnmadd lanes over whole groups of 8 dims, one 4-wide step
+// into lanes 0..3, HorizontalSum3X = ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), the remaining dims fused on the scalar.
+// Pinned to the reference's compiled kernel through the oracle (tests/test_oracle_ref.py).
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float neg_dot_asym_order(LoadQ q, LoadX x, uint32_t n) {
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a[l] = __fmaf_rn(-q(j + l), x(j + l), a[l]);
+  }
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a[l] = __fmaf_rn(-q(j + l), x(j + l), a[l]);
+    j += 4;
+  }
+  float r = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])),
+                      __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
+  for (; j < n; ++j) r = __fmaf_rn(-q(j), x(j), r);
+  return r;
+}
+
+// FusedMultiplyOp<kIsSquaredL2 = true, int16_t> (:102-116): diff = q - x; acc = fma(diff, diff, acc), same lanes
+template <typename LoadQ, typename LoadX>
+__device__ __forceinline__ float sql2_asym_order(LoadQ q, LoadX x, uint32_t n) {
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  uint32_t j = 0;
+  for (; j + 8 <= n; j += 8) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      const float t = __fsub_rn(q(j + l), x(j + l));
+      a[l] = __fmaf_rn(t, t, a[l]);
+    }
+  }
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const float t = __fsub_rn(q(j + l), x(j + l));
+      a[l] = __fmaf_rn(t, t, a[l]);
+    }
+    j += 4;
+  }
+  float r = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])),
+                      __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
+  for (; j < n; ++j) {
+    const float t = __fsub_rn(q(j), x(j));
+    r = __fmaf_rn(t, t, r);
+  }
+  return r;
+}
+
 // SquaredL2DistanceLambdas::FmaTerm (one_to_many_symmetric.h:1043-1051).
 template <typename LoadQ, typename LoadX>
 __device__ __forceinline__ float sql2_avx2_order(LoadQ q, LoadX x, uint32_t n) {

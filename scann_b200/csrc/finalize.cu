@@ -53,10 +53,11 @@ __device__ __forceinline__ float exact_distance(const DevIndex& ix, const float*
   const uint32_t row = ix.dp_row ? ix.dp_row[dp] : dp;
   auto lq = [&](uint32_t i) { return q[i]; };
   if (!ix.dataset) {
-    // bfloat16 reordering (utils/reordering_helper.cc:745-757): f32 query x bf16 row, f32 FMA, 8-lane order
+    // bfloat16 reordering (utils/reordering_helper.cc:745-757): f32 query x bf16 row, f32 FMA, in the order of the
+    // reference's asymmetric one-to-many kernel (exact_math.cuh)
     const uint16_t* xb = ix.dataset_bf16 + (size_t)row * ix.d;
     auto lb = [&](uint32_t i) { return __uint_as_float((uint32_t)__ldg(xb + i) << 16); };
-    return ix.distance == 0 ? neg_dot_avx2_order(lq, lb, ix.d) : sql2_avx2_order(lq, lb, ix.d);
+    return ix.distance == 0 ? neg_dot_asym_order(lq, lb, ix.d) : sql2_asym_order(lq, lb, ix.d);
   }
   const float* x = ix.dataset + (size_t)row * ix.d;
   auto lx = [&](uint32_t i) { return __ldg(x + i); };
@@ -120,7 +121,9 @@ __device__ __forceinline__ float exact_distance_lanes8(const DevIndex& ix, const
   return r;
 }
 
-// bf16 rows: the same lane structure with Bfloat16Decompress on every load.
+// bf16 rows: lane l owns AVX lane l of the reference's ASYMMETRIC kernel (one_to_many_asymmetric_impl.inc:296-353, see
+// neg_dot_asym_order in exact_math.cuh): the 4-wide step goes into lanes 0..3 BEFORE the lanes are summed, and every
+// remaining dim is fused onto the sum.
 __device__ __forceinline__ float exact_distance_lanes8_bf16(const DevIndex& ix, const float* __restrict__ q,
                                                        uint32_t dp, int l) {
   const uint32_t row = ix.dp_row ? ix.dp_row[dp] : dp;
@@ -134,29 +137,23 @@ __device__ __forceinline__ float exact_distance_lanes8_bf16(const DevIndex& ix, 
     if (dot) a = __fmaf_rn(-qv, xv, a);
     else { const float t = __fsub_rn(qv, xv); a = __fmaf_rn(t, t, a); }
   }
-  float b = __fadd_rn(__shfl_down_sync(0xFFFFFFFFu, a, 4, 8), a);  // lanes 0..3: a[l+4] + a[l]
   if (j + 4 <= n) {
     if (l < 4) {
       const float xv = __uint_as_float((uint32_t)__ldg(x + j + l) << 16), qv = q[j + l];
-      if (dot) b = __fmaf_rn(-qv, xv, b);
-      else { const float t = __fsub_rn(qv, xv); b = __fmaf_rn(t, t, b); }
+      if (dot) a = __fmaf_rn(-qv, xv, a);
+      else { const float t = __fsub_rn(qv, xv); a = __fmaf_rn(t, t, a); }
     }
     j += 4;
   }
-  if (j + 2 <= n) {
-    if (l == 2 || l == 3) {
-      const float xv = __uint_as_float((uint32_t)__ldg(x + j + (l - 2)) << 16), qv = q[j + (l - 2)];
-      if (dot) b = __fmaf_rn(-qv, xv, b);
-      else { const float t = __fsub_rn(qv, xv); b = __fmaf_rn(t, t, b); }
+  const float b = __fadd_rn(a, __shfl_down_sync(0xFFFFFFFFu, a, 4, 8));    // lanes 0..3: a[l] + a[l+4]
+  const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));   // lanes 0,1: (a0+a4)+(a2+a6), (a1+a5)+(a3+a7)
+  float r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));        // lane 0
+  if (l == 0) {
+    for (; j < n; ++j) {
+      const float xv = __uint_as_float((uint32_t)__ldg(x + j) << 16), qv = q[j];
+      if (dot) r = __fmaf_rn(-qv, xv, r);
+      else { const float t = __fsub_rn(qv, xv); r = __fmaf_rn(t, t, r); }
     }
-    j += 2;
-  }
-  const float t2 = __fadd_rn(b, __shfl_down_sync(0xFFFFFFFFu, b, 2, 8));   // lanes 0,1: b0+b2, b1+b3
-  float r = __fadd_rn(t2, __shfl_down_sync(0xFFFFFFFFu, t2, 1, 8));        // lane 0: (b0+b2)+(b1+b3)
-  if (j < n && l == 0) {
-    const float xv = __uint_as_float((uint32_t)__ldg(x + j) << 16), qv = q[j];
-    if (dot) r = __fmaf_rn(-qv, xv, r);
-    else { const float t = __fsub_rn(qv, xv); r = __fmaf_rn(t, t, r); }
   }
   return r;
 }

@@ -165,3 +165,101 @@ def test_bfloat16_helpers_equal_the_reference():
   want = ref.bf16_decompress(bits)
   got = (bits.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
   np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ---- the asymmetric one-to-many kernels (ref_glue_asym.cc): int8 tokenization, int8 / bfloat16 reordering -----------
+
+needs_asym = pytest.mark.skipif(not (ref.available() and ref.has_asymmetric()),
+                                reason="oracle/_ref/libscann_ref.so without the asymmetric kernels")
+
+
+@needs_asym
+@pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
+@pytest.mark.parametrize("L,D", [(99, 100), (100, 100), (101, 17), (32, 23), (40, 31), (20, 12), (11, 7), (5, 3),
+                                 (64, 128), (50, 64), (2, 24), (1, 40), (700, 96)])
+def test_int8_tokenization_equals_the_reference_kernel(L, D, distance):
+  """KMeansTreeNode::GetAllDistancesInt8 (kmeans_tree_node.h:222-256) assembled around the REFERENCE'S OWN
+  DenseDotProductDistanceOneToManyInt8Float: the oracle's centre distances, all L of them -- the three-at-a-time order
+  and the one-to-one order of the last L mod 3 centres -- bit for bit.  D = 128 / 64 take the fixed-dimension template
+  instances (one_to_many_asymmetric_impl.inc:681-695)."""
+  import oracle
+  from helpers import i8_tok_arrays
+  from scann_b200 import index_build
+  a, q = i8_tok_arrays(L, D, distance, seed=L * 1000 + D)
+  ci8, inv, sqn = oracle.quantize_centers(a.centers)
+  oi = oracle.OracleIndex(a, min(L, 7), 10, 5)
+  leaf, cdist = oi.tokenize(q, leaves=L)
+  l2 = distance == "squared_l2"
+  for i in range(len(q)):
+    qp = (q[i] * (inv * np.float32(2.0) if l2 else inv)).astype(np.float32)
+    want = ref.one_to_many_int8_float(qp, ci8)
+    if l2:
+      qn = index_build.squared_l2_norms(q[i:i + 1])[0]
+      want = (want + (qn + sqn).astype(np.float32)).astype(np.float32)
+    np.testing.assert_array_equal(cdist[i].view(np.uint32), want[leaf[i]].view(np.uint32))
+
+
+@needs_asym
+@pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
+@pytest.mark.parametrize("D", [100, 64, 128, 23, 7])
+def test_int8_reordering_distances_equal_the_reference_kernel(D, distance):
+  """FixedPointFloatDense{DotProduct,SquaredL2}ReorderingHelper (utils/reordering_helper.cc:430-441,610-618): the
+  oracle's int8 reordering distance against the reference's indexed one-to-many kernel.  The reference sends the last
+  n mod 3 entries of a candidate list through its one-to-one kernel (another summation order, list order unspecified);
+  the oracle states the three-at-a-time order for every row, so lists of 3 m candidates are compared."""
+  import oracle
+  from scann_b200 import index_build
+  rng = np.random.default_rng(D)
+  n = 600
+  db = (rng.standard_normal((n, D)) * rng.uniform(0.1, 4.0, D)[None, :]).astype(np.float32)
+  a = index_build.IndexArrays(distance=distance, dataset=None, n=n, d=D)
+  a.int8_dataset, a.int8_multipliers = index_build.int8_quantize(db)
+  if distance == "squared_l2":
+    a.dp_norms = index_build.squared_l2_norms(db)
+  a.centers = db[:4].copy()
+  a.tokens = (np.arange(n) % 4).astype(np.int32)
+  a.codes = rng.integers(0, 16, (n, D), dtype=np.uint8)
+  a.codebook = rng.standard_normal((D, 16, 1)).astype(np.float32)
+  a.block_dims = np.ones(D, np.int32)
+  a.soar, a.soar_codes, a.overretrieve, a.residual = False, None, 2.0, distance == "dot_product"
+  oi = oracle.OracleIndex(a, 2, 30, 10)
+  inv = (np.float32(1.0) / a.int8_multipliers).astype(np.float32)
+  for qi in range(5):
+    q = rng.standard_normal(D).astype(np.float32)
+    dps = rng.permutation(n)[:300].astype(np.uint32)      # 3 m candidates
+    got = oi.exact_distances(q, dps)
+    val = ref.one_to_many_int8_float((inv * q).astype(np.float32), a.int8_dataset, dps)
+    if distance == "squared_l2":
+      qn = index_build.squared_l2_norms(q[None, :])[0]
+      val = ((qn + a.dp_norms[dps]).astype(np.float32) + (np.float32(2.0) * val).astype(np.float32)).astype(np.float32)
+    np.testing.assert_array_equal(got.view(np.uint32), val.view(np.uint32))
+
+
+@needs_asym
+@pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
+@pytest.mark.parametrize("D", [100, 64, 128, 23, 7, 768])
+def test_bfloat16_reordering_distances_equal_the_reference_kernel(D, distance):
+  """Bfloat16ReorderingHelper (utils/reordering_helper.cc:745-757): f32 query x bf16 row, the oracle against
+  DenseDotProductDistanceOneToManyBf16Float / OneToManyBf16FloatSquaredL2 over 3 m rows (see the int8 test)."""
+  import oracle
+  from scann_b200 import index_build
+  rng = np.random.default_rng(D + 1)
+  n = 300
+  db = rng.standard_normal((n, D)).astype(np.float32)
+  a = index_build.IndexArrays(distance=distance, dataset=None, n=n, d=D)
+  a.bf16_dataset = index_build.bfloat16_quantize(db)
+  B = min(D, 64)
+  a.centers = db[:4].copy()
+  a.tokens = (np.arange(n) % 4).astype(np.int32)
+  dims = np.full(B, D // B, np.int32)
+  dims[:D % B] += 1
+  a.codes = rng.integers(0, 16, (n, B), dtype=np.uint8)
+  a.codebook = rng.standard_normal((B, 16, int(dims.max()))).astype(np.float32)
+  a.block_dims = dims
+  a.soar, a.soar_codes, a.overretrieve, a.residual = False, None, 2.0, distance == "dot_product"
+  oi = oracle.OracleIndex(a, 2, 30, 10)
+  for qi in range(5):
+    q = rng.standard_normal(D).astype(np.float32)
+    got = oi.exact_distances(q, np.arange(n, dtype=np.uint32))
+    want = ref.one_to_many_bf16_float(q, a.bf16_dataset, squared_l2=distance == "squared_l2")
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
