@@ -37,6 +37,10 @@ def lib():
       L.ref_one_to_many_int8_float.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
       L.ref_one_to_many_int8_float_indexed.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
       L.ref_one_to_many_bf16_float.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+    if hasattr(L, "ref_one_to_many_f32"):
+      L.ref_one_to_many_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
+      L.ref_squared_l2_norm.restype = C.c_double
+      L.ref_squared_l2_norm.argtypes = [C.c_void_p, C.c_uint64]
     _LIB = L
   return _LIB
 
@@ -137,3 +141,25 @@ def one_to_many_bf16_float(query, rows, squared_l2=False):
   out = np.zeros(rows.shape[0], np.float32)
   lib().ref_one_to_many_bf16_float(_p(query), _p(rows), rows.shape[0], rows.shape[1], 1 if squared_l2 else 0, _p(out))
   return out
+
+
+def has_symmetric():
+  """True when the library carries the symmetric float one-to-many kernel (ref_glue_sym.cc)."""
+  return available() and hasattr(lib(), "ref_one_to_many_f32")
+
+
+def one_to_many_f32(query, rows, squared_l2=False):
+  """DenseAccumulatingDistanceMeasureOneToManyInternalAvx2 (one_to_many_symmetric.h:373-503) with the dot-product or
+  squared-L2 lambdas over a row-major f32 matrix of 3 m rows, dims >= 8."""
+  query = np.ascontiguousarray(query, dtype=np.float32)
+  rows = np.ascontiguousarray(rows, dtype=np.float32)
+  out = np.zeros(rows.shape[0], np.float32)
+  rc = lib().ref_one_to_many_f32(_p(query), _p(rows), rows.shape[0], rows.shape[1], 1 if squared_l2 else 0, _p(out))
+  assert rc == 0, "ref_one_to_many_f32 needs dims >= 8 and 3 m rows"
+  return out
+
+
+def squared_l2_norm(v):
+  """SquaredL2Norm(ConstSpan<float>) = DenseSingleAccumulate(v, Square()) (utils/reduction.h:357-390), a double."""
+  v = np.ascontiguousarray(v, dtype=np.float32)
+  return float(lib().ref_squared_l2_norm(_p(v), v.size))

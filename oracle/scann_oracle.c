@@ -441,12 +441,10 @@ static void center_distances(const so_index* ix, const float* q, float* out) {
       for (uint32_t l = 0; l < L; ++l) out[l] = fmaf(nq, c[l], out[l]);
     }
   } else {
-    /* SquaredL2Norm(q): distance_measures/one_to_one/l2_distance.h DenseSquaredL2Norm,
-     * accumulated in double and narrowed (query norm is a scalar shared by all leaves,
-     * so its rounding cannot reorder leaves; it only shifts the reported distance). */
-    double qn = 0.0;
-    for (uint32_t k = 0; k < D; ++k) qn += (double)q[k] * (double)q[k];
-    const float qnf = (float)qn;
+    /* query_norms[i] = SquaredL2Norm(query i) (many_to_many_impl.inc:417-426; distance_measures/one_to_one/
+     * l2_distance.h:108-120 -> DenseSingleAccumulate, utils/reduction.h:357-390: four strided double accumulators),
+     * narrowed to float. */
+    const float qnf = (float)squared_l2_norm_f64(q, D);
     for (uint32_t l = 0; l < L; ++l) out[l] = 0.0f;
     for (uint32_t k = 0; k < D; ++k) {
       const float* c = ix->centers_t + (size_t)k * L;
@@ -1217,9 +1215,7 @@ int so_bruteforce_f32_l2(const float* db, uint32_t n, uint32_t d, const float* q
     topn_t tn;
     topn_init(&tn, (size_t)k);
     const float* qi = q + (size_t)i * d;
-    double qn = 0.0;
-    for (uint32_t j = 0; j < d; ++j) qn += (double)qi[j] * (double)qi[j];
-    const float qnf = (float)qn;
+    const float qnf = (float)squared_l2_norm_f64(qi, d);
     for (uint32_t r = 0; r < n; ++r) {
       const float* x = db + (size_t)r * d;
       float acc = xn[r] + qnf;
@@ -1260,9 +1256,7 @@ uint64_t so_last_encode_ties(void) { return g_encode_ties; }
  * (many_to_many_impl.inc:236-257,522-567), ManyToManyTop1Callback keeps the first strict minimum
  * (many_to_many_common.h:176-199) = argmin by (distance, centre index). */
 static void l2_center_distances(const float* x, const float* centers_t, const float* cnorm, uint32_t L, uint32_t D, float* out) {
-  double qn = 0.0;
-  for (uint32_t k = 0; k < D; ++k) qn += (double)x[k] * (double)x[k];
-  const float qnf = (float)qn;
+  const float qnf = (float)squared_l2_norm_f64(x, D);  /* SquaredL2Norm of the "query" (a datapoint), see center_distances */
   for (uint32_t l = 0; l < L; ++l) out[l] = cnorm[l] + qnf;
   for (uint32_t k = 0; k < D; ++k) {
     const float nq = -x[k];

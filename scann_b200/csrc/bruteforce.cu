@@ -30,6 +30,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exact_math.cuh"
 #include "kernels.h"
 
 namespace sb {
@@ -633,13 +634,9 @@ struct SafetyArgs {
   // q' = [q, 1] (t = ||x||^2 / 2 - <q, x> = (L2 - ||q||^2) / 2), the exact keys are squared-L2 chain values
   int l2;
 };
-// ||q||^2 as SquaredL2Norm computes it for the many-to-many kernel (many_to_many_impl.inc:417-426): double accumulation
-// in dimension order, narrowed once
-__device__ __forceinline__ float query_sqnorm_ref(const float* sq, uint32_t d) {
-  double a = 0.0;
-  for (uint32_t i = 0; i < d; ++i) a += (double)sq[i] * (double)sq[i];
-  return (float)a;
-}
+// ||q||^2 as SquaredL2Norm computes it for the many-to-many kernel (many_to_many_impl.inc:417-426): the four strided
+// double accumulators of DenseSingleAccumulate, narrowed once (exact_math.cuh)
+__device__ __forceinline__ float query_sqnorm_ref(const float* sq, uint32_t d) { return squared_l2_norm_strided(sq, d); }
 __device__ __forceinline__ void check_window(const SafetyArgs& sa, uint32_t qi, const float* sq, uint32_t d, uint32_t m,
                                              uint32_t kprime, uint32_t kk, const uint64_t* src, const uint64_t* ka) {
   if (!sa.unsafe) return;

@@ -13,6 +13,30 @@
 
 namespace sb {
 
+// float(SquaredL2Norm(v)) (distance_measures/one_to_one/l2_distance.h:108-120 -> DenseSingleAccumulate, utils/reduction.h:
+// 357-390): four strided double accumulators, folded r2 += r3, a 2-wide step, r1 += r2, the last element, r0 + r1.  The
+// squares of floats are exact in double, so fusing or not cannot matter.  Pinned to the reference's compiled
+// DenseSingleAccumulate through the oracle (tests/test_oracle_ref.py).
+__device__ __forceinline__ float squared_l2_norm_strided(const float* __restrict__ v, uint32_t D) {
+  double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+  uint32_t k = 0;
+  for (; k + 4 <= D; k += 4) {
+    r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
+    r1 = __dadd_rn(r1, __dmul_rn((double)v[k + 1], (double)v[k + 1]));
+    r2 = __dadd_rn(r2, __dmul_rn((double)v[k + 2], (double)v[k + 2]));
+    r3 = __dadd_rn(r3, __dmul_rn((double)v[k + 3], (double)v[k + 3]));
+  }
+  r2 = __dadd_rn(r2, r3);
+  if (k + 2 <= D) {
+    r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
+    r1 = __dadd_rn(r1, __dmul_rn((double)v[k + 1], (double)v[k + 1]));
+    k += 2;
+  }
+  r1 = __dadd_rn(r1, r2);
+  if (k < D) r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
+  return (float)__dadd_rn(r0, r1);
+}
+
 // distance_measures/one_to_many/one_to_many_symmetric.h:373-503 (AVX2 one-to-many, dims >= 8):
 // eight fnmadd lanes, top+bottom fold, 4-wide and 2-wide steps, (x0+x2)+(x1+x3), fused tail.
 template <typename LoadQ, typename LoadX>

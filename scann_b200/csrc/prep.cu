@@ -36,13 +36,10 @@ tokenize_kernel(const float* __restrict__ q, const float* __restrict__ c,
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   float acc[4][4];
   if (sql2) {
-    // acc = ||c||^2 + ||q||^2 (many_to_many_impl.inc:530-541); ||q||^2 accumulated in double.
+    // acc = ||c||^2 + ||q||^2 (many_to_many_impl.inc:530-541); ||q||^2 = float(SquaredL2Norm(q)) (:417-426)
     if (tid < TM) {
-      double s = 0.0;
       const int r = m0 + tid;
-      if (r < nq)
-        for (int k = 0; k < D; ++k) s += (double)q[(size_t)r * D + k] * (double)q[(size_t)r * D + k];
-      qn[tid] = (float)s;
+      qn[tid] = r < nq ? squared_l2_norm_strided(q + (size_t)r * D, (uint32_t)D) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -110,27 +107,6 @@ tokenize_kernel(const float* __restrict__ q, const float* __restrict__ c,
 // lane sees its dims in the reference's order whatever the tiling over k.
 // ---------------------------------------------------------------------------------------
 constexpr int I8M = 64, I8N = 32, I8K = 16, I8PAD = 4;
-
-// float(SquaredL2Norm(q)): DenseSingleAccumulate, four strided double accumulators (utils/reduction.h:357-390)
-__device__ __forceinline__ float squared_l2_norm_strided(const float* __restrict__ v, uint32_t D) {
-  double r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-  uint32_t k = 0;
-  for (; k + 4 <= D; k += 4) {
-    r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
-    r1 = __dadd_rn(r1, __dmul_rn((double)v[k + 1], (double)v[k + 1]));
-    r2 = __dadd_rn(r2, __dmul_rn((double)v[k + 2], (double)v[k + 2]));
-    r3 = __dadd_rn(r3, __dmul_rn((double)v[k + 3], (double)v[k + 3]));
-  }
-  r2 = __dadd_rn(r2, r3);
-  if (k + 2 <= D) {
-    r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
-    r1 = __dadd_rn(r1, __dmul_rn((double)v[k + 1], (double)v[k + 1]));
-    k += 2;
-  }
-  r1 = __dadd_rn(r1, r2);
-  if (k < D) r0 = __dadd_rn(r0, __dmul_rn((double)v[k], (double)v[k]));
-  return (float)__dadd_rn(r0, r1);
-}
 
 __device__ __forceinline__ float i8_scaled_query(float q, float inv, int sql2) {
   return __fmul_rn(q, sql2 ? __fmul_rn(inv, 2.0f) : inv);
@@ -594,12 +570,8 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
 #pragma unroll
   for (int i = 0; i < kWarps; ++i) ssq += red_a[i];
   float qn = 0.f;
-  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
-    if (tid == 0) {
-      double acc = 0.0;
-      for (int k = 0; k < D; ++k) acc += (double)sq[k] * (double)sq[k];
-      red_b[0] = (float)acc;
-    }
+  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: float(SquaredL2Norm(q))
+    if (tid == 0) red_b[0] = squared_l2_norm_strided(sq, (uint32_t)D);
     __syncthreads();
     qn = red_b[0];
   }
@@ -889,10 +861,10 @@ topp_stream_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, o);
   __syncwarp();
   float qn = 0.f;
-  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
-    double acc = 0.0;
-    if (lane == 0) for (int k = 0; k < D; ++k) acc += (double)sq[k] * (double)sq[k];
-    qn = (float)__shfl_sync(0xFFFFFFFFu, acc, 0);
+  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: float(SquaredL2Norm(q))
+    float acc = 0.f;
+    if (lane == 0) acc = squared_l2_norm_strided(sq, (uint32_t)D);
+    qn = __shfl_sync(0xFFFFFFFFu, acc, 0);
   }
   const float qnorm = sqrtf(ssq) * 1.001f, cmax = ix.center_max_norm;
   float eps = eps_rel * qnorm * cmax;
@@ -1039,10 +1011,10 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
   for (int o = 16; o > 0; o >>= 1) ssq += __shfl_xor_sync(0xFFFFFFFFu, ssq, o);
   __syncwarp();
   float qn = 0.f;
-  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: sequential double accumulation
-    double acc = 0.0;
-    if (lane == 0) for (int k = 0; k < D; ++k) acc += (double)sq[k] * (double)sq[k];
-    qn = (float)__shfl_sync(0xFFFFFFFFu, acc, 0);
+  if (sql2) {  // ||q||^2 exactly as tokenize_kernel: float(SquaredL2Norm(q))
+    float acc = 0.f;
+    if (lane == 0) acc = squared_l2_norm_strided(sq, (uint32_t)D);
+    qn = __shfl_sync(0xFFFFFFFFu, acc, 0);
   }
   // chunk minima of the approximate distance: -max(S) (dot product), -max(2 S - ||c||^2) + ||q||^2 (squared L2)
   const float* cmr = cmax_ws + (size_t)qi * Lc;

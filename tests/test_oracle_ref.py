@@ -263,3 +263,62 @@ def test_bfloat16_reordering_distances_equal_the_reference_kernel(D, distance):
     got = oi.exact_distances(q, np.arange(n, dtype=np.uint32))
     want = ref.one_to_many_bf16_float(q, a.bf16_dataset, squared_l2=distance == "squared_l2")
     np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+# ---- the symmetric float one-to-many kernel (ref_glue_sym.cc): exact f32 reordering, LUT build for dims >= 8 --------
+
+needs_sym = pytest.mark.skipif(not (ref.available() and ref.has_symmetric()),
+                               reason="oracle/_ref/libscann_ref.so without the symmetric float kernel")
+
+
+@needs_sym
+@pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
+@pytest.mark.parametrize("D", [8, 9, 10, 11, 12, 13, 14, 15, 16, 24, 50, 64, 96, 100, 101, 102, 103, 128, 768])
+def test_f32_reordering_distances_equal_the_reference_kernel(D, distance):
+  """ExactReorderingHelper (utils/reordering_helper.cc) -> DenseDotProductDistanceOneToMany / DenseSquaredL2Distance
+  OneToMany -> DenseAccumulatingDistanceMeasureOneToManyInternalAvx2 (one_to_many_symmetric.h:373-503): the oracle's
+  exact f32 reordering distance against the reference's compiled kernel, every tail of the dimension loop (8-wide,
+  4-wide, 2-wide, the last scalar dim).  3 m rows: the last n mod 3 rows of a call take a one-to-one kernel whose place
+  in a candidate list is unspecified (see the oracle)."""
+  import oracle
+  from scann_b200 import index_build
+  rng = np.random.default_rng(D + 7)
+  n = 300
+  db = (rng.standard_normal((n, D)) * rng.uniform(0.1, 4.0, D)[None, :]).astype(np.float32)
+  a = index_build.IndexArrays(distance=distance, dataset=db, n=n, d=D)
+  B = min(D, 64)
+  dims = np.full(B, D // B, np.int32)
+  dims[:D % B] += 1
+  a.centers = db[:4].copy()
+  a.tokens = (np.arange(n) % 4).astype(np.int32)
+  a.codes = rng.integers(0, 16, (n, B), dtype=np.uint8)
+  a.codebook = rng.standard_normal((B, 16, int(dims.max()))).astype(np.float32)
+  a.block_dims = dims
+  a.soar, a.soar_codes, a.overretrieve, a.residual = False, None, 2.0, distance == "dot_product"
+  oi = oracle.OracleIndex(a, 2, 30, 10)
+  for qi in range(5):
+    q = rng.standard_normal(D).astype(np.float32)
+    got = oi.exact_distances(q, np.arange(n, dtype=np.uint32))
+    want = ref.one_to_many_f32(q, db, squared_l2=distance == "squared_l2")
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@needs_sym
+def test_squared_l2_norm_equals_the_reference_reduction():
+  """SquaredL2Norm = DenseSingleAccumulate(v, Square()) (utils/reduction.h:357-390): what dp_norms.npy holds, the query
+  norm of squared-L2 tokenization (many_to_many_impl.inc:417-426) and the centre norms of int8 tokenization.  The numpy
+  restatement the index build uses and, through the squared-L2 tokenization distances, the oracle's C restatement."""
+  import oracle
+  from helpers import i8_tok_arrays
+  from scann_b200 import index_build
+  rng = np.random.default_rng(3)
+  for D in [1, 2, 3, 4, 5, 6, 7, 8, 9, 30, 96, 100, 101, 102, 103, 768]:
+    x = (rng.standard_normal((40, D)) * 10.0 ** rng.integers(-3, 4, (40, 1))).astype(np.float32)
+    want = np.asarray([np.float32(ref.squared_l2_norm(r)) for r in x], np.float32)
+    np.testing.assert_array_equal(index_build.squared_l2_norms(x).view(np.uint32), want.view(np.uint32))
+  # the oracle's own C restatement, observed through so_quantize_centers' squared norms
+  for L, D in [(33, 17), (50, 100), (9, 7)]:
+    a, _ = i8_tok_arrays(L, D, "squared_l2", seed=D)
+    _, _, sqn = oracle.quantize_centers(a.centers)
+    want = np.asarray([np.float32(ref.squared_l2_norm(r)) for r in a.centers], np.float32)
+    np.testing.assert_array_equal(sqn.view(np.uint32), want.view(np.uint32))
