@@ -117,6 +117,43 @@ __device__ __forceinline__ float sql2_asym_order(LoadQ q, LoadX x, uint32_t n) {
   return r;
 }
 
+// -<q', float(c)> for one int8 row in the order of the reference's ONE-TO-ONE kernel, DenseDotProductInt8FloatAvxImpl
+// (distance_measures/one_to_one/dot_product_impl.inc:3-54; the last n mod 3 rows of an asymmetric one-to-many call):
+// two 8-lane fmadd accumulators over whole groups of 16 dims, one 8-wide fmadd step into the first, one 4-wide step as
+// a rounded product ADDED to lanes 0..3 of the first, Sum8(acc0 + acc1) = ((x0+x4)+(x2+x6)) + ((x1+x5)+(x3+x7)), the
+// last < 4 dims fused on the scalar; negated at the end.
+template <typename LoadQ>
+__device__ __forceinline__ float neg_dot_i8_one_to_one(LoadQ q, const int8_t* __restrict__ x, uint32_t n) {
+  float a0[8], a1[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) a0[l] = a1[l] = 0.f;
+  uint32_t j = 0;
+  for (; j + 16 <= n; j += 16) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) {
+      a0[l] = __fmaf_rn((float)x[j + l], q(j + l), a0[l]);
+      a1[l] = __fmaf_rn((float)x[j + 8 + l], q(j + 8 + l), a1[l]);
+    }
+  }
+  if (j + 8 <= n) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a0[l] = __fmaf_rn((float)x[j + l], q(j + l), a0[l]);
+    j += 8;
+  }
+  if (j + 4 <= n) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) a0[l] = __fadd_rn(a0[l], __fmul_rn((float)x[j + l], q(j + l)));
+    j += 4;
+  }
+  float v[8];
+#pragma unroll
+  for (int l = 0; l < 8; ++l) v[l] = __fadd_rn(a0[l], a1[l]);
+  float s = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[4]), __fadd_rn(v[2], v[6])),
+                      __fadd_rn(__fadd_rn(v[1], v[5]), __fadd_rn(v[3], v[7])));
+  for (; j < n; ++j) s = __fmaf_rn((float)x[j], q(j), s);
+  return -s;
+}
+
 // SquaredL2DistanceLambdas::FmaTerm (one_to_many_symmetric.h:1043-1051).
 template <typename LoadQ, typename LoadX>
 __device__ __forceinline__ float sql2_avx2_order(LoadQ q, LoadX x, uint32_t n) {

@@ -352,9 +352,13 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     std::vector<int8_t> ci8((size_t)L * D);
     for (uint32_t l = 0; l < L; ++l)
       for (uint32_t k = 0; k < D; ++k) mult[k] = std::max(mult[k], std::fabs(d->centers[(size_t)l * D + k]));
+    const bool l2 = d->distance == SCANN_B200_SQUARED_L2;
     for (uint32_t k = 0; k < D; ++k) {
       mult[k] = mult[k] == 0.0f ? 1.0f : 127.0f / mult[k];
       inv[k] = 1.0f / mult[k];
+      // GetAllDistancesInt8 scales the query by inv_mult, `inv_mult * 2` for squared L2 (kmeans_tree_node.h:239-244);
+      // the doubling is exact, so the kernels read the ready-made scale
+      if (l2) inv[k] = inv[k] * 2.0f;
     }
     for (uint32_t l = 0; l < L; ++l) {
       const float* c = d->centers + (size_t)l * D;
@@ -387,8 +391,31 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     CU(ix->cen_sqn.ensure(sizeof(float) * L));
     CU(cudaMemcpy(ix->cen_sqn.p, sqn.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
     v.centers_i8 = ix->cen_i8.as<int8_t>();
-    v.cen_inv_mult = ix->cen_inv.as<float>();
+    v.cen_qscale = ix->cen_inv.as<float>();
     v.cen_sqnorm = ix->cen_sqn.as<float>();
+    // tensor-core pre-filter of the int8 tokenization (prep.cu): an int8 value is exact in bf16, so the centre operand
+    // is [c | c | 0] and the only dropped term of the split GEMM is the query's third bf16 term
+    {
+      std::vector<float> cf(ci8.size());
+      double m2 = 0.0, s2 = 0.0;
+      for (uint32_t l = 0; l < L; ++l) {
+        double a = 0.0;
+        for (uint32_t k = 0; k < D; ++k) {
+          const float f = (float)ci8[(size_t)l * D + k];
+          cf[(size_t)l * D + k] = f;
+          a += (double)f * (double)f;
+        }
+        m2 = std::max(m2, a);
+        s2 = std::max(s2, (double)sqn[l]);
+      }
+      v.cen_i8_max_norm = (float)(std::sqrt(m2) * 1.0001);
+      v.cen_sqnorm_max = (float)(s2 * 1.0001);
+      sbi::DevBuf tmp;
+      CU(tmp.ensure(sizeof(float) * std::max<size_t>(cf.size(), 4)));
+      CU(cudaMemcpy(tmp.p, cf.data(), sizeof(float) * cf.size(), cudaMemcpyHostToDevice));
+      CU(sb::build_tokenize_operand(tmp.as<float>(), L, D, 2, ix->tok_b.p, 0));
+      CU(cudaStreamSynchronize(0));
+    }
   }
   v.centers_t = nullptr;
   v.center_sqnorm = ix->cnorm.as<float>();

@@ -41,8 +41,10 @@ struct DevIndex {
   // int8 (fixed point) query tokenization (query_tokenization_type FIXED_POINT_INT8, prep.cu tokenize_i8_kernel):
   // non-NULL centers_i8 switches launch_tokenize / launch_tokenize_topp to it
   const int8_t* centers_i8;   // [L][D] ScalarQuantizeFloatDataset(centres, 1.0, NaN)
-  const float* cen_inv_mult;  // [D] 1.0f / multiplier_by_dimension
+  const float* cen_qscale;    // [D] query scale: 1.0f / multiplier_by_dimension, times 2 for squared L2
   const float* cen_sqnorm;    // [L] float(SquaredL2Norm(float centre)) (squared L2 only)
+  float cen_i8_max_norm;      // >= max_l ||float(int8 centre l)|| (error term of the tensor-core pre-filter)
+  float cen_sqnorm_max;       // >= max_l cen_sqnorm[l]
   // tensor-core tokenization (prep.cu): centres as the bf16 operand [L][tok_kp] = [hi | hi | lo | 0]
   const void* tok_b;
   uint32_t tok_kp;
@@ -111,7 +113,10 @@ void launch_lut(const DevIndex& ix, const float* q, uint32_t nq, uint8_t* lut, f
 // centre operand (tokenize_tensor_path), else the SIMT pair above.  `a_ws` holds tokenize_operand_bytes(nq, d).
 uint32_t tokenize_kpitch(uint32_t d);
 size_t tokenize_operand_bytes(uint32_t rows, uint32_t d);
-cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, int lo_term, void* out, cudaStream_t s);
+// scale (optional, [d]): rows are multiplied by it (one fp32 rounding) before the split -- the scaled queries of int8
+// tokenization
+cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, int lo_term, void* out, cudaStream_t s,
+                                   const float* scale = nullptr);
 bool tokenize_tensor_path(const DevIndex& ix, uint32_t P);
 cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq, uint32_t P, float* dist, void* a_ws,
                                  int32_t* leaves, float* bias, uint32_t* fallbacks, cudaStream_t s, int* launches);

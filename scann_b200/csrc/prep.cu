@@ -108,12 +108,12 @@ tokenize_kernel(const float* __restrict__ q, const float* __restrict__ c,
 // ---------------------------------------------------------------------------------------
 constexpr int I8M = 64, I8N = 32, I8K = 16, I8PAD = 4;
 
-__device__ __forceinline__ float i8_scaled_query(float q, float inv, int sql2) {
-  return __fmul_rn(q, sql2 ? __fmul_rn(inv, 2.0f) : inv);
-}
+// q'[k] = q[k] * scale[k], scale = inv_mult (dot product) or inv_mult * 2 (squared L2: `q *= inv_mult * 2`,
+// kmeans_tree_node.h:239-241); the index stores the scale (DevIndex::cen_qscale)
+__device__ __forceinline__ float i8_scaled_query(float q, float scale) { return __fmul_rn(q, scale); }
 
 __global__ void __launch_bounds__(256)
-tokenize_i8_kernel(const float* __restrict__ q, const float* __restrict__ inv_mult, const int8_t* __restrict__ c,
+tokenize_i8_kernel(const float* __restrict__ q, const float* __restrict__ qscale, const int8_t* __restrict__ c,
                    const float* __restrict__ csq, float* __restrict__ out, int nq, int L, int D, int sql2) {
   __shared__ __align__(16) float As[I8K][I8M + I8PAD];  // -q'
   __shared__ __align__(16) float Bs[I8K][I8N + I8PAD];  // float(centre)
@@ -140,7 +140,7 @@ tokenize_i8_kernel(const float* __restrict__ q, const float* __restrict__ inv_mu
       const int idx = tid + i * 256;
       const int row = idx >> 4, kk = idx & 15;
       const int gr = m0 + row, gk = k0 + kk;
-      As[kk][row] = (gr < nq && gk < klim) ? -i8_scaled_query(q[(size_t)gr * D + gk], inv_mult[gk], sql2) : 0.f;
+      As[kk][row] = (gr < nq && gk < klim) ? -i8_scaled_query(q[(size_t)gr * D + gk], qscale[gk]) : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -209,43 +209,15 @@ tokenize_i8_kernel(const float* __restrict__ q, const float* __restrict__ inv_mu
 // 0..3 of the first, Sum8(acc0 + acc1) = ((x0+x4)+(x2+x6)) + ((x1+x5)+(x3+x7)), the last < 4 dims fused on the scalar.
 // One thread per (query, tail centre).
 __global__ void __launch_bounds__(128)
-tokenize_i8_tail_kernel(const float* __restrict__ q, const float* __restrict__ inv_mult, const int8_t* __restrict__ c,
+tokenize_i8_tail_kernel(const float* __restrict__ q, const float* __restrict__ qscale, const int8_t* __restrict__ c,
                         const float* __restrict__ csq, float* __restrict__ out, int nq, int L, int D, int sql2, int L3) {
   const int nt = L - L3;
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= nq * nt) return;
   const int r = g / nt, col = L3 + g % nt;
   const float* qr = q + (size_t)r * D;
-  const int8_t* x = c + (size_t)col * D;
-  auto qp = [&](int k) { return i8_scaled_query(qr[k], inv_mult[k], sql2); };
-  float a0[8], a1[8];
-#pragma unroll
-  for (int l = 0; l < 8; ++l) a0[l] = a1[l] = 0.f;
-  int j = 0;
-  for (; j + 16 <= D; j += 16) {
-#pragma unroll
-    for (int l = 0; l < 8; ++l) {
-      a0[l] = __fmaf_rn((float)x[j + l], qp(j + l), a0[l]);
-      a1[l] = __fmaf_rn((float)x[j + 8 + l], qp(j + 8 + l), a1[l]);
-    }
-  }
-  if (j + 8 <= D) {
-#pragma unroll
-    for (int l = 0; l < 8; ++l) a0[l] = __fmaf_rn((float)x[j + l], qp(j + l), a0[l]);
-    j += 8;
-  }
-  if (j + 4 <= D) {
-#pragma unroll
-    for (int l = 0; l < 4; ++l) a0[l] = __fadd_rn(a0[l], __fmul_rn((float)x[j + l], qp(j + l)));
-    j += 4;
-  }
-  float v[8];
-#pragma unroll
-  for (int l = 0; l < 8; ++l) v[l] = __fadd_rn(a0[l], a1[l]);
-  float s = __fadd_rn(__fadd_rn(__fadd_rn(v[0], v[4]), __fadd_rn(v[2], v[6])),
-                      __fadd_rn(__fadd_rn(v[1], v[5]), __fadd_rn(v[3], v[7])));
-  for (; j < D; ++j) s = __fmaf_rn((float)x[j], qp(j), s);
-  const float val = -s;
+  auto qp = [&](uint32_t k) { return i8_scaled_query(qr[k], qscale[k]); };
+  const float val = neg_dot_i8_one_to_one(qp, c + (size_t)col * D, (uint32_t)D);
   out[(size_t)r * L + col] = sql2 ? __fadd_rn(val, __fadd_rn(squared_l2_norm_strided(qr, (uint32_t)D), csq[col])) : val;
 }
 
@@ -253,11 +225,11 @@ void launch_tokenize(const DevIndex& ix, const float* q, uint32_t nq, float* dis
   if (ix.centers_i8) {
     const int sql2 = ix.distance == 1;
     dim3 grid((ix.L + I8N - 1) / I8N, (nq + I8M - 1) / I8M);
-    tokenize_i8_kernel<<<grid, 256, 0, s>>>(q, ix.cen_inv_mult, ix.centers_i8, ix.cen_sqnorm, dist, (int)nq, (int)ix.L,
+    tokenize_i8_kernel<<<grid, 256, 0, s>>>(q, ix.cen_qscale, ix.centers_i8, ix.cen_sqnorm, dist, (int)nq, (int)ix.L,
                                             (int)ix.d, sql2);
     const int L3 = (int)(ix.L / 3 * 3), nt = (int)ix.L - L3;
     if (nt)
-      tokenize_i8_tail_kernel<<<((int)nq * nt + 127) / 128, 128, 0, s>>>(q, ix.cen_inv_mult, ix.centers_i8, ix.cen_sqnorm,
+      tokenize_i8_tail_kernel<<<((int)nq * nt + 127) / 128, 128, 0, s>>>(q, ix.cen_qscale, ix.centers_i8, ix.cen_sqnorm,
                                                                          dist, (int)nq, (int)ix.L, (int)ix.d, sql2, L3);
     return;
   }
@@ -498,11 +470,12 @@ void launch_topp(const DevIndex& ix, const float* dist, uint32_t nq, uint32_t P,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 split_rows_kernel(const float* __restrict__ src, uint32_t rows, uint32_t d, uint32_t kp, int lo_term,
-                  __nv_bfloat16* __restrict__ out) {
+                  __nv_bfloat16* __restrict__ out, const float* __restrict__ scale) {
   const uint32_t r = blockIdx.x;
   __nv_bfloat16* o = out + (size_t)r * kp;
   for (uint32_t k = threadIdx.x; k < d; k += 128) {
-    const float x = r < rows ? src[(size_t)r * d + k] : 0.f;
+    float x = r < rows ? src[(size_t)r * d + k] : 0.f;
+    if (scale) x = __fmul_rn(x, scale[k]);  // int8 tokenization: the scaled query q' (the same rounding as the exact chain's)
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
     const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
     o[k] = hi;
@@ -516,9 +489,10 @@ uint32_t tokenize_kpitch(uint32_t d) { return (3 * d + 63) / 64 * 64; }
 size_t tokenize_operand_bytes(uint32_t rows, uint32_t d) {
   return (size_t)((rows + 127) / 128 * 128) * tokenize_kpitch(d) * 2;
 }
-cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, int lo_term, void* out, cudaStream_t s) {
+cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, int lo_term, void* out, cudaStream_t s,
+                                   const float* scale) {
   const uint32_t kp = tokenize_kpitch(d), rows_pad = (rows + 127) / 128 * 128;
-  split_rows_kernel<<<rows_pad, 128, 0, s>>>(src, rows, d, kp, lo_term, reinterpret_cast<__nv_bfloat16*>(out));
+  split_rows_kernel<<<rows_pad, 128, 0, s>>>(src, rows, d, kp, lo_term, reinterpret_cast<__nv_bfloat16*>(out), scale);
   return cudaGetLastError();
 }
 
@@ -550,6 +524,9 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   const int qi = blockIdx.x;
   const int L = (int)ix.L, D = (int)ix.d, Dp = (D + 3) & ~3;
   const bool sql2 = ix.distance == 1;
+  // int8 tokenization (see tokenize_i8_kernel): S = <q', float(int8 centre)>, the exact function is the int8 chain
+  const bool i8 = ix.centers_i8 != nullptr;
+  const float* __restrict__ cnp = i8 ? ix.cen_sqnorm : ix.center_sqnorm;
   const int Lp = (L + 4 * kRefineThreads - 1) / (4 * kRefineThreads) * (4 * kRefineThreads);  // whole LDS.128 iterations of the block
   uint64_t* skeys = reinterpret_cast<uint64_t*>(smem_raw);
   float* sq = reinterpret_cast<float*>(smem_raw + (size_t)Cp * 8);
@@ -558,7 +535,8 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
 
   float ssq = 0.f;
   for (int k = tid; k < D; k += kRefineThreads) {
-    const float v = q[(size_t)qi * D + k];
+    float v = q[(size_t)qi * D + k];
+    if (i8) v = __fmul_rn(v, ix.cen_qscale[k]);  // q' (sq holds the scaled query; ||q||^2 below reads the raw one)
     sq[k] = v;
     ssq = fmaf(v, v, ssq);
   }
@@ -571,23 +549,26 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   for (int i = 0; i < kWarps; ++i) ssq += red_a[i];
   float qn = 0.f;
   if (sql2) {  // ||q||^2 exactly as tokenize_kernel: float(SquaredL2Norm(q))
-    if (tid == 0) red_b[0] = squared_l2_norm_strided(sq, (uint32_t)D);
+    if (tid == 0) red_b[0] = squared_l2_norm_strided(i8 ? q + (size_t)qi * D : sq, (uint32_t)D);
     __syncthreads();
     qn = red_b[0];
   }
   __syncthreads();
-  const float qnorm = sqrtf(ssq) * 1.001f, cmax = ix.center_max_norm;
+  const float qnorm = sqrtf(ssq) * 1.001f, cmax = i8 ? ix.cen_i8_max_norm : ix.center_max_norm;
   float eps = eps_rel * qnorm * cmax;
-  if (sql2) eps = 2.f * eps + (float)(D + 8) * 1.1920929e-7f * (qn + cmax * cmax + 2.f * qnorm * cmax);
+  if (sql2 && !i8) eps = 2.f * eps + (float)(D + 8) * 1.1920929e-7f * (qn + cmax * cmax + 2.f * qnorm * cmax);
+  // int8, squared L2: approx = (cn + qn) - S and exact = val + (qn + cn) share the rounded (qn + cn); what differs is
+  // S against -val (eps: q' carries the factor 2 already) and the two final roundings, each <= 2^-24 of the sum
+  if (sql2 && i8) eps = eps + 8.f * 1.1920929e-7f * (qn + ix.cen_sqnorm_max + qnorm * cmax);
   auto approx = [&](float sdot, float cn) -> float {
-    return sql2 ? __fsub_rn(__fadd_rn(cn, qn), __fmul_rn(2.f, sdot)) : -sdot;
+    return sql2 ? __fsub_rn(__fadd_rn(cn, qn), i8 ? sdot : __fmul_rn(2.f, sdot)) : -sdot;
   };
 
   // ---- pass A: approximate distances (to shared memory), their min and max ----
   float amin = __int_as_float(0x7F800000), amax = __int_as_float(0xFF800000);
   if constexpr (kSmemRow) {
     const float4* row4 = reinterpret_cast<const float4*>(row);
-    const float4* cn4 = reinterpret_cast<const float4*>(ix.center_sqnorm);
+    const float4* cn4 = reinterpret_cast<const float4*>(cnp);
 #pragma unroll 4
     for (int i4 = tid; i4 < (Lp >> 2); i4 += kRefineThreads) {
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -604,7 +585,7 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   } else {
 #pragma unroll 4
     for (int i = tid; i < L; i += kRefineThreads) {
-      const float a = approx(row[i], sql2 ? ix.center_sqnorm[i] : 0.f);
+      const float a = approx(row[i], sql2 ? cnp[i] : 0.f);
       amin = fminf(amin, a);
       amax = fmaxf(amax, a);
     }
@@ -635,7 +616,7 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
     } else {
       for (int t0 = 0; t0 < L; t0 += kRefineThreads) {
         const int i = t0 + tid;
-        fn(i, i < L ? ufn(approx(row[i], sql2 ? ix.center_sqnorm[i] : 0.f)) : 0xFFFFFFFFu);
+        fn(i, i < L ? ufn(approx(row[i], sql2 ? cnp[i] : 0.f)) : 0xFFFFFFFFu);
       }
     }
   };
@@ -718,8 +699,44 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   __syncthreads();
   const uint32_t count = s_sel[3];
 
+  // int8 tokenization: the reference's int8 chain -- the three-at-a-time order for centres below 3 (L / 3), the
+  // one-to-one order for the last L mod 3 (exact_math.cuh; tokenize_i8_kernel / tokenize_i8_tail_kernel compute the same)
+  const int L3 = L / 3 * 3;
+  auto lsq = [&](uint32_t k) { return sq[k]; };
+  auto exact_i8 = [&](int idx) -> float {
+    const int8_t* __restrict__ c = ix.centers_i8 + (size_t)idx * D;
+    float val;
+    if (idx >= L3) {
+      val = neg_dot_i8_one_to_one(lsq, c, (uint32_t)D);
+    } else if ((D & 3) == 0) {
+      // rows are 4-byte aligned: one 32-bit load per four dims (the lanes and their order are neg_dot_asym_order's)
+      const uint32_t* __restrict__ cw = reinterpret_cast<const uint32_t*>(c);
+      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int j = 0;
+      for (; j + 8 <= D; j += 8) {
+        const uint32_t w0 = __ldg(cw + (j >> 2)), w1 = __ldg(cw + (j >> 2) + 1);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          a[l] = __fmaf_rn(-sq[j + l], (float)(int8_t)(w0 >> (8 * l)), a[l]);
+          a[l + 4] = __fmaf_rn(-sq[j + 4 + l], (float)(int8_t)(w1 >> (8 * l)), a[l + 4]);
+        }
+      }
+      if (j + 4 <= D) {
+        const uint32_t w0 = __ldg(cw + (j >> 2));
+#pragma unroll
+        for (int l = 0; l < 4; ++l) a[l] = __fmaf_rn(-sq[j + l], (float)(int8_t)(w0 >> (8 * l)), a[l]);
+      }
+      val = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])),
+                      __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
+    } else {
+      auto lc = [&](uint32_t k) { return (float)c[k]; };
+      val = neg_dot_asym_order(lsq, lc, (uint32_t)D);
+    }
+    return sql2 ? __fadd_rn(val, __fadd_rn(qn, cnp[idx])) : val;
+  };
   // the reference's exact fp32 chain for one centre (scalar loads: fallback and D % 4 != 0)
   auto exact = [&](int idx) -> float {
+    if (i8) return exact_i8(idx);
     const float* c = ix.centers + (size_t)idx * D;
     float acc = sql2 ? __fadd_rn(ix.center_sqnorm[idx], qn) : 0.f;
     const float scale2 = sql2 ? 2.0f : 1.0f;
@@ -765,7 +782,7 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
       const bool live = (uint32_t)j < count;
       const uint32_t idx = live ? (uint32_t)skeys[j] : 0u;
       float e = 0.f;
-      if (live) e = (D & 3) == 0 ? exact_v4((int)idx) : exact((int)idx);
+      if (live) e = ((D & 3) == 0 && !i8) ? exact_v4((int)idx) : exact((int)idx);
       if (j < ns) skeys[j] = live ? (((uint64_t)f2ord(e) << 32) | idx) : kKeyMax;
     }
     __syncthreads();
@@ -812,7 +829,12 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
     for (int i = tid; i < P; i += kRefineThreads) {
       const uint64_t k = i < max(ns, 128) && i < Cp ? skeys[i] : kKeyMax;
       lout[i] = (k == kKeyMax) ? -1 : (int32_t)(uint32_t)k;
-      bout[i] = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
+      float bv = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
+      // the key's order-preserving image folds -0.0 into +0.0.  The only zero with a sign: the one-to-one kernel of
+      // the last L mod 3 int8 centres returns -(+0.0) for a zero dot product (its sums start at +0.0, so they never end
+      // at -0.0); the three-at-a-time kernel and every squared-L2 distance end at +0.0
+      if (i8 && !sql2 && bv == 0.f && k != kKeyMax && (int)(uint32_t)k >= L3) bv = -0.0f;
+      bout[i] = bv;
     }
   } else {
     if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1u);
@@ -1115,7 +1137,8 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
 }
 
 bool tokenize_tensor_path(const DevIndex& ix, uint32_t P) {
-  if (ix.centers_i8) return false;  // int8 tokenization: its own exact SIMT kernels (launch_tokenize)
+  // int8 tokenization takes the same route (the centre operand then holds the int8 centres, exact in bf16): tcgen05
+  // pre-filter + radix refinement with the int8 chain, or the exact SIMT kernels (launch_tokenize)
   if (!ix.tok_b || P + 32 > (uint32_t)kRefineMaxCand || ix.d > 2048) return false;
   const char* e = getenv("SCANN_B200_TOKENIZE");
   if (e && !strcmp(e, "simt")) return false;
@@ -1131,12 +1154,13 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
     if (launches) *launches += (ix.centers_i8 && ix.L % 3) ? 3 : 2;
     return cudaGetLastError();
   }
-  cudaError_t e = build_tokenize_operand(q, nq, ix.d, 1, a_ws, s);
+  const bool i8 = ix.centers_i8 != nullptr;
+  cudaError_t e = build_tokenize_operand(q, nq, ix.d, 1, a_ws, s, i8 ? ix.cen_qscale : nullptr);
   if (e != cudaSuccess) return e;
   // chunk pre-selection: P <= 128, at least 2 P chunks; default from 4096 centres
   // (SCANN_B200_TOKENIZE=chunk forces it where it applies, =tcgen05 the radix refinement)
   const uint32_t n_chunks = (ix.L + 31) / 32;
-  bool chunked = ix.tok_cmax_ws && P <= 128 && n_chunks >= 2 * P && n_chunks <= (uint32_t)kChunkMaxChunks;
+  bool chunked = !i8 && ix.tok_cmax_ws && P <= 128 && n_chunks >= 2 * P && n_chunks <= (uint32_t)kChunkMaxChunks;
   {
     const char* env = getenv("SCANN_B200_TOKENIZE");
     if (env && (!strcmp(env, "tcgen05") || !strcmp(env, "stream"))) chunked = false;
@@ -1150,7 +1174,7 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   bool store_rows = true;
   if (const char* env = getenv("SCANN_B200_TOKENIZE_ROWS")) store_rows = !(env[0] == '0' && chunked && ix.tok_need_rows == 0);
   e = gemm_bf16_nt(a_ws, nq, (nq + 127) / 128 * 128, ix.tok_b, ix.L, ix.tok_kp, store_rows ? dist : nullptr, ix.L, s,
-                   chunked ? ix.tok_cmax_ws : nullptr, n_chunks, ix.distance == 1 ? ix.center_sqnorm : nullptr);
+                   chunked ? ix.tok_cmax_ws : nullptr, n_chunks, (ix.distance == 1 && !i8) ? ix.center_sqnorm : nullptr);
   if (e != cudaSuccess) return e;
   if (chunked) {
     int sp = 2;
@@ -1175,7 +1199,7 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
     const char* env = getenv("SCANN_B200_TOKENIZE");
     const bool force_stream = env && !strcmp(env, "stream"), force_radix = env && !strcmp(env, "tcgen05");
     (void)force_radix;
-    if (P <= 128 && force_stream) {  // measured slower than the radix refinement (see the kernel's comment): opt-in only
+    if (P <= 128 && force_stream && !i8) {  // measured slower than the radix refinement (see the kernel's comment): opt-in only
       int sp = 2;
       while (sp < (int)P) sp <<= 1;
       const size_t per_warp = (size_t)kStreamCand * 8 + 1024 + (size_t)((ix.d + 3) & ~3u) * 4;

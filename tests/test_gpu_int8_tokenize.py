@@ -33,12 +33,62 @@ def test_int8_tokenization_full_rows_bit_exact(L, D, distance):
   ni.close()
 
 
+# Both routes of the library: the exact SIMT kernels, and the tcgen05 pre-filter (the int8 centres as an exact bf16
+# operand) + radix refinement with the int8 chain -- the default from 256 centres.  L = 700: row image in shared
+# memory, 128 threads per query; 335: L % 4 != 0, no staged row; 4100: 256 threads; 2000 x 100: the C2 shape.  The zero
+# query has every approximate distance equal: more candidates than the buffer, the exact all-centres fallback.
+@pytest.mark.parametrize("route", ["simt", "tcgen05"])
+@pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
+@pytest.mark.parametrize("L,D", [(700, 96), (335, 50), (4100, 33), (2000, 100), (301, 128), (1000, 7)])
+def test_int8_tokenization_routes_bit_exact(L, D, distance, route, monkeypatch):
+  import oracle
+  from scann_b200 import _lib
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", route)
+  a, q = i8_tok_arrays(L, D, distance, seed=L * 1000 + D)
+  rng = np.random.default_rng(6)
+  q = np.concatenate([q, rng.standard_normal((150, D)).astype(np.float32) * rng.uniform(0.01, 30.0, (150, 1)).astype(np.float32),
+                      np.zeros((1, D), np.float32), a.centers[:5], -a.centers[5:8]])
+  oi = oracle.OracleIndex(a, 10, 10, 5)
+  ni = _lib.NativeIndex(a, 10, 10, 5)
+  for P in (1, 10, 100, 250):
+    l0, d0 = oi.tokenize(q, leaves=P)
+    l1, d1 = ni.tokenize(q, leaves=P)
+    np.testing.assert_array_equal(l0, l1)
+    np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+  ni.close()
+
+
+def test_int8_tokenization_near_ties_and_duplicate_centres(monkeypatch):
+  """Centres that quantize to the same int8 row (exact ties, broken by index) and centres a hair apart: the window of
+  the pre-filter must keep every one of them for the exact chain to order."""
+  import oracle
+  from scann_b200 import _lib
+  monkeypatch.setenv("SCANN_B200_TOKENIZE", "tcgen05")
+  for distance in ("dot_product", "squared_l2"):
+    a, q = i8_tok_arrays(600, 64, distance, seed=77)
+    rng = np.random.default_rng(8)
+    a.centers[300:400] = a.centers[:100]                                     # exact duplicates
+    a.centers[400:500] = a.centers[100:200] * np.float32(1.0 + 1e-6)        # same int8 row, other float norm
+    a.centers[500:600] = a.centers[200:300] + rng.standard_normal((100, 64)).astype(np.float32) * np.float32(1e-3)
+    q = np.concatenate([q, rng.standard_normal((120, 64)).astype(np.float32)])
+    oi = oracle.OracleIndex(a, 10, 10, 5)
+    ni = _lib.NativeIndex(a, 10, 10, 5)
+    for P in (1, 16, 200):
+      l0, d0 = oi.tokenize(q, leaves=P)
+      l1, d1 = ni.tokenize(q, leaves=P)
+      np.testing.assert_array_equal(l0, l1)
+      np.testing.assert_array_equal(d0.view(np.uint32), d1.view(np.uint32))
+    ni.close()
+
+
 CASES = [
     dict(int8_tok=True),                                                     # C1-like, L = 100 (L mod 3 = 1)
     dict(int8_tok=True, soar=1.5),                                           # SOAR: the leaf bias is the int8 distance
     dict(int8_tok=True, distance="squared_l2", d=64, leaves=50, n=10000),    # L mod 3 = 2, squared L2
     dict(int8_tok=True, n=6000, leaves=300, probe=300, pre=50, d=32),        # every leaf probed
     dict(int8_tok=True, dpb=4, d=96, leaves=64, n=12000),
+    dict(int8_tok=True, n=20000, leaves=400, probe=30, pre=100, soar=1.5),   # >= 256 centres: the tcgen05 route by default
+    dict(int8_tok=True, distance="squared_l2", d=64, leaves=320, n=16000, probe=20),
 ]
 
 
