@@ -393,6 +393,13 @@ int build_index(scann_b200_index* ix, const scann_b200_index_desc* d) {
     v.centers_i8 = ix->cen_i8.as<int8_t>();
     v.cen_qscale = ix->cen_inv.as<float>();
     v.cen_sqnorm = ix->cen_sqn.as<float>();
+    {
+      std::vector<float> sqn2(L);
+      for (uint32_t l = 0; l < L; ++l) sqn2[l] = 2.0f * sqn[l];
+      CU(ix->cen_sqn2.ensure(sizeof(float) * L));
+      CU(cudaMemcpy(ix->cen_sqn2.p, sqn2.data(), sizeof(float) * L, cudaMemcpyHostToDevice));
+      v.cen_sqnorm2 = ix->cen_sqn2.as<float>();
+    }
     // tensor-core pre-filter of the int8 tokenization (prep.cu): an int8 value is exact in bf16, so the centre operand
     // is [c | c | 0] and the only dropped term of the split GEMM is the query's third bf16 term
     {

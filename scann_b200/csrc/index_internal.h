@@ -74,7 +74,7 @@ struct scann_b200_index {
   std::vector<uint32_t> h_leaf_size;
   // persistent device arrays
   sbi::DevBuf i8_inv, i8_norm, tok_cmax, pair_pos;
-  sbi::DevBuf cen_i8, cen_inv, cen_sqn;  // int8 query tokenization: the fixed-point centres (index.cu)
+  sbi::DevBuf cen_i8, cen_inv, cen_sqn, cen_sqn2;  // int8 query tokenization: the fixed-point centres (index.cu)
   sbi::DevBuf centers, cnorm, codebook, block_dims, block_off, leaf_size, leaf_goff, leaf_ntiles, leaf_gpt,
       codes, slot_dp, slot_tie, dataset, dp_row, tok_b;
   // workspace

@@ -43,6 +43,7 @@ struct DevIndex {
   const int8_t* centers_i8;   // [L][D] ScalarQuantizeFloatDataset(centres, 1.0, NaN)
   const float* cen_qscale;    // [D] query scale: 1.0f / multiplier_by_dimension, times 2 for squared L2
   const float* cen_sqnorm;    // [L] float(SquaredL2Norm(float centre)) (squared L2 only)
+  const float* cen_sqnorm2;   // [L] 2 * cen_sqnorm: the bias of the chunk statistic of the tokenization GEMM (prep.cu)
   float cen_i8_max_norm;      // >= max_l ||float(int8 centre l)|| (error term of the tensor-core pre-filter)
   float cen_sqnorm_max;       // >= max_l cen_sqnorm[l]
   // tensor-core tokenization (prep.cu): centres as the bf16 operand [L][tok_kp] = [hi | hi | lo | 0]

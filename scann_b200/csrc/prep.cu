@@ -496,6 +496,44 @@ cudaError_t build_tokenize_operand(const float* src, uint32_t rows, uint32_t d, 
   return cudaGetLastError();
 }
 
+// The exact distance of int8 tokenization for one centre, as the refinement kernels re-score it: `sq` = the scaled
+// query q' (shared memory), the reference's three-at-a-time order for centres below L3 = 3 (L / 3), its one-to-one order
+// for the last L mod 3 (exact_math.cuh; tokenize_i8_kernel / tokenize_i8_tail_kernel compute the same bits);
+// squared L2: val + (|q|^2 + |float centre|^2).
+__device__ __forceinline__ float i8_center_distance(const DevIndex& ix, const float* __restrict__ sq, int idx, int D, int L3,
+                                                    bool sql2, float qn) {
+  const int8_t* __restrict__ c = ix.centers_i8 + (size_t)idx * D;
+  auto lsq = [&](uint32_t k) { return sq[k]; };
+  float val;
+  if (idx >= L3) {
+    val = neg_dot_i8_one_to_one(lsq, c, (uint32_t)D);
+  } else if ((D & 3) == 0) {
+    // rows are 4-byte aligned: one 32-bit load per four dims (the lanes and their order are neg_dot_asym_order's)
+    const uint32_t* __restrict__ cw = reinterpret_cast<const uint32_t*>(c);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int j = 0;
+    for (; j + 8 <= D; j += 8) {
+      const uint32_t w0 = __ldg(cw + (j >> 2)), w1 = __ldg(cw + (j >> 2) + 1);
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        a[l] = __fmaf_rn(-sq[j + l], (float)(int8_t)(w0 >> (8 * l)), a[l]);
+        a[l + 4] = __fmaf_rn(-sq[j + 4 + l], (float)(int8_t)(w1 >> (8 * l)), a[l + 4]);
+      }
+    }
+    if (j + 4 <= D) {
+      const uint32_t w0 = __ldg(cw + (j >> 2));
+#pragma unroll
+      for (int l = 0; l < 4; ++l) a[l] = __fmaf_rn(-sq[j + l], (float)(int8_t)(w0 >> (8 * l)), a[l]);
+    }
+    val = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])),
+                    __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
+  } else {
+    auto lc = [&](uint32_t k) { return (float)c[k]; };
+    val = neg_dot_asym_order(lsq, lc, (uint32_t)D);
+  }
+  return sql2 ? __fadd_rn(val, __fadd_rn(qn, ix.cen_sqnorm[idx])) : val;
+}
+
 constexpr int kRefineMaxCand = 512;
 
 // One 128-thread CTA per query.  The row of approximate distances is mapped to a fixed-point image
@@ -702,38 +740,7 @@ topp_refine_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__
   // int8 tokenization: the reference's int8 chain -- the three-at-a-time order for centres below 3 (L / 3), the
   // one-to-one order for the last L mod 3 (exact_math.cuh; tokenize_i8_kernel / tokenize_i8_tail_kernel compute the same)
   const int L3 = L / 3 * 3;
-  auto lsq = [&](uint32_t k) { return sq[k]; };
-  auto exact_i8 = [&](int idx) -> float {
-    const int8_t* __restrict__ c = ix.centers_i8 + (size_t)idx * D;
-    float val;
-    if (idx >= L3) {
-      val = neg_dot_i8_one_to_one(lsq, c, (uint32_t)D);
-    } else if ((D & 3) == 0) {
-      // rows are 4-byte aligned: one 32-bit load per four dims (the lanes and their order are neg_dot_asym_order's)
-      const uint32_t* __restrict__ cw = reinterpret_cast<const uint32_t*>(c);
-      float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      int j = 0;
-      for (; j + 8 <= D; j += 8) {
-        const uint32_t w0 = __ldg(cw + (j >> 2)), w1 = __ldg(cw + (j >> 2) + 1);
-#pragma unroll
-        for (int l = 0; l < 4; ++l) {
-          a[l] = __fmaf_rn(-sq[j + l], (float)(int8_t)(w0 >> (8 * l)), a[l]);
-          a[l + 4] = __fmaf_rn(-sq[j + 4 + l], (float)(int8_t)(w1 >> (8 * l)), a[l + 4]);
-        }
-      }
-      if (j + 4 <= D) {
-        const uint32_t w0 = __ldg(cw + (j >> 2));
-#pragma unroll
-        for (int l = 0; l < 4; ++l) a[l] = __fmaf_rn(-sq[j + l], (float)(int8_t)(w0 >> (8 * l)), a[l]);
-      }
-      val = __fadd_rn(__fadd_rn(__fadd_rn(a[0], a[4]), __fadd_rn(a[2], a[6])),
-                      __fadd_rn(__fadd_rn(a[1], a[5]), __fadd_rn(a[3], a[7])));
-    } else {
-      auto lc = [&](uint32_t k) { return (float)c[k]; };
-      val = neg_dot_asym_order(lsq, lc, (uint32_t)D);
-    }
-    return sql2 ? __fadd_rn(val, __fadd_rn(qn, cnp[idx])) : val;
-  };
+  auto exact_i8 = [&](int idx) -> float { return i8_center_distance(ix, sq, idx, D, L3, sql2, qn); };
   // the reference's exact fp32 chain for one centre (scalar loads: fallback and D % 4 != 0)
   auto exact = [&](int idx) -> float {
     if (i8) return exact_i8(idx);
@@ -1023,9 +1030,12 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
   const uint32_t lt = (1u << lane) - 1u;
 
   const bool sql2 = ix.distance == 1;
+  const bool i8 = ix.centers_i8 != nullptr;  // int8 tokenization: S = <q', float(int8 centre)>, see topp_refine_kernel
+  const int L3 = L / 3 * 3;
   float ssq = 0.f;
   for (int k = lane; k < Dp; k += 32) {
-    const float v = k < D ? q[(size_t)qi * D + k] : 0.f;
+    float v = k < D ? q[(size_t)qi * D + k] : 0.f;
+    if (i8 && k < D) v = __fmul_rn(v, ix.cen_qscale[k]);
     sq[k] = v;
     ssq = fmaf(v, v, ssq);
   }
@@ -1035,20 +1045,24 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
   float qn = 0.f;
   if (sql2) {  // ||q||^2 exactly as tokenize_kernel: float(SquaredL2Norm(q))
     float acc = 0.f;
-    if (lane == 0) acc = squared_l2_norm_strided(sq, (uint32_t)D);
+    if (lane == 0) acc = squared_l2_norm_strided(i8 ? q + (size_t)qi * D : sq, (uint32_t)D);
     qn = __shfl_sync(0xFFFFFFFFu, acc, 0);
   }
   // chunk minima of the approximate distance: -max(S) (dot product), -max(2 S - ||c||^2) + ||q||^2 (squared L2)
   const float* cmr = cmax_ws + (size_t)qi * Lc;
-  for (int j = lane; j < Lc; j += 32) cm[j] = sql2 ? __fadd_rn(-cmr[j], qn) : -cmr[j];
+  // int8, squared L2: the statistic is max(2 S - 2 |c|^2) (the GEMM gets 2 |c|^2 as its bias), the approximate
+  // distance (|c|^2 + |q|^2) - S: chunk minimum = |q|^2 - statistic / 2
+  for (int j = lane; j < Lc; j += 32) cm[j] = sql2 ? __fadd_rn(i8 ? __fmul_rn(-0.5f, cmr[j]) : -cmr[j], qn) : -cmr[j];
   __syncwarp();
-  const float qnorm = sqrtf(ssq) * 1.001f, cmaxn = ix.center_max_norm;
+  const float qnorm = sqrtf(ssq) * 1.001f, cmaxn = i8 ? ix.cen_i8_max_norm : ix.center_max_norm;
   float eps = eps_rel * qnorm * cmaxn;
+  if (sql2 && i8) eps = eps + 16.f * 1.1920929e-7f * (qn + ix.cen_sqnorm_max + qnorm * cmaxn);
   // squared L2: as the radix refinement, plus the few ulps by which "(b - 2S) + |q|^2" of the chunk statistic and
   // "(b + |q|^2) - 2S" of the element test may differ
-  if (sql2) eps = 2.f * eps + (float)(D + 16) * 1.1920929e-7f * (qn + cmaxn * cmaxn + 2.f * qnorm * cmaxn);
+  if (sql2 && !i8) eps = 2.f * eps + (float)(D + 16) * 1.1920929e-7f * (qn + cmaxn * cmaxn + 2.f * qnorm * cmaxn);
   auto approx = [&](int i) -> float {
     const float sdot = row[i];
+    if (i8) return sql2 ? __fsub_rn(__fadd_rn(__ldg(ix.cen_sqnorm + i), qn), sdot) : -sdot;
     return sql2 ? __fsub_rn(__fadd_rn(__ldg(ix.center_sqnorm + i), qn), __fmul_rn(2.f, sdot)) : -sdot;
   };
   uint32_t need = 0;
@@ -1056,6 +1070,7 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
   const float U = ord2f(prefix);
   const float thr = __fadd_ru(U, __fmul_ru(2.f, eps));
   auto exact = [&](int idx) -> float {  // the reference's sequential fnmadd chain (tokenize_kernel)
+    if (i8) return i8_center_distance(ix, sq, idx, D, L3, sql2, qn);
     const float* c = ix.centers + (size_t)idx * D;
     float acc = sql2 ? __fadd_rn(ix.center_sqnorm[idx], qn) : 0.f;
     const float scale2 = sql2 ? 2.0f : 1.0f;
@@ -1125,7 +1140,9 @@ topp_chunk_kernel(DevIndex ix, const float* __restrict__ q, float* __restrict__ 
     for (int i = lane; i < P; i += 32) {
       const uint64_t k = i < ns ? skeys[i] : kKeyMax;
       lout[i] = (k == kKeyMax) ? -1 : (int32_t)(uint32_t)k;
-      bout[i] = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
+      float bv = (k == kKeyMax) ? 0.f : ord2f((uint32_t)(k >> 32));
+      if (i8 && !sql2 && bv == 0.f && k != kKeyMax && (int)(uint32_t)k >= L3) bv = -0.0f;  // see topp_refine_kernel
+      bout[i] = bv;
     }
   } else {
     if (lane == 0 && fallbacks) atomicAdd(fallbacks, 1u);
@@ -1160,7 +1177,7 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   // chunk pre-selection: P <= 128, at least 2 P chunks; default from 4096 centres
   // (SCANN_B200_TOKENIZE=chunk forces it where it applies, =tcgen05 the radix refinement)
   const uint32_t n_chunks = (ix.L + 31) / 32;
-  bool chunked = !i8 && ix.tok_cmax_ws && P <= 128 && n_chunks >= 2 * P && n_chunks <= (uint32_t)kChunkMaxChunks;
+  bool chunked = ix.tok_cmax_ws && P <= 128 && n_chunks >= 2 * P && n_chunks <= (uint32_t)kChunkMaxChunks;
   {
     const char* env = getenv("SCANN_B200_TOKENIZE");
     if (env && (!strcmp(env, "tcgen05") || !strcmp(env, "stream"))) chunked = false;
@@ -1174,7 +1191,7 @@ cudaError_t launch_tokenize_topp(const DevIndex& ix, const float* q, uint32_t nq
   bool store_rows = true;
   if (const char* env = getenv("SCANN_B200_TOKENIZE_ROWS")) store_rows = !(env[0] == '0' && chunked && ix.tok_need_rows == 0);
   e = gemm_bf16_nt(a_ws, nq, (nq + 127) / 128 * 128, ix.tok_b, ix.L, ix.tok_kp, store_rows ? dist : nullptr, ix.L, s,
-                   chunked ? ix.tok_cmax_ws : nullptr, n_chunks, (ix.distance == 1 && !i8) ? ix.center_sqnorm : nullptr);
+                   chunked ? ix.tok_cmax_ws : nullptr, n_chunks, ix.distance == 1 ? (i8 ? ix.cen_sqnorm2 : ix.center_sqnorm) : nullptr);
   if (e != cudaSuccess) return e;
   if (chunked) {
     int sp = 2;

@@ -37,9 +37,10 @@ def test_int8_tokenization_full_rows_bit_exact(L, D, distance):
 # operand) + radix refinement with the int8 chain -- the default from 256 centres.  L = 700: row image in shared
 # memory, 128 threads per query; 335: L % 4 != 0, no staged row; 4100: 256 threads; 2000 x 100: the C2 shape.  The zero
 # query has every approximate distance equal: more candidates than the buffer, the exact all-centres fallback.
-@pytest.mark.parametrize("route", ["simt", "tcgen05"])
+# "chunk": the chunk pre-selection of long rows (default from 4096 centres; forced here wherever L / 32 >= 2 P).
+@pytest.mark.parametrize("route", ["simt", "tcgen05", "chunk"])
 @pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
-@pytest.mark.parametrize("L,D", [(700, 96), (335, 50), (4100, 33), (2000, 100), (301, 128), (1000, 7)])
+@pytest.mark.parametrize("L,D", [(700, 96), (335, 50), (4100, 33), (2000, 100), (301, 128), (1000, 7), (8201, 40)])
 def test_int8_tokenization_routes_bit_exact(L, D, distance, route, monkeypatch):
   import oracle
   from scann_b200 import _lib
@@ -59,12 +60,12 @@ def test_int8_tokenization_routes_bit_exact(L, D, distance, route, monkeypatch):
 
 
 def test_int8_tokenization_near_ties_and_duplicate_centres(monkeypatch):
-  """Centres that quantize to the same int8 row (exact ties, broken by index) and centres a hair apart: the window of
+  """Both refinements.  Centres that quantize to the same int8 row (exact ties, broken by index) and centres a hair apart: the window of
   the pre-filter must keep every one of them for the exact chain to order."""
   import oracle
   from scann_b200 import _lib
-  monkeypatch.setenv("SCANN_B200_TOKENIZE", "tcgen05")
-  for distance in ("dot_product", "squared_l2"):
+  for distance, route in (("dot_product", "tcgen05"), ("squared_l2", "tcgen05"), ("dot_product", "chunk"), ("squared_l2", "chunk")):
+    monkeypatch.setenv("SCANN_B200_TOKENIZE", route)
     a, q = i8_tok_arrays(600, 64, distance, seed=77)
     rng = np.random.default_rng(8)
     a.centers[300:400] = a.centers[:100]                                     # exact duplicates
