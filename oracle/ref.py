@@ -40,6 +40,8 @@ def lib():
     if hasattr(L, "ref_one_to_many_f32"):
       L.ref_one_to_many_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
       L.ref_squared_l2_norm.restype = C.c_double
+    if hasattr(L, "ref_many_to_many_f32"):
+      L.ref_many_to_many_f32.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
       L.ref_squared_l2_norm.argtypes = [C.c_void_p, C.c_uint64]
     _LIB = L
   return _LIB
@@ -163,3 +165,17 @@ def squared_l2_norm(v):
   """SquaredL2Norm(ConstSpan<float>) = DenseSingleAccumulate(v, Square()) (utils/reduction.h:357-390), a double."""
   v = np.ascontiguousarray(v, dtype=np.float32)
   return float(lib().ref_squared_l2_norm(_p(v), v.size))
+
+
+def has_many_to_many():
+  return available() and hasattr(lib(), "ref_many_to_many_f32")
+
+
+def many_to_many_f32(queries, db, squared_l2=False):
+  """DenseDistanceManyToMany's accumulators (many_to_many_impl.inc:236-257,522-560): [nq, n] f32 -- -<q, x> or
+  (|x|^2 + |q|^2) - 2 <q, x> in the reference's per-dimension fnmadd order."""
+  queries = np.ascontiguousarray(queries, dtype=np.float32)
+  db = np.ascontiguousarray(db, dtype=np.float32)
+  out = np.zeros((queries.shape[0], db.shape[0]), np.float32)
+  lib().ref_many_to_many_f32(_p(queries), queries.shape[0], _p(db), db.shape[0], db.shape[1], 1 if squared_l2 else 0, _p(out))
+  return out

@@ -3,13 +3,27 @@
  * (tokenize -> AH LUT -> LUT16 scan -> top-N -> SOAR dedup -> exact reorder -> sort), of bf16 / float brute force,
  * and of the per-datapoint stage of index construction (database tokenization, SOAR assignment, AH encoding).
  *
- * TEST INFRASTRUCTURE ONLY -- see scann_oracle.h.  "parity unpinned" with
- * respect to the reference binary (it cannot be built here and ships no golden
- * vectors); pinned by tests/test_oracle.py and tests/golden/.
+ * TEST INFRASTRUCTURE ONLY -- see scann_oracle.h.  The reference as a whole cannot be built here and ships no golden
+ * vectors for this path; its self-contained arithmetic can, and is (oracle/Makefile -> oracle/_ref/libscann_ref.so,
+ * compiled from /root/reference).  PINNED to that compiled reference code, bit for bit (tests/test_oracle_ref.py):
+ * code packing, LUT fixed-point conversion, LUT16 int16 sums and float scores, the candidate contract, bf16 helpers,
+ * the float tokenization chain (many-to-many accumulation, centre and query norms), the int8 tokenization distances,
+ * the f32 / bf16 / int8 reordering distances (dims >= 8 for f32), SquaredL2Norm.  RESTATED ONLY (no compilable
+ * reference piece: they need Highway): the raw LUT distances of AH blocks with < 8 dims and of codebook centre 15,
+ * the f32 reordering distance for dims < 8, the index-build arithmetic -- pinned by the numpy / pure-Python
+ * restatements of tests/test_oracle.py, tests/test_oracle_build.py and by tests/golden/.
  *
  * Build: gcc -O3 -std=gnu11 -mavx2 -mfma -ffp-contract=off -fopenmp -shared -fPIC
  * (-ffp-contract=off matters: every FMA below is an explicit fmaf(), every
  *  "mul then add" must stay two roundings.)
+ *
+ * Contraction rule of the restatements.  The reference's documented build (README.md:98) is clang with
+ * --copt=-mavx --copt=-mfma and no -ffp-contract flag, i.e. clang's default "on": a multiply feeding an add or a
+ * subtract INSIDE ONE SOURCE EXPRESSION becomes one fused instruction (`acc - a * b`, `acc += a * b`,
+ * `acc + tmp * tmp`), whatever the function's own target attribute, while operations written as separate intrinsic
+ * calls or operator functions (`_mm_add_ps(acc, _mm_mul_ps(a, b))`, Highway's `add - mul * x`) stay two roundings.
+ * The _ref build reproduces exactly that for the pieces it compiles (oracle/Makefile), which is how the rule was
+ * checked where it matters (the scalar tails of the asymmetric and symmetric one-to-many kernels).
  *
  * Paths in comments are relative to /root/reference/scann/.
  */
@@ -212,8 +226,10 @@ static float sql2_avx2_order(const float* q, const float* x, uint32_t n) {
 
 /* one_to_many_symmetric.h:691-800 (Highway path taken when dims < 8; the static
  * Highway target of a plain x86-64 build has 4 f32 lanes, half vector 2 lanes),
- * NegMulAdd without FMA = acc - a*b with two roundings; ReduceSum of 4 lanes =
- * (a0+a2)+(a1+a3); at most one scalar tail step because Lanes(d) <= 4 breaks. */
+ * NegMulAdd without FMA = acc - a*b with two roundings (Highway's 128-bit NegMulAdd below AVX2 is `add - mul * x`
+ * through its operator functions, which no contraction mode fuses); ReduceSum of 4 lanes = (a0+a2)+(a1+a3); at most
+ * one scalar tail step because Lanes(d) <= 4 breaks -- the lambdas' scalar AccTerm, ONE expression `acc - a * b`, which
+ * the reference's documented build (README.md:98: clang, --copt=-mfma, default -ffp-contract=on) fuses. */
 static float neg_dot_small(const float* q, const float* x, uint32_t n) {
   float a[4] = {0, 0, 0, 0};
   uint32_t j = 0;
@@ -226,7 +242,7 @@ static float neg_dot_small(const float* q, const float* x, uint32_t n) {
     j += 2;
   }
   float r = (a[0] + a[2]) + (a[1] + a[3]);
-  if (j < n) { float p = q[j] * x[j]; r = r - p; }
+  if (j < n) r = fmaf(-q[j], x[j], r);  /* scalar AccTerm `acc - a * b` (:1013): one expression, contracts (see the header) */
   return r;
 }
 static float sql2_small(const float* q, const float* x, uint32_t n) {
@@ -242,7 +258,7 @@ static float sql2_small(const float* q, const float* x, uint32_t n) {
     j += 2;
   }
   float r = (a[0] + a[2]) + (a[1] + a[3]);
-  if (j < n) { float t = q[j] - x[j]; float p = t * t; r = r + p; }
+  if (j < n) { float t = q[j] - x[j]; r = fmaf(t, t, r); }  /* scalar AccTerm `acc + tmp * tmp` (:1063-1066) */
   return r;
 }
 
@@ -275,7 +291,7 @@ static float dot_sse4_order(const float* q, const float* x, uint32_t n) {
     a[3] = a[3] + p3;
     j += 2;
   }
-  if (j < n) { float p = q[j] * x[j]; a[0] = a[0] + p; }
+  if (j < n) a[0] = fmaf(q[j], x[j], a[0]);  /* `accumulator[0] += aptr[0] * bptr[0]` (:291-293): contracts */
   return (a[0] + a[1]) + (a[2] + a[3]);
 }
 /* l2_distance_sse4.cc (DenseSquaredL2DistanceSse4, float): same shape with (a-b)^2. */
@@ -309,7 +325,7 @@ static float sql2_sse4_order(const float* q, const float* x, uint32_t n) {
     a[3] = a[3] + p3;
     j += 2;
   }
-  if (j < n) { float t = q[j] - x[j]; float p = t * t; a[0] = a[0] + p; }
+  if (j < n) { float t = q[j] - x[j]; a[0] = fmaf(t, t, a[0]); }  /* l2_distance_sse4.cc:214-216: contracts */
   return (a[0] + a[1]) + (a[2] + a[3]);
 }
 

@@ -206,7 +206,7 @@ __device__ __forceinline__ float neg_dot_small(LoadQ q, LoadX x, uint32_t n) {
     j += 2;
   }
   float r = __fadd_rn(__fadd_rn(a[0], a[2]), __fadd_rn(a[1], a[3]));
-  if (j < n) r = __fsub_rn(r, __fmul_rn(q(j), x(j)));
+  if (j < n) r = __fmaf_rn(-q(j), x(j), r);  // the scalar AccTerm `acc - a * b`: one expression, fused by the reference's build
   return r;
 }
 template <typename LoadQ, typename LoadX>
@@ -229,7 +229,7 @@ __device__ __forceinline__ float sql2_small(LoadQ q, LoadX x, uint32_t n) {
   float r = __fadd_rn(__fadd_rn(a[0], a[2]), __fadd_rn(a[1], a[3]));
   if (j < n) {
     const float t = __fsub_rn(q(j), x(j));
-    r = __fadd_rn(r, __fmul_rn(t, t));
+    r = __fmaf_rn(t, t, r);  // scalar AccTerm `acc + tmp * tmp`: fused
   }
   return r;
 }
@@ -269,7 +269,7 @@ __device__ __forceinline__ float dot_sse4_order(LoadQ q, LoadX x, uint32_t n) {
     a[3] = __fadd_rn(a[3], __fmul_rn(q(j + 1), x(j + 1)));
     j += 2;
   }
-  if (j < n) a[0] = __fadd_rn(a[0], __fmul_rn(q(j), x(j)));
+  if (j < n) a[0] = __fmaf_rn(q(j), x(j), a[0]);  // `accumulator[0] += aptr[0] * bptr[0]`: fused
   return __fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3]));
 }
 template <typename LoadQ, typename LoadX>
@@ -312,7 +312,7 @@ __device__ __forceinline__ float sql2_sse4_order(LoadQ q, LoadX x, uint32_t n) {
   }
   if (j < n) {
     const float t = __fsub_rn(q(j), x(j));
-    a[0] = __fadd_rn(a[0], __fmul_rn(t, t));
+    a[0] = __fmaf_rn(t, t, a[0]);  // `accumulator[0] += (a - b) * (a - b)`: fused
   }
   return __fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3]));
 }

@@ -322,3 +322,42 @@ def test_squared_l2_norm_equals_the_reference_reduction():
     _, _, sqn = oracle.quantize_centers(a.centers)
     want = np.asarray([np.float32(ref.squared_l2_norm(r)) for r in a.centers], np.float32)
     np.testing.assert_array_equal(sqn.view(np.uint32), want.view(np.uint32))
+
+
+# ---- the batched float tokenization chain (ref_glue_m2m.cc) ---------------------------------------------------------
+
+needs_m2m = pytest.mark.skipif(not (ref.available() and ref.has_many_to_many()),
+                               reason="oracle/_ref/libscann_ref.so without the many-to-many pieces")
+
+
+@needs_m2m
+@pytest.mark.parametrize("distance", ["dot_product", "squared_l2"])
+@pytest.mark.parametrize("L,D", [(100, 100), (33, 17), (50, 64), (7, 3), (16, 128), (17, 96), (1, 40), (257, 30)])
+def test_float_tokenization_equals_the_reference_many_to_many(L, D, distance):
+  """KMeansTreePartitioner::TokensForDatapointWithSpillingBatched -> DenseDistanceManyToManyTopK: the oracle's centre
+  distances (all L, ragged last block of 2 x 8 centres included) against the reference's own AugmentWithL2Norms /
+  DoAccumulationTransposedTemplate and SquaredL2Norm, bit for bit."""
+  import oracle
+  from helpers import i8_tok_arrays
+  a, q = i8_tok_arrays(L, D, distance, seed=L * 100 + D)
+  a.int8_tokenization = False
+  oi = oracle.OracleIndex(a, min(L, 7), 10, 5)
+  leaf, cdist = oi.tokenize(q, leaves=L)
+  want = ref.many_to_many_f32(q, a.centers, squared_l2=distance == "squared_l2")
+  for i in range(len(q)):
+    np.testing.assert_array_equal(cdist[i].view(np.uint32), want[i, leaf[i]].view(np.uint32))
+
+
+@needs_m2m
+def test_database_tokenization_distances_equal_the_reference_many_to_many():
+  """The index build assigns every datapoint to its nearest centre under squared L2 through the same kernel
+  (kmeans_tree_partitioner.cc:561-612): the oracle's primary assignment is the argmin of the reference's accumulators."""
+  import oracle
+  rng = np.random.default_rng(12)
+  for n, L, D in [(500, 37, 24), (300, 100, 100), (200, 16, 7)]:
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    centers = rng.standard_normal((L, D)).astype(np.float32)
+    want = ref.many_to_many_f32(x, centers, squared_l2=True)
+    tok, dist = oracle.assign_primary(x, centers, threads=1)
+    np.testing.assert_array_equal(tok, want.argmin(1))
+    np.testing.assert_array_equal(dist.view(np.uint32), want.min(1).view(np.uint32))
