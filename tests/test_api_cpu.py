@@ -291,3 +291,58 @@ def test_int8_quantizer_semantics():
   np.testing.assert_array_equal(q[:, 3], np.array([127, 126, -127], np.int8))          # 0.996 * 127 = 126.49 -> 126
   n = index_build.squared_l2_norms(x)
   np.testing.assert_allclose(n, (x.astype(np.float64) ** 2).sum(1), rtol=1e-7)
+
+
+def test_quantized_centroids_config_reaches_the_index_descriptor(tmp_path):
+  """tree(quantize_centroids=True) -> `query_tokenization_type: FIXED_POINT_INT8` (scann_builder.py:231) survives
+  serialization (binary scann_config.pb) and comes back in scann_b200_index_desc.query_tokenization_type; nothing extra
+  is written -- the fixed-point centres are derived at load time, as KMeansTreeNode::CreateFixedPointCenters does."""
+  from scann_b200.scann_pybind import _Plan
+  a, z = load_golden("dot_b16")
+  L = _lib.lib()
+  keep = []
+
+  def own(x, dt):
+    y = np.ascontiguousarray(x, dtype=dt)
+    keep.append(y)
+    return _lib.ptr(y)
+
+  for quantized in (False, True):
+    d = _lib.IndexDesc()
+    d.distance, d.n, d.d = 0, a.n, a.d
+    d.n_leaves, d.n_blocks, d.dims_per_block = a.centers.shape[0], a.codes.shape[1], a.codebook.shape[2]
+    d.block_dims, d.centers, d.tokens = own(a.block_dims, np.int32), own(a.centers, np.float32), own(a.tokens, np.int32)
+    d.codes, d.codebook, d.dataset = own(a.codes, np.uint8), own(a.codebook, np.float32), own(a.dataset, np.float32)
+    cfg = scann_builder.ScannBuilder(a.dataset, 10, "dot_product").tree(
+        a.centers.shape[0], 4, quantize_centroids=quantized).score_ah(2).reorder(40).create_config()
+    assert ("FIXED_POINT_INT8" in cfg) == quantized
+    out = tmp_path / ("q" if quantized else "f")
+    out.mkdir()
+    buf = C.create_string_buffer(1 << 16)
+    assert L.scann_b200_assets_save(str(out).encode(), C.byref(d), cfg.encode(), 0, buf, len(buf)) == 0, L.scann_b200_last_error()
+    assert sorted(p.name for p in out.iterdir()) == sorted(
+        ["scann_config.pb", "serialized_partitioner.pb", "ah_codebook.pb", "datapoint_to_token.npy",
+         "hashed_dataset.npy", "dataset.npy"])  # (the manifest text is returned to the caller, who writes it)
+    h = C.c_void_p()
+    assert L.scann_b200_assets_load(str(out).encode(), buf.value, C.byref(h)) == 0, L.scann_b200_last_error()
+    d2 = _lib.IndexDesc()
+    assert L.scann_b200_assets_describe(h, C.byref(d2)) == 0
+    plan = _Plan(L.scann_b200_assets_config(h).decode())
+    L.scann_b200_assets_free(h)
+    assert d2.query_tokenization_type == (1 if quantized else 0)
+    plan.check_supported()
+    assert plan.int8_tokenization() == quantized
+
+
+def test_plan_refuses_what_is_not_built_around_the_tree():
+  """Two-level trees (upper_tree) and a quantized DATABASE tokenization are refused, not ignored."""
+  from scann_b200.scann_pybind import _Plan
+  db = np.zeros((10, 8), np.float32)
+  ok = scann_builder.ScannBuilder(db, 5, "dot_product").tree(4, 2, quantize_centroids=True).score_ah(2).create_config()
+  _Plan(ok).check_supported()
+  with pytest.raises(Exception, match="upper_tree"):
+    _Plan(ok.replace("query_tokenization_type: FIXED_POINT_INT8",
+                     "query_tokenization_type: FIXED_POINT_INT8\n bottom_up_top_level_partitioner { enabled: true num_centroids: 2 }")).check_supported()
+  with pytest.raises(Exception, match="database_tokenization_type"):
+    _Plan(ok.replace("query_tokenization_type: FIXED_POINT_INT8",
+                     "query_tokenization_type: FIXED_POINT_INT8\n database_tokenization_type: FIXED_POINT_INT8")).check_supported()
