@@ -40,6 +40,12 @@ def lib():
     if hasattr(L, "ref_one_to_many_f32"):
       L.ref_one_to_many_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
       L.ref_squared_l2_norm.restype = C.c_double
+    if hasattr(L, "ref_encode_noise_shaped"):
+      L.ref_encode_noise_shaped.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                            C.c_uint64, C.c_void_p, C.c_double, C.c_void_p]
+    if hasattr(L, "ref_soar_costs"):
+      L.ref_soar_costs.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_float,
+                                   C.c_void_p, C.c_void_p]
     if hasattr(L, "ref_many_to_many_f32"):
       L.ref_many_to_many_f32.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
       L.ref_squared_l2_norm.argtypes = [C.c_void_p, C.c_uint64]
@@ -178,4 +184,37 @@ def many_to_many_f32(queries, db, squared_l2=False):
   db = np.ascontiguousarray(db, dtype=np.float32)
   out = np.zeros((queries.shape[0], db.shape[0]), np.float32)
   lib().ref_many_to_many_f32(_p(queries), queries.shape[0], _p(db), db.shape[0], db.shape[1], 1 if squared_l2 else 0, _p(out))
+  return out
+
+
+def has_soar_costs():
+  return available() and hasattr(lib(), "ref_soar_costs")
+
+
+def soar_costs(x, centers, primary, lam):
+  """ComputeNormalizedResidual + DenseManyToManyOrthogonalityAmplified's accumulation: (costs [n, L], rhat [n, D])."""
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  c = np.ascontiguousarray(centers, dtype=np.float32)
+  p = np.ascontiguousarray(primary, dtype=np.int32)
+  cost = np.zeros((x.shape[0], c.shape[0]), np.float32)
+  rhat = np.zeros(x.shape, np.float32)
+  lib().ref_soar_costs(_p(x), x.shape[0], x.shape[1], _p(c), c.shape[0], _p(p), C.c_float(float(lam)), _p(cost), _p(rhat))
+  return cost, rhat
+
+
+def has_noise_shaped():
+  return available() and hasattr(lib(), "ref_encode_noise_shaped")
+
+
+def encode_noise_shaped(x, codebook, block_dims=None, centers=None, token=None, threshold=0.2):
+  """AhImpl<float>::IndexDatapointNoiseShaped (asymmetric_hashing_impl.cc:434-503) over rows of x (residual against
+  centers[token] when given, the original being x): codes [n, B] u8."""
+  x = np.ascontiguousarray(x, dtype=np.float32)
+  cb = np.ascontiguousarray(codebook, dtype=np.float32)
+  bd = None if block_dims is None else np.ascontiguousarray(block_dims, dtype=np.int32)
+  c = None if centers is None else np.ascontiguousarray(centers, dtype=np.float32)
+  t = None if token is None else np.ascontiguousarray(token, dtype=np.int32)
+  out = np.zeros((x.shape[0], cb.shape[0]), np.uint8)
+  lib().ref_encode_noise_shaped(_p(x), x.shape[0], x.shape[1], None if c is None else _p(c), None if t is None else _p(t),
+                                _p(cb), cb.shape[0], cb.shape[2], None if bd is None else _p(bd), float(threshold), _p(out))
   return out

@@ -7,6 +7,9 @@
 // many_to_many_impl.inc, extracted by line range at BUILD time into oracle/_ref/gen/ (git-ignored) by oracle/Makefile:
 //   _ref/gen/m2m_augment.inc    = :236-257  M2MTransposer::AugmentWithL2Norms (|c|^2 = -(fnmadd chain), rows doubled)
 //   _ref/gen/m2m_accumulate.inc = :522-560  DenseManyToManyTransposed::DoAccumulationTransposedTemplate
+//   _ref/gen/m2m_oa_accumulate.inc = :729-773  DenseManyToManyOrthogonalityAmplified::DoAccumulationTransposedTemplate
+//       (the SOAR cost t1 + (lambda t2) t2 of the index build's secondary assignment)
+// and partitioning/orthogonality_amplification_utils.h:27-46 (ComputeNormalizedResidual) as _ref/gen/oa_residual.inc
 // as static members of a struct that supplies what they name from their classes (kIsSquaredL2, FloatT,
 // kElementsPerRegister), with the reference's own AVX2 wrappers (utils/intrinsics/avx2.h, fma.inc).  The transposition
 // (many_to_many_impl.inc:169-207: element moves, no arithmetic) and the loop over blocks of 2 x 8 datapoints are written
@@ -36,6 +39,36 @@ struct M2MPieces {
 #include "m2m_augment.inc"
 #include "m2m_accumulate.inc"
 };
+
+struct M2MOaPieces {
+  using FloatT = float;
+  static constexpr size_t kElementsPerRegister = Simd<float>::kElementsPerRegister;
+#include "m2m_oa_accumulate.inc"
+};
+
+// one datapoint ("query") with its normalised residual against centres [0, n): out[i] = SOAR cost of centre i
+SCANN_AVX2_OUTLINE void RunOneSoarQuery(const float* x, const float* rhat, float lambda, const float* centers, size_t n,
+                                        size_t dims, float* out) {
+  constexpr size_t kE = M2MOaPieces::kElementsPerRegister;
+  const size_t tsz = dims * kE;
+  float* storage = static_cast<float*>(aligned_alloc(64, (2 * tsz * sizeof(float) + 63) / 64 * 64));
+  float* t0 = storage;
+  float* t1 = storage + tsz;
+  for (size_t first = 0; first < n; first += 2 * kE) {
+    const size_t cnt = std::min(n - first, 2 * kE);
+    for (size_t i = 0; i < 2 * tsz; ++i) storage[i] = 0.0f;
+    for (size_t j = 0; j < cnt; ++j) {
+      float* t = j < kE ? t0 : t1;
+      for (size_t dim = 0; dim < dims; ++dim) t[dim * kE + (j % kE)] = centers[(first + j) * dims + dim];
+    }
+    const float* qptrs[1] = {x};
+    const float* rptrs[1] = {rhat};
+    auto acc = M2MOaPieces::DoAccumulationTransposedTemplate<1>(t0, t1, qptrs, rptrs, lambda, dims);
+    auto results = acc.Store();
+    for (size_t j = 0; j < cnt; ++j) out[first + j] = results[0].data()[j];
+  }
+  free(storage);
+}
 
 // one query against rows [0, n): out[i] = the accumulator of datapoint i
 template <bool kIsSquaredL2>
@@ -67,7 +100,38 @@ SCANN_AVX2_OUTLINE void RunOneQuery(const float* query, const float* db, size_t 
 }  // namespace avx2
 }  // namespace research_scann
 
+namespace research_scann {
+template <typename T>
+class DatapointPtr {
+ public:
+  DatapointPtr(const T* values, size_t dims) : values_(values), d_(dims) {}
+  const T* values() const { return values_; }
+  size_t dimensionality() const { return d_; }
+ private:
+  const T* values_;
+  size_t d_;
+};
+#include "oa_residual.inc"  // _ref/gen: partitioning/orthogonality_amplification_utils.h:27-46
+}  // namespace research_scann
+
 extern "C" {
+
+// OrthogonalityAmplifiedTokenForDatapointBatched's arithmetic (partitioning/kmeans_tree_partitioner.cc:925-997): for every
+// datapoint i, rhat = ComputeNormalizedResidual(x_i, centre primary[i]) -> out_rhat [n][dims] (optional), and the SOAR
+// cost of every centre -> out_cost [n][L]
+int ref_soar_costs(const float* x, uint64_t n, uint64_t dims, const float* centers, uint64_t L, const int32_t* primary,
+                   float lambda, float* out_cost, float* out_rhat) {
+  using namespace research_scann;
+  std::vector<float> rhat(dims);
+  for (uint64_t i = 0; i < n; ++i) {
+    ComputeNormalizedResidual(DatapointPtr<float>(x + i * dims, dims),
+                              DatapointPtr<float>(centers + (uint64_t)primary[i] * dims, dims),
+                              MutableSpan<float>(rhat.data(), dims));
+    if (out_rhat) memcpy(out_rhat + i * dims, rhat.data(), sizeof(float) * dims);
+    avx2::RunOneSoarQuery(x + i * dims, rhat.data(), lambda, centers, L, dims, out_cost + i * L);
+  }
+  return 0;
+}
 
 // out[q][i] = DenseDistanceManyToMany(dot product | squared L2)(queries, db) as the reference accumulates it
 int ref_many_to_many_f32(const float* queries, uint64_t nq, const float* db, uint64_t n, uint64_t dims, int squared_l2,

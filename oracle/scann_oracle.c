@@ -8,9 +8,10 @@
  * compiled from /root/reference).  PINNED to that compiled reference code, bit for bit (tests/test_oracle_ref.py):
  * code packing, LUT fixed-point conversion, LUT16 int16 sums and float scores, the candidate contract, bf16 helpers,
  * the float tokenization chain (many-to-many accumulation, centre and query norms), the int8 tokenization distances,
- * the f32 / bf16 / int8 reordering distances (dims >= 8 for f32), SquaredL2Norm.  RESTATED ONLY (no compilable
+ * the f32 / bf16 / int8 reordering distances (dims >= 8 for f32), SquaredL2Norm, and of the index build the database
+ * tokenization, the SOAR assignment and the noise-shaped encoder.  RESTATED ONLY (no compilable
  * reference piece: they need Highway): the raw LUT distances of AH blocks with < 8 dims and of codebook centre 15,
- * the f32 reordering distance for dims < 8, the index-build arithmetic -- pinned by the numpy / pure-Python
+ * the f32 reordering distance for dims < 8, plain AH codes of blocks with < 8 dims, k-means -- pinned by the numpy / pure-Python
  * restatements of tests/test_oracle.py, tests/test_oracle_build.py and by tests/golden/.
  *
  * Build: gcc -O3 -std=gnu11 -mavx2 -mfma -ffp-contract=off -fopenmp -shared -fPIC

@@ -361,3 +361,63 @@ def test_database_tokenization_distances_equal_the_reference_many_to_many():
     tok, dist = oracle.assign_primary(x, centers, threads=1)
     np.testing.assert_array_equal(tok, want.argmin(1))
     np.testing.assert_array_equal(dist.view(np.uint32), want.min(1).view(np.uint32))
+
+
+@needs_m2m
+@pytest.mark.parametrize("n,L,D,lam", [(400, 37, 24, 1.5), (300, 100, 100, 1.0), (200, 16, 7, 2.5), (150, 33, 64, 0.0)])
+def test_soar_assignment_equals_the_reference_arithmetic(n, L, D, lam):
+  """The index build's SOAR secondary assignment (KMeansTreePartitioner::OrthogonalityAmplifiedTokenForDatapointBatched,
+  partitioning/kmeans_tree_partitioner.cc:925-997): the oracle's choice and cost against the argmin / min of the costs the
+  reference's own ComputeNormalizedResidual + DenseManyToManyOrthogonalityAmplified accumulation produce (first strict
+  minimum over all centres).  A datapoint that coincides with its primary centre has a zero residual."""
+  import oracle
+  if not ref.has_soar_costs():
+    pytest.skip("library without ref_soar_costs")
+  rng = np.random.default_rng(n + L)
+  x = rng.standard_normal((n, D)).astype(np.float32)
+  centers = rng.standard_normal((L, D)).astype(np.float32)
+  primary, _ = oracle.assign_primary(x, centers, threads=1)
+  x[0] = centers[primary[0]]                                  # sqnorm < 1e-7: rhat = 0
+  want_cost, _ = ref.soar_costs(x, centers, primary, lam)
+  tok, cost = oracle.assign_soar(x, centers, primary, lam, threads=1)
+  np.testing.assert_array_equal(tok, want_cost.argmin(1))
+  np.testing.assert_array_equal(cost.view(np.uint32), want_cost.min(1).view(np.uint32))
+
+
+# ---- the noise-shaped AH encoder (ref_glue_ns.cc) -------------------------------------------------------------------
+
+needs_ns = pytest.mark.skipif(not (ref.available() and ref.has_noise_shaped()),
+                              reason="oracle/_ref/libscann_ref.so without the noise-shaped encoder")
+
+
+@needs_ns
+@pytest.mark.parametrize("D,dpb,residual,threshold", [(32, 2, True, 0.2), (100, 2, True, 0.2), (100, 3, True, 0.2),
+                                                      (64, 4, False, 0.3), (96, 8, True, 0.5), (40, 1, True, 0.2)])
+def test_noise_shaped_codes_equal_the_reference_encoder(D, dpb, residual, threshold):
+  """Indexer::HashWithNoiseShaping -> AhImpl<float>::IndexDatapointNoiseShaped (asymmetric_hashing_impl.cc:434-503): the
+  oracle's noise-shaped codes against the reference's own residual statistics, cost multiplier, block order
+  (utils/zip_sort.h) and coordinate descent, on clustered data with trained-looking codebooks (VARIABLE_CHUNK when dpb
+  does not divide D)."""
+  import oracle
+  rng = np.random.default_rng(D * 10 + dpb)
+  n, L = 600, 12
+  centers = rng.standard_normal((L, D)).astype(np.float32)
+  token = rng.integers(0, L, n).astype(np.int32)
+  x = centers[token] + 0.3 * rng.standard_normal((n, D))
+  x = (x / np.linalg.norm(x, axis=1, keepdims=True)).astype(np.float32)      # unit rows: the threshold is relative to |x|
+  centers = (centers / np.linalg.norm(centers, axis=1, keepdims=True)).astype(np.float32)
+  B = (D + dpb - 1) // dpb
+  bd = np.full(B, dpb, np.int32)
+  if D % dpb:
+    bd[-1] = D % dpb
+  scale = (0.3 if residual else 1.0) / np.sqrt(D)
+  codebook = (scale * rng.standard_normal((B, 16, dpb))).astype(np.float32)
+  for b in range(B):
+    codebook[b, :, bd[b]:] = 0.0
+  cen = centers if residual else None
+  tok = token if residual else None
+  got, ties = oracle.encode(x, codebook, bd, cen, tok, threshold, threads=1)
+  want = ref.encode_noise_shaped(x, codebook, bd, cen, tok, threshold)
+  np.testing.assert_array_equal(got, want)
+  plain, _ = oracle.encode(x, codebook, bd, cen, tok, float("nan"), threads=1)
+  assert (plain != want).mean() > 0.01        # the shaping does move codes: the test is not vacuous
