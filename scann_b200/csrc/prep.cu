@@ -104,7 +104,9 @@ tokenize_kernel(const float* __restrict__ q, const float* __restrict__ c,
 // into lanes 0..3, ((a0+a4)+(a2+a6)) + ((a1+a5)+(a3+a7)), the remaining dims on the scalar -- and the last L mod 3
 // centres through the one-to-one kernel (tokenize_i8_tail_kernel).  Here: a 64-query x 32-centre SIMT tile, four
 // queries x two centres per thread, the eight lane accumulators of every (query, centre) pair in registers, so each
-// lane sees its dims in the reference's order whatever the tiling over k.
+// lane sees its dims in the reference's order whatever the tiling over k.  These exact kernels serve small trees; from
+// 256 centres launch_tokenize_topp takes the tensor-core route (the int8 centres are an exact bf16 operand) and only
+// re-scores the candidates of the top P with the same chains (i8_center_distance below).
 // ---------------------------------------------------------------------------------------
 constexpr int I8M = 64, I8N = 32, I8K = 16, I8PAD = 4;
 
