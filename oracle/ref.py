@@ -40,6 +40,10 @@ def lib():
     if hasattr(L, "ref_one_to_many_f32"):
       L.ref_one_to_many_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]
       L.ref_squared_l2_norm.restype = C.c_double
+    if hasattr(L, "ref_dot_sse4_f32"):
+      for f in (L.ref_dot_sse4_f32, L.ref_sql2_sse4_f32):
+        f.restype = C.c_double
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
     if hasattr(L, "ref_encode_noise_shaped"):
       L.ref_encode_noise_shaped.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                             C.c_uint64, C.c_void_p, C.c_double, C.c_void_p]
@@ -218,3 +222,15 @@ def encode_noise_shaped(x, codebook, block_dims=None, centers=None, token=None, 
   lib().ref_encode_noise_shaped(_p(x), x.shape[0], x.shape[1], None if c is None else _p(c), None if t is None else _p(t),
                                 _p(cb), cb.shape[0], cb.shape[2], None if bd is None else _p(bd), float(threshold), _p(out))
   return out
+
+
+def has_sse4_one_to_one():
+  return available() and hasattr(lib(), "ref_dot_sse4_f32")
+
+
+def one_to_one_sse4(a, b, squared_l2=False):
+  """DenseDotProductSse4 / DenseSquaredL2DistanceSse4 (float, float), even lengths: the double the reference returns."""
+  a = np.ascontiguousarray(a, dtype=np.float32)
+  b = np.ascontiguousarray(b, dtype=np.float32)
+  f = lib().ref_sql2_sse4_f32 if squared_l2 else lib().ref_dot_sse4_f32
+  return float(f(_p(a), _p(b), a.size))

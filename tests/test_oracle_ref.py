@@ -421,3 +421,33 @@ def test_noise_shaped_codes_equal_the_reference_encoder(D, dpb, residual, thresh
   np.testing.assert_array_equal(got, want)
   plain, _ = oracle.encode(x, codebook, bd, cen, tok, float("nan"), threads=1)
   assert (plain != want).mean() > 0.01        # the shaping does move codes: the test is not vacuous
+
+
+# ---- a lookup table computed by reference code only (dims per block >= 8 and even) ----------------------------------
+
+@pytest.mark.skipif(not (ref.available() and ref.has_symmetric() and ref.has_sse4_one_to_one()),
+                    reason="oracle/_ref/libscann_ref.so without the float one-to-many / one-to-one kernels")
+@pytest.mark.parametrize("kw", [dict(dpb=8, d=128, leaves=32, n=6000), dict(dpb=16, d=64, leaves=20, n=4000),
+                                dict(distance="squared_l2", dpb=8, d=64, leaves=20, n=4000)],
+                         ids=["dot_dpb8", "dot_dpb16", "l2_dpb8"])
+def test_lookup_tables_equal_the_reference_pipeline(kw):
+  """AsymmetricQueryer::CreateLookupTable for blocks of >= 8 dims, assembled from REFERENCE code only: centres 0..14 of a
+  block through DenseAccumulatingDistanceMeasureOneToManyInternalAvx2 (three at a time), centre 15 (16 mod 3 = 1) through
+  the SSE4 one-to-one kernel (negated for dot product, one_to_many_symmetric.h:793-799), the whole float table through
+  ConvertLookupToFixedPoint<uint8_t> -- against the oracle's u8 tables and multipliers, bit for bit."""
+  c = get_case(**kw)
+  l2 = c.arrays.distance == "squared_l2"
+  cb = c.arrays.codebook                                       # [B, 16, dpb]
+  B, _, dpb = cb.shape
+  q = c.q[:8]
+  lut, mult = c.oracle.lut(q)
+  for i in range(len(q)):
+    raw = np.empty((B, 16), np.float32)
+    for b in range(B):
+      qb = q[i, b * dpb:(b + 1) * dpb]
+      raw[b, :15] = ref.one_to_many_f32(qb, cb[b, :15], squared_l2=l2)
+      one = ref.one_to_one_sse4(qb, cb[b, 15], squared_l2=l2)
+      raw[b, 15] = np.float32(one if l2 else -one)
+    want_lut, want_mult = ref.lut_to_fixed_point(raw)
+    np.testing.assert_array_equal(np.float32(mult[i]).view(np.uint32), np.float32(want_mult).view(np.uint32))
+    np.testing.assert_array_equal(lut[i].reshape(-1), want_lut)
