@@ -203,3 +203,53 @@ def np_search(arrays, q, probe, pre, k):
       ids[i, j] = dp
       dists[i, j] = -dist
   return ids, dists, cd, lut, mult, cands
+
+
+def reference_pipeline_search(c, q):
+  """SearchBatched of the tree-AH index of `c` (a conftest.Case with >= 8, even dims per block, no SOAR) in which every
+  NUMBER comes from the reference's own compiled code (oracle/_ref): centre distances (many-to-many accumulation), the
+  lookup table (one-to-many AVX2 kernel, SSE4 one-to-one kernel for centre 15, fixed-point conversion), per-leaf scores
+  (LUT16 AVX2 kernel on the reference's packing), exact reordering distances (one-to-many AVX2 kernel).  Only the
+  selections are written here: top P leaves by (distance, leaf), top N' candidates by (score, leaf, slot) -- (score, id)
+  for squared L2, TreeXHybridSMMD -- and top k by (distance, id).  Returns (ids [nq, k] u32, distances [nq, k] f32) as
+  the API reports them (dot product: similarities, result_multiplier_ of scann_ops/cc/scann.cc:365-369)."""
+  from oracle import ref
+  a = c.arrays
+  assert not a.soar
+  l2 = a.distance == "squared_l2"
+  L = a.centers.shape[0]
+  B, _, dpb = a.codebook.shape
+  assert dpb >= 8 and dpb % 2 == 0 and a.block_dims.min() == dpb
+  canon = lambda x: np.float32(x) + np.float32(0.0)           # DistanceComparator: -0.0 == +0.0
+  cd_all = ref.many_to_many_f32(q, a.centers, squared_l2=l2)
+  ids = np.zeros((len(q), c.k), np.uint32)
+  dists = np.full((len(q), c.k), np.nan, np.float32)
+  for i in range(len(q)):
+    leaves = np.lexsort((np.arange(L), canon(cd_all[i])))[:c.probe]
+    raw = np.empty((B, 16), np.float32)
+    for b in range(B):
+      qb = q[i, b * dpb:(b + 1) * dpb]
+      raw[b, :15] = ref.one_to_many_f32(qb, a.codebook[b, :15], squared_l2=l2)
+      one = ref.one_to_one_sse4(qb, a.codebook[b, 15], squared_l2=l2)
+      raw[b, 15] = np.float32(one if l2 else -one)
+    lut, mult = ref.lut_to_fixed_point(raw)
+    rows = []
+    for leaf in leaves.tolist():
+      dps = c.oracle.leaf_datapoints(leaf)
+      if len(dps) == 0:
+        continue
+      packed = ref.pack_dataset(a.codes[dps])
+      bias = np.float32(0.0) if l2 else cd_all[i, leaf]       # squared L2 (SMMD): no leaf bias
+      (idx, dist), = ref.lut16_top_float(packed, len(dps), B, [lut], [bias], [mult])
+      assert len(idx) == len(dps)
+      for s, d in zip(idx.tolist(), dist.tolist()):
+        rows.append((float(canon(d)), (int(dps[s]),) if l2 else (leaf, s), int(dps[s])))
+    rows.sort(key=lambda t: (t[0], t[1]))
+    cand = np.asarray([r[2] for r in rows[:c.pre]], np.int64)
+    pad = (-len(cand)) % 3                                     # the kernel takes three rows at a time
+    padded = np.concatenate([cand, np.repeat(cand[-1:], pad)])
+    exact = ref.one_to_many_f32(q[i], a.dataset[padded], squared_l2=l2)[:len(cand)]
+    order = np.lexsort((cand, canon(exact)))[:c.k]
+    ids[i, :len(order)] = cand[order]
+    dists[i, :len(order)] = exact[order] if l2 else -exact[order]
+  return ids, dists

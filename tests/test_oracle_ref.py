@@ -465,45 +465,10 @@ def test_whole_search_from_reference_arithmetic_only(kw):
   distances (one-to-many AVX2 kernel) -- and only the selections (top P leaves, top N' candidates by (score, leaf, slot)
   or (score, id), top k by (distance, id)) are written here.  It equals the oracle's search_batched, ids and distance
   bits: the oracle -- and through the `-m gpu` tests the CUDA path -- computes what the reference's arithmetic computes."""
+  from helpers import reference_pipeline_search
   c = get_case(**kw)
-  a = c.arrays
-  l2 = a.distance == "squared_l2"
-  L = a.centers.shape[0]
-  B, _, dpb = a.codebook.shape
-  nq = 6
-  q = c.q[:nq]
+  q = c.q[:6]
   want_idx, want_dist = c.oracle.search_batched(q)
-  cd_all = ref.many_to_many_f32(q, a.centers, squared_l2=l2)
-  canon = lambda x: np.float32(x) + np.float32(0.0)           # DistanceComparator: -0.0 == +0.0
-  for i in range(nq):
-    leaves = np.lexsort((np.arange(L), canon(cd_all[i])))[:c.probe]
-    raw = np.empty((B, 16), np.float32)
-    for b in range(B):
-      qb = q[i, b * dpb:(b + 1) * dpb]
-      raw[b, :15] = ref.one_to_many_f32(qb, a.codebook[b, :15], squared_l2=l2)
-      one = ref.one_to_one_sse4(qb, a.codebook[b, 15], squared_l2=l2)
-      raw[b, 15] = np.float32(one if l2 else -one)
-    lut, mult = ref.lut_to_fixed_point(raw)
-    rows = []
-    for leaf in leaves.tolist():
-      dps = c.oracle.leaf_datapoints(leaf)
-      if len(dps) == 0:
-        continue
-      packed = ref.pack_dataset(a.codes[dps])
-      # squared L2 (TreeXHybridSMMD): no leaf bias, ties by datapoint id; dot product: bias = centre distance, ties by
-      # (leaf, slot)
-      bias = np.float32(0.0) if l2 else cd_all[i, leaf]
-      (idx, dist), = ref.lut16_top_float(packed, len(dps), B, [lut], [bias], [mult])
-      assert len(idx) == len(dps)
-      for s, d in zip(idx.tolist(), dist.tolist()):
-        rows.append((float(canon(d)), (int(dps[s]),) if l2 else (leaf, s), int(dps[s])))
-    rows.sort(key=lambda t: (t[0], t[1]))
-    cand = np.asarray([r[2] for r in rows[:c.pre]], np.int64)
-    pad = (-len(cand)) % 3                                     # the kernel takes three rows at a time
-    padded = np.concatenate([cand, np.repeat(cand[-1:], pad)])
-    exact = ref.one_to_many_f32(q[i], a.dataset[padded], squared_l2=l2)[:len(cand)]
-    order = np.lexsort((cand, canon(exact)))[:c.k]
-    np.testing.assert_array_equal(cand[order].astype(np.uint32), want_idx[i, :len(order)])
-    # dot product: the API reports the similarity, i.e. the negated distance (result_multiplier_, scann_ops/cc/scann.cc:365-369)
-    reported = exact[order] if l2 else -exact[order]
-    np.testing.assert_array_equal(reported.view(np.uint32), want_dist[i, :len(order)].view(np.uint32))
+  got_idx, got_dist = reference_pipeline_search(c, q)
+  np.testing.assert_array_equal(got_idx, want_idx)
+  np.testing.assert_array_equal(got_dist.view(np.uint32), want_dist.view(np.uint32))
