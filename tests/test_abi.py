@@ -65,3 +65,24 @@ def test_product_package_does_not_import_oracle():
         text = open(os.path.join(dirpath, f)).read()
         assert not re.search(r"^\s*(import oracle|from oracle)", text, flags=re.M), f
         assert not re.search(r"#include.*oracle|dlopen.*oracle|CDLL.*oracle", text), f
+
+
+def test_built_library_is_hand_written_sm100a_code():
+  """Evidence hygiene (no GPU needed): the in-tree libscann_b200.so carries sm_100a cubins only, their SASS holds the
+  Blackwell tensor-core / TMA / TMEM instructions the kernels are written with (tcgen05.mma -> UTCHMMA, TMA loads ->
+  UTMALDG, tcgen05.ld -> LDTM), and the kernels of every stage -- the int8 tokenization ones included -- are in it."""
+  import shutil
+  import subprocess
+  tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+  if not os.path.exists(tool):
+    pytest.skip("cuobjdump not available")
+  so = os.path.join(ROOT, "scann_b200", "libscann_b200.so")
+  elfs = subprocess.run([tool, "-lelf", so], capture_output=True, text=True, check=True).stdout.split()
+  cubins = [e for e in elfs if e.endswith(".cubin")]
+  assert cubins and all("sm_100a" in e for e in cubins), cubins
+  sass = subprocess.run([tool, "-sass", so], capture_output=True, text=True, check=True).stdout
+  for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D", "LDTM.x32", "UTCBAR"):
+    assert mnemonic in sass, mnemonic
+  for kernel in ("scan_main_kernel", "pilot_kernel", "tokenize_i8_kernel", "tokenize_i8_tail_kernel", "topp_refine_kernel",
+                 "topp_chunk_kernel", "gemm_pair_kernel", "gemm_kernel", "finalize_kernel", "scan_tc_kernel"):
+    assert kernel in sass, kernel
